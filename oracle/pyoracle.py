@@ -1,0 +1,141 @@
+"""ctypes front-ends for the CPU checkers under oracle/ (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, bench.py's cpu_baseline / --impl reference legs and __graft_entry__.smoke() may import
+this module; the product package (genomics_gpu_b200) never does.
+
+* ``Oracle``  -- oracle/gotoh_compat.c, our plain-C restatement of the reference recurrences.
+* ``RefHost`` -- oracle/_ref/libgasal_ref_host_mq<N>.so, the reference's own kernel headers
+  (Non-CDP/GASAL2/src/kernels/*.h) compiled unmodified for the host (see oracle/ref_shim/).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Dict, Optional
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# enums of the reference (Non-CDP/GASAL2/src/gasal.h:37-72)
+WITHOUT_START, WITH_START, WITH_TB = 0, 1, 2
+NONE, QUERY, TARGET, BOTH = 0, 1, 2, 3
+GLOBAL, SEMI_GLOBAL, LOCAL, MICROLOCAL, BANDED, KSW = 1, 2, 3, 4, 5, 6
+
+u32p = np.ctypeslib.ndpointer(dtype=np.uint32, flags="C_CONTIGUOUS")
+u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def _ptr(a: Optional[np.ndarray], ctype):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ctype))
+
+
+def build_oracle(target: str = "oracle") -> None:
+    subprocess.run(["make", "-s", "-C", HERE, target], check=True)
+
+
+class _Scoring(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("match", "mismatch", "gap_open", "gap_extend", "n_code", "n_penalty")]
+
+
+class _Params(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("algo", "start_mode", "second_best", "head", "tail", "k_band")] + [("max_query_len", C.c_uint32)]
+
+
+class _Results(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_int32)) for n in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start",
+                                                    "target_batch_start", "aln_score2", "query_batch_end2", "target_batch_end2")] + \
+               [("cigar", C.POINTER(C.c_uint8)), ("n_cigar_ops", C.POINTER(C.c_uint32))]
+
+
+def _alloc_results(n: int, q_bytes: int) -> Dict[str, np.ndarray]:
+    r = {k: np.zeros(n, dtype=np.int32) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start",
+                                                 "target_batch_start", "aln_score2", "query_batch_end2", "target_batch_end2")}
+    r["cigar"] = np.zeros(max(q_bytes, 8), dtype=np.uint8)
+    r["n_cigar_ops"] = np.zeros(n, dtype=np.uint32)
+    return r
+
+
+class Oracle:
+    """oracle/gotoh_compat.c"""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_build", "libgotoh_compat.so")
+        if not os.path.exists(path):
+            build_oracle("oracle")
+        self.lib = C.CDLL(path)
+        self.lib.gc_pack.argtypes = [u8p, C.c_uint32, u32p]
+        self.lib.gc_align_batch.restype = C.c_int
+        self.lib.gc_revcomp_batch.argtypes = [u32p, u32p, u32p, u32p, u32p, u32p, u8p, u8p, C.c_uint32]
+
+    def pack(self, ascii_bytes: np.ndarray) -> np.ndarray:
+        assert ascii_bytes.dtype == np.uint8 and ascii_bytes.size % 8 == 0
+        out = np.zeros(ascii_bytes.size // 8, dtype=np.uint32)
+        if ascii_bytes.size:
+            self.lib.gc_pack(np.ascontiguousarray(ascii_bytes), ascii_bytes.size, out)
+        return out
+
+    def revcomp(self, pq, pt, q_lens, t_lens, q_offs, t_offs, q_op, t_op):
+        pq, pt = pq.copy(), pt.copy()
+        self.lib.gc_revcomp_batch(pq, pt, q_lens, t_lens, q_offs, t_offs, np.ascontiguousarray(q_op, dtype=np.uint8),
+                                  np.ascontiguousarray(t_op, dtype=np.uint8), len(q_lens))
+        return pq, pt
+
+    def align(self, pq, pt, q_lens, t_lens, q_offs, t_offs, *, algo, start=WITHOUT_START, second_best=False, head=TARGET,
+              tail=TARGET, k_band=0, scoring=(1, 4, 6, 1), seed_scores=None, max_query_len=0, n_threads=0,
+              n_code=0x4E, n_penalty=-1) -> Dict[str, np.ndarray]:
+        n = len(q_lens)
+        res = _alloc_results(n, pq.size * 8)
+        sc = _Scoring(*scoring, n_code, n_penalty)
+        p = _Params(algo, start, int(bool(second_best)), head, tail, k_band, max_query_len)
+        rs = _Results(*[_ptr(res[k], C.c_int32) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start",
+                                                          "target_batch_start", "aln_score2", "query_batch_end2", "target_batch_end2")],
+                      _ptr(res["cigar"], C.c_uint8), _ptr(res["n_cigar_ops"], C.c_uint32))
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32) for a in (pq, pt, q_lens, t_lens, q_offs, t_offs)]
+        seed = None if seed_scores is None else np.ascontiguousarray(seed_scores, dtype=np.uint32)
+        rc = self.lib.gc_align_batch(C.byref(sc), C.byref(p), *[_ptr(a, C.c_uint32) for a in arrs], _ptr(seed, C.c_uint32),
+                                     C.c_uint32(n), C.byref(rs), C.c_int(n_threads))
+        if rc != 0:
+            raise RuntimeError("gc_align_batch failed")
+        return res
+
+
+class RefHost:
+    """The reference's own kernels on the host (oracle/_ref/libgasal_ref_host_mq<N>.so)."""
+
+    def __init__(self, max_query_len: int = 1024):
+        path = os.path.join(HERE, "_ref", f"libgasal_ref_host_mq{max_query_len}.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path + " (run `make -C oracle ref_host` where /root/reference exists)")
+        self.lib = C.CDLL(path)
+        self.max_query_len = self.lib.ref_max_query_len()
+        self.lib.ref_align.restype = C.c_int
+
+    @staticmethod
+    def available(max_query_len: int = 1024) -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", f"libgasal_ref_host_mq{max_query_len}.so"))
+
+    def pack(self, uq: np.ndarray, ut: np.ndarray, n_alns: int):
+        pq = np.zeros(uq.size // 8, dtype=np.uint32)
+        pt = np.zeros(ut.size // 8, dtype=np.uint32)
+        self.lib.ref_pack(_ptr(uq, C.c_uint8), _ptr(ut, C.c_uint8), _ptr(pq, C.c_uint32), _ptr(pt, C.c_uint32),
+                          C.c_uint32(uq.size), C.c_uint32(ut.size), C.c_uint32(n_alns))
+        return pq, pt
+
+    def align(self, pq, pt, q_lens, t_lens, q_offs, t_offs, *, algo, start=WITHOUT_START, second_best=False, head=TARGET,
+              tail=TARGET, k_band=0, scoring=(1, 4, 6, 1), seed_scores=None, n_threads=0) -> Dict[str, np.ndarray]:
+        n = len(q_lens)
+        assert int(max(q_lens)) <= self.max_query_len
+        res = _alloc_results(n, pq.size * 8)
+        self.lib.ref_set_scores(*[C.c_int(int(v)) for v in scoring])
+        arrs = [np.ascontiguousarray(a, dtype=np.uint32).copy() for a in (pq, pt, q_lens, t_lens, q_offs, t_offs)]
+        seed = None if seed_scores is None else np.ascontiguousarray(seed_scores, dtype=np.uint32)
+        rc = self.lib.ref_align(algo, start, int(bool(second_best)), head, tail, k_band, *[_ptr(a, C.c_uint32) for a in arrs],
+                                _ptr(seed, C.c_uint32), n,
+                                *[_ptr(res[k], C.c_int32) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start",
+                                                                    "target_batch_start", "aln_score2", "query_batch_end2", "target_batch_end2")],
+                                _ptr(res["cigar"], C.c_uint8), _ptr(res["n_cigar_ops"], C.c_uint32), n_threads)
+        if rc != 0:
+            raise RuntimeError("ref_align failed")
+        return res
