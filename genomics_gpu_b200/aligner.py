@@ -1,0 +1,152 @@
+"""Host-side driver over the C ABI, mirroring how the reference's only caller uses GASAL2
+(Non-CDP/GASAL2/test_prog/test_prog.cpp:203-437): init storages -> fill host batches -> gasal_aln_async ->
+poll gasal_is_aln_async_done -> read host_res.  All compute happens in libgasal_b200.so on the GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import time
+from typing import Dict, Optional, Sequence
+
+import numpy as np
+
+from . import capi
+from .synth import PairBatch
+
+
+def _np_view(ptr, n, dtype):
+    if not ptr:
+        return None
+    return np.ctypeslib.as_array(ptr, shape=(n,)).view(dtype)
+
+
+class Aligner:
+    """One thread's worth of GASAL2 state: `n_streams` storages (reference NB_STREAMS, test_prog.cpp:12)."""
+
+    def __init__(self, *, algo: int, start: int = capi.WITHOUT_START, second_best: bool = False, head: int = capi.TARGET,
+                 tail: int = capi.TARGET, k_band: int = 0, is_packed: bool = False, reverse_complement: bool = False,
+                 scoring: Sequence[int] = (1, 4, 6, 1), max_query_len: int = 160, max_target_len: int = 320,
+                 max_n_alns: int = 5000, n_streams: int = 2, device: Optional[int] = None):
+        self.lib = capi.load()
+        if device is not None:
+            self.lib.gasal_set_device(device, 0)
+        self.params = capi.Params()
+        self.lib.gasal_params_default(C.byref(self.params))
+        self.params.algo = algo; self.params.start_pos = start; self.params.secondBest = int(bool(second_best))
+        self.params.semiglobal_skipping_head = head; self.params.semiglobal_skipping_tail = tail; self.params.k_band = k_band
+        self.params.isPacked = int(is_packed); self.params.isReverseComplement = int(reverse_complement)
+        sc = capi.SubstScores(*[int(v) for v in scoring])
+        self.lib.gasal_copy_subst_scores(C.byref(sc))
+        self.vec = self.lib.gasal_init_gpu_storage_v(n_streams)
+        self.lib.gasal_init_streams(C.byref(self.vec), max_query_len, max_target_len, max_n_alns, C.byref(self.params))
+        self.max_n_alns = max_n_alns
+        self._closed = False
+
+    def storage(self, i: int) -> capi.GpuStorage:
+        return self.vec.a[i]
+
+    # -- filling: test_prog.cpp:279-315 ----------------------------------------------------------------
+    def fill(self, i: int, batch: PairBatch, q_op: Optional[np.ndarray] = None, t_op: Optional[np.ndarray] = None) -> None:
+        """Stage a whole PairBatch (already in gasal_host_batch_fill layout) into storage i with two bulk
+        gasal_host_batch_add calls, then write offsets / lens / ops as the reference's caller does."""
+        s = self.vec.a[i]
+        n = batch.n
+        if n > s.host_max_n_alns:
+            self.lib.gasal_host_alns_resize(C.byref(s), max(n, 2 * s.host_max_n_alns), C.byref(self.params))
+        self.lib.gasal_host_batch_add(C.byref(s), 0, batch.q_bytes.ctypes.data_as(C.c_char_p), batch.q_bytes.size, capi.QUERY)
+        self.lib.gasal_host_batch_add(C.byref(s), 0, batch.t_bytes.ctypes.data_as(C.c_char_p), batch.t_bytes.size, capi.TARGET)
+        C.memmove(s.host_query_batch_offsets, batch.q_offs.ctypes.data, 4 * n)
+        C.memmove(s.host_target_batch_offsets, batch.t_offs.ctypes.data, 4 * n)
+        C.memmove(s.host_query_batch_lens, batch.q_lens.ctypes.data, 4 * n)
+        C.memmove(s.host_target_batch_lens, batch.t_lens.ctypes.data, 4 * n)
+        if q_op is not None:
+            q_op = np.ascontiguousarray(q_op, dtype=np.uint8); t_op = np.ascontiguousarray(t_op, dtype=np.uint8)
+            self.lib.gasal_op_fill(C.byref(s), q_op.ctypes.data_as(C.POINTER(C.c_uint8)), n, capi.QUERY)
+            self.lib.gasal_op_fill(C.byref(s), t_op.ctypes.data_as(C.POINTER(C.c_uint8)), n, capi.TARGET)
+        s.current_n_alns = n
+
+    def fill_one_by_one(self, i: int, queries: Sequence[bytes], targets: Sequence[bytes]) -> None:
+        """The literal per-sequence loop of test_prog.cpp:289-313 (gasal_host_batch_fill pads with 'N')."""
+        s = self.vec.a[i]
+        qi = ti = 0
+        for j, (q, t) in enumerate(zip(queries, targets)):
+            s.current_n_alns += 1
+            if s.current_n_alns > s.host_max_n_alns:
+                self.lib.gasal_host_alns_resize(C.byref(s), s.host_max_n_alns * 2, C.byref(self.params))
+            s.host_query_batch_offsets[j] = qi; s.host_target_batch_offsets[j] = ti
+            qi = self.lib.gasal_host_batch_fill(C.byref(s), qi, q, len(q), capi.QUERY)
+            ti = self.lib.gasal_host_batch_fill(C.byref(s), ti, t, len(t), capi.TARGET)
+            s.host_query_batch_lens[j] = len(q); s.host_target_batch_lens[j] = len(t)
+        self._last_bytes = (qi, ti)
+
+    def set_seed_scores(self, i: int, seeds: np.ndarray) -> None:
+        s = self.vec.a[i]
+        seeds = np.ascontiguousarray(seeds, dtype=np.uint32)
+        C.memmove(s.host_seed_scores, seeds.ctypes.data, 4 * seeds.size)
+
+    def launch(self, i: int, q_bytes: int, t_bytes: int, n: int) -> None:
+        self.lib.gasal_aln_async(C.byref(self.vec.a[i]), q_bytes, t_bytes, n, C.byref(self.params))
+
+    def done(self, i: int) -> int:
+        return self.lib.gasal_is_aln_async_done(C.byref(self.vec.a[i]))
+
+    def wait(self, i: int) -> None:
+        while True:
+            r = self.done(i)
+            if r == 0:
+                return
+            if r == -2:
+                raise RuntimeError("gasal_is_aln_async_done: nothing was launched on this storage")
+            time.sleep(0)
+
+    def results(self, i: int, n: int, q_bytes: int = 0) -> Dict[str, np.ndarray]:
+        """Copies of host_res (valid after done() returned 0)."""
+        s = self.vec.a[i]
+        out: Dict[str, np.ndarray] = {}
+        r = s.host_res.contents
+        for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start"):
+            v = _np_view(getattr(r, k), n, np.int32)
+            if v is not None:
+                out[k] = v.copy()
+        if self.params.start_pos == capi.WITH_TB and r.cigar and r.n_cigar_ops:
+            out["cigar"] = _np_view(r.cigar, q_bytes, np.uint8).copy()
+            out["n_cigar_ops"] = _np_view(r.n_cigar_ops, n, np.uint32).copy()
+        if self.params.secondBest and s.host_res_second:
+            r2 = s.host_res_second.contents
+            for k in ("aln_score", "query_batch_end", "target_batch_end"):
+                v = _np_view(getattr(r2, k), n, np.int32)
+                if v is not None:
+                    out[k + "2"] = v.copy()
+        return out
+
+    def align(self, batch: PairBatch, i: int = 0, q_op=None, t_op=None, seeds=None) -> Dict[str, np.ndarray]:
+        """fill -> gasal_aln_async -> wait -> results, for one batch on storage i."""
+        self.fill(i, batch, q_op, t_op)
+        if seeds is not None:
+            self.set_seed_scores(i, seeds)
+        self.launch(i, batch.q_bytes.size, batch.t_bytes.size, batch.n)
+        self.wait(i)
+        return self.results(i, batch.n, batch.q_bytes.size)
+
+    def last_ms(self, i: int):
+        buf = (C.c_float * 3)()
+        rc = self.lib.gasalx_last_batch_ms(C.byref(self.vec.a[i]), buf)
+        return None if rc != 0 else (buf[0], buf[1], buf[2])
+
+    def kernel_name(self, i: int) -> str:
+        return self.lib.gasalx_last_kernel_name(C.byref(self.vec.a[i])).decode()
+
+    def launches(self, i: int) -> int:
+        return int(self.lib.gasalx_kernel_launches(C.byref(self.vec.a[i])))
+
+    def close(self) -> None:
+        if not self._closed:
+            self.lib.gasal_destroy_streams(C.byref(self.vec), C.byref(self.params))
+            self.lib.gasal_destroy_gpu_storage_v(C.byref(self.vec))
+            self._closed = True
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()

@@ -1,0 +1,70 @@
+// dp_common.cuh -- shared device helpers for the B200 alignment kernels.
+// Packed-base layout is GASAL2's: 8 bases per uint32, first base in bits 31:28
+// (reference Non-CDP/GASAL2/src/kernels/pack_rc_seqs.h:13-53).
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+namespace gb200 {
+
+// enums mirror the reference's (src/gasal.h:37-72) so host code can pass them straight through
+enum { START_NONE = 0, START_POS = 1, START_TB = 2 };
+enum { SKIP_NONE = 0, SKIP_QUERY = 1, SKIP_TARGET = 2, SKIP_BOTH = 3 };
+enum { ALGO_GLOBAL = 1, ALGO_SEMI_GLOBAL = 2, ALGO_LOCAL = 3, ALGO_BANDED = 5, ALGO_KSW = 6 };
+
+constexpr int kMinusInf = -32768;   // MINUS_INF = SHRT_MIN, src/gasal_kernels.h:35
+
+// Everything a DP kernel needs, passed by value as the kernel parameter (no process-global
+// __constant__ state: the reference's _cudaGapO etc., src/gasal_kernels.h:29-33, become fields).
+struct DpArgs {
+  const uint32_t* __restrict__ pq;       // packed query batch
+  const uint32_t* __restrict__ pt;       // packed target batch
+  const uint32_t* __restrict__ q_lens;
+  const uint32_t* __restrict__ t_lens;
+  const uint32_t* __restrict__ q_offs;   // byte offsets (x8); word index = off >> 3
+  const uint32_t* __restrict__ t_offs;
+  const uint32_t* __restrict__ seed_scores;
+  int n;                                 // pairs in this launch
+  // scoring (positive penalties, src/gasal.h:160-165)
+  int match, mismatch, gap_open, gap_extend;
+  uint32_t n_value;                      // N_CODE & 15
+  int n_score;                           // score of a pair involving N under the LOCAL rule (0 or -N_PENALTY)
+  int n_is_wild_global;                  // 1 if N_PENALTY is defined (then the GLOBAL rule treats N specially too)
+  // results (SoA, gasal_res_t arrays; any may be null)
+  int32_t* score; int32_t* q_end; int32_t* t_end; int32_t* q_start; int32_t* t_start;
+  int32_t* score2; int32_t* q_end2; int32_t* t_end2;
+  // per-launch scratch: column state (H,E) as short2, laid out [column][pair] so a warp's accesses coalesce
+  uint32_t* colstate; uint32_t col_stride; uint32_t col_rows;   // col_rows = columns available per pair
+  // traceback
+  uint4* tb; uint32_t tb_stride;         // tile t of pair p lives at tb[t * tb_stride + p]
+  uint8_t* cigar; uint32_t* n_cigar_ops;
+  int head, tail, k_band;
+};
+
+__device__ __forceinline__ uint32_t nib(uint32_t w, int k) { return (w >> (28 - 4 * k)) & 15u; }
+__device__ __forceinline__ uint32_t n_words(uint32_t len) { return (len + 7u) >> 3; }
+
+// reverse the order of the 8 nibbles of a word
+__device__ __forceinline__ uint32_t nibrev(uint32_t x) {
+  x = __byte_perm(x, 0, 0x0123);
+  return ((x & 0x0F0F0F0Fu) << 4) | ((x >> 4) & 0x0F0F0F0Fu);
+}
+
+// word j of the TRUE-LENGTH reversed sequence with zero pad nibbles -- what the reference builds in
+// per-thread arrays before the semi-global start pass (semiglobal_kernel_template.h:232-266).
+__device__ __forceinline__ uint32_t rev_true_word(const uint32_t* __restrict__ w, int len, int j) {
+  const int hi = len - 1 - 8 * j;
+  if (hi < 0) return 0u;
+  const int lo = hi - 7;
+  const int wi = lo >> 3;                 // arithmetic shift: floor
+  const int sh = lo - 8 * wi;
+  const uint32_t a = (wi >= 0) ? w[wi] : 0u;
+  const uint32_t b = (sh != 0 || wi < 0) ? w[wi + 1] : 0u;
+  const uint32_t x = __funnelshift_l(b, a, 4 * sh);
+  return nibrev(x);
+}
+
+__device__ __forceinline__ short2 u32_as_short2(uint32_t v) { short2 r; r.x = (short)(v & 0xFFFFu); r.y = (short)(v >> 16); return r; }
+__device__ __forceinline__ uint32_t pack_short2(int h, int e) { return ((uint32_t)h & 0xFFFFu) | ((uint32_t)e << 16); }
+
+}  // namespace gb200

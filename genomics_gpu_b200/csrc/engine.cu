@@ -1,0 +1,696 @@
+// engine.cu -- host runtime of the B200 alignment engine behind the GASAL2 C API
+// (include/gasal_b200.h).  One storage == one CUDA stream; everything gasal_aln_async enqueues
+// goes on that stream and nothing synchronises (reference Non-CDP/GASAL2/src/gasal_align.cu:29-307,
+// src/ctors.cpp:26-190, src/res.cpp, src/host_batch.cpp, src/interfaces.cpp).
+//
+// There is NO CPU fallback anywhere in this file: if the CUDA runtime is unusable the calls print
+// "[GASAL CUDA ERROR:]" and exit, exactly like the reference's CHECKCUDAERROR (src/gasal.h:15-22).
+#include <stdio.h>
+#include <string.h>
+#include <math.h>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "../../include/gasal_b200.h"
+#include "dp_common.cuh"
+#include "pack_tb.cuh"
+#include "dp_generic.cuh"
+#include "dp_s16.cuh"
+
+using namespace gb200;
+
+#define CHECKCUDAERROR(call)                                                                                          \
+  do {                                                                                                                \
+    cudaError_t err_ = (call);                                                                                        \
+    if (cudaSuccess != err_) {                                                                                        \
+      fprintf(stderr, "[GASAL CUDA ERROR:] %s(CUDA error no.=%d). Line no. %d in file %s\n", cudaGetErrorString(err_), \
+              err_, __LINE__, __FILE__);                                                                              \
+      exit(EXIT_FAILURE);                                                                                             \
+    }                                                                                                                 \
+  } while (0)
+
+#define CHECK_LAUNCH() CHECKCUDAERROR(cudaGetLastError())
+
+namespace {
+
+// process-wide scoring, set by gasal_copy_subst_scores (the reference keeps these in __constant__
+// memory, src/gasal_kernels.h:29-33; here they travel as kernel arguments)
+gasal_subst_scores g_scores = {1, 4, 6, 1};
+int g_n_code = 0x4E;
+int g_n_penalty = -1;
+int g_kernel_policy = 0;
+
+struct Priv {
+  uint32_t* colstate = nullptr; size_t colstate_words = 0;
+  uint8_t* d_cigar = nullptr; size_t cigar_bytes = 0;
+  uint32_t* d_n_cigar_ops = nullptr; size_t n_cigar_cap = 0;
+  FastScratch fast;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, packed, dp done, end
+  bool timing_pending = false;
+  uint64_t launches = 0;
+  const char* last_kernel = "none";
+  int max_query_len_8 = 0, max_target_len_8 = 0;
+};
+
+inline Priv* priv(gasal_gpu_storage_t* s) { return (Priv*)s->b200_priv; }
+
+template <typename T>
+void dev_realloc(T** p, size_t n) {
+  if (*p) CHECKCUDAERROR(cudaFree(*p));
+  *p = nullptr;
+  if (n) CHECKCUDAERROR(cudaMalloc((void**)p, n * sizeof(T)));
+}
+
+inline uint32_t round8(uint32_t x) { return (x + 7u) & ~7u; }
+
+template <typename T>
+T* cudaHostRealloc(void* source, int new_size, int old_size) {
+  T* destination = NULL;
+  if (new_size < old_size) { fprintf(stderr, "[GASAL ERROR] cudoHostRealloc: invalid sizes. New size < old size (%d < %d)", new_size, old_size); exit(EXIT_FAILURE); }
+  CHECKCUDAERROR(cudaHostAlloc(&destination, new_size * sizeof(T), cudaHostAllocDefault));
+  memcpy(destination, source, old_size * sizeof(T));
+  CHECKCUDAERROR(cudaFreeHost(source));
+  return destination;
+}
+
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* gasalx_version(void) { return "gasal-b200 0.1 (sm_100a)"; }
+
+void gasal_params_default(gasal_params_t* p) {   // src/args_parser.cpp:12-29
+  memset(p, 0, sizeof(*p));
+  p->algo = UNKNOWN; p->start_pos = WITHOUT_START; p->secondBest = FALSE; p->isPacked = 0; p->isReverseComplement = 0;
+  p->semiglobal_skipping_head = TARGET; p->semiglobal_skipping_tail = TARGET; p->k_band = 0;
+}
+
+void gasalx_set_n_code(int n_code, int n_penalty) { g_n_code = n_code; g_n_penalty = n_penalty; }
+void gasalx_set_kernel_policy(int policy) { g_kernel_policy = policy; }
+
+void gasal_copy_subst_scores(gasal_subst_scores* subst) { g_scores = *subst; }   // src/gasal_align.cu:329-339
+
+// ---- results: src/res.cpp --------------------------------------------------------------------------
+gasal_res_t* gasal_res_new_host(uint32_t max_n_alns, const gasal_params_t* params) {
+  gasal_res_t* res = (gasal_res_t*)calloc(1, sizeof(gasal_res_t));   // zero-initialised (the reference mallocs: Q12)
+  if (res == NULL) { fprintf(stderr, "Malloc error on res host "); exit(1); }
+  CHECKCUDAERROR(cudaHostAlloc(&(res->aln_score), max_n_alns * sizeof(int32_t), cudaHostAllocDefault));
+  if (params->algo != GLOBAL) {                                       // :26-30
+    CHECKCUDAERROR(cudaHostAlloc(&(res->query_batch_end), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+    CHECKCUDAERROR(cudaHostAlloc(&(res->target_batch_end), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+    if (params->start_pos == WITH_START || params->start_pos == WITH_TB) {   // :54-58
+      CHECKCUDAERROR(cudaHostAlloc(&(res->query_batch_start), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+      CHECKCUDAERROR(cudaHostAlloc(&(res->target_batch_start), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+    }
+  }
+  if (params->start_pos == WITH_TB) CHECKCUDAERROR(cudaHostAlloc(&(res->n_cigar_ops), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+  return res;
+}
+
+gasal_res_t* gasal_res_new_device_cpy(uint32_t max_n_alns, const gasal_params_t* params) {
+  gasal_res_t* res = (gasal_res_t*)calloc(1, sizeof(gasal_res_t));
+  CHECKCUDAERROR(cudaMalloc(&(res->aln_score), max_n_alns * sizeof(int32_t)));
+  if (params->algo != GLOBAL) {
+    CHECKCUDAERROR(cudaMalloc(&(res->query_batch_end), max_n_alns * sizeof(uint32_t)));
+    CHECKCUDAERROR(cudaMalloc(&(res->target_batch_end), max_n_alns * sizeof(uint32_t)));
+    if (params->start_pos == WITH_START || params->start_pos == WITH_TB) {
+      CHECKCUDAERROR(cudaMalloc(&(res->query_batch_start), max_n_alns * sizeof(uint32_t)));
+      CHECKCUDAERROR(cudaMalloc(&(res->target_batch_start), max_n_alns * sizeof(uint32_t)));
+    }
+  }
+  return res;
+}
+
+gasal_res_t* gasal_res_new_device(gasal_res_t* device_cpy) {   // src/res.cpp:76-101 (one copy instead of five)
+  gasal_res_t* d_c;
+  CHECKCUDAERROR(cudaMalloc((void**)&d_c, sizeof(gasal_res_t)));
+  CHECKCUDAERROR(cudaMemcpy(d_c, device_cpy, sizeof(gasal_res_t), cudaMemcpyHostToDevice));
+  return d_c;
+}
+
+void gasal_res_destroy_host(gasal_res_t* res) {
+  if (res == NULL) return;
+  if (res->aln_score != NULL) CHECKCUDAERROR(cudaFreeHost(res->aln_score));
+  if (res->query_batch_start != NULL) CHECKCUDAERROR(cudaFreeHost(res->query_batch_start));
+  if (res->target_batch_start != NULL) CHECKCUDAERROR(cudaFreeHost(res->target_batch_start));
+  if (res->query_batch_end != NULL) CHECKCUDAERROR(cudaFreeHost(res->query_batch_end));
+  if (res->target_batch_end != NULL) CHECKCUDAERROR(cudaFreeHost(res->target_batch_end));
+  if (res->n_cigar_ops != NULL) CHECKCUDAERROR(cudaFreeHost(res->n_cigar_ops));
+  if (res->cigar != NULL) CHECKCUDAERROR(cudaFreeHost(res->cigar));
+  free(res);
+}
+
+void gasal_res_destroy_device(gasal_res_t* device_res, gasal_res_t* device_cpy) {
+  if (device_cpy == NULL || device_res == NULL) return;
+  if (device_cpy->aln_score != NULL) CHECKCUDAERROR(cudaFree(device_cpy->aln_score));
+  if (device_cpy->query_batch_start != NULL) CHECKCUDAERROR(cudaFree(device_cpy->query_batch_start));
+  if (device_cpy->target_batch_start != NULL) CHECKCUDAERROR(cudaFree(device_cpy->target_batch_start));
+  if (device_cpy->query_batch_end != NULL) CHECKCUDAERROR(cudaFree(device_cpy->query_batch_end));
+  if (device_cpy->target_batch_end != NULL) CHECKCUDAERROR(cudaFree(device_cpy->target_batch_end));
+  CHECKCUDAERROR(cudaFree(device_res));
+  free(device_cpy);
+}
+
+// ---- host staging pages: src/host_batch.cpp ----------------------------------------------------------
+host_batch_t* gasal_host_batch_new(uint32_t batch_bytes, uint32_t offset) {
+  host_batch_t* res = (host_batch_t*)calloc(1, sizeof(host_batch_t));
+  CHECKCUDAERROR(cudaHostAlloc(&(res->data), (size_t)batch_bytes * sizeof(uint8_t), cudaHostAllocDefault));
+  res->page_size = batch_bytes; res->data_size = 0; res->is_locked = 0; res->offset = offset; res->next = NULL;
+  return res;
+}
+
+void gasal_host_batch_destroy(host_batch_t* res) {
+  if (res == NULL) { fprintf(stderr, "[GASAL ERROR] Trying to free a NULL pointer\n"); exit(1); }
+  while (res != NULL) {   // iterative (the reference recurses)
+    host_batch_t* next = res->next;
+    if (res->data != NULL) CHECKCUDAERROR(cudaFreeHost(res->data));
+    free(res);
+    res = next;
+  }
+}
+
+host_batch_t* gasal_host_batch_getlast(host_batch_t* arg) { while (arg->next != NULL) arg = arg->next; return arg; }
+
+void gasal_host_batch_reset(gasal_gpu_storage_t* gpu_storage) {   // :49-75
+  host_batch_t* heads[2] = {gpu_storage->extensible_host_unpacked_query_batch, gpu_storage->extensible_host_unpacked_target_batch};
+  for (int i = 0; i < 2; i++)
+    for (host_batch_t* cur = heads[i]; cur != NULL; cur = cur->next) { cur->data_size = 0; cur->offset = 0; cur->is_locked = 0; }
+}
+
+// append one sequence, pad with N_CODE to a multiple of 8, grow by a linked 2x page when full (:79-153)
+uint32_t gasal_host_batch_fill(gasal_gpu_storage_t* gpu_storage, uint32_t idx, const char* data, uint32_t size, enum data_source SRC) {
+  host_batch_t* cur_page = NULL; uint32_t* p_batch_bytes = NULL;
+  switch (SRC) {
+    case QUERY: cur_page = gpu_storage->extensible_host_unpacked_query_batch; p_batch_bytes = &(gpu_storage->host_max_query_batch_bytes); break;
+    case TARGET: cur_page = gpu_storage->extensible_host_unpacked_target_batch; p_batch_bytes = &(gpu_storage->host_max_target_batch_bytes); break;
+    default: fprintf(stderr, "[GASAL ERROR:] gasal_host_batch_fill: SRC must be QUERY or TARGET\n"); exit(EXIT_FAILURE);
+  }
+  const uint32_t nbr_N = (8u - (size & 7u)) & 7u;
+  while (cur_page->is_locked) cur_page = cur_page->next;
+  if (cur_page->next == NULL && cur_page->page_size - cur_page->data_size < size + nbr_N) {
+    uint32_t new_size = cur_page->page_size * 2;
+    while (new_size < size + nbr_N) new_size *= 2;   // (the reference assumes one doubling is enough)
+    fprintf(stderr, "[GASAL WARNING:] Trying to write %d bytes while only %d remain (%s) (block size %d, filled %d bytes).\n"
+            "                 Allocating a new block of size %d, total size available reaches %d. Doing this repeadtedly slows down the execution.\n",
+            size + nbr_N, cur_page->page_size - cur_page->data_size, (SRC == QUERY ? "query" : "target"), cur_page->page_size,
+            cur_page->data_size, new_size, *p_batch_bytes + new_size);
+    host_batch_t* res = gasal_host_batch_new(new_size, cur_page->offset + cur_page->data_size);
+    cur_page->next = res; cur_page->is_locked = 1;
+    *p_batch_bytes = *p_batch_bytes + new_size;
+    cur_page = cur_page->next;
+  }
+  if (cur_page->next != NULL && cur_page->page_size - cur_page->data_size < size + nbr_N) {
+    cur_page->next->offset = cur_page->offset + cur_page->data_size;
+    cur_page->is_locked = 1;
+    cur_page = cur_page->next;
+  }
+  if (cur_page->page_size - cur_page->data_size >= size + nbr_N) {
+    memcpy(&(cur_page->data[idx - cur_page->offset]), data, size);
+    memset(&(cur_page->data[idx + size - cur_page->offset]), g_n_code, nbr_N);
+    idx = idx + size + nbr_N;
+    cur_page->data_size += size + nbr_N;
+  }
+  return idx;
+}
+
+uint32_t gasal_host_batch_add(gasal_gpu_storage_t* gpu_storage, uint32_t idx, const char* data, uint32_t size, enum data_source SRC) {   // :163-223
+  host_batch_t* cur_page = NULL; uint32_t* p_batch_bytes = NULL;
+  switch (SRC) {
+    case QUERY: cur_page = gpu_storage->extensible_host_unpacked_query_batch; p_batch_bytes = &(gpu_storage->host_max_query_batch_bytes); break;
+    case TARGET: cur_page = gpu_storage->extensible_host_unpacked_target_batch; p_batch_bytes = &(gpu_storage->host_max_target_batch_bytes); break;
+    default: fprintf(stderr, "[GASAL ERROR:] gasal_host_batch_add: SRC must be QUERY or TARGET\n"); exit(EXIT_FAILURE);
+  }
+  int is_done = 0;
+  while (!is_done) {
+    if (*p_batch_bytes >= idx + size && (cur_page->next == NULL || (cur_page->next->offset >= idx + size))) {
+      memcpy(&(cur_page->data[idx - cur_page->offset]), data, size);
+      if (cur_page->data_size < idx + size - cur_page->offset) cur_page->data_size = idx + size - cur_page->offset;
+      idx = idx + size; is_done = 1;
+    } else if ((*p_batch_bytes >= idx + size) && (cur_page->next != NULL) && (cur_page->next->offset < idx + size)) {
+      cur_page = cur_page->next;
+    } else {
+      fprintf(stderr, "[GASAL WARNING:] Trying to write %d bytes at position %d on host memory (%s) while only  %d bytes are available. "
+              "Therefore, allocating %d bytes more on CPU. Repeating this many times can provoke a degradation of performance.\n",
+              size, idx, (SRC == QUERY ? "query" : "target"), *p_batch_bytes, *p_batch_bytes * 2);
+      *p_batch_bytes += *p_batch_bytes;
+      while (*p_batch_bytes < size) *p_batch_bytes += *p_batch_bytes;
+      host_batch_t* res = gasal_host_batch_new(*p_batch_bytes, idx);
+      cur_page->next = res; cur_page = cur_page->next;
+    }
+  }
+  return idx;
+}
+
+uint32_t gasal_host_batch_addbase(gasal_gpu_storage_t* gpu_storage, uint32_t idx, const char base, enum data_source SRC) {
+  return gasal_host_batch_add(gpu_storage, idx, &base, 1, SRC);
+}
+
+void gasal_host_batch_print(host_batch_t* res) {
+  fprintf(stderr, "[GASAL PRINT] Page data: offset=%d, next_offset=%d, data size=%d, page size=%d\n", res->offset,
+          (res->next != NULL ? (int)res->next->offset : -1), res->data_size, res->page_size);
+}
+void gasal_host_batch_printall(host_batch_t* res) {
+  for (; res != NULL; res = res->next) { gasal_host_batch_print(res); if (res->next) fprintf(stderr, "+--->"); }
+}
+
+// ---- src/interfaces.cpp ---------------------------------------------------------------------------------
+void gasal_host_alns_resize(gasal_gpu_storage_t* gpu_storage, int new_max_alns, const gasal_params_t* params) {   // :26-78
+  fprintf(stderr, "[GASAL WARNING] Resizing gpu_storage from %d sequences to %d sequences... ", gpu_storage->host_max_n_alns, new_max_alns);
+  const int old = (int)gpu_storage->host_max_n_alns;
+  gpu_storage->host_query_op = cudaHostRealloc<uint8_t>((void*)gpu_storage->host_query_op, new_max_alns, old);
+  gpu_storage->host_target_op = cudaHostRealloc<uint8_t>((void*)gpu_storage->host_target_op, new_max_alns, old);
+  memset(gpu_storage->host_query_op + old, 0, new_max_alns - old);
+  memset(gpu_storage->host_target_op + old, 0, new_max_alns - old);
+  if (params->algo == KSW) gpu_storage->host_seed_scores = cudaHostRealloc<uint32_t>(gpu_storage->host_seed_scores, new_max_alns, old);
+  gpu_storage->host_query_batch_lens = cudaHostRealloc<uint32_t>((void*)gpu_storage->host_query_batch_lens, new_max_alns, old);
+  gpu_storage->host_target_batch_lens = cudaHostRealloc<uint32_t>((void*)gpu_storage->host_target_batch_lens, new_max_alns, old);
+  gpu_storage->host_query_batch_offsets = cudaHostRealloc<uint32_t>((void*)gpu_storage->host_query_batch_offsets, new_max_alns, old);
+  gpu_storage->host_target_batch_offsets = cudaHostRealloc<uint32_t>((void*)gpu_storage->host_target_batch_offsets, new_max_alns, old);
+  uint8_t* old_cigar = gpu_storage->host_res->cigar; gpu_storage->host_res->cigar = NULL;   // the CIGAR page is sized in bytes, keep it
+  gasal_res_destroy_host(gpu_storage->host_res);
+  gpu_storage->host_res = gasal_res_new_host(new_max_alns, params);
+  gpu_storage->host_res->cigar = old_cigar;
+  if (params->secondBest) {
+    gasal_res_destroy_host(gpu_storage->host_res_second);
+    gpu_storage->host_res_second = gasal_res_new_host(new_max_alns, params);
+  }
+  // device side is regrown by gasal_aln_async when the batch is larger than gpu_max_n_alns
+  gpu_storage->host_max_n_alns = new_max_alns;
+  fprintf(stderr, " done. This can harm performance.\n");
+}
+
+void gasal_op_fill(gasal_gpu_storage_t* gpu_storage_t, uint8_t* data, uint32_t nbr_seqs_in_stream, enum data_source SRC) {   // :81-96
+  uint8_t* host_op = NULL;
+  switch (SRC) { case QUERY: host_op = gpu_storage_t->host_query_op; break; case TARGET: host_op = gpu_storage_t->host_target_op; break; default: break; }
+  if (host_op) memcpy(host_op, data, nbr_seqs_in_stream);
+}
+
+void gasal_set_device(int gpu_select, int isPrintingProp) {   // :98-128
+  if (isPrintingProp) {
+    int num_devices = 0;
+    cudaGetDeviceCount(&num_devices);
+    fprintf(stderr, "Found %d GPUs\n", num_devices);
+    if (gpu_select > num_devices - 1) {
+      fprintf(stderr, "Error: can't select device %d when only %d devices are selected (range from 0 to %d)\n", gpu_select, num_devices, num_devices - 1);
+      exit(EXIT_FAILURE);
+    }
+    for (int device = 0; device < num_devices; device++) {
+      cudaDeviceProp properties; cudaGetDeviceProperties(&properties, device);
+      fprintf(stderr, "\tGPU %d: %s\n", device, properties.name);
+    }
+    if (num_devices > 0) {
+      cudaDeviceProp properties; cudaGetDeviceProperties(&properties, gpu_select);
+      fprintf(stderr, "Selected device %d : %s\n", gpu_select, properties.name);
+    }
+  }
+  CHECKCUDAERROR(cudaSetDevice(gpu_select));
+}
+
+// ---- src/ctors.cpp -----------------------------------------------------------------------------------------
+gasal_gpu_storage_v gasal_init_gpu_storage_v(int n_streams) {
+  gasal_gpu_storage_v v;
+  v.a = (gasal_gpu_storage_t*)calloc(n_streams, sizeof(gasal_gpu_storage_t));
+  v.n = n_streams;
+  return v;
+}
+
+static void alloc_tb(gasal_gpu_storage_t* s, uint64_t q8, uint64_t t8, uint64_t n) {
+  // ctors.cpp:112-115, plus one strip of slack so the GLOBAL walker's first read (Q5) stays in bounds
+  const uint64_t tiles = (q8 * (t8 + 8) + 31) / 32 + 2;
+  if (tiles * n > s->packed_tb_matrix_size) {
+    if (s->packed_tb_matrices) CHECKCUDAERROR(cudaFree(s->packed_tb_matrices));
+    s->packed_tb_matrix_size = tiles * n;
+    CHECKCUDAERROR(cudaMalloc(&(s->packed_tb_matrices), s->packed_tb_matrix_size * sizeof(uint4)));
+  }
+}
+
+void gasal_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len, int max_target_len, int max_n_alns, const gasal_params_t* params) {
+  const int max_query_len_8 = (int)round8((uint32_t)max_query_len), max_target_len_8 = (int)round8((uint32_t)max_target_len);
+  const uint64_t qb = (uint64_t)max_n_alns * max_query_len_8, tb = (uint64_t)max_n_alns * max_target_len_8;
+  if (qb > 0xFFFFFFF0ull || tb > 0xFFFFFFF0ull) {
+    fprintf(stderr, "[GASAL ERROR:] batch of %d alignments x (%d, %d) bases does not fit the 32-bit byte offsets of the GASAL2 API\n", max_n_alns, max_query_len_8, max_target_len_8);
+    exit(EXIT_FAILURE);
+  }
+  for (int i = 0; i < gpu_storage_vec->n; i++) {
+    gasal_gpu_storage_t* s = &gpu_storage_vec->a[i];
+    Priv* pv = new Priv();
+    s->b200_priv = pv;
+    pv->max_query_len_8 = max_query_len_8; pv->max_target_len_8 = max_target_len_8;
+    s->extensible_host_unpacked_query_batch = gasal_host_batch_new((uint32_t)qb, 0);
+    s->extensible_host_unpacked_target_batch = gasal_host_batch_new((uint32_t)tb, 0);
+    CHECKCUDAERROR(cudaMalloc(&(s->unpacked_query_batch), qb));
+    CHECKCUDAERROR(cudaMalloc(&(s->unpacked_target_batch), tb));
+    CHECKCUDAERROR(cudaHostAlloc(&(s->host_query_op), max_n_alns, cudaHostAllocDefault));
+    CHECKCUDAERROR(cudaHostAlloc(&(s->host_target_op), max_n_alns, cudaHostAllocDefault));
+    memset(s->host_query_op, 0, max_n_alns); memset(s->host_target_op, 0, max_n_alns);
+    CHECKCUDAERROR(cudaMalloc(&(s->query_op), max_n_alns));
+    CHECKCUDAERROR(cudaMalloc(&(s->target_op), max_n_alns));
+    if (params->isPacked) {   // ctors.cpp:64-67: the "unpacked" buffers ARE the packed words
+      s->packed_query_batch = (uint32_t*)s->unpacked_query_batch;
+      s->packed_target_batch = (uint32_t*)s->unpacked_target_batch;
+    } else {
+      CHECKCUDAERROR(cudaMalloc(&(s->packed_query_batch), (qb / 8) * sizeof(uint32_t)));
+      CHECKCUDAERROR(cudaMalloc(&(s->packed_target_batch), (tb / 8) * sizeof(uint32_t)));
+    }
+    if (params->algo == KSW) {
+      CHECKCUDAERROR(cudaHostAlloc(&(s->host_seed_scores), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+      CHECKCUDAERROR(cudaMalloc(&(s->seed_scores), max_n_alns * sizeof(uint32_t)));
+    }
+    CHECKCUDAERROR(cudaHostAlloc(&(s->host_query_batch_lens), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+    CHECKCUDAERROR(cudaHostAlloc(&(s->host_target_batch_lens), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+    CHECKCUDAERROR(cudaHostAlloc(&(s->host_query_batch_offsets), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+    CHECKCUDAERROR(cudaHostAlloc(&(s->host_target_batch_offsets), max_n_alns * sizeof(uint32_t), cudaHostAllocDefault));
+    CHECKCUDAERROR(cudaMalloc(&(s->query_batch_lens), max_n_alns * sizeof(uint32_t)));
+    CHECKCUDAERROR(cudaMalloc(&(s->target_batch_lens), max_n_alns * sizeof(uint32_t)));
+    CHECKCUDAERROR(cudaMalloc(&(s->query_batch_offsets), max_n_alns * sizeof(uint32_t)));
+    CHECKCUDAERROR(cudaMalloc(&(s->target_batch_offsets), max_n_alns * sizeof(uint32_t)));
+    s->host_res = gasal_res_new_host(max_n_alns, params);
+    if (params->start_pos == WITH_TB) CHECKCUDAERROR(cudaHostAlloc(&(s->host_res->cigar), qb, cudaHostAllocDefault));
+    s->device_cpy = gasal_res_new_device_cpy(max_n_alns, params);
+    s->device_res = gasal_res_new_device(s->device_cpy);
+    if (params->secondBest) {
+      s->host_res_second = gasal_res_new_host(max_n_alns, params);
+      s->device_cpy_second = gasal_res_new_device_cpy(max_n_alns, params);
+      s->device_res_second = gasal_res_new_device(s->device_cpy_second);
+    }
+    if (params->start_pos == WITH_TB && (params->algo == LOCAL || params->algo == GLOBAL))
+      alloc_tb(s, max_query_len_8, max_target_len_8, max_n_alns);
+    CHECKCUDAERROR(cudaStreamCreateWithFlags(&(s->str), cudaStreamNonBlocking));
+    for (int e = 0; e < 4; e++) CHECKCUDAERROR(cudaEventCreate(&pv->ev[e]));
+    s->is_free = 1;
+    s->host_max_query_batch_bytes = (uint32_t)qb; s->host_max_target_batch_bytes = (uint32_t)tb;
+    s->host_max_n_alns = max_n_alns;
+    s->gpu_max_query_batch_bytes = (uint32_t)qb; s->gpu_max_target_batch_bytes = (uint32_t)tb;
+    s->gpu_max_n_alns = max_n_alns;
+    s->current_n_alns = 0;
+  }
+}
+
+void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_params_t* params) {
+  for (int i = 0; i < gpu_storage_vec->n; i++) {
+    gasal_gpu_storage_t* s = &gpu_storage_vec->a[i];
+    if (s->str) CHECKCUDAERROR(cudaStreamSynchronize(s->str));
+    gasal_host_batch_destroy(s->extensible_host_unpacked_query_batch);
+    gasal_host_batch_destroy(s->extensible_host_unpacked_target_batch);
+    gasal_res_destroy_host(s->host_res);
+    gasal_res_destroy_device(s->device_res, s->device_cpy);
+    gasal_res_destroy_host(s->host_res_second);
+    gasal_res_destroy_device(s->device_res_second, s->device_cpy_second);
+    if (s->seed_scores) CHECKCUDAERROR(cudaFree(s->seed_scores));
+    if (s->host_seed_scores) CHECKCUDAERROR(cudaFreeHost(s->host_seed_scores));
+    if (s->query_op) CHECKCUDAERROR(cudaFree(s->query_op));
+    if (s->target_op) CHECKCUDAERROR(cudaFree(s->target_op));
+    if (s->host_query_op) CHECKCUDAERROR(cudaFreeHost(s->host_query_op));
+    if (s->host_target_op) CHECKCUDAERROR(cudaFreeHost(s->host_target_op));
+    if (s->host_query_batch_offsets) CHECKCUDAERROR(cudaFreeHost(s->host_query_batch_offsets));
+    if (s->host_target_batch_offsets) CHECKCUDAERROR(cudaFreeHost(s->host_target_batch_offsets));
+    if (s->host_query_batch_lens) CHECKCUDAERROR(cudaFreeHost(s->host_query_batch_lens));
+    if (s->host_target_batch_lens) CHECKCUDAERROR(cudaFreeHost(s->host_target_batch_lens));
+    if (s->unpacked_query_batch) CHECKCUDAERROR(cudaFree(s->unpacked_query_batch));
+    if (s->unpacked_target_batch) CHECKCUDAERROR(cudaFree(s->unpacked_target_batch));
+    if (!params->isPacked) {
+      if (s->packed_query_batch) CHECKCUDAERROR(cudaFree(s->packed_query_batch));
+      if (s->packed_target_batch) CHECKCUDAERROR(cudaFree(s->packed_target_batch));
+    }
+    if (s->query_batch_offsets) CHECKCUDAERROR(cudaFree(s->query_batch_offsets));
+    if (s->target_batch_offsets) CHECKCUDAERROR(cudaFree(s->target_batch_offsets));
+    if (s->query_batch_lens) CHECKCUDAERROR(cudaFree(s->query_batch_lens));
+    if (s->target_batch_lens) CHECKCUDAERROR(cudaFree(s->target_batch_lens));
+    if (s->packed_tb_matrices) CHECKCUDAERROR(cudaFree(s->packed_tb_matrices));
+    Priv* pv = priv(s);
+    if (pv) {
+      if (pv->colstate) CHECKCUDAERROR(cudaFree(pv->colstate));
+      if (pv->d_cigar) CHECKCUDAERROR(cudaFree(pv->d_cigar));
+      if (pv->d_n_cigar_ops) CHECKCUDAERROR(cudaFree(pv->d_n_cigar_ops));
+      pv->fast.release();
+      for (int e = 0; e < 4; e++) if (pv->ev[e]) CHECKCUDAERROR(cudaEventDestroy(pv->ev[e]));
+      delete pv;
+    }
+    if (s->str) CHECKCUDAERROR(cudaStreamDestroy(s->str));
+    memset(s, 0, sizeof(*s));
+  }
+}
+
+void gasal_destroy_gpu_storage_v(gasal_gpu_storage_v* gpu_storage_vec) {
+  if (gpu_storage_vec->a != NULL) free(gpu_storage_vec->a);
+  gpu_storage_vec->a = NULL; gpu_storage_vec->n = 0;
+}
+
+// ---- the hot path -----------------------------------------------------------------------------------------------
+static void grow_device(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n, const gasal_params_t* params) {
+  // src/gasal_align.cu:70-145 (same policy: integer multiples, warn on stderr)
+  if (s->gpu_max_query_batch_bytes < q_bytes) {
+    int i = 2; while ((uint64_t)s->gpu_max_query_batch_bytes * i < q_bytes) i++;
+    fprintf(stderr, "[GASAL WARNING:] actual_query_batch_bytes(%d) > Allocated GPU memory (gpu_max_query_batch_bytes=%d). Therefore, allocating %d bytes on GPU (gpu_max_query_batch_bytes=%d). Performance may be lost if this is repeated many times.\n",
+            q_bytes, s->gpu_max_query_batch_bytes, s->gpu_max_query_batch_bytes * i, s->gpu_max_query_batch_bytes * i);
+    s->gpu_max_query_batch_bytes *= i;
+    const bool alias = (void*)s->packed_query_batch == (void*)s->unpacked_query_batch;
+    dev_realloc(&s->unpacked_query_batch, s->gpu_max_query_batch_bytes);
+    if (alias) s->packed_query_batch = (uint32_t*)s->unpacked_query_batch;
+    else dev_realloc(&s->packed_query_batch, s->gpu_max_query_batch_bytes / 8);
+    if (params->start_pos == WITH_TB) {
+      if (s->host_res->cigar != NULL) CHECKCUDAERROR(cudaFreeHost(s->host_res->cigar));
+      CHECKCUDAERROR(cudaHostAlloc(&(s->host_res->cigar), s->gpu_max_query_batch_bytes, cudaHostAllocDefault));
+    }
+  }
+  if (s->gpu_max_target_batch_bytes < t_bytes) {
+    int i = 2; while ((uint64_t)s->gpu_max_target_batch_bytes * i < t_bytes) i++;
+    fprintf(stderr, "[GASAL WARNING:] actual_target_batch_bytes(%d) > Allocated GPU memory (gpu_max_target_batch_bytes=%d). Therefore, allocating %d bytes on GPU (gpu_max_target_batch_bytes=%d). Performance may be lost if this is repeated many times.\n",
+            t_bytes, s->gpu_max_target_batch_bytes, s->gpu_max_target_batch_bytes * i, s->gpu_max_target_batch_bytes * i);
+    s->gpu_max_target_batch_bytes *= i;
+    const bool alias = (void*)s->packed_target_batch == (void*)s->unpacked_target_batch;
+    dev_realloc(&s->unpacked_target_batch, s->gpu_max_target_batch_bytes);
+    if (alias) s->packed_target_batch = (uint32_t*)s->unpacked_target_batch;
+    else dev_realloc(&s->packed_target_batch, s->gpu_max_target_batch_bytes / 8);
+  }
+  if (s->gpu_max_n_alns < n) {
+    int i = 2; while ((uint64_t)s->gpu_max_n_alns * i < n) i++;
+    fprintf(stderr, "[GASAL WARNING:] actual_n_alns(%d) > gpu_max_n_alns(%d). Therefore, allocating memory for %d alignments on  GPU (gpu_max_n_alns=%d). Performance may be lost if this is repeated many times.\n",
+            n, s->gpu_max_n_alns, s->gpu_max_n_alns * i, s->gpu_max_n_alns * i);
+    s->gpu_max_n_alns *= i;
+    dev_realloc(&s->query_batch_lens, s->gpu_max_n_alns); dev_realloc(&s->target_batch_lens, s->gpu_max_n_alns);
+    dev_realloc(&s->query_batch_offsets, s->gpu_max_n_alns); dev_realloc(&s->target_batch_offsets, s->gpu_max_n_alns);
+    dev_realloc(&s->query_op, s->gpu_max_n_alns); dev_realloc(&s->target_op, s->gpu_max_n_alns);
+    if (s->seed_scores) dev_realloc(&s->seed_scores, s->gpu_max_n_alns);
+    gasal_res_destroy_device(s->device_res, s->device_cpy);
+    s->device_cpy = gasal_res_new_device_cpy(s->gpu_max_n_alns, params);
+    s->device_res = gasal_res_new_device(s->device_cpy);
+    if (params->secondBest) {
+      gasal_res_destroy_device(s->device_res_second, s->device_cpy_second);
+      s->device_cpy_second = gasal_res_new_device_cpy(s->gpu_max_n_alns, params);
+      s->device_res_second = gasal_res_new_device(s->device_cpy_second);
+    }
+  }
+}
+
+static void launch_pack(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes) {
+  Priv* pv = priv(s);
+  const uint32_t n16q = q_bytes / 16, n16t = t_bytes / 16;
+  const uint32_t total = n16q + n16t;
+  if (total) {
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const uint32_t blocks = std::min<uint32_t>((total + 255) / 256, (uint32_t)sms * 8);
+    k_pack<<<blocks, 256, 0, s->str>>>((const uint4*)s->unpacked_query_batch, (uint2*)s->packed_query_batch, n16q,
+                                      (const uint4*)s->unpacked_target_batch, (uint2*)s->packed_target_batch, n16t);
+    CHECK_LAUNCH(); pv->launches++;
+  }
+  if (q_bytes & 8) { k_pack_tail<<<1, 1, 0, s->str>>>((const uint2*)(s->unpacked_query_batch + 16 * (size_t)n16q), s->packed_query_batch + 2 * (size_t)n16q); CHECK_LAUNCH(); pv->launches++; }
+  if (t_bytes & 8) { k_pack_tail<<<1, 1, 0, s->str>>>((const uint2*)(s->unpacked_target_batch + 16 * (size_t)n16t), s->packed_target_batch + 2 * (size_t)n16t); CHECK_LAUNCH(); pv->launches++; }
+}
+
+struct BatchShape { uint32_t max_q, max_t, min_q, min_t; };
+
+static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, const gasal_params_t* params, const BatchShape& shape) {
+  Priv* pv = priv(s);
+  DpArgs a; memset(&a, 0, sizeof(a));
+  a.pq = s->packed_query_batch; a.pt = s->packed_target_batch;
+  a.q_lens = s->query_batch_lens; a.t_lens = s->target_batch_lens; a.q_offs = s->query_batch_offsets; a.t_offs = s->target_batch_offsets;
+  a.seed_scores = s->seed_scores; a.n = (int)n;
+  a.match = g_scores.match; a.mismatch = g_scores.mismatch; a.gap_open = g_scores.gap_open; a.gap_extend = g_scores.gap_extend;
+  a.n_value = (uint32_t)g_n_code & 15u; a.n_score = (g_n_penalty >= 0) ? -g_n_penalty : 0; a.n_is_wild_global = (g_n_penalty >= 0);
+  a.score = s->device_cpy->aln_score; a.q_end = s->device_cpy->query_batch_end; a.t_end = s->device_cpy->target_batch_end;
+  a.q_start = s->device_cpy->query_batch_start; a.t_start = s->device_cpy->target_batch_start;
+  if (s->device_cpy_second) { a.score2 = s->device_cpy_second->aln_score; a.q_end2 = s->device_cpy_second->query_batch_end; a.t_end2 = s->device_cpy_second->target_batch_end; }
+  a.head = params->semiglobal_skipping_head; a.tail = params->semiglobal_skipping_tail; a.k_band = params->k_band;
+  const uint32_t q8 = round8(shape.max_q), t8 = round8(shape.max_t);
+  const bool second = params->secondBest != 0;
+  const int start = params->start_pos;
+  const bool want_tb = (start == WITH_TB) && (params->algo == LOCAL || params->algo == GLOBAL);
+
+  if (want_tb) {
+    alloc_tb(s, q8, t8, n);
+    a.tb = s->packed_tb_matrices; a.tb_stride = n;
+    if (pv->cigar_bytes < q_bytes) { dev_realloc(&pv->d_cigar, q_bytes); pv->cigar_bytes = q_bytes; }
+    if (pv->n_cigar_cap < n) { dev_realloc(&pv->d_n_cigar_ops, n); pv->n_cigar_cap = n; }
+    a.cigar = pv->d_cigar; a.n_cigar_ops = pv->d_n_cigar_ops;
+  }
+
+  // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
+  if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
+    const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, s->str);
+    CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "s16x2";
+    return;
+  }
+
+  // ---- general int32 kernels ----
+  const uint32_t stride = (n + 31u) & ~31u;
+  const size_t need = (size_t)stride * std::max<uint32_t>(q8, 8);
+  if (pv->colstate_words < need) { dev_realloc(&pv->colstate, need); pv->colstate_words = need; }
+  a.colstate = pv->colstate; a.col_stride = stride; a.col_rows = q8;
+  const uint32_t BLOCKDIM = 128, N_BLOCKS = (n + BLOCKDIM - 1) / BLOCKDIM;
+  pv->last_kernel = "int32";
+  switch (params->algo) {
+    case LOCAL:
+      if (start == WITH_TB) { if (second) k_local_generic<START_TB, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_local_generic<START_TB, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
+      else if (start == WITH_START) { if (second) k_local_generic<START_POS, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_local_generic<START_POS, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
+      else { if (second) k_local_generic<START_NONE, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_local_generic<START_NONE, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
+      CHECK_LAUNCH(); pv->launches++;
+      if (start == WITH_TB) { k_get_tb<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }   // gasal_align.h:45-53
+      break;
+    case SEMI_GLOBAL:
+      if (start == WITH_START) { if (second) k_semiglobal_generic<START_POS, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_semiglobal_generic<START_POS, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
+      else { if (second) k_semiglobal_generic<START_NONE, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_semiglobal_generic<START_NONE, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
+      CHECK_LAUNCH(); pv->launches++;
+      break;
+    case GLOBAL:
+      if (start == WITH_TB) k_global_generic<START_TB><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_global_generic<START_NONE><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a);
+      CHECK_LAUNCH(); pv->launches++;
+      if (start == WITH_TB) { k_get_tb<false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }   // gasal_align.h:60-68
+      break;
+    case BANDED:
+      k_banded_generic<<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
+      break;
+    default:
+      fprintf(stderr, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo);
+      exit(EXIT_FAILURE);
+  }
+}
+
+static BatchShape scan_shape(const gasal_gpu_storage_t* s, uint32_t n, const Priv* pv, bool have_host_lens) {
+  BatchShape sh;
+  if (!have_host_lens) { sh.max_q = sh.min_q = pv->max_query_len_8; sh.max_t = sh.min_t = pv->max_target_len_8; return sh; }
+  uint32_t mq = 0, mt = 0, nq = 0xFFFFFFFFu, nt = 0xFFFFFFFFu;
+  const uint32_t* ql = s->host_query_batch_lens; const uint32_t* tl = s->host_target_batch_lens;
+  for (uint32_t i = 0; i < n; i++) { mq = std::max(mq, ql[i]); mt = std::max(mt, tl[i]); nq = std::min(nq, ql[i]); nt = std::min(nt, tl[i]); }
+  sh.max_q = mq; sh.max_t = mt; sh.min_q = nq; sh.min_t = nt;
+  return sh;
+}
+
+static void validate(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n) {
+  // src/gasal_align.cu:32-67
+  if (n <= 0) { fprintf(stderr, "[GASAL ERROR:] actual_n_alns <= 0\n"); exit(EXIT_FAILURE); }
+  if (q_bytes <= 0) { fprintf(stderr, "[GASAL ERROR:] actual_query_batch_bytes <= 0\n"); exit(EXIT_FAILURE); }
+  if (t_bytes <= 0) { fprintf(stderr, "[GASAL ERROR:] actual_target_batch_bytes <= 0\n"); exit(EXIT_FAILURE); }
+  if (q_bytes % 8) { fprintf(stderr, "[GASAL ERROR:] actual_query_batch_bytes=%d is not a multiple of 8\n", q_bytes); exit(EXIT_FAILURE); }
+  if (t_bytes % 8) { fprintf(stderr, "[GASAL ERROR:] actual_target_batch_bytes=%d is not a multiple of 8\n", t_bytes); exit(EXIT_FAILURE); }
+  if (q_bytes > s->host_max_query_batch_bytes) { fprintf(stderr, "[GASAL ERROR:] actual_query_batch_bytes(%d) > host_max_query_batch_bytes(%d)\n", q_bytes, s->host_max_query_batch_bytes); exit(EXIT_FAILURE); }
+  if (t_bytes > s->host_max_target_batch_bytes) { fprintf(stderr, "[GASAL ERROR:] actual_target_batch_bytes(%d) > host_max_target_batch_bytes(%d)\n", t_bytes, s->host_max_target_batch_bytes); exit(EXIT_FAILURE); }
+  if (n > s->host_max_n_alns) { fprintf(stderr, "[GASAL ERROR:] actual_n_alns(%d) > host_max_n_alns(%d)\n", n, s->host_max_n_alns); exit(EXIT_FAILURE); }
+}
+
+static void device_stage(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n, const gasal_params_t* params, const BatchShape& shape) {
+  Priv* pv = priv(s);
+  if (!params->isPacked) launch_pack(s, q_bytes, t_bytes);                             // gasal_align.cu:190-201
+  if (params->isReverseComplement) {                                                    // :232-246
+    const uint32_t warps = 2 * n, blocks = (warps * 32 + 255) / 256;
+    k_revcomp<<<blocks, 256, 0, s->str>>>(s->packed_query_batch, s->packed_target_batch, s->query_batch_lens, s->target_batch_lens,
+                                          s->query_batch_offsets, s->target_batch_offsets, s->query_op, s->target_op, n);
+    CHECK_LAUNCH(); pv->launches++;
+  }
+  CHECKCUDAERROR(cudaEventRecord(pv->ev[1], s->str));
+  launch_dp(s, q_bytes, n, params, shape);                                              // :249
+  CHECKCUDAERROR(cudaEventRecord(pv->ev[2], s->str));
+}
+
+void gasal_aln_async(gasal_gpu_storage_t* s, const uint32_t actual_query_batch_bytes, const uint32_t actual_target_batch_bytes,
+                     const uint32_t actual_n_alns, const gasal_params_t* params) {
+  validate(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns);
+  Priv* pv = priv(s);
+  if (pv == NULL) { fprintf(stderr, "[GASAL ERROR:] storage was not initialised with gasal_init_streams\n"); exit(EXIT_FAILURE); }
+  grow_device(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns, params);
+  const uint32_t n = actual_n_alns;
+  const BatchShape shape = scan_shape(s, n, pv, true);
+
+  CHECKCUDAERROR(cudaEventRecord(pv->ev[0], s->str));
+  // H2D: one copy per host page (gasal_align.cu:152-175), then lens/offsets (:207-210), seeds, ops
+  for (host_batch_t* cur = s->extensible_host_unpacked_query_batch; cur != NULL; cur = cur->next)
+    if (cur->data_size) CHECKCUDAERROR(cudaMemcpyAsync(&(s->unpacked_query_batch[cur->offset]), cur->data, cur->data_size, cudaMemcpyHostToDevice, s->str));
+  for (host_batch_t* cur = s->extensible_host_unpacked_target_batch; cur != NULL; cur = cur->next)
+    if (cur->data_size) CHECKCUDAERROR(cudaMemcpyAsync(&(s->unpacked_target_batch[cur->offset]), cur->data, cur->data_size, cudaMemcpyHostToDevice, s->str));
+  CHECKCUDAERROR(cudaMemcpyAsync(s->query_batch_lens, s->host_query_batch_lens, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
+  CHECKCUDAERROR(cudaMemcpyAsync(s->target_batch_lens, s->host_target_batch_lens, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
+  CHECKCUDAERROR(cudaMemcpyAsync(s->query_batch_offsets, s->host_query_batch_offsets, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
+  CHECKCUDAERROR(cudaMemcpyAsync(s->target_batch_offsets, s->host_target_batch_offsets, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
+  if (params->algo == KSW) {
+    if (s->seed_scores == NULL || s->host_seed_scores == NULL) { fprintf(stderr, "seed_scores == NULL\n"); exit(EXIT_FAILURE); }
+    CHECKCUDAERROR(cudaMemcpyAsync(s->seed_scores, s->host_seed_scores, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
+  }
+  if (params->isReverseComplement) {
+    CHECKCUDAERROR(cudaMemcpyAsync(s->query_op, s->host_query_op, n, cudaMemcpyHostToDevice, s->str));
+    CHECKCUDAERROR(cudaMemcpyAsync(s->target_op, s->host_target_op, n, cudaMemcpyHostToDevice, s->str));
+  }
+
+  device_stage(s, actual_query_batch_bytes, actual_target_batch_bytes, n, params, shape);
+
+  // D2H (gasal_align.cu:266-304)
+  gasal_res_t* h = s->host_res; gasal_res_t* d = s->device_cpy;
+  if (h->aln_score && d->aln_score) CHECKCUDAERROR(cudaMemcpyAsync(h->aln_score, d->aln_score, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+  if (h->query_batch_start && d->query_batch_start) CHECKCUDAERROR(cudaMemcpyAsync(h->query_batch_start, d->query_batch_start, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+  if (h->target_batch_start && d->target_batch_start) CHECKCUDAERROR(cudaMemcpyAsync(h->target_batch_start, d->target_batch_start, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+  if (h->query_batch_end && d->query_batch_end) CHECKCUDAERROR(cudaMemcpyAsync(h->query_batch_end, d->query_batch_end, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+  if (h->target_batch_end && d->target_batch_end) CHECKCUDAERROR(cudaMemcpyAsync(h->target_batch_end, d->target_batch_end, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+  if (params->start_pos == WITH_TB && pv->d_cigar && h->cigar) {
+    CHECKCUDAERROR(cudaMemcpyAsync(h->cigar, pv->d_cigar, actual_query_batch_bytes, cudaMemcpyDeviceToHost, s->str));
+    CHECKCUDAERROR(cudaMemcpyAsync(h->n_cigar_ops, pv->d_n_cigar_ops, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->str));
+  }
+  if (params->secondBest && s->host_res_second && s->device_cpy_second) {
+    gasal_res_t* h2 = s->host_res_second; gasal_res_t* d2 = s->device_cpy_second;
+    if (h2->aln_score && d2->aln_score) CHECKCUDAERROR(cudaMemcpyAsync(h2->aln_score, d2->aln_score, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+    if (h2->query_batch_end && d2->query_batch_end) CHECKCUDAERROR(cudaMemcpyAsync(h2->query_batch_end, d2->query_batch_end, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+    if (h2->target_batch_end && d2->target_batch_end) CHECKCUDAERROR(cudaMemcpyAsync(h2->target_batch_end, d2->target_batch_end, n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->str));
+  }
+  CHECKCUDAERROR(cudaEventRecord(pv->ev[3], s->str));
+  pv->timing_pending = true;
+  s->is_free = 0;
+}
+
+void gasalx_aln_device_resident(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n, const gasal_params_t* params) {
+  Priv* pv = priv(s);
+  BatchShape shape = scan_shape(s, n, pv, true);
+  CHECKCUDAERROR(cudaEventRecord(pv->ev[0], s->str));
+  device_stage(s, q_bytes, t_bytes, n, params, shape);
+  CHECKCUDAERROR(cudaEventRecord(pv->ev[3], s->str));
+  pv->timing_pending = true;
+  s->is_free = 0;
+}
+
+int gasal_is_aln_async_done(gasal_gpu_storage_t* s) {   // src/gasal_align.cu:310-326
+  if (s->is_free == 1) return -2;
+  cudaError_t err = cudaStreamQuery(s->str);
+  if (err != cudaSuccess) {
+    if (err == cudaErrorNotReady) return -1;
+    fprintf(stderr, "[GASAL CUDA ERROR:] %s(CUDA error no.=%d). Line no. %d in file %s\n", cudaGetErrorString(err), err, __LINE__, __FILE__);
+    exit(EXIT_FAILURE);
+  }
+  gasal_host_batch_reset(s);
+  s->is_free = 1;
+  s->current_n_alns = 0;
+  return 0;
+}
+
+int gasalx_last_batch_ms(gasal_gpu_storage_t* s, float out_ms[3]) {
+  Priv* pv = priv(s);
+  if (!pv || !pv->timing_pending) return -1;
+  if (cudaEventQuery(pv->ev[3]) != cudaSuccess) return -1;
+  CHECKCUDAERROR(cudaEventElapsedTime(&out_ms[0], pv->ev[0], pv->ev[3]));
+  CHECKCUDAERROR(cudaEventElapsedTime(&out_ms[2], pv->ev[1], pv->ev[2]));
+  float to_packed; CHECKCUDAERROR(cudaEventElapsedTime(&to_packed, pv->ev[0], pv->ev[1]));
+  out_ms[1] = to_packed;
+  return 0;
+}
+
+uint64_t gasalx_kernel_launches(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return pv ? pv->launches : 0; }
+const char* gasalx_last_kernel_name(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return pv ? pv->last_kernel : "none"; }
+
+}  // extern "C"

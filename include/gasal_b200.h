@@ -1,0 +1,228 @@
+/*
+ * gasal_b200.h -- the C ABI of the B200-native batched pairwise-alignment engine.
+ *
+ * This is the drop-in boundary for the GASAL2 path of Genomics-GPU (reference tree
+ * Non-CDP/GASAL2/src/).  Every type and entry point below keeps the NAME, argument meaning,
+ * ownership rules and error behaviour of the reference interface it replaces (cited file:line);
+ * the only change is that the reference's C++ `Parameters*` argument (src/args_parser.h:24-68, a
+ * class with std::string / std::ifstream members) becomes the POD `gasal_params_t`, so the library
+ * is callable from C, cgo, JNI, ctypes ...  C++ callers that want the unchanged reference
+ * signatures include gasal_header.h instead, which layers `class Parameters` on top of this file.
+ *
+ * Plain pointers and sizes only; no C++ or torch types cross this boundary.
+ */
+#ifndef GASAL_B200_H
+#define GASAL_B200_H
+
+#include <stdint.h>
+#include <stdlib.h>
+
+#if defined(__CUDACC__) || defined(__CUDA_RUNTIME_H__) || defined(GASAL_B200_WITH_CUDA_RUNTIME)
+#include <cuda_runtime.h>
+#else
+/* C callers without the CUDA headers: same representation as the toolkit's types */
+typedef struct CUstream_st* cudaStream_t;
+#ifndef GASAL_B200_UINT4_DEFINED
+#define GASAL_B200_UINT4_DEFINED
+typedef struct __attribute__((aligned(16))) { unsigned int x, y, z, w; } uint4;
+#endif
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- enums: src/gasal.h:37-72 (same enumerator names and values) ---------------------------- */
+enum comp_start { WITHOUT_START, WITH_START, WITH_TB };
+enum Bool { FALSE, TRUE };
+enum data_source { NONE, QUERY, TARGET, BOTH };
+enum algo_type { UNKNOWN, GLOBAL, SEMI_GLOBAL, LOCAL, MICROLOCAL, BANDED, KSW };
+enum operation_on_seq { FORWARD_NATURAL, REVERSE_NATURAL, FORWARD_COMPLEMENT, REVERSE_COMPLEMENT };
+
+/* ---- host staging page: src/gasal.h:75-83 --------------------------------------------------- */
+struct host_batch {
+  uint8_t* data;
+  uint32_t page_size;
+  uint32_t data_size;
+  uint32_t offset;
+  int is_locked;
+  struct host_batch* next;
+};
+typedef struct host_batch host_batch_t;
+
+/* ---- results, SoA: src/gasal.h:86-95 -------------------------------------------------------- */
+struct gasal_res {
+  int32_t* aln_score;
+  int32_t* query_batch_end;
+  int32_t* target_batch_end;
+  int32_t* query_batch_start;
+  int32_t* target_batch_start;
+  uint8_t* cigar;          /* (count<<2)|op bytes, REVERSE alignment order, at host_query_batch_offsets[i] */
+  uint32_t* n_cigar_ops;
+};
+typedef struct gasal_res gasal_res_t;
+
+/* ---- per-stream storage: src/gasal.h:98-150 (same fields, same order; one private tail field) - */
+typedef struct {
+  uint8_t* unpacked_query_batch;
+  uint8_t* unpacked_target_batch;
+  uint32_t* packed_query_batch;
+  uint32_t* packed_target_batch;
+  uint32_t* query_batch_offsets;
+  uint32_t* target_batch_offsets;
+  uint32_t* query_batch_lens;
+  uint32_t* target_batch_lens;
+
+  uint32_t* host_seed_scores;
+  uint32_t* seed_scores;
+
+  host_batch_t* extensible_host_unpacked_query_batch;
+  host_batch_t* extensible_host_unpacked_target_batch;
+
+  uint8_t* host_query_op;
+  uint8_t* host_target_op;
+  uint8_t* query_op;
+  uint8_t* target_op;
+
+  uint32_t* host_query_batch_offsets;
+  uint32_t* host_target_batch_offsets;
+  uint32_t* host_query_batch_lens;
+  uint32_t* host_target_batch_lens;
+
+  gasal_res_t* host_res;          /* struct on host, arrays in pinned host memory */
+  gasal_res_t* device_cpy;        /* struct on host, arrays in device memory */
+  gasal_res_t* device_res;        /* struct on device (kept for source compatibility; kernels take raw arrays) */
+
+  gasal_res_t* host_res_second;
+  gasal_res_t* device_res_second;
+  gasal_res_t* device_cpy_second;
+
+  uint32_t gpu_max_query_batch_bytes;
+  uint32_t gpu_max_target_batch_bytes;
+
+  uint32_t host_max_query_batch_bytes;
+  uint32_t host_max_target_batch_bytes;
+
+  uint32_t gpu_max_n_alns;
+  uint32_t host_max_n_alns;
+  uint32_t current_n_alns;
+
+  uint64_t packed_tb_matrix_size;
+  uint4* packed_tb_matrices;
+
+  cudaStream_t str;
+  int is_free;
+  int id;
+
+  void* b200_priv;                /* engine-private scratch (column state, events, counters); never touch */
+} gasal_gpu_storage_t;
+
+/* vector of storages: src/gasal.h:153-156 */
+typedef struct {
+  int n;
+  gasal_gpu_storage_t* a;
+} gasal_gpu_storage_v;
+
+/* match / mismatch / gap penalties, all positive: src/gasal.h:160-165 */
+typedef struct {
+  int32_t match;
+  int32_t mismatch;
+  int32_t gap_open;
+  int32_t gap_extend;
+} gasal_subst_scores;
+
+/* ---- run-time options the library consumes: the POD image of `class Parameters` ---------------
+ * (src/args_parser.h:24-68; defaults src/args_parser.cpp:12-29).  Field names are the reference's. */
+typedef struct {
+  int32_t algo;                      /* enum algo_type */
+  int32_t start_pos;                 /* enum comp_start */
+  int32_t secondBest;                /* enum Bool */
+  int32_t isPacked;                  /* input already 4-bit packed (src/ctors.cpp:64-67) */
+  int32_t isReverseComplement;       /* apply host_query_op / host_target_op */
+  int32_t semiglobal_skipping_head;  /* enum data_source */
+  int32_t semiglobal_skipping_tail;  /* enum data_source */
+  int32_t k_band;
+} gasal_params_t;
+
+/* defaults of Parameters::Parameters (algo is left UNKNOWN there; callers set it) */
+void gasal_params_default(gasal_params_t* p);
+
+/* ---- src/ctors.h:4-16 ------------------------------------------------------------------------ */
+gasal_gpu_storage_v gasal_init_gpu_storage_v(int n_streams);
+void gasal_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len, int max_target_len, int max_n_alns,
+                        const gasal_params_t* params);
+void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_params_t* params);
+void gasal_destroy_gpu_storage_v(gasal_gpu_storage_v* gpu_storage_vec);
+
+/* ---- src/gasal_align.h:114-120 --------------------------------------------------------------- */
+void gasal_copy_subst_scores(gasal_subst_scores* subst);
+/* Enqueue H2D copies, pack (+ reverse/complement), the DP kernel(s) (+ traceback) and D2H copies on
+ * gpu_storage->str and return without synchronising; sets is_free = 0.  Invalid arguments or a CUDA
+ * error print "[GASAL ERROR:] ..." to stderr and exit(EXIT_FAILURE), like the reference
+ * (src/gasal_align.cu:29-307). */
+void gasal_aln_async(gasal_gpu_storage_t* gpu_storage, const uint32_t actual_query_batch_bytes,
+                     const uint32_t actual_target_batch_bytes, const uint32_t actual_n_alns, const gasal_params_t* params);
+/* 0: finished (host pages reset, is_free = 1, current_n_alns = 0); -1: still running; -2: nothing launched
+ * (src/gasal_align.cu:310-326) */
+int gasal_is_aln_async_done(gasal_gpu_storage_t* gpu_storage);
+
+/* ---- src/host_batch.h:9-17 ------------------------------------------------------------------- */
+host_batch_t* gasal_host_batch_new(uint32_t batch_bytes, uint32_t offset);
+void gasal_host_batch_destroy(host_batch_t* res);
+host_batch_t* gasal_host_batch_getlast(host_batch_t* arg);
+void gasal_host_batch_reset(gasal_gpu_storage_t* gpu_storage);
+uint32_t gasal_host_batch_fill(gasal_gpu_storage_t* gpu_storage, uint32_t idx, const char* data, uint32_t size, enum data_source SRC);
+uint32_t gasal_host_batch_add(gasal_gpu_storage_t* gpu_storage, uint32_t idx, const char* data, uint32_t size, enum data_source SRC);
+uint32_t gasal_host_batch_addbase(gasal_gpu_storage_t* gpu_storage, uint32_t idx, const char base, enum data_source SRC);
+void gasal_host_batch_print(host_batch_t* res);
+void gasal_host_batch_printall(host_batch_t* res);
+
+/* ---- src/interfaces.h:8-14 ------------------------------------------------------------------- */
+void gasal_host_alns_resize(gasal_gpu_storage_t* gpu_storage, int new_max_alns, const gasal_params_t* params);
+void gasal_op_fill(gasal_gpu_storage_t* gpu_storage_t, uint8_t* data, uint32_t nbr_seqs_in_stream, enum data_source SRC);
+/* the reference declares defaults (gpu_select = 0, isPrintingProp = true) in C++; C callers pass both */
+void gasal_set_device(int gpu_select, int isPrintingProp);
+
+/* ---- src/res.h:4-8 --------------------------------------------------------------------------- */
+gasal_res_t* gasal_res_new_host(uint32_t max_n_alns, const gasal_params_t* params);
+gasal_res_t* gasal_res_new_device(gasal_res_t* device_cpy);
+gasal_res_t* gasal_res_new_device_cpy(uint32_t max_n_alns, const gasal_params_t* params);
+void gasal_res_destroy_host(gasal_res_t* res);
+void gasal_res_destroy_device(gasal_res_t* device_res, gasal_res_t* device_cpy);
+
+/* ================================================================================================
+ * Extensions (no counterpart in the reference; prefix gasalx_).
+ * ============================================================================================== */
+
+/* Run-time replacement of the reference's compile-time -DN_CODE / -DN_PENALTY (Makefile:45-49).
+ * n_penalty < 0 means "N_PENALTY not defined" (N scores 0 in local/semi-global/banded/ksw). */
+void gasalx_set_n_code(int n_code, int n_penalty);
+
+/* Which DP implementation gasal_aln_async may pick: 0 = automatic (s16x2 fast path when the batch
+ * qualifies, else the general int32 kernels), 1 = force the general int32 kernels. */
+void gasalx_set_kernel_policy(int policy);
+
+/* Device-side timing of the last finished batch of a storage, in milliseconds, measured with CUDA
+ * events on gpu_storage->str: [0] whole pipeline (first H2D .. last D2H), [1] pack(+revcomp),
+ * [2] DP kernels (+traceback).  Returns 0 on success, -1 if the batch has not finished. */
+int gasalx_last_batch_ms(gasal_gpu_storage_t* gpu_storage, float out_ms[3]);
+
+/* Number of kernels the engine has launched on this storage since init (for launch accounting). */
+uint64_t gasalx_kernel_launches(const gasal_gpu_storage_t* gpu_storage);
+
+/* Name of the DP kernel family used by the last batch of this storage ("s16x2", "int32", ...). */
+const char* gasalx_last_kernel_name(const gasal_gpu_storage_t* gpu_storage);
+
+/* Device-resident entry: run pack -> DP -> (traceback) for a batch whose UNPACKED (or, with
+ * params->isPacked, packed) sequences, lens and offsets are ALREADY in the storage's device buffers
+ * (no host<->device copies).  Used to time the kernels alone.  Results stay in device_cpy arrays. */
+void gasalx_aln_device_resident(gasal_gpu_storage_t* gpu_storage, uint32_t actual_query_batch_bytes,
+                                uint32_t actual_target_batch_bytes, uint32_t actual_n_alns, const gasal_params_t* params);
+
+/* Version string of the engine. */
+const char* gasalx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GASAL_B200_H */

@@ -1,0 +1,195 @@
+"""GPU parity: the CUDA engine (through the C ABI) must be BIT-EXACT against the oracle on every
+result field, for every mode of the GASAL2 path (a11-a15, Q1-Q14)."""
+import numpy as np
+import pytest
+
+from genomics_gpu_b200 import capi, synth
+from genomics_gpu_b200.aligner import Aligner
+from oracle import pyoracle as po
+
+from helpers import K3, K5, K2ND, assert_same, oracle_align, cigar_slices, cigar_rescore
+
+pytestmark = pytest.mark.gpu
+
+SCORINGS = [(1, 4, 6, 1), (2, 3, 5, 2), (5, 4, 10, 1)]
+
+
+def ragged(seed, n=600, **kw):
+    return synth.random_ragged_pairs(n, 9, 220, 9, 330, seed=seed, n_frac=0.01, **kw)
+
+
+def run(batch, *, policy=0, **kw):
+    lib = capi.load()
+    lib.gasalx_set_kernel_policy(policy)
+    mq = int(batch.q_lens.max()) + 7; mt = int(batch.t_lens.max()) + 7
+    with Aligner(max_query_len=mq, max_target_len=mt, max_n_alns=batch.n, n_streams=1, **kw) as al:
+        res = al.align(batch)
+        res["_kernel"] = al.kernel_name(0)
+    lib.gasalx_set_kernel_policy(0)
+    return res
+
+
+@pytest.mark.parametrize("scoring", SCORINGS)
+@pytest.mark.parametrize("policy", [0, 1])
+def test_local_score_end(oracle, scoring, policy):
+    b = ragged(11)
+    want = oracle_align(oracle, b, algo=po.LOCAL, scoring=scoring)
+    got = run(b, policy=policy, algo=capi.LOCAL, scoring=scoring)
+    assert_same(got, want, K3, f"local {scoring} policy={policy} kernel={got['_kernel']}")
+
+
+@pytest.mark.parametrize("policy", [0, 1])
+def test_local_with_start(oracle, policy):
+    b = ragged(12)
+    want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_START)
+    got = run(b, policy=policy, algo=capi.LOCAL, start=capi.WITH_START)
+    assert_same(got, want, K5, f"local start kernel={got['_kernel']}")
+
+
+def test_local_second_best(oracle):
+    b = ragged(13)
+    want = oracle_align(oracle, b, algo=po.LOCAL, second_best=True)
+    got = run(b, algo=capi.LOCAL, second_best=True)
+    assert_same(got, want, K3 + K2ND, "local second-best")
+
+
+@pytest.mark.parametrize("scoring", SCORINGS[:2])
+def test_local_traceback(oracle, scoring):
+    b = ragged(14, n=300)
+    want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_TB, scoring=scoring)
+    got = run(b, algo=capi.LOCAL, start=capi.WITH_TB, scoring=scoring)
+    assert_same(got, want, K5 + ["n_cigar_ops"], "local tb")
+    gc, wc = cigar_slices(got, b), cigar_slices(want, b)
+    assert gc == wc
+    if scoring == (1, 4, 6, 1):
+        # property: at the default scoring every CIGAR re-scores to aln_score
+        for i, c in enumerate(gc):
+            if got["aln_score"][i] > 0:
+                assert cigar_rescore(c, scoring) == got["aln_score"][i]
+
+
+@pytest.mark.parametrize("head", [po.NONE, po.QUERY, po.TARGET, po.BOTH])
+@pytest.mark.parametrize("tail", [po.NONE, po.QUERY, po.TARGET, po.BOTH])
+def test_semiglobal_all_head_tail(oracle, head, tail):
+    b = ragged(15 + 4 * head + tail, n=300)
+    mql = 1024
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, head=head, tail=tail, start=po.WITH_START, max_query_len=mql)
+    got = run(b, algo=capi.SEMI_GLOBAL, head=head, tail=tail, start=capi.WITH_START)
+    assert_same(got, want, K5, f"semi-global h{head} t{tail} with start")
+    got = run(b, algo=capi.SEMI_GLOBAL, head=head, tail=tail)
+    assert_same(got, want, K3, f"semi-global h{head} t{tail}")
+
+
+@pytest.mark.parametrize("scoring", SCORINGS)
+@pytest.mark.parametrize("policy", [0, 1])
+def test_semiglobal_default_with_start(oracle, scoring, policy):
+    b = ragged(40)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, start=po.WITH_START, scoring=scoring, max_query_len=1024)
+    got = run(b, policy=policy, algo=capi.SEMI_GLOBAL, start=capi.WITH_START, scoring=scoring)
+    assert_same(got, want, K5, f"semi-global default {scoring} kernel={got['_kernel']}")
+
+
+def test_semiglobal_second_best(oracle):
+    b = ragged(41, n=300)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, second_best=True, max_query_len=1024)
+    got = run(b, algo=capi.SEMI_GLOBAL, second_best=True)
+    assert_same(got, want, K3 + K2ND, "semi-global second-best")
+
+
+@pytest.mark.parametrize("scoring", SCORINGS)
+@pytest.mark.parametrize("policy", [0, 1])
+def test_global_score(oracle, scoring, policy):
+    b = ragged(42)
+    want = oracle_align(oracle, b, algo=po.GLOBAL, scoring=scoring)
+    got = run(b, policy=policy, algo=capi.GLOBAL, scoring=scoring)
+    assert_same(got, want, ["aln_score"], f"global {scoring}")
+
+
+def test_global_traceback(oracle):
+    b = ragged(43, n=300)
+    want = oracle_align(oracle, b, algo=po.GLOBAL, start=po.WITH_TB)
+    got = run(b, algo=capi.GLOBAL, start=capi.WITH_TB)
+    assert_same(got, want, ["aln_score"], "global tb score")
+    # parity domain: neither length a multiple of 8 (otherwise the walker's first tile is never written)
+    ok = (b.q_lens % 8 != 0) & (b.t_lens % 8 != 0)
+    assert ok.sum() > 100
+    assert np.array_equal(got["n_cigar_ops"][ok], want["n_cigar_ops"][ok])
+    gc, wc = cigar_slices(got, b), cigar_slices(want, b)
+    for i in np.nonzero(ok)[0]:
+        assert gc[i] == wc[i], f"pair {i}"
+
+
+@pytest.mark.parametrize("k_band", [8, 24, 64, 4096])
+def test_banded(oracle, k_band):
+    b = ragged(44 + k_band, n=400)
+    want = oracle_align(oracle, b, algo=po.BANDED, k_band=k_band)
+    got = run(b, algo=capi.BANDED, k_band=k_band)
+    assert_same(got, want, K3, f"banded k={k_band}")
+
+
+def test_reverse_complement(oracle):
+    b = synth.random_ragged_pairs(400, 9, 200, 9, 300, seed=77)
+    rng = np.random.default_rng(5)
+    q_op = rng.integers(0, 4, size=b.n).astype(np.uint8); t_op = rng.integers(0, 4, size=b.n).astype(np.uint8)
+    pq = oracle.pack(b.q_bytes); pt = oracle.pack(b.t_bytes)
+    rq, rt = oracle.revcomp(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, q_op, t_op)
+    want = oracle.align(rq, rt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, algo=po.LOCAL, start=po.WITH_START)
+    mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
+    with Aligner(algo=capi.LOCAL, start=capi.WITH_START, reverse_complement=True, max_query_len=mq, max_target_len=mt,
+                 max_n_alns=b.n, n_streams=1) as al:
+        got = al.align(b, q_op=q_op, t_op=t_op)
+    assert_same(got, want, K5, "reverse-complement + local")
+
+
+def test_prepacked_input(oracle):
+    b = ragged(90, n=300)
+    pq = oracle.pack(b.q_bytes); pt = oracle.pack(b.t_bytes)
+    want = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, algo=po.LOCAL)
+    # isPacked: the caller hands over packed words in the "unpacked" pages (src/ctors.cpp:64-67); byte counts are 1/2 per base,
+    # offsets still index bases (kernels use offset >> 3)
+    packed = synth.PairBatch(pq.view(np.uint8), pt.view(np.uint8), b.q_offs, b.t_offs, b.q_lens, b.t_lens)
+    mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
+    with Aligner(algo=capi.LOCAL, is_packed=True, max_query_len=mq, max_target_len=mt, max_n_alns=b.n, n_streams=1) as al:
+        al.fill(0, packed)
+        al.launch(0, ((packed.q_bytes.size + 7) // 8) * 8, ((packed.t_bytes.size + 7) // 8) * 8, b.n)
+        al.wait(0)
+        got = al.results(0, b.n)
+    assert_same(got, want, K3, "pre-packed input")
+
+
+def test_edge_shapes(oracle):
+    """tiny, one-word, exact-multiple-of-8 and very unbalanced pairs; identical sequences; no similarity"""
+    qs = [b"A", b"ACGTACGT", b"ACGTACGTA", b"ACGT" * 40, b"T" * 33, b"ACGTTGCA" * 3, b"G" * 8, b"ACGTN" * 10, b"NNNNNNNN"]
+    ts = [b"A", b"ACGTACGT", b"TTACGTACGTATT", b"ACGT" * 40, b"A" * 300, b"ACGTTGCA" * 30, b"C" * 16, b"ACGTN" * 20, b"NNNNNNNNNNNN"]
+    b = synth.batch_from_sequences(qs, ts)
+    for algo, keys, extra in [(po.LOCAL, K5, dict(start=po.WITH_START)), (po.SEMI_GLOBAL, K5, dict(start=po.WITH_START, max_query_len=1024)),
+                              (po.GLOBAL, ["aln_score"], {}), (po.BANDED, K3, dict(k_band=16))]:
+        want = oracle_align(oracle, b, algo=algo, **extra)
+        extra.pop("max_query_len", None)
+        got = run(b, algo=algo, **extra)
+        assert_same(got, want, keys, f"edge shapes algo={algo}")
+
+
+def test_multi_storage_round_robin(oracle):
+    """two storages in flight, as test_prog.cpp does; also exercises regrow of device buffers"""
+    b = ragged(91, n=900)
+    want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_START)
+    chunks = [(0, 300), (300, 600), (600, 900)]
+    with Aligner(algo=capi.LOCAL, start=capi.WITH_START, max_query_len=64, max_target_len=64, max_n_alns=100, n_streams=2) as al:
+        outs = {}
+        pending = {}
+        for ci, (lo, hi) in enumerate(chunks):
+            si = ci % 2
+            if si in pending:
+                plo, phi, pb = pending.pop(si); al.wait(si); outs[plo] = al.results(si, phi - plo)
+            sub = b.slice(lo, hi)
+            # host pages were sized for 100 x 64 bases: grow them the way a caller would (fill one by one)
+            al.fill_one_by_one(si, [sub.query(i) for i in range(sub.n)], [sub.target(i) for i in range(sub.n)])
+            qb, tb = al._last_bytes
+            al.launch(si, qb, tb, sub.n)
+            pending[si] = (lo, hi, sub)
+        for si, (plo, phi, pb) in pending.items():
+            al.wait(si); outs[plo] = al.results(si, phi - plo)
+    for lo, hi in chunks:
+        sub_want = {k: want[k][lo:hi] for k in K5}
+        assert_same(outs[lo], sub_want, K5, f"chunk {lo}:{hi}")
