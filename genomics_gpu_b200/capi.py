@@ -79,7 +79,7 @@ EXPORTED_SYMBOLS = [
     "gasal_host_alns_resize", "gasal_op_fill", "gasal_set_device",
     "gasal_res_new_host", "gasal_res_new_device", "gasal_res_new_device_cpy", "gasal_res_destroy_host", "gasal_res_destroy_device",
     "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
-    "gasalx_aln_device_resident", "gasalx_version",
+    "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
 ]
 
 _lib = None
@@ -115,6 +115,7 @@ def load() -> C.CDLL:
     lib.gasalx_kernel_launches.argtypes = [P(GpuStorage)]; lib.gasalx_kernel_launches.restype = C.c_uint64
     lib.gasalx_last_kernel_name.argtypes = [P(GpuStorage)]; lib.gasalx_last_kernel_name.restype = C.c_char_p
     lib.gasalx_aln_device_resident.argtypes = [P(GpuStorage), C.c_uint32, C.c_uint32, C.c_uint32, P(Params)]
+    lib.gasalx_host_batch_rearm.argtypes = [P(GpuStorage), C.c_uint32, C.c_uint32, C.c_uint32]
     lib.gasalx_version.restype = C.c_char_p
     _lib = lib
     return lib

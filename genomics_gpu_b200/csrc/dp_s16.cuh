@@ -1,8 +1,332 @@
-// dp_s16.cuh -- s16x2 DPX fast path (placeholder until the kernel lands).
+// dp_s16.cuh -- the s16x2 DPX fast path (K2): inter-task kernels for short-read shapes.
+//
+// One thread = one pair.  The two 16-bit lanes of every register hold TWO CONSECUTIVE 8-ROW STRIPS
+// OF THE SAME PAIR, skewed by one query column: at step k lane L (bits 15:0) computes column k of
+// strip 2j while lane H (bits 31:16) computes column k-1 of strip 2j+1, so lane L's bottom row feeds
+// lane H's top row through registers one step later and only one (H,E) word per column per 16 target
+// rows goes through shared memory.  Per cell pair the work is split over BOTH integer pipes of the SM
+// (measured on B200, profiles/dpx_microbench_r01.json: VIADD.16x2 / IMAD issue on the FMA pipe
+// concurrently with the DPX/ALU pipe):
+//     ALU pipe : PRMT (substitution lookup), VIMNMX3.S16x2.RELU (H), 2 x VIADDMNMX.S16x2 (E, F)
+//     FMA pipe : 2 x VIADD.16x2 (D = diag + s, D - oe), IMAD (argmax key)
+// Substitution scores come from a per-row 4-byte table (one byte per query base A/C/G/T, sign
+// replicated to 16 bits by PRMT) selected by a per-column selector byte that is precomputed once per
+// pair into shared memory.  The argmax with the reference's (strip, column, row) tie order is tracked
+// without branches: key = H*8 + (7-row) per cell, a VIMNMX3 tree per column, and a predicated record of
+// the column -- see DESIGN.md "K2".
+//
+// Exactness: identical results to the general kernels / the reference for every pair the fast path
+// accepts.  Pairs it cannot represent (a base that is not A/C/G/T inside the true length, e.g. N) are
+// pushed to a worklist and recomputed by the general int32 kernel in the same stream.
 #pragma once
 #include "dp_common.cuh"
+#include "dp_generic.cuh"
+
 namespace gb200 {
-struct FastScratch { void release() {} };
-inline bool fast_path_eligible(const DpArgs&, int, int, bool, uint32_t, uint32_t) { return false; }
-inline int fast_path_launch(const DpArgs&, int, int, FastScratch&, uint32_t, uint32_t, cudaStream_t) { return 0; }
+
+constexpr int kFastThreads = 128;
+constexpr uint32_t kFastMaxQ8 = 360;      // (q8+2) * 128 * 5 B must fit one CTA's shared memory
+constexpr uint32_t kFastFallbackSlots = 8192;
+
+struct FastScratch {
+  uint32_t* worklist = nullptr; uint32_t* work_count = nullptr; size_t cap = 0;
+  uint32_t* colstate = nullptr; size_t colstate_words = 0;
+  bool attr_set = false;
+  void release() {
+    if (worklist) cudaFree(worklist);
+    if (work_count) cudaFree(work_count);
+    if (colstate) cudaFree(colstate);
+    worklist = work_count = colstate = nullptr; cap = 0; colstate_words = 0;
+  }
+};
+
+struct FastArgs {
+  DpArgs a;
+  uint32_t q8max;          // columns reserved per thread in shared memory (multiple of 8)
+  uint32_t* worklist; uint32_t* work_count;
+  uint32_t eight;          // == 8, passed at run time so the key multiply stays an IMAD (FMA pipe)
+  uint32_t one;            // == 1, run-time so that the sweep's trip count (columns + 1) is opaque to the unroller
+};
+
+// 4-bit code -> 0..3 for A(1) C(3) G(7) T(4), 4 for anything else
+__device__ __forceinline__ uint32_t base_idx(uint32_t code) {
+  return (uint32_t)((0x4444444424431404ull >> (4 * code)) & 15ull);
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
+__device__ __forceinline__ uint32_t splat16(int v) { const uint32_t u = (uint32_t)v & 0xFFFFu; return u | (u << 16); }
+
+// per-row substitution table: byte i = score of query base i against this row's target base
+__device__ __forceinline__ uint32_t row_table(uint32_t idx, uint32_t mis4, uint32_t delta) {
+  return (idx < 4) ? (mis4 ^ (delta << (8 * idx))) : mis4;
+}
+
+struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
+
+// bestK7 = max.s16x2(bestK7, c7); lanes that strictly improved record (cm, pos).  One asm block so that
+// ptxas fuses the per-lane compares into the predicate outputs of VIMNMX.S16x2 (the CUDA header's
+// __vibmax_s16x2 lost its predicate uses in partially unrolled loops with nvcc 12.9).
+__device__ __forceinline__ void track_update(LaneBest& lb, uint32_t c7, uint32_t cm, uint32_t pos) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pl, ph;\n\t"
+      ".reg .s16 n0, n1, o0, o1;\n\t"
+      ".reg .b32 nb;\n\t"
+      "max.s16x2 nb, %0, %5;\n\t"
+      "mov.b32 {n0, n1}, nb;\n\t"
+      "mov.b32 {o0, o1}, %0;\n\t"
+      "setp.eq.s16 pl, n0, o0;\n\t"
+      "setp.eq.s16 ph, n1, o1;\n\t"
+      "mov.b32 %0, nb;\n\t"
+      "@!pl mov.b32 %1, %6;\n\t"
+      "@!pl mov.b32 %3, %7;\n\t"
+      "@!ph mov.b32 %2, %6;\n\t"
+      "@!ph mov.b32 %4, %7;\n\t"
+      "}"
+      : "+r"(lb.bestK7), "+r"(lb.keyL), "+r"(lb.keyH), "+r"(lb.posL), "+r"(lb.posH)
+      : "r"(c7), "r"(cm), "r"(pos));
+}
+
+// One double-strip sweep of the D-based local recurrence (reference local_kernel_template.h:19-30).
+//   HE  : shared (H | E<<16) per column, slot c+1 holds column c; slot 0 / slot ncol+1 are dummies
+//   V   : shared selector byte per column, same slot numbering
+//   rowA/rowB : substitution tables of the 8 rows of lane L's strip / lane H's strip
+//   pos_base  : (double-strip index << 16), OR-ed with the step to form the recorded position
+__device__ __forceinline__ void local_sweep(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
+                                            const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                            uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t pos_base, LaneBest& lb) {
+  uint32_t p[8], f[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { p[r] = 0; f[r] = 0; }
+  uint32_t h8 = 0, eo = 0;                   // bottom-row H and outgoing E of the previous step (lane L feeds lane H)
+  uint32_t prevsh = 0xCC00u;                 // lane-H selector of the phantom column -1: score 0 / -1
+  uint32_t he = HE[kFastThreads];            // slot 1 = column 0
+  uint32_t v = V[kFastThreads];
+  uint32_t pos = pos_base;
+  for (int k = 0; k < nsteps; k++) {
+    const uint32_t sel = v | prevsh;
+    prevsh = v * 256u + 0x4400u;
+    // lane L takes (H,E) of the strip above from shared memory, lane H takes lane L's bottom row of the previous step
+    uint32_t up = prmt(he, h8, 0x5410);
+    uint32_t e = prmt(he, eo, 0x5432);
+    // prefetch the next step's inputs
+    he = HE[(k + 2) * kFastThreads];
+    v = V[(k + 2) * kFastThreads];
+    uint32_t key[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint32_t s2 = prmt(rowA[r], rowB[r], sel);
+      const uint32_t d = __vadd2(p[r], s2);
+      const uint32_t dm = __vadd2(d, neg_oe2);
+      const uint32_t h = __vimax3_s16x2_relu(d, f[r], e);
+      f[r] = __viaddmax_s16x2(f[r], neg_ext2, dm);
+      e = __viaddmax_s16x2(e, neg_ext2, dm);
+      key[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+      p[r] = up; up = h;
+    }
+    // lane H finished column k-1 of its strip: park (H,E) for the next double-strip
+    HE[k * kFastThreads] = prmt(up, e, 0x7632);
+    h8 = up; eo = e;
+    // branch-free argmax: column max of the keys, strict improvement test per lane on (score<<3 | 7)
+    uint32_t cm = __vimax3_s16x2(key[0], key[1], key[2]);
+    cm = __vimax3_s16x2(cm, key[3], key[4]);
+    cm = __vimax3_s16x2(cm, key[5], key[6]);
+    cm = __vmaxs2(cm, key[7]);
+    const uint32_t c7 = cm | 0x00070007u;
+    track_update(lb, c7, cm, pos);
+    pos++;
+  }
+}
+
+// decode the two lanes' records into the reference's (score, column, row) winner
+struct Winner { int score, col, row; };   // row = absolute row index in sweep order (strip*8 + r)
+__device__ __forceinline__ Winner pick_winner(const LaneBest& lb) {
+  const int sL = (int)(short)(lb.bestK7 & 0xFFFFu) >> 3, sH = (int)(short)(lb.bestK7 >> 16) >> 3;
+  Winner w; w.score = 0; w.col = 0; w.row = 0;
+  const int stripL = 2 * (int)(lb.posL >> 16), stripH = 2 * (int)(lb.posH >> 16) + 1;
+  const bool takeL = (sL > sH) || (sL == sH && stripL < stripH);
+  if (takeL) {
+    if (sL > 0) { w.score = sL; w.col = (int)(lb.posL & 0xFFFFu); w.row = stripL * 8 + (7 - (int)(lb.keyL & 7u)); }
+  } else {
+    if (sH > 0) { w.score = sH; w.col = (int)(lb.posH & 0xFFFFu) - 1; w.row = stripH * 8 + (7 - (int)((lb.keyH >> 16) & 7u)); }
+  }
+  return w;
+}
+
+template <int START>
+__global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
+  extern __shared__ uint32_t smem[];
+  const DpArgs& a = fa.a;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (uint32_t)a.n) return;
+  uint32_t* HE = smem + threadIdx.x;
+  uint8_t* V = (uint8_t*)(smem + (fa.q8max + 3) * kFastThreads) + threadIdx.x;
+
+  const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
+  const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
+  const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
+  const int QR = (int)n_words(qlen), TR = (int)n_words(tlen);
+  const uint32_t mis4 = ((uint32_t)(-a.mismatch) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
+  const uint32_t neg_oe2 = splat16(-(a.gap_open + a.gap_extend)), neg_ext2 = splat16(-a.gap_extend);
+
+  // ---- prologue: selector bytes of the query, (H,E) = 0; detect bases the fast path cannot score ----
+  bool odd = false;
+  const int ncol = QR * 8;
+  V[0] = 0x88; HE[0] = 0;
+  for (int j = 0; j < QR; j++) {
+    const uint32_t w = qw[j];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = 8 * j + k;
+      const uint32_t idx = base_idx(nib(w, k));
+      const bool pad = (uint32_t)c >= qlen;
+      odd |= (idx > 3) && !pad;
+      V[(c + 1) * kFastThreads] = (idx > 3) ? 0x88 : (uint8_t)(0x80u + 0x11u * idx);
+      HE[(c + 1) * kFastThreads] = 0;
+    }
+  }
+  V[(ncol + 1) * kFastThreads] = 0x88; HE[(ncol + 1) * kFastThreads] = 0;
+  V[(ncol + 2) * kFastThreads] = 0x88; HE[(ncol + 2) * kFastThreads] = 0;
+  for (int i = 0; i < TR && !odd; i++) {
+    const uint32_t w = tw[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) odd |= (base_idx(nib(w, k)) > 3) && ((uint32_t)(8 * i + k) < tlen);
+  }
+  if (odd) {   // hand the pair to the general kernel (same stream, next launch)
+    const uint32_t slot = atomicAdd(fa.work_count, 1u);
+    fa.worklist[slot] = tid;
+    return;
+  }
+
+  // ---- forward pass over double-strips ----
+  LaneBest lb; lb.bestK7 = 0x00070007u; lb.keyL = lb.keyH = 0; lb.posL = lb.posH = 0;
+  const int ND = (TR + 1) >> 1;
+  const int nsteps = ncol + (int)fa.one;   // run-time 1: keeps the trip count opaque (compiler note)
+  for (int j = 0; j < ND; j++) {
+    uint32_t rowA[8], rowB[8];
+    const uint32_t wa = tw[2 * j];
+    const uint32_t wb = (2 * j + 1 < TR) ? tw[2 * j + 1] : 0u;     // phantom strip: every base mismatches
+#pragma unroll
+    for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
+    local_sweep(HE, V, nsteps, rowA, rowB, neg_oe2, neg_ext2, fa.eight, (uint32_t)j << 16, lb);
+  }
+  const Winner fw = pick_winner(lb);
+  a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row;
+
+  if (START == START_POS) {
+    // ---- reverse pass (local_kernel_template.h:441-511): same recurrence over the reversed words that hold the
+    // end cell; the first cell that reaches the forward score is the start (target coordinate mirrored, Q3) ----
+    int sx = 0, sy = 0;
+    if (fw.score > 0) {
+      const int rend_reg = min((fw.col >> 3) + 1, QR), gend_reg = min((fw.row >> 3) + 1, TR);
+      const int rcol = rend_reg * 8;
+      for (int j = 0; j < rend_reg; j++) {
+        const uint32_t w = nibrev(qw[rend_reg - 1 - j]);
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+          const int c = 8 * j + k;
+          const uint32_t idx = base_idx(nib(w, k));
+          V[(c + 1) * kFastThreads] = (idx > 3) ? 0x88 : (uint8_t)(0x80u + 0x11u * idx);
+          HE[(c + 1) * kFastThreads] = 0;
+        }
+      }
+      V[(rcol + 1) * kFastThreads] = 0x88; HE[(rcol + 1) * kFastThreads] = 0;
+      V[(rcol + 2) * kFastThreads] = 0x88; HE[(rcol + 2) * kFastThreads] = 0;
+      LaneBest rb; rb.bestK7 = 0x00070007u; rb.keyL = rb.keyH = 0; rb.posL = rb.posH = 0;
+      const int RD = (gend_reg + 1) >> 1;
+      const int fwd7 = (fw.score << 3) | 7;
+      for (int j = 0; j < RD; j++) {
+        uint32_t rowA[8], rowB[8];
+        const uint32_t wa = nibrev(tw[gend_reg - 1 - 2 * j]);
+        const uint32_t wb = (2 * j + 1 < gend_reg) ? nibrev(tw[gend_reg - 2 - 2 * j]) : 0u;
+#pragma unroll
+        for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
+        local_sweep(HE, V, rcol + (int)fa.one, rowA, rowB, neg_oe2, neg_ext2, fa.eight, (uint32_t)j << 16, rb);
+        if ((int)(short)(rb.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.bestK7 >> 16) >= fwd7) break;
+      }
+      const Winner rw = pick_winner(rb);
+      if (rw.score > 0) {
+        sx = rcol - 1 - rw.col;                                    // ridx
+        const int strip = rw.row >> 3, r = rw.row & 7;
+        sy = (8 * gend_reg - 1 - 8 * strip) + r;                   // gidx + (m-1): mirrored inside the word (Q3)
+      }
+    }
+    a.q_start[tid] = sx; a.t_start[tid] = sy;
+  }
+}
+
+// ---- general kernel over the fallback worklist ----------------------------------------------------
+template <int START>
+__global__ void __launch_bounds__(128) k_local_worklist(const FastArgs fa) {
+  const DpArgs& a = fa.a;
+  const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
+  const uint32_t count = *fa.work_count;
+  const Sc sc = make_sc(a, false);
+  for (uint32_t w = gtid; w < count; w += nthreads) {
+    const uint32_t pi = fa.worklist[w];
+    PairCtx p;
+    p.qw = a.pq + (a.q_offs[pi] >> 3); p.tw = a.pt + (a.t_offs[pi] >> 3);
+    p.qlen = a.q_lens[pi]; p.tlen = a.t_lens[pi]; p.QR = n_words(p.qlen); p.TR = n_words(p.tlen);
+    p.cs = a.colstate + gtid; p.stride = a.col_stride;
+    int best, bq, bt;
+    local_forward<false, false>(a, sc, p, pi, best, bq, bt);
+    a.score[pi] = best; a.q_end[pi] = bq; a.t_end[pi] = bt;
+    if (START == START_POS) { int sx, sy; local_reverse(sc, p, best, bq, bt, sx, sy); a.q_start[pi] = sx; a.t_start[pi] = sy; }
+  }
+}
+
+__global__ void k_zero_u32(uint32_t* p) { *p = 0; }
+
+// ---- host side --------------------------------------------------------------------------------------
+inline bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
+  if (algo != ALGO_LOCAL || second || start == START_TB) return false;
+  const uint32_t q8 = (max_q + 7u) & ~7u, t8 = (max_t + 7u) & ~7u;
+  if (q8 == 0 || q8 > kFastMaxQ8) return false;
+  if (a.match < 0 || a.match > 127 || a.mismatch < 0 || a.mismatch > 127) return false;
+  if (a.gap_open < 0 || a.gap_extend < 0 || a.gap_open + a.gap_extend > 2000) return false;
+  // keys are score*8+7 in a signed 16-bit lane; E/F stay above -(mismatch + gap_open + gap_extend)
+  const uint64_t max_score = (uint64_t)std::min(q8, t8) * (uint64_t)a.match;
+  if (max_score > 4000) return false;
+  return true;
+}
+
+inline int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, cudaStream_t str) {
+  (void)algo; (void)max_t;
+  const uint32_t q8 = (max_q + 7u) & ~7u;
+  if (fs.cap < (size_t)a.n) {
+    if (fs.worklist) cudaFree(fs.worklist);
+    fs.worklist = nullptr;
+    if (cudaMalloc(&fs.worklist, sizeof(uint32_t) * (size_t)a.n) != cudaSuccess) return -1;
+    fs.cap = (size_t)a.n;
+  }
+  if (!fs.work_count && cudaMalloc(&fs.work_count, sizeof(uint32_t)) != cudaSuccess) return -1;
+  const size_t cs_need = (size_t)kFastFallbackSlots * q8;
+  if (fs.colstate_words < cs_need) {
+    if (fs.colstate) cudaFree(fs.colstate);
+    fs.colstate = nullptr;
+    if (cudaMalloc(&fs.colstate, cs_need * sizeof(uint32_t)) != cudaSuccess) return -1;
+    fs.colstate_words = cs_need;
+  }
+  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.work_count = fs.work_count; fa.eight = 8; fa.one = 1;
+  const size_t smem = (size_t)(q8 + 3) * kFastThreads * 4 + (size_t)(q8 + 3) * kFastThreads;
+  if (!fs.attr_set) {
+    cudaFuncSetAttribute(k_local_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    cudaFuncSetAttribute(k_local_s16<START_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    fs.attr_set = true;
+  }
+  k_zero_u32<<<1, 1, 0, str>>>(fs.work_count);
+  const uint32_t blocks = ((uint32_t)a.n + kFastThreads - 1) / kFastThreads;
+  if (start == START_POS) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa);
+  else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
+  // fallback pairs (bases outside A/C/G/T): general kernel over the worklist, bounded scratch
+  fa.a.colstate = fs.colstate; fa.a.col_stride = kFastFallbackSlots; fa.a.col_rows = q8;
+  if (start == START_POS) k_local_worklist<START_POS><<<kFastFallbackSlots / 128, 128, 0, str>>>(fa);
+  else k_local_worklist<START_NONE><<<kFastFallbackSlots / 128, 128, 0, str>>>(fa);
+  return 3;
+}
+
 }  // namespace gb200

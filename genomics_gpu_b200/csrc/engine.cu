@@ -529,6 +529,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
   if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
     const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, s->str);
+    if (nl < 0) { fprintf(stderr, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); exit(EXIT_FAILURE); }
     CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "s16x2";
     return;
   }
@@ -688,6 +689,20 @@ int gasalx_last_batch_ms(gasal_gpu_storage_t* s, float out_ms[3]) {
   float to_packed; CHECKCUDAERROR(cudaEventElapsedTime(&to_packed, pv->ev[0], pv->ev[1]));
   out_ms[1] = to_packed;
   return 0;
+}
+
+void gasalx_host_batch_rearm(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n_alns) {
+  host_batch_t* heads[2] = {s->extensible_host_unpacked_query_batch, s->extensible_host_unpacked_target_batch};
+  uint32_t want[2] = {q_bytes, t_bytes};
+  for (int i = 0; i < 2; i++) {
+    uint32_t off = 0, left = want[i];
+    for (host_batch_t* cur = heads[i]; cur != NULL; cur = cur->next) {
+      const uint32_t take = left < cur->page_size ? left : cur->page_size;
+      cur->offset = off; cur->data_size = take; cur->is_locked = (cur->next != NULL && left > take);
+      off += take; left -= take;
+    }
+  }
+  s->current_n_alns = n_alns;
 }
 
 uint64_t gasalx_kernel_launches(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return pv ? pv->launches : 0; }

@@ -219,6 +219,11 @@ const char* gasalx_last_kernel_name(const gasal_gpu_storage_t* gpu_storage);
 void gasalx_aln_device_resident(gasal_gpu_storage_t* gpu_storage, uint32_t actual_query_batch_bytes,
                                 uint32_t actual_target_batch_bytes, uint32_t actual_n_alns, const gasal_params_t* params);
 
+/* Benchmark helper: mark the storage's pinned host pages as holding `q_bytes` / `t_bytes` of staged
+ * sequence data again after gasal_is_aln_async_done reset them, WITHOUT re-copying (the bytes are
+ * still there).  Lets a caller re-submit the same pre-filled pinned batch. */
+void gasalx_host_batch_rearm(gasal_gpu_storage_t* gpu_storage, uint32_t q_bytes, uint32_t t_bytes, uint32_t n_alns);
+
 /* Version string of the engine. */
 const char* gasalx_version(void);
 
