@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 alignment engine (contract: see the task statement).
+
+Workload (BASELINE.json configs[1], "C2"): GASAL2 local + semi-global alignment WITH start/end
+positions on synthetic 150 bp x 600 bp read/window pairs, 1,000,000 pairs PER GPU (weak scaling).
+One "step" = one pass of the hot path over that batch in BOTH modes (local WITH_START, then semi-global
+HEAD=TAIL=TARGET WITH_START).  Metric: GCUPS = sum(query_len * target_len) of the forward DP cells
+(both modes) / time / 1e9 (same definition as the suite's own sw-benchmark).
+
+  value : device-timed (CUDA events on the storages' streams), inputs already resident in HBM; the
+          timed region is pack -> DP (forward + start pass) per mode.
+  e2e   : same metric through the reference-facing C ABI (gasal_aln_async / gasal_is_aln_async_done)
+          with HOST buffers: pinned H2D of the sequences + lens/offsets and D2H of the results inside the
+          timed region, chunked over 2 storages per mode so copies overlap kernels (as test_prog.cpp does).
+  --impl reference : the reference's own kernels (oracle/_ref, built from /root/reference sources for
+          the host) on all host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+QLEN, TLEN = 150, 600
+SCORING = (1, 4, 6, 1)
+
+
+def make_workload(n_pairs: int, seed: int):
+    from genomics_gpu_b200 import synth
+    chunks = []
+    step = 100_000
+    for i, lo in enumerate(range(0, n_pairs, step)):
+        chunks.append(synth.config2(min(step, n_pairs - lo), seed=seed * 1000 + i))
+    if len(chunks) == 1:
+        return chunks[0]
+    q8, t8 = (QLEN + 7) // 8 * 8, (TLEN + 7) // 8 * 8
+    n = sum(c.n for c in chunks)
+    return synth.PairBatch(np.concatenate([c.q_bytes for c in chunks]), np.concatenate([c.t_bytes for c in chunks]),
+                           (np.arange(n, dtype=np.uint64) * q8).astype(np.uint32), (np.arange(n, dtype=np.uint64) * t8).astype(np.uint32),
+                           np.full(n, QLEN, dtype=np.uint32), np.full(n, TLEN, dtype=np.uint32))
+
+
+# ---------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, power, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2])); power.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        # samples under load only (the box idles at ~120 MHz between launches)
+        loaded = [s for s in sm if s > 0.5 * max(sm)] if sm else []
+        return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": max(smax) if smax else None,
+                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def dpx_peak_ops_per_s():
+    """R = measured lane-ops/s of the DPX/ALU integer pipe of one B200 (profiles/dpx_microbench_r01.json)."""
+    p = os.path.join(ROOT, "profiles", "dpx_microbench_r01.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)
+        return float(d["R_alu_lane_ops_per_s"]), "measured (profiles/dpx_microbench_r01.json)"
+    except Exception:
+        return 148 * 64 * 1.965e9, "a-priori 148 SM x 64 lanes/clk x 1.965 GHz (microbenchmark file missing)"
+
+
+def ncu_traffic(kernel_key: str):
+    p = os.path.join(ROOT, "profiles", "ncu_summary_r01.json")
+    try:
+        with open(p) as f:
+            return json.load(f)[kernel_key]["dram_bytes_per_launch"]
+    except Exception:
+        return None
+
+
+def cpu_baseline_run(batch, n_sample: int, threads: int):
+    """The reference's own kernels compiled for the host (kind 'reference'), else our C port (kind 'port')."""
+    from oracle import pyoracle as po
+    sub = batch.slice(0, min(n_sample, batch.n))
+    orc = po.Oracle()
+    pq, pt = orc.pack(sub.q_bytes), orc.pack(sub.t_bytes)
+    if po.RefHost.available(1024):
+        eng, kind = po.RefHost(1024), "reference"
+    else:
+        eng, kind = orc, "port"
+    t0 = time.perf_counter()
+    for algo in (po.LOCAL, po.SEMI_GLOBAL):
+        kw = dict(algo=algo, start=po.WITH_START, scoring=SCORING, n_threads=threads)
+        if kind == "port":
+            kw["max_query_len"] = 1024
+        eng.align(pq, pt, sub.q_lens, sub.t_lens, sub.q_offs, sub.t_offs, **kw)
+    dt = time.perf_counter() - t0
+    return 2 * sub.cells / dt / 1e9, kind, sub.n, dt
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    n_sample = args.ref_pairs
+    batch = make_workload(n_sample, seed=2)
+    for _ in range(args.warmup):
+        cpu_baseline_run(batch, max(n_sample // 10, 1000), threads)
+    t_total, cells = 0.0, 0
+    kind = "port"
+    for _ in range(args.steps):
+        g, kind, n, dt = cpu_baseline_run(batch, n_sample, threads)
+        t_total += dt; cells += 2 * batch.slice(0, n).cells
+    value = cells / t_total / 1e9
+    line = {"metric": "GCUPS", "impl": "reference", "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
+            "data": "synthetic",
+            "config": {"workload": "C2: local + semi-global WITH_START, 150x600 bp pairs", "pairs_per_step": n_sample, "scoring": list(SCORING)},
+            "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": kind,
+                             "sample": f"{n_sample} pairs of the C2 workload per step, both modes, reference kernels compiled for the host (OpenMP)"},
+            "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "pairs_per_s": 2 * n_sample * args.steps / t_total}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    from genomics_gpu_b200 import capi
+    from genomics_gpu_b200.aligner import Aligner
+
+    lib = capi.load()
+    lib.gasal_set_device(local_rank, 0)
+    n = args.pairs
+    batch = make_workload(n, seed=2 + rank)
+    cells_mode = batch.cells
+    q_bytes, t_bytes = int(batch.q_bytes.size), int(batch.t_bytes.size)
+
+    modes = [("local", capi.LOCAL), ("semi_global", capi.SEMI_GLOBAL)]
+    # ---- device-resident arm: one storage per mode holding the whole batch --------------------------------
+    res_al = {}
+    for name, algo in modes:
+        al = Aligner(algo=algo, start=capi.WITH_START, scoring=SCORING, max_query_len=QLEN + 7, max_target_len=TLEN + 7, max_n_alns=n,
+                     n_streams=1, device=local_rank)
+        al.fill(0, batch)
+        al.launch(0, q_bytes, t_bytes, n)      # uploads the inputs once; afterwards they are resident in HBM
+        al.wait(0)
+        res_al[name] = al
+
+    def resident_step():
+        out = {}
+        for name, _ in modes:
+            al = res_al[name]
+            s = al.vec.a[0]
+            s.current_n_alns = n
+            lib.gasalx_aln_device_resident(C.byref(s), q_bytes, t_bytes, n, C.byref(al.params))
+            al.wait(0)
+            out[name] = al.last_ms(0)
+        return out
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        resident_step()
+    launches0 = sum(al.launches(0) for al in res_al.values())
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    t0 = time.perf_counter()
+    per_mode = {name: [] for name, _ in modes}
+    for _ in range(args.steps):
+        r = resident_step()
+        for k, v in r.items():
+            per_mode[k].append(v)
+    barrier()
+    wall_ms = 1e3 * (time.perf_counter() - t0)
+    clocks = sampler.stop()
+    launches = sum(al.launches(0) for al in res_al.values()) - launches0
+    dev_ms = sum(v[0] for vs in per_mode.values() for v in vs)            # CUDA-event time, whole device pipeline
+    kernel_names = {name: res_al[name].kernel_name(0) for name, _ in modes}
+    for al in res_al.values():
+        al.close()
+
+    # ---- e2e arm: host buffers; the batch is split into chunks, one storage (pinned pages + stream) per chunk ----
+    # The pinned host pages are filled ONCE (gasal_host_batch_add); every step re-submits them with
+    # gasal_aln_async, i.e. the timed region holds the pinned H2D of all sequences + lens/offsets, the kernels,
+    # and the D2H of the results, pipelined over the storages' streams as a GASAL2 caller would.
+    n_chunks = args.e2e_chunks
+    chunk = (n + n_chunks - 1) // n_chunks
+    subs = [batch.slice(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
+    e2e_al = {}
+    for name, algo in modes:
+        al = Aligner(algo=algo, start=capi.WITH_START, scoring=SCORING, max_query_len=QLEN + 7, max_target_len=TLEN + 7, max_n_alns=chunk,
+                     n_streams=len(subs), device=local_rank)
+        for si, sub in enumerate(subs):
+            al.fill(si, sub)
+        e2e_al[name] = al
+    checksum = np.zeros(1, dtype=np.int64)
+
+    def e2e_step():
+        for name, _ in modes:
+            al = e2e_al[name]
+            for si, sub in enumerate(subs):
+                s = al.vec.a[si]
+                lib.gasalx_host_batch_rearm(C.byref(s), int(sub.q_bytes.size), int(sub.t_bytes.size), sub.n)
+                al.launch(si, int(sub.q_bytes.size), int(sub.t_bytes.size), sub.n)
+            for si, sub in enumerate(subs):
+                al.wait(si)
+                r = al.results(si, sub.n)          # host_res arrays (D2H already done on the stream)
+                checksum[0] += int(r["aln_score"].sum())
+
+    for _ in range(max(1, args.warmup // 2)):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = args.steps
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_wall = time.perf_counter() - t0
+    for al in e2e_al.values():
+        al.close()
+
+    # ---- reductions over ranks: time = max, work = sum -------------------------------------------------------
+    t = torch.tensor([dev_ms, wall_ms, 1e3 * e2e_wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms_max, wall_ms_max, e2e_ms_max = [float(x) for x in t.tolist()]
+    total_cells_per_step = 2 * cells_mode * world            # weak scaling: every rank has its own n pairs
+    value = total_cells_per_step * args.steps / (dev_ms_max * 1e-3) / 1e9
+    e2e_value = total_cells_per_step * e2e_steps / (e2e_ms_max * 1e-3) / 1e9
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant DP kernel (by time in the step) ---------------------------------------------
+    R, R_src = dpx_peak_ops_per_s()
+    dp_ms = {name: statistics.mean(v[2] for v in per_mode[name]) for name, _ in modes}
+    pack_ms = {name: statistics.mean(v[1] for v in per_mode[name]) for name, _ in modes}
+    top = max(dp_ms, key=dp_ms.get)
+    ops_per_cell = 3.0 if kernel_names[top] == "s16x2" else 6.0
+    peak_gcups = R / ops_per_cell / 1e9
+    achieved = cells_mode / (dp_ms[top] * 1e-3) / 1e9
+    hbm_peak = None
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm_peak = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        hbm_peak = 6650.0
+    pack_bytes = 1.5 * (q_bytes + t_bytes)
+    pack_gbs = pack_bytes / (statistics.mean(pack_ms.values()) * 1e-3) / 1e9
+
+    cpu_threads = os.cpu_count() or 1
+    cpu_val, cpu_kind, cpu_n, cpu_dt = cpu_baseline_run(batch, args.cpu_pairs, cpu_threads)
+
+    line = {
+        "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "s16x2/int32 (DPX integer)", "data": "synthetic",
+        "config": {"workload": "C2: GASAL2 local + semi-global, WITH_START, 150x600 bp synthetic pairs", "pairs_per_gpu": n,
+                   "modes_per_step": ["local WITH_START", "semi_global TARGET/TARGET WITH_START"], "scoring": list(SCORING),
+                   "l2_policy": "inputs larger than L2 (752 MB unpacked + 376 MB packed per mode)",
+                   "kernels": kernel_names, "timing": "CUDA events on each storage's stream, summed over the step's batches"},
+        "pairs_per_s": 2 * n * world * args.steps / (dev_ms_max * 1e-3),
+        "wall_ms_per_step": wall_ms_max / args.steps,
+        "per_mode": {name: {"pipeline_ms": statistics.mean(v[0] for v in per_mode[name]), "pack_ms": pack_ms[name], "dp_ms": dp_ms[name],
+                            "gcups_dp_only": cells_mode / (dp_ms[name] * 1e-3) / 1e9} for name, _ in modes},
+        "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": 2 * (q_bytes + t_bytes + 16 * n), "d2h_bytes_per_step": 2 * 20 * n,
+                "chunks_per_mode": len(subs), "streams_per_mode": len(subs), "score_checksum": int(checksum[0]), "timing": "wall clock bracketed by barrier + cuda synchronize",
+                "pairs_per_s": 2 * n * world * e2e_steps / (e2e_ms_max * 1e-3)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "dpx-integer-pipe", "kernel": f"{top} DP ({kernel_names[top]})", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
+                     "frac": achieved / peak_gcups, "traffic": ncu_traffic(top),
+                     "peak_def": f"R / {ops_per_cell:g} ops per cell, R = {R:.4g} lane-ops/s, {R_src}",
+                     "note": "compute-bound integer DP (SURVEY 8d): compulsory HBM traffic is < 0.01 B/cell; the HBM-bound stage is pack, below"},
+        "roofline_pack": {"bound": "hbm", "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pack_gbs / hbm_peak,
+                          "traffic": ncu_traffic("pack"), "bytes_def": "1.5 B per base (1 read + 0.5 written)"},
+        "cpu_baseline": {"value": cpu_val, "unit": "GCUPS", "cores": cpu_threads, "kind": cpu_kind,
+                         "sample": f"first {cpu_n} pairs of the same workload, both modes, {cpu_dt:.1f} s"},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per mode")
+    ap.add_argument("--e2e-chunks", type=int, default=8)
+    ap.add_argument("--cpu-pairs", type=int, default=60_000, help="bounded sample for the cpu_baseline leg")
+    ap.add_argument("--ref-pairs", type=int, default=60_000, help="pairs per step of the --impl reference arm")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

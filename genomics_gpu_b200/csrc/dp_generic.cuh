@@ -405,16 +405,14 @@ __global__ void __launch_bounds__(128) k_local_generic(const DpArgs a) {
   }
 }
 
+// one pair, forward (+ start pass); `pi` indexes the result arrays
 template <int START, bool SECOND>
-__global__ void __launch_bounds__(128) k_semiglobal_generic(const DpArgs a) {
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  PairCtx p; if (!make_ctx(a, tid, p)) return;
-  const Sc sc = make_sc(a, false);
+__device__ __forceinline__ void semiglobal_pair(const DpArgs& a, const Sc& sc, const PairCtx& p, uint32_t pi) {
   SgTrack tr; tr.best = kMinusInf; tr.x = (int)p.tlen; tr.y = (int)p.qlen;              // :63-64
   tr.best2 = kMinusInf; tr.x2 = (int)p.tlen; tr.y2 = (int)p.qlen;
   semiglobal_pass<false, SECOND>(a, sc, p, 0, 0, tr);
-  a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = tr.x;
-  if (SECOND) { a.score2[tid] = tr.best2; a.t_end2[tid] = tr.y2; a.q_end2[tid] = tr.x2; }
+  a.score[pi] = tr.best; a.t_end[pi] = tr.y; a.q_end[pi] = tr.x;
+  if (SECOND) { a.score2[pi] = tr.best2; a.t_end2[pi] = tr.y2; a.q_end2[pi] = tr.x2; }
   if (START == START_POS) {
     const int fwd = tr.best;
     // :273 -- unsigned arithmetic in the reference: a wrapped value makes the strip loop a no-op
@@ -422,9 +420,17 @@ __global__ void __launch_bounds__(128) k_semiglobal_generic(const DpArgs a) {
     const uint32_t gend_reg = ua > 0 ? ua - 1 : ua;
     tr.best = kMinusInf; tr.y = 0;                                                      // :275-276
     semiglobal_pass<true, false>(a, sc, p, gend_reg, fwd, tr);
-    a.t_start[tid] = ((int)p.tlen - 1) - tr.y;                                          // :380-381
-    a.q_start[tid] = ((int)p.qlen - 1) - tr.x;
+    a.t_start[pi] = ((int)p.tlen - 1) - tr.y;                                           // :380-381
+    a.q_start[pi] = ((int)p.qlen - 1) - tr.x;
   }
+}
+
+template <int START, bool SECOND>
+__global__ void __launch_bounds__(128) k_semiglobal_generic(const DpArgs a) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  PairCtx p; if (!make_ctx(a, tid, p)) return;
+  const Sc sc = make_sc(a, false);
+  semiglobal_pair<START, SECOND>(a, sc, p, tid);
 }
 
 template <int START>

@@ -259,23 +259,264 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   }
 }
 
-// ---- general kernel over the fallback worklist ----------------------------------------------------
+// =====================================================================================================
+// Semi-global (H-based opening, reference semiglobal_kernel_template.h:17-28) and global (D-based,
+// no clamp, global.h:4-12) in the same two-lane skewed layout.  These recurrences have no zero clamp,
+// so (a) the lane that starts one column late (lane H) gets its strip-start state re-imposed after the
+// phantom step 0, and (b) "minus infinity" is a finite floor that a single `- gap_extend` cannot wrap
+// in 16 bits; eligibility (fast_path_eligible) proves every real value stays far above it.
+constexpr int kNegSafe = -16384;
+
+__device__ __forceinline__ int lane_lo(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+__device__ __forceinline__ int lane_hi(uint32_t v) { return (int)(short)(v >> 16); }
+__device__ __forceinline__ uint32_t pack2(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+
+struct NcTrack {
+  int best, y;          // semi-global: running (maxHH, maxXY_y)
+  int stop;             // reverse pass: stop once best >= stop
+  int cap;              // global: captured H(tlen-1, qlen-1)
+};
+
+template <int ALGO, bool REV>
+__device__ __forceinline__ void nc_sweep(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
+                                         const uint32_t (&rowA)[8], const uint32_t (&rowB)[8], const uint32_t (&pinit)[8],
+                                         uint32_t neg_oe2, uint32_t neg_ext2,
+                                         int kscanL, int kscanH, int rowbaseL, int rowbaseH, int tlen, int caprow, NcTrack& tr) {
+  constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
+  const uint32_t neg2 = splat16(kNegSafe);
+  uint32_t p[8], f[8], gl[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { p[r] = pinit[r]; f[r] = neg2; gl[r] = neg_oe2; }   // left column: H = 0 (semi), F = -inf
+  uint32_t h8 = 0, eo = 0;
+  uint32_t prevsh = 0xCC00u;
+  uint32_t he = HE[kFastThreads];
+  uint32_t v = V[kFastThreads];
+  for (int k = 0; k < nsteps; k++) {
+    const uint32_t sel = v | prevsh;
+    prevsh = v * 256u + 0x4400u;
+    uint32_t up = prmt(he, h8, 0x5410);
+    uint32_t e = prmt(he, eo, 0x5432);
+    he = HE[(k + 2) * kFastThreads];
+    v = V[(k + 2) * kFastThreads];
+    uint32_t hh[8];
+    uint32_t gu = __vadd2(up, neg_oe2);
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const uint32_t s2 = prmt(rowA[r], rowB[r], sel);
+      const uint32_t d = __vadd2(p[r], s2);
+      uint32_t h;
+      if (SEMI) {
+        f[r] = __viaddmax_s16x2(f[r], neg_ext2, gl[r]);        // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
+        e = __viaddmax_s16x2(e, neg_ext2, gu);                 // E(t,q) = max(H(t-1,q) - oe, E(t-1,q) - e)
+        h = __vimax3_s16x2(d, f[r], e);
+        gu = __vadd2(h, neg_oe2);
+        gl[r] = gu;
+      } else {
+        const uint32_t dm = __vadd2(d, neg_oe2);
+        h = __vimax3_s16x2(d, f[r], e);
+        f[r] = __viaddmax_s16x2(f[r], neg_ext2, dm);
+        e = __viaddmax_s16x2(e, neg_ext2, dm);
+      }
+      hh[r] = h;
+      p[r] = up; up = h;
+    }
+    HE[k * kFastThreads] = prmt(up, e, 0x7632);
+    h8 = up; eo = e;
+    if (k == 0) {
+      // lane H just ran its phantom column -1: restore its strip-start state
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        p[r] = prmt(p[r], pinit[r], 0x7610);
+        f[r] = prmt(f[r], neg2, 0x7610);
+        if (SEMI) gl[r] = prmt(gl[r], neg_oe2, 0x7610);
+      }
+    }
+    if (SEMI) {
+      // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178)
+      if (k == kscanL) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) { const int hv = lane_lo(hh[r]); if (rowbaseL + r < tlen && hv > tr.best) { tr.best = hv; tr.y = rowbaseL + r; } }
+      }
+      if (k == kscanH && (!REV || tr.best < tr.stop)) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) { const int hv = lane_hi(hh[r]); if (rowbaseH + r < tlen && hv > tr.best) { tr.best = hv; tr.y = rowbaseH + r; } }
+      }
+    } else {
+      if (k == kscanL) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) if (r == caprow) tr.cap = lane_lo(hh[r]);
+      }
+      if (k == kscanH) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) if (r == caprow) tr.cap = lane_hi(hh[r]);
+      }
+    }
+  }
+}
+
+// selector bytes + top boundary of one pass into shared memory.  mode 0: forward words; mode 2: true-length reversed.
+template <bool TOP_ZERO>
+__device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint32_t* qw, uint32_t qlen, int QR, int mode, int o, int ext) {
+  bool odd = false;
+  const int ncol = QR * 8;
+  V[0] = 0x88; HE[0] = pack2(0, kNegSafe);
+  for (int j = 0; j < QR; j++) {
+    const uint32_t w = (mode == 2) ? rev_true_word(qw, (int)qlen, j) : qw[j];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = 8 * j + k;
+      const uint32_t idx = base_idx(nib(w, k));
+      odd |= (idx > 3) && ((uint32_t)c < qlen);
+      V[(c + 1) * kFastThreads] = (idx > 3) ? 0x88 : (uint8_t)(0x80u + 0x11u * idx);
+      // top boundary: H(-1, c), E = -inf   (semiglobal_kernel_template.h:87-99, global.h:57-60)
+      HE[(c + 1) * kFastThreads] = TOP_ZERO ? 0u : pack2(c == 0 ? 0 : -(o + ext * c), kNegSafe);   // free top row: (H,E) = (0,0)
+    }
+  }
+  V[(ncol + 1) * kFastThreads] = 0x88; HE[(ncol + 1) * kFastThreads] = pack2(0, kNegSafe);
+  V[(ncol + 2) * kFastThreads] = 0x88; HE[(ncol + 2) * kFastThreads] = pack2(0, kNegSafe);
+  return odd;
+}
+
+__device__ __forceinline__ bool target_has_odd_base(const uint32_t* tw, uint32_t tlen, int TR) {
+  bool odd = false;
+  for (int i = 0; i < TR && !odd; i++) {
+    const uint32_t w = tw[i];
+#pragma unroll
+    for (int k = 0; k < 8; k++) odd |= (base_idx(nib(w, k)) > 3) && ((uint32_t)(8 * i + k) < tlen);
+  }
+  return odd;
+}
+
 template <int START>
-__global__ void __launch_bounds__(128) k_local_worklist(const FastArgs fa) {
+__global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs fa) {
+  extern __shared__ uint32_t smem[];
+  const DpArgs& a = fa.a;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (uint32_t)a.n) return;
+  uint32_t* HE = smem + threadIdx.x;
+  uint8_t* V = (uint8_t*)(smem + (fa.q8max + 3) * kFastThreads) + threadIdx.x;
+  const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
+  const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
+  const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
+  const int QR = (int)n_words(qlen), TR = (int)n_words(tlen);
+  const uint32_t mis4 = ((uint32_t)(-a.mismatch) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
+  const int oe = a.gap_open + a.gap_extend;
+  const uint32_t neg_oe2 = splat16(-oe), neg_ext2 = splat16(-a.gap_extend);
+  const bool top_zero = (a.head == SKIP_BOTH);          // HEAD in {QUERY,BOTH}: free top row (:87)
+  const int ncol = QR * 8, nsteps = ncol + (int)fa.one;
+
+  bool odd = top_zero ? nc_prologue<true>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend)
+                      : nc_prologue<false>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend);
+  odd |= target_has_odd_base(tw, tlen, TR);
+  if (odd || qlen == 0) {
+    const uint32_t slot = atomicAdd(fa.work_count, 1u);
+    fa.worklist[slot] = tid;
+    return;
+  }
+  uint32_t pinit[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) pinit[r] = 0;             // HEAD in {TARGET,BOTH}: free left column, diag = 0 (:114-121)
+
+  NcTrack tr; tr.best = kMinusInf; tr.y = (int)qlen; tr.stop = 0; tr.cap = 0;       // :63-64
+  const int ND = (TR + 1) >> 1;
+  for (int j = 0; j < ND; j++) {
+    uint32_t rowA[8], rowB[8];
+    const uint32_t wa = tw[2 * j];
+    const uint32_t wb = (2 * j + 1 < TR) ? tw[2 * j + 1] : 0u;
+#pragma unroll
+    for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
+    nc_sweep<ALGO_SEMI_GLOBAL, false>(HE, V, nsteps, rowA, rowB, pinit, neg_oe2, neg_ext2, (int)qlen - 1, (int)qlen, 16 * j, 16 * j + 8, (int)tlen, 0, tr);
+  }
+  a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = (int)tlen;            // query_batch_end = ref_len (Q8)
+
+  if (START == START_POS) {
+    // start pass (:227-384): the same DP over the TRUE-LENGTH reversed sequences, from the strip that holds the
+    // end row, until the running best reaches the forward score
+    const int fwd = tr.best;
+    const uint32_t ua = (uint32_t)TR - (uint32_t)((tr.y >> 3) + 1);
+    const uint32_t gend_reg = ua > 0 ? ua - 1 : ua;                                   // :273 (unsigned in the reference)
+    if (top_zero) nc_prologue<true>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend);
+    else nc_prologue<false>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend);
+    NcTrack rt; rt.best = kMinusInf; rt.y = 0; rt.stop = fwd; rt.cap = 0;             // :275-276
+    for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 2) {
+      uint32_t rowA[8], rowB[8];
+      const uint32_t wa = rev_true_word(tw, (int)tlen, (int)i);
+      const uint32_t wb = (i + 1 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 1) : 0u;
+#pragma unroll
+      for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
+      nc_sweep<ALGO_SEMI_GLOBAL, true>(HE, V, nsteps, rowA, rowB, pinit, neg_oe2, neg_ext2, (int)qlen - 1, (int)qlen, 8 * (int)i, 8 * (int)i + 8, (int)tlen, 0, rt);
+    }
+    a.t_start[tid] = ((int)tlen - 1) - rt.y;                                          // :380-381
+    a.q_start[tid] = ((int)qlen - 1) - (int)tlen;
+  }
+}
+
+__global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) {
+  extern __shared__ uint32_t smem[];
+  const DpArgs& a = fa.a;
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (uint32_t)a.n) return;
+  uint32_t* HE = smem + threadIdx.x;
+  uint8_t* V = (uint8_t*)(smem + (fa.q8max + 3) * kFastThreads) + threadIdx.x;
+  const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
+  const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
+  const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
+  const int QR = (int)n_words(qlen), TR = (int)n_words(tlen);
+  const uint32_t mis4 = ((uint32_t)(-a.mismatch) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
+  const int o = a.gap_open, ext = a.gap_extend;
+  const uint32_t neg_oe2 = splat16(-(o + ext)), neg_ext2 = splat16(-ext);
+  const int ncol = QR * 8, nsteps = ncol + (int)fa.one;
+  bool odd = nc_prologue<false>(HE, V, qw, qlen, QR, 0, o, ext);
+  odd |= target_has_odd_base(tw, tlen, TR);
+  if (odd || qlen == 0 || tlen == 0) {
+    const uint32_t slot = atomicAdd(fa.work_count, 1u);
+    fa.worklist[slot] = tid;
+    return;
+  }
+  NcTrack tr; tr.best = 0; tr.y = 0; tr.stop = 0; tr.cap = 0;
+  const int ND = (TR + 1) >> 1;
+  const int last_strip = (int)(tlen - 1) >> 3, caprow = (int)(tlen - 1) & 7;
+  for (int j = 0; j < ND; j++) {
+    uint32_t rowA[8], rowB[8], pinit[8];
+    const uint32_t wa = tw[2 * j];
+    const uint32_t wb = (2 * j + 1 < TR) ? tw[2 * j + 1] : 0u;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
+      const int tL = 16 * j + r, tH = 16 * j + 8 + r;                               // diag(t) = t ? -(o + e*t) : 0   (global.h:66-70)
+      pinit[r] = pack2(tL == 0 ? 0 : -(o + ext * tL), -(o + ext * tH));
+    }
+    const int kL = (2 * j == last_strip) ? (int)qlen - 1 : -1, kH = (2 * j + 1 == last_strip) ? (int)qlen : -1;
+    nc_sweep<ALGO_GLOBAL, false>(HE, V, nsteps, rowA, rowB, pinit, neg_oe2, neg_ext2, kL, kH, 0, 0, (int)tlen, caprow, tr);
+  }
+  a.score[tid] = tr.cap;                                                              // H(ref_len-1, read_len-1)  (global.h:285-299)
+}
+
+// ---- general kernel over the fallback worklist ----------------------------------------------------
+template <int ALGO, int START>
+__global__ void __launch_bounds__(128) k_worklist(const FastArgs fa) {
   const DpArgs& a = fa.a;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
   const uint32_t count = *fa.work_count;
-  const Sc sc = make_sc(a, false);
+  const Sc sc = make_sc(a, ALGO == ALGO_GLOBAL);
   for (uint32_t w = gtid; w < count; w += nthreads) {
     const uint32_t pi = fa.worklist[w];
     PairCtx p;
     p.qw = a.pq + (a.q_offs[pi] >> 3); p.tw = a.pt + (a.t_offs[pi] >> 3);
     p.qlen = a.q_lens[pi]; p.tlen = a.t_lens[pi]; p.QR = n_words(p.qlen); p.TR = n_words(p.tlen);
     p.cs = a.colstate + gtid; p.stride = a.col_stride;
-    int best, bq, bt;
-    local_forward<false, false>(a, sc, p, pi, best, bq, bt);
-    a.score[pi] = best; a.q_end[pi] = bq; a.t_end[pi] = bt;
-    if (START == START_POS) { int sx, sy; local_reverse(sc, p, best, bq, bt, sx, sy); a.q_start[pi] = sx; a.t_start[pi] = sy; }
+    if (ALGO == ALGO_LOCAL) {
+      int best, bq, bt;
+      local_forward<false, false>(a, sc, p, pi, best, bq, bt);
+      a.score[pi] = best; a.q_end[pi] = bq; a.t_end[pi] = bt;
+      if (START == START_POS) { int sx, sy; local_reverse(sc, p, best, bq, bt, sx, sy); a.q_start[pi] = sx; a.t_start[pi] = sy; }
+    } else if (ALGO == ALGO_SEMI_GLOBAL) {
+      semiglobal_pair<START, false>(a, sc, p, pi);
+    } else {
+      a.score[pi] = global_forward<false>(a, sc, p, pi);
+    }
   }
 }
 
@@ -283,19 +524,33 @@ __global__ void k_zero_u32(uint32_t* p) { *p = 0; }
 
 // ---- host side --------------------------------------------------------------------------------------
 inline bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
-  if (algo != ALGO_LOCAL || second || start == START_TB) return false;
+  if (second || start == START_TB) return false;
   const uint32_t q8 = (max_q + 7u) & ~7u, t8 = (max_t + 7u) & ~7u;
-  if (q8 == 0 || q8 > kFastMaxQ8) return false;
+  if (q8 == 0 || q8 > kFastMaxQ8 || t8 == 0) return false;
   if (a.match < 0 || a.match > 127 || a.mismatch < 0 || a.mismatch > 127) return false;
   if (a.gap_open < 0 || a.gap_extend < 0 || a.gap_open + a.gap_extend > 2000) return false;
-  // keys are score*8+7 in a signed 16-bit lane; E/F stay above -(mismatch + gap_open + gap_extend)
-  const uint64_t max_score = (uint64_t)std::min(q8, t8) * (uint64_t)a.match;
-  if (max_score > 4000) return false;
-  return true;
+  const int64_t oe = (int64_t)a.gap_open + a.gap_extend;
+  if (algo == ALGO_LOCAL) {
+    // keys are score*8+7 in a signed 16-bit lane; E/F stay above -(mismatch + gap_open + gap_extend)
+    return (uint64_t)std::min(q8, t8) * (uint64_t)a.match <= 4000;
+  }
+  if (algo == ALGO_SEMI_GLOBAL) {
+    // default read-vs-window shape only (free target head/tail); the other 14 head/tail variants use the general kernel
+    if (a.tail != SKIP_TARGET || !(a.head == SKIP_TARGET || a.head == SKIP_BOTH)) return false;
+    // every H/E/F is >= -(2*oe + ext*(q8+2) + mismatch) and <= q8*match: keep both well inside (kNegSafe, 32767)
+    if (2 * oe + (int64_t)a.gap_extend * (q8 + 2) + a.mismatch + 64 > 12000) return false;
+    return (int64_t)q8 * a.match <= 30000;
+  }
+  if (algo == ALGO_GLOBAL) {
+    if (start != START_NONE) return false;
+    if (2 * oe + (int64_t)a.gap_extend * (q8 + t8 + 2) + a.mismatch + 64 > 12000) return false;
+    return (int64_t)std::min(q8, t8) * a.match <= 30000;
+  }
+  return false;
 }
 
 inline int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, cudaStream_t str) {
-  (void)algo; (void)max_t;
+  (void)max_t;
   const uint32_t q8 = (max_q + 7u) & ~7u;
   if (fs.cap < (size_t)a.n) {
     if (fs.worklist) cudaFree(fs.worklist);
@@ -314,18 +569,26 @@ inline int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& f
   FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.work_count = fs.work_count; fa.eight = 8; fa.one = 1;
   const size_t smem = (size_t)(q8 + 3) * kFastThreads * 4 + (size_t)(q8 + 3) * kFastThreads;
   if (!fs.attr_set) {
-    cudaFuncSetAttribute(k_local_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    cudaFuncSetAttribute(k_local_s16<START_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+    const int lim = 227 * 1024;
+    cudaFuncSetAttribute(k_local_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_global_s16, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     fs.attr_set = true;
   }
   k_zero_u32<<<1, 1, 0, str>>>(fs.work_count);
   const uint32_t blocks = ((uint32_t)a.n + kFastThreads - 1) / kFastThreads;
-  if (start == START_POS) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa);
-  else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
+  const bool sp = (start == START_POS);
+  if (algo == ALGO_LOCAL) { if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
+  else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
+  else k_global_s16<<<blocks, kFastThreads, smem, str>>>(fa);
   // fallback pairs (bases outside A/C/G/T): general kernel over the worklist, bounded scratch
   fa.a.colstate = fs.colstate; fa.a.col_stride = kFastFallbackSlots; fa.a.col_rows = q8;
-  if (start == START_POS) k_local_worklist<START_POS><<<kFastFallbackSlots / 128, 128, 0, str>>>(fa);
-  else k_local_worklist<START_NONE><<<kFastFallbackSlots / 128, 128, 0, str>>>(fa);
+  const int wb = kFastFallbackSlots / 128;
+  if (algo == ALGO_LOCAL) { if (sp) k_worklist<ALGO_LOCAL, START_POS><<<wb, 128, 0, str>>>(fa); else k_worklist<ALGO_LOCAL, START_NONE><<<wb, 128, 0, str>>>(fa); }
+  else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_worklist<ALGO_SEMI_GLOBAL, START_POS><<<wb, 128, 0, str>>>(fa); else k_worklist<ALGO_SEMI_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa); }
+  else k_worklist<ALGO_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa);
   return 3;
 }
 

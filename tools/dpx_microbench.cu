@@ -68,7 +68,7 @@ __global__ void __launch_bounds__(256) k_bench(uint32_t* out, const uint32_t* in
   if (threadIdx.x == 0) { cyc[2 * blockIdx.x] = t0; cyc[2 * blockIdx.x + 1] = t1; }
 }
 
-struct Result { std::string name; double ops_per_clk_sm; double ms; double ghz; };
+struct Result { std::string name; double ops_per_clk_sm; double ms; double ghz; double lane_ops_per_s; int nops; };
 
 static const char* opname(int op) {
   switch (op) {
@@ -86,7 +86,7 @@ template <int OP1, int OP2, int ILP>
 Result run(int n_sm, uint32_t* d_out, uint32_t* d_in, long long* d_cyc) {
   const int blocks_per_sm = 4, threads = 256;
   const int grid = n_sm * blocks_per_sm;
-  const int iters = 4096;
+  const int iters = 131072;   // ~35 ms per kernel: long enough for the SM clock to settle
   k_bench<OP1, OP2, ILP><<<grid, threads>>>(d_out, d_in, 64, d_cyc);  // warm-up
   CK(cudaDeviceSynchronize());
   cudaEvent_t e0, e1; CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -108,6 +108,8 @@ Result run(int n_sm, uint32_t* d_out, uint32_t* d_in, long long* d_cyc) {
   r.ops_per_clk_sm = warp_instr_per_sm * 32.0 / avg_cyc;   // lane-ops per clock per SM
   r.ms = ms;
   r.ghz = avg_cyc / (ms * 1e6);
+  r.lane_ops_per_s = warp_instr_per_sm * 32.0 * n_sm / (ms * 1e-3);   // wall-clock (CUDA events): the roofline number
+  r.nops = nops;
   return r;
 }
 
@@ -131,10 +133,18 @@ int main() {
   RUN2(OP_VIADDMNMX_S16X2, OP_IMAD); RUN2(OP_VIADDMNMX_S16X2, OP_LOP3); RUN2(OP_VIADDMNMX_S16X2, OP_HSET2);
   RUN2(OP_VIADDMNMX_S16X2, OP_PRMT); RUN2(OP_VIADDMNMX_S16X2, OP_HADD2); RUN2(OP_VIADD_16X2, OP_IMAD); RUN2(OP_VIADD_16X2, OP_LOP3);
   RUN2(OP_HSET2, OP_IMAD); RUN2(OP_HSET2, OP_LOP3); RUN2(OP_IMAD, OP_LOP3); RUN2(OP_VIMNMX3_S32, OP_IMAD);
-  printf("{\"gpu\": \"%s\", \"n_sm\": %d, \"clock_rate_khz\": %d, \"results\": [\n", prop.name, n_sm, prop.clockRate);
+  double R_alu = 0, R_fma = 0, R_dual = 0;
+  for (auto& r : res) {
+    if (r.nops == 1 && (r.name.find("VIADDMNMX.S16x2") == 0 || r.name.find("VIMNMX3.S16x2") == 0)) R_alu = std::max(R_alu, r.lane_ops_per_s);
+    if (r.nops == 1 && (r.name == "VIADD.16x2" || r.name == "IMAD")) R_fma = std::max(R_fma, r.lane_ops_per_s);
+    if (r.name == "VIADDMNMX.S16x2+VIADD.16x2") R_dual = r.lane_ops_per_s;
+  }
+  printf("{\"gpu\": \"%s\", \"n_sm\": %d, \"clock_rate_khz\": %d,\n", prop.name, n_sm, prop.clockRate);
+  printf(" \"R_alu_lane_ops_per_s\": %.6g, \"R_fma_lane_ops_per_s\": %.6g, \"R_alu_plus_fma_lane_ops_per_s\": %.6g,\n", R_alu, R_fma, R_dual);
+  printf(" \"note\": \"lane_ops_per_s = warp instructions x 32 / CUDA-event time over all SMs (1024 threads/SM, ILP 8 or 6+6); R_alu is the DPX/ALU-pipe peak used as the GCUPS roofline denominator; the clk-based column divides by clock64() deltas and is informational only\",\n \"results\": [\n");
   for (size_t i = 0; i < res.size(); i++)
-    printf("  {\"op\": \"%s\", \"lane_ops_per_clk_per_sm\": %.2f, \"ms\": %.4f, \"sm_ghz\": %.4f}%s\n", res[i].name.c_str(),
-           res[i].ops_per_clk_sm, res[i].ms, res[i].ghz, i + 1 < res.size() ? "," : "");
+    printf("  {\"op\": \"%s\", \"lane_ops_per_s\": %.5g, \"ms\": %.3f, \"lane_ops_per_clk_per_sm_by_clock64\": %.2f}%s\n", res[i].name.c_str(),
+           res[i].lane_ops_per_s, res[i].ms, res[i].ops_per_clk_sm, i + 1 < res.size() ? "," : "");
   printf("]}\n");
   return 0;
 }
