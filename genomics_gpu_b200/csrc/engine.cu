@@ -38,6 +38,7 @@ gasal_subst_scores g_scores = {1, 4, 6, 1};
 int g_n_code = 0x4E;
 int g_n_penalty = -1;
 int g_kernel_policy = 0;
+int g_revcomp_mode = 0;
 
 struct Priv {
   uint32_t* colstate = nullptr; size_t colstate_words = 0;
@@ -88,6 +89,7 @@ void gasal_params_default(gasal_params_t* p) {   // src/args_parser.cpp:12-29
 
 void gasalx_set_n_code(int n_code, int n_penalty) { g_n_code = n_code; g_n_penalty = n_penalty; }
 void gasalx_set_kernel_policy(int policy) { g_kernel_policy = policy; }
+void gasalx_set_revcomp_mode(int mode) { g_revcomp_mode = mode; }
 
 void gasal_copy_subst_scores(gasal_subst_scores* subst) { g_scores = *subst; }   // src/gasal_align.cu:329-339
 
@@ -596,7 +598,7 @@ static void device_stage(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_by
   if (params->isReverseComplement) {                                                    // :232-246
     const uint32_t warps = 2 * n, blocks = (warps * 32 + 255) / 256;
     k_revcomp<<<blocks, 256, 0, s->str>>>(s->packed_query_batch, s->packed_target_batch, s->query_batch_lens, s->target_batch_lens,
-                                          s->query_batch_offsets, s->target_batch_offsets, s->query_op, s->target_op, n);
+                                          s->query_batch_offsets, s->target_batch_offsets, s->query_op, s->target_op, n, g_revcomp_mode);
     CHECK_LAUNCH(); pv->launches++;
   }
   CHECKCUDAERROR(cudaEventRecord(pv->ev[1], s->str));

@@ -37,8 +37,9 @@ __global__ void k_pack_tail(const uint2* __restrict__ in8, uint32_t* __restrict_
 }
 
 // ---- K1b: reverse / complement ------------------------------------------------------------------
-// Same observable behaviour as the reference kernel ON THE GPU: op bit0 reverses the
-// nibbles of the pair's whole padded word array, op bit1 complements A<->T (1<->4), C<->G (3<->7).
+// op bit0 reverses, op bit1 complements A<->T (1<->4), C<->G (3<->7).  The reference's reverse branch has
+// undefined behaviour (32-bit shifts by 32): mode 0 = clean nibble reversal of the pair's whole padded word
+// array (PTX shift semantics, the default), mode 1 = what its nvcc 12.9 / sm_100 build actually does.
 // One WARP per sequence (lanes stride over the words) instead of one thread per pair.
 __device__ __forceinline__ uint32_t complement_word(uint32_t w) {
   uint32_t o = 0;
@@ -54,7 +55,7 @@ __device__ __forceinline__ uint32_t complement_word(uint32_t w) {
 __global__ void __launch_bounds__(256) k_revcomp(uint32_t* __restrict__ pq, uint32_t* __restrict__ pt,
                                                  const uint32_t* __restrict__ q_lens, const uint32_t* __restrict__ t_lens,
                                                  const uint32_t* __restrict__ q_offs, const uint32_t* __restrict__ t_offs,
-                                                 const uint8_t* __restrict__ q_op, const uint8_t* __restrict__ t_op, uint32_t n) {
+                                                 const uint8_t* __restrict__ q_op, const uint8_t* __restrict__ t_op, uint32_t n, int mode) {
   const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (warp >= 2 * n) return;
   const uint32_t pair = warp >> 1; const bool isq = (warp & 1) == 0;
@@ -62,7 +63,18 @@ __global__ void __launch_bounds__(256) k_revcomp(uint32_t* __restrict__ pq, uint
   if (op == 0) return;
   uint32_t* w = (isq ? pq : pt) + ((isq ? q_offs : t_offs)[pair] >> 3);
   const uint32_t nw = n_words(isq ? q_lens[pair] : t_lens[pair]);
-  if (op & 1) {
+  if ((op & 1) && mode == 1) {
+    // literal behaviour of the reference as compiled by nvcc 12.9 for sm_100 (undefined shifts folded to 0):
+    // out[nw-1-i] = reverse(in[i]), out[i] = 0 for i < ceil(nw/2); complement of a 0 nibble is 0
+    for (uint32_t i = lane; i < (nw + 1) / 2; i += 32) {
+      uint32_t a = nibrev(w[i]);
+      if (op & 2) a = complement_word(a);
+      const uint32_t j = nw - 1 - i;
+      if (j != i) w[i] = 0u;
+      w[j] = a;
+    }
+    if ((op & 2) && lane == 0) { /* second-half words were all overwritten above; nothing else to complement */ }
+  } else if (op & 1) {
     for (uint32_t i = lane; i < (nw + 1) / 2; i += 32) {
       const uint32_t j = nw - 1 - i;
       uint32_t a = nibrev(w[i]), b = nibrev(w[j]);

@@ -202,6 +202,13 @@ void gasalx_set_n_code(int n_code, int n_penalty);
  * qualifies, else the general int32 kernels), 1 = force the general int32 kernels. */
 void gasalx_set_kernel_policy(int policy);
 
+/* Semantics of the "reverse" bit of host_query_op / host_target_op.  The reference kernel
+ * (src/kernels/pack_rc_seqs.h:56-212) shifts 32-bit words by 32, which is undefined in C:
+ *   0 (default) = nibble reversal of the whole padded word array (what PTX shift semantics give);
+ *   1           = bit-exact emulation of the reference as built by nvcc 12.9 for sm_100, where the undefined
+ *                 operand is folded to 0 (first half of the words zeroed, second half = reversed first half). */
+void gasalx_set_revcomp_mode(int mode);
+
 /* Device-side timing of the last finished batch of a storage, in milliseconds, measured with CUDA
  * events on gpu_storage->str: [0] whole pipeline (first H2D .. last D2H), [1] pack(+revcomp),
  * [2] DP kernels (+traceback).  Returns 0 on success, -1 if the batch has not finished. */

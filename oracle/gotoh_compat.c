@@ -83,20 +83,37 @@ static inline uint32_t rev_nibbles(uint32_t w)
     return r;
 }
 
-/* kernels/pack_rc_seqs.h:56-212 with the semantics the code has ON THE GPU:
- * nbr_N is always 0 (a nibble is compared with the full N_CODE 0x4E), the <<32 / >>32 shifts
- * clamp to 0, so "reverse" is a clean nibble reversal of the whole PADDED word array (pads end
- * up in front); "complement" swaps codes 1<->4 (A<->T) and 3<->7 (C<->G).  op bit0 = reverse,
- * bit1 = complement.  (If N_CODE < 16 the N count would be live; that build is not modelled.) */
+/* kernels/pack_rc_seqs.h:56-212.  op bit0 = reverse, bit1 = complement (A<->T = 1<->4, C<->G = 3<->7).
+ * The reverse branch has UNDEFINED BEHAVIOUR in C: the pad counter compares a nibble with the full
+ * N_CODE 0x4E, so nbr_N is always 0 and the code shifts 32-bit words by 32 (:136,153).  Two readings:
+ *   mode 0 (GC_REVCOMP_PADDED): shifts by 32 give 0 (PTX shl/shr semantics) -> a clean nibble reversal
+ *          of the whole PADDED word array, pads end up in front.  Engine default.
+ *   mode 1 (GC_REVCOMP_REF_NVCC129): what nvcc 12.9 actually emits for sm_100 (it folds the undefined
+ *          operand to 0; SASS in profiles/reference_revcomp_kernel_sm100_nvcc12.9.sass): for
+ *          i < ceil(nw/2): out[nw-1-i] = reverse(in[i]), out[i] = 0 (the middle word keeps its reversal);
+ *          the second half of the input is lost.  Verified against the reference binary on a B200
+ *          (tests/test_ref_gpu.py). */
+static int g_revcomp_mode = 0;
+void gc_set_revcomp_mode(int mode) { g_revcomp_mode = mode; }
+
 void gc_revcomp_one(uint32_t *words, uint32_t len, uint8_t op)
 {
     uint32_t nw = n_words(len);
     if (op & 1) {
-        for (uint32_t i = 0; i < nw / 2; i++) {
-            uint32_t a = rev_nibbles(words[i]), b = rev_nibbles(words[nw - 1 - i]);
-            words[i] = b; words[nw - 1 - i] = a;
+        if (g_revcomp_mode == 1) {
+            uint32_t swap = (nw >> 1) + (nw & 1);
+            for (uint32_t i = 0; i < swap; i++) {
+                uint32_t a = rev_nibbles(words[i]);
+                words[i] = 0;
+                words[nw - 1 - i] = a;
+            }
+        } else {
+            for (uint32_t i = 0; i < nw / 2; i++) {
+                uint32_t a = rev_nibbles(words[i]), b = rev_nibbles(words[nw - 1 - i]);
+                words[i] = b; words[nw - 1 - i] = a;
+            }
+            if (nw & 1) words[nw / 2] = rev_nibbles(words[nw / 2]);
         }
-        if (nw & 1) words[nw / 2] = rev_nibbles(words[nw / 2]);
     }
     if (op & 2) {
         for (uint32_t i = 0; i < nw; i++) {

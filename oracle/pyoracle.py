@@ -76,8 +76,10 @@ class Oracle:
             self.lib.gc_pack(np.ascontiguousarray(ascii_bytes), ascii_bytes.size, out)
         return out
 
-    def revcomp(self, pq, pt, q_lens, t_lens, q_offs, t_offs, q_op, t_op):
+    def revcomp(self, pq, pt, q_lens, t_lens, q_offs, t_offs, q_op, t_op, mode=0):
+        """mode 0: padded-array reversal (engine default); 1: the reference as built by nvcc 12.9 for sm_100 (UB artefact)"""
         pq, pt = pq.copy(), pt.copy()
+        self.lib.gc_set_revcomp_mode(int(mode))
         self.lib.gc_revcomp_batch(pq, pt, q_lens, t_lens, q_offs, t_offs, np.ascontiguousarray(q_op, dtype=np.uint8),
                                   np.ascontiguousarray(t_op, dtype=np.uint8), len(q_lens))
         return pq, pt
@@ -138,4 +140,52 @@ class RefHost:
                                 _ptr(res["cigar"], C.c_uint8), _ptr(res["n_cigar_ops"], C.c_uint32), n_threads)
         if rc != 0:
             raise RuntimeError("ref_align failed")
+        return res
+
+
+class RefGpu:
+    """The UNMODIFIED reference library built for sm_100 (oracle/_ref/ref_gpu_driver_mq<N>, see
+    oracle/ref_gpu/), run as a subprocess on a batch file.  Needs a GPU.  Used (a) to pin the oracle
+    against the reference's real GPU build, including gasal_reversecomplement_kernel whose C is only
+    well-defined on the GPU, and (b) as the same-GPU baseline bench.py reports."""
+
+    def __init__(self, max_query_len: int = 160):
+        self.path = os.path.join(HERE, "_ref", f"ref_gpu_driver_mq{max_query_len}")
+        if not os.path.exists(self.path):
+            raise FileNotFoundError(self.path)
+        self.max_query_len = max_query_len
+
+    @staticmethod
+    def available(max_query_len: int = 160) -> bool:
+        return os.path.exists(os.path.join(HERE, "_ref", f"ref_gpu_driver_mq{max_query_len}"))
+
+    def run(self, batch, *, algo, start=WITHOUT_START, second_best=False, head=TARGET, tail=TARGET, k_band=0, scoring=(1, 4, 6, 1),
+            q_op=None, t_op=None, batch_size=5000, reps=1, workdir=None):
+        import json
+        import tempfile
+        n = batch.n
+        q_op = np.zeros(n, np.uint8) if q_op is None else np.ascontiguousarray(q_op, dtype=np.uint8)
+        t_op = np.zeros(n, np.uint8) if t_op is None else np.ascontiguousarray(t_op, dtype=np.uint8)
+        revcomp = int(bool(q_op.any() or t_op.any()))
+        with tempfile.TemporaryDirectory(dir=workdir) as d:
+            fin, fout = os.path.join(d, "in.bin"), os.path.join(d, "out.bin")
+            with open(fin, "wb") as f:
+                np.array([n, batch.q_bytes.size, batch.t_bytes.size], dtype=np.uint32).tofile(f)
+                for a in (batch.q_bytes, batch.t_bytes, batch.q_offs, batch.t_offs, batch.q_lens, batch.t_lens, q_op, t_op):
+                    np.ascontiguousarray(a).tofile(f)
+            cmd = [self.path, fin, fout] + [str(int(x)) for x in (algo, start, int(bool(second_best)), head, tail, k_band, revcomp, *scoring, batch_size, reps)]
+            p = subprocess.run(cmd, capture_output=True, text=True)
+            if p.returncode != 0:
+                raise RuntimeError(f"reference GPU driver failed: {p.stderr[-2000:]}")
+            timing = json.loads(p.stdout.strip().splitlines()[-1])
+            raw = np.fromfile(fout, dtype=np.uint8)
+        nn = int(raw[:4].view(np.uint32)[0])
+        body = raw[4:4 + 4 * 9 * nn].view(np.int32).reshape(9, nn)
+        keys = ["aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start", "aln_score2", "query_batch_end2", "target_batch_end2"]
+        res = {k: body[i].copy() for i, k in enumerate(keys)}
+        res["n_cigar_ops"] = body[8].view(np.uint32).copy()
+        off = 4 + 4 * 9 * nn
+        qb = int(raw[off:off + 4].view(np.uint32)[0])
+        res["cigar"] = raw[off + 4:off + 4 + qb].copy()
+        res["_timing"] = timing
         return res
