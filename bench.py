@@ -144,6 +144,30 @@ def cpu_baseline_run(batch, n_sample: int, threads: int):
     return 2 * sub.cells / dt / 1e9, kind, sub.n, dt
 
 
+def ref_gpu_baseline(batch, n_sample: int):
+    """The reference's own CUDA library recompiled for sm_100 (oracle/_ref/ref_gpu_driver_mq*), same GPU, same workload
+    sample, through its own API with its example's 2-stream pipeline; batch size = half the sample (its GPU-filling
+    setting) -- a reported baseline (north_star), not the judged reference arm."""
+    from oracle import pyoracle as po
+    if not (po.RefGpu.available(160) and po.RefGpu.available(608)):
+        return {"unavailable": "oracle/_ref/ref_gpu_driver_mq160/608 not built"}
+    sub = batch.slice(0, min(n_sample, batch.n))
+    out = {"pairs": sub.n, "batch_size": sub.n // 2, "streams": 2}
+    t_ev = t_wall = 0.0
+    try:
+        for name, algo, mq in (("local", po.LOCAL, 160), ("semi_global", po.SEMI_GLOBAL, 608)):
+            r = po.RefGpu(mq).run(sub, algo=algo, start=po.WITH_START, scoring=SCORING, batch_size=sub.n // 2, reps=3)["_timing"]
+            out[name] = {"max_query_len": mq, "event_ms": r["event_ms_sum"], "wall_ms": r["wall_ms"], "gcups_events": r["gcups_events"], "gcups_wall": r["gcups_wall"]}
+            t_ev += r["event_ms_sum"]; t_wall += r["wall_ms"]
+    except Exception as e:  # the baseline must never break the bench line
+        return {"unavailable": f"reference GPU driver failed: {e}"[:200]}
+    out["value"] = 2 * sub.cells / (t_ev * 1e-3) / 1e9
+    out["value_wall"] = 2 * sub.cells / (t_wall * 1e-3) / 1e9
+    out["unit"] = "GCUPS"
+    out["timing"] = "value: CUDA events around each gasal_aln_async batch (H2D + kernels + D2H), summed; value_wall: host wall clock incl. its per-sequence host fill"
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -309,6 +333,7 @@ def run_ours(args, rank, world, local_rank):
 
     cpu_threads = os.cpu_count() or 1
     cpu_val, cpu_kind, cpu_n, cpu_dt = cpu_baseline_run(batch, args.cpu_pairs, cpu_threads)
+    refgpu = ref_gpu_baseline(batch, args.refgpu_pairs) if args.refgpu_pairs > 0 else {"unavailable": "disabled"}
 
     line = {
         "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -335,6 +360,7 @@ def run_ours(args, rank, world, local_rank):
                           "traffic": ncu_traffic("pack"), "bytes_def": "1.5 B per base (1 read + 0.5 written)"},
         "cpu_baseline": {"value": cpu_val, "unit": "GCUPS", "cores": cpu_threads, "kind": cpu_kind,
                          "sample": f"first {cpu_n} pairs of the same workload, both modes, {cpu_dt:.1f} s"},
+        "ref_gpu_baseline": refgpu,
     }
     print(json.dumps(line))
 
@@ -349,6 +375,7 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=8)
     ap.add_argument("--cpu-pairs", type=int, default=60_000, help="bounded sample for the cpu_baseline leg")
     ap.add_argument("--ref-pairs", type=int, default=60_000, help="pairs per step of the --impl reference arm")
+    ap.add_argument("--refgpu-pairs", type=int, default=262_144, help="sample for the reference-CUDA-build baseline on the same GPU (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
