@@ -150,3 +150,57 @@ class Aligner:
 
     def __exit__(self, *exc):
         self.close()
+
+
+def plan_batches(q_lens: np.ndarray, t_lens: np.ndarray, *, n_gpus: int = 1, max_batch_pairs: int = 262144, max_batch_bytes: int = 1 << 30,
+                 max_batch_cells: int = 1 << 36, keep_input_order: bool = False):
+    """Pure host planning of the batcher (no GPU needed): length-binned batches and their LPT assignment to GPUs."""
+    lib = capi.load()
+    sched = capi.Sched(); lib.gasalx_sched_default(C.byref(sched))
+    sched.n_gpus = n_gpus; sched.max_batch_pairs = max_batch_pairs; sched.max_batch_bytes = max_batch_bytes
+    sched.max_batch_cells = max_batch_cells; sched.keep_input_order = int(keep_input_order)
+    ql = np.ascontiguousarray(q_lens, dtype=np.uint32); tl = np.ascontiguousarray(t_lens, dtype=np.uint32)
+    n = ql.size
+    nb = int(lib.gasalx_plan_batches(ql.ctypes.data, tl.ctypes.data, n, C.byref(sched), None, None, None, None, 0))
+    order = np.zeros(n, dtype=np.uint32); start = np.zeros(nb + 1, dtype=np.uint32); gpu = np.zeros(nb, dtype=np.int32); cells = np.zeros(nb, dtype=np.uint64)
+    lib.gasalx_plan_batches(ql.ctypes.data, tl.ctypes.data, n, C.byref(sched), order.ctypes.data, start.ctypes.data, gpu.ctypes.data, cells.ctypes.data, nb)
+    return {"order": order, "batch_start": start, "batch_gpu": gpu, "batch_cells": cells}
+
+
+def align_all(batch: PairBatch, *, algo: int, start: int = capi.WITHOUT_START, second_best: bool = False, head: int = capi.TARGET,
+              tail: int = capi.TARGET, k_band: int = 0, scoring: Sequence[int] = (1, 4, 6, 1), n_gpus: int = 1, gpu_ids: Optional[Sequence[int]] = None,
+              streams_per_gpu: int = 2, max_batch_pairs: int = 262144, max_batch_cells: int = 1 << 36, q_op=None, t_op=None,
+              keep_input_order: bool = False) -> Dict[str, np.ndarray]:
+    """The whole job through the library-side batcher (gasalx_align_all): length binning, LPT sharding over the GPUs of this
+    process, pinned streaming on per-storage streams, host-side gather in the caller's order."""
+    lib = capi.load()
+    params = capi.Params(); lib.gasal_params_default(C.byref(params))
+    params.algo = algo; params.start_pos = start; params.secondBest = int(bool(second_best))
+    params.semiglobal_skipping_head = head; params.semiglobal_skipping_tail = tail; params.k_band = k_band
+    params.isReverseComplement = int(q_op is not None or t_op is not None)
+    sc = capi.SubstScores(*[int(v) for v in scoring]); lib.gasal_copy_subst_scores(C.byref(sc))
+    sched = capi.Sched(); lib.gasalx_sched_default(C.byref(sched))
+    sched.n_gpus = n_gpus; sched.streams_per_gpu = streams_per_gpu; sched.max_batch_pairs = max_batch_pairs; sched.max_batch_cells = max_batch_cells
+    sched.keep_input_order = int(keep_input_order)
+    ids = None
+    if gpu_ids is not None:
+        ids = (C.c_int32 * n_gpus)(*gpu_ids); sched.gpu_ids = ids
+    n = batch.n
+    out = {k: np.zeros(n, dtype=np.int32) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start",
+                                                    "aln_score2", "query_batch_end2", "target_batch_end2")}
+    out["n_cigar_ops"] = np.zeros(n, dtype=np.uint32)
+    out["cigar"] = np.zeros(batch.q_bytes.size if start == capi.WITH_TB else 8, dtype=np.uint8)
+    res = capi.Results(*[out[k].ctypes.data_as(C.POINTER(C.c_int32)) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start",
+                                                                                "target_batch_start", "aln_score2", "query_batch_end2", "target_batch_end2")],
+                       out["cigar"].ctypes.data_as(C.POINTER(C.c_uint8)), out["n_cigar_ops"].ctypes.data_as(C.POINTER(C.c_uint32)))
+    qo = np.ascontiguousarray(batch.q_offs, dtype=np.uint64); to = np.ascontiguousarray(batch.t_offs, dtype=np.uint64)
+    qop = None if q_op is None else np.ascontiguousarray(q_op, dtype=np.uint8)
+    top = None if t_op is None else np.ascontiguousarray(t_op, dtype=np.uint8)
+    gpu_ms = np.zeros(n_gpus, dtype=np.float64)
+    rc = lib.gasalx_align_all(batch.q_bytes.ctypes.data, batch.t_bytes.ctypes.data, qo.ctypes.data, to.ctypes.data, batch.q_lens.ctypes.data,
+                              batch.t_lens.ctypes.data, None if qop is None else qop.ctypes.data, None if top is None else top.ctypes.data, None,
+                              n, C.byref(params), C.byref(sched), C.byref(res), gpu_ms.ctypes.data)
+    if rc != 0:
+        raise RuntimeError(f"gasalx_align_all failed ({rc})")
+    out["_gpu_ms"] = gpu_ms
+    return out

@@ -64,6 +64,17 @@ class SubstScores(C.Structure):
     _fields_ = [("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_extend", C.c_int32)]
 
 
+class Sched(C.Structure):
+    _fields_ = [("n_gpus", C.c_int32), ("gpu_ids", C.POINTER(C.c_int32)), ("streams_per_gpu", C.c_int32), ("max_batch_pairs", C.c_uint32),
+                ("max_batch_bytes", C.c_uint64), ("max_batch_cells", C.c_uint64), ("keep_input_order", C.c_int32)]
+
+
+class Results(C.Structure):
+    _fields_ = [(n, C.POINTER(C.c_int32)) for n in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start",
+                                                    "aln_score2", "query_batch_end2", "target_batch_end2")] + \
+               [("cigar", C.POINTER(C.c_uint8)), ("n_cigar_ops", C.POINTER(C.c_uint32))]
+
+
 class Params(C.Structure):
     _fields_ = [("algo", C.c_int32), ("start_pos", C.c_int32), ("secondBest", C.c_int32), ("isPacked", C.c_int32),
                 ("isReverseComplement", C.c_int32), ("semiglobal_skipping_head", C.c_int32), ("semiglobal_skipping_tail", C.c_int32),
@@ -80,6 +91,7 @@ EXPORTED_SYMBOLS = [
     "gasal_res_new_host", "gasal_res_new_device", "gasal_res_new_device_cpy", "gasal_res_destroy_host", "gasal_res_destroy_device",
     "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
     "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
+    "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all",
 ]
 
 _lib = None
@@ -118,5 +130,10 @@ def load() -> C.CDLL:
     lib.gasalx_aln_device_resident.argtypes = [P(GpuStorage), C.c_uint32, C.c_uint32, C.c_uint32, P(Params)]
     lib.gasalx_host_batch_rearm.argtypes = [P(GpuStorage), C.c_uint32, C.c_uint32, C.c_uint32]
     lib.gasalx_version.restype = C.c_char_p
+    lib.gasalx_sched_default.argtypes = [P(Sched)]
+    lib.gasalx_plan_batches.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, P(Sched), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.gasalx_plan_batches.restype = C.c_int64
+    lib.gasalx_align_all.argtypes = [C.c_void_p] * 9 + [C.c_uint64, P(Params), P(Sched), P(Results), C.c_void_p]
+    lib.gasalx_align_all.restype = C.c_int
     _lib = lib
     return lib

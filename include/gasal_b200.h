@@ -231,6 +231,38 @@ void gasalx_aln_device_resident(gasal_gpu_storage_t* gpu_storage, uint32_t actua
  * still there).  Lets a caller re-submit the same pre-filled pinned batch. */
 void gasalx_host_batch_rearm(gasal_gpu_storage_t* gpu_storage, uint32_t q_bytes, uint32_t t_bytes, uint32_t n_alns);
 
+/* ---- host batcher / multi-GPU sharder (genomics_gpu_b200/csrc/batcher.cpp) -------------------------
+ * The reference leaves batching to the caller and has no multi-GPU mode; these entry points take ALL pairs
+ * of a job, length-bin them, cut batches, spread the batches over the GPUs by LPT on DP cells, stream them
+ * through gasal_aln_async on per-storage streams (one host worker thread per GPU) and return the results
+ * in the caller's original pair order. */
+typedef struct {
+  int32_t n_gpus;                /* GPUs of this process to use (>= 1) */
+  const int32_t* gpu_ids;        /* NULL: 0 .. n_gpus-1 */
+  int32_t streams_per_gpu;       /* storages (streams) per GPU, default 2 (reference NB_STREAMS, test_prog.cpp:12) */
+  uint32_t max_batch_pairs;      /* default 262144 (the reference's commented GPU-filling STREAM_BATCH_SIZE, test_prog.cpp:14) */
+  uint64_t max_batch_bytes;      /* per sequence side, default 1 GiB (must stay < 4 GiB: 32-bit offsets of the GASAL2 API) */
+  uint64_t max_batch_cells;      /* default 2^36 DP cells */
+  int32_t keep_input_order;      /* 1: no length binning (batches follow input order, like test_prog) */
+} gasalx_sched_t;
+
+typedef struct {                 /* any pointer may be NULL; arrays have one entry per pair of the job */
+  int32_t *aln_score, *query_batch_end, *target_batch_end, *query_batch_start, *target_batch_start;
+  int32_t *aln_score2, *query_batch_end2, *target_batch_end2;
+  uint8_t* cigar;                /* WITH_TB: same layout as the caller's query buffer (pair i writes at q_offs[i]) */
+  uint32_t* n_cigar_ops;
+} gasalx_results_t;
+
+void gasalx_sched_default(gasalx_sched_t* s);
+/* pure host planning (no CUDA): number of batches; optional outputs order[n], batch_start[nb+1], batch_gpu[nb], batch_cells[nb] (first `cap` batches) */
+int64_t gasalx_plan_batches(const uint32_t* q_lens, const uint32_t* t_lens, uint64_t n, const gasalx_sched_t* sched,
+                            uint32_t* order, uint32_t* batch_start, int32_t* batch_gpu, uint64_t* batch_cells, uint64_t cap);
+/* align all pairs; sequences concatenated in gasal_host_batch_fill layout at 64-bit byte offsets. 0 on success.
+ * gpu_ms (optional, n_gpus doubles): device time per GPU from CUDA events. */
+int gasalx_align_all(const uint8_t* q_bytes, const uint8_t* t_bytes, const uint64_t* q_offs, const uint64_t* t_offs,
+                     const uint32_t* q_lens, const uint32_t* t_lens, const uint8_t* q_op, const uint8_t* t_op, const uint32_t* seed_scores,
+                     uint64_t n, const gasal_params_t* params, const gasalx_sched_t* sched, gasalx_results_t* out, double* gpu_ms);
+
 /* Version string of the engine. */
 const char* gasalx_version(void);
 
