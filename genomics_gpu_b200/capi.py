@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "lib", "libgasal_b200.so")
+LIB_PATH = os.environ.get("GASAL_B200_LIB") or os.path.join(HERE, "lib", "libgasal_b200.so")   # env override: A/B builds during development
 
 # enums (include/gasal_b200.h, reference src/gasal.h:37-72)
 WITHOUT_START, WITH_START, WITH_TB = 0, 1, 2

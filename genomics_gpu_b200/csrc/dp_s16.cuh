@@ -24,8 +24,12 @@
 
 namespace gb200 {
 
-constexpr int kFastThreads = 128;
-constexpr uint32_t kFastMaxQ8 = 360;      // (q8+2) * 128 * 5 B must fit one CTA's shared memory
+#ifndef GB200_FAST_THREADS
+#define GB200_FAST_THREADS 128
+#endif
+constexpr int kFastThreads = GB200_FAST_THREADS;
+constexpr uint32_t kFastMaxQ8 = 352;      // (q8 + kSlotPad) * 128 * 5 B must fit one CTA's shared memory
+constexpr uint32_t kSlotPad = 7;          // dummy column slots: 2 below column 0 (late lanes' phantom columns), 5 above the last column
 constexpr uint32_t kFastFallbackSlots = 8192;
 
 struct FastScratch {
@@ -69,7 +73,9 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 // bestK7 = max.s16x2(bestK7, c7); lanes that strictly improved record (cm, pos).  One asm block so that
 // ptxas fuses the per-lane compares into the predicate outputs of VIMNMX.S16x2 (the CUDA header's
 // __vibmax_s16x2 lost its predicate uses in partially unrolled loops with nvcc 12.9).
-__device__ __forceinline__ void track_update(LaneBest& lb, uint32_t c7, uint32_t cm, uint32_t pos) {
+__device__ __forceinline__ void track_update(LaneBest& lb, uint32_t c7, uint32_t cm, uint32_t pos, uint32_t one = 1u) {
+  // the four conditional record moves are written as predicated multiply-adds by a run-time 1 so that they issue on
+  // the FMA pipe (IMAD) instead of competing with the DP recurrence for the ALU pipe (SEL / MOV)
   asm volatile(
       "{\n\t"
       ".reg .pred pl, ph;\n\t"
@@ -81,13 +87,13 @@ __device__ __forceinline__ void track_update(LaneBest& lb, uint32_t c7, uint32_t
       "setp.eq.s16 pl, n0, o0;\n\t"
       "setp.eq.s16 ph, n1, o1;\n\t"
       "mov.b32 %0, nb;\n\t"
-      "@!pl mov.b32 %1, %6;\n\t"
-      "@!pl mov.b32 %3, %7;\n\t"
-      "@!ph mov.b32 %2, %6;\n\t"
-      "@!ph mov.b32 %4, %7;\n\t"
+      "@!pl mad.lo.u32 %1, %6, %8, 0;\n\t"
+      "@!pl mad.lo.u32 %3, %7, %8, 0;\n\t"
+      "@!ph mad.lo.u32 %2, %6, %8, 0;\n\t"
+      "@!ph mad.lo.u32 %4, %7, %8, 0;\n\t"
       "}"
       : "+r"(lb.bestK7), "+r"(lb.keyL), "+r"(lb.keyH), "+r"(lb.posL), "+r"(lb.posH)
-      : "r"(c7), "r"(cm), "r"(pos));
+      : "r"(c7), "r"(cm), "r"(pos), "r"(one));
 }
 
 // One double-strip sweep of the D-based local recurrence (reference local_kernel_template.h:19-30).
@@ -156,14 +162,120 @@ __device__ __forceinline__ Winner pick_winner(const LaneBest& lb) {
   return w;
 }
 
+
+// ---- quad-strip variant: FOUR consecutive strips per thread and sweep -------------------------------------
+// Register set A holds strips 4j (lane L) and 4j+1 (lane H), set B strips 4j+2 / 4j+3; the four strips are skewed
+// by one query column each (A.L col k, A.H col k-1, B.L col k-2, B.H col k-3), so B.L's top row is A.H's bottom row
+// of the previous step.  Two independent dependency chains per thread (twice the ILP at the 8-9 resident warps per
+// SM that shared memory allows), and the per-column shared-memory round trip is paid once per 32 target rows.
+struct LaneBest4 { LaneBest a, b; };
+
+__device__ __forceinline__ uint32_t key_tree(const uint32_t (&key)[8]) {
+  uint32_t cm = __vimax3_s16x2(key[0], key[1], key[2]);
+  cm = __vimax3_s16x2(cm, key[3], key[4]);
+  cm = __vimax3_s16x2(cm, key[5], key[6]);
+  return __vmaxs2(cm, key[7]);
+}
+
+__device__ __forceinline__ void local_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
+                                             const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                             const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                             uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t one, uint32_t pos_base, LaneBest4& lb) {
+  uint32_t pA[8], fA[8], pB[8], fB[8], keyA[8], keyB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { pA[r] = 0; fA[r] = 0; pB[r] = 0; fB[r] = 0; keyA[r] = 0; keyB[r] = 0; }
+  uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
+  uint32_t prevsh = 0xCC00u;
+  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;   // phantom columns: score 0 / -1
+  uint32_t he = HE[kFastThreads];                  // slot 1 = column 0
+  uint32_t v = V[kFastThreads];
+  uint32_t pos = pos_base;                         // position code of the step whose keys are in keyA / keyB
+  for (int k = 0; k < nsteps; k++) {
+    const uint32_t selA = v | prevsh;
+    prevsh = v * 256u + 0x4400u;
+    uint32_t upA = prmt(he, h8A, 0x5410);
+    uint32_t eA = prmt(he, eoA, 0x5432);
+    uint32_t upB = prmt(h8A, h8B, 0x5432);
+    uint32_t eB = prmt(eoA, eoB, 0x5432);
+    he = HE[(k + 2) * kFastThreads];
+    v = V[(k + 2) * kFastThreads];
+    // branch-free argmax of the PREVIOUS step's keys (software-pipelined: this dependent chain of 7 ALU ops has no
+    // input from the current step, so it overlaps the row updates below instead of trailing them)
+    {
+      const uint32_t cm = key_tree(keyA);
+      track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+      const uint32_t cn = key_tree(keyB);
+      track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+      pos = pos_base + (uint32_t)k;
+    }
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      {
+        const uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        const uint32_t d = __vadd2(pA[r], s2);
+        const uint32_t dm = __vadd2(d, neg_oe2);
+        const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
+        fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, dm);
+        eA = __viaddmax_s16x2(eA, neg_ext2, dm);
+        keyA[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+        pA[r] = upA; upA = h;
+      }
+      {
+        const uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        const uint32_t d = __vadd2(pB[r], s2);
+        const uint32_t dm = __vadd2(d, neg_oe2);
+        const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
+        fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, dm);
+        eB = __viaddmax_s16x2(eB, neg_ext2, dm);
+        keyB[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+        pB[r] = upB; upB = h;
+      }
+    }
+    // B.H finished column k-3 (slot k-2): park (H,E) for the next quad-strip
+    HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+    h8A = upA; eoA = eA; h8B = upB; eoB = eB;
+    selB = selA_prev; selA_prev = selA;
+  }
+  {
+    const uint32_t cm = key_tree(keyA);
+    track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+    const uint32_t cn = key_tree(keyB);
+    track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+  }
+}
+
+__device__ __forceinline__ void lanebest_init(LaneBest& lb) { lb.bestK7 = 0x00070007u; lb.keyL = lb.keyH = 0; lb.posL = lb.posH = 0; }
+
+// winner over the four records; pos = (quad-strip index << 16) | step
+__device__ __forceinline__ Winner pick_winner4(const LaneBest4& lb) {
+  int sc[4], strip[4], col[4], row[4];
+  sc[0] = (int)(short)(lb.a.bestK7 & 0xFFFFu) >> 3; sc[1] = (int)(short)(lb.a.bestK7 >> 16) >> 3;
+  sc[2] = (int)(short)(lb.b.bestK7 & 0xFFFFu) >> 3; sc[3] = (int)(short)(lb.b.bestK7 >> 16) >> 3;
+  const uint32_t pos[4] = {lb.a.posL, lb.a.posH, lb.b.posL, lb.b.posH};
+  const uint32_t key[4] = {lb.a.keyL & 0xFFFFu, lb.a.keyH >> 16, lb.b.keyL & 0xFFFFu, lb.b.keyH >> 16};
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    strip[i] = 4 * (int)(pos[i] >> 16) + i;
+    col[i] = (int)(pos[i] & 0xFFFFu) - i;
+    row[i] = strip[i] * 8 + (7 - (int)(key[i] & 7u));
+  }
+  Winner w; w.score = 0; w.col = 0; w.row = 0;
+  int bs = 0, bstrip = 0x7FFFFFFF;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    if (sc[i] > bs || (sc[i] == bs && sc[i] > 0 && strip[i] < bstrip)) { bs = sc[i]; bstrip = strip[i]; w.score = sc[i]; w.col = col[i]; w.row = row[i]; }
+  }
+  return w;
+}
+
 template <int START>
 __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (uint32_t)a.n) return;
-  uint32_t* HE = smem + threadIdx.x;
-  uint8_t* V = (uint8_t*)(smem + (fa.q8max + 3) * kFastThreads) + threadIdx.x;
+  uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
+  uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
 
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
   const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
@@ -189,8 +301,8 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
       HE[(c + 1) * kFastThreads] = 0;
     }
   }
-  V[(ncol + 1) * kFastThreads] = 0x88; HE[(ncol + 1) * kFastThreads] = 0;
-  V[(ncol + 2) * kFastThreads] = 0x88; HE[(ncol + 2) * kFastThreads] = 0;
+#pragma unroll
+  for (int x = 1; x <= 4; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = 0; }
   for (int i = 0; i < TR && !odd; i++) {
     const uint32_t w = tw[i];
 #pragma unroll
@@ -202,19 +314,24 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     return;
   }
 
-  // ---- forward pass over double-strips ----
-  LaneBest lb; lb.bestK7 = 0x00070007u; lb.keyL = lb.keyH = 0; lb.posL = lb.posH = 0;
-  const int ND = (TR + 1) >> 1;
-  const int nsteps = ncol + (int)fa.one;   // run-time 1: keeps the trip count opaque (compiler note)
-  for (int j = 0; j < ND; j++) {
-    uint32_t rowA[8], rowB[8];
-    const uint32_t wa = tw[2 * j];
-    const uint32_t wb = (2 * j + 1 < TR) ? tw[2 * j + 1] : 0u;     // phantom strip: every base mismatches
+  // ---- forward pass over quad-strips ----
+  LaneBest4 lb; lanebest_init(lb.a); lanebest_init(lb.b);
+  const int NQ = (TR + 3) >> 2;
+  const int nsteps = ncol + 2 + (int)fa.one;   // run-time 1: keeps the trip count opaque (compiler note)
+  for (int j = 0; j < NQ; j++) {
+    uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
+    const uint32_t wa = tw[4 * j];
+    const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;     // phantom strips: every base mismatches
+    const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
+    const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
 #pragma unroll
-    for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
-    local_sweep(HE, V, nsteps, rowA, rowB, neg_oe2, neg_ext2, fa.eight, (uint32_t)j << 16, lb);
+    for (int r = 0; r < 8; r++) {
+      rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
+      rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
+    }
+    local_sweep4(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb);
   }
-  const Winner fw = pick_winner(lb);
+  const Winner fw = pick_winner4(lb);
   a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row;
 
   if (START == START_POS) {
@@ -234,21 +351,27 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
           HE[(c + 1) * kFastThreads] = 0;
         }
       }
-      V[(rcol + 1) * kFastThreads] = 0x88; HE[(rcol + 1) * kFastThreads] = 0;
-      V[(rcol + 2) * kFastThreads] = 0x88; HE[(rcol + 2) * kFastThreads] = 0;
-      LaneBest rb; rb.bestK7 = 0x00070007u; rb.keyL = rb.keyH = 0; rb.posL = rb.posH = 0;
-      const int RD = (gend_reg + 1) >> 1;
+#pragma unroll
+      for (int x = 1; x <= 4; x++) { V[(rcol + x) * kFastThreads] = 0x88; HE[(rcol + x) * kFastThreads] = 0; }
+      LaneBest4 rb; lanebest_init(rb.a); lanebest_init(rb.b);
+      const int RD = (gend_reg + 3) >> 2;
       const int fwd7 = (fw.score << 3) | 7;
       for (int j = 0; j < RD; j++) {
-        uint32_t rowA[8], rowB[8];
-        const uint32_t wa = nibrev(tw[gend_reg - 1 - 2 * j]);
-        const uint32_t wb = (2 * j + 1 < gend_reg) ? nibrev(tw[gend_reg - 2 - 2 * j]) : 0u;
+        uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
+        const uint32_t wa = nibrev(tw[gend_reg - 1 - 4 * j]);
+        const uint32_t wb = (4 * j + 1 < gend_reg) ? nibrev(tw[gend_reg - 2 - 4 * j]) : 0u;
+        const uint32_t wc = (4 * j + 2 < gend_reg) ? nibrev(tw[gend_reg - 3 - 4 * j]) : 0u;
+        const uint32_t wd = (4 * j + 3 < gend_reg) ? nibrev(tw[gend_reg - 4 - 4 * j]) : 0u;
 #pragma unroll
-        for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
-        local_sweep(HE, V, rcol + (int)fa.one, rowA, rowB, neg_oe2, neg_ext2, fa.eight, (uint32_t)j << 16, rb);
-        if ((int)(short)(rb.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.bestK7 >> 16) >= fwd7) break;
+        for (int r = 0; r < 8; r++) {
+          rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
+          rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
+        }
+        local_sweep4(HE, V, rcol + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb);
+        if ((int)(short)(rb.a.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.a.bestK7 >> 16) >= fwd7 ||
+            (int)(short)(rb.b.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.b.bestK7 >> 16) >= fwd7) break;
       }
-      const Winner rw = pick_winner(rb);
+      const Winner rw = pick_winner4(rb);
       if (rw.score > 0) {
         sx = rcol - 1 - rw.col;                                    // ridx
         const int strip = rw.row >> 3, r = rw.row & 7;
@@ -299,18 +422,20 @@ __device__ __forceinline__ void nc_sweep(uint32_t* __restrict__ HE, const uint8_
     he = HE[(k + 2) * kFastThreads];
     v = V[(k + 2) * kFastThreads];
     uint32_t hh[8];
-    uint32_t gu = __vadd2(up, neg_oe2);
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       const uint32_t s2 = prmt(rowA[r], rowB[r], sel);
       const uint32_t d = __vadd2(p[r], s2);
       uint32_t h;
       if (SEMI) {
+        // H-based opening without the serial H -> E -> H chain: with M = max(D, F) and H = max(M, E),
+        // E(t+1,q) = max(H - oe, E - e) = max(D - oe, F - oe, E - e) because oe >= e.  `e` therefore enters a row
+        // as E(t,q) and leaves it as E(t+1,q); the parked / handed-over E is the NEXT row's.
         f[r] = __viaddmax_s16x2(f[r], neg_ext2, gl[r]);        // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
-        e = __viaddmax_s16x2(e, neg_ext2, gu);                 // E(t,q) = max(H(t-1,q) - oe, E(t-1,q) - e)
         h = __vimax3_s16x2(d, f[r], e);
-        gu = __vadd2(h, neg_oe2);
-        gl[r] = gu;
+        const uint32_t dm = __vadd2(d, neg_oe2), fm = __vadd2(f[r], neg_oe2), ee = __vadd2(e, neg_ext2);
+        e = __vimax3_s16x2(dm, fm, ee);
+        gl[r] = __vadd2(h, neg_oe2);
       } else {
         const uint32_t dm = __vadd2(d, neg_oe2);
         h = __vimax3_s16x2(d, f[r], e);
@@ -354,8 +479,126 @@ __device__ __forceinline__ void nc_sweep(uint32_t* __restrict__ HE, const uint8_
   }
 }
 
+// ---- quad-strip variant of nc_sweep (see local_sweep4): strips 4j..4j+3 as A.L, A.H, B.L, B.H, skewed by one column each.
+// The rare per-step work (re-imposing the strip-start state of the late lanes after their phantom columns; the scan of
+// the last true query column; the global capture) is gathered behind ONE compare per step (k == knext).
+//   kq      : step at which lane A.L is on the scanned / captured column (qlen - 1); lane i is there at step kq + i
+//   lane_lo/lane_hi of hhA / hhB give the four lanes' H values of the current step
+template <int ALGO, bool REV>
+__device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
+                                          const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                          const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                          const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8],
+                                          uint32_t neg_oe2, uint32_t neg_ext2,
+                                          int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr) {
+  constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
+  const uint32_t neg2 = splat16(kNegSafe);
+  uint32_t pA[8], fA[8], glA[8], pB[8], fB[8], glB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { pA[r] = pinitA[r]; fA[r] = neg2; glA[r] = neg_oe2; pB[r] = pinitB[r]; fB[r] = neg2; glB[r] = neg_oe2; }
+  uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
+  uint32_t prevsh = 0xCC00u;
+  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;
+  uint32_t he = HE[kFastThreads];
+  uint32_t v = V[kFastThreads];
+  int knext = 0;
+  for (int k = 0; k < nsteps; k++) {
+    const uint32_t selA = v | prevsh;
+    prevsh = v * 256u + 0x4400u;
+    uint32_t upA = prmt(he, h8A, 0x5410);
+    uint32_t eA = prmt(he, eoA, 0x5432);
+    uint32_t upB = prmt(h8A, h8B, 0x5432);
+    uint32_t eB = prmt(eoA, eoB, 0x5432);
+    he = HE[(k + 2) * kFastThreads];
+    v = V[(k + 2) * kFastThreads];
+    uint32_t hhA[8], hhB[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      {
+        const uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        const uint32_t d = __vadd2(pA[r], s2);
+        uint32_t h;
+        if (SEMI) {
+          // H-based opening without the serial H -> E -> H chain: with H = max(D, F, E),
+          // E(t+1,q) = max(H - oe, E - e) = max(D - oe, F - oe, E - e) because oe >= e.  `e` enters a row as E(t,q) and
+          // leaves it as E(t+1,q); the parked / handed-over E is the NEXT row's.
+          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, glA[r]);   // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
+          h = __vimax3_s16x2(d, fA[r], eA);
+          const uint32_t dm = __vadd2(d, neg_oe2), fm = __vadd2(fA[r], neg_oe2), ee = __vadd2(eA, neg_ext2);
+          eA = __vimax3_s16x2(dm, fm, ee);
+          glA[r] = __vadd2(h, neg_oe2);
+        } else {
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          h = __vimax3_s16x2(d, fA[r], eA);
+          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, dm);
+          eA = __viaddmax_s16x2(eA, neg_ext2, dm);
+        }
+        hhA[r] = h; pA[r] = upA; upA = h;
+      }
+      {
+        const uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        const uint32_t d = __vadd2(pB[r], s2);
+        uint32_t h;
+        if (SEMI) {
+          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, glB[r]);
+          h = __vimax3_s16x2(d, fB[r], eB);
+          const uint32_t dm = __vadd2(d, neg_oe2), fm = __vadd2(fB[r], neg_oe2), ee = __vadd2(eB, neg_ext2);
+          eB = __vimax3_s16x2(dm, fm, ee);
+          glB[r] = __vadd2(h, neg_oe2);
+        } else {
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          h = __vimax3_s16x2(d, fB[r], eB);
+          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, dm);
+          eB = __viaddmax_s16x2(eB, neg_ext2, dm);
+        }
+        hhB[r] = h; pB[r] = upB; upB = h;
+      }
+    }
+    HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+    h8A = upA; eoA = eA; h8B = upB; eoB = eB;
+    selB = selA_prev; selA_prev = selA;
+    if (k == knext) {
+      if (k <= 2) {
+        // lanes that just ran a phantom column (A.H: step 0; B.L: 0,1; B.H: 0,1,2) get their strip-start state back
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          if (k == 0) { pA[r] = prmt(pA[r], pinitA[r], 0x7610); fA[r] = prmt(fA[r], neg2, 0x7610); if (SEMI) glA[r] = prmt(glA[r], neg_oe2, 0x7610); }
+          if (k <= 1) { pB[r] = pinitB[r]; fB[r] = neg2; if (SEMI) glB[r] = neg_oe2; }
+          else { pB[r] = prmt(pB[r], pinitB[r], 0x7610); fB[r] = prmt(fB[r], neg2, 0x7610); if (SEMI) glB[r] = prmt(glB[r], neg_oe2, 0x7610); }
+        }
+      }
+      const int li = k - kq;
+      if (li >= 0 && li <= 3) {
+        int hv[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          const uint32_t w = (li & 2) ? hhB[r] : hhA[r];
+          hv[r] = (li & 1) ? lane_hi(w) : lane_lo(w);
+        }
+        if (SEMI) {
+          // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178); the start
+          // pass stops between strips once the forward score is reached (:301)
+          if (!REV || li == 0 || tr.best < tr.stop) {
+            const int rb = rowbase + 8 * li;
+#pragma unroll
+            for (int r = 0; r < 8; r++) if (rb + r < tlen && hv[r] > tr.best) { tr.best = hv[r]; tr.y = rb + r; }
+          }
+        } else if (li == caplane) {
+#pragma unroll
+          for (int r = 0; r < 8; r++) if (r == caprow) tr.cap = hv[r];
+        }
+      }
+      int nxt = -1;
+      if (k < 2) nxt = k + 1; else if (k < kq) nxt = kq;
+      if (k >= kq && k < kq + 3) nxt = k + 1;
+      knext = nxt;
+    }
+  }
+}
+
 // selector bytes + top boundary of one pass into shared memory.  mode 0: forward words; mode 2: true-length reversed.
-template <bool TOP_ZERO>
+// SEMI: the parked E is the first row's own E(0,c) = max(H(-1,c) - oe, E(-1,c) - e) (see nc_sweep); otherwise E(-1,c).
+template <bool TOP_ZERO, bool SEMI = true>
 __device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint32_t* qw, uint32_t qlen, int QR, int mode, int o, int ext) {
   bool odd = false;
   const int ncol = QR * 8;
@@ -369,11 +612,16 @@ __device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint
       odd |= (idx > 3) && ((uint32_t)c < qlen);
       V[(c + 1) * kFastThreads] = (idx > 3) ? 0x88 : (uint8_t)(0x80u + 0x11u * idx);
       // top boundary: H(-1, c), E = -inf   (semiglobal_kernel_template.h:87-99, global.h:57-60)
-      HE[(c + 1) * kFastThreads] = TOP_ZERO ? 0u : pack2(c == 0 ? 0 : -(o + ext * c), kNegSafe);   // free top row: (H,E) = (0,0)
+      if (SEMI) {
+        const int htop = TOP_ZERO ? 0 : (c == 0 ? 0 : -(o + ext * c));                  // free top row: (H,E)(-1,c) = (0,0)
+        HE[(c + 1) * kFastThreads] = pack2(htop, TOP_ZERO ? -ext : htop - (o + ext));
+      } else {
+        HE[(c + 1) * kFastThreads] = pack2(c == 0 ? 0 : -(o + ext * c), kNegSafe);
+      }
     }
   }
-  V[(ncol + 1) * kFastThreads] = 0x88; HE[(ncol + 1) * kFastThreads] = pack2(0, kNegSafe);
-  V[(ncol + 2) * kFastThreads] = 0x88; HE[(ncol + 2) * kFastThreads] = pack2(0, kNegSafe);
+#pragma unroll
+  for (int x = 1; x <= 4; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = pack2(0, kNegSafe); }
   return odd;
 }
 
@@ -393,8 +641,8 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const DpArgs& a = fa.a;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (uint32_t)a.n) return;
-  uint32_t* HE = smem + threadIdx.x;
-  uint8_t* V = (uint8_t*)(smem + (fa.q8max + 3) * kFastThreads) + threadIdx.x;
+  uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
+  uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
   const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
   const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
@@ -404,7 +652,7 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const int oe = a.gap_open + a.gap_extend;
   const uint32_t neg_oe2 = splat16(-oe), neg_ext2 = splat16(-a.gap_extend);
   const bool top_zero = (a.head == SKIP_BOTH);          // HEAD in {QUERY,BOTH}: free top row (:87)
-  const int ncol = QR * 8, nsteps = ncol + (int)fa.one;
+  const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
 
   bool odd = top_zero ? nc_prologue<true>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend)
                       : nc_prologue<false>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend);
@@ -419,14 +667,19 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   for (int r = 0; r < 8; r++) pinit[r] = 0;             // HEAD in {TARGET,BOTH}: free left column, diag = 0 (:114-121)
 
   NcTrack tr; tr.best = kMinusInf; tr.y = (int)qlen; tr.stop = 0; tr.cap = 0;       // :63-64
-  const int ND = (TR + 1) >> 1;
-  for (int j = 0; j < ND; j++) {
-    uint32_t rowA[8], rowB[8];
-    const uint32_t wa = tw[2 * j];
-    const uint32_t wb = (2 * j + 1 < TR) ? tw[2 * j + 1] : 0u;
+  const int NQ = (TR + 3) >> 2;
+  for (int j = 0; j < NQ; j++) {
+    uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
+    const uint32_t wa = tw[4 * j];
+    const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;
+    const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
+    const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
 #pragma unroll
-    for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
-    nc_sweep<ALGO_SEMI_GLOBAL, false>(HE, V, nsteps, rowA, rowB, pinit, neg_oe2, neg_ext2, (int)qlen - 1, (int)qlen, 16 * j, 16 * j + 8, (int)tlen, 0, tr);
+    for (int r = 0; r < 8; r++) {
+      rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
+      rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
+    }
+    nc_sweep4<ALGO_SEMI_GLOBAL, false>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr);
   }
   a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = (int)tlen;            // query_batch_end = ref_len (Q8)
 
@@ -439,13 +692,18 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     if (top_zero) nc_prologue<true>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend);
     else nc_prologue<false>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend);
     NcTrack rt; rt.best = kMinusInf; rt.y = 0; rt.stop = fwd; rt.cap = 0;             // :275-276
-    for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 2) {
-      uint32_t rowA[8], rowB[8];
+    for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 4) {
+      uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
       const uint32_t wa = rev_true_word(tw, (int)tlen, (int)i);
       const uint32_t wb = (i + 1 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 1) : 0u;
+      const uint32_t wc = (i + 2 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 2) : 0u;
+      const uint32_t wd = (i + 3 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 3) : 0u;
 #pragma unroll
-      for (int r = 0; r < 8; r++) { rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta); }
-      nc_sweep<ALGO_SEMI_GLOBAL, true>(HE, V, nsteps, rowA, rowB, pinit, neg_oe2, neg_ext2, (int)qlen - 1, (int)qlen, 8 * (int)i, 8 * (int)i + 8, (int)tlen, 0, rt);
+      for (int r = 0; r < 8; r++) {
+        rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
+        rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
+      }
+      nc_sweep4<ALGO_SEMI_GLOBAL, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt);
     }
     a.t_start[tid] = ((int)tlen - 1) - rt.y;                                          // :380-381
     a.q_start[tid] = ((int)qlen - 1) - (int)tlen;
@@ -457,8 +715,8 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
   const DpArgs& a = fa.a;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (uint32_t)a.n) return;
-  uint32_t* HE = smem + threadIdx.x;
-  uint8_t* V = (uint8_t*)(smem + (fa.q8max + 3) * kFastThreads) + threadIdx.x;
+  uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
+  uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
   const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
   const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
@@ -467,8 +725,8 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
   const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
   const int o = a.gap_open, ext = a.gap_extend;
   const uint32_t neg_oe2 = splat16(-(o + ext)), neg_ext2 = splat16(-ext);
-  const int ncol = QR * 8, nsteps = ncol + (int)fa.one;
-  bool odd = nc_prologue<false>(HE, V, qw, qlen, QR, 0, o, ext);
+  const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
+  bool odd = nc_prologue<false, false>(HE, V, qw, qlen, QR, 0, o, ext);
   odd |= target_has_odd_base(tw, tlen, TR);
   if (odd || qlen == 0 || tlen == 0) {
     const uint32_t slot = atomicAdd(fa.work_count, 1u);
@@ -476,20 +734,25 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
     return;
   }
   NcTrack tr; tr.best = 0; tr.y = 0; tr.stop = 0; tr.cap = 0;
-  const int ND = (TR + 1) >> 1;
+  const int NQ = (TR + 3) >> 2;
   const int last_strip = (int)(tlen - 1) >> 3, caprow = (int)(tlen - 1) & 7;
-  for (int j = 0; j < ND; j++) {
-    uint32_t rowA[8], rowB[8], pinit[8];
-    const uint32_t wa = tw[2 * j];
-    const uint32_t wb = (2 * j + 1 < TR) ? tw[2 * j + 1] : 0u;
+  for (int j = 0; j < NQ; j++) {
+    uint32_t rowA[8], rowB[8], rowC[8], rowD[8], pinitA[8], pinitB[8];
+    const uint32_t wa = tw[4 * j];
+    const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;
+    const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
+    const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
-      const int tL = 16 * j + r, tH = 16 * j + 8 + r;                               // diag(t) = t ? -(o + e*t) : 0   (global.h:66-70)
-      pinit[r] = pack2(tL == 0 ? 0 : -(o + ext * tL), -(o + ext * tH));
+      rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
+      const int t0 = 32 * j + r;                                                     // diag(t) = t ? -(o + e*t) : 0   (global.h:66-70)
+      pinitA[r] = pack2(t0 == 0 ? 0 : -(o + ext * t0), -(o + ext * (t0 + 8)));
+      pinitB[r] = pack2(-(o + ext * (t0 + 16)), -(o + ext * (t0 + 24)));
     }
-    const int kL = (2 * j == last_strip) ? (int)qlen - 1 : -1, kH = (2 * j + 1 == last_strip) ? (int)qlen : -1;
-    nc_sweep<ALGO_GLOBAL, false>(HE, V, nsteps, rowA, rowB, pinit, neg_oe2, neg_ext2, kL, kH, 0, 0, (int)tlen, caprow, tr);
+    const bool has_last = (last_strip >> 2) == j;
+    nc_sweep4<ALGO_GLOBAL, false>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinitA, pinitB, neg_oe2, neg_ext2,
+                                  has_last ? (int)qlen - 1 : -1000, 0, (int)tlen, last_strip & 3, caprow, tr);
   }
   a.score[tid] = tr.cap;                                                              // H(ref_len-1, read_len-1)  (global.h:285-299)
 }
@@ -567,7 +830,7 @@ inline int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& f
     fs.colstate_words = cs_need;
   }
   FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.work_count = fs.work_count; fa.eight = 8; fa.one = 1;
-  const size_t smem = (size_t)(q8 + 3) * kFastThreads * 4 + (size_t)(q8 + 3) * kFastThreads;
+  const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads;
   if (!fs.attr_set) {
     const int lim = 227 * 1024;
     cudaFuncSetAttribute(k_local_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);

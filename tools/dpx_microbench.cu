@@ -18,7 +18,7 @@
 
 enum Op {
   OP_VIADDMNMX_S16X2 = 0, OP_VIMNMX3_S16X2, OP_VIMNMX_S16X2, OP_VIADD_16X2, OP_VIADDMNMX_S32, OP_VIMNMX3_S32,
-  OP_IADD, OP_IMAD, OP_LOP3, OP_HSET2, OP_PRMT, OP_SHF, OP_VIADDMNMX_S16X2_RELU, OP_HADD2, OP_NOP_COUNT
+  OP_IADD, OP_IMAD, OP_LOP3, OP_HSET2, OP_PRMT, OP_SHF, OP_VIADDMNMX_S16X2_RELU, OP_HADD2, OP_HMNMX2, OP_SELP, OP_NOP_COUNT
 };
 
 template <int OP>
@@ -37,6 +37,8 @@ __device__ __forceinline__ uint32_t apply(uint32_t a, uint32_t b, uint32_t c) {
   if (OP == OP_PRMT) { uint32_t r; asm volatile("prmt.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
   if (OP == OP_SHF) { uint32_t r; asm volatile("shf.l.wrap.b32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
   if (OP == OP_HADD2) { uint32_t r; asm volatile("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
+  if (OP == OP_HMNMX2) { uint32_t r; asm volatile("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+  if (OP == OP_SELP) { uint32_t r; asm volatile("{.reg .pred p; setp.ne.u32 p, %3, 0; selp.b32 %0, %1, %2, p;}" : "=r"(r) : "r"(a), "r"(b), "r"(c)); return r; }
   return a;
 }
 
@@ -78,13 +80,14 @@ static const char* opname(int op) {
     case OP_IADD: return "IADD3"; case OP_IMAD: return "IMAD"; case OP_LOP3: return "LOP3";
     case OP_HSET2: return "HSET2"; case OP_PRMT: return "PRMT"; case OP_SHF: return "SHF";
     case OP_VIADDMNMX_S16X2_RELU: return "VIADDMNMX.S16x2.RELU"; case OP_HADD2: return "HFMA2";
+    case OP_HMNMX2: return "HMNMX2"; case OP_SELP: return "SEL";
   }
   return "none";
 }
 
 template <int OP1, int OP2, int ILP>
-Result run(int n_sm, uint32_t* d_out, uint32_t* d_in, long long* d_cyc) {
-  const int blocks_per_sm = 4, threads = 256;
+Result run(int n_sm, uint32_t* d_out, uint32_t* d_in, long long* d_cyc, int threads = 256) {
+  const int blocks_per_sm = 4;
   const int grid = n_sm * blocks_per_sm;
   const int iters = 131072;   // ~35 ms per kernel: long enough for the SM clock to settle
   k_bench<OP1, OP2, ILP><<<grid, threads>>>(d_out, d_in, 64, d_cyc);  // warm-up
@@ -105,6 +108,7 @@ Result run(int n_sm, uint32_t* d_out, uint32_t* d_in, long long* d_cyc) {
   if (OP1 == OP_VIMNMX_S16X2 && OP2 == OP_NOP_COUNT) warp_instr_per_sm *= 0.5;  // ptxas fuses max(max(a,b),b) pairs into one VIMNMX3
   Result r;
   r.name = std::string(opname(OP1)) + (OP2 == OP_NOP_COUNT ? "" : std::string("+") + opname(OP2));
+  if (threads != 256) r.name += " @" + std::to_string(threads * blocks_per_sm / 32) + " warps/SM";
   r.ops_per_clk_sm = warp_instr_per_sm * 32.0 / avg_cyc;   // lane-ops per clock per SM
   r.ms = ms;
   r.ghz = avg_cyc / (ms * 1e6);
@@ -133,6 +137,11 @@ int main() {
   RUN2(OP_VIADDMNMX_S16X2, OP_IMAD); RUN2(OP_VIADDMNMX_S16X2, OP_LOP3); RUN2(OP_VIADDMNMX_S16X2, OP_HSET2);
   RUN2(OP_VIADDMNMX_S16X2, OP_PRMT); RUN2(OP_VIADDMNMX_S16X2, OP_HADD2); RUN2(OP_VIADD_16X2, OP_IMAD); RUN2(OP_VIADD_16X2, OP_LOP3);
   RUN2(OP_HSET2, OP_IMAD); RUN2(OP_HSET2, OP_LOP3); RUN2(OP_IMAD, OP_LOP3); RUN2(OP_VIMNMX3_S32, OP_IMAD);
+  RUN1(OP_HMNMX2); RUN2(OP_VIADDMNMX_S16X2, OP_HMNMX2); RUN2(OP_VIADD_16X2, OP_HMNMX2); RUN2(OP_VIADDMNMX_S16X2, OP_SELP);
+  // the same mixes at the occupancy the DP fast path runs at (8 warps per SM = 2 per scheduler)
+  res.push_back(run<OP_VIADDMNMX_S16X2, OP_NOP_COUNT, 8>(n_sm, d_out, d_in, d_cyc, 64));
+  res.push_back(run<OP_VIADDMNMX_S16X2, OP_VIADD_16X2, 6>(n_sm, d_out, d_in, d_cyc, 64));
+  res.push_back(run<OP_VIADDMNMX_S16X2, OP_VIMNMX3_S16X2, 6>(n_sm, d_out, d_in, d_cyc, 64));
   double R_alu = 0, R_fma = 0, R_dual = 0;
   for (auto& r : res) {
     if (r.nops == 1 && (r.name.find("VIADDMNMX.S16x2") == 0 || r.name.find("VIMNMX3.S16x2") == 0)) R_alu = std::max(R_alu, r.lane_ops_per_s);
