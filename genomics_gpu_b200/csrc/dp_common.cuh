@@ -64,6 +64,15 @@ __device__ __forceinline__ uint32_t rev_true_word(const uint32_t* __restrict__ w
   return nibrev(x);
 }
 
+// 4-bit code -> 0..3 for A(1) C(3) G(7) T(4), 4 for anything else
+__device__ __forceinline__ uint32_t base_idx(uint32_t code) {
+  return (uint32_t)((0x4444444424431404ull >> (4 * code)) & 15ull);
+}
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+
 __device__ __forceinline__ short2 u32_as_short2(uint32_t v) { short2 r; r.x = (short)(v & 0xFFFFu); r.y = (short)(v >> 16); return r; }
 __device__ __forceinline__ uint32_t pack_short2(int h, int e) { return ((uint32_t)h & 0xFFFFu) | ((uint32_t)e << 16); }
 

@@ -52,15 +52,6 @@ struct FastArgs {
   uint32_t one;            // == 1, run-time so that the sweep's trip count (columns + 1) is opaque to the unroller
 };
 
-// 4-bit code -> 0..3 for A(1) C(3) G(7) T(4), 4 for anything else
-__device__ __forceinline__ uint32_t base_idx(uint32_t code) {
-  return (uint32_t)((0x4444444424431404ull >> (4 * code)) & 15ull);
-}
-
-__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
-  uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
-}
-
 __device__ __forceinline__ uint32_t splat16(int v) { const uint32_t u = (uint32_t)v & 0xFFFFu; return u | (u << 16); }
 
 // per-row substitution table: byte i = score of query base i against this row's target base
@@ -74,8 +65,6 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 // ptxas fuses the per-lane compares into the predicate outputs of VIMNMX.S16x2 (the CUDA header's
 // __vibmax_s16x2 lost its predicate uses in partially unrolled loops with nvcc 12.9).
 __device__ __forceinline__ void track_update(LaneBest& lb, uint32_t c7, uint32_t cm, uint32_t pos, uint32_t one = 1u) {
-  // the four conditional record moves are written as predicated multiply-adds by a run-time 1 so that they issue on
-  // the FMA pipe (IMAD) instead of competing with the DP recurrence for the ALU pipe (SEL / MOV)
   asm volatile(
       "{\n\t"
       ".reg .pred pl, ph;\n\t"
@@ -87,10 +76,10 @@ __device__ __forceinline__ void track_update(LaneBest& lb, uint32_t c7, uint32_t
       "setp.eq.s16 pl, n0, o0;\n\t"
       "setp.eq.s16 ph, n1, o1;\n\t"
       "mov.b32 %0, nb;\n\t"
-      "@!pl mad.lo.u32 %1, %6, %8, 0;\n\t"
-      "@!pl mad.lo.u32 %3, %7, %8, 0;\n\t"
-      "@!ph mad.lo.u32 %2, %6, %8, 0;\n\t"
-      "@!ph mad.lo.u32 %4, %7, %8, 0;\n\t"
+      "@!pl mov.b32 %1, %6;\n\t"
+      "@!pl mov.b32 %3, %7;\n\t"
+      "@!ph mov.b32 %2, %6;\n\t"
+      "@!ph mov.b32 %4, %7;\n\t"
       "}"
       : "+r"(lb.bestK7), "+r"(lb.keyL), "+r"(lb.keyH), "+r"(lb.posL), "+r"(lb.posH)
       : "r"(c7), "r"(cm), "r"(pos), "r"(one));
@@ -429,7 +418,7 @@ __device__ __forceinline__ void nc_sweep(uint32_t* __restrict__ HE, const uint8_
       uint32_t h;
       if (SEMI) {
         // H-based opening without the serial H -> E -> H chain: with M = max(D, F) and H = max(M, E),
-        // E(t+1,q) = max(H - oe, E - e) = max(D - oe, F - oe, E - e) because oe >= e.  `e` therefore enters a row
+        // E(t+1,q) = max(H - oe, E - e) = max(max(D, F) - oe, E - e) because oe >= e.  `e` therefore enters a row
         // as E(t,q) and leaves it as E(t+1,q); the parked / handed-over E is the NEXT row's.
         f[r] = __viaddmax_s16x2(f[r], neg_ext2, gl[r]);        // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
         h = __vimax3_s16x2(d, f[r], e);
@@ -520,12 +509,12 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
         uint32_t h;
         if (SEMI) {
           // H-based opening without the serial H -> E -> H chain: with H = max(D, F, E),
-          // E(t+1,q) = max(H - oe, E - e) = max(D - oe, F - oe, E - e) because oe >= e.  `e` enters a row as E(t,q) and
+          // E(t+1,q) = max(H - oe, E - e) = max(max(D, F) - oe, E - e) because oe >= e.  `e` enters a row as E(t,q) and
           // leaves it as E(t+1,q); the parked / handed-over E is the NEXT row's.
           fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, glA[r]);   // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
-          h = __vimax3_s16x2(d, fA[r], eA);
-          const uint32_t dm = __vadd2(d, neg_oe2), fm = __vadd2(fA[r], neg_oe2), ee = __vadd2(eA, neg_ext2);
-          eA = __vimax3_s16x2(dm, fm, ee);
+          const uint32_t m = __vmaxs2(d, fA[r]);
+          h = __vmaxs2(m, eA);
+          eA = __viaddmax_s16x2(eA, neg_ext2, __vadd2(m, neg_oe2));
           glA[r] = __vadd2(h, neg_oe2);
         } else {
           const uint32_t dm = __vadd2(d, neg_oe2);
@@ -541,9 +530,9 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
         uint32_t h;
         if (SEMI) {
           fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, glB[r]);
-          h = __vimax3_s16x2(d, fB[r], eB);
-          const uint32_t dm = __vadd2(d, neg_oe2), fm = __vadd2(fB[r], neg_oe2), ee = __vadd2(eB, neg_ext2);
-          eB = __vimax3_s16x2(dm, fm, ee);
+          const uint32_t m = __vmaxs2(d, fB[r]);
+          h = __vmaxs2(m, eB);
+          eB = __viaddmax_s16x2(eB, neg_ext2, __vadd2(m, neg_oe2));
           glB[r] = __vadd2(h, neg_oe2);
         } else {
           const uint32_t dm = __vadd2(d, neg_oe2);

@@ -15,6 +15,7 @@
 #include "pack_tb.cuh"
 #include "dp_generic.cuh"
 #include "dp_s16.cuh"
+#include "dp_wave.cuh"
 
 using namespace gb200;
 
@@ -45,6 +46,7 @@ struct Priv {
   uint8_t* d_cigar = nullptr; size_t cigar_bytes = 0;
   uint32_t* d_n_cigar_ops = nullptr; size_t n_cigar_cap = 0;
   FastScratch fast;
+  WaveScratch wave;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};   // start, packed, dp done, end
   bool timing_pending = false;
   uint64_t launches = 0;
@@ -426,6 +428,7 @@ void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_par
       if (pv->d_cigar) CHECKCUDAERROR(cudaFree(pv->d_cigar));
       if (pv->d_n_cigar_ops) CHECKCUDAERROR(cudaFree(pv->d_n_cigar_ops));
       pv->fast.release();
+      pv->wave.release();
       for (int e = 0; e < 4; e++) if (pv->ev[e]) CHECKCUDAERROR(cudaEventDestroy(pv->ev[e]));
       delete pv;
     }
@@ -533,6 +536,17 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
     const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, s->str);
     if (nl < 0) { fprintf(stderr, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); exit(EXIT_FAILURE); }
     CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "s16x2";
+    return;
+  }
+
+  // ---- long pairs: intra-task wavefront kernel (dp_wave.cuh) ----
+  // policy 0: whenever the batch is too long for the fast path; policy 2: wherever the wavefront kernel is eligible
+  if (g_kernel_policy != 1 && wave_eligible(a, params->algo, start, second, shape.min_q, shape.min_t) &&
+      (g_kernel_policy == 2 || q8 > kFastMaxQ8)) {
+    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nl = wave_launch(a, params->algo, start, pv->wave, s->host_query_batch_lens, s->host_target_batch_lens, shape.max_t, sms, s->str);
+    if (nl < 0) { fprintf(stderr, "[GASAL CUDA ERROR:] out of device memory for the wavefront scratch\n"); exit(EXIT_FAILURE); }
+    CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "wave";
     return;
   }
 

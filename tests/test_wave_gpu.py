@@ -1,0 +1,131 @@
+"""GPU parity of the intra-task wavefront kernel (K3, dp_wave.cuh) against the oracle, through the C ABI.
+
+policy 2 forces the wavefront kernel wherever it is eligible, so the ragged short batches of the general parity suite
+exercise every edge (1-strip targets, partial row-blocks, pads, N bases, exotic IUPAC codes); the long batches exercise the
+multi-block pipeline (boundary hand-over through global memory, tickets, per-pair reduction)."""
+import numpy as np
+import pytest
+
+from genomics_gpu_b200 import capi, synth
+from genomics_gpu_b200.aligner import Aligner
+from oracle import pyoracle as po
+
+from helpers import K3, K5, assert_same, oracle_align
+
+pytestmark = pytest.mark.gpu
+
+SCORINGS = [(1, 4, 6, 1), (2, 3, 5, 2), (5, 4, 10, 1)]
+
+
+def run(batch, *, policy=2, **kw):
+    lib = capi.load()
+    lib.gasalx_set_kernel_policy(policy)
+    mq = int(batch.q_lens.max()) + 7; mt = int(batch.t_lens.max()) + 7
+    try:
+        with Aligner(max_query_len=mq, max_target_len=mt, max_n_alns=batch.n, n_streams=1, **kw) as al:
+            res = al.align(batch)
+            res["_kernel"] = al.kernel_name(0)
+    finally:
+        lib.gasalx_set_kernel_policy(0)
+    return res
+
+
+def ragged(seed, n=500, **kw):
+    return synth.random_ragged_pairs(n, 9, 220, 9, 700, seed=seed, n_frac=0.01, **kw)
+
+
+def long_pairs(seed, n=24, lo=1500, hi=5000):
+    rng = np.random.default_rng(seed)
+    qs, ts = [], []
+    for _ in range(n):
+        L = int(rng.integers(lo, hi))
+        t, q = synth.nw_style_pair(rng, L)
+        qs.append(q); ts.append(t)
+    return synth.batch_from_sequences(qs, ts)
+
+
+@pytest.mark.parametrize("scoring", SCORINGS)
+def test_wave_local_ragged(oracle, scoring):
+    b = ragged(301)
+    want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_START, scoring=scoring)
+    got = run(b, algo=capi.LOCAL, start=capi.WITH_START, scoring=scoring)
+    assert got["_kernel"] == "wave"
+    assert_same(got, want, K5, f"wave local {scoring}")
+    got = run(b, algo=capi.LOCAL, scoring=scoring)
+    assert_same(got, want, K3, f"wave local score/end {scoring}")
+
+
+@pytest.mark.parametrize("scoring", SCORINGS)
+def test_wave_global_ragged(oracle, scoring):
+    b = ragged(302)
+    want = oracle_align(oracle, b, algo=po.GLOBAL, scoring=scoring)
+    got = run(b, algo=capi.GLOBAL, scoring=scoring)
+    assert got["_kernel"] == "wave"
+    assert_same(got, want, ["aln_score"], f"wave global {scoring}")
+
+
+@pytest.mark.parametrize("head", [po.TARGET, po.BOTH])
+@pytest.mark.parametrize("scoring", SCORINGS[:2])
+def test_wave_semiglobal_ragged(oracle, scoring, head):
+    b = ragged(303 + head)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, head=head, tail=po.TARGET, start=po.WITH_START, scoring=scoring, max_query_len=1024)
+    got = run(b, algo=capi.SEMI_GLOBAL, head=head, tail=capi.TARGET, start=capi.WITH_START, scoring=scoring)
+    assert got["_kernel"] == "wave"
+    assert_same(got, want, K5, f"wave semi-global head={head} {scoring}")
+
+
+def test_wave_exotic_codes(oracle):
+    """IUPAC letters other than ACGTN are ordinary symbols (equal -> match); they take the compare path"""
+    rng = np.random.default_rng(9)
+    alpha = np.frombuffer(b"ACGTACGTACGTNRYK", dtype=np.uint8)
+    qs = [bytes(alpha[rng.integers(0, alpha.size, size=int(rng.integers(20, 400)))]) for _ in range(200)]
+    ts = [bytes(alpha[rng.integers(0, alpha.size, size=int(rng.integers(20, 600)))]) for _ in range(200)]
+    b = synth.batch_from_sequences(qs, ts)
+    for algo, keys, extra in [(po.LOCAL, K5, dict(start=po.WITH_START)), (po.GLOBAL, ["aln_score"], {}),
+                              (po.SEMI_GLOBAL, K5, dict(start=po.WITH_START, max_query_len=1024))]:
+        want = oracle_align(oracle, b, algo=algo, **extra)
+        extra.pop("max_query_len", None)
+        got = run(b, algo=algo, **extra)
+        assert got["_kernel"] == "wave"
+        assert_same(got, want, keys, f"wave exotic codes algo={algo}")
+
+
+def test_wave_long_local_with_start(oracle):
+    b = long_pairs(41)
+    want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_START, max_query_len=8192)
+    got = run(b, policy=0, algo=capi.LOCAL, start=capi.WITH_START)          # policy 0: long batches pick the wavefront kernel themselves
+    assert got["_kernel"] == "wave"
+    assert_same(got, want, K5, "wave long local")
+
+
+def test_wave_long_global(oracle):
+    b = long_pairs(42)
+    want = oracle_align(oracle, b, algo=po.GLOBAL, max_query_len=8192)
+    got = run(b, policy=0, algo=capi.GLOBAL)
+    assert got["_kernel"] == "wave"
+    assert_same(got, want, ["aln_score"], "wave long global")
+
+
+def test_wave_long_semiglobal_with_start(oracle):
+    rng = np.random.default_rng(43)
+    qs, ts = [], []
+    for _ in range(24):
+        L = int(rng.integers(800, 3000))
+        t, q = synth.nw_style_pair(rng, L)
+        flank_l = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(0, 900))))
+        flank_r = bytes(rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(0, 900))))
+        qs.append(q); ts.append(flank_l + t + flank_r)
+    b = synth.batch_from_sequences(qs, ts)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, start=po.WITH_START, max_query_len=8192)
+    got = run(b, policy=0, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)
+    assert got["_kernel"] == "wave"
+    assert_same(got, want, K5, "wave long semi-global")
+
+
+def test_wave_matches_general_kernel_on_mixed_lengths(oracle):
+    """size-independent property: the wavefront kernel and the one-thread-per-pair kernel agree on a mixed 100 bp - 6 kb batch"""
+    b = synth.config5(96, seed=7, lo=100, hi=6000)
+    a = run(b, policy=1, algo=capi.LOCAL, start=capi.WITH_START)
+    w = run(b, policy=0, algo=capi.LOCAL, start=capi.WITH_START)
+    assert a["_kernel"] == "int32" and w["_kernel"] == "wave"
+    assert_same(w, a, K5, "wave vs general kernel, mixed lengths")
