@@ -5,10 +5,13 @@
 // (lane L is on column k - L at step k), so lane L's bottom row (H, E) reaches lane L+1 with __shfl_up_sync one step
 // later -- no shared-memory column array at all inside a block.  Lane 31's bottom row is the top boundary of the next
 // row-block of the same pair; it goes through a small per-warp shared-memory ring and is flushed 32 columns at a time
-// (coalesced) to a per-pair double buffer in global memory (L2-resident), with a release/acquire progress counter
-// per task.  Tasks are handed out by a global ticket counter in (pair, block) order, so a task only ever waits on a
-// LOWER ticket that some resident warp already holds: deadlock-free for any grid size, no cooperative launch, and all
-// row-blocks of a pair (and of the next pairs) run concurrently as a pipeline across the whole GPU.
+// (coalesced) to a per-pair double buffer in global memory (L2-resident).  Each 16-byte column entry is two
+// self-validating 8-byte words (H, tag) (E, tag) -- the tag names the launch and the producing block -- so the consumer
+// simply re-reads a chunk until every tag matches: no flags, no fences (8-byte stores are single-copy atomic; the same
+// idea as NCCL's LL protocol), and the next chunk is prefetched a whole chunk ahead.  Tasks are handed out by a global
+// ticket counter in (pair, block) order, so a task only ever waits on a LOWER ticket that some resident warp already
+// holds: deadlock-free for any grid size, no cooperative launch, and all row-blocks of a pair (and of the next pairs)
+// run concurrently as a pipeline across the whole GPU.
 //
 // Same recurrences, boundaries and tie-breaking as the inter-task kernels (dp_generic.cuh), int32 lanes on the DPX
 // instructions (VIMNMX3 / VIADDMNMX); the substitution score is ONE PRMT per cell from a per-row 4-byte table.
@@ -35,10 +38,10 @@ struct WaveArgs {
   uint32_t maxblk;           // tickets reserved per pair
   const uint64_t* qoff;      // per pair: first column slot in bnd (exclusive prefix sum of padded query lengths)
   const uint64_t* soff;      // per pair: first strip slot in cand (exclusive prefix sum of target words)
-  uint2* bnd;                // two column buffers: bnd[buf * bnd_stride + qoff[p] + c] = (H, E) below the block's last row
+  uint4* bnd;                // two column buffers: bnd[buf * bnd_stride + qoff[p] + c] = (H, tag, E, tag) below the block's last row
   uint64_t bnd_stride;
+  uint32_t tag_base;         // tag of block b = tag_base + b (unique per launch and block, never 0)
   int2* cand;                // per strip: (score, position) candidate of the strip
-  uint32_t* prog;            // per ticket: number of columns whose bottom boundary is published
   uint32_t* ticket;          // global ticket counter
   uint32_t* done;            // per pair: finished row-blocks
 };
@@ -51,11 +54,12 @@ struct WaveGeom {
   int fwd;         // forward score (start passes)
 };
 
-__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
-  uint32_t v; asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory"); return v;
+// boundary entries travel through L2 only (never L1): relaxed gpu-scope vector accesses, each 8-byte half atomic
+__device__ __forceinline__ uint4 ld_bnd(const uint4* p) {
+  uint4 v; asm volatile("ld.relaxed.gpu.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory"); return v;
 }
-__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
-  asm volatile("st.release.gpu.global.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
+__device__ __forceinline__ void st_bnd(uint4* p, uint4 v) {
+  asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1, %2, %3, %4};" :: "l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
 
 __device__ __forceinline__ WaveGeom wave_geometry(const WaveArgs& w, uint32_t pair) {
@@ -149,19 +153,127 @@ __device__ __forceinline__ void wave_finalize(const WaveArgs& w, uint32_t pair, 
   }
 }
 
+template <int SR>
+struct WaveLane {
+  uint32_t tword[SR];           // this lane's packed target words
+  uint32_t tbl[8 * SR];         // per row: score against query A, C, G, T (one byte each)
+  int p[8 * SR], f[8 * SR], gl[8 * SR];
+  int best[SR], bpos[SR];
+  int h_bot, e_bot; uint32_t sel_cur;
+};
+
+// up to 32 consecutive steps [k0, kend).  STEADY: every lane is inside the matrix for the whole chunk and the scanned /
+// captured column (ncol - 1) is not touched, so the body carries no activity or capture tests.  EXOTIC: some column of
+// this or the previous chunk holds a query code outside the PRMT table (IUPAC letters; N under the GLOBAL rule).
+template <int ALGO, int SR, bool STEADY, bool EXOTIC>
+__device__ __forceinline__ void wave_steps(WaveLane<SR>& L, const Sc& sc, uint32_t ntab, const uint2* sin, const uint32_t* ssel, uint2* sout,
+                                           int k0, int kend, int ncol, int lane, int qlen, int tlen, int row0, int lstrip, int32_t* score_out) {
+  constexpr int ROWS = 8 * SR;
+  constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL), LOCALA = (ALGO == ALGO_LOCAL);
+  const int oe = sc.oe, ext = sc.ext;
+  for (int k = k0; k < kend; k++) {
+    // ---- (H, E) of the row above come from the lane above, lane 0 takes them from the chunk ring; every lane reads its
+    // column's selector from the 64-column selector ring (address known a step ahead, off the critical path) ----
+#ifdef WAVE_SEL_SHFL
+    uint32_t sel = __shfl_up_sync(0xFFFFFFFFu, L.sel_cur, 1);
+    int h_in = __shfl_up_sync(0xFFFFFFFFu, L.h_bot, 1);
+    int e_in = __shfl_up_sync(0xFFFFFFFFu, L.e_bot, 1);
+    if (lane == 0) { const uint2 top = sin[k & 31]; h_in = (int)top.x; e_in = (int)top.y; sel = ssel[k & 63]; }
+#else
+    const uint2 top = sin[k & 31];
+    const uint32_t sel = ssel[(k - lane) & 63];
+    int h_in = __shfl_up_sync(0xFFFFFFFFu, L.h_bot, 1);
+    int e_in = __shfl_up_sync(0xFFFFFFFFu, L.e_bot, 1);
+    if (lane == 0) { h_in = (int)top.x; e_in = (int)top.y; }
+#endif
+    const int c = k - lane;
+    if (STEADY || (c >= 0 && c < ncol)) {
+#ifdef WAVE_SEL_SHFL
+      L.sel_cur = sel;
+#endif
+      int sv[ROWS];
+      if (EXOTIC && (sel & kWaveExotic)) {
+        const uint32_t qc = (sel >> 20) & 15u;
+#pragma unroll
+        for (int s = 0; s < SR; s++)
+#pragma unroll
+          for (int r = 0; r < 8; r++) sv[8 * s + r] = score_general(sc, qc, nib(L.tword[s], r));
+      } else {
+#pragma unroll
+        for (int r = 0; r < ROWS; r++) sv[r] = (int)prmt(L.tbl[r], ntab, sel);
+      }
+      int up = h_in, e = e_in;
+      int hh[ROWS];
+#pragma unroll
+      for (int r = 0; r < ROWS; r++) {
+        const int d = L.p[r] + sv[r];
+        int h;
+        if (SEMI) {
+          L.f[r] = __viaddmax_s32(L.f[r], -ext, L.gl[r]);           // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
+          const int m = max(d, L.f[r]);
+          h = max(m, e);
+          e = __viaddmax_s32(e, -ext, m - oe);                      // E(t+1,q) = max(max(D,F) - oe, E - e)  (oe >= e)
+          L.gl[r] = h - oe;
+        } else {
+          h = LOCALA ? __vimax3_s32_relu(d, L.f[r], e) : __vimax3_s32(d, L.f[r], e);
+          const int dm = d - oe;
+          L.f[r] = __viaddmax_s32(L.f[r], -ext, dm);
+          e = __viaddmax_s32(e, -ext, dm);
+        }
+        hh[r] = h; L.p[r] = up; up = h;
+      }
+      L.h_bot = up; L.e_bot = e;
+      if (LOCALA) {
+#pragma unroll
+        for (int s = 0; s < SR; s++) {
+          const int cm = max(__vimax3_s32(hh[8 * s], hh[8 * s + 1], hh[8 * s + 2]),
+                             __vimax3_s32(__vimax3_s32(hh[8 * s + 3], hh[8 * s + 4], hh[8 * s + 5]), hh[8 * s + 6], hh[8 * s + 7]));
+          if (cm > L.best[s]) {
+            int rr = 7;
+#pragma unroll
+            for (int r = 6; r >= 0; r--) rr = (hh[8 * s + r] == cm) ? r : rr;
+            L.best[s] = cm; L.bpos[s] = (c << 3) | rr;
+          }
+        }
+      } else if (!STEADY && c == qlen - 1) {
+        if (SEMI) {
+          // TAIL == TARGET: last true query column, rows inside the target, strict '>' top-down (:160-178)
+#pragma unroll
+          for (int s = 0; s < SR; s++)
+#pragma unroll
+            for (int r = 0; r < 8; r++) {
+              const int t = row0 + 8 * s + r;
+              if (t < tlen && hh[8 * s + r] > L.best[s]) { L.best[s] = hh[8 * s + r]; L.bpos[s] = t; }
+            }
+        } else {
+          const int t_last = tlen - 1;
+          if ((unsigned)((t_last >> 3) - lstrip) < (unsigned)SR) {
+            int v = hh[0];
+#pragma unroll
+            for (int r = 1; r < ROWS; r++) v = ((t_last - 8 * lstrip) == r) ? hh[r] : v;
+            *score_out = v;                                         // H(ref_len-1, read_len-1)  (global.h:285-299)
+          }
+        }
+      }
+      if (lane == 31) sout[k & 31] = make_uint2((uint32_t)up, (uint32_t)e);
+    }
+  }
+}
+
 template <int ALGO, int SR>
 __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
-  constexpr int ROWS = 8 * SR;
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL), LOCALA = (ALGO == ALGO_LOCAL), GLOB = (ALGO == ALGO_GLOBAL);
-  __shared__ uint4 s_in[kWaveWarps][32];     // top boundary + selector of the current 32-column chunk: (H, E, sel, -)
-  __shared__ uint2 s_out[kWaveWarps][32];    // bottom boundary of the chunk being produced
+  __shared__ uint2 s_in[kWaveWarps][32];     // top boundary (H, E) of the current 32-column chunk
+  __shared__ uint32_t s_sel[kWaveWarps][64]; // PRMT selectors of the last two chunks' columns
+  __shared__ uint2 s_out[kWaveWarps][32];    // bottom boundary produced during the current chunk (slot = step & 31)
   const DpArgs& a = w.a;
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  uint4* sin = s_in[wib]; uint2* sout = s_out[wib];
+  uint2* sin = s_in[wib]; uint32_t* ssel = s_sel[wib]; uint2* sout = s_out[wib];
   const Sc sc = make_sc(a, GLOB);
   const int oe = sc.oe, ext = sc.ext;
   const bool top_zero = SEMI && (a.head == SKIP_BOTH);
   const uint32_t total = (uint32_t)a.n * w.maxblk;
+  const uint32_t ntab = (uint32_t)sc.nscore & 0xFFu;            // query N under the LOCAL rule: same score in every row
 
   for (;;) {
     uint32_t T = 0;
@@ -180,163 +292,90 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
     const uint32_t* tw = a.pt + (a.t_offs[pair] >> 3);
     const int ncol = g.ncol;
     const int lstrip = ((int)blk * 32 + lane) * SR;             // this lane's first strip, pass-local numbering
+    const int row0 = 8 * (g.strip0 + lstrip);                   // its first row in the pass' sequence numbering
     const bool last_blk = ((int)blk == nblk - 1);
 
-    // ---- per-row substitution tables (4 bytes: score against query A, C, G, T) and left-boundary state ----
-    uint32_t tword[SR];
-    uint32_t tbl[ROWS];
-    int p[ROWS], f[ROWS], gl[ROWS];
+    // ---- per-row substitution tables and left-boundary state ----
+    WaveLane<SR> L;
 #pragma unroll
     for (int s = 0; s < SR; s++) {
-      tword[s] = (lstrip + s < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip + s) : 0u;
+      L.tword[s] = (lstrip + s < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip + s) : 0u;
 #pragma unroll
       for (int r = 0; r < 8; r++) {
-        const uint32_t tc = nib(tword[s], r);
+        const uint32_t tc = nib(L.tword[s], r);
         const uint32_t b0 = (uint32_t)score_general(sc, 1u, tc) & 0xFFu, b1 = (uint32_t)score_general(sc, 3u, tc) & 0xFFu;
         const uint32_t b2 = (uint32_t)score_general(sc, 7u, tc) & 0xFFu, b3 = (uint32_t)score_general(sc, 4u, tc) & 0xFFu;
-        tbl[8 * s + r] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
-        const int t = 8 * (g.strip0 + lstrip + s) + r;          // row index in the pass' sequence numbering
-        if (LOCALA) { p[8 * s + r] = 0; f[8 * s + r] = 0; }
-        else if (GLOB) { p[8 * s + r] = (t == 0) ? 0 : -(sc.o + ext * t); f[8 * s + r] = kMinusInf; }     // global.h:63-71
-        else { p[8 * s + r] = 0; f[8 * s + r] = kMinusInf; }                                              // free left column (:114-121)
-        gl[8 * s + r] = -oe;
+        L.tbl[8 * s + r] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
+        const int t = row0 + 8 * s + r;
+        if (LOCALA) { L.p[8 * s + r] = 0; L.f[8 * s + r] = 0; }
+        else if (GLOB) { L.p[8 * s + r] = (t == 0) ? 0 : -(sc.o + ext * t); L.f[8 * s + r] = kMinusInf; }     // global.h:63-71
+        else { L.p[8 * s + r] = 0; L.f[8 * s + r] = kMinusInf; }                                              // free left column (:114-121)
+        L.gl[8 * s + r] = -oe;
       }
+      L.best[s] = LOCALA ? 0 : kMinusInf; L.bpos[s] = 0;
     }
-    const uint32_t ntab = (uint32_t)sc.nscore & 0xFFu;          // query N under the LOCAL rule: same score in every row
+    L.h_bot = 0; L.e_bot = 0; L.sel_cur = 0;
 
-    // ---- tracking state ----
-    int best[SR], bpos[SR];
-#pragma unroll
-    for (int s = 0; s < SR; s++) { best[s] = LOCALA ? 0 : kMinusInf; bpos[s] = SEMI ? ((w.pass == 0) ? qlen : 0) : 0; }
+    const uint4* bnd_in = w.bnd + (uint64_t)((blk + 1) & 1) * w.bnd_stride + w.qoff[pair];
+    uint4* bnd_out = w.bnd + (uint64_t)(blk & 1) * w.bnd_stride + w.qoff[pair];
+    const uint32_t tag_in = w.tag_base + blk - 1, tag_out = w.tag_base + blk;
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    if (blk != 0 && lane < ncol) pre = ld_bnd(bnd_in + lane);
 
-    const uint2* bnd_in = w.bnd + (uint64_t)((blk + 1) & 1) * w.bnd_stride + w.qoff[pair];
-    uint2* bnd_out = w.bnd + (uint64_t)(blk & 1) * w.bnd_stride + w.qoff[pair];
-    const uint32_t* prog_in = w.prog + (T - 1);
-    uint32_t* prog_out = w.prog + T;
-
-    int h_bot = 0, e_bot = 0; uint32_t sel_cur = 0;
     const int nsteps = ncol + 31;
+    bool exo_prev = false, exo_cur = false;
     for (int k0 = 0; k0 < nsteps; k0 += 32) {
-      // ---- chunk prologue: top boundary and selectors of columns [k0, k0 + 32) ----
+      // ---- chunk prologue: top boundary and selectors of columns [k0, k0 + 32) into the ring ----
       if (k0 < ncol) {
         const int c = k0 + lane;
         uint4 v = make_uint4(0, 0, 0, 0);
         if (blk == 0) {
           if (c < ncol) {
-            if (LOCALA) { v.x = 0; v.y = 0; }
-            else if (GLOB) { v.x = (uint32_t)(c == 0 ? 0 : -(sc.o + ext * c)); v.y = (uint32_t)kMinusInf; }      // global.h:57-60
-            else {
+            if (GLOB) { v.x = (uint32_t)(c == 0 ? 0 : -(sc.o + ext * c)); v.y = (uint32_t)kMinusInf; }            // global.h:57-60
+            else if (SEMI) {
               // semi-global hands E over as the first row's own E(0,c) = max(H(-1,c) - oe, E(-1,c) - e)
-              const int htop = top_zero ? 0 : (c == 0 ? 0 : -(sc.o + ext * c));                                  // :87-99
+              const int htop = top_zero ? 0 : (c == 0 ? 0 : -(sc.o + ext * c));                                   // :87-99
               const int etop = top_zero ? 0 : kMinusInf;
               v.x = (uint32_t)htop; v.y = (uint32_t)max(htop - oe, etop - ext);
             }
           }
         } else {
-          const uint32_t need = (uint32_t)min(k0 + 32, ncol);
-          if (lane == 0) { while (ld_acquire_u32(prog_in) < need) __nanosleep(40); }
-          __syncwarp();
-          if (c < ncol) { const uint2 t2 = __ldcg(bnd_in + c); v.x = t2.x; v.y = t2.y; }
+          // the producer's entries validate themselves: (H, tag) (E, tag); re-read until the whole chunk is there
+          bool ok = (c >= ncol) || (pre.y == tag_in && pre.w == tag_in);
+          while (!__all_sync(0xFFFFFFFFu, ok)) {
+            __nanosleep(20);
+            if (!ok) { pre = ld_bnd(bnd_in + c); ok = (pre.y == tag_in && pre.w == tag_in); }
+          }
+          v.x = pre.x; v.y = pre.z;
+          if (c + 32 < ncol) pre = ld_bnd(bnd_in + c + 32);      // prefetch the next chunk a whole chunk ahead
         }
+        uint32_t selv = 0x8880u;
         if (c < ncol) {
           const uint32_t qword = wave_qword(w, g, qw, qlen, c >> 3);
           const uint32_t qc = nib(qword, c & 7);
           const uint32_t idx = base_idx(qc);
-          if (idx < 4) v.z = idx * 0x1111u + 0x8880u;
-          else if (!GLOB && qc == sc.nval) v.z = 0xCCC4u;       // byte 4 = ntab
-          else v.z = kWaveExotic | (qc << 20);
+          if (idx < 4) selv = idx * 0x1111u + 0x8880u;
+          else if (!GLOB && qc == sc.nval) selv = 0xCCC4u;      // PRMT byte 4 = ntab
+          else selv = kWaveExotic | (qc << 20);
         }
+        exo_prev = exo_cur;
+        exo_cur = __any_sync(0xFFFFFFFFu, (selv & kWaveExotic) != 0);
         __syncwarp();
-        sin[lane] = v;
+        sin[lane] = make_uint2(v.x, v.y);
+        ssel[c & 63] = selv;
         __syncwarp();
-      }
+      } else { exo_prev = exo_cur; exo_cur = false; }
       const int kend = min(k0 + 32, nsteps);
-      for (int k = k0; k < kend; k++) {
-        // ---- receive (H, E) of the row above and the column's selector from the lane above ----
-        int h_in = __shfl_up_sync(0xFFFFFFFFu, h_bot, 1);
-        int e_in = __shfl_up_sync(0xFFFFFFFFu, e_bot, 1);
-        uint32_t sel = __shfl_up_sync(0xFFFFFFFFu, sel_cur, 1);
-        if (lane == 0) { const uint4 t4 = sin[k & 31]; h_in = (int)t4.x; e_in = (int)t4.y; sel = t4.z; }
-        const int c = k - lane;
-        if (c >= 0 && c < ncol) {
-          sel_cur = sel;
-          int sv[ROWS];
-          if (sel & kWaveExotic) {
-            const uint32_t qc = (sel >> 20) & 15u;
-#pragma unroll
-            for (int s = 0; s < SR; s++)
-#pragma unroll
-              for (int r = 0; r < 8; r++) sv[8 * s + r] = score_general(sc, qc, nib(tword[s], r));
-          } else {
-#pragma unroll
-            for (int r = 0; r < ROWS; r++) sv[r] = (int)prmt(tbl[r], ntab, sel);
-          }
-          int up = h_in, e = e_in;
-          int hh[ROWS];
-#pragma unroll
-          for (int r = 0; r < ROWS; r++) {
-            const int d = p[r] + sv[r];
-            int h;
-            if (SEMI) {
-              f[r] = __viaddmax_s32(f[r], -ext, gl[r]);               // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
-              const int m = max(d, f[r]);
-              h = max(m, e);
-              e = __viaddmax_s32(e, -ext, m - oe);                    // E(t+1,q) = max(max(D,F) - oe, E - e)  (oe >= e)
-              gl[r] = h - oe;
-            } else {
-              h = LOCALA ? __vimax3_s32_relu(d, f[r], e) : __vimax3_s32(d, f[r], e);
-              const int dm = d - oe;
-              f[r] = __viaddmax_s32(f[r], -ext, dm);
-              e = __viaddmax_s32(e, -ext, dm);
-            }
-            hh[r] = h; p[r] = up; up = h;
-          }
-          h_bot = up; e_bot = e;
-          // ---- tracking ----
-          if (LOCALA) {
-#pragma unroll
-            for (int s = 0; s < SR; s++) {
-              const int cm = max(__vimax3_s32(hh[8 * s], hh[8 * s + 1], hh[8 * s + 2]),
-                                 __vimax3_s32(__vimax3_s32(hh[8 * s + 3], hh[8 * s + 4], hh[8 * s + 5]), hh[8 * s + 6], hh[8 * s + 7]));
-              if (cm > best[s]) {
-                int rr = 7;
-#pragma unroll
-                for (int r = 6; r >= 0; r--) rr = (hh[8 * s + r] == cm) ? r : rr;
-                best[s] = cm; bpos[s] = (c << 3) | rr;
-              }
-            }
-          } else if (c == qlen - 1) {
-            if (SEMI) {
-#pragma unroll
-              for (int s = 0; s < SR; s++)
-#pragma unroll
-                for (int r = 0; r < 8; r++) {
-                  const int t = 8 * (g.strip0 + lstrip + s) + r;
-                  if (t < tlen && hh[8 * s + r] > best[s]) { best[s] = hh[8 * s + r]; bpos[s] = t; }
-                }
-            } else {
-              const int t_last = tlen - 1;
-#pragma unroll
-              for (int s = 0; s < SR; s++)
-                if ((t_last >> 3) == lstrip + s) {
-                  int v = hh[8 * s];
-#pragma unroll
-                  for (int r = 1; r < 8; r++) v = ((t_last & 7) == r) ? hh[8 * s + r] : v;
-                  a.score[pair] = v;                                  // H(ref_len-1, read_len-1)  (global.h:285-299)
-                }
-            }
-          }
-          if (lane == 31) sout[c & 31] = make_uint2((uint32_t)h_bot, (uint32_t)e_bot);
-        }
-        // ---- publish the bottom boundary 32 columns at a time ----
-        const int c31 = k - 31;
-        if (!last_blk && c31 >= 0 && (((c31 & 31) == 31) || c31 == ncol - 1)) {
-          __syncwarp();
-          const int cb = (c31 & ~31) + lane;
-          if (cb <= c31) __stcg(bnd_out + cb, sout[lane]);
-          __syncwarp();
-          if (lane == 0) { __threadfence(); st_release_u32(prog_out, (uint32_t)(c31 + 1)); }
-        }
+      int32_t* sp = a.score + pair;
+      if (exo_prev || exo_cur) wave_steps<ALGO, SR, false, true>(L, sc, ntab, sin, ssel, sout, k0, kend, ncol, lane, qlen, tlen, row0, lstrip, sp);
+      else if (k0 >= 32 && k0 + 32 < ncol) wave_steps<ALGO, SR, true, false>(L, sc, ntab, sin, ssel, sout, k0, kend, ncol, lane, qlen, tlen, row0, lstrip, sp);
+      else wave_steps<ALGO, SR, false, false>(L, sc, ntab, sin, ssel, sout, k0, kend, ncol, lane, qlen, tlen, row0, lstrip, sp);
+      // ---- lane 31 finished columns k0-31 .. kend-32 during this chunk: hand them to the next row-block ----
+      if (!last_blk) {
+        __syncwarp();
+        const int cb = k0 - 31 + lane;
+        if (cb >= 0 && cb < ncol && k0 + lane < kend) { const uint2 o = sout[lane]; st_bnd(bnd_out + cb, make_uint4(o.x, tag_out, o.y, tag_out)); }
+        __syncwarp();
       }
     }
     // ---- per-strip candidates, then the last block of the pair folds them ----
@@ -344,7 +383,11 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
       int2* cand = w.cand + w.soff[pair];
 #pragma unroll
       for (int s = 0; s < SR; s++)
-        if (lstrip + s < g.nstrips) __stcg(&cand[lstrip + s], make_int2(best[s], bpos[s]));
+        if (lstrip + s < g.nstrips) {
+          int bp = L.bpos[s];
+          if (SEMI && L.best[s] == kMinusInf) bp = 0;
+          __stcg(&cand[lstrip + s], make_int2(L.best[s], bp));
+        }
       __syncwarp();
       uint32_t old = 0;
       if (lane == 0) { __threadfence(); old = atomicAdd(w.done + pair, 1u); }
@@ -358,9 +401,10 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
 struct WaveScratch {
   uint64_t* qoff = nullptr; uint64_t* soff = nullptr; size_t n_cap = 0;
   uint64_t* h_off = nullptr; size_t h_cap = 0;                    // pinned staging: qoff[n] then soff[n]
-  uint2* bnd = nullptr; size_t bnd_cap = 0;
+  uint4* bnd = nullptr; size_t bnd_cap = 0;
+  uint32_t next_tag = 1;                                          // boundary tags handed out so far (never reused while bnd lives)
   int2* cand = nullptr; size_t cand_cap = 0;
-  uint32_t* prog = nullptr; size_t prog_cap = 0;                  // prog[...], then done[n], then ticket
+  uint32_t* prog = nullptr; size_t prog_cap = 0;                  // done[n], then the ticket counter
   void release() {
     if (qoff) cudaFree(qoff);
     if (h_off) cudaFreeHost(h_off);
@@ -408,24 +452,33 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
     ws.soff = ws.qoff + n; ws.n_cap = n;
   }
   ws.soff = ws.qoff + ws.n_cap;
-  uint64_t qs = 0, ss = 0;
+  uint64_t qs = 0, ss = 0, tasks1 = 0, tasks2 = 0;
   for (size_t i = 0; i < n; i++) {
     ws.h_off[i] = qs; ws.h_off[n + i] = ss;
+    const uint64_t tr = ((uint64_t)h_tlens[i] + 7u) >> 3;
     qs += ((uint64_t)h_qlens[i] + 7u) & ~7ull;
-    ss += ((uint64_t)h_tlens[i] + 7u) >> 3;
+    ss += tr;
+    tasks1 += (tr + 31) >> 5; tasks2 += (tr + 63) >> 6;
   }
-  // rows per lane: 16 when that still leaves every SM several row-blocks to work on, else 8
-  const uint64_t strips_total = ss;
-  const int SR = (strips_total / 64 >= (uint64_t)n_sm * 8) ? 2 : 1;
+  // Row-blocks of one pair form a pipeline that runs at the pace of its slowest stage, so the warp-workers must be
+  // spread evenly over the SM sub-partitions: 16 rows per lane as long as that still gives every sub-partition a task
+  // (fewer, longer pipeline stages), else 8; and never more workers than tasks (the hardware deals CTAs round-robin).
+  const int SR = (tasks2 * 4 >= (uint64_t)n_sm * 4 * 3) ? 2 : 1;
+  const uint64_t tasks = (SR == 2) ? tasks2 : tasks1;
   const uint32_t max_tr = (max_t + 7u) >> 3;
   const uint32_t maxblk = std::max<uint32_t>(1u, (max_tr + 32u * SR - 1) / (32u * SR));
   const size_t n_tickets = n * maxblk;
   if (n_tickets >= 0xFFFFFFF0ull) return -1;
-  if (ws.bnd_cap < 2 * qs) {
-    if (ws.bnd) cudaFree(ws.bnd);
-    ws.bnd = nullptr;
-    if (cudaMalloc(&ws.bnd, std::max<uint64_t>(2 * qs, 16) * sizeof(uint2)) != cudaSuccess) return -1;
-    ws.bnd_cap = 2 * qs;
+  const int npass = (start == START_POS) ? 2 : 1;
+  if (ws.bnd_cap < 2 * qs || (uint64_t)ws.next_tag + (uint64_t)npass * maxblk >= 0xFFFFFFF0ull) {
+    if (ws.bnd_cap < 2 * qs) {
+      if (ws.bnd) cudaFree(ws.bnd);
+      ws.bnd = nullptr;
+      if (cudaMalloc(&ws.bnd, std::max<uint64_t>(2 * qs, 16) * sizeof(uint4)) != cudaSuccess) return -1;
+      ws.bnd_cap = std::max<uint64_t>(2 * qs, 16);
+    }
+    cudaMemsetAsync(ws.bnd, 0, ws.bnd_cap * sizeof(uint4), str);   // tag 0 = never written
+    ws.next_tag = 1;
   }
   if (ws.cand_cap < ss) {
     if (ws.cand) cudaFree(ws.cand);
@@ -433,7 +486,7 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
     if (cudaMalloc(&ws.cand, std::max<uint64_t>(ss, 16) * sizeof(int2)) != cudaSuccess) return -1;
     ws.cand_cap = ss;
   }
-  const size_t prog_words = n_tickets + n + 1;
+  const size_t prog_words = n + 1;
   if (ws.prog_cap < prog_words) {
     if (ws.prog) cudaFree(ws.prog);
     ws.prog = nullptr;
@@ -443,13 +496,12 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   cudaMemcpyAsync(ws.qoff, ws.h_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, str);
   cudaMemcpyAsync(ws.soff, ws.h_off + n, n * sizeof(uint64_t), cudaMemcpyHostToDevice, str);
   WaveArgs wa; wa.a = a; wa.algo = algo; wa.maxblk = maxblk; wa.qoff = ws.qoff; wa.soff = ws.soff;
-  wa.bnd = ws.bnd; wa.bnd_stride = qs; wa.cand = ws.cand; wa.prog = ws.prog; wa.done = ws.prog + n_tickets; wa.ticket = ws.prog + n_tickets + n;
-  const int blocks = n_sm * 4;                                   // 16 resident warp-workers per SM
+  wa.bnd = ws.bnd; wa.bnd_stride = qs; wa.cand = ws.cand; wa.done = ws.prog; wa.ticket = ws.prog + n;
+  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_sm * 4, (tasks + kWaveWarps - 1) / kWaveWarps));   // <= 16 warp-workers per SM
   int launches = 0;
-  const int npass = (start == START_POS) ? 2 : 1;
   for (int pass = 0; pass < npass; pass++) {
     cudaMemsetAsync(ws.prog, 0, prog_words * sizeof(uint32_t), str);
-    wa.pass = pass;
+    wa.pass = pass; wa.tag_base = ws.next_tag; ws.next_tag += maxblk;
     if (SR == 2) wave_launch_kernel<2>(algo, blocks, wa, str); else wave_launch_kernel<1>(algo, blocks, wa, str);
     launches++;
   }
