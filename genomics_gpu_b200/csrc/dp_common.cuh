@@ -37,6 +37,7 @@ struct DpArgs {
   uint32_t* colstate; uint32_t col_stride; uint32_t col_rows;   // col_rows = columns available per pair
   // traceback
   uint4* tb; uint32_t tb_stride;         // tile t of pair p lives at tb[t * tb_stride + p]
+  int tb_banded;                         // 1: only the tile band of banded.h:35,83-85 is stored (see band_geom)
   uint8_t* cigar; uint32_t* n_cigar_ops;
   int head, tail, k_band;
 };
@@ -72,6 +73,17 @@ __device__ __forceinline__ uint32_t base_idx(uint32_t code) {
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
   uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
 }
+
+// Tile band of one pair (banded.h:35,83-85): strip i covers query words [lo(i), hi(i)).  The banded traceback matrix
+// keeps W = max width words per strip: tile of (strip i, word j, half) = (i * W + (j - lo(i))) * 2 + half.
+struct BandGeom { int kw, k_other, W; };
+__device__ __forceinline__ BandGeom band_geom(int QR, int TR, int k_band) {
+  BandGeom b; b.kw = k_band >> 3; b.k_other = TR - (QR - b.kw);
+  b.W = max(1, min(QR, b.kw + b.k_other - 1));
+  return b;
+}
+__device__ __forceinline__ int band_lo(const BandGeom& b, int i) { return max(0, i - b.k_other + 1); }
+__device__ __forceinline__ int band_hi(const BandGeom& b, int i, int QR) { return min(b.kw + i, QR); }
 
 __device__ __forceinline__ short2 u32_as_short2(uint32_t v) { short2 r; r.x = (short)(v & 0xFFFFu); r.y = (short)(v >> 16); return r; }
 __device__ __forceinline__ uint32_t pack_short2(int h, int e) { return ((uint32_t)h & 0xFFFFu) | ((uint32_t)e << 16); }

@@ -381,6 +381,65 @@ __device__ __forceinline__ void banded_forward(const DpArgs& a, const Sc& sc, co
 }
 
 // ------------------------------------------------------------------------------------------------
+// BANDED + WITH_TB (extension; the reference has no banded traceback -- SURVEY 8c, config 4): the LOCAL recurrence and
+// direction nibbles (local_kernel_template.h:19-60) over the tile band of banded.h:35,83-85, cells outside the band read
+// as 0 exactly as in the banded kernel; only the band's tiles are written (0.5 B per in-band cell).
+__device__ __forceinline__ void banded_tb_forward(const DpArgs& a, const Sc& sc, const PairCtx& p, uint32_t tid, int& best, int& best_q, int& best_t) {
+  const int QR = (int)p.QR, TR = (int)p.TR;
+  const BandGeom bg = band_geom(QR, TR, a.k_band);
+  best = 0; best_q = 0; best_t = 0;
+  for (int c = 0; c < QR * 8; c++) p.cs[(size_t)c * p.stride] = 0u;
+  for (int i = 0; i < TR; i++) {
+    int F[8], diag[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) { F[r] = 0; diag[r] = 0; }
+    StripRows R; load_rows(sc, p.tw[i], R);
+    const int lo = band_lo(bg, i), hi = band_hi(bg, i, QR);
+    int c = lo << 3;
+    for (int j = lo; j < hi; j++) {
+      const uint32_t rpac = p.qw[j];
+      uint4 dir = make_uint4(0, 0, 0, 0);
+      const size_t tile0 = ((size_t)i * bg.W + (j - lo)) * 2;
+#pragma unroll
+      for (int k = 0; k < 8; k++, c++) {
+        const uint32_t rb = nib(rpac, k);
+        const bool rn = (rb == sc.nval);
+        const short2 hd = u32_as_short2(p.cs[(size_t)c * p.stride]);
+        int up = hd.x, e = hd.y;
+        int colmax = 0; int hcol[8];
+        uint32_t dw = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+          int s = (rb == R.g[r]) ? sc.match : R.mm[r];
+          s = rn ? sc.nscore : s;
+          const int d = diag[r] + s;
+          const int h = __vimax3_s32_relu(d, F[r], e);
+          const int dm = d - sc.oe;
+          const uint32_t mx = (s >= 0) ? 0u : 1u;
+          const uint32_t code = (h == d) ? mx : ((h == F[r]) ? 3u : 2u);
+          const uint32_t fb = (dm > F[r] - sc.ext) ? 0u : 8u;
+          const uint32_t eb = (dm > e - sc.ext) ? 0u : 4u;
+          dw |= (code | fb | eb) << (28 - 4 * r);
+          F[r] = __viaddmax_s32(F[r], -sc.ext, dm);
+          e = __viaddmax_s32(e, -sc.ext, dm);
+          hcol[r] = h; colmax = max(colmax, h);
+          diag[r] = up; up = h;
+        }
+        p.cs[(size_t)c * p.stride] = pack_short2(up, e);
+        if ((k & 3) == 0) dir.x = dw; else if ((k & 3) == 1) dir.y = dw; else if ((k & 3) == 2) dir.z = dw; else dir.w = dw;
+        if ((k & 3) == 3) { a.tb[(tile0 + (k >> 2)) * a.tb_stride + tid] = dir; dir = make_uint4(0, 0, 0, 0); }
+        if (colmax > best) {
+          int rr = 7;
+#pragma unroll
+          for (int r = 6; r >= 0; r--) rr = (hcol[r] == colmax) ? r : rr;
+          best = colmax; best_q = c; best_t = 8 * i + rr;
+        }
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool make_ctx(const DpArgs& a, uint32_t tid, PairCtx& p) {
   if (tid >= (uint32_t)a.n) return false;
   p.qw = a.pq + (a.q_offs[tid] >> 3);
@@ -441,12 +500,13 @@ __global__ void __launch_bounds__(128) k_global_generic(const DpArgs a) {
   a.score[tid] = global_forward<START == START_TB>(a, sc, p, tid);
 }
 
+template <bool TB>
 __global__ void __launch_bounds__(128) k_banded_generic(const DpArgs a) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   PairCtx p; if (!make_ctx(a, tid, p)) return;
   const Sc sc = make_sc(a, false);
   int best, bq, bt;
-  banded_forward(a, sc, p, best, bq, bt);
+  if (TB) banded_tb_forward(a, sc, p, tid, best, bq, bt); else banded_forward(a, sc, p, best, bq, bt);
   a.score[tid] = best; a.q_end[tid] = bq; a.t_end[tid] = bt;
 }
 

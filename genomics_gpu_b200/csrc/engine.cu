@@ -379,7 +379,7 @@ void gasal_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len,
       s->device_res_second = gasal_res_new_device(s->device_cpy_second);
     }
     if (params->start_pos == WITH_TB && (params->algo == LOCAL || params->algo == GLOBAL))
-      alloc_tb(s, max_query_len_8, max_target_len_8, max_n_alns);
+      alloc_tb(s, max_query_len_8, max_target_len_8, max_n_alns);   // (BANDED + WITH_TB sizes its band matrix per batch)
     CHECKCUDAERROR(cudaStreamCreateWithFlags(&(s->str), cudaStreamNonBlocking));
     for (int e = 0; e < 4; e++) CHECKCUDAERROR(cudaEventCreate(&pv->ev[e]));
     s->is_free = 1;
@@ -521,10 +521,21 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   const uint32_t q8 = round8(shape.max_q), t8 = round8(shape.max_t);
   const bool second = params->secondBest != 0;
   const int start = params->start_pos;
-  const bool want_tb = (start == WITH_TB) && (params->algo == LOCAL || params->algo == GLOBAL);
+  const bool want_tb = (start == WITH_TB) && (params->algo == LOCAL || params->algo == GLOBAL || params->algo == BANDED);
 
   if (want_tb) {
-    alloc_tb(s, q8, t8, n);
+    if (params->algo == BANDED) {
+      // band matrix: TR strips x W words x 2 tiles, W = widest strip of any pair in the batch (dp_common.cuh band_geom)
+      const int qr_max = (int)(q8 >> 3), qr_min = (int)((shape.min_q + 7) >> 3), tr_max = (int)(t8 >> 3), kw = params->k_band >> 3;
+      const int w_max = std::max(1, std::min(qr_max, kw + (tr_max - (qr_min - kw)) - 1));
+      const uint64_t tiles = (uint64_t)tr_max * (uint64_t)w_max * 2 + 2;
+      if (tiles * n > s->packed_tb_matrix_size) {
+        if (s->packed_tb_matrices) CHECKCUDAERROR(cudaFree(s->packed_tb_matrices));
+        s->packed_tb_matrix_size = tiles * n;
+        CHECKCUDAERROR(cudaMalloc(&(s->packed_tb_matrices), s->packed_tb_matrix_size * sizeof(uint4)));
+      }
+      a.tb_banded = 1;
+    } else alloc_tb(s, q8, t8, n);
     a.tb = s->packed_tb_matrices; a.tb_stride = n;
     if (pv->cigar_bytes < q_bytes) { dev_realloc(&pv->d_cigar, q_bytes); pv->cigar_bytes = q_bytes; }
     if (pv->n_cigar_cap < n) { dev_realloc(&pv->d_n_cigar_ops, n); pv->n_cigar_cap = n; }
@@ -576,7 +587,10 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
       if (start == WITH_TB) { k_get_tb<false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }   // gasal_align.h:60-68
       break;
     case BANDED:
-      k_banded_generic<<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
+      if (start == WITH_TB) {
+        k_banded_generic<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
+        k_get_tb<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
+      } else { k_banded_generic<false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }
       break;
     default:
       fprintf(stderr, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo);

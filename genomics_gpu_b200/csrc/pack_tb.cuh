@@ -101,15 +101,26 @@ __global__ void __launch_bounds__(128) k_get_tb(const DpArgs a) {
   else { i = (int)tlen; j = (int)qlen; }
   const int q8 = (int)(n_words(qlen) * 8);
   const int oe = a.gap_open + a.gap_extend;
+  const BandGeom bg = band_geom(q8 >> 3, (int)n_words(tlen), a.k_band);   // used when only the tile band is stored
   uint8_t* out = a.cigar + a.q_offs[tid];
   uint32_t prev_op = 0, op_fill = 0;
   int n_ops = 0, count = 0, op_select = 3, op_shift = 0, prev_tile = -1;
   uint4 tile = make_uint4(0, 0, 0, 0);
   while (i >= 0 && j >= 0) {
-    const int cell = (((i >> 3) * q8) << 3) + (j << 3) + (i & 7);
-    const int tile_no = cell >> 5;
+    int tile_no, in_tile;
+    if (IS_LOCAL && a.tb_banded) {
+      const int strip = i >> 3, word = j >> 3, lo = band_lo(bg, strip);
+      in_tile = ((j & 3) << 3) + (i & 7);
+      if (word < lo || word >= band_hi(bg, strip, q8 >> 3)) {
+        // outside the stored band (only reachable from a score-0 end cell or through quirk Q14): reads as an all-zero tile
+        tile_no = -2; if (prev_tile != -2) { tile = make_uint4(0, 0, 0, 0); prev_tile = -2; }
+      } else tile_no = ((strip * bg.W + (word - lo)) << 1) + ((j & 7) >> 2);
+    } else {
+      const int cell = (((i >> 3) * q8) << 3) + (j << 3) + (i & 7);
+      tile_no = cell >> 5;
+      in_tile = cell - (tile_no << 5);
+    }
     if (tile_no != prev_tile) { tile = a.tb[(size_t)tile_no * a.tb_stride + tid]; prev_tile = tile_no; }
-    const int in_tile = cell - (tile_no << 5);
     const int reg_no = in_tile >> 3, cell_in_reg = in_tile & 7;
     const uint32_t reg = reg_no == 0 ? tile.x : (reg_no == 1 ? tile.y : (reg_no == 2 ? tile.z : tile.w));
     const uint32_t cell_op = (reg >> (28 - (cell_in_reg << 2))) & 15u;

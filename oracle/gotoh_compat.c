@@ -444,6 +444,54 @@ static void banded_one(const gc_scoring_t *sc, const uint32_t *qw, const uint32_
 }
 
 /* ------------------------------------------------------------------------------------------ */
+/* BANDED + WITH_TB (an EXTENSION: the reference has no banded traceback).  */
+/* Definition: the LOCAL recurrence and direction nibbles (local_kernel_template.h:19-60) computed only */
+/* inside the tile band of banded.h:35,83-85; cells outside the band read as 0, exactly as in the      */
+/* banded kernel.  Wherever the band does not cut the optimal alignment this equals the reference's     */
+/* LOCAL WITH_TB result (tests pin it that way).  The oracle keeps the full-matrix tile layout so the   */
+/* walker below is shared; the engine stores only the band.                                             */
+static void banded_tb_one(const gc_scoring_t *sc, const uint32_t *qw, const uint32_t *tw, uint32_t qlen, uint32_t tlen,
+                          int32_t k_band, colstate_t *cs, gc_uint4 *tb, uint64_t n_tasks, uint64_t tid, gc_result_t *out)
+{
+    const int32_t ext = sc->gap_extend, oe = sc->gap_open + ext;
+    const int32_t QR = (int32_t)n_words(qlen), TR = (int32_t)n_words(tlen);
+    const int32_t kw = k_band >> 3;
+    const int32_t k_other = TR - (QR - kw);
+    int32_t best = 0, prev_best = 0, bx = 0, by = 0;
+    for (int32_t c = 0; c < QR * 8; c++) { cs[c].h = 0; cs[c].e = 0; }
+    for (int32_t i = 0; i < TR; i++) {
+        int32_t F[8], diag[8];
+        for (int r = 0; r < 8; r++) { F[r] = 0; diag[r] = 0; }
+        const uint32_t gpac = tw[i];
+        int32_t c = imax(0, i - k_other + 1) << 3;
+        const int32_t last_tile = imin(kw + i, QR);
+        for (int32_t j = c >> 3; j < last_tile; j++) {
+            const uint32_t rpac = qw[j];
+            for (int k = 0; k < 8; k++, c++) {
+                const uint32_t rb = nib(rpac, k);
+                int32_t up = cs[c].h, e = cs[c].e;
+                uint32_t dirword = 0;
+                for (int r = 0; r < 8; r++) {
+                    const int32_t s = sub_local(sc, rb, nib(gpac, r));
+                    const int32_t d = diag[r] + s;
+                    int32_t h = imax(imax(imax(d, F[r]), e), 0);
+                    dirword |= tb_nibble(d, diag[r], h, F[r], e, oe, ext) << (28 - 4 * r);
+                    F[r] = imax(d - oe, F[r] - ext);
+                    e = imax(d - oe, e - ext);
+                    if (best < h) { by = 8 * i + r; best = h; }
+                    diag[r] = up; up = h;
+                }
+                cs[c].h = (int16_t)up; cs[c].e = (int16_t)e;
+                tb_store(tb, ((uint64_t)i * QR + j) * 2 + (k >> 2), n_tasks, tid, k & 3, dirword);
+                if (prev_best < best) bx = c;
+                prev_best = imax(best, prev_best);
+            }
+        }
+    }
+    out->score = best; out->q_end = bx; out->t_end = by;
+}
+
+/* ------------------------------------------------------------------------------------------ */
 /* Traceback walker: kernels/get_tb.h:4-149.  Emits (count<<2)|op bytes in REVERSE alignment   */
 /* order; op 0=M 1=X 2=D 3=I; runs capped at 63.  Returns n_ops; LOCAL also yields the starts. */
 static uint32_t get_tb_one(const gc_scoring_t *sc, int is_local, const gc_uint4 *tb, uint64_t n_tasks, uint64_t tid,
@@ -576,7 +624,7 @@ int gc_align_batch(const gc_scoring_t *sc, const gc_params_t *p,
     uint32_t mql = p->max_query_len;
     if (mql == 0) { mql = max_q8 > max_t8 ? max_q8 : max_t8; mql += 16; }
     gc_uint4 *tb = NULL;
-    if (p->start_mode == GC_WITH_TB && (p->algo == GC_LOCAL || p->algo == GC_GLOBAL)) {
+    if (p->start_mode == GC_WITH_TB && (p->algo == GC_LOCAL || p->algo == GC_GLOBAL || p->algo == GC_BANDED)) {
         uint64_t tiles = ((uint64_t)max_q8 * (max_t8 + 8) + 31) / 32 + 2;                 /* ctors.cpp:112-115 (+slack for Q5 reads) */
         tb = (gc_uint4 *)calloc(tiles * n, sizeof(gc_uint4));
         if (!tb) return -1;
@@ -611,7 +659,8 @@ int gc_align_batch(const gc_scoring_t *sc, const gc_params_t *p,
                     global_one(sc, qw, tw, q_lens[i], t_lens[i], p->start_mode, cs, tb, n, i, &r);
                     break;
                 case GC_BANDED:
-                    banded_one(sc, qw, tw, q_lens[i], t_lens[i], p->k_band, cs, &r);
+                    if (p->start_mode == GC_WITH_TB) banded_tb_one(sc, qw, tw, q_lens[i], t_lens[i], p->k_band, cs, tb, n, i, &r);
+                    else banded_one(sc, qw, tw, q_lens[i], t_lens[i], p->k_band, cs, &r);
                     break;
                 case GC_KSW:
                     ksw_one(sc, qw, tw, q_lens[i], t_lens[i], seed_scores ? seed_scores[i] : 0, eh_h, eh_e, mql + 16, &r);
@@ -619,7 +668,7 @@ int gc_align_batch(const gc_scoring_t *sc, const gc_params_t *p,
                 default: break;
                 }
                 if (tb && res->cigar && res->n_cigar_ops)
-                    res->n_cigar_ops[i] = get_tb_one(sc, p->algo == GC_LOCAL, tb, n, i, q_lens[i], t_lens[i], &r, res->cigar + q_offs[i]);
+                    res->n_cigar_ops[i] = get_tb_one(sc, p->algo != GC_GLOBAL, tb, n, i, q_lens[i], t_lens[i], &r, res->cigar + q_offs[i]);
                 if (res->aln_score) res->aln_score[i] = r.score;
                 if (res->query_batch_end) res->query_batch_end[i] = r.q_end;
                 if (res->target_batch_end) res->target_batch_end[i] = r.t_end;

@@ -142,3 +142,16 @@ def test_revcomp_gpu_semantics(oracle):
     assert rq.tolist() == [int("EEEEEE74", 16), int("47311374", 16)]
     want_t = oracle.pack(np.frombuffer((b"AAAAAAAAACCCCCCCCCGTNNNN")[::-1], dtype=np.uint8))
     assert np.array_equal(rt, want_t)
+
+
+def test_banded_tb_extension_with_full_band_equals_local_tb(oracle):
+    """oracle-only pin of the BANDED + WITH_TB extension: with a band wider than the matrix it IS the LOCAL WITH_TB restatement
+    (which tests above pin to the reference's own kernels)"""
+    from genomics_gpu_b200 import synth
+    b = synth.random_ragged_pairs(300, 9, 200, 9, 300, seed=321, n_frac=0.01)
+    pq, pt = oracle.pack(b.q_bytes), oracle.pack(b.t_bytes)
+    loc = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, algo=po.LOCAL, start=po.WITH_TB)
+    ban = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, algo=po.BANDED, start=po.WITH_TB, k_band=8192)
+    for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start", "n_cigar_ops"):
+        assert np.array_equal(loc[k], ban[k]), k
+    assert np.array_equal(loc["cigar"], ban["cigar"])
