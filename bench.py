@@ -194,6 +194,38 @@ def run_reference(args, rank, world):
 
 
 # ---------------------------------------------------------------------------------------------------------
+def run_extras(local_rank: int, n_fwd: int):
+    """Device-timed GCUPS of the other BASELINE.json configurations (parity-test cases, reported for context only; bounded
+    samples): forward-only kernels on the C2 shape, C3 (global 16k x 16k, wavefront kernel), C4 (banded k=64 + CIGAR),
+    C5 (mixed 100 bp - 10 kb, local WITH_START)."""
+    from genomics_gpu_b200 import capi, synth
+    from genomics_gpu_b200.aligner import Aligner
+    out = {}
+
+    def timed(batch, reps=3, **kw):
+        mq = int(batch.q_lens.max()) + 7; mt = int(batch.t_lens.max()) + 7
+        with Aligner(max_query_len=mq, max_target_len=mt, max_n_alns=batch.n, n_streams=1, scoring=SCORING, device=local_rank, **kw) as al:
+            best = None
+            for _ in range(reps):
+                al.align(batch)
+                ms = al.last_ms(0)
+                best = ms if best is None or ms[2] < best[2] else best
+            return {"kernel": al.kernel_name(0), "pairs": batch.n, "dp_ms": best[2], "gcups_dp": batch.cells / (best[2] * 1e-3) / 1e9}
+
+    try:
+        b2 = synth.config2(n_fwd, seed=2)
+        out["C2_forward_only"] = {"local": timed(b2, algo=capi.LOCAL), "semi_global": timed(b2, algo=capi.SEMI_GLOBAL), "global": timed(b2, algo=capi.GLOBAL)}
+        out["C3_global_16k_x_16k"] = {"n32": timed(synth.config3(32, 16384, seed=3), algo=capi.GLOBAL), "n16": timed(synth.config3(16, 16384, seed=3), algo=capi.GLOBAL)}
+        b4 = synth.config4(n_fwd, seed=4)
+        out["C4_banded_k64_250bp"] = {"score_end": timed(b4, algo=capi.BANDED, k_band=64), "with_cigar": timed(b4, algo=capi.BANDED, k_band=64, start=capi.WITH_TB)}
+        out["C5_mixed_100bp_10kb_local_with_start"] = timed(synth.config5(4000, seed=5), algo=capi.LOCAL, start=capi.WITH_START)
+        out["note"] = "gcups_dp counts q_len x t_len forward cells per pair (banded and start passes add time, not cells); device-timed DP stage, best of 3"
+    except Exception as e:  # context only: never break the bench line
+        out["error"] = str(e)[:200]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
     import torch
     if not torch.cuda.is_available():
@@ -334,6 +366,7 @@ def run_ours(args, rank, world, local_rank):
     cpu_threads = os.cpu_count() or 1
     cpu_val, cpu_kind, cpu_n, cpu_dt = cpu_baseline_run(batch, args.cpu_pairs, cpu_threads)
     refgpu = ref_gpu_baseline(batch, args.refgpu_pairs) if args.refgpu_pairs > 0 else {"unavailable": "disabled"}
+    extras = run_extras(local_rank, 262_144) if args.extras else {"skipped": True}
 
     line = {
         "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -355,12 +388,15 @@ def run_ours(args, rank, world, local_rank):
         "roofline": {"bound": "dpx-integer-pipe", "kernel": f"{top} DP ({kernel_names[top]})", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
                      "frac": achieved / peak_gcups, "traffic": ncu_traffic(top),
                      "peak_def": f"R / {ops_per_cell:g} ops per cell, R = {R:.4g} lane-ops/s, {R_src}",
-                     "note": "compute-bound integer DP (SURVEY 8d): compulsory HBM traffic is < 0.01 B/cell; the HBM-bound stage is pack, below"},
+                     "note": "compute-bound integer DP (SURVEY 8d): compulsory HBM traffic is < 0.01 B/cell; the HBM-bound stage is pack, below. "
+                             "achieved counts FORWARD cells only while the launch also runs the start pass (about 25-35 % more cells); "
+                             "other_configs.C2_forward_only has the same kernels without it"},
         "roofline_pack": {"bound": "hbm", "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pack_gbs / hbm_peak,
                           "traffic": ncu_traffic("pack"), "bytes_def": "1.5 B per base (1 read + 0.5 written)"},
         "cpu_baseline": {"value": cpu_val, "unit": "GCUPS", "cores": cpu_threads, "kind": cpu_kind,
                          "sample": f"first {cpu_n} pairs of the same workload, both modes, {cpu_dt:.1f} s"},
         "ref_gpu_baseline": refgpu,
+        "other_configs": extras,
     }
     print(json.dumps(line))
 
@@ -373,8 +409,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per mode")
     ap.add_argument("--e2e-chunks", type=int, default=8)
-    ap.add_argument("--cpu-pairs", type=int, default=60_000, help="bounded sample for the cpu_baseline leg")
-    ap.add_argument("--ref-pairs", type=int, default=60_000, help="pairs per step of the --impl reference arm")
+    ap.add_argument("--cpu-pairs", type=int, default=600_000, help="bounded sample for the cpu_baseline leg (~15 s on 16 cores)")
+    ap.add_argument("--ref-pairs", type=int, default=200_000, help="pairs per step of the --impl reference arm (~5 s per step on 16 cores)")
+    ap.add_argument("--extras", type=int, default=1, help="also time the other BASELINE.json configurations on rank 0 (context only)")
     ap.add_argument("--refgpu-pairs", type=int, default=262_144, help="sample for the reference-CUDA-build baseline on the same GPU (0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
