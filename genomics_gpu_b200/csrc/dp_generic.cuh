@@ -440,6 +440,66 @@ __device__ __forceinline__ void banded_tb_forward(const DpArgs& a, const Sc& sc,
 }
 
 // ------------------------------------------------------------------------------------------------
+// KSW seed extension (ksw_kernel_template.h:46-199 = BWA's ksw_extend with z-drop off): row-major sweep with the adaptive
+// [beg, end) column window, initial score h0 from seed_scores, the 5-point clipping rule at the end.  One thread per
+// pair; the (H, E) row lives in the coalesced scratch as int32 pairs (the reference keeps eh_t eh[MAX_QUERY_LEN] per
+// thread in local memory and zeroes all of it).  Quirk kept: the query word count is (qlen >> 3) + 1, so when qlen is a
+// multiple of 8 the loop variable ends on j == qlen in EVERY row and the to-end score is always considered (:57,142-145).
+__device__ __forceinline__ void ksw_extend(const DpArgs& a, const Sc& sc, const PairCtx& p, uint32_t tid, int& o_score, int& o_qe, int& o_te) {
+  const int qlen = (int)p.qlen, tlen = (int)p.tlen, h0 = (int)a.seed_scores[tid];
+  const int e_del = sc.ext, e_ins = sc.ext, oe_del = sc.oe, oe_ins = sc.oe;
+  uint2* eh = (uint2*)p.cs;                                   // eh[j * stride] = (h, e)
+  const size_t st = p.stride;
+  for (int j = 0; j <= qlen + 1; j++) eh[(size_t)j * st] = make_uint2(0u, 0u);
+  { uint2 v = eh[0]; v.x = (uint32_t)h0; eh[0] = v; }
+  int prev = h0 > oe_ins ? h0 - oe_ins : 0;
+  { uint2 v = eh[st]; v.x = (uint32_t)prev; eh[st] = v; }
+  for (int j = 2; j <= qlen && prev > e_ins; ++j) { prev -= e_ins; uint2 v = eh[(size_t)j * st]; v.x = (uint32_t)prev; eh[(size_t)j * st] = v; }
+  int mx = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, beg = 0, end = qlen;
+  const int qt_last = qlen >> 3;                              // last query word the reference visits
+  bool stop = false;
+  for (int i = 0; i < tlen && !stop; i++) {
+    const uint32_t gbase = nib(p.tw[i >> 3], i & 7);
+    const bool gn = (gbase == sc.nval);
+    int f = 0, h1, m = 0, mj = -1;
+    if (beg == 0) { h1 = h0 - (sc.o + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
+    uint32_t rpac = 0;
+    for (int j = beg; j < end; j++) {
+      if ((j & 7) == 0 || j == beg) rpac = p.qw[j >> 3];
+      const uint32_t rbase = nib(rpac, j & 7);
+      const uint2 cell = eh[(size_t)j * st];
+      int M = (int)cell.x, e = (int)cell.y;
+      int s = (rbase == gbase) ? sc.match : sc.nmis;
+      s = (gn || rbase == sc.nval) ? sc.nscore : s;
+      M = M ? M + s : 0;                                      // separating H and M to disallow a cigar like "100M3I3D20M" (:126)
+      int h = M > e ? M : e; h = h > f ? h : f;
+      mj = m > h ? mj : j;
+      m = m > h ? m : h;
+      int t = M - oe_del; t = t > 0 ? t : 0; e -= e_del; e = e > t ? e : t;
+      eh[(size_t)j * st] = make_uint2((uint32_t)h1, (uint32_t)e);     // H(i,j-1) for the next row, E(i+1,j)
+      h1 = h;
+      t = M - oe_ins; t = t > 0 ? t : 0; f -= e_ins; f = f > t ? f : t;
+    }
+    eh[(size_t)end * st] = make_uint2((uint32_t)h1, 0u);
+    const int j_final = max(end, qt_last * 8);                // value of the reference's loop variable after the sweep
+    if (j_final == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+    if (m == 0) {
+      // `break` only leaves the reference's 8-row loop (:150): the sweep resumes with the next target word
+      i |= 7;
+      continue;
+    }
+    if (m > mx) { mx = m; max_i = i; max_j = mj; }
+    int j = beg;
+    for (; j < end; ++j) { const uint2 v = eh[(size_t)j * st]; if (v.x != 0u || v.y != 0u) break; }
+    beg = j;
+    for (j = end; j >= beg; --j) { const uint2 v = eh[(size_t)j * st]; if (v.x != 0u || v.y != 0u) break; }
+    end = j + 2 < qlen ? j + 2 : qlen;
+  }
+  if (gscore <= 0 || gscore <= mx - 5) { o_score = mx; o_qe = max_j + 1; o_te = max_i + 1; }    // PEN_CLIP5 (:22,189-198)
+  else { o_score = gscore; o_qe = qlen; o_te = max_ie + 1; }
+}
+
+// ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool make_ctx(const DpArgs& a, uint32_t tid, PairCtx& p) {
   if (tid >= (uint32_t)a.n) return false;
   p.qw = a.pq + (a.q_offs[tid] >> 3);
@@ -498,6 +558,16 @@ __global__ void __launch_bounds__(128) k_global_generic(const DpArgs a) {
   PairCtx p; if (!make_ctx(a, tid, p)) return;
   const Sc sc = make_sc(a, true);
   a.score[tid] = global_forward<START == START_TB>(a, sc, p, tid);
+}
+
+__global__ void __launch_bounds__(128) k_ksw_generic(const DpArgs a) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  PairCtx p; if (!make_ctx(a, tid, p)) return;
+  p.cs = a.colstate + 2 * (size_t)tid;                        // int32 pairs: two words per column entry
+  const Sc sc = make_sc(a, false);
+  int score, qe, te;
+  ksw_extend(a, sc, p, tid, score, qe, te);
+  a.score[tid] = score; a.q_end[tid] = qe; a.t_end[tid] = te;
 }
 
 template <bool TB>

@@ -563,7 +563,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
 
   // ---- general int32 kernels ----
   const uint32_t stride = (n + 31u) & ~31u;
-  const size_t need = (size_t)stride * std::max<uint32_t>(q8, 8);
+  const size_t need = (params->algo == KSW) ? 2 * (size_t)stride * (q8 + 16) : (size_t)stride * std::max<uint32_t>(q8, 8);
   if (pv->colstate_words < need) { dev_realloc(&pv->colstate, need); pv->colstate_words = need; }
   a.colstate = pv->colstate; a.col_stride = stride; a.col_rows = q8;
   const uint32_t BLOCKDIM = 128, N_BLOCKS = (n + BLOCKDIM - 1) / BLOCKDIM;
@@ -591,6 +591,9 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
         k_banded_generic<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
         k_get_tb<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
       } else { k_banded_generic<false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }
+      break;
+    case KSW:                                                                             // gasal_align.h:73-78
+      k_ksw_generic<<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
       break;
     default:
       fprintf(stderr, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo);

@@ -193,3 +193,42 @@ def test_multi_storage_round_robin(oracle):
     for lo, hi in chunks:
         sub_want = {k: want[k][lo:hi] for k in K5}
         assert_same(outs[lo], sub_want, K5, f"chunk {lo}:{hi}")
+
+
+@pytest.mark.parametrize("scoring", SCORINGS)
+def test_ksw_seed_extension(oracle, scoring):
+    """algo=KSW (BWA ksw_extend, ksw_kernel_template.h:46-199): h0 from host_seed_scores, adaptive beg/end window, clip rule.
+    Lengths include multiples of 8 (the reference's (qlen >> 3) + 1 word count makes the to-end score unconditional there)."""
+    b = synth.random_ragged_pairs(600, 8, 200, 8, 260, seed=95, n_frac=0.01)
+    rng = np.random.default_rng(7)
+    seeds = rng.integers(0, 60, size=b.n).astype(np.uint32)
+    seeds[::7] = 0
+    pq, pt = oracle.pack(b.q_bytes), oracle.pack(b.t_bytes)
+    want = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, algo=po.KSW, scoring=scoring, seed_scores=seeds, max_query_len=1024)
+    mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
+    with Aligner(algo=capi.KSW, scoring=scoring, max_query_len=mq, max_target_len=mt, max_n_alns=b.n, n_streams=1) as al:
+        got = al.align(b, seeds=seeds)
+    assert_same(got, want, K3, f"ksw {scoring}")
+
+
+def test_ksw_extension_from_matching_prefix(oracle):
+    """extensions that run to the end of the query (gscore branch) and ones that are clipped"""
+    rng = np.random.default_rng(3)
+    qs, ts, seeds = [], [], []
+    for k in range(300):
+        L = int(rng.integers(16, 150))
+        core = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L)
+        t = np.concatenate([core, rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=int(rng.integers(0, 40)))])
+        q = core.copy()
+        if k % 3 == 0:
+            q[L // 2:] = rng.choice(np.frombuffer(b"ACGT", dtype=np.uint8), size=L - L // 2)     # second half unrelated: clipped
+        qs.append(q.tobytes()); ts.append(t.tobytes()); seeds.append(int(rng.integers(10, 40)))
+    b = synth.batch_from_sequences(qs, ts)
+    seeds = np.asarray(seeds, dtype=np.uint32)
+    pq, pt = oracle.pack(b.q_bytes), oracle.pack(b.t_bytes)
+    want = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, algo=po.KSW, seed_scores=seeds, max_query_len=1024)
+    mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
+    with Aligner(algo=capi.KSW, max_query_len=mq, max_target_len=mt, max_n_alns=b.n, n_streams=1) as al:
+        got = al.align(b, seeds=seeds)
+    assert_same(got, want, K3, "ksw prefix extension")
+    assert (got["query_batch_end"] == b.q_lens.astype(np.int32)).sum() > 100      # the to-end branch was exercised
