@@ -53,7 +53,7 @@ def make_workload(n_pairs: int, seed: int):
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampled every 200 ms during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi sampled every 50 ms during the timed region (B200_PROFILING.md recipe)."""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -65,7 +65,7 @@ class ClockSampler:
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200", "-i", str(self.gpu)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -344,6 +344,11 @@ def run_ours(args, rank, world, local_rank):
     value = total_cells_per_step * args.steps / (dev_ms_max * 1e-3) / 1e9
     e2e_value = total_cells_per_step * e2e_steps / (e2e_ms_max * 1e-3) / 1e9
 
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        if rank != 0:
+            dist.destroy_process_group()
     if rank != 0:
         return
     # ---- roofline of the dominant DP kernel (by time in the step) ---------------------------------------------
@@ -398,7 +403,10 @@ def run_ours(args, rank, world, local_rank):
         "ref_gpu_baseline": refgpu,
         "other_configs": extras,
     }
-    print(json.dumps(line))
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
 
 
 def main():

@@ -48,7 +48,7 @@ void make_plan(const uint32_t* q_lens, const uint32_t* t_lens, uint64_t n, const
   if (!sc->keep_input_order)
     std::stable_sort(pl.order.begin(), pl.order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
   // 2. cut into batches; never mix pairs on different sides of the fast-path query limit
-  const uint32_t fast_q8 = 360;
+  const uint32_t fast_q8 = 352;   // == kFastMaxQ8 (dp_s16.cuh)
   pl.batch_start.push_back(0);
   uint64_t cells = 0, qb = 0, tb = 0; uint32_t cnt = 0, mq = 0, mt = 0;
   auto close = [&](uint64_t pos) {
@@ -61,7 +61,9 @@ void make_plan(const uint32_t* q_lens, const uint32_t* t_lens, uint64_t n, const
     const uint32_t i = pl.order[k];
     const uint64_t q8 = pad8(q_lens[i]), t8 = pad8(t_lens[i]);
     const bool crosses = cnt > 0 && ((pad8(mq) <= fast_q8) != (q8 <= fast_q8));
-    if (cnt >= max_pairs || qb + q8 > max_bytes || tb + t8 > max_bytes || qb + q8 > 0xFFFFFFF0ull || tb + t8 > 0xFFFFFFF0ull ||
+    // long pairs run on the wavefront kernel, whose boundary double buffer takes 32 B per query base of the batch
+    const bool wave_full = q8 > fast_q8 && qb + q8 > (64ull << 20);
+    if (cnt >= max_pairs || qb + q8 > max_bytes || tb + t8 > max_bytes || qb + q8 > 0xFFFFFFF0ull || tb + t8 > 0xFFFFFFF0ull || (cnt > 0 && wave_full) ||
         (cnt > 0 && cells + (uint64_t)q_lens[i] * t_lens[i] > max_cells) || crosses)
       close(k);
     cells += (uint64_t)q_lens[i] * t_lens[i]; qb += q8; tb += t8; cnt++;

@@ -31,7 +31,7 @@ def test_plan_is_a_permutation_and_respects_limits():
         assert int(cells[idx].sum()) == int(p["batch_cells"][b])
         assert idx.size == 1 or int(cells[idx].sum()) <= (1 << 33) + int(cells[idx].max())
         q8 = (q[idx] + 7) // 8 * 8
-        assert (q8 <= 360).all() or (q8 > 360).all(), "fast-path and general pairs must not share a batch"
+        assert (q8 <= 352).all() or (q8 > 352).all(), "fast-path and general pairs must not share a batch"
 
 
 def test_length_binning_sorts_by_shape():
