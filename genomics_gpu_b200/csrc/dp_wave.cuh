@@ -397,6 +397,199 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
   }
 }
 
+// =====================================================================================================
+// k_wave16: the same row-block pipeline with s16x2 lanes for LOCAL alignment (long reads whose scores fit 16 bits).
+// A lane owns a DOUBLE-strip: strip 2m in the low 16-bit halves of its registers, strip 2m+1 in the high halves, skewed by
+// one query column as in the inter-task fast path (low half on column k - 2*lane, high half one column behind), so the low
+// strip's bottom row reaches the high strip through registers and the high strip's bottom row reaches the next lane's low
+// strip by one packed __shfl_up_sync.  A row-block is 32 lanes x 16 rows = 512 target rows; per 16 cells a lane issues the
+// 8 packed recurrences of dp_s16.cuh (PRMT, 2 x VIADD.16x2, VIMNMX3.S16x2.RELU, 2 x VIADDMNMX.S16x2) -- half the
+// instructions per cell of the int32 wavefront kernel.  Halves that are before column 0 or past the last column keep
+// computing on benign selectors (score 0 / -1): with the 0 clamp that leaves their state equivalent to the initial one, so
+// the step body has no activity tests at all; only the (rare, divergent) record-an-improvement branch checks the column.
+struct Wave16Lane {
+  uint32_t twA, twB;              // packed target words of the low / high strip
+  uint32_t rowA[8], rowB[8];      // per-row substitution tables (dp_s16.cuh row_table layout)
+  uint32_t p[8], f[8];
+  uint32_t out_h, out_e;          // bottom (H, E) of both strips after the previous step
+  uint32_t prevsh;                // selector bits of the high half (the low half's previous column)
+  uint32_t vprev;                 // ring word of the previous step (exotic path)
+  uint32_t bestpk;                // running per-half maxima, packed (fast improvement test)
+  int bestL, bestH, bposL, bposH;
+};
+
+template <bool EXOTIC>
+__device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const uint2* sin, const uint32_t* ssel, uint2* sout,
+                                             int k0, int kend, int ncol, int lane, uint32_t neg_oe2, uint32_t neg_ext2) {
+  for (int k = k0; k < kend; k++) {
+    const uint2 top = sin[k & 31];
+    const uint32_t v = ssel[(k - 2 * lane) & 127];
+    uint32_t xh = __shfl_up_sync(0xFFFFFFFFu, L.out_h, 1);
+    uint32_t xe = __shfl_up_sync(0xFFFFFFFFu, L.out_e, 1);
+    if (lane == 0) { xh = top.x << 16; xe = top.y << 16; }
+    uint32_t up = prmt(xh, L.out_h, 0x5432);       // low half <- lane above, high strip; high half <- own low strip, previous step
+    uint32_t e = prmt(xe, L.out_e, 0x5432);
+    const uint32_t sel = (v & 0xFFu) | L.prevsh;
+    L.prevsh = (v & 0xFFu) * 256u + 0x4400u;
+    uint32_t hh[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t s2;
+      if (EXOTIC && ((v | L.vprev) & kWaveExotic)) {
+        const int sl = score_general(sc, (v >> 20) & 15u, nib(L.twA, r)), sh = score_general(sc, (L.vprev >> 20) & 15u, nib(L.twB, r));
+        s2 = ((uint32_t)sl & 0xFFFFu) | ((uint32_t)sh << 16);
+      } else s2 = prmt(L.rowA[r], L.rowB[r], sel);
+      const uint32_t d = __vadd2(L.p[r], s2);
+      const uint32_t dm = __vadd2(d, neg_oe2);
+      const uint32_t h = __vimax3_s16x2_relu(d, L.f[r], e);
+      L.f[r] = __viaddmax_s16x2(L.f[r], neg_ext2, dm);
+      e = __viaddmax_s16x2(e, neg_ext2, dm);
+      hh[r] = h; L.p[r] = up; up = h;
+    }
+    L.out_h = up; L.out_e = e;
+    L.vprev = v;
+    if (lane == 31) sout[k & 31] = make_uint2((uint32_t)(int)(short)(up >> 16), (uint32_t)(int)(short)(e >> 16));
+    // ---- arg-max: column maxima of both halves, then a rare divergent branch that resolves row and column ----
+    uint32_t cm = __vimax3_s16x2(hh[0], hh[1], hh[2]);
+    cm = __vimax3_s16x2(cm, hh[3], hh[4]);
+    cm = __vimax3_s16x2(cm, hh[5], hh[6]);
+    cm = __vmaxs2(cm, hh[7]);
+    const uint32_t nb = __vmaxs2(L.bestpk, cm);
+    if (nb != L.bestpk) {
+      L.bestpk = nb;
+      const int cL = k - 2 * lane, cH = cL - 1;
+      const int mL = (int)(short)(cm & 0xFFFFu), mH = (int)(short)(cm >> 16);
+      if (mL > L.bestL && cL >= 0 && cL < ncol) {
+        int rr = 7;
+#pragma unroll
+        for (int r = 6; r >= 0; r--) rr = ((int)(short)(hh[r] & 0xFFFFu) == mL) ? r : rr;
+        L.bestL = mL; L.bposL = (cL << 3) | rr;
+      }
+      if (mH > L.bestH && cH >= 0 && cH < ncol) {
+        int rr = 7;
+#pragma unroll
+        for (int r = 6; r >= 0; r--) rr = ((int)(short)(hh[r] >> 16) == mH) ? r : rr;
+        L.bestH = mH; L.bposH = (cH << 3) | rr;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kWaveWarps * 32) k_wave16_local(const WaveArgs w) {
+  __shared__ uint2 s_in[kWaveWarps][32];
+  __shared__ uint32_t s_sel[kWaveWarps][128];
+  __shared__ uint2 s_out[kWaveWarps][32];
+  const DpArgs& a = w.a;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint2* sin = s_in[wib]; uint32_t* ssel = s_sel[wib]; uint2* sout = s_out[wib];
+  const Sc sc = make_sc(a, false);
+  const uint32_t total = (uint32_t)a.n * w.maxblk;
+  const uint32_t neg_oe2 = (((uint32_t)(-sc.oe)) & 0xFFFFu) * 0x00010001u, neg_ext2 = (((uint32_t)(-sc.ext)) & 0xFFFFu) * 0x00010001u;
+
+  for (;;) {
+    uint32_t T = 0;
+    if (lane == 0) T = atomicAdd(w.ticket, 1u);
+    T = __shfl_sync(0xFFFFFFFFu, T, 0);
+    if (T >= total) break;
+    const uint32_t pair = T / w.maxblk, blk = T - pair * w.maxblk;
+    const WaveGeom g = wave_geometry(w, pair);
+    const int nblk = (g.nstrips + 63) / 64;
+    if ((int)blk >= nblk) {
+      if (blk == 0) wave_finalize<ALGO_LOCAL>(w, pair, g, lane);
+      continue;
+    }
+    const int qlen = (int)a.q_lens[pair], tlen = (int)a.t_lens[pair];
+    const uint32_t* qw = a.pq + (a.q_offs[pair] >> 3);
+    const uint32_t* tw = a.pt + (a.t_offs[pair] >> 3);
+    const int ncol = g.ncol;
+    const int lstrip = ((int)blk * 32 + lane) * 2;
+    const bool last_blk = ((int)blk == nblk - 1);
+
+    Wave16Lane L;
+    L.twA = (lstrip < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip) : 0u;
+    L.twB = (lstrip + 1 < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip + 1) : 0u;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t ta = 0, tb = 0;
+      const uint32_t ca = nib(L.twA, r), cb = nib(L.twB, r);
+      const uint32_t qcodes[4] = {1u, 3u, 7u, 4u};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        ta |= ((uint32_t)score_general(sc, qcodes[i], ca) & 0xFFu) << (8 * i);
+        tb |= ((uint32_t)score_general(sc, qcodes[i], cb) & 0xFFu) << (8 * i);
+      }
+      L.rowA[r] = ta; L.rowB[r] = tb; L.p[r] = 0; L.f[r] = 0;
+    }
+    L.out_h = 0; L.out_e = 0; L.prevsh = 0xCC00u; L.vprev = 0x88u; L.bestpk = 0; L.bestL = L.bestH = 0; L.bposL = L.bposH = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ssel[lane + 32 * i] = 0x88u;     // columns before 0 / after the end: score 0 or -1
+    __syncwarp();
+
+    const uint4* bnd_in = w.bnd + (uint64_t)((blk + 1) & 1) * w.bnd_stride + w.qoff[pair];
+    uint4* bnd_out = w.bnd + (uint64_t)(blk & 1) * w.bnd_stride + w.qoff[pair];
+    const uint32_t tag_in = w.tag_base + blk - 1, tag_out = w.tag_base + blk;
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    if (blk != 0 && lane < ncol) pre = ld_bnd(bnd_in + lane);
+
+    const int nsteps = ncol + 63;
+    int exo_hist = 0;                                            // bit i: chunk (current - i) holds an exotic column
+    for (int k0 = 0; k0 < nsteps; k0 += 32) {
+      exo_hist <<= 1;
+      {
+        const int c = k0 + lane;
+        uint2 v = make_uint2(0u, 0u);
+        uint32_t selv = 0x88u;
+        if (k0 < ncol) {
+          if (blk != 0) {
+            bool ok = (c >= ncol) || (pre.y == tag_in && pre.w == tag_in);
+            while (!__all_sync(0xFFFFFFFFu, ok)) {
+              __nanosleep(20);
+              if (!ok) { pre = ld_bnd(bnd_in + c); ok = (pre.y == tag_in && pre.w == tag_in); }
+            }
+            v.x = pre.x; v.y = pre.z;
+            if (c + 32 < ncol) pre = ld_bnd(bnd_in + c + 32);
+          }
+          if (c < ncol) {
+            const uint32_t qword = wave_qword(w, g, qw, qlen, c >> 3);
+            const uint32_t qc = nib(qword, c & 7);
+            const uint32_t idx = base_idx(qc);
+            selv = (idx < 4) ? (0x80u + 0x11u * idx) | (qc << 20) : (0x88u | kWaveExotic | (qc << 20));
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, (selv & kWaveExotic) != 0)) exo_hist |= 1;
+        __syncwarp();
+        sin[lane] = v;
+        ssel[c & 127] = selv;
+        __syncwarp();
+      }
+      const int kend = min(k0 + 32, nsteps);
+      if (exo_hist & 7) wave16_steps<true>(L, sc, sin, ssel, sout, k0, kend, ncol, lane, neg_oe2, neg_ext2);
+      else wave16_steps<false>(L, sc, sin, ssel, sout, k0, kend, ncol, lane, neg_oe2, neg_ext2);
+      // ---- lane 31's high strip finished columns k0-63 .. kend-64 during this chunk ----
+      if (!last_blk) {
+        __syncwarp();
+        const int cb = k0 - 63 + lane;
+        if (cb >= 0 && cb < ncol && k0 + lane < kend) { const uint2 o = sout[lane]; st_bnd(bnd_out + cb, make_uint4(o.x, tag_out, o.y, tag_out)); }
+        __syncwarp();
+      }
+    }
+    int2* cand = w.cand + w.soff[pair];
+    if (lstrip < g.nstrips) __stcg(&cand[lstrip], make_int2(L.bestL, L.bposL));
+    if (lstrip + 1 < g.nstrips) __stcg(&cand[lstrip + 1], make_int2(L.bestH, L.bposH));
+    __syncwarp();
+    uint32_t old = 0;
+    if (lane == 0) { __threadfence(); old = atomicAdd(w.done + pair, 1u); }
+    old = __shfl_sync(0xFFFFFFFFu, old, 0);
+    if ((int)old == nblk - 1) { __threadfence(); wave_finalize<ALGO_LOCAL>(w, pair, g, lane); }
+  }
+}
+
+inline bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t) {
+  if (algo != ALGO_LOCAL) return false;
+  if ((uint64_t)std::min(max_q, max_t) * (uint64_t)a.match > 32000ull) return false;          // scores stay in 16 bits
+  return a.gap_open + a.gap_extend + a.mismatch + std::max(0, -a.n_score) < 8000;
+}
+
 // ---- host side ---------------------------------------------------------------------------------------------
 struct WaveScratch {
   uint64_t* qoff = nullptr; uint64_t* soff = nullptr; size_t n_cap = 0;
@@ -437,7 +630,7 @@ inline void wave_launch_kernel(int algo, int blocks, const WaveArgs& wa, cudaStr
 // h_qlens / h_tlens: the batch's lengths on the host (the caller's pinned arrays).  Returns the number of kernel
 // launches, or -1 when a scratch allocation failed.
 inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uint32_t* h_qlens, const uint32_t* h_tlens,
-                       uint32_t max_t, int n_sm, cudaStream_t str) {
+                       uint32_t max_t, int n_sm, cudaStream_t str, bool* s16_inout = nullptr, bool force_s16 = false) {
   const size_t n = (size_t)a.n;
   if (ws.h_cap < 2 * n) {
     if (ws.h_off) cudaFreeHost(ws.h_off);
@@ -463,7 +656,11 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   // Row-blocks of one pair form a pipeline that runs at the pace of its slowest stage, so the warp-workers must be
   // spread evenly over the SM sub-partitions: 16 rows per lane as long as that still gives every sub-partition a task
   // (fewer, longer pipeline stages), else 8; and never more workers than tasks (the hardware deals CTAs round-robin).
-  const int SR = (tasks2 * 4 >= (uint64_t)n_sm * 4 * 3) ? 2 : 1;
+  const bool many = tasks2 * 4 >= (uint64_t)n_sm * 4 * 3;
+  // the s16x2 kernel's row-block is 64 strips; with few tasks the finer int32 blocks (SR = 1) fill the machine better
+  const bool use_s16 = s16_inout && *s16_inout && (many || force_s16);
+  if (s16_inout) *s16_inout = use_s16;
+  const int SR = (many || use_s16) ? 2 : 1;
   const uint64_t tasks = (SR == 2) ? tasks2 : tasks1;
   const uint32_t max_tr = (max_t + 7u) >> 3;
   const uint32_t maxblk = std::max<uint32_t>(1u, (max_tr + 32u * SR - 1) / (32u * SR));
@@ -502,7 +699,8 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   for (int pass = 0; pass < npass; pass++) {
     cudaMemsetAsync(ws.prog, 0, prog_words * sizeof(uint32_t), str);
     wa.pass = pass; wa.tag_base = ws.next_tag; ws.next_tag += maxblk;
-    if (SR == 2) wave_launch_kernel<2>(algo, blocks, wa, str); else wave_launch_kernel<1>(algo, blocks, wa, str);
+    if (use_s16) k_wave16_local<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
+    else if (SR == 2) wave_launch_kernel<2>(algo, blocks, wa, str); else wave_launch_kernel<1>(algo, blocks, wa, str);
     launches++;
   }
   return launches;

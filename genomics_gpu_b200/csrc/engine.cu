@@ -553,11 +553,12 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   // ---- long pairs: intra-task wavefront kernel (dp_wave.cuh) ----
   // policy 0: whenever the batch is too long for the fast path; policy 2: wherever the wavefront kernel is eligible
   if (g_kernel_policy != 1 && wave_eligible(a, params->algo, start, second, shape.min_q, shape.min_t) &&
-      (g_kernel_policy == 2 || q8 > kFastMaxQ8)) {
+      (g_kernel_policy >= 2 || q8 > kFastMaxQ8)) {
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int nl = wave_launch(a, params->algo, start, pv->wave, s->host_query_batch_lens, s->host_target_batch_lens, shape.max_t, sms, s->str);
+    bool s16 = g_kernel_policy != 3 && wave16_eligible(a, params->algo, shape.max_q, shape.max_t);
+    const int nl = wave_launch(a, params->algo, start, pv->wave, s->host_query_batch_lens, s->host_target_batch_lens, shape.max_t, sms, s->str, &s16, g_kernel_policy == 4);
     if (nl < 0) { fprintf(stderr, "[GASAL CUDA ERROR:] out of device memory for the wavefront scratch\n"); exit(EXIT_FAILURE); }
-    CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "wave";
+    CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = s16 ? "wave16" : "wave";
     return;
   }
 

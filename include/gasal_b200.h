@@ -198,8 +198,13 @@ void gasal_res_destroy_device(gasal_res_t* device_res, gasal_res_t* device_cpy);
  * n_penalty < 0 means "N_PENALTY not defined" (N scores 0 in local/semi-global/banded/ksw). */
 void gasalx_set_n_code(int n_code, int n_penalty);
 
-/* Which DP implementation gasal_aln_async may pick: 0 = automatic (s16x2 fast path when the batch
- * qualifies, else the general int32 kernels), 1 = force the general int32 kernels. */
+/* Which DP implementation gasal_aln_async may pick:
+ *   0 = automatic: s16x2 inter-task fast path when the batch qualifies (short reads), the intra-task wavefront
+ *       kernel for batches with longer queries (s16x2 lanes for LOCAL when the scores fit and there are enough
+ *       row-blocks, int32 lanes otherwise), else the general one-thread-per-pair int32 kernels;
+ *   1 = general int32 kernels only;
+ *   2 = wavefront kernel wherever it is eligible (any length), s16x2 / int32 chosen as in 0;
+ *   3 = as 2 but int32 lanes only;   4 = as 2 but s16x2 lanes whenever the scores fit (testing). */
 void gasalx_set_kernel_policy(int policy);
 
 /* Semantics of the "reverse" bit of host_query_op / host_target_op.  The reference kernel

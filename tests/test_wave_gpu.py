@@ -45,14 +45,16 @@ def long_pairs(seed, n=24, lo=1500, hi=5000):
 
 
 @pytest.mark.parametrize("scoring", SCORINGS)
-def test_wave_local_ragged(oracle, scoring):
+@pytest.mark.parametrize("policy,kernel", [(4, "wave16"), (3, "wave")])
+def test_wave_local_ragged(oracle, scoring, policy, kernel):
+    """policy 4: s16x2 wavefront kernel (k_wave16_local); policy 3: the int32 wavefront kernel"""
     b = ragged(301)
     want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_START, scoring=scoring)
-    got = run(b, algo=capi.LOCAL, start=capi.WITH_START, scoring=scoring)
-    assert got["_kernel"] == "wave"
-    assert_same(got, want, K5, f"wave local {scoring}")
-    got = run(b, algo=capi.LOCAL, scoring=scoring)
-    assert_same(got, want, K3, f"wave local score/end {scoring}")
+    got = run(b, policy=policy, algo=capi.LOCAL, start=capi.WITH_START, scoring=scoring)
+    assert got["_kernel"] == kernel
+    assert_same(got, want, K5, f"{kernel} local {scoring}")
+    got = run(b, policy=policy, algo=capi.LOCAL, scoring=scoring)
+    assert_same(got, want, K3, f"{kernel} local score/end {scoring}")
 
 
 @pytest.mark.parametrize("scoring", SCORINGS)
@@ -85,17 +87,22 @@ def test_wave_exotic_codes(oracle):
                               (po.SEMI_GLOBAL, K5, dict(start=po.WITH_START, max_query_len=1024))]:
         want = oracle_align(oracle, b, algo=algo, **extra)
         extra.pop("max_query_len", None)
-        got = run(b, algo=algo, **extra)
-        assert got["_kernel"] == "wave"
-        assert_same(got, want, keys, f"wave exotic codes algo={algo}")
+        for policy in ((4, 3) if algo == po.LOCAL else (2,)):
+            got = run(b, policy=policy, algo=algo, **extra)
+            assert got["_kernel"] in ("wave", "wave16")
+            assert_same(got, want, keys, f"wave exotic codes algo={algo} policy={policy}")
 
 
 def test_wave_long_local_with_start(oracle):
     b = long_pairs(41)
     want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_START, max_query_len=8192)
     got = run(b, policy=0, algo=capi.LOCAL, start=capi.WITH_START)          # policy 0: long batches pick the wavefront kernel themselves
-    assert got["_kernel"] == "wave"
+    assert got["_kernel"] in ("wave", "wave16")
     assert_same(got, want, K5, "wave long local")
+    for policy, kernel in ((4, "wave16"), (3, "wave")):
+        got = run(b, policy=policy, algo=capi.LOCAL, start=capi.WITH_START)
+        assert got["_kernel"] == kernel
+        assert_same(got, want, K5, f"{kernel} long local")
 
 
 def test_wave_long_global(oracle):
@@ -127,5 +134,5 @@ def test_wave_matches_general_kernel_on_mixed_lengths(oracle):
     b = synth.config5(96, seed=7, lo=100, hi=6000)
     a = run(b, policy=1, algo=capi.LOCAL, start=capi.WITH_START)
     w = run(b, policy=0, algo=capi.LOCAL, start=capi.WITH_START)
-    assert a["_kernel"] == "int32" and w["_kernel"] == "wave"
+    assert a["_kernel"] == "int32" and w["_kernel"] in ("wave", "wave16")
     assert_same(w, a, K5, "wave vs general kernel, mixed lengths")

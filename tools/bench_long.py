@@ -13,6 +13,8 @@ policies = [int(x) for x in sys.argv[3].split(",")] if len(sys.argv) > 3 else [0
 t0 = time.time()
 if what == "c3":
     batch = synth.config3(n, 16384, seed=3); algo, start = capi.GLOBAL, capi.WITHOUT_START
+elif what == "l3":   # the C3 sequences under LOCAL scoring (scores fit 16 bits: exercises the s16x2 wavefront kernel)
+    batch = synth.config3(n, 16384, seed=3); algo, start = capi.LOCAL, capi.WITHOUT_START
 else:
     batch = synth.config5(n, seed=5); algo, start = capi.LOCAL, capi.WITH_START
 print(f"generated {batch.n} pairs, {batch.cells/1e9:.2f} Gcells in {time.time()-t0:.1f}s", flush=True)
