@@ -9,9 +9,10 @@
 // self-validating 8-byte words (H, tag) (E, tag) -- the tag names the launch and the producing block -- so the consumer
 // simply re-reads a chunk until every tag matches: no flags, no fences (8-byte stores are single-copy atomic; the same
 // idea as NCCL's LL protocol), and the next chunk is prefetched a whole chunk ahead.  Tasks are handed out by a global
-// ticket counter in (pair, block) order, so a task only ever waits on a LOWER ticket that some resident warp already
-// holds: deadlock-free for any grid size, no cooperative launch, and all row-blocks of a pair (and of the next pairs)
-// run concurrently as a pipeline across the whole GPU.
+// ticket counter in BLOCK-MAJOR order (ticket = block * n_pairs + pair), so a task only ever waits on a LOWER ticket that
+// some resident warp already holds: deadlock-free for any grid size, no cooperative launch.  With many pairs every worker
+// starts on a different pair and a pair's next row-block is picked up long after its predecessor finished (no waiting at
+// all); with few pairs the row-blocks of one pair run concurrently as a pipeline across the whole GPU.
 //
 // Same recurrences, boundaries and tie-breaking as the inter-task kernels (dp_generic.cuh), int32 lanes on the DPX
 // instructions (VIMNMX3 / VIADDMNMX); the substitution score is ONE PRMT per cell from a per-row 4-byte table.
@@ -280,7 +281,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
     if (lane == 0) T = atomicAdd(w.ticket, 1u);
     T = __shfl_sync(0xFFFFFFFFu, T, 0);
     if (T >= total) break;
-    const uint32_t pair = T / w.maxblk, blk = T - pair * w.maxblk;
+    const uint32_t blk = T / (uint32_t)a.n, pair = T - blk * (uint32_t)a.n;   // block-major tickets (see header)
     const WaveGeom g = wave_geometry(w, pair);
     const int nblk = (g.nstrips + 32 * SR - 1) / (32 * SR);
     if ((int)blk >= nblk) {
@@ -491,7 +492,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave16_local(const WaveArgs
     if (lane == 0) T = atomicAdd(w.ticket, 1u);
     T = __shfl_sync(0xFFFFFFFFu, T, 0);
     if (T >= total) break;
-    const uint32_t pair = T / w.maxblk, blk = T - pair * w.maxblk;
+    const uint32_t blk = T / (uint32_t)a.n, pair = T - blk * (uint32_t)a.n;   // block-major tickets (see header)
     const WaveGeom g = wave_geometry(w, pair);
     const int nblk = (g.nstrips + 63) / 64;
     if ((int)blk >= nblk) {
