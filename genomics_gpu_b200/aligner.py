@@ -204,3 +204,43 @@ def align_all(batch: PairBatch, *, algo: int, start: int = capi.WITHOUT_START, s
         raise RuntimeError(f"gasalx_align_all failed ({rc})")
     out["_gpu_ms"] = gpu_ms
     return out
+
+
+def read_fasta_pairs(query_path: str, target_path: str, n_code: int = 0x4E):
+    """Two FASTA files (plain or gzip) -> (PairBatch, q_op, t_op, q_names, t_names) through the native reader
+    (gasalx_read_fasta_pairs; header conventions of test_prog.cpp:79-89).  Offsets are 64-bit; a PairBatch is what
+    align_all() / Aligner.fill() take (slice it to keep one batch within the 32-bit offsets of the GASAL2 API)."""
+    lib = capi.load()
+    fp = capi.FastaPairs()
+    rc = lib.gasalx_read_fasta_pairs(query_path.encode(), target_path.encode(), n_code, C.byref(fp))
+    if rc != 0:
+        raise RuntimeError(f"gasalx_read_fasta_pairs failed ({rc})")
+    try:
+        n = int(fp.n)
+        arr = lambda ptr, cnt, dt: np.ctypeslib.as_array(ptr, shape=(max(cnt, 1),))[:cnt].view(dt).copy() if cnt else np.zeros(0, dtype=dt)
+        batch = PairBatch(arr(fp.q, int(fp.q_bytes), np.uint8), arr(fp.t, int(fp.t_bytes), np.uint8), arr(fp.q_offs, n, np.uint64), arr(fp.t_offs, n, np.uint64),
+                          arr(fp.q_lens, n, np.uint32), arr(fp.t_lens, n, np.uint32))
+        q_op, t_op = arr(fp.q_op, n, np.uint8), arr(fp.t_op, n, np.uint8)
+        qn = C.string_at(fp.q_names).decode().split("\n")[:n]; tn = C.string_at(fp.t_names).decode().split("\n")[:n]
+    finally:
+        lib.gasalx_free_fasta_pairs(C.byref(fp))
+    return batch, q_op, t_op, qn, tn
+
+
+def pack_host(ascii_bytes: np.ndarray) -> np.ndarray:
+    """4-bit packing on the host in the device layout (for isPacked storages)."""
+    a = np.ascontiguousarray(ascii_bytes, dtype=np.uint8)
+    assert a.size % 8 == 0
+    out = np.zeros(a.size // 8, dtype=np.uint32)
+    capi.load().gasalx_pack_host(a.ctypes.data, a.size, out.ctypes.data)
+    return out
+
+
+def cigar_string(cigar_bytes: np.ndarray, n_ops: int) -> str:
+    """gasal_res_t::cigar bytes of one pair (reverse order) -> '12M1X3D...' as the reference's test_prog prints it."""
+    c = np.ascontiguousarray(cigar_bytes[:n_ops], dtype=np.uint8)
+    buf = C.create_string_buffer(16 * max(n_ops, 1) + 16)
+    n = capi.load().gasalx_cigar_string(c.ctypes.data, n_ops, buf, len(buf))
+    if n < 0:
+        raise RuntimeError("cigar buffer too small")
+    return buf.value.decode()

@@ -92,7 +92,16 @@ EXPORTED_SYMBOLS = [
     "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
     "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
     "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all",
+    "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_cigar_string",
 ]
+
+
+class FastaPairs(C.Structure):
+    _fields_ = [("n", C.c_uint64), ("q", C.POINTER(C.c_uint8)), ("t", C.POINTER(C.c_uint8)), ("q_bytes", C.c_uint64), ("t_bytes", C.c_uint64),
+                ("q_offs", C.POINTER(C.c_uint64)), ("t_offs", C.POINTER(C.c_uint64)), ("q_lens", C.POINTER(C.c_uint32)), ("t_lens", C.POINTER(C.c_uint32)),
+                ("q_op", C.POINTER(C.c_uint8)), ("t_op", C.POINTER(C.c_uint8)), ("q_names", C.c_void_p), ("t_names", C.c_void_p),
+                ("max_query_len", C.c_uint32), ("max_target_len", C.c_uint32), ("any_op", C.c_int)]
+
 
 _lib = None
 
@@ -135,5 +144,9 @@ def load() -> C.CDLL:
     lib.gasalx_plan_batches.restype = C.c_int64
     lib.gasalx_align_all.argtypes = [C.c_void_p] * 9 + [C.c_uint64, P(Params), P(Sched), P(Results), C.c_void_p]
     lib.gasalx_align_all.restype = C.c_int
+    lib.gasalx_read_fasta_pairs.argtypes = [C.c_char_p, C.c_char_p, C.c_int, P(FastaPairs)]; lib.gasalx_read_fasta_pairs.restype = C.c_int
+    lib.gasalx_free_fasta_pairs.argtypes = [P(FastaPairs)]
+    lib.gasalx_pack_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.gasalx_cigar_string.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]; lib.gasalx_cigar_string.restype = C.c_int
     _lib = lib
     return lib

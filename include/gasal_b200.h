@@ -268,6 +268,27 @@ int gasalx_align_all(const uint8_t* q_bytes, const uint8_t* t_bytes, const uint6
                      const uint32_t* q_lens, const uint32_t* t_lens, const uint8_t* q_op, const uint8_t* t_op, const uint32_t* seed_scores,
                      uint64_t n, const gasal_params_t* params, const gasalx_sched_t* sched, gasalx_results_t* out, double* gpu_ms);
 
+/* ---- caller-side I/O (replaces the file loop and CIGAR printer of test_prog.cpp:79-137,382-428) ---- */
+typedef struct {
+  uint64_t n;                          /* pairs */
+  uint8_t* q; uint8_t* t;              /* concatenated sequences, each padded with N_CODE to a multiple of 8 (gasal_host_batch_fill layout) */
+  uint64_t q_bytes, t_bytes;
+  uint64_t* q_offs; uint64_t* t_offs;  /* byte offsets (multiples of 8) */
+  uint32_t* q_lens; uint32_t* t_lens;  /* true lengths */
+  uint8_t* q_op; uint8_t* t_op;        /* 0 '>' forward, 1 '<' reverse, 2 '/' complement, 3 '+' reverse-complement (test_prog.cpp:80-89) */
+  char* q_names; char* t_names;        /* header texts, one per line */
+  uint32_t max_query_len, max_target_len;
+  int any_op;                          /* some sequence asks for reverse / complement: set isReverseComplement */
+} gasalx_fasta_pairs_t;
+/* Read a query and a target FASTA file (plain or gzip) with the same number of records. 0 on success. */
+int gasalx_read_fasta_pairs(const char* query_path, const char* target_path, int n_code, gasalx_fasta_pairs_t* out);
+void gasalx_free_fasta_pairs(gasalx_fasta_pairs_t* p);
+/* 4-bit packing on the host, device layout (pack_rc_seqs.h:13-53): n_bytes must be a multiple of 8; words[n_bytes / 8]. */
+void gasalx_pack_host(const uint8_t* ascii, uint64_t n_bytes, uint32_t* words);
+/* gasal_res_t::cigar bytes of one pair (reverse order) -> "12M1X3D..." as test_prog.cpp:382-428 prints it.
+ * Returns the length, or -(needed capacity) if cap is too small. */
+int gasalx_cigar_string(const uint8_t* cigar, uint32_t n_ops, char* out, uint32_t cap);
+
 /* Version string of the engine. */
 const char* gasalx_version(void);
 

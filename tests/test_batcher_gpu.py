@@ -57,3 +57,29 @@ def test_align_all_input_order_mode(oracle):
     want = oracle_align(oracle, job, algo=po.LOCAL)
     got = align_all(job, algo=capi.LOCAL, n_gpus=1, max_batch_pairs=128, keep_input_order=True)
     assert_same(got, want, K3, "align_all keep_input_order")
+
+
+def test_fasta_files_to_cigar_strings_end_to_end(oracle, tmp_path):
+    """the reference caller's whole flow without its host code: FASTA files -> native reader -> batcher -> CIGAR strings
+    (test_prog.cpp:79-137, 203-437); header marks drive reverse / complement (modes agree for complement-only ops)"""
+    from genomics_gpu_b200.aligner import read_fasta_pairs, cigar_string
+    b = synth.random_ragged_pairs(500, 20, 200, 20, 300, seed=12)
+    marks = [">", "/"] * 250                                       # forward / complement (well defined in the reference, SURVEY Q9)
+    for name, seqs, mk in (("q.fa", [b.query(i) for i in range(b.n)], marks), ("t.fa", [b.target(i) for i in range(b.n)], [">"] * b.n)):
+        with open(tmp_path / name, "w") as f:
+            for i, s in enumerate(seqs):
+                f.write(f"{mk[i]}r{i}\n{s.decode()}\n")
+    job, q_op, t_op, qn, tn = read_fasta_pairs(str(tmp_path / "q.fa"), str(tmp_path / "t.fa"))
+    assert job.n == b.n and qn[3] == "r3"
+    pq, pt = oracle.pack(job.q_bytes), oracle.pack(job.t_bytes)
+    q32, t32 = job.q_offs.astype(np.uint32), job.t_offs.astype(np.uint32)
+    rq, rt = oracle.revcomp(pq, pt, job.q_lens, job.t_lens, q32, t32, q_op, t_op)
+    want = oracle.align(rq, rt, job.q_lens, job.t_lens, q32, t32, algo=po.LOCAL, start=po.WITH_TB)
+    got = align_all(job, algo=capi.LOCAL, start=capi.WITH_TB, n_gpus=2, gpu_ids=[0, 0], max_batch_pairs=128, q_op=q_op, t_op=t_op)
+    assert_same(got, want, K5 + ["n_cigar_ops"], "fasta -> align_all -> tb")
+    for i in range(job.n):
+        o, n = int(job.q_offs[i]), int(got["n_cigar_ops"][i])
+        s = cigar_string(got["cigar"][o:o + n], n)
+        assert s == cigar_string(want["cigar"][o:o + n], n)
+        if got["aln_score"][i] > 0:
+            assert sum(int(x) for x in __import__("re").findall(r"(\d+)[MXI]", s)) == got["query_batch_end"][i] - got["query_batch_start"][i] + 1
