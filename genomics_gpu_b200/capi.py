@@ -91,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "gasal_res_new_host", "gasal_res_new_device", "gasal_res_new_device_cpy", "gasal_res_destroy_host", "gasal_res_destroy_device",
     "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
     "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
-    "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all",
+    "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all", "gasalx_batcher_release",
     "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_cigar_string",
 ]
 

@@ -16,6 +16,7 @@
 #include <string.h>
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <numeric>
 #include <thread>
 #include <vector>
@@ -45,7 +46,9 @@ void make_plan(const uint32_t* q_lens, const uint32_t* t_lens, uint64_t n, const
   // 1. length binning: class = (padded query words, padded target words); stable so equal shapes keep input order
   std::vector<uint64_t> key(n);
   for (uint64_t i = 0; i < n; i++) key[i] = ((uint64_t)(pad8(q_lens[i]) >> 3) << 32) | (uint64_t)(pad8(t_lens[i]) >> 3);
-  if (!sc->keep_input_order)
+  bool uniform = true;
+  for (uint64_t i = 1; i < n && uniform; i++) uniform = (key[i] == key[0]);
+  if (!sc->keep_input_order && !uniform)
     std::stable_sort(pl.order.begin(), pl.order.end(), [&](uint32_t a, uint32_t b) { return key[a] < key[b]; });
   // 2. cut into batches; never mix pairs on different sides of the fast-path query limit
   const uint32_t fast_q8 = 352;   // == kFastMaxQ8 (dp_s16.cuh)
@@ -83,6 +86,23 @@ void make_plan(const uint32_t* q_lens, const uint32_t* t_lens, uint64_t n, const
   }
 }
 
+// Storages (pinned host pages, device buffers, streams) are expensive to create -- a GB of pinned memory takes a few hundred
+// milliseconds -- so each device keeps the set of its last job and reuses it while the parameters match and the capacity
+// suffices.  One job at a time per device (the mutex is held for the duration of a worker).
+struct DeviceCache {
+  std::mutex mu;
+  bool valid = false;
+  gasal_gpu_storage_v v;
+  gasal_params_t params;
+  int max_q = 0, max_t = 0, max_pairs = 0;
+};
+DeviceCache g_cache[64];
+
+bool same_params(const gasal_params_t& a, const gasal_params_t& b) {
+  return a.algo == b.algo && a.start_pos == b.start_pos && a.secondBest == b.secondBest && a.isPacked == b.isPacked &&
+         a.isReverseComplement == b.isReverseComplement;
+}
+
 struct Job {
   const uint8_t* q; const uint8_t* t; const uint64_t* q_offs; const uint64_t* t_offs; const uint32_t* q_lens; const uint32_t* t_lens;
   const uint8_t* q_op; const uint8_t* t_op; const uint32_t* seeds;
@@ -103,13 +123,26 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
   // process big batches first so the tail is short
   std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return pl.batch_cells[a] > pl.batch_cells[b]; });
   const int ns = sc->streams_per_gpu > 0 ? sc->streams_per_gpu : 2;
-  gasal_gpu_storage_v v = gasal_init_gpu_storage_v(ns);
   // size the pages for the largest batch in BYTES (ragged batches are much smaller than max_pairs x max_len)
   uint64_t maxqb = 0, maxtb = 0;
   for (uint32_t b : mine) { maxqb = std::max(maxqb, pl.batch_q_bytes[b]); maxtb = std::max(maxtb, pl.batch_t_bytes[b]); }
   const int eff_q = (int)std::max<uint64_t>(8, (maxqb + max_pairs - 1) / std::max(1u, max_pairs));
   const int eff_t = (int)std::max<uint64_t>(8, (maxtb + max_pairs - 1) / std::max(1u, max_pairs));
-  gasal_init_streams(&v, eff_q + 7, eff_t + 7, (int)max_pairs, job.params);
+  DeviceCache& dc = g_cache[device & 63];
+  std::lock_guard<std::mutex> lock(dc.mu);
+  const bool fits = dc.valid && dc.v.n == ns && same_params(dc.params, *job.params) && (int)max_pairs <= dc.max_pairs &&
+                    (uint64_t)dc.max_pairs * dc.max_q >= maxqb && (uint64_t)dc.max_pairs * dc.max_t >= maxtb;
+  if (!fits) {
+    int nq = eff_q + 7, nt = eff_t + 7, np = (int)max_pairs;
+    if (dc.valid) {
+      if (dc.v.n == ns && same_params(dc.params, *job.params)) { nq = std::max(nq, dc.max_q); nt = std::max(nt, dc.max_t); np = std::max(np, dc.max_pairs); }
+      gasal_destroy_streams(&dc.v, &dc.params); gasal_destroy_gpu_storage_v(&dc.v); dc.valid = false;
+    }
+    dc.v = gasal_init_gpu_storage_v(ns);
+    gasal_init_streams(&dc.v, nq, nt, np, job.params);
+    dc.params = *job.params; dc.max_q = ((nq + 7) / 8) * 8; dc.max_t = ((nt + 7) / 8) * 8; dc.max_pairs = np; dc.valid = true;
+  }
+  gasal_gpu_storage_v& v = dc.v;
   std::vector<int> running(ns, -1);
   size_t next = 0, done = 0;
   double ms_total = 0;
@@ -162,15 +195,35 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
       const uint32_t lo = pl.batch_start[b], cnt = pl.batch_start[b + 1] - lo;
       if (cnt > st->host_max_n_alns) gasal_host_alns_resize(st, (int)cnt, P);
       uint32_t qi = 0, ti = 0;
-      for (uint32_t j = 0; j < cnt; j++) {
-        const uint32_t i = pl.order[lo + j];
-        st->host_query_batch_offsets[j] = qi; st->host_target_batch_offsets[j] = ti;
-        qi = gasal_host_batch_fill(st, qi, (const char*)job.q + job.q_offs[i], job.q_lens[i], QUERY);
-        ti = gasal_host_batch_fill(st, ti, (const char*)job.t + job.t_offs[i], job.t_lens[i], TARGET);
-        st->host_query_batch_lens[j] = job.q_lens[i]; st->host_target_batch_lens[j] = job.t_lens[i];
-        if (job.q_op) st->host_query_op[j] = job.q_op[i];
-        if (job.t_op) st->host_target_op[j] = job.t_op[i];
-        if (job.seeds && st->host_seed_scores) st->host_seed_scores[j] = job.seeds[i];
+      for (uint32_t j = 0; j < cnt;) {
+        // the job is already in the padded host layout: pairs that are neighbours in the input AND in the batch are staged
+        // with ONE bulk copy per sequence buffer instead of one gasal_host_batch_fill per sequence
+        const uint32_t i0 = pl.order[lo + j];
+        uint32_t run = 1;
+        while (j + run < cnt) {
+          const uint32_t ip = pl.order[lo + j + run - 1], in = pl.order[lo + j + run];
+          if (in != ip + 1 || job.q_offs[in] != job.q_offs[ip] + pad8(job.q_lens[ip]) || job.t_offs[in] != job.t_offs[ip] + pad8(job.t_lens[ip])) break;
+          run++;
+        }
+        const uint32_t il = i0 + run - 1;
+        const uint64_t qbytes = job.q_offs[il] + pad8(job.q_lens[il]) - job.q_offs[i0], tbytes = job.t_offs[il] + pad8(job.t_lens[il]) - job.t_offs[i0];
+        for (uint32_t r = 0; r < run; r++) {
+          const uint32_t i = i0 + r;
+          st->host_query_batch_offsets[j + r] = qi + (uint32_t)(job.q_offs[i] - job.q_offs[i0]);
+          st->host_target_batch_offsets[j + r] = ti + (uint32_t)(job.t_offs[i] - job.t_offs[i0]);
+          st->host_query_batch_lens[j + r] = job.q_lens[i]; st->host_target_batch_lens[j + r] = job.t_lens[i];
+          if (job.q_op) st->host_query_op[j + r] = job.q_op[i];
+          if (job.t_op) st->host_target_op[j + r] = job.t_op[i];
+          if (job.seeds && st->host_seed_scores) st->host_seed_scores[j + r] = job.seeds[i];
+        }
+        if (run > 1) {
+          qi = gasal_host_batch_add(st, qi, (const char*)job.q + job.q_offs[i0], (uint32_t)qbytes, QUERY);
+          ti = gasal_host_batch_add(st, ti, (const char*)job.t + job.t_offs[i0], (uint32_t)tbytes, TARGET);
+        } else {
+          qi = gasal_host_batch_fill(st, qi, (const char*)job.q + job.q_offs[i0], job.q_lens[i0], QUERY);
+          ti = gasal_host_batch_fill(st, ti, (const char*)job.t + job.t_offs[i0], job.t_lens[i0], TARGET);
+        }
+        j += run;
       }
       st->current_n_alns = cnt;
       gasal_aln_async(st, qi, ti, cnt, P);
@@ -178,8 +231,6 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
     }
     if (!progressed) std::this_thread::yield();
   }
-  gasal_destroy_streams(&v, P);
-  gasal_destroy_gpu_storage_v(&v);
   if (gpu_ms) *gpu_ms = ms_total;
 }
 
@@ -230,6 +281,17 @@ int gasalx_align_all(const uint8_t* q_bytes, const uint8_t* t_bytes, const uint6
   for (auto& t : th) t.join();
   if (gpu_ms) memcpy(gpu_ms, ms.data(), sizeof(double) * n_gpus);
   return err.load() ? -1 : 0;
+}
+
+// Free the per-device storage caches of gasalx_align_all (also safe to never call: process exit releases them).
+void gasalx_batcher_release(void) {
+  for (int d = 0; d < 64; d++) {
+    DeviceCache& dc = g_cache[d];
+    std::lock_guard<std::mutex> lock(dc.mu);
+    if (!dc.valid) continue;
+    if (cudaSetDevice(d) == cudaSuccess) { gasal_destroy_streams(&dc.v, &dc.params); gasal_destroy_gpu_storage_v(&dc.v); }
+    dc.valid = false;
+  }
 }
 
 }  // extern "C"

@@ -268,6 +268,9 @@ int gasalx_align_all(const uint8_t* q_bytes, const uint8_t* t_bytes, const uint6
                      const uint32_t* q_lens, const uint32_t* t_lens, const uint8_t* q_op, const uint8_t* t_op, const uint32_t* seed_scores,
                      uint64_t n, const gasal_params_t* params, const gasalx_sched_t* sched, gasalx_results_t* out, double* gpu_ms);
 
+/* gasalx_align_all keeps one set of storages per device between calls (pinned pages are expensive to create); this frees them. */
+void gasalx_batcher_release(void);
+
 /* ---- caller-side I/O (replaces the file loop and CIGAR printer of test_prog.cpp:79-137,382-428) ---- */
 typedef struct {
   uint64_t n;                          /* pairs */
