@@ -311,12 +311,16 @@ def run_ours(args, rank, world, local_rank):
     checksum = np.zeros(1, dtype=np.int64)
 
     def e2e_step():
+        # all storages of both modes are put in flight before the first wait, as a caller with 2 x 8 storages would: the
+        # H2D of later chunks (and of the second mode) overlaps the kernels of earlier ones
         for name, _ in modes:
             al = e2e_al[name]
             for si, sub in enumerate(subs):
                 s = al.vec.a[si]
                 lib.gasalx_host_batch_rearm(C.byref(s), int(sub.q_bytes.size), int(sub.t_bytes.size), sub.n)
                 al.launch(si, int(sub.q_bytes.size), int(sub.t_bytes.size), sub.n)
+        for name, _ in modes:
+            al = e2e_al[name]
             for si, sub in enumerate(subs):
                 al.wait(si)
                 r = al.results(si, sub.n)          # host_res arrays (D2H already done on the stream)

@@ -411,13 +411,39 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
 struct Wave16Lane {
   uint32_t twA, twB;              // packed target words of the low / high strip
   uint32_t rowA[8], rowB[8];      // per-row substitution tables (dp_s16.cuh row_table layout)
-  uint32_t p[8], f[8];
+  uint32_t p[8], f[8], hh[8];     // hh: H of the last computed step (its arg-max is taken one step later)
   uint32_t out_h, out_e;          // bottom (H, E) of both strips after the previous step
   uint32_t prevsh;                // selector bits of the high half (the low half's previous column)
   uint32_t vprev;                 // ring word of the previous step (exotic path)
   uint32_t bestpk;                // running per-half maxima, packed (fast improvement test)
   int bestL, bestH, bposL, bposH;
 };
+
+// record an improvement of the running maxima: hh = the H values of step k (low half on column k - 2*lane, high half one behind)
+__device__ __forceinline__ void wave16_track(Wave16Lane& L, int k, int ncol, int lane) {
+  uint32_t cm = __vimax3_s16x2(L.hh[0], L.hh[1], L.hh[2]);
+  cm = __vimax3_s16x2(cm, L.hh[3], L.hh[4]);
+  cm = __vimax3_s16x2(cm, L.hh[5], L.hh[6]);
+  cm = __vmaxs2(cm, L.hh[7]);
+  const uint32_t nb = __vmaxs2(L.bestpk, cm);
+  if (nb != L.bestpk) {                              // rare and divergent: resolve row and column, check the column is real
+    L.bestpk = nb;
+    const int cL = k - 2 * lane, cH = cL - 1;
+    const int mL = (int)(short)(cm & 0xFFFFu), mH = (int)(short)(cm >> 16);
+    if (mL > L.bestL && cL >= 0 && cL < ncol) {
+      int rr = 7;
+#pragma unroll
+      for (int r = 6; r >= 0; r--) rr = ((int)(short)(L.hh[r] & 0xFFFFu) == mL) ? r : rr;
+      L.bestL = mL; L.bposL = (cL << 3) | rr;
+    }
+    if (mH > L.bestH && cH >= 0 && cH < ncol) {
+      int rr = 7;
+#pragma unroll
+      for (int r = 6; r >= 0; r--) rr = ((int)(short)(L.hh[r] >> 16) == mH) ? r : rr;
+      L.bestH = mH; L.bposH = (cH << 3) | rr;
+    }
+  }
+}
 
 template <bool EXOTIC>
 __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const uint2* sin, const uint32_t* ssel, uint2* sout,
@@ -427,12 +453,14 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
     const uint32_t v = ssel[(k - 2 * lane) & 127];
     uint32_t xh = __shfl_up_sync(0xFFFFFFFFu, L.out_h, 1);
     uint32_t xe = __shfl_up_sync(0xFFFFFFFFu, L.out_e, 1);
+    // arg-max of the PREVIOUS step while the shuffles and ring loads are in flight (software-pipelined by one step: the
+    // data-dependent branch no longer sits between a step's last row and the next step's shuffle)
+    wave16_track(L, k - 1, ncol, lane);
     if (lane == 0) { xh = top.x << 16; xe = top.y << 16; }
     uint32_t up = prmt(xh, L.out_h, 0x5432);       // low half <- lane above, high strip; high half <- own low strip, previous step
     uint32_t e = prmt(xe, L.out_e, 0x5432);
     const uint32_t sel = (v & 0xFFu) | L.prevsh;
     L.prevsh = (v & 0xFFu) * 256u + 0x4400u;
-    uint32_t hh[8];
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       uint32_t s2;
@@ -445,34 +473,11 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
       const uint32_t h = __vimax3_s16x2_relu(d, L.f[r], e);
       L.f[r] = __viaddmax_s16x2(L.f[r], neg_ext2, dm);
       e = __viaddmax_s16x2(e, neg_ext2, dm);
-      hh[r] = h; L.p[r] = up; up = h;
+      L.hh[r] = h; L.p[r] = up; up = h;
     }
     L.out_h = up; L.out_e = e;
     L.vprev = v;
     if (lane == 31) sout[k & 31] = make_uint2((uint32_t)(int)(short)(up >> 16), (uint32_t)(int)(short)(e >> 16));
-    // ---- arg-max: column maxima of both halves, then a rare divergent branch that resolves row and column ----
-    uint32_t cm = __vimax3_s16x2(hh[0], hh[1], hh[2]);
-    cm = __vimax3_s16x2(cm, hh[3], hh[4]);
-    cm = __vimax3_s16x2(cm, hh[5], hh[6]);
-    cm = __vmaxs2(cm, hh[7]);
-    const uint32_t nb = __vmaxs2(L.bestpk, cm);
-    if (nb != L.bestpk) {
-      L.bestpk = nb;
-      const int cL = k - 2 * lane, cH = cL - 1;
-      const int mL = (int)(short)(cm & 0xFFFFu), mH = (int)(short)(cm >> 16);
-      if (mL > L.bestL && cL >= 0 && cL < ncol) {
-        int rr = 7;
-#pragma unroll
-        for (int r = 6; r >= 0; r--) rr = ((int)(short)(hh[r] & 0xFFFFu) == mL) ? r : rr;
-        L.bestL = mL; L.bposL = (cL << 3) | rr;
-      }
-      if (mH > L.bestH && cH >= 0 && cH < ncol) {
-        int rr = 7;
-#pragma unroll
-        for (int r = 6; r >= 0; r--) rr = ((int)(short)(hh[r] >> 16) == mH) ? r : rr;
-        L.bestH = mH; L.bposH = (cH << 3) | rr;
-      }
-    }
   }
 }
 
@@ -519,7 +524,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave16_local(const WaveArgs
         ta |= ((uint32_t)score_general(sc, qcodes[i], ca) & 0xFFu) << (8 * i);
         tb |= ((uint32_t)score_general(sc, qcodes[i], cb) & 0xFFu) << (8 * i);
       }
-      L.rowA[r] = ta; L.rowB[r] = tb; L.p[r] = 0; L.f[r] = 0;
+      L.rowA[r] = ta; L.rowB[r] = tb; L.p[r] = 0; L.f[r] = 0; L.hh[r] = 0;
     }
     L.out_h = 0; L.out_e = 0; L.prevsh = 0xCC00u; L.vprev = 0x88u; L.bestpk = 0; L.bestL = L.bestH = 0; L.bposL = L.bposH = 0;
 #pragma unroll
@@ -574,6 +579,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave16_local(const WaveArgs
         __syncwarp();
       }
     }
+    wave16_track(L, nsteps - 1, ncol, lane);                    // the last step's arg-max is still pending
     int2* cand = w.cand + w.soff[pair];
     if (lstrip < g.nstrips) __stcg(&cand[lstrip], make_int2(L.bestL, L.bposL));
     if (lstrip + 1 < g.nstrips) __stcg(&cand[lstrip + 1], make_int2(L.bestH, L.bposH));
