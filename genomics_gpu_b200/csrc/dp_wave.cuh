@@ -481,7 +481,10 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
   }
 }
 
-__global__ void __launch_bounds__(kWaveWarps * 32) k_wave16_local(const WaveArgs w) {
+#ifndef WAVE16_MIN_CTAS
+#define WAVE16_MIN_CTAS 4
+#endif
+__global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_local(const WaveArgs w) {
   __shared__ uint2 s_in[kWaveWarps][32];
   __shared__ uint32_t s_sel[kWaveWarps][128];
   __shared__ uint2 s_out[kWaveWarps][32];
@@ -701,7 +704,8 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   cudaMemcpyAsync(ws.soff, ws.h_off + n, n * sizeof(uint64_t), cudaMemcpyHostToDevice, str);
   WaveArgs wa; wa.a = a; wa.algo = algo; wa.maxblk = maxblk; wa.qoff = ws.qoff; wa.soff = ws.soff;
   wa.bnd = ws.bnd; wa.bnd_stride = qs; wa.cand = ws.cand; wa.done = ws.prog; wa.ticket = ws.prog + n;
-  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_sm * 4, (tasks + kWaveWarps - 1) / kWaveWarps));   // <= 16 warp-workers per SM
+  const int ctas_per_sm = use_s16 ? WAVE16_MIN_CTAS : 4;
+  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_sm * ctas_per_sm, (tasks + kWaveWarps - 1) / kWaveWarps));   // <= 16 (24) warp-workers per SM
   int launches = 0;
   for (int pass = 0; pass < npass; pass++) {
     cudaMemsetAsync(ws.prog, 0, prog_words * sizeof(uint32_t), str);

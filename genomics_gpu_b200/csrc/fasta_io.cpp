@@ -1,5 +1,5 @@
 // fasta_io.cpp -- the caller-side I/O step of the GASAL2 path, native and GPU-free:
-//   * gasalx_read_fasta_pairs: two FASTA files (plain or gzip) -> the engine's host layout in one pass
+//   * gasalx_read_fasta_pairs: two FASTA or FASTQ files (plain or gzip; the format is sniffed per file) -> the engine's host layout in one pass
 //     (concatenated sequences padded with N to a multiple of 8, 64-bit offsets, lengths, per-sequence ops), ready for
 //     gasalx_align_all or for slicing into gasal_host_batch_add.  The reference's only caller reads the files with a serial
 //     getline loop into std::vector<std::string> and copies every sequence again (test_prog.cpp:90-137, 289-313).
@@ -80,6 +80,39 @@ bool parse(const std::vector<char>& buf, Records& r, int n_code) {
   return true;
 }
 
+// FASTQ: strict 4-line records  @name / sequence / + / qualities  (qualities are skipped: the aligner is quality-free)
+bool parse_fastq(const std::vector<char>& buf, Records& r, int n_code) {
+  const char* p = buf.data(); const char* end = p + buf.size();
+  r.bytes.reserve(buf.size() / 2 + 64);
+  int line_in_rec = 0;
+  while (p < end) {
+    const char* nl = (const char*)memchr(p, '\n', (size_t)(end - p));
+    const char* le = nl ? nl : end;
+    const char* stop = le;
+    if (stop > p && stop[-1] == '\r') stop--;
+    if (line_in_rec == 0) {
+      if (stop == p) { p = nl ? nl + 1 : end; continue; }           // blank line between records
+      if (p[0] != '@') return false;
+      r.ops.push_back(0); r.offs.push_back(r.bytes.size());
+      r.names.append(p + 1, (size_t)(stop - p - 1)); r.names.push_back('\n');
+    } else if (line_in_rec == 1) {
+      const uint64_t start = r.bytes.size();
+      r.bytes.insert(r.bytes.end(), (const uint8_t*)p, (const uint8_t*)stop);
+      close_record(r, start, n_code);
+    } else if (line_in_rec == 2) {
+      if (stop == p || p[0] != '+') return false;
+    }
+    line_in_rec = (line_in_rec + 1) & 3;
+    p = nl ? nl + 1 : end;
+  }
+  return line_in_rec == 0 || line_in_rec == 3 ? (r.lens.size() == r.offs.size()) : false;
+}
+
+bool looks_like_fastq(const std::vector<char>& buf) {
+  for (char c : buf) { if (c == '\n' || c == '\r' || c == ' ') continue; return c == '@'; }
+  return false;
+}
+
 template <typename T>
 T* dup(const std::vector<T>& v) {
   T* p = (T*)malloc(std::max<size_t>(v.size(), 1) * sizeof(T));
@@ -97,7 +130,9 @@ int gasalx_read_fasta_pairs(const char* query_path, const char* target_path, int
   if (!slurp(query_path, qb)) { fprintf(stderr, "[GASAL ERROR:] cannot read %s\n", query_path); return -1; }
   if (!slurp(target_path, tb)) { fprintf(stderr, "[GASAL ERROR:] cannot read %s\n", target_path); return -1; }
   Records q, t;
-  if (!parse(qb, q, n_code) || !parse(tb, t, n_code)) { fprintf(stderr, "[GASAL ERROR:] malformed FASTA (sequence data before the first header)\n"); return -2; }
+  const bool okq = looks_like_fastq(qb) ? parse_fastq(qb, q, n_code) : parse(qb, q, n_code);
+  const bool okt = looks_like_fastq(tb) ? parse_fastq(tb, t, n_code) : parse(tb, t, n_code);
+  if (!okq || !okt) { fprintf(stderr, "[GASAL ERROR:] malformed FASTA / FASTQ input\n"); return -2; }
   if (q.lens.size() != t.lens.size()) {
     fprintf(stderr, "Batch1 and target_batch files should be fasta having same number of sequences\n");   // test_prog.cpp:131
     return -3;

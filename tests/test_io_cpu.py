@@ -57,3 +57,17 @@ def test_cigar_string():
     assert cigar_string(enc([(63, "M"), (63, "M"), (10, "M"), (2, "I"), (5, "M")]), 5) == "136M2I5M"   # runs capped at 63 are merged back
     assert cigar_string(enc([(7, "M")]), 1) == "7M"
     assert cigar_string(np.zeros(0, dtype=np.uint8), 0) == ""
+
+
+def test_fastq_reads_against_fasta_windows(tmp_path):
+    """queries as FASTQ (gzip), targets as FASTA: the format is sniffed per file; qualities are ignored"""
+    b = synth.random_ragged_pairs(50, 10, 150, 10, 300, seed=8)
+    with gzip.open(tmp_path / "q.fq.gz", "wb") as f:
+        for i in range(b.n):
+            s = b.query(i)
+            f.write(b"@read%d\n" % i + s + b"\n+\n" + b"I" * len(s) + b"\n")
+    write_fasta(str(tmp_path / "t.fa"), [b.target(i) for i in range(b.n)])
+    got, q_op, t_op, qn, tn = read_fasta_pairs(str(tmp_path / "q.fq.gz"), str(tmp_path / "t.fa"))
+    assert got.n == b.n and qn[7] == "read7"
+    assert np.array_equal(got.q_bytes, b.q_bytes) and np.array_equal(got.t_bytes, b.t_bytes)
+    assert np.array_equal(got.q_lens, b.q_lens) and not q_op.any()
