@@ -21,6 +21,8 @@
 #pragma once
 #include "dp_common.cuh"
 #include "dp_generic.cuh"
+#include <type_traits>
+#pragma nv_diag_suppress 128   // "loop is not reachable": k_local_s16<START_TB> returns before the score-only sweeps
 
 namespace gb200 {
 
@@ -29,7 +31,7 @@ namespace gb200 {
 #endif
 constexpr int kFastThreads = GB200_FAST_THREADS;
 constexpr uint32_t kFastMaxQ8 = 352;      // (q8 + kSlotPad) * 128 * 5 B must fit one CTA's shared memory
-constexpr uint32_t kSlotPad = 7;          // dummy column slots: 2 below column 0 (late lanes' phantom columns), 5 above the last column
+constexpr uint32_t kSlotPad = 8;          // dummy column slots: 2 below column 0 (late lanes' phantom columns), 6 above the last column
 constexpr uint32_t kFastFallbackSlots = 8192;
 
 struct FastScratch {
@@ -50,6 +52,7 @@ struct FastArgs {
   uint32_t* worklist; uint32_t* work_count;
   uint32_t eight;          // == 8, passed at run time so the key multiply stays an IMAD (FMA pipe)
   uint32_t one;            // == 1, run-time so that the sweep's trip count (columns + 1) is opaque to the unroller
+  uint32_t mm, sixteen;    // == 0x00204081 / 16, run-time so the direction-nibble gather stays on IMAD (FMA pipe)
 };
 
 __device__ __forceinline__ uint32_t splat16(int v) { const uint32_t u = (uint32_t)v & 0xFFFFu; return u | (u << 16); }
@@ -257,6 +260,123 @@ __device__ __forceinline__ Winner pick_winner4(const LaneBest4& lb) {
   return w;
 }
 
+// ---- direction matrix from the packed lanes (LOCAL WITH_TB fast path) ---------------------------------------------------
+// The four predicates of a direction nibble (local_kernel_template.h:45-60) are read off SIGN BITS of packed differences that
+// cost one VIADD.16x2 each on the FMA pipe:
+//   bit3 (F extended)  <=>  D-oe <= F-e   <=>  sign((D-oe-1) - (F-e))
+//   bit2 (E extended)  <=>  D-oe <= E-e   <=>  sign((D-oe-1) - (E-e))
+//   bit1               <=>  H != D        <=>  sign(D - H)                     (H >= D always)
+//   bit0               <=>  H == D ? S < 0 : H == F   =  (~a & sign(S)) | (a & ~sign(F - H)), one LOP3 on the sign words
+// Two PRMTs gather the sign-carrying bytes of the four words lane by lane, and one multiply by 0x00204081 moves the four sign
+// bits of a lane into one nibble (the "movemask" multiplication), which a second multiply-add appends to the row word:
+// 9 ALU + 11 FMA-pipe instructions per cell pair on top of the recurrence, no compares, no selects.
+__device__ __forceinline__ uint32_t lop3_code0(uint32_t a, uint32_t b, uint32_t s) {   // (~a & s) | (a & ~b)
+  uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x3a;" : "=r"(d) : "r"(a), "r"(b), "r"(s)); return d;
+}
+
+__device__ __forceinline__ void tb_nibbles(uint32_t d, uint32_t dm, uint32_t h, uint32_t f, uint32_t e, uint32_t s2,
+                                           uint32_t neg_ext2, uint32_t minus1_2, uint32_t mm, uint32_t sixteen, uint32_t& wL, uint32_t& wH) {
+  const uint32_t fe = __vadd2(f, neg_ext2), ee = __vadd2(e, neg_ext2), dm1 = __vadd2(dm, minus1_2);
+  const uint32_t qf = __vsub2(dm1, fe), qe = __vsub2(dm1, ee), a = __vsub2(d, h), b = __vsub2(f, h);
+  const uint32_t c0 = lop3_code0(a, b, s2);
+  const uint32_t g1 = prmt(c0, a, 0x7351);          // [c0.L, a.L, c0.H, a.H]   (sign-carrying bytes)
+  const uint32_t g2 = prmt(qe, qf, 0x7351);         // [qe.L, qf.L, qe.H, qf.H]
+  const uint32_t xl = prmt(g1, g2, 0x5410) & 0x80808080u, xh = prmt(g1, g2, 0x7632) & 0x80808080u;
+  wL = wL * sixteen + ((xl * mm) >> 28);
+  wH = wH * sixteen + ((xh * mm) >> 28);
+}
+
+// One quad-strip sweep with direction output.  tb points at this thread's element of tile 0 of strip 4j (A.L); tiles of one
+// strip are 2*QR apart; `ts` = tb_stride.  valid[i]: strip 4j+i exists.  Each lane keeps the words of its last four columns
+// in a 4-deep shift register and stores them as one uint4 when its column index reaches 3 mod 4; the lanes are one column
+// apart, so exactly one of the four stores fires per step.  (A 4x unrolled variant with compile-time phases was 40 KB of
+// code and ran at the speed of the int32 kernel: instruction-cache bound.)
+__device__ __forceinline__ void tb_push(uint32_t (&d)[4], uint32_t w) { d[0] = d[1]; d[1] = d[2]; d[2] = d[3]; d[3] = w; }
+
+__device__ __forceinline__ void tb_flush(uint4* __restrict__ tb, size_t ts, int QR2, int k, int ncol,
+                                         uint32_t (&dAL)[4], uint32_t (&dAH)[4], uint32_t (&dBL)[4], uint32_t (&dBH)[4],
+                                         uint32_t wAL, uint32_t wAH, uint32_t wBL, uint32_t wBH, const bool (&valid)[4]) {
+  tb_push(dAL, wAL); tb_push(dAH, wAH); tb_push(dBL, wBL); tb_push(dBH, wBH);
+  const int ph = k & 3;
+  if (ph == 3) { const int c = k;     if (valid[0] && c < ncol)           tb[(size_t)(0 * QR2 + (c >> 2)) * ts] = make_uint4(dAL[0], dAL[1], dAL[2], dAL[3]); }
+  if (ph == 0) { const int c = k - 1; if (valid[1] && c >= 3 && c < ncol) tb[(size_t)(1 * QR2 + (c >> 2)) * ts] = make_uint4(dAH[0], dAH[1], dAH[2], dAH[3]); }
+  if (ph == 1) { const int c = k - 2; if (valid[2] && c >= 3 && c < ncol) tb[(size_t)(2 * QR2 + (c >> 2)) * ts] = make_uint4(dBL[0], dBL[1], dBL[2], dBL[3]); }
+  if (ph == 2) { const int c = k - 3; if (valid[3] && c >= 3 && c < ncol) tb[(size_t)(3 * QR2 + (c >> 2)) * ts] = make_uint4(dBH[0], dBH[1], dBH[2], dBH[3]); }
+}
+
+__device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int ncol,
+                                                const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                                const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                                uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t one, uint32_t mm, uint32_t sixteen, uint32_t pos_base,
+                                                LaneBest4& lb, uint4* __restrict__ tb, size_t ts, int QR2, const bool (&valid)[4]) {
+  uint32_t pA[8], fA[8], pB[8], fB[8], keyA[8], keyB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { pA[r] = 0; fA[r] = 0; pB[r] = 0; fB[r] = 0; keyA[r] = 0; keyB[r] = 0; }
+  uint32_t dAL[4] = {0, 0, 0, 0}, dAH[4] = {0, 0, 0, 0}, dBL[4] = {0, 0, 0, 0}, dBH[4] = {0, 0, 0, 0};
+  uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
+  uint32_t prevsh = 0xCC00u;
+  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;
+  uint32_t he = HE[kFastThreads];
+  uint32_t v = V[kFastThreads];
+  uint32_t pos = pos_base;
+  const uint32_t minus1_2 = 0xFFFFFFFFu;
+  const int nsteps = ncol + 2 + (int)one;          // run-time 1: opaque trip count (see the compiler note in DESIGN.md)
+#pragma unroll 1
+  for (int k = 0; k < nsteps; k++) {
+    const uint32_t selA = v | prevsh;
+    prevsh = v * 256u + 0x4400u;
+    uint32_t upA = prmt(he, h8A, 0x5410);
+    uint32_t eA = prmt(he, eoA, 0x5432);
+    uint32_t upB = prmt(h8A, h8B, 0x5432);
+    uint32_t eB = prmt(eoA, eoB, 0x5432);
+    he = HE[(k + 2) * kFastThreads];
+    v = V[(k + 2) * kFastThreads];
+    {
+      const uint32_t cm = key_tree(keyA);
+      track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+      const uint32_t cn = key_tree(keyB);
+      track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+      pos = pos_base + (uint32_t)k;
+    }
+    uint32_t wAL = 0, wAH = 0, wBL = 0, wBH = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      {
+        const uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        const uint32_t d = __vadd2(pA[r], s2);
+        const uint32_t dm = __vadd2(d, neg_oe2);
+        const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
+        tb_nibbles(d, dm, h, fA[r], eA, s2, neg_ext2, minus1_2, mm, sixteen, wAL, wAH);
+        fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, dm);
+        eA = __viaddmax_s16x2(eA, neg_ext2, dm);
+        keyA[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+        pA[r] = upA; upA = h;
+      }
+      {
+        const uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        const uint32_t d = __vadd2(pB[r], s2);
+        const uint32_t dm = __vadd2(d, neg_oe2);
+        const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
+        tb_nibbles(d, dm, h, fB[r], eB, s2, neg_ext2, minus1_2, mm, sixteen, wBL, wBH);
+        fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, dm);
+        eB = __viaddmax_s16x2(eB, neg_ext2, dm);
+        keyB[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+        pB[r] = upB; upB = h;
+      }
+    }
+    HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+    h8A = upA; eoA = eA; h8B = upB; eoB = eB;
+    selB = selA_prev; selA_prev = selA;
+    tb_flush(tb, ts, QR2, k, ncol, dAL, dAH, dBL, dBH, wAL, wAH, wBL, wBH, valid);
+  }
+  {
+    const uint32_t cm = key_tree(keyA);
+    track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+    const uint32_t cn = key_tree(keyB);
+    track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+  }
+}
+
 template <int START>
 __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
@@ -291,7 +411,7 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     }
   }
 #pragma unroll
-  for (int x = 1; x <= 4; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = 0; }
+  for (int x = 1; x <= 5; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = 0; }
   for (int i = 0; i < TR && !odd; i++) {
     const uint32_t w = tw[i];
 #pragma unroll
@@ -307,6 +427,29 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   LaneBest4 lb; lanebest_init(lb.a); lanebest_init(lb.b);
   const int NQ = (TR + 3) >> 2;
   const int nsteps = ncol + 2 + (int)fa.one;   // run-time 1: keeps the trip count opaque (compiler note)
+  if (START == START_TB) {
+    // WITH_TB: same sweep, plus the 4-bit direction matrix in the reference's tile layout (local_kernel_template.h:257,380):
+    // tile (strip * QR + word) * 2 + half of pair `tid` at tb[tile * tb_stride + tid]; get_tb walks it afterwards
+    for (int j = 0; j < NQ; j++) {
+      uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
+      const bool valid[4] = {4 * j < TR, 4 * j + 1 < TR, 4 * j + 2 < TR, 4 * j + 3 < TR};
+      const uint32_t wa = tw[4 * j];
+      const uint32_t wb = valid[1] ? tw[4 * j + 1] : 0u;
+      const uint32_t wc = valid[2] ? tw[4 * j + 2] : 0u;
+      const uint32_t wd = valid[3] ? tw[4 * j + 3] : 0u;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
+        rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
+      }
+      uint4* tbq = a.tb + (size_t)(4 * j) * (size_t)(2 * QR) * a.tb_stride + tid;
+      local_sweep4_tb(HE, V, ncol, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, fa.mm, fa.sixteen, (uint32_t)j << 16, lb,
+                      tbq, (size_t)a.tb_stride, 2 * QR, valid);
+    }
+    const Winner tw_ = pick_winner4(lb);
+    a.score[tid] = tw_.score; a.q_end[tid] = tw_.col; a.t_end[tid] = tw_.row;
+    return;
+  }
   for (int j = 0; j < NQ; j++) {
     uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
     const uint32_t wa = tw[4 * j];
@@ -761,7 +904,8 @@ __global__ void __launch_bounds__(128) k_worklist(const FastArgs fa) {
     p.cs = a.colstate + gtid; p.stride = a.col_stride;
     if (ALGO == ALGO_LOCAL) {
       int best, bq, bt;
-      local_forward<false, false>(a, sc, p, pi, best, bq, bt);
+      if (START == START_TB) local_forward<true, false>(a, sc, p, pi, best, bq, bt);
+      else local_forward<false, false>(a, sc, p, pi, best, bq, bt);
       a.score[pi] = best; a.q_end[pi] = bq; a.t_end[pi] = bt;
       if (START == START_POS) { int sx, sy; local_reverse(sc, p, best, bq, bt, sx, sy); a.q_start[pi] = sx; a.t_start[pi] = sy; }
     } else if (ALGO == ALGO_SEMI_GLOBAL) {
@@ -776,7 +920,7 @@ __global__ void k_zero_u32(uint32_t* p) { *p = 0; }
 
 // ---- host side --------------------------------------------------------------------------------------
 inline bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
-  if (second || start == START_TB) return false;
+  if (second || (start == START_TB && algo != ALGO_LOCAL)) return false;
   const uint32_t q8 = (max_q + 7u) & ~7u, t8 = (max_t + 7u) & ~7u;
   if (q8 == 0 || q8 > kFastMaxQ8 || t8 == 0) return false;
   if (a.match < 0 || a.match > 127 || a.mismatch < 0 || a.mismatch > 127) return false;
@@ -818,12 +962,13 @@ inline int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& f
     if (cudaMalloc(&fs.colstate, cs_need * sizeof(uint32_t)) != cudaSuccess) return -1;
     fs.colstate_words = cs_need;
   }
-  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.work_count = fs.work_count; fa.eight = 8; fa.one = 1;
+  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.work_count = fs.work_count; fa.eight = 8; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
   const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads;
   if (!fs.attr_set) {
     const int lim = 227 * 1024;
     cudaFuncSetAttribute(k_local_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_local_s16<START_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_global_s16, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -832,13 +977,20 @@ inline int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& f
   k_zero_u32<<<1, 1, 0, str>>>(fs.work_count);
   const uint32_t blocks = ((uint32_t)a.n + kFastThreads - 1) / kFastThreads;
   const bool sp = (start == START_POS);
-  if (algo == ALGO_LOCAL) { if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
+  const bool tbm = (start == START_TB);
+  if (algo == ALGO_LOCAL) {
+    if (tbm) k_local_s16<START_TB><<<blocks, kFastThreads, smem, str>>>(fa);
+    else if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
+  }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
   else k_global_s16<<<blocks, kFastThreads, smem, str>>>(fa);
   // fallback pairs (bases outside A/C/G/T): general kernel over the worklist, bounded scratch
   fa.a.colstate = fs.colstate; fa.a.col_stride = kFastFallbackSlots; fa.a.col_rows = q8;
   const int wb = kFastFallbackSlots / 128;
-  if (algo == ALGO_LOCAL) { if (sp) k_worklist<ALGO_LOCAL, START_POS><<<wb, 128, 0, str>>>(fa); else k_worklist<ALGO_LOCAL, START_NONE><<<wb, 128, 0, str>>>(fa); }
+  if (algo == ALGO_LOCAL) {
+    if (tbm) k_worklist<ALGO_LOCAL, START_TB><<<wb, 128, 0, str>>>(fa);
+    else if (sp) k_worklist<ALGO_LOCAL, START_POS><<<wb, 128, 0, str>>>(fa); else k_worklist<ALGO_LOCAL, START_NONE><<<wb, 128, 0, str>>>(fa);
+  }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_worklist<ALGO_SEMI_GLOBAL, START_POS><<<wb, 128, 0, str>>>(fa); else k_worklist<ALGO_SEMI_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa); }
   else k_worklist<ALGO_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa);
   return 3;

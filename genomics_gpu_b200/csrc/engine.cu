@@ -547,6 +547,10 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
     const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, s->str);
     if (nl < 0) { fprintf(stderr, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); exit(EXIT_FAILURE); }
     CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "s16x2";
+    if (want_tb) {                                                                        // gasal_align.h:45-53
+      const uint32_t nb = (n + 127) / 128;
+      k_get_tb<true><<<nb, 128, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
+    }
     return;
   }
 

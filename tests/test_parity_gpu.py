@@ -53,12 +53,15 @@ def test_local_second_best(oracle):
     assert_same(got, want, K3 + K2ND, "local second-best")
 
 
-@pytest.mark.parametrize("scoring", SCORINGS[:2])
-def test_local_traceback(oracle, scoring):
-    b = ragged(14, n=300)
+@pytest.mark.parametrize("scoring", SCORINGS)
+@pytest.mark.parametrize("policy,kernel", [(0, "s16x2"), (1, "int32")])
+def test_local_traceback(oracle, scoring, policy, kernel):
+    """policy 0: direction matrix from the packed s16x2 lanes (sign-bit gather); policy 1: the general int32 kernel"""
+    b = ragged(14, n=600)
     want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_TB, scoring=scoring)
-    got = run(b, algo=capi.LOCAL, start=capi.WITH_TB, scoring=scoring)
-    assert_same(got, want, K5 + ["n_cigar_ops"], "local tb")
+    got = run(b, policy=policy, algo=capi.LOCAL, start=capi.WITH_TB, scoring=scoring)
+    assert got["_kernel"] == kernel
+    assert_same(got, want, K5 + ["n_cigar_ops"], f"local tb {kernel}")
     gc, wc = cigar_slices(got, b), cigar_slices(want, b)
     assert gc == wc
     if scoring == (1, 4, 6, 1):
