@@ -53,7 +53,9 @@ def make_workload(n_pairs: int, seed: int):
 
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi sampled every 50 ms during the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled
+    in-process every 5 ms (the timed region of the default run is well under a second, too short for `nvidia-smi -lms` to
+    start up on an 8-GPU box); nvidia-smi is the fallback when the NVML binding is missing."""
 
     Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
@@ -62,8 +64,45 @@ class ClockSampler:
         self.gpu = gpu_index
         self.proc = None
         self.lines = []
+        self.samples = []          # (sm_mhz, power_w, reasons_bitmask)
+        self.sm_max = None
+        self.nvml = None
+        self.stop_flag = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = nvml_handle_for_cuda_index(pynvml, gpu_index)
+            self.sm_max = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nvml = None
+
+    def _poll(self):
+        nv = self.nvml
+        while not self.stop_flag.is_set():
+            try:
+                sm = float(nv.nvmlDeviceGetClockInfo(self.handle, nv.NVML_CLOCK_SM))
+                try:
+                    pw = nv.nvmlDeviceGetPowerUsage(self.handle) / 1000.0
+                except Exception:
+                    pw = None
+                try:
+                    rs = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+                except Exception:
+                    try:
+                        rs = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+                    except Exception:
+                        rs = 0
+                self.samples.append((sm, pw, rs))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.005)
 
     def start(self):
+        if self.nvml is not None:
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(self.gpu)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -77,6 +116,17 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        if self.nvml is not None:
+            self.stop_flag.set(); self.thread.join(timeout=1)
+            # NVML reason bits: 0x4 sw_power_cap, 0x8 hw_slowdown, 0x20 sw_thermal_slowdown, 0x40 hw_thermal_slowdown
+            bits = {"sw_power_cap": 0x4, "hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40}
+            sm = [x[0] for x in self.samples]
+            loaded_idx = [i for i, v in enumerate(sm) if v > 0.5 * max(sm)] if sm else []
+            reasons = sorted({nm for i in loaded_idx for nm, b in bits.items() if self.samples[i][2] & b})
+            power = [x[1] for x in self.samples if x[1] is not None]
+            return {"sm_mhz": statistics.median([sm[i] for i in loaded_idx]) if loaded_idx else None, "sm_max_mhz": self.sm_max,
+                    "power_w_max": max(power) if power else None, "samples": len(sm), "source": "nvml, 5 ms poll", "reasons": reasons}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -85,7 +135,6 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, power, reasons = [], [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 8:
@@ -100,7 +149,39 @@ class ClockSampler:
         # samples under load only (the box idles at ~120 MHz between launches)
         loaded = [s for s in sm if s > 0.5 * max(sm)] if sm else []
         return {"sm_mhz": statistics.median(loaded) if loaded else None, "sm_max_mhz": max(smax) if smax else None,
-                "power_w_max": max(power) if power else None, "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": max(power) if power else None, "samples": len(sm), "source": "nvidia-smi -lms 50", "reasons": sorted(reasons)}
+
+
+def nvml_handle_for_cuda_index(pynvml, cuda_index: int):
+    """NVML handle of the CUDA device `cuda_index` of this process (PCI bus id match, so CUDA_VISIBLE_DEVICES is honoured)."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(cuda_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(cuda_index), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(cuda_index).pci_device_id
+        return pynvml.nvmlDeviceGetHandleByPciBusId(f"{dom:08x}:{bus:02x}:{dev:02x}.0".encode())
+    except Exception:
+        return pynvml.nvmlDeviceGetHandleByIndex(cuda_index)
+
+
+def bind_to_gpu_numa_node(cuda_index: int):
+    """Run this rank on the CPUs NVML reports as local to its GPU, so the pinned staging pages of the e2e arm are allocated
+    (first touch) on the GPU's NUMA node.  Returns the previous affinity set (restored before the CPU baseline), or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = nvml_handle_for_cuda_index(pynvml, cuda_index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (int(m) >> b) & 1}
+        prev = os.sched_getaffinity(0)
+        want = cpus & prev
+        if want and want != prev:
+            os.sched_setaffinity(0, want)
+            return prev
+    except Exception:
+        pass
+    return None
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -239,6 +320,7 @@ def run_ours(args, rank, world, local_rank):
 
     lib = capi.load()
     lib.gasal_set_device(local_rank, 0)
+    prev_affinity = bind_to_gpu_numa_node(local_rank) if args.numa_bind else None
     n = args.pairs
     batch = make_workload(n, seed=2 + rank)
     cells_mode = batch.cells
@@ -372,7 +454,9 @@ def run_ours(args, rank, world, local_rank):
     pack_bytes = 1.5 * (q_bytes + t_bytes)
     pack_gbs = pack_bytes / (statistics.mean(pack_ms.values()) * 1e-3) / 1e9
 
-    cpu_threads = os.cpu_count() or 1
+    if prev_affinity:
+        os.sched_setaffinity(0, prev_affinity)      # the CPU baseline uses every host core
+    cpu_threads = len(os.sched_getaffinity(0)) or 1
     cpu_val, cpu_kind, cpu_n, cpu_dt = cpu_baseline_run(batch, args.cpu_pairs, cpu_threads)
     refgpu = ref_gpu_baseline(batch, args.refgpu_pairs) if args.refgpu_pairs > 0 else {"unavailable": "disabled"}
     extras = run_extras(local_rank, 262_144) if args.extras else {"skipped": True}
@@ -416,7 +500,8 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--numa-bind", type=int, default=1, help="bind each rank to the CPUs local to its GPU (NVML affinity)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per mode")

@@ -119,14 +119,27 @@ class Aligner:
                     out[k + "2"] = v.copy()
         return out
 
-    def align(self, batch: PairBatch, i: int = 0, q_op=None, t_op=None, seeds=None) -> Dict[str, np.ndarray]:
-        """fill -> gasal_aln_async -> wait -> results, for one batch on storage i."""
+    def align(self, batch: PairBatch, i: int = 0, q_op=None, t_op=None, seeds=None, cigar_text_style: Optional[int] = None,
+              cigar_stride: int = 64) -> Dict[str, np.ndarray]:
+        """fill -> gasal_aln_async -> wait -> results, for one batch on storage i.  With cigar_text_style (0 reference
+        letters / 1 SAM) the CIGAR text is formatted on the device in the same stream: out["cigar_text"] is a list of str."""
         self.fill(i, batch, q_op, t_op)
         if seeds is not None:
             self.set_seed_scores(i, seeds)
         self.launch(i, batch.q_bytes.size, batch.t_bytes.size, batch.n)
+        text = lens = None
+        if cigar_text_style is not None:
+            text = np.zeros(batch.n * cigar_stride, dtype=np.uint8); lens = np.zeros(batch.n, dtype=np.uint32)
+            rc = self.lib.gasalx_cigar_text_async(C.byref(self.vec.a[i]), cigar_text_style, text.ctypes.data, cigar_stride, lens.ctypes.data)
+            if rc != 0:
+                raise RuntimeError("gasalx_cigar_text_async: the storage holds no traceback results (start must be WITH_TB)")
         self.wait(i)
-        return self.results(i, batch.n, batch.q_bytes.size)
+        out = self.results(i, batch.n, batch.q_bytes.size)
+        if text is not None:
+            out["cigar_text_lens"] = lens
+            rows = text.reshape(batch.n, cigar_stride)
+            out["cigar_text"] = [rows[p, :min(int(lens[p]) & 0x7FFFFFFF, cigar_stride - 1)].tobytes().decode() for p in range(batch.n)]
+        return out
 
     def last_ms(self, i: int):
         buf = (C.c_float * 3)()
@@ -243,4 +256,15 @@ def cigar_string(cigar_bytes: np.ndarray, n_ops: int) -> str:
     n = capi.load().gasalx_cigar_string(c.ctypes.data, n_ops, buf, len(buf))
     if n < 0:
         raise RuntimeError("cigar buffer too small")
+    return buf.value.decode()
+
+
+def sam_record(qname: str, flag: int, rname: str, pos1: int, mapq: int, cigar: str, seq: Optional[bytes], qual: Optional[bytes],
+               score: int, score2: int = -1) -> str:
+    """One SAM line through the C ABI (gasalx_sam_record)."""
+    n = len(seq) if seq else 0
+    buf = C.create_string_buffer(256 + len(qname) + len(rname) + len(cigar) + 2 * n)
+    r = capi.load().gasalx_sam_record(buf, len(buf), qname.encode(), flag, rname.encode(), pos1, mapq, cigar.encode(), seq, n, qual, score, score2)
+    if r < 0:
+        raise RuntimeError("sam buffer too small")
     return buf.value.decode()

@@ -93,6 +93,7 @@ EXPORTED_SYMBOLS = [
     "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
     "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all", "gasalx_batcher_release",
     "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_cigar_string",
+    "gasalx_cigar_text_async", "gasalx_sam_record",
 ]
 
 
@@ -148,5 +149,9 @@ def load() -> C.CDLL:
     lib.gasalx_free_fasta_pairs.argtypes = [P(FastaPairs)]
     lib.gasalx_pack_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
     lib.gasalx_cigar_string.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]; lib.gasalx_cigar_string.restype = C.c_int
+    lib.gasalx_cigar_text_async.argtypes = [P(GpuStorage), C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]; lib.gasalx_cigar_text_async.restype = C.c_int
+    lib.gasalx_sam_record.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_int, C.c_char_p, C.c_int64, C.c_int, C.c_char_p, C.c_char_p, C.c_uint32,
+                                      C.c_char_p, C.c_int32, C.c_int32]
+    lib.gasalx_sam_record.restype = C.c_int
     _lib = lib
     return lib

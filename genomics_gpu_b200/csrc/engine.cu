@@ -52,6 +52,9 @@ struct Priv {
   uint64_t launches = 0;
   const char* last_kernel = "none";
   int max_query_len_8 = 0, max_target_len_8 = 0;
+  char* d_text = nullptr; size_t text_bytes = 0;             // gasalx_cigar_text_async
+  uint32_t* d_text_lens = nullptr; size_t text_lens_cap = 0;
+  uint32_t tb_n = 0; int tb_algo = 0;                         // pairs / algo of the last WITH_TB batch (0: none)
 };
 
 inline Priv* priv(gasal_gpu_storage_t* s) { return (Priv*)s->b200_priv; }
@@ -427,6 +430,8 @@ void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_par
       if (pv->colstate) CHECKCUDAERROR(cudaFree(pv->colstate));
       if (pv->d_cigar) CHECKCUDAERROR(cudaFree(pv->d_cigar));
       if (pv->d_n_cigar_ops) CHECKCUDAERROR(cudaFree(pv->d_n_cigar_ops));
+      if (pv->d_text) CHECKCUDAERROR(cudaFree(pv->d_text));
+      if (pv->d_text_lens) CHECKCUDAERROR(cudaFree(pv->d_text_lens));
       pv->fast.release();
       pv->wave.release();
       for (int e = 0; e < 4; e++) if (pv->ev[e]) CHECKCUDAERROR(cudaEventDestroy(pv->ev[e]));
@@ -541,6 +546,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
     if (pv->n_cigar_cap < n) { dev_realloc(&pv->d_n_cigar_ops, n); pv->n_cigar_cap = n; }
     a.cigar = pv->d_cigar; a.n_cigar_ops = pv->d_n_cigar_ops;
   }
+  pv->tb_n = want_tb ? n : 0; pv->tb_algo = want_tb ? params->algo : 0;
 
   // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
   if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
@@ -741,6 +747,23 @@ void gasalx_host_batch_rearm(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t 
     }
   }
   s->current_n_alns = n_alns;
+}
+
+int gasalx_cigar_text_async(gasal_gpu_storage_t* s, int style, char* host_text, uint32_t stride, uint32_t* host_lens) {
+  Priv* pv = priv(s);
+  if (!pv || pv->tb_n == 0 || !pv->d_cigar || !host_text || !host_lens || stride < 2) return -1;
+  const uint32_t n = pv->tb_n;
+  const size_t bytes = (size_t)n * stride;
+  if (pv->text_bytes < bytes) { dev_realloc(&pv->d_text, bytes); pv->text_bytes = bytes; }
+  if (pv->text_lens_cap < n) { dev_realloc(&pv->d_text_lens, n); pv->text_lens_cap = n; }
+  const bool local_like = (pv->tb_algo == LOCAL || pv->tb_algo == BANDED);        // start/end cells exist: soft clips
+  k_cigar_text<<<(n + 127) / 128, 128, 0, s->str>>>(pv->d_cigar, pv->d_n_cigar_ops, s->query_batch_offsets, s->query_batch_lens,
+                                                    s->device_cpy->query_batch_start, s->device_cpy->query_batch_end,
+                                                    (int)n, style, local_like ? 1 : 0, pv->d_text, stride, pv->d_text_lens);
+  CHECK_LAUNCH(); pv->launches++;
+  CHECKCUDAERROR(cudaMemcpyAsync(host_text, pv->d_text, bytes, cudaMemcpyDeviceToHost, s->str));
+  CHECKCUDAERROR(cudaMemcpyAsync(host_lens, pv->d_text_lens, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->str));
+  return 0;
 }
 
 uint64_t gasalx_kernel_launches(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return pv ? pv->launches : 0; }

@@ -186,4 +186,24 @@ int gasalx_cigar_string(const uint8_t* cigar, uint32_t n_ops, char* out, uint32_
   return (int)s.size();
 }
 
+// SAM v1 mandatory fields + AS/XS tags; RNEXT/PNEXT/TLEN are "*", 0, 0 (single-end)
+int gasalx_sam_record(char* out, uint32_t cap, const char* qname, int flag, const char* rname, int64_t pos1, int mapq,
+                      const char* cigar, const char* seq, uint32_t seq_len, const char* qual, int32_t score, int32_t score2) {
+  std::string s;
+  s += (qname && *qname) ? qname : "*"; s.push_back('\t');
+  s += std::to_string(flag); s.push_back('\t');
+  s += (rname && *rname) ? rname : "*"; s.push_back('\t');
+  s += std::to_string((long long)pos1); s.push_back('\t');
+  s += std::to_string(mapq); s.push_back('\t');
+  s += (cigar && *cigar) ? cigar : "*"; s += "\t*\t0\t0\t";
+  if (seq && seq_len) s.append(seq, seq_len); else s.push_back('*');
+  s.push_back('\t');
+  if (qual && seq_len) s.append(qual, seq_len); else s.push_back('*');
+  s += "\tAS:i:" + std::to_string(score);
+  if (score2 >= 0) s += "\tXS:i:" + std::to_string(score2);
+  if (s.size() + 1 > cap) return -(int)(s.size() + 1);
+  memcpy(out, s.c_str(), s.size() + 1);
+  return (int)s.size();
+}
+
 }  // extern "C"

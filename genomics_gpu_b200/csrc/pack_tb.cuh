@@ -150,4 +150,47 @@ __global__ void __launch_bounds__(128) k_get_tb(const DpArgs a) {
   a.n_cigar_ops[tid] = (uint32_t)n_ops;
 }
 
+// ---- K5: CIGAR text on the device -----------------------------------------------------------------
+// The reference leaves text formatting to a serial host loop (test_prog.cpp:382-428: walk the (count<<2)|op bytes from
+// the LAST one to the first, merge neighbouring runs of the same op, print "<count><op>").  Here one thread per pair does
+// the same walk on the device and writes the text of pair p at text[p * stride]; lens[p] = characters written.
+// style 0: the reference's letters M / X / D / I.   style 1: SAM CIGAR -- M and X merge into M, and for LOCAL the clipped
+// query ends become soft clips (q_start leading, q_len - 1 - q_end trailing).  If the text does not fit in stride - 1
+// characters it is truncated and lens[p] = 0x80000000 | needed length.
+__device__ __forceinline__ void cigar_emit(char* out, uint32_t cap, uint32_t& len, uint32_t count, char op) {
+  char d[10]; int nd = 0;
+  do { d[nd++] = (char)('0' + count % 10u); count /= 10u; } while (count);
+  while (nd > 0) { --nd; if (len < cap) out[len] = d[nd]; len++; }
+  if (len < cap) out[len] = op;
+  len++;
+}
+
+__global__ void __launch_bounds__(128) k_cigar_text(const uint8_t* __restrict__ cigar, const uint32_t* __restrict__ n_cigar_ops,
+                                                     const uint32_t* __restrict__ q_offs, const uint32_t* __restrict__ q_lens,
+                                                     const int32_t* __restrict__ q_start, const int32_t* __restrict__ q_end,
+                                                     int n, int style, int clip, char* __restrict__ text, uint32_t stride, uint32_t* __restrict__ lens) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (uint32_t)n) return;
+  const uint8_t* c = cigar + q_offs[tid];
+  const uint32_t nops = n_cigar_ops[tid];
+  char* out = text + (size_t)tid * stride;
+  const uint32_t cap = stride ? stride - 1 : 0;
+  uint32_t len = 0;
+  const char opc[4] = {'M', style ? 'M' : 'X', 'D', 'I'};
+  if (style && clip && q_start[tid] > 0) cigar_emit(out, cap, len, (uint32_t)q_start[tid], 'S');
+  if (nops > 0) {
+    char last = opc[c[nops - 1] & 3];
+    uint32_t count = c[nops - 1] >> 2;
+    for (int u = (int)nops - 2; u >= 0; u--) {
+      const char op = opc[c[u] & 3];
+      if (op == last) count += c[u] >> 2;
+      else { cigar_emit(out, cap, len, count, last); count = c[u] >> 2; last = op; }
+    }
+    cigar_emit(out, cap, len, count, last);
+  }
+  if (style && clip) { const int tail = (int)q_lens[tid] - 1 - q_end[tid]; if (tail > 0) cigar_emit(out, cap, len, (uint32_t)tail, 'S'); }
+  if (stride) out[len < cap ? len : cap] = 0;
+  lens[tid] = len <= cap ? len : (0x80000000u | len);
+}
+
 }  // namespace gb200

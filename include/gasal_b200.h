@@ -292,6 +292,23 @@ void gasalx_pack_host(const uint8_t* ascii, uint64_t n_bytes, uint32_t* words);
  * Returns the length, or -(needed capacity) if cap is too small. */
 int gasalx_cigar_string(const uint8_t* cigar, uint32_t n_ops, char* out, uint32_t cap);
 
+/* CIGAR TEXT formatted on the device (one thread per pair), for the WITH_TB batch last submitted on this storage.  Call it
+ * right after gasal_aln_async(..., WITH_TB): the kernel and the two D2H copies are queued on gpu_storage->str, so host_text /
+ * host_lens are valid once gasal_is_aln_async_done returns 0 (use pinned memory for a truly asynchronous copy).  The text of
+ * pair p is at host_text[p * stride], NUL-terminated; host_lens[p] = its length, or 0x80000000 | needed length if it was
+ * truncated to stride - 1 characters.
+ *   style 0: the letters test_prog.cpp:382-428 prints (M match, X mismatch, D, I), identical to gasalx_cigar_string;
+ *   style 1: SAM CIGAR: M and X merge into M; for LOCAL / BANDED the unaligned query ends become soft clips.
+ * Returns 0, or -1 if the storage holds no traceback results. */
+int gasalx_cigar_text_async(gasal_gpu_storage_t* gpu_storage, int style, char* host_text, uint32_t stride, uint32_t* host_lens);
+
+/* One SAM alignment line (no trailing newline) from the fields a GASAL2 caller has after a LOCAL WITH_TB batch:
+ * pos1 = 1-based leftmost target coordinate (target_batch_start + 1 + the window's offset in the reference), cigar = style-1
+ * text; seq / qual may be NULL ("*").  score -> AS:i, score2 >= 0 -> XS:i (second best).  Returns the length, or
+ * -(needed capacity) if cap is too small. */
+int gasalx_sam_record(char* out, uint32_t cap, const char* qname, int flag, const char* rname, int64_t pos1, int mapq,
+                      const char* cigar, const char* seq, uint32_t seq_len, const char* qual, int32_t score, int32_t score2);
+
 /* Version string of the engine. */
 const char* gasalx_version(void);
 

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from genomics_gpu_b200 import synth
-from genomics_gpu_b200.aligner import cigar_string, pack_host, read_fasta_pairs
+from genomics_gpu_b200.aligner import cigar_string, pack_host, read_fasta_pairs, sam_record
 
 
 def write_fasta(path, seqs, marks=None, width=None, gz=False, crlf=False):
@@ -57,6 +57,14 @@ def test_cigar_string():
     assert cigar_string(enc([(63, "M"), (63, "M"), (10, "M"), (2, "I"), (5, "M")]), 5) == "136M2I5M"   # runs capped at 63 are merged back
     assert cigar_string(enc([(7, "M")]), 1) == "7M"
     assert cigar_string(np.zeros(0, dtype=np.uint8), 0) == ""
+
+
+def test_sam_record_fields():
+    line = sam_record("r1", 16, "chr2", 1234, 37, "3S97M", b"ACGT" * 25, b"I" * 100, 97, 40)
+    f = line.split("\t")
+    assert f[:9] == ["r1", "16", "chr2", "1234", "37", "3S97M", "*", "0", "0"]
+    assert f[9] == "ACGT" * 25 and f[10] == "I" * 100 and f[11:] == ["AS:i:97", "XS:i:40"]
+    assert sam_record("", 4, "", 0, 0, "", None, None, 0).split("\t") == ["*", "4", "*", "0", "0", "*", "*", "0", "0", "*", "*", "AS:i:0"]
 
 
 def test_fastq_reads_against_fasta_windows(tmp_path):
