@@ -169,6 +169,27 @@ def nw_style_pair(rng: np.random.Generator, n: int) -> Tuple[bytes, bytes]:
     return out.tobytes(), t.tobytes()
 
 
+def nw_benchmark_pair(n: int, seed: int = 7) -> Tuple[np.ndarray, np.ndarray]:
+    """The NW benchmark's own input model (Non-CDP/NW/main.cu:40-61,93-96): reference bytes uniform in 0..255, the query
+    copies the reference with probability 0.8, inserts a random byte with 0.1, skips a reference byte with 0.1.
+    Vectorised: the walk is a cumulative sum of the per-event query / reference advances.  Returns (reference, query)."""
+    rng = np.random.default_rng(seed)
+    ref = rng.integers(0, 256, size=n, dtype=np.uint8)
+    m = 2 * n + 64
+    ev = rng.random(m)
+    copy, ins = ev < 0.8, (ev >= 0.8) & (ev < 0.9)
+    r_adv = np.cumsum(copy | ~(copy | ins)); q_adv = np.cumsum(copy | ins)     # reference / query positions consumed AFTER each event
+    r_before = r_adv - (copy | ~(copy | ins)); q_before = q_adv - (copy | ins)
+    ok = (r_before < n) & (q_before < n)                                       # main.cu:48 `while (r < N && q < N)`
+    rnd = rng.integers(0, 256, size=m, dtype=np.uint8)
+    qry = rng.integers(0, 256, size=n, dtype=np.uint8)                          # tail insertions (main.cu:58-60)
+    sel = ok & copy
+    qry[q_before[sel]] = ref[r_before[sel]]
+    sel = ok & ins
+    qry[q_before[sel]] = rnd[sel]
+    return ref, qry
+
+
 def config3(n_pairs: int = 128, length: int = 16_384, seed: int = 3) -> PairBatch:
     rng = np.random.default_rng(seed)
     qs, ts = zip(*[nw_style_pair(rng, length) for _ in range(n_pairs)])

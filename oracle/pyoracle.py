@@ -189,3 +189,60 @@ class RefGpu:
         res["cigar"] = raw[off + 4:off + 4 + qb].copy()
         res["_timing"] = timing
         return res
+
+
+# ---- full-matrix linear-gap NW (oracle/nw_linear.c; reference Non-CDP/NW/main.cu:9-27) -------------------------------
+class NwOracle:
+    """oracle/nw_linear.c: nw_linear_matrix / nw_linear_checksum."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_build", "libnw_linear.so")
+        if not os.path.exists(path):
+            build_oracle("oracle")
+        self.lib = C.CDLL(path)
+        self.lib.nw_linear_matrix.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
+        self.lib.nw_linear_checksum.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int]
+        self.lib.nw_linear_checksum.restype = C.c_uint64
+
+    def matrix(self, reference: np.ndarray, query: np.ndarray, scores=(1, -1, -1, -1)) -> np.ndarray:
+        reference = np.ascontiguousarray(reference, dtype=np.uint8); query = np.ascontiguousarray(query, dtype=np.uint8)
+        n = reference.size
+        out = np.empty((n, n), dtype=np.int32)
+        self.lib.nw_linear_matrix(reference.ctypes.data, query.ctypes.data, out.ctypes.data, n, *scores)
+        return out
+
+    def checksum(self, reference: np.ndarray, query: np.ndarray, scores=(1, -1, -1, -1)) -> int:
+        reference = np.ascontiguousarray(reference, dtype=np.uint8); query = np.ascontiguousarray(query, dtype=np.uint8)
+        return int(self.lib.nw_linear_checksum(reference.ctypes.data, query.ctypes.data, reference.size, *scores))
+
+
+def nw_checksum_of(matrix: np.ndarray) -> int:
+    """The hash of include/nw_b200.h (nwx_checksum) over a host matrix."""
+    flat = matrix.reshape(-1).astype(np.uint32).astype(np.uint64)
+    idx = np.arange(flat.size, dtype=np.uint64)
+    w = ((idx * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)) | np.uint64(1)
+    return int((flat * w).sum(dtype=np.uint64))
+
+
+class NwRefHost:
+    """oracle/_ref/libnw_ref_host.so: the reference's own nw_cpu and generateQuery (NW/main.cu) compiled for the host."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_ref", "libnw_ref_host.so")
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.lib = C.CDLL(path)
+        self.lib.nw_ref_cpu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint]
+        self.lib.nw_ref_generate_query.argtypes = [C.c_void_p, C.c_void_p, C.c_uint, C.c_uint]
+
+    def matrix(self, reference: np.ndarray, query: np.ndarray) -> np.ndarray:
+        reference = np.ascontiguousarray(reference, dtype=np.uint8); query = np.ascontiguousarray(query, dtype=np.uint8)
+        n = reference.size
+        out = np.empty((n, n), dtype=np.int32)
+        self.lib.nw_ref_cpu(reference.ctypes.data, query.ctypes.data, out.ctypes.data, n)
+        return out
+
+    def generate(self, n: int, seed: int):
+        reference = np.empty(n, dtype=np.uint8); query = np.empty(n, dtype=np.uint8)
+        self.lib.nw_ref_generate_query(reference.ctypes.data, query.ctypes.data, n, seed)
+        return reference, query
