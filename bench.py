@@ -300,9 +300,48 @@ def run_extras(local_rank: int, n_fwd: int):
         b4 = synth.config4(n_fwd, seed=4)
         out["C4_banded_k64_250bp"] = {"score_end": timed(b4, algo=capi.BANDED, k_band=64), "with_cigar": timed(b4, algo=capi.BANDED, k_band=64, start=capi.WITH_TB)}
         out["C5_mixed_100bp_10kb_local_with_start"] = timed(synth.config5(4000, seed=5), algo=capi.LOCAL, start=capi.WITH_START)
+        out["C4_local_250bp_with_cigar_s16x2"] = timed(b4, algo=capi.LOCAL, start=capi.WITH_TB)
+        out["NW_linear_full_matrix_N32000"] = nw_extra(32000)
         out["note"] = "gcups_dp counts q_len x t_len forward cells per pair (banded and start passes add time, not cells); device-timed DP stage, best of 3"
     except Exception as e:  # context only: never break the bench line
         out["error"] = str(e)[:200]
+    return out
+
+
+def nw_extra(n: int):
+    """The suite's NW benchmark shape (Non-CDP/NW/main.cu:67, N = 32000): full int32 matrix, device-timed, against the HBM write
+    roofline (4 B per cell); with the reference's own nw_gpu3 on the same GPU when oracle/_ref/nw_ref_gpu travelled here."""
+    import re
+    import tempfile
+    from genomics_gpu_b200 import nw as nwmod, synth
+    ref, qry = synth.nw_benchmark_pair(n, seed=7)
+    best = None
+    for it in range(4):
+        _, ms, _ = nwmod.nw_matrix(ref, qry, want_matrix=False)
+        if it and (best is None or ms[1] < best):
+            best = ms[1]
+    nwmod.release()
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            hbm = float(json.load(f)["hbm_gbs"])
+    except Exception:
+        hbm = 6650.0
+    cells = float(n) * n
+    out = {"N": n, "kernel_ms": best, "gcups": cells / best / 1e6, "write_gbs": 4 * cells / best / 1e6, "frac_of_hbm_peak": 4 * cells / best / 1e6 / hbm,
+           "bound": "wavefront critical path (2N/4 dependent tile steps), not HBM: see DESIGN.md K6"}
+    exe = os.path.join(ROOT, "oracle", "_ref", "nw_ref_gpu")
+    if os.path.exists(exe):
+        try:
+            with tempfile.TemporaryDirectory() as td:      # the reference appends runtimes_*.txt to its cwd
+                p = subprocess.run([exe, "-N", str(n), "-3"], cwd=td, capture_output=True, text=True, timeout=300)
+            txt = re.sub(r"\x1b\[[0-9;]*m", "", p.stdout)
+            m = re.search(r"GPU kernel time \(version 3\): ([0-9.]+) ms", txt)
+            c = re.search(r"CPU time: ([0-9.]+) ms", txt)
+            out["reference_nw_gpu3_ms"] = float(m.group(1)) if m else None
+            out["reference_nw_cpu_ms_1_core"] = float(c.group(1)) if c else None
+            out["reference_verified_itself"] = "Verification succeeded" in txt
+        except Exception as e:
+            out["reference_error"] = str(e)[:100]
     return out
 
 

@@ -61,6 +61,7 @@ struct NwArgs {
   uint2* bnd;                              // [2][Spad * 4] (value, tag)
   uint32_t* ticket;
   uint32_t seq, nblocks, Spad;
+  int one;                                 // == 1 at run time: keeps `up * one + ins` an IMAD (FMA pipe) instead of an ALU-pipe add
   unsigned long long* dbg;                 // optional [nblocks][4]: start ns, end ns, failed chunk polls, SM id (NWX_DEBUG_TIMING=1)
 };
 
@@ -236,7 +237,7 @@ __global__ void __launch_bounds__(64) k_nw_matrix_ws(const NwArgs a) {
   const bool helper = threadIdx.x >= 32;
   const uint32_t N = a.N;
   const int Spad = (int)a.Spad, nsteps = Spad + 32, G = nsteps / kGroup;
-  const int match = a.match, mismatch = a.mismatch, ins = a.ins, del = a.del;
+  const int match = a.match, mismatch = a.mismatch, ins = a.ins, del = a.del, one = a.one;
 
   for (;;) {
     __syncthreads();
@@ -340,7 +341,7 @@ NW_UNROLL(NW_UNROLL_STEPS)
               const int tl = (i == 0) ? (j == 0 ? corner : top[j - 1]) : (j == 0 ? left[i - 1] : h[i - 1][j - 1]);
               const int up = (i == 0) ? top[j] : h[i - 1][j];
               const int lf = (j == 0) ? left[i] : h[i][j - 1];
-              h[i][j] = __vimax3_s32(tl + (qb[i] == rb[j] ? match : mismatch), up + ins, lf + del);
+              h[i][j] = __vimax3_s32(tl + (qb[i] == rb[j] ? match : mismatch), up * one + ins, lf + del);
             }
           }
           corner = t3;
@@ -427,7 +428,7 @@ int launch(const uint8_t* ref_d, const uint8_t* qry_d, int* mat_d, uint32_t N, c
   a.match = scores ? scores->match : 1; a.mismatch = scores ? scores->mismatch : -1;
   a.ins = scores ? scores->insertion : -1; a.del = scores ? scores->deletion : -1;
   a.bnd = sc->bnd; a.ticket = sc->ticket; a.seq = sc->seq; a.nblocks = (N + kBlockRows - 1) / kBlockRows; a.Spad = Spad;
-  a.dbg = nullptr;
+  a.dbg = nullptr; a.one = 1;
   const bool debug = getenv("NWX_DEBUG_TIMING") != nullptr;
   if (debug) NW_CHECK(cudaMalloc(&a.dbg, (size_t)a.nblocks * 4 * sizeof(unsigned long long)));
   k_nw_prep<<<(unsigned)((words + 255) / 256), 256, 0, st>>>(ref_d, N, sc->ref32, (uint32_t)words, sc->ticket);
