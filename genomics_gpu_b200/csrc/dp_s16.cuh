@@ -625,9 +625,19 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
                                           int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
   const uint32_t neg2 = splat16(kNegSafe);
+  // SEMI runs in a BIASED frame: every H/E/F of (strip row r, column q) carries + (q + r) * ext.  Gap extension is then
+  // free (F' = max(F, Hleft - open), E' = max(E, M - open): one VIADDMNMX each, no separate "- oe" adds), the diagonal
+  // step costs + 2 ext, which the caller folds into the substitution tables, and a value that leaves a strip through its
+  // bottom row re-enters the next strip's frame with - 8 ext.  `neg_oe2` is -gap_open here, glA/glB hold H of the previous
+  // column (no add).  Left column of a strip: H(r, -1) = 0 -> (r - 1) ext, diagonal H(r - 1, -1) = 0 -> (r - 2) ext (pinit).
+  const int bias_ext = SEMI ? -lane_lo(neg_ext2) : 0;
+  const uint32_t conv8 = splat16(-8 * bias_ext);
+  uint32_t hpinit[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) hpinit[r] = SEMI ? splat16((r - 1) * bias_ext) : neg_oe2;
   uint32_t pA[8], fA[8], glA[8], pB[8], fB[8], glB[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) { pA[r] = pinitA[r]; fA[r] = neg2; glA[r] = neg_oe2; pB[r] = pinitB[r]; fB[r] = neg2; glB[r] = neg_oe2; }
+  for (int r = 0; r < 8; r++) { pA[r] = pinitA[r]; fA[r] = neg2; glA[r] = hpinit[r]; pB[r] = pinitB[r]; fB[r] = neg2; glB[r] = hpinit[r]; }
   uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
   uint32_t prevsh = 0xCC00u;
   uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;
@@ -654,11 +664,11 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
           // H-based opening without the serial H -> E -> H chain: with H = max(D, F, E),
           // E(t+1,q) = max(H - oe, E - e) = max(max(D, F) - oe, E - e) because oe >= e.  `e` enters a row as E(t,q) and
           // leaves it as E(t+1,q); the parked / handed-over E is the NEXT row's.
-          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, glA[r]);   // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
+          fA[r] = __viaddmax_s16x2(glA[r], neg_oe2, fA[r]);    // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e), biased frame
           const uint32_t m = __vmaxs2(d, fA[r]);
           h = __vmaxs2(m, eA);
-          eA = __viaddmax_s16x2(eA, neg_ext2, __vadd2(m, neg_oe2));
-          glA[r] = __vadd2(h, neg_oe2);
+          eA = __viaddmax_s16x2(m, neg_oe2, eA);               // E(t+1,q) = max(M - oe, E - e), biased frame
+          glA[r] = h;
         } else {
           const uint32_t dm = __vadd2(d, neg_oe2);
           h = __vimax3_s16x2(d, fA[r], eA);
@@ -672,11 +682,11 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
         const uint32_t d = __vadd2(pB[r], s2);
         uint32_t h;
         if (SEMI) {
-          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, glB[r]);
+          fB[r] = __viaddmax_s16x2(glB[r], neg_oe2, fB[r]);
           const uint32_t m = __vmaxs2(d, fB[r]);
           h = __vmaxs2(m, eB);
-          eB = __viaddmax_s16x2(eB, neg_ext2, __vadd2(m, neg_oe2));
-          glB[r] = __vadd2(h, neg_oe2);
+          eB = __viaddmax_s16x2(m, neg_oe2, eB);
+          glB[r] = h;
         } else {
           const uint32_t dm = __vadd2(d, neg_oe2);
           h = __vimax3_s16x2(d, fB[r], eB);
@@ -686,6 +696,7 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
         hhB[r] = h; pB[r] = upB; upB = h;
       }
     }
+    if (SEMI) { upA = __vadd2(upA, conv8); eA = __vadd2(eA, conv8); upB = __vadd2(upB, conv8); eB = __vadd2(eB, conv8); }   // bottom row -> next strip's frame
     HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
     h8A = upA; eoA = eA; h8B = upB; eoB = eB;
     selB = selA_prev; selA_prev = selA;
@@ -694,9 +705,9 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
         // lanes that just ran a phantom column (A.H: step 0; B.L: 0,1; B.H: 0,1,2) get their strip-start state back
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-          if (k == 0) { pA[r] = prmt(pA[r], pinitA[r], 0x7610); fA[r] = prmt(fA[r], neg2, 0x7610); if (SEMI) glA[r] = prmt(glA[r], neg_oe2, 0x7610); }
-          if (k <= 1) { pB[r] = pinitB[r]; fB[r] = neg2; if (SEMI) glB[r] = neg_oe2; }
-          else { pB[r] = prmt(pB[r], pinitB[r], 0x7610); fB[r] = prmt(fB[r], neg2, 0x7610); if (SEMI) glB[r] = prmt(glB[r], neg_oe2, 0x7610); }
+          if (k == 0) { pA[r] = prmt(pA[r], pinitA[r], 0x7610); fA[r] = prmt(fA[r], neg2, 0x7610); if (SEMI) glA[r] = prmt(glA[r], hpinit[r], 0x7610); }
+          if (k <= 1) { pB[r] = pinitB[r]; fB[r] = neg2; if (SEMI) glB[r] = hpinit[r]; }
+          else { pB[r] = prmt(pB[r], pinitB[r], 0x7610); fB[r] = prmt(fB[r], neg2, 0x7610); if (SEMI) glB[r] = prmt(glB[r], hpinit[r], 0x7610); }
         }
       }
       const int li = k - kq;
@@ -705,7 +716,7 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
 #pragma unroll
         for (int r = 0; r < 8; r++) {
           const uint32_t w = (li & 2) ? hhB[r] : hhA[r];
-          hv[r] = (li & 1) ? lane_hi(w) : lane_lo(w);
+          hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (kq + r) * bias_ext;     // SEMI: back to the unbiased score (this lane is on column kq)
         }
         if (SEMI) {
           // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178); the start
@@ -746,7 +757,8 @@ __device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint
       // top boundary: H(-1, c), E = -inf   (semiglobal_kernel_template.h:87-99, global.h:57-60)
       if (SEMI) {
         const int htop = TOP_ZERO ? 0 : (c == 0 ? 0 : -(o + ext * c));                  // free top row: (H,E)(-1,c) = (0,0)
-        HE[(c + 1) * kFastThreads] = pack2(htop, TOP_ZERO ? -ext : htop - (o + ext));
+        // biased frame of nc_sweep4: H(-1,c) carries (c - 1) ext, E(0,c) carries c ext
+        HE[(c + 1) * kFastThreads] = pack2(htop + (c - 1) * ext, (TOP_ZERO ? -ext : htop - (o + ext)) + c * ext);
       } else {
         HE[(c + 1) * kFastThreads] = pack2(c == 0 ? 0 : -(o + ext * c), kNegSafe);
       }
@@ -779,10 +791,10 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
   const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
   const int QR = (int)n_words(qlen), TR = (int)n_words(tlen);
-  const uint32_t mis4 = ((uint32_t)(-a.mismatch) & 0xFFu) * 0x01010101u;
-  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
-  const int oe = a.gap_open + a.gap_extend;
-  const uint32_t neg_oe2 = splat16(-oe), neg_ext2 = splat16(-a.gap_extend);
+  // biased frame (nc_sweep4): a diagonal step moves one row and one column, so both substitution scores carry + 2 ext
+  const uint32_t mis4 = ((uint32_t)(-a.mismatch + 2 * a.gap_extend) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)(a.match + 2 * a.gap_extend) ^ (uint32_t)(-a.mismatch + 2 * a.gap_extend)) & 0xFFu;
+  const uint32_t neg_oe2 = splat16(-a.gap_open), neg_ext2 = splat16(-a.gap_extend);      // gap OPEN only: extension is free in the biased frame
   const bool top_zero = (a.head == SKIP_BOTH);          // HEAD in {QUERY,BOTH}: free top row (:87)
   const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
 
@@ -796,7 +808,7 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   }
   uint32_t pinit[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) pinit[r] = 0;             // HEAD in {TARGET,BOTH}: free left column, diag = 0 (:114-121)
+  for (int r = 0; r < 8; r++) pinit[r] = splat16((r - 2) * a.gap_extend);   // HEAD in {TARGET,BOTH}: free left column, diag H(r-1,-1) = 0 (:114-121), biased
 
   NcTrack tr; tr.best = kMinusInf; tr.y = (int)qlen; tr.stop = 0; tr.cap = 0;       // :63-64
   const int NQ = (TR + 3) >> 2;
@@ -935,7 +947,9 @@ inline bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second
     if (a.tail != SKIP_TARGET || !(a.head == SKIP_TARGET || a.head == SKIP_BOTH)) return false;
     // every H/E/F is >= -(2*oe + ext*(q8+2) + mismatch) and <= q8*match: keep both well inside (kNegSafe, 32767)
     if (2 * oe + (int64_t)a.gap_extend * (q8 + 2) + a.mismatch + 64 > 12000) return false;
-    return (int64_t)q8 * a.match <= 30000;
+    // the biased frame adds up to (q8 + 16) * ext to every value, and the substitution bytes carry + 2 ext
+    if (a.match + 2 * a.gap_extend > 127) return false;
+    return (int64_t)q8 * a.match + (int64_t)(q8 + 24) * a.gap_extend <= 30000;
   }
   if (algo == ALGO_GLOBAL) {
     if (start != START_NONE) return false;
