@@ -625,12 +625,13 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
                                           int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
   const uint32_t neg2 = splat16(kNegSafe);
-  // SEMI runs in a BIASED frame: every H/E/F of (strip row r, column q) carries + (q + r) * ext.  Gap extension is then
-  // free (F' = max(F, Hleft - open), E' = max(E, M - open): one VIADDMNMX each, no separate "- oe" adds), the diagonal
-  // step costs + 2 ext, which the caller folds into the substitution tables, and a value that leaves a strip through its
-  // bottom row re-enters the next strip's frame with - 8 ext.  `neg_oe2` is -gap_open here, glA/glB hold H of the previous
-  // column (no add).  Left column of a strip: H(r, -1) = 0 -> (r - 1) ext, diagonal H(r - 1, -1) = 0 -> (r - 2) ext (pinit).
-  const int bias_ext = SEMI ? -lane_lo(neg_ext2) : 0;
+  // Both recurrences run in a BIASED frame: every H/E/F of (strip row r, column q) carries + (q + r) * ext.  Gap extension is
+  // then free (semi-global: F' = max(F, Hleft - open), E' = max(E, M - open); global: F' = max(F, D - open), E' = max(E, D - open):
+  // one VIADDMNMX each, no separate "- oe" adds), the diagonal step costs + 2 ext, which the caller folds into the substitution
+  // tables, and a value that leaves a strip through its bottom row re-enters the next strip's frame with - 8 ext.  `neg_oe2` is
+  // -gap_open here; for SEMI glA/glB hold H of the previous column (no add).  Left column of a semi-global strip: H(r, -1) = 0 ->
+  // (r - 1) ext; the diagonal inputs (pinit) carry (r - 2) ext.  The -infinity floors stay unbiased: they only ever lose a max.
+  const int bias_ext = -lane_lo(neg_ext2);
   const uint32_t conv8 = splat16(-8 * bias_ext);
   uint32_t hpinit[8];
 #pragma unroll
@@ -670,10 +671,9 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
           eA = __viaddmax_s16x2(m, neg_oe2, eA);               // E(t+1,q) = max(M - oe, E - e), biased frame
           glA[r] = h;
         } else {
-          const uint32_t dm = __vadd2(d, neg_oe2);
           h = __vimax3_s16x2(d, fA[r], eA);
-          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, dm);
-          eA = __viaddmax_s16x2(eA, neg_ext2, dm);
+          fA[r] = __viaddmax_s16x2(d, neg_oe2, fA[r]);         // F(t,q+1) = max(F - e, D - oe), biased frame
+          eA = __viaddmax_s16x2(d, neg_oe2, eA);               // E(t+1,q) = max(E - e, D - oe), biased frame
         }
         hhA[r] = h; pA[r] = upA; upA = h;
       }
@@ -688,15 +688,14 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
           eB = __viaddmax_s16x2(m, neg_oe2, eB);
           glB[r] = h;
         } else {
-          const uint32_t dm = __vadd2(d, neg_oe2);
           h = __vimax3_s16x2(d, fB[r], eB);
-          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, dm);
-          eB = __viaddmax_s16x2(eB, neg_ext2, dm);
+          fB[r] = __viaddmax_s16x2(d, neg_oe2, fB[r]);
+          eB = __viaddmax_s16x2(d, neg_oe2, eB);
         }
         hhB[r] = h; pB[r] = upB; upB = h;
       }
     }
-    if (SEMI) { upA = __vadd2(upA, conv8); eA = __vadd2(eA, conv8); upB = __vadd2(upB, conv8); eB = __vadd2(eB, conv8); }   // bottom row -> next strip's frame
+    upA = __vadd2(upA, conv8); eA = __vadd2(eA, conv8); upB = __vadd2(upB, conv8); eB = __vadd2(eB, conv8);   // bottom row -> next strip's frame
     HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
     h8A = upA; eoA = eA; h8B = upB; eoB = eB;
     selB = selA_prev; selA_prev = selA;
@@ -716,7 +715,7 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
 #pragma unroll
         for (int r = 0; r < 8; r++) {
           const uint32_t w = (li & 2) ? hhB[r] : hhA[r];
-          hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (kq + r) * bias_ext;     // SEMI: back to the unbiased score (this lane is on column kq)
+          hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (kq + r) * bias_ext;     // back to the unbiased score (this lane is on column kq)
         }
         if (SEMI) {
           // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178); the start
@@ -760,7 +759,7 @@ __device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint
         // biased frame of nc_sweep4: H(-1,c) carries (c - 1) ext, E(0,c) carries c ext
         HE[(c + 1) * kFastThreads] = pack2(htop + (c - 1) * ext, (TOP_ZERO ? -ext : htop - (o + ext)) + c * ext);
       } else {
-        HE[(c + 1) * kFastThreads] = pack2(c == 0 ? 0 : -(o + ext * c), kNegSafe);
+        HE[(c + 1) * kFastThreads] = pack2((c == 0 ? 0 : -(o + ext * c)) + (c - 1) * ext, kNegSafe);   // H(-1,c) in the biased frame
       }
     }
   }
@@ -865,10 +864,11 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
   const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
   const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
   const int QR = (int)n_words(qlen), TR = (int)n_words(tlen);
-  const uint32_t mis4 = ((uint32_t)(-a.mismatch) & 0xFFu) * 0x01010101u;
-  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
   const int o = a.gap_open, ext = a.gap_extend;
-  const uint32_t neg_oe2 = splat16(-(o + ext)), neg_ext2 = splat16(-ext);
+  // biased frame (nc_sweep4): both substitution scores carry + 2 ext, gaps cost their OPEN part only
+  const uint32_t mis4 = ((uint32_t)(-a.mismatch + 2 * ext) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)(a.match + 2 * ext) ^ (uint32_t)(-a.mismatch + 2 * ext)) & 0xFFu;
+  const uint32_t neg_oe2 = splat16(-o), neg_ext2 = splat16(-ext);
   const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
   bool odd = nc_prologue<false, false>(HE, V, qw, qlen, QR, 0, o, ext);
   odd |= target_has_odd_base(tw, tlen, TR);
@@ -891,8 +891,9 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
       rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
       rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
       const int t0 = 32 * j + r;                                                     // diag(t) = t ? -(o + e*t) : 0   (global.h:66-70)
-      pinitA[r] = pack2(t0 == 0 ? 0 : -(o + ext * t0), -(o + ext * (t0 + 8)));
-      pinitB[r] = pack2(-(o + ext * (t0 + 16)), -(o + ext * (t0 + 24)));
+      const int fb = (r - 2) * ext;                                                   // frame of (row r - 1, column -1)
+      pinitA[r] = pack2((t0 == 0 ? 0 : -(o + ext * t0)) + fb, -(o + ext * (t0 + 8)) + fb);
+      pinitB[r] = pack2(-(o + ext * (t0 + 16)) + fb, -(o + ext * (t0 + 24)) + fb);
     }
     const bool has_last = (last_strip >> 2) == j;
     nc_sweep4<ALGO_GLOBAL, false>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinitA, pinitB, neg_oe2, neg_ext2,
@@ -954,7 +955,8 @@ inline bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second
   if (algo == ALGO_GLOBAL) {
     if (start != START_NONE) return false;
     if (2 * oe + (int64_t)a.gap_extend * (q8 + t8 + 2) + a.mismatch + 64 > 12000) return false;
-    return (int64_t)std::min(q8, t8) * a.match <= 30000;
+    if (a.match + 2 * a.gap_extend > 127) return false;                      // biased frame, as for semi-global
+    return (int64_t)std::min(q8, t8) * a.match + (int64_t)(q8 + 24) * a.gap_extend <= 30000;
   }
   return false;
 }
