@@ -171,7 +171,11 @@ __device__ __forceinline__ void wave_steps(WaveLane<SR>& L, const Sc& sc, uint32
                                            int k0, int kend, int ncol, int lane, int qlen, int tlen, int row0, int lstrip, int32_t* score_out) {
   constexpr int ROWS = 8 * SR;
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL), LOCALA = (ALGO == ALGO_LOCAL);
-  const int oe = sc.oe, ext = sc.ext;
+  // SEMI and GLOBAL run in a BIASED frame (see dp_s16.cuh nc_sweep4): the value of (lane row r, column c) carries + (c + r) * ext,
+  // so a gap extension is free, opening costs `o`, a diagonal step costs + 2 ext (folded into the tables by the caller) and
+  // the bottom row leaves the lane with - ROWS * ext.  The reference's finite -infinity (-32768, Q7) is biased like any
+  // other value, so its decay by `ext` per step is reproduced exactly.  LOCAL (0 clamp) stays unbiased.
+  const int oe = sc.oe, ext = sc.ext, o = sc.o, bias = LOCALA ? 0 : ext;
   for (int k = k0; k < kend; k++) {
     // ---- (H, E) of the row above come from the lane above, lane 0 takes them from the chunk ring; every lane reads its
     // column's selector from the 64-column selector ring (address known a step ahead, off the critical path) ----
@@ -198,7 +202,7 @@ __device__ __forceinline__ void wave_steps(WaveLane<SR>& L, const Sc& sc, uint32
 #pragma unroll
         for (int s = 0; s < SR; s++)
 #pragma unroll
-          for (int r = 0; r < 8; r++) sv[8 * s + r] = score_general(sc, qc, nib(L.tword[s], r));
+          for (int r = 0; r < 8; r++) sv[8 * s + r] = score_general(sc, qc, nib(L.tword[s], r)) + 2 * bias;
       } else {
 #pragma unroll
         for (int r = 0; r < ROWS; r++) sv[r] = (int)prmt(L.tbl[r], ntab, sel);
@@ -210,19 +214,24 @@ __device__ __forceinline__ void wave_steps(WaveLane<SR>& L, const Sc& sc, uint32
         const int d = L.p[r] + sv[r];
         int h;
         if (SEMI) {
-          L.f[r] = __viaddmax_s32(L.f[r], -ext, L.gl[r]);           // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e)
+          L.f[r] = __viaddmax_s32(L.gl[r], -o, L.f[r]);             // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e), biased frame
           const int m = max(d, L.f[r]);
           h = max(m, e);
-          e = __viaddmax_s32(e, -ext, m - oe);                      // E(t+1,q) = max(max(D,F) - oe, E - e)  (oe >= e)
-          L.gl[r] = h - oe;
-        } else {
-          h = LOCALA ? __vimax3_s32_relu(d, L.f[r], e) : __vimax3_s32(d, L.f[r], e);
+          e = __viaddmax_s32(m, -o, e);                             // E(t+1,q) = max(max(D,F) - oe, E - e)  (oe >= e), biased frame
+          L.gl[r] = h;
+        } else if (LOCALA) {
+          h = __vimax3_s32_relu(d, L.f[r], e);
           const int dm = d - oe;
           L.f[r] = __viaddmax_s32(L.f[r], -ext, dm);
           e = __viaddmax_s32(e, -ext, dm);
+        } else {
+          h = __vimax3_s32(d, L.f[r], e);
+          L.f[r] = __viaddmax_s32(d, -o, L.f[r]);                   // F(t,q+1) = max(F - e, D - oe), biased frame
+          e = __viaddmax_s32(d, -o, e);                             // E(t+1,q) = max(E - e, D - oe), biased frame
         }
         hh[r] = h; L.p[r] = up; up = h;
       }
+      if (!LOCALA) { up -= ROWS * bias; e -= ROWS * bias; }       // into the frame of the lane below (row -1 / row 0)
       L.h_bot = up; L.e_bot = e;
       if (LOCALA) {
 #pragma unroll
@@ -243,15 +252,15 @@ __device__ __forceinline__ void wave_steps(WaveLane<SR>& L, const Sc& sc, uint32
           for (int s = 0; s < SR; s++)
 #pragma unroll
             for (int r = 0; r < 8; r++) {
-              const int t = row0 + 8 * s + r;
-              if (t < tlen && hh[8 * s + r] > L.best[s]) { L.best[s] = hh[8 * s + r]; L.bpos[s] = t; }
+              const int t = row0 + 8 * s + r, hv = hh[8 * s + r] - (c + 8 * s + r) * bias;
+              if (t < tlen && hv > L.best[s]) { L.best[s] = hv; L.bpos[s] = t; }
             }
         } else {
           const int t_last = tlen - 1;
           if ((unsigned)((t_last >> 3) - lstrip) < (unsigned)SR) {
-            int v = hh[0];
+            int v = hh[0] - c * bias;
 #pragma unroll
-            for (int r = 1; r < ROWS; r++) v = ((t_last - 8 * lstrip) == r) ? hh[r] : v;
+            for (int r = 1; r < ROWS; r++) v = ((t_last - 8 * lstrip) == r) ? hh[r] - (c + r) * bias : v;
             *score_out = v;                                         // H(ref_len-1, read_len-1)  (global.h:285-299)
           }
         }
@@ -274,7 +283,7 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
   const int oe = sc.oe, ext = sc.ext;
   const bool top_zero = SEMI && (a.head == SKIP_BOTH);
   const uint32_t total = (uint32_t)a.n * w.maxblk;
-  const uint32_t ntab = (uint32_t)sc.nscore & 0xFFu;            // query N under the LOCAL rule: same score in every row
+  const uint32_t ntab = (uint32_t)(sc.nscore + (LOCALA ? 0 : 2 * ext)) & 0xFFu;   // query N under the LOCAL rule: same score in every row
 
   for (;;) {
     uint32_t T = 0;
@@ -304,14 +313,15 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
 #pragma unroll
       for (int r = 0; r < 8; r++) {
         const uint32_t tc = nib(L.tword[s], r);
-        const uint32_t b0 = (uint32_t)score_general(sc, 1u, tc) & 0xFFu, b1 = (uint32_t)score_general(sc, 3u, tc) & 0xFFu;
-        const uint32_t b2 = (uint32_t)score_general(sc, 7u, tc) & 0xFFu, b3 = (uint32_t)score_general(sc, 4u, tc) & 0xFFu;
+        const int b2e = LOCALA ? 0 : 2 * ext;                    // biased frame: a diagonal step carries + 2 ext
+        const uint32_t b0 = (uint32_t)(score_general(sc, 1u, tc) + b2e) & 0xFFu, b1 = (uint32_t)(score_general(sc, 3u, tc) + b2e) & 0xFFu;
+        const uint32_t b2 = (uint32_t)(score_general(sc, 7u, tc) + b2e) & 0xFFu, b3 = (uint32_t)(score_general(sc, 4u, tc) + b2e) & 0xFFu;
         L.tbl[8 * s + r] = b0 | (b1 << 8) | (b2 << 16) | (b3 << 24);
         const int t = row0 + 8 * s + r;
-        if (LOCALA) { L.p[8 * s + r] = 0; L.f[8 * s + r] = 0; }
-        else if (GLOB) { L.p[8 * s + r] = (t == 0) ? 0 : -(sc.o + ext * t); L.f[8 * s + r] = kMinusInf; }     // global.h:63-71
-        else { L.p[8 * s + r] = 0; L.f[8 * s + r] = kMinusInf; }                                              // free left column (:114-121)
-        L.gl[8 * s + r] = -oe;
+        const int lr = 8 * s + r;                                 // row inside the lane: frame of (lr, c) is (c + lr) * ext
+        if (LOCALA) { L.p[lr] = 0; L.f[lr] = 0; L.gl[lr] = -oe; }
+        else if (GLOB) { L.p[lr] = ((t == 0) ? 0 : -(sc.o + ext * t)) + (lr - 2) * ext; L.f[lr] = kMinusInf + lr * ext; L.gl[lr] = 0; }   // global.h:63-71
+        else { L.p[lr] = (lr - 2) * ext; L.f[lr] = kMinusInf + lr * ext; L.gl[lr] = (lr - 1) * ext; }          // free left column (:114-121): H(t,-1) = 0
       }
       L.best[s] = LOCALA ? 0 : kMinusInf; L.bpos[s] = 0;
     }
@@ -332,12 +342,12 @@ __global__ void __launch_bounds__(kWaveWarps * 32) k_wave(const WaveArgs w) {
         uint4 v = make_uint4(0, 0, 0, 0);
         if (blk == 0) {
           if (c < ncol) {
-            if (GLOB) { v.x = (uint32_t)(c == 0 ? 0 : -(sc.o + ext * c)); v.y = (uint32_t)kMinusInf; }            // global.h:57-60
+            if (GLOB) { v.x = (uint32_t)((c == 0 ? 0 : -(sc.o + ext * c)) + (c - 1) * ext); v.y = (uint32_t)(kMinusInf + c * ext); }   // global.h:57-60, biased
             else if (SEMI) {
               // semi-global hands E over as the first row's own E(0,c) = max(H(-1,c) - oe, E(-1,c) - e)
               const int htop = top_zero ? 0 : (c == 0 ? 0 : -(sc.o + ext * c));                                   // :87-99
               const int etop = top_zero ? 0 : kMinusInf;
-              v.x = (uint32_t)htop; v.y = (uint32_t)max(htop - oe, etop - ext);
+              v.x = (uint32_t)(htop + (c - 1) * ext); v.y = (uint32_t)(max(htop - oe, etop - ext) + c * ext);      // biased frame
             }
           }
         } else {
@@ -625,6 +635,7 @@ inline bool wave_eligible(const DpArgs& a, int algo, int start, bool second, uin
   if (a.n_score < -127) return false;
   if (a.gap_open < 0 || a.gap_extend < 0) return false;
   if (algo == ALGO_LOCAL) return true;
+  if (a.match + 2 * a.gap_extend > 127) return false;          // biased frame: the substitution bytes carry + 2 ext
   if (algo == ALGO_GLOBAL) return start == START_NONE;
   if (algo == ALGO_SEMI_GLOBAL) return a.tail == SKIP_TARGET && (a.head == SKIP_TARGET || a.head == SKIP_BOTH);
   return false;
