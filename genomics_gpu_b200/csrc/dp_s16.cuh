@@ -721,7 +721,7 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
         int hv[8];
 #pragma unroll
         for (int r = 0; r < 8; r++) {
-          const uint32_t w = (li & 2) ? hhB[r] : hhA[r];
+          const uint32_t w = SEMI ? ((li & 2) ? glB[r] : glA[r]) : ((li & 2) ? hhB[r] : hhA[r]);   // SEMI: gl already holds this step's H
           hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (kq + r) * bias_ext;     // back to the unbiased score (this lane is on column kq)
         }
         if (SEMI) {
