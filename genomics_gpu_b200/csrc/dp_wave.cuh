@@ -154,6 +154,7 @@ __device__ __forceinline__ void wave_finalize(const WaveArgs& w, uint32_t pair, 
   }
 }
 
+constexpr int kWaveSteadyUnroll = 2;
 template <int SR>
 struct WaveLane {
   uint32_t tword[SR];           // this lane's packed target words
@@ -176,6 +177,7 @@ __device__ __forceinline__ void wave_steps(WaveLane<SR>& L, const Sc& sc, uint32
   // the bottom row leaves the lane with - ROWS * ext.  The reference's finite -infinity (-32768, Q7) is biased like any
   // other value, so its decay by `ext` per step is reproduced exactly.  LOCAL (0 clamp) stays unbiased.
   const int oe = sc.oe, ext = sc.ext, o = sc.o, bias = LOCALA ? 0 : ext;
+#pragma unroll (STEADY ? kWaveSteadyUnroll : 1)   // steady chunks are 32 steps: two steps per trip turn the p[r] <- up rotation into renaming
   for (int k = k0; k < kend; k++) {
     // ---- (H, E) of the row above come from the lane above, lane 0 takes them from the chunk ring; every lane reads its
     // column's selector from the 64-column selector ring (address known a step ahead, off the critical path) ----
