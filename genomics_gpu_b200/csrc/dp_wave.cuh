@@ -154,7 +154,7 @@ __device__ __forceinline__ void wave_finalize(const WaveArgs& w, uint32_t pair, 
   }
 }
 
-constexpr int kWaveSteadyUnroll = 2;
+constexpr int kWaveSteadyUnroll = 4;
 template <int SR>
 struct WaveLane {
   uint32_t tword[SR];           // this lane's packed target words
@@ -718,7 +718,12 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   WaveArgs wa; wa.a = a; wa.algo = algo; wa.maxblk = maxblk; wa.qoff = ws.qoff; wa.soff = ws.soff;
   wa.bnd = ws.bnd; wa.bnd_stride = qs; wa.cand = ws.cand; wa.done = ws.prog; wa.ticket = ws.prog + n;
   const int ctas_per_sm = use_s16 ? WAVE16_MIN_CTAS : 4;
-  const int blocks = (int)std::max<uint64_t>(1, std::min<uint64_t>((uint64_t)n_sm * ctas_per_sm, (tasks + kWaveWarps - 1) / kWaveWarps));   // <= 16 (24) warp-workers per SM
+  // <= 16 (24) warp-workers per SM.  Once there is at least one CTA (= one warp per scheduler) for every SM, only whole multiples of
+  // the SM count are started: a pipeline runs at the pace of its most crowded scheduler, so 1.7 workers per scheduler (two on
+  // some, one on others) is slower than one everywhere and a second round of tickets (32 pairs of 16k x 16k: 1651 -> see DESIGN.md)
+  uint64_t ctas = std::min<uint64_t>((uint64_t)n_sm * ctas_per_sm, (tasks + kWaveWarps - 1) / kWaveWarps);
+  if (ctas > (uint64_t)n_sm) ctas = ctas / (uint64_t)n_sm * (uint64_t)n_sm;
+  const int blocks = (int)std::max<uint64_t>(1, ctas);
   int launches = 0;
   for (int pass = 0; pass < npass; pass++) {
     cudaMemsetAsync(ws.prog, 0, prog_words * sizeof(uint32_t), str);
