@@ -473,6 +473,13 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
     uint32_t e = prmt(xe, L.out_e, 0x5432);
     const uint32_t sel = (v & 0xFFu) | L.prevsh;
     L.prevsh = (v & 0xFFu) * 256u + 0x4400u;
+    // the diagonal input of row r is the previous step's H of row r - 1, which L.hh keeps for the arg-max anyway: no second
+    // rotating array (8 register moves per step); row 0 takes the previous step's incoming top H from L.p[0]
+    uint32_t dg[8];
+    dg[0] = L.p[0];
+#pragma unroll
+    for (int r = 1; r < 8; r++) dg[r] = L.hh[r - 1];
+    L.p[0] = up;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       uint32_t s2;
@@ -480,12 +487,12 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
         const int sl = score_general(sc, (v >> 20) & 15u, nib(L.twA, r)), sh = score_general(sc, (L.vprev >> 20) & 15u, nib(L.twB, r));
         s2 = ((uint32_t)sl & 0xFFFFu) | ((uint32_t)sh << 16);
       } else s2 = prmt(L.rowA[r], L.rowB[r], sel);
-      const uint32_t d = __vadd2(L.p[r], s2);
+      const uint32_t d = __vadd2(dg[r], s2);
       const uint32_t dm = __vadd2(d, neg_oe2);
       const uint32_t h = __vimax3_s16x2_relu(d, L.f[r], e);
       L.f[r] = __viaddmax_s16x2(L.f[r], neg_ext2, dm);
       e = __viaddmax_s16x2(e, neg_ext2, dm);
-      L.hh[r] = h; L.p[r] = up; up = h;
+      L.hh[r] = h; up = h;
     }
     L.out_h = up; L.out_e = e;
     L.vprev = v;
