@@ -183,7 +183,7 @@ def plan_batches(q_lens: np.ndarray, t_lens: np.ndarray, *, n_gpus: int = 1, max
 def align_all(batch: PairBatch, *, algo: int, start: int = capi.WITHOUT_START, second_best: bool = False, head: int = capi.TARGET,
               tail: int = capi.TARGET, k_band: int = 0, scoring: Sequence[int] = (1, 4, 6, 1), n_gpus: int = 1, gpu_ids: Optional[Sequence[int]] = None,
               streams_per_gpu: int = 2, max_batch_pairs: int = 262144, max_batch_cells: int = 1 << 36, q_op=None, t_op=None,
-              keep_input_order: bool = False) -> Dict[str, np.ndarray]:
+              keep_input_order: bool = False, host_threads_per_gpu: int = 0) -> Dict[str, np.ndarray]:
     """The whole job through the library-side batcher (gasalx_align_all): length binning, LPT sharding over the GPUs of this
     process, pinned streaming on per-storage streams, host-side gather in the caller's order."""
     lib = capi.load()
@@ -194,7 +194,7 @@ def align_all(batch: PairBatch, *, algo: int, start: int = capi.WITHOUT_START, s
     sc = capi.SubstScores(*[int(v) for v in scoring]); lib.gasal_copy_subst_scores(C.byref(sc))
     sched = capi.Sched(); lib.gasalx_sched_default(C.byref(sched))
     sched.n_gpus = n_gpus; sched.streams_per_gpu = streams_per_gpu; sched.max_batch_pairs = max_batch_pairs; sched.max_batch_cells = max_batch_cells
-    sched.keep_input_order = int(keep_input_order)
+    sched.keep_input_order = int(keep_input_order); sched.host_threads_per_gpu = int(host_threads_per_gpu)
     ids = None
     if gpu_ids is not None:
         ids = (C.c_int32 * n_gpus)(*gpu_ids); sched.gpu_ids = ids

@@ -66,7 +66,7 @@ class SubstScores(C.Structure):
 
 class Sched(C.Structure):
     _fields_ = [("n_gpus", C.c_int32), ("gpu_ids", C.POINTER(C.c_int32)), ("streams_per_gpu", C.c_int32), ("max_batch_pairs", C.c_uint32),
-                ("max_batch_bytes", C.c_uint64), ("max_batch_cells", C.c_uint64), ("keep_input_order", C.c_int32)]
+                ("max_batch_bytes", C.c_uint64), ("max_batch_cells", C.c_uint64), ("keep_input_order", C.c_int32), ("host_threads_per_gpu", C.c_int32)]
 
 
 class Results(C.Structure):

@@ -144,14 +144,21 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
   }
   gasal_gpu_storage_v& v = dc.v;
   std::vector<int> running(ns, -1);
-  size_t next = 0, done = 0;
+  // Staging (one bulk copy per run of neighbouring pairs into the pinned pages) and the scatter of the results are host
+  // memory traffic: one thread per GPU moves ~11 GB/s, less than a B200 consumes on short reads.  The storages of a GPU are
+  // therefore split over `nthreads` host threads; each owns its storages (and their streams) and pulls batches from one queue.
+  int nthreads = sc->host_threads_per_gpu > 0 ? sc->host_threads_per_gpu : std::min(ns, 4);
+  nthreads = std::max(1, std::min(nthreads, ns));
+  std::atomic<size_t> next(0), done(0);
+  std::mutex ms_mu;
   double ms_total = 0;
   const gasal_params_t* P = job.params;
+  auto run_storages = [&](int s_lo, int s_hi) {
   auto harvest = [&](int s) {
     gasal_gpu_storage_t* st = &v.a[s];
     const uint32_t b = (uint32_t)running[s];
     const uint32_t lo = pl.batch_start[b], cnt = pl.batch_start[b + 1] - lo;
-    float ms[3]; if (gasalx_last_batch_ms(st, ms) == 0) ms_total += ms[0];
+    float ms[3]; if (gasalx_last_batch_ms(st, ms) == 0) { std::lock_guard<std::mutex> g(ms_mu); ms_total += ms[0]; }
     gasal_res_t* h = st->host_res; gasalx_results_t* o = job.out;
     for (uint32_t j = 0; j < cnt; j++) {
       const uint32_t i = pl.order[lo + j];
@@ -180,18 +187,19 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
         memcpy(o->cigar + job.q_offs[i], h->cigar + st->host_query_batch_offsets[j], std::min(nops, room));
       }
     }
-    running[s] = -1; done++;
+    running[s] = -1; done.fetch_add(1);
   };
-  while (done < mine.size()) {
-    bool progressed = false;
-    for (int s = 0; s < ns; s++) {
+  for (;;) {
+    bool progressed = false, busy = false;
+    for (int s = s_lo; s < s_hi; s++) {
       gasal_gpu_storage_t* st = &v.a[s];
       if (running[s] >= 0) {
-        if (gasal_is_aln_async_done(st) == 0) { harvest(s); progressed = true; }
+        if (gasal_is_aln_async_done(st) == 0) { harvest(s); progressed = true; } else busy = true;
         continue;
       }
-      if (next >= mine.size()) continue;
-      const uint32_t b = mine[next++];
+      const size_t take = next.fetch_add(1);
+      if (take >= mine.size()) continue;
+      const uint32_t b = mine[take];
       const uint32_t lo = pl.batch_start[b], cnt = pl.batch_start[b + 1] - lo;
       if (cnt > st->host_max_n_alns) gasal_host_alns_resize(st, (int)cnt, P);
       uint32_t qi = 0, ti = 0;
@@ -227,10 +235,17 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
       }
       st->current_n_alns = cnt;
       gasal_aln_async(st, qi, ti, cnt, P);
-      running[s] = (int)b; progressed = true;
+      running[s] = (int)b; progressed = true; busy = true;
     }
+    if (!busy && next.load() >= mine.size()) break;          // nothing in flight on my storages and the queue is empty
     if (!progressed) std::this_thread::yield();
   }
+  };   // run_storages
+  std::vector<std::thread> helpers;
+  for (int t = 1; t < nthreads; t++)
+    helpers.emplace_back([&, t] { if (cudaSetDevice(device) != cudaSuccess) { err->store(1); return; } run_storages(t * ns / nthreads, (t + 1) * ns / nthreads); });
+  run_storages(0, ns / nthreads);
+  for (auto& h : helpers) h.join();
   if (gpu_ms) *gpu_ms = ms_total;
 }
 
@@ -241,6 +256,7 @@ extern "C" {
 void gasalx_sched_default(gasalx_sched_t* s) {
   memset(s, 0, sizeof(*s));
   s->n_gpus = 1; s->streams_per_gpu = 2; s->max_batch_pairs = 262144; s->max_batch_bytes = 1ull << 30; s->max_batch_cells = 1ull << 36;
+  s->host_threads_per_gpu = 0;
 }
 
 // Pure host planning (no CUDA): returns the number of batches; fills order[n], and, for up to `cap` batches,

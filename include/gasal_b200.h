@@ -249,6 +249,7 @@ typedef struct {
   uint64_t max_batch_bytes;      /* per sequence side, default 1 GiB (must stay < 4 GiB: 32-bit offsets of the GASAL2 API) */
   uint64_t max_batch_cells;      /* default 2^36 DP cells */
   int32_t keep_input_order;      /* 1: no length binning (batches follow input order, like test_prog) */
+  int32_t host_threads_per_gpu;  /* host threads that stage batches / gather results per GPU; 0 = auto (min(streams_per_gpu, 4)) */
 } gasalx_sched_t;
 
 typedef struct {                 /* any pointer may be NULL; arrays have one entry per pair of the job */
