@@ -235,3 +235,25 @@ def test_ksw_extension_from_matching_prefix(oracle):
         got = al.align(b, seeds=seeds)
     assert_same(got, want, K3, "ksw prefix extension")
     assert (got["query_batch_end"] == b.q_lens.astype(np.int32)).sum() > 100      # the to-end branch was exercised
+
+
+# gap costs that stress the biased frame of the semi-global / global kernels ((row + column) * ext folded into every value):
+# no extension cost at all, extension as expensive as opening, free opening, large extension, and a scoring whose
+# substitution bytes (+ 2 ext) no longer fit the packed tables so that the engine must fall back by itself
+ODD_SCORINGS = [(1, 4, 6, 0), (2, 3, 0, 2), (1, 1, 0, 1), (3, 5, 9, 7), (10, 9, 20, 5), (100, 60, 7, 20)]
+
+
+@pytest.mark.parametrize("scoring", ODD_SCORINGS)
+@pytest.mark.parametrize("policy", [0, 2])
+def test_biased_frame_scorings(oracle, scoring, policy):
+    """policy 0: s16x2 fast path where eligible; policy 2: the wavefront kernel wherever it is eligible"""
+    b = ragged(70 + scoring[3], n=400)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, start=po.WITH_START, scoring=scoring, max_query_len=1024)
+    got = run(b, policy=policy, algo=capi.SEMI_GLOBAL, start=capi.WITH_START, scoring=scoring)
+    assert_same(got, want, K5, f"semi-global {scoring} policy={policy} kernel={got['_kernel']}")
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, head=po.BOTH, tail=po.TARGET, scoring=scoring, max_query_len=1024)
+    got = run(b, policy=policy, algo=capi.SEMI_GLOBAL, head=capi.BOTH, tail=capi.TARGET, scoring=scoring)
+    assert_same(got, want, K3, f"semi-global BOTH/TARGET {scoring} policy={policy} kernel={got['_kernel']}")
+    want = oracle_align(oracle, b, algo=po.GLOBAL, scoring=scoring)
+    got = run(b, policy=policy, algo=capi.GLOBAL, scoring=scoring)
+    assert_same(got, want, ["aln_score"], f"global {scoring} policy={policy} kernel={got['_kernel']}")
