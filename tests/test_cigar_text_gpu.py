@@ -88,3 +88,21 @@ def test_no_traceback_results_is_an_error():
     b = synth.make_read_window_pairs(32, 100, 200, sub=0.02, indel=0.0, seed=34)
     with pytest.raises(RuntimeError):
         run_text(b, 0, algo=capi.LOCAL, start=capi.WITH_START)
+
+
+@pytest.mark.parametrize("kw", [dict(algo=capi.GLOBAL, start=capi.WITH_TB), dict(algo=capi.BANDED, k_band=64, start=capi.WITH_TB)])
+@pytest.mark.parametrize("style", [0, 1])
+def test_text_for_global_and_banded_traceback(kw, style):
+    """the device formatter against the host decoder of the SAME result bytes (GLOBAL has no clipped ends: no soft clips)"""
+    b = synth.make_read_window_pairs(200, 101, 131, sub=0.03, indel=0.01, seed=35)
+    got = run_text(b, style, stride=160, **kw)
+    for i in range(b.n):
+        o, n = int(b.q_offs[i]), int(got["n_cigar_ops"][i])
+        ref_text = cigar_string(got["cigar"][o:o + n], n)
+        if style == 0:
+            exp = ref_text
+        elif kw["algo"] == capi.GLOBAL:
+            exp = sam_style(ref_text, 0, int(b.q_lens[i]) - 1, int(b.q_lens[i]))
+        else:
+            exp = sam_style(ref_text, int(got["query_batch_start"][i]), int(got["query_batch_end"][i]), int(b.q_lens[i]))
+        assert got["cigar_text"][i] == exp, (i, got["cigar_text"][i], exp)
