@@ -51,6 +51,9 @@ def make_workload(n_pairs: int, seed: int):
                            np.full(n, QLEN, dtype=np.uint32), np.full(n, TLEN, dtype=np.uint32))
 
 
+WORKLOAD = "C2: GASAL2 local + semi-global, WITH_START, 150x600 bp synthetic pairs"
+
+
 # ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """SM clock / power / throttle reasons sampled DURING the timed region (B200_PROFILING.md clocks line).  NVML is polled
@@ -266,7 +269,8 @@ def run_reference(args, rank, world):
     line = {"metric": "GCUPS", "impl": "reference", "value": value, "unit": "GCUPS", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int32",
             "data": "synthetic",
-            "config": {"workload": "C2: local + semi-global WITH_START, 150x600 bp pairs", "pairs_per_step": n_sample, "scoring": list(SCORING)},
+            "config": {"workload": WORKLOAD, "modes_per_step": ["local WITH_START", "semi_global TARGET/TARGET WITH_START"], "scoring": list(SCORING),
+                       "pairs_per_step": n_sample, "note": "bounded sample of the same workload per step (the CPU needs minutes for the full 1 M pairs)"},
             "cpu_baseline": {"value": value, "unit": "GCUPS", "cores": threads, "kind": kind,
                              "sample": f"{n_sample} pairs of the C2 workload per step, both modes, reference kernels compiled for the host (OpenMP)"},
             "e2e": {"value": value, "unit": "GCUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -518,7 +522,7 @@ def run_ours(args, rank, world, local_rank):
         "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "s16x2/int32 (DPX integer)", "data": "synthetic",
-        "config": {"workload": "C2: GASAL2 local + semi-global, WITH_START, 150x600 bp synthetic pairs", "pairs_per_gpu": n,
+        "config": {"workload": WORKLOAD, "pairs_per_gpu": n,
                    "modes_per_step": ["local WITH_START", "semi_global TARGET/TARGET WITH_START"], "scoring": list(SCORING),
                    "l2_policy": "inputs larger than L2 (752 MB unpacked + 376 MB packed per mode)",
                    "kernels": kernel_names, "timing": "CUDA events on each storage's stream, summed over the step's batches"},
