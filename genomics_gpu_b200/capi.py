@@ -94,6 +94,7 @@ EXPORTED_SYMBOLS = [
     "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all", "gasalx_batcher_release",
     "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_cigar_string",
     "gasalx_cigar_text_async", "gasalx_sam_record",
+    "gasalx_try_aln_async", "gasalx_try_init_streams", "gasalx_last_error",
 ]
 
 
@@ -153,5 +154,8 @@ def load() -> C.CDLL:
     lib.gasalx_sam_record.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_int, C.c_char_p, C.c_int64, C.c_int, C.c_char_p, C.c_char_p, C.c_uint32,
                                       C.c_char_p, C.c_int32, C.c_int32]
     lib.gasalx_sam_record.restype = C.c_int
+    lib.gasalx_try_aln_async.argtypes = [P(GpuStorage), C.c_uint32, C.c_uint32, C.c_uint32, P(Params)]; lib.gasalx_try_aln_async.restype = C.c_int
+    lib.gasalx_try_init_streams.argtypes = [P(GpuStorageV), C.c_int, C.c_int, C.c_int, P(Params)]; lib.gasalx_try_init_streams.restype = C.c_int
+    lib.gasalx_last_error.restype = C.c_char_p
     _lib = lib
     return lib

@@ -19,13 +19,33 @@
 
 using namespace gb200;
 
+// ---- error handling: the reference prints to stderr and exit()s (src/gasal.h:15-22, gasal_align.cu:32-67); that stays the
+// default.  The gasalx_try_* entry points ("opt-in non-fatal status code") run the same code with
+// tl_soft set: gasal_die() then throws instead of exiting, the extern "C" wrapper catches and returns the code, and the
+// message stays readable through gasalx_last_error().
+namespace {
+thread_local bool tl_soft = false;
+thread_local char tl_msg[512] = "";
+struct SoftError { int code; };
+[[noreturn]] void gasal_die(int code) {
+  if (tl_soft) throw SoftError{code};
+  exit(EXIT_FAILURE);
+}
+}  // namespace
+#define GASAL_FAIL(code, ...)                          \
+  do {                                                 \
+    snprintf(tl_msg, sizeof(tl_msg), __VA_ARGS__);     \
+    fputs(tl_msg, stderr);                             \
+    gasal_die(code);                                   \
+  } while (0)
+
 #define CHECKCUDAERROR(call)                                                                                          \
   do {                                                                                                                \
     cudaError_t err_ = (call);                                                                                        \
     if (cudaSuccess != err_) {                                                                                        \
-      fprintf(stderr, "[GASAL CUDA ERROR:] %s(CUDA error no.=%d). Line no. %d in file %s\n", cudaGetErrorString(err_), \
-              err_, __LINE__, __FILE__);                                                                              \
-      exit(EXIT_FAILURE);                                                                                             \
+      GASAL_FAIL(err_ == cudaErrorMemoryAllocation ? GASALX_E_NOMEM : GASALX_E_CUDA,                                    \
+                 "[GASAL CUDA ERROR:] %s(CUDA error no.=%d). Line no. %d in file %s\n", cudaGetErrorString(err_),      \
+                 (int)err_, __LINE__, __FILE__);                                                                      \
     }                                                                                                                 \
   } while (0)
 
@@ -71,7 +91,7 @@ inline uint32_t round8(uint32_t x) { return (x + 7u) & ~7u; }
 template <typename T>
 T* cudaHostRealloc(void* source, int new_size, int old_size) {
   T* destination = NULL;
-  if (new_size < old_size) { fprintf(stderr, "[GASAL ERROR] cudoHostRealloc: invalid sizes. New size < old size (%d < %d)", new_size, old_size); exit(EXIT_FAILURE); }
+  if (new_size < old_size) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR] cudoHostRealloc: invalid sizes. New size < old size (%d < %d)", new_size, old_size); }
   CHECKCUDAERROR(cudaHostAlloc(&destination, new_size * sizeof(T), cudaHostAllocDefault));
   memcpy(destination, source, old_size * sizeof(T));
   CHECKCUDAERROR(cudaFreeHost(source));
@@ -191,7 +211,7 @@ uint32_t gasal_host_batch_fill(gasal_gpu_storage_t* gpu_storage, uint32_t idx, c
   switch (SRC) {
     case QUERY: cur_page = gpu_storage->extensible_host_unpacked_query_batch; p_batch_bytes = &(gpu_storage->host_max_query_batch_bytes); break;
     case TARGET: cur_page = gpu_storage->extensible_host_unpacked_target_batch; p_batch_bytes = &(gpu_storage->host_max_target_batch_bytes); break;
-    default: fprintf(stderr, "[GASAL ERROR:] gasal_host_batch_fill: SRC must be QUERY or TARGET\n"); exit(EXIT_FAILURE);
+    default: GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] gasal_host_batch_fill: SRC must be QUERY or TARGET\n");
   }
   const uint32_t nbr_N = (8u - (size & 7u)) & 7u;
   while (cur_page->is_locked) cur_page = cur_page->next;
@@ -226,7 +246,7 @@ uint32_t gasal_host_batch_add(gasal_gpu_storage_t* gpu_storage, uint32_t idx, co
   switch (SRC) {
     case QUERY: cur_page = gpu_storage->extensible_host_unpacked_query_batch; p_batch_bytes = &(gpu_storage->host_max_query_batch_bytes); break;
     case TARGET: cur_page = gpu_storage->extensible_host_unpacked_target_batch; p_batch_bytes = &(gpu_storage->host_max_target_batch_bytes); break;
-    default: fprintf(stderr, "[GASAL ERROR:] gasal_host_batch_add: SRC must be QUERY or TARGET\n"); exit(EXIT_FAILURE);
+    default: GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] gasal_host_batch_add: SRC must be QUERY or TARGET\n");
   }
   int is_done = 0;
   while (!is_done) {
@@ -299,8 +319,7 @@ void gasal_set_device(int gpu_select, int isPrintingProp) {   // :98-128
     cudaGetDeviceCount(&num_devices);
     fprintf(stderr, "Found %d GPUs\n", num_devices);
     if (gpu_select > num_devices - 1) {
-      fprintf(stderr, "Error: can't select device %d when only %d devices are selected (range from 0 to %d)\n", gpu_select, num_devices, num_devices - 1);
-      exit(EXIT_FAILURE);
+      GASAL_FAIL(GASALX_E_ARG, "Error: can't select device %d when only %d devices are selected (range from 0 to %d)\n", gpu_select, num_devices, num_devices - 1);
     }
     for (int device = 0; device < num_devices; device++) {
       cudaDeviceProp properties; cudaGetDeviceProperties(&properties, device);
@@ -336,8 +355,7 @@ void gasal_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len,
   const int max_query_len_8 = (int)round8((uint32_t)max_query_len), max_target_len_8 = (int)round8((uint32_t)max_target_len);
   const uint64_t qb = (uint64_t)max_n_alns * max_query_len_8, tb = (uint64_t)max_n_alns * max_target_len_8;
   if (qb > 0xFFFFFFF0ull || tb > 0xFFFFFFF0ull) {
-    fprintf(stderr, "[GASAL ERROR:] batch of %d alignments x (%d, %d) bases does not fit the 32-bit byte offsets of the GASAL2 API\n", max_n_alns, max_query_len_8, max_target_len_8);
-    exit(EXIT_FAILURE);
+    GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] batch of %d alignments x (%d, %d) bases does not fit the 32-bit byte offsets of the GASAL2 API\n", max_n_alns, max_query_len_8, max_target_len_8);
   }
   for (int i = 0; i < gpu_storage_vec->n; i++) {
     gasal_gpu_storage_t* s = &gpu_storage_vec->a[i];
@@ -551,7 +569,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
   if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
     const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, s->str);
-    if (nl < 0) { fprintf(stderr, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); exit(EXIT_FAILURE); }
+    if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); }
     CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "s16x2";
     if (want_tb) {                                                                        // gasal_align.h:45-53
       const uint32_t nb = (n + 127) / 128;
@@ -567,7 +585,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
     int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     bool s16 = g_kernel_policy != 3 && wave16_eligible(a, params->algo, shape.max_q, shape.max_t);
     const int nl = wave_launch(a, params->algo, start, pv->wave, s->host_query_batch_lens, s->host_target_batch_lens, shape.max_t, sms, s->str, &s16, g_kernel_policy == 4);
-    if (nl < 0) { fprintf(stderr, "[GASAL CUDA ERROR:] out of device memory for the wavefront scratch\n"); exit(EXIT_FAILURE); }
+    if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the wavefront scratch\n"); }
     CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = s16 ? "wave16" : "wave";
     return;
   }
@@ -607,8 +625,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
       k_ksw_generic<<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
       break;
     default:
-      fprintf(stderr, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo);
-      exit(EXIT_FAILURE);
+      GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo);
   }
 }
 
@@ -624,14 +641,14 @@ static BatchShape scan_shape(const gasal_gpu_storage_t* s, uint32_t n, const Pri
 
 static void validate(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n) {
   // src/gasal_align.cu:32-67
-  if (n <= 0) { fprintf(stderr, "[GASAL ERROR:] actual_n_alns <= 0\n"); exit(EXIT_FAILURE); }
-  if (q_bytes <= 0) { fprintf(stderr, "[GASAL ERROR:] actual_query_batch_bytes <= 0\n"); exit(EXIT_FAILURE); }
-  if (t_bytes <= 0) { fprintf(stderr, "[GASAL ERROR:] actual_target_batch_bytes <= 0\n"); exit(EXIT_FAILURE); }
-  if (q_bytes % 8) { fprintf(stderr, "[GASAL ERROR:] actual_query_batch_bytes=%d is not a multiple of 8\n", q_bytes); exit(EXIT_FAILURE); }
-  if (t_bytes % 8) { fprintf(stderr, "[GASAL ERROR:] actual_target_batch_bytes=%d is not a multiple of 8\n", t_bytes); exit(EXIT_FAILURE); }
-  if (q_bytes > s->host_max_query_batch_bytes) { fprintf(stderr, "[GASAL ERROR:] actual_query_batch_bytes(%d) > host_max_query_batch_bytes(%d)\n", q_bytes, s->host_max_query_batch_bytes); exit(EXIT_FAILURE); }
-  if (t_bytes > s->host_max_target_batch_bytes) { fprintf(stderr, "[GASAL ERROR:] actual_target_batch_bytes(%d) > host_max_target_batch_bytes(%d)\n", t_bytes, s->host_max_target_batch_bytes); exit(EXIT_FAILURE); }
-  if (n > s->host_max_n_alns) { fprintf(stderr, "[GASAL ERROR:] actual_n_alns(%d) > host_max_n_alns(%d)\n", n, s->host_max_n_alns); exit(EXIT_FAILURE); }
+  if (n <= 0) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_n_alns <= 0\n"); }
+  if (q_bytes <= 0) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_query_batch_bytes <= 0\n"); }
+  if (t_bytes <= 0) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_target_batch_bytes <= 0\n"); }
+  if (q_bytes % 8) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_query_batch_bytes=%d is not a multiple of 8\n", q_bytes); }
+  if (t_bytes % 8) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_target_batch_bytes=%d is not a multiple of 8\n", t_bytes); }
+  if (q_bytes > s->host_max_query_batch_bytes) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_query_batch_bytes(%d) > host_max_query_batch_bytes(%d)\n", q_bytes, s->host_max_query_batch_bytes); }
+  if (t_bytes > s->host_max_target_batch_bytes) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_target_batch_bytes(%d) > host_max_target_batch_bytes(%d)\n", t_bytes, s->host_max_target_batch_bytes); }
+  if (n > s->host_max_n_alns) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] actual_n_alns(%d) > host_max_n_alns(%d)\n", n, s->host_max_n_alns); }
 }
 
 static void device_stage(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n, const gasal_params_t* params, const BatchShape& shape) {
@@ -652,7 +669,7 @@ void gasal_aln_async(gasal_gpu_storage_t* s, const uint32_t actual_query_batch_b
                      const uint32_t actual_n_alns, const gasal_params_t* params) {
   validate(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns);
   Priv* pv = priv(s);
-  if (pv == NULL) { fprintf(stderr, "[GASAL ERROR:] storage was not initialised with gasal_init_streams\n"); exit(EXIT_FAILURE); }
+  if (pv == NULL) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] storage was not initialised with gasal_init_streams\n"); }
   grow_device(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns, params);
   const uint32_t n = actual_n_alns;
   const BatchShape shape = scan_shape(s, n, pv, true);
@@ -668,7 +685,7 @@ void gasal_aln_async(gasal_gpu_storage_t* s, const uint32_t actual_query_batch_b
   CHECKCUDAERROR(cudaMemcpyAsync(s->query_batch_offsets, s->host_query_batch_offsets, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
   CHECKCUDAERROR(cudaMemcpyAsync(s->target_batch_offsets, s->host_target_batch_offsets, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
   if (params->algo == KSW) {
-    if (s->seed_scores == NULL || s->host_seed_scores == NULL) { fprintf(stderr, "seed_scores == NULL\n"); exit(EXIT_FAILURE); }
+    if (s->seed_scores == NULL || s->host_seed_scores == NULL) { GASAL_FAIL(GASALX_E_ARG, "seed_scores == NULL\n"); }
     CHECKCUDAERROR(cudaMemcpyAsync(s->seed_scores, s->host_seed_scores, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
   }
   if (params->isReverseComplement) {
@@ -715,8 +732,7 @@ int gasal_is_aln_async_done(gasal_gpu_storage_t* s) {   // src/gasal_align.cu:31
   cudaError_t err = cudaStreamQuery(s->str);
   if (err != cudaSuccess) {
     if (err == cudaErrorNotReady) return -1;
-    fprintf(stderr, "[GASAL CUDA ERROR:] %s(CUDA error no.=%d). Line no. %d in file %s\n", cudaGetErrorString(err), err, __LINE__, __FILE__);
-    exit(EXIT_FAILURE);
+    GASAL_FAIL(GASALX_E_CUDA, "[GASAL CUDA ERROR:] %s(CUDA error no.=%d). Line no. %d in file %s\n", cudaGetErrorString(err), (int)err, __LINE__, __FILE__);
   }
   gasal_host_batch_reset(s);
   s->is_free = 1;
@@ -765,6 +781,27 @@ int gasalx_cigar_text_async(gasal_gpu_storage_t* s, int style, char* host_text, 
   CHECKCUDAERROR(cudaMemcpyAsync(host_lens, pv->d_text_lens, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->str));
   return 0;
 }
+
+int gasalx_try_aln_async(gasal_gpu_storage_t* s, uint32_t actual_query_batch_bytes, uint32_t actual_target_batch_bytes, uint32_t actual_n_alns,
+                         const gasal_params_t* params) {
+  tl_soft = true; tl_msg[0] = 0;
+  int rc = GASALX_OK;
+  try { gasal_aln_async(s, actual_query_batch_bytes, actual_target_batch_bytes, actual_n_alns, params); }
+  catch (const SoftError& e) { rc = e.code; }
+  tl_soft = false;
+  return rc;
+}
+
+int gasalx_try_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len, int max_target_len, int max_n_alns, const gasal_params_t* params) {
+  tl_soft = true; tl_msg[0] = 0;
+  int rc = GASALX_OK;
+  try { gasal_init_streams(gpu_storage_vec, max_query_len, max_target_len, max_n_alns, params); }
+  catch (const SoftError& e) { rc = e.code; }
+  tl_soft = false;
+  return rc;
+}
+
+const char* gasalx_last_error(void) { return tl_msg; }
 
 uint64_t gasalx_kernel_launches(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return pv ? pv->launches : 0; }
 const char* gasalx_last_kernel_name(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return pv ? pv->last_kernel : "none"; }

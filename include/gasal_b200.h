@@ -310,6 +310,17 @@ int gasalx_cigar_text_async(gasal_gpu_storage_t* gpu_storage, int style, char* h
 int gasalx_sam_record(char* out, uint32_t cap, const char* qname, int flag, const char* rname, int64_t pos1, int mapq,
                       const char* cigar, const char* seq, uint32_t seq_len, const char* qual, int32_t score, int32_t score2);
 
+/* Opt-in NON-FATAL error mode.  The reference prints to stderr and exit()s on invalid arguments and CUDA errors (src/gasal.h:15-22,
+ * src/gasal_align.cu:32-67), and so do the gasal_* entry points above.  These two run the same code but return a status instead of
+ * ending the process (a server should not die on an oversized batch): GASALX_OK, or one of the codes below with the message that
+ * was printed kept in gasalx_last_error() (thread-local).  After GASALX_E_ARG nothing was queued and the storage is unchanged;
+ * after GASALX_E_NOMEM / GASALX_E_CUDA the storage must be destroyed (CUDA errors are sticky). */
+enum { GASALX_OK = 0, GASALX_E_ARG = 1, GASALX_E_NOMEM = 2, GASALX_E_CUDA = 3 };
+int gasalx_try_aln_async(gasal_gpu_storage_t* gpu_storage, uint32_t actual_query_batch_bytes, uint32_t actual_target_batch_bytes,
+                         uint32_t actual_n_alns, const gasal_params_t* params);
+int gasalx_try_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len, int max_target_len, int max_n_alns, const gasal_params_t* params);
+const char* gasalx_last_error(void);
+
 /* Version string of the engine. */
 const char* gasalx_version(void);
 

@@ -70,3 +70,15 @@ def test_params_default_matches_reference_defaults():
     # reference src/args_parser.cpp:12-29
     assert (p.algo, p.start_pos, p.secondBest, p.isPacked, p.isReverseComplement) == (capi.UNKNOWN, capi.WITHOUT_START, 0, 0, 0)
     assert (p.semiglobal_skipping_head, p.semiglobal_skipping_tail, p.k_band) == (capi.TARGET, capi.TARGET, 0)
+
+
+def test_non_fatal_error_mode_returns_a_status_without_a_gpu():
+    """gasalx_try_init_streams validates before it touches CUDA: an impossible batch returns GASALX_E_ARG instead of exit()"""
+    import ctypes as C
+    lib = capi.load()
+    p = capi.Params(); lib.gasal_params_default(C.byref(p)); p.algo = capi.LOCAL
+    v = lib.gasal_init_gpu_storage_v(1)
+    rc = lib.gasalx_try_init_streams(C.byref(v), 100_000, 100_000, 1_000_000, C.byref(p))      # 10^11 bytes: beyond 32-bit offsets
+    assert rc == 1                                                                             # GASALX_E_ARG
+    assert b"32-bit byte offsets" in lib.gasalx_last_error()
+    lib.gasal_destroy_gpu_storage_v(C.byref(v))

@@ -257,3 +257,24 @@ def test_biased_frame_scorings(oracle, scoring, policy):
     want = oracle_align(oracle, b, algo=po.GLOBAL, scoring=scoring)
     got = run(b, policy=policy, algo=capi.GLOBAL, scoring=scoring)
     assert_same(got, want, ["aln_score"], f"global {scoring} policy={policy} kernel={got['_kernel']}")
+
+
+def test_non_fatal_error_mode(oracle):
+    """gasalx_try_aln_async returns the reference's fatal argument errors as a status; the storage stays usable"""
+    import ctypes as C
+    b = ragged(95, n=200)
+    lib = capi.load()
+    mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
+    with Aligner(algo=capi.LOCAL, max_query_len=mq, max_target_len=mt, max_n_alns=b.n, n_streams=1) as al:
+        al.fill(0, b)
+        s = al.vec.a[0]
+        rc = lib.gasalx_try_aln_async(C.byref(s), b.q_bytes.size, b.t_bytes.size, s.host_max_n_alns + 1, C.byref(al.params))
+        assert rc == 1 and b"actual_n_alns" in lib.gasalx_last_error()
+        rc = lib.gasalx_try_aln_async(C.byref(s), b.q_bytes.size + 4, b.t_bytes.size, b.n, C.byref(al.params))
+        assert rc == 1 and b"multiple of 8" in lib.gasalx_last_error()
+        assert al.done(0) == -2                                      # nothing was launched
+        rc = lib.gasalx_try_aln_async(C.byref(s), b.q_bytes.size, b.t_bytes.size, b.n, C.byref(al.params))
+        assert rc == 0
+        al.wait(0)
+        got = al.results(0, b.n)
+    assert_same(got, oracle_align(oracle, b, algo=po.LOCAL), K3, "after soft errors")
