@@ -300,7 +300,8 @@ def run_extras(local_rank: int, n_fwd: int):
     try:
         b2 = synth.config2(n_fwd, seed=2)
         out["C2_forward_only"] = {"local": timed(b2, algo=capi.LOCAL), "semi_global": timed(b2, algo=capi.SEMI_GLOBAL), "global": timed(b2, algo=capi.GLOBAL)}
-        out["C3_global_16k_x_16k"] = {"n32": timed(synth.config3(32, 16384, seed=3), algo=capi.GLOBAL), "n16": timed(synth.config3(16, 16384, seed=3), algo=capi.GLOBAL)}
+        out["C3_global_16k_x_16k"] = {"n128": timed(synth.config3(128, 16384, seed=3), algo=capi.GLOBAL), "n32": timed(synth.config3(32, 16384, seed=3), algo=capi.GLOBAL),
+                                      "n16": timed(synth.config3(16, 16384, seed=3), algo=capi.GLOBAL)}
         b4 = synth.config4(n_fwd, seed=4)
         out["C4_banded_k64_250bp"] = {"score_end": timed(b4, algo=capi.BANDED, k_band=64), "with_cigar": timed(b4, algo=capi.BANDED, k_band=64, start=capi.WITH_TB)}
         out["C5_mixed_100bp_10kb_local_with_start"] = timed(synth.config5(4000, seed=5), algo=capi.LOCAL, start=capi.WITH_START)

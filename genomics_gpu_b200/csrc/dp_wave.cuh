@@ -45,6 +45,7 @@ struct WaveArgs {
   int2* cand;                // per strip: (score, position) candidate of the strip
   uint32_t* ticket;          // global ticket counter
   uint32_t* done;            // per pair: finished row-blocks
+  int kshift, floor16;       // k_wave16_global: constant subtracted from every biased value; finite -infinity (both fit 16 bits)
 };
 
 struct WaveGeom {
@@ -613,7 +614,206 @@ __global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_loc
   }
 }
 
+
+// =====================================================================================================
+// k_wave16_global: GLOBAL score (global.h) on the s16x2 row-block pipeline of k_wave16_local.  A 16k x 16k global matrix
+// does not fit 16 bits as it stands (H runs from -(o + 16384 e) to +16384 match), but in the BIASED frame of dp_s16.cuh every
+// value carries + (column + row-in-strip) * ext, which cancels the linear decay of the gap costs, and a constant shift K
+// (recurrences only add and max: a constant commutes with both) centres what is left: wave16_global_range() proves on the
+// host, from the batch's lengths and the scoring, that every real value stays inside (floor16, 32767) -- else the batch runs
+// on the int32 kernel.  Per cell pair: PRMT, VIADD.16x2, VIMNMX3.S16x2, 2 x VIADDMNMX.S16x2 (5 instructions for two cells;
+// the int32 kernel needs 5 per cell).  There is no 0 clamp to neutralise the columns a half computes before its column 0,
+// so each half gets its strip-start state (diagonal inputs, F = -infinity) imposed at the step it enters the matrix.
+struct Wave16G {
+  uint32_t rowA[8], rowB[8];
+  uint32_t f[8], hh[8];           // hh: H of the previous step = diagonal input of the row below
+  uint32_t p0;                    // incoming top H of the previous step = diagonal input of row 0
+  uint32_t out_h, out_e, prevsh, vprev;
+  uint32_t twA, twB;
+};
+
+template <bool EXOTIC>
+__device__ __forceinline__ void wave16g_steps(Wave16G& L, const Sc& sc, const uint2* sin, const uint32_t* ssel, uint2* sout,
+                                              int k0, int kend, int lane, uint32_t neg_o2, uint32_t conv8, const uint32_t (&dinit)[8], uint32_t floor2,
+                                              int kcapL, int kcapH, int caprow, int unbias_cap, int32_t* score_out) {
+  for (int k = k0; k < kend; k++) {
+    const uint2 top = sin[k & 31];
+    const uint32_t v = ssel[(k - 2 * lane) & 127];
+    uint32_t xh = __shfl_up_sync(0xFFFFFFFFu, L.out_h, 1);
+    uint32_t xe = __shfl_up_sync(0xFFFFFFFFu, L.out_e, 1);
+    if (lane == 0) { xh = top.x << 16; xe = top.y << 16; }
+    uint32_t up = prmt(xh, L.out_h, 0x5432);       // low half <- lane above, high strip; high half <- own low strip, previous step
+    uint32_t e = prmt(xe, L.out_e, 0x5432);
+    const uint32_t sel = (v & 0xFFu) | L.prevsh;
+    L.prevsh = (v & 0xFFu) * 256u + 0x4400u;
+    // a half enters the matrix: low half at step 2 * lane (column 0), high half one step later
+    const int kin = k - 2 * lane;
+    if ((unsigned)kin < 2u) {
+      const uint32_t m = kin ? 0x7610u : 0x3254u;  // PRMT selector: replace the high (kin = 1) or the low (kin = 0) half by the second operand's
+      L.p0 = prmt(L.p0, dinit[0], m);
+#pragma unroll
+      for (int r = 0; r < 7; r++) L.hh[r] = prmt(L.hh[r], dinit[r + 1], m);
+#pragma unroll
+      for (int r = 0; r < 8; r++) L.f[r] = prmt(L.f[r], floor2, m);
+    }
+    uint32_t dg[8];
+    dg[0] = L.p0;
+#pragma unroll
+    for (int r = 1; r < 8; r++) dg[r] = L.hh[r - 1];
+    L.p0 = up;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t s2;
+      if (EXOTIC && ((v | L.vprev) & kWaveExotic)) {
+        const int sl = score_general(sc, (v >> 20) & 15u, nib(L.twA, r)) + 2 * sc.ext, sh = score_general(sc, (L.vprev >> 20) & 15u, nib(L.twB, r)) + 2 * sc.ext;
+        s2 = ((uint32_t)sl & 0xFFFFu) | ((uint32_t)sh << 16);
+      } else s2 = prmt(L.rowA[r], L.rowB[r], sel);
+      const uint32_t d = __vadd2(dg[r], s2);
+      const uint32_t h = __vimax3_s16x2(d, L.f[r], e);
+      L.f[r] = __viaddmax_s16x2(d, neg_o2, L.f[r]);
+      e = __viaddmax_s16x2(d, neg_o2, e);
+      L.hh[r] = h; up = h;
+    }
+    if (k == kcapL || k == kcapH) {                                                         // H(ref_len-1, read_len-1)  (global.h:285-299)
+      uint32_t hv = L.hh[0];
+#pragma unroll
+      for (int r = 1; r < 8; r++) hv = (caprow == r) ? L.hh[r] : hv;                        // select chain: no dynamic register indexing
+      *score_out = ((k == kcapL) ? (int)(short)(hv & 0xFFFFu) : (int)(short)(hv >> 16)) - unbias_cap;
+    }
+    L.out_h = __vadd2(up, conv8); L.out_e = __vadd2(e, conv8);                              // into the frame of the strip below
+    L.vprev = v;
+    if (lane == 31) sout[k & 31] = make_uint2((uint32_t)(int)(short)(L.out_h >> 16), (uint32_t)(int)(short)(L.out_e >> 16));
+  }
+}
+
+__global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_global(const WaveArgs w) {
+  __shared__ uint2 s_in[kWaveWarps][32];
+  __shared__ uint32_t s_sel[kWaveWarps][128];
+  __shared__ uint2 s_out[kWaveWarps][32];
+  const DpArgs& a = w.a;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint2* sin = s_in[wib]; uint32_t* ssel = s_sel[wib]; uint2* sout = s_out[wib];
+  const Sc sc = make_sc(a, true);
+  const int ext = sc.ext, o = sc.o, K = w.kshift;
+  const uint32_t total = (uint32_t)a.n * w.maxblk;
+  const uint32_t neg_o2 = (((uint32_t)(-o)) & 0xFFFFu) * 0x00010001u, conv8 = (((uint32_t)(-8 * ext)) & 0xFFFFu) * 0x00010001u;
+  const uint32_t floor2 = (((uint32_t)w.floor16) & 0xFFFFu) * 0x00010001u;
+
+  for (;;) {
+    uint32_t T = 0;
+    if (lane == 0) T = atomicAdd(w.ticket, 1u);
+    T = __shfl_sync(0xFFFFFFFFu, T, 0);
+    if (T >= total) break;
+    const uint32_t blk = T / (uint32_t)a.n, pair = T - blk * (uint32_t)a.n;
+    const WaveGeom g = wave_geometry(w, pair);
+    const int nblk = (g.nstrips + 63) / 64;
+    if ((int)blk >= nblk) continue;
+    const int qlen = (int)a.q_lens[pair], tlen = (int)a.t_lens[pair];
+    const uint32_t* qw = a.pq + (a.q_offs[pair] >> 3);
+    const uint32_t* tw = a.pt + (a.t_offs[pair] >> 3);
+    const int ncol = g.ncol;
+    const int lstrip = ((int)blk * 32 + lane) * 2;
+    const bool last_blk = ((int)blk == nblk - 1);
+
+    Wave16G L;
+    L.twA = (lstrip < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip) : 0u;
+    L.twB = (lstrip + 1 < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip + 1) : 0u;
+    uint32_t dinit[8];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t ta = 0, tb = 0;
+      const uint32_t ca = nib(L.twA, r), cb = nib(L.twB, r);
+      const uint32_t qcodes[4] = {1u, 3u, 7u, 4u};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        ta |= ((uint32_t)(score_general(sc, qcodes[i], ca) + 2 * ext) & 0xFFu) << (8 * i);
+        tb |= ((uint32_t)(score_general(sc, qcodes[i], cb) + 2 * ext) & 0xFFu) << (8 * i);
+      }
+      L.rowA[r] = ta; L.rowB[r] = tb; L.f[r] = floor2; L.hh[r] = 0;
+      // diagonal input of (row r, column 0) = H(t - 1, -1) = t ? -(o + e t) : 0 (global.h:66-70), in the frame of (r - 1, -1), shifted by K
+      const int tA = 8 * lstrip + r, tB = tA + 8, fb = (r - 2) * ext - K;
+      dinit[r] = ((uint32_t)(((tA == 0) ? 0 : -(o + ext * tA)) + fb) & 0xFFFFu) | ((uint32_t)(-(o + ext * tB) + fb) << 16);
+    }
+    L.p0 = 0; L.out_h = 0; L.out_e = 0; L.prevsh = 0xCC00u; L.vprev = 0x88u;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ssel[lane + 32 * i] = 0x88u;
+    __syncwarp();
+    // which half of which lane holds row tlen - 1, and at which step it is on column qlen - 1
+    const int t_last = tlen - 1, sl = t_last >> 3, caprow = t_last & 7;
+    const int kcapL = (sl == lstrip) ? (qlen - 1) + 2 * lane : -1, kcapH = (sl == lstrip + 1) ? (qlen - 1) + 2 * lane + 1 : -1;
+    const int unbias_cap = (qlen - 1 + caprow) * ext - K;
+
+    const uint4* bnd_in = w.bnd + (uint64_t)((blk + 1) & 1) * w.bnd_stride + w.qoff[pair];
+    uint4* bnd_out = w.bnd + (uint64_t)(blk & 1) * w.bnd_stride + w.qoff[pair];
+    const uint32_t tag_in = w.tag_base + blk - 1, tag_out = w.tag_base + blk;
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    if (blk != 0 && lane < ncol) pre = ld_bnd(bnd_in + lane);
+
+    const int nsteps = ncol + 63;
+    int exo_hist = 0;
+    for (int k0 = 0; k0 < nsteps; k0 += 32) {
+      exo_hist <<= 1;
+      {
+        const int c = k0 + lane;
+        uint2 v = make_uint2(0u, 0u);
+        uint32_t selv = 0x88u;
+        if (k0 < ncol) {
+          if (blk != 0) {
+            bool ok = (c >= ncol) || (pre.y == tag_in && pre.w == tag_in);
+            while (!__all_sync(0xFFFFFFFFu, ok)) {
+              __nanosleep(20);
+              if (!ok) { pre = ld_bnd(bnd_in + c); ok = (pre.y == tag_in && pre.w == tag_in); }
+            }
+            v.x = pre.x; v.y = pre.z;
+            if (c + 32 < ncol) pre = ld_bnd(bnd_in + c + 32);
+          } else if (c < ncol) {
+            // top boundary (global.h:57-60): H(-1,c) = c ? -(o + e c) : 0 in the frame of (row -1, column c); E(0,c) = -infinity
+            v.x = (uint32_t)(((c == 0) ? 0 : -(o + ext * c)) + (c - 1) * ext - K); v.y = (uint32_t)w.floor16;
+          }
+          if (c < ncol) {
+            const uint32_t qword = wave_qword(w, g, qw, qlen, c >> 3);
+            const uint32_t qc = nib(qword, c & 7);
+            const uint32_t idx = base_idx(qc);
+            selv = (idx < 4) ? (0x80u + 0x11u * idx) | (qc << 20) : (0x88u | kWaveExotic | (qc << 20));
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, (selv & kWaveExotic) != 0)) exo_hist |= 1;
+        __syncwarp();
+        sin[lane] = v;
+        ssel[c & 127] = selv;
+        __syncwarp();
+      }
+      const int kend = min(k0 + 32, nsteps);
+      int32_t* sp = a.score + pair;
+      if (exo_hist & 7) wave16g_steps<true>(L, sc, sin, ssel, sout, k0, kend, lane, neg_o2, conv8, dinit, floor2, kcapL, kcapH, caprow, unbias_cap, sp);
+      else wave16g_steps<false>(L, sc, sin, ssel, sout, k0, kend, lane, neg_o2, conv8, dinit, floor2, kcapL, kcapH, caprow, unbias_cap, sp);
+      if (!last_blk) {
+        __syncwarp();
+        const int cb = k0 - 63 + lane;
+        if (cb >= 0 && cb < ncol && k0 + lane < kend) { const uint2 ov = sout[lane]; st_bnd(bnd_out + cb, make_uint4(ov.x, tag_out, ov.y, tag_out)); }
+        __syncwarp();
+      }
+    }
+  }
+}
+
+// Range proof for k_wave16_global: biased values X + (c + r) ext - K of every real H / E / F, for all pairs of the batch.
+//   upper: H <= match * min(q, t), bias <= (q8 + 64 + 8) ext        lower: H, E, F >= -(2 oe + ext * (t8 + 8) + mismatch + 64) (bias >= 0 cancels the query side)
+// The shift K centres the interval; the floor sits 1000 below the lower end and must itself fit.
+inline bool wave16_global_range(const DpArgs& a, uint32_t max_q, uint32_t max_t, int* kshift, int* floor16) {
+  if (a.match < 0 || a.mismatch < 0 || a.gap_open < 0 || a.gap_extend < 0 || a.match + 2 * a.gap_extend > 127) return false;
+  if (a.n_is_wild_global && (a.n_score < -127 || a.n_score + 2 * a.gap_extend > 127)) return false;
+  const int64_t q8 = (max_q + 7) & ~7ll, t8 = (max_t + 7) & ~7ll, oe = (int64_t)a.gap_open + a.gap_extend;
+  const int64_t ub = (int64_t)a.match * std::min<int64_t>(q8, t8) + (q8 + 72) * a.gap_extend + 64;
+  const int64_t lb = -(2 * oe + (int64_t)a.gap_extend * (t8 + 8) + a.mismatch + 64);
+  const int64_t K = (ub + lb) / 2, fl = lb - K - 1000;
+  if (ub - K > 32000 || fl < -32700 || K > 32000 || K < -32000) return false;
+  *kshift = (int)K; *floor16 = (int)fl;
+  return true;
+}
+
 inline bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t) {
+  if (algo == ALGO_GLOBAL) { int k, f; return wave16_global_range(a, max_q, max_t, &k, &f); }
   if (algo != ALGO_LOCAL) return false;
   if ((uint64_t)std::min(max_q, max_t) * (uint64_t)a.match > 32000ull) return false;          // scores stay in 16 bits
   return a.gap_open + a.gap_extend + a.mismatch + std::max(0, -a.n_score) < 8000;
@@ -676,8 +876,10 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   }
   ws.soff = ws.qoff + ws.n_cap;
   uint64_t qs = 0, ss = 0, tasks1 = 0, tasks2 = 0;
+  uint32_t max_q = 0;
   for (size_t i = 0; i < n; i++) {
     ws.h_off[i] = qs; ws.h_off[n + i] = ss;
+    max_q = std::max(max_q, h_qlens[i]);
     const uint64_t tr = ((uint64_t)h_tlens[i] + 7u) >> 3;
     qs += ((uint64_t)h_qlens[i] + 7u) & ~7ull;
     ss += tr;
@@ -688,7 +890,10 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   // (fewer, longer pipeline stages), else 8; and never more workers than tasks (the hardware deals CTAs round-robin).
   const bool many = tasks2 * 4 >= (uint64_t)n_sm * 4 * 3;
   // the s16x2 kernel's row-block is 64 strips; with few tasks the finer int32 blocks (SR = 1) fill the machine better
-  const bool use_s16 = s16_inout && *s16_inout && (many || force_s16);
+  // GLOBAL: the s16x2 kernel wins once there are two row-blocks per scheduler (16k x 16k: 48 pairs and up, 3670 vs 2757 GCUPS at
+  // 128); below that the finer int32 blocks keep more schedulers busy (32 pairs: 2521 vs 1964)
+  const bool many16 = (algo == ALGO_GLOBAL) ? (tasks2 >= (uint64_t)n_sm * 8) : many;
+  const bool use_s16 = s16_inout && *s16_inout && (many16 || force_s16);
   if (s16_inout) *s16_inout = use_s16;
   const int SR = (many || use_s16) ? 2 : 1;
   const uint64_t tasks = (SR == 2) ? tasks2 : tasks1;
@@ -724,6 +929,8 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   cudaMemcpyAsync(ws.soff, ws.h_off + n, n * sizeof(uint64_t), cudaMemcpyHostToDevice, str);
   WaveArgs wa; wa.a = a; wa.algo = algo; wa.maxblk = maxblk; wa.qoff = ws.qoff; wa.soff = ws.soff;
   wa.bnd = ws.bnd; wa.bnd_stride = qs; wa.cand = ws.cand; wa.done = ws.prog; wa.ticket = ws.prog + n;
+  wa.kshift = 0; wa.floor16 = 0;
+  if (use_s16 && algo == ALGO_GLOBAL && !wave16_global_range(a, max_q, max_t, &wa.kshift, &wa.floor16)) return -1;   // cannot happen: checked by wave16_eligible
   const int ctas_per_sm = use_s16 ? WAVE16_MIN_CTAS : 4;
   // <= 16 (24) warp-workers per SM.  Once there is at least one CTA (= one warp per scheduler) for every SM, only whole multiples of
   // the SM count are started: a pipeline runs at the pace of its most crowded scheduler, so 1.7 workers per scheduler (two on
@@ -735,7 +942,8 @@ inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, co
   for (int pass = 0; pass < npass; pass++) {
     cudaMemsetAsync(ws.prog, 0, prog_words * sizeof(uint32_t), str);
     wa.pass = pass; wa.tag_base = ws.next_tag; ws.next_tag += maxblk;
-    if (use_s16) k_wave16_local<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
+    if (use_s16 && algo == ALGO_GLOBAL) k_wave16_global<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
+    else if (use_s16) k_wave16_local<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
     else if (SR == 2) wave_launch_kernel<2>(algo, blocks, wa, str); else wave_launch_kernel<1>(algo, blocks, wa, str);
     launches++;
   }

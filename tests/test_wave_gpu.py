@@ -61,7 +61,7 @@ def test_wave_local_ragged(oracle, scoring, policy, kernel):
 def test_wave_global_ragged(oracle, scoring):
     b = ragged(302)
     want = oracle_align(oracle, b, algo=po.GLOBAL, scoring=scoring)
-    got = run(b, algo=capi.GLOBAL, scoring=scoring)
+    got = run(b, policy=3, algo=capi.GLOBAL, scoring=scoring)            # policy 3: int32 lanes
     assert got["_kernel"] == "wave"
     assert_same(got, want, ["aln_score"], f"wave global {scoring}")
 
@@ -87,7 +87,7 @@ def test_wave_exotic_codes(oracle):
                               (po.SEMI_GLOBAL, K5, dict(start=po.WITH_START, max_query_len=1024))]:
         want = oracle_align(oracle, b, algo=algo, **extra)
         extra.pop("max_query_len", None)
-        for policy in ((4, 3) if algo == po.LOCAL else (2,)):
+        for policy in ((4, 3) if algo in (po.LOCAL, po.GLOBAL) else (2,)):
             got = run(b, policy=policy, algo=algo, **extra)
             assert got["_kernel"] in ("wave", "wave16")
             assert_same(got, want, keys, f"wave exotic codes algo={algo} policy={policy}")
@@ -108,9 +108,21 @@ def test_wave_long_local_with_start(oracle):
 def test_wave_long_global(oracle):
     b = long_pairs(42)
     want = oracle_align(oracle, b, algo=po.GLOBAL, max_query_len=8192)
-    got = run(b, policy=0, algo=capi.GLOBAL)
-    assert got["_kernel"] == "wave"
-    assert_same(got, want, ["aln_score"], "wave long global")
+    for policy, kernel in ((3, "wave"), (4, "wave16")):
+        got = run(b, policy=policy, algo=capi.GLOBAL)
+        assert got["_kernel"] == kernel
+        assert_same(got, want, ["aln_score"], f"{kernel} long global")
+
+
+@pytest.mark.parametrize("scoring", SCORINGS + [(1, 4, 6, 0), (2, 3, 0, 2), (3, 5, 9, 7)])
+def test_wave16_global_ragged(oracle, scoring):
+    """policy 4: k_wave16_global (s16x2 lanes, biased + shifted frame) on ragged short pairs: every boundary case of the
+    half-entry logic (pairs shorter than one strip, one lane, one row-block), N codes (ordinary symbols under the global rule)"""
+    b = ragged(60 + scoring[0])
+    want = oracle_align(oracle, b, algo=po.GLOBAL, scoring=scoring)
+    got = run(b, policy=4, algo=capi.GLOBAL, scoring=scoring)
+    assert got["_kernel"] == "wave16"
+    assert_same(got, want, ["aln_score"], f"wave16 global {scoring}")
 
 
 def test_wave_long_semiglobal_with_start(oracle):
