@@ -1,0 +1,490 @@
+// nvb_batched.cu -- nvbio-style batched alignment SCORING on B200 (C ABI: include/nvbio_b200.h).
+//
+// What the reference does (Non-CDP/NvB/nvbio/alignment): BatchedAlignmentScore<stream, DeviceThreadScheduler>::enact
+// (batched_inl.h) runs one CUDA thread per (pattern, text) job through aln::alignment_score (alignment.h:456-530), which
+// for Gotoh is gotoh_alignment_score_dispatch::run (gotoh/gotoh_inl.h:473-900): bands of 8 pattern columns in int32
+// registers, the band's right border (H, E) parked per text row in a short2 column in local / global memory.
+//
+// This module (same arithmetic, bit-exact -- oracle/nvbio_compat.c is the pinned restatement):
+//   k_nvb_pack  one warp per sequence: bytes -> 2-bit codes, 16 per word, plus a per-sequence "not pure ACGT" flag
+//   k_nvb_s16   fast path: ONE THREAD = TWO JOBS, one per 16-bit lane of the Blackwell DPX s16x2 instructions
+//               (VIADDMNMX.S16x2, VIMNMX3.S16x2[.RELU]); bands of 16 pattern columns in registers; substitution scores
+//               by one PRMT per cell pair from per-column byte tables (sign-replicating selector built once per text
+//               row); H is kept as H + Go so that E, F and the diagonal each cost one instruction; the band border
+//               goes through a coalesced [text row][thread] scratch (8 B per 32 cells).  Used when a host-side range
+//               proof shows every DP value of the batch fits 16 bits; jobs containing a non-ACGT symbol are pushed to a
+//               worklist and redone by
+//   k_nvb_i32   general path: one thread per job, int32 DPX (VIADDMNMX, VIMNMX3[.RELU]), raw byte comparison (any
+//               alphabet), asymmetric Smith-Waterman gap costs, and the BestSink coordinates in the reference's
+//               report order.
+// No CPU fallback: without a CUDA device every entry point fails with a message.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <limits.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "../../include/nvbio_b200.h"
+
+namespace nvb200 {
+
+constexpr int kNeg32 = -(1 << 29);
+constexpr int kNeg16 = -32000;
+constexpr int kThreads = 128;
+constexpr uint32_t kFull = 0xFFFFFFFFu;
+
+struct NvbArgs {
+  const uint8_t* pbytes; const uint32_t* poffs; const uint32_t* ppk; const uint8_t* pflag;
+  const uint8_t* tbytes; const uint32_t* toffs; const uint32_t* tpk; const uint8_t* tflag;
+  const uint32_t* pair_p; const uint32_t* pair_t; int text_shared;     // text_shared: every job uses text 0
+  uint32_t first, count;                                               // job range of this launch
+  int match, mismatch, go_t, ge_t, go_p, ge_p;                         // _t: gap consuming text (F), _p: consuming pattern (E)
+  int band_shift;                                                      // log2 of the reference's BAND_LEN (tie order of LOCAL sinks)
+  int32_t* score; int32_t* sink_i; int32_t* sink_j;
+  uint2* scratch; uint32_t stride;                                     // band border (H, E) per text row: scratch[row * stride + thread]
+  uint32_t* worklist; uint32_t* work_count;
+};
+
+__device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
+  uint32_t d; asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c)); return d;
+}
+__device__ __forceinline__ uint32_t splat16(int v) { const uint32_t u = (uint32_t)v & 0xFFFFu; return u | (u << 16); }
+__device__ __forceinline__ int lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+__device__ __forceinline__ int hi16(uint32_t v) { return (int)(short)(v >> 16); }
+
+// ------------------------------------------------------------------------------------------------------------------
+// 2-bit packing: symbol k of a sequence in bits 2(k&15).. of word (k >> 4); sequence s starts at word (offs[s] >> 4) + s
+__global__ void __launch_bounds__(256) k_nvb_pack(const uint8_t* __restrict__ bytes, const uint32_t* __restrict__ offs, uint32_t nseq, int alphabet,
+                                                  uint32_t* __restrict__ packed, uint8_t* __restrict__ flag) {
+  const uint32_t s = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (s >= nseq) return;
+  const uint32_t o = offs[s], len = offs[s + 1] - o, wo = (o >> 4) + s, nw = (len + 15) >> 4;
+  uint32_t bad = 0;
+  for (uint32_t w = lane; w < nw; w += 32) {
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      const uint32_t c = 16 * w + k;
+      if (c < len) {
+        const uint32_t b = bytes[o + c];
+        uint32_t code;
+        if (alphabet == NVBX_CODES) code = b < 4 ? b : 4;
+        else code = b == 'A' ? 0 : b == 'C' ? 1 : b == 'G' ? 2 : b == 'T' ? 3 : 4;
+        bad |= code >> 2;
+        v |= (code & 3) << (2 * k);
+      }
+    }
+    packed[wo + w] = v;
+  }
+  bad = __any_sync(kFull, bad != 0);
+  if (lane == 0) flag[s] = (uint8_t)bad;
+}
+
+struct Job { uint32_t pi, ti, M, N; };
+__device__ __forceinline__ Job load_job(const NvbArgs& a, uint32_t job) {
+  Job j;
+  j.pi = a.pair_p ? a.pair_p[job] : job;
+  j.ti = a.text_shared ? 0u : (a.pair_t ? a.pair_t[job] : job);
+  j.M = a.poffs[j.pi + 1] - a.poffs[j.pi];
+  j.N = a.toffs[j.ti + 1] - a.toffs[j.ti];
+  return j;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// general path: one thread per job, int32, bands of 8 pattern columns (gotoh_inl.h:473-593 with BAND_LEN = 8)
+template <int N> __device__ __forceinline__ int select_reg(const int (&v)[N], int k) {
+  int x = v[N - 1];
+#pragma unroll
+  for (int j = 0; j < N - 1; j++) x = (k == j) ? v[j] : x;
+  return x;
+}
+// is cell (i, j) reported after cell (bi, bj) in the reference's order (band of columns, then row, then column)?
+__device__ __forceinline__ bool reported_later(int i, int j, int bi, int bj, int band_shift) {
+  if (bj < 0) return true;
+  const int b1 = (j - 1) >> band_shift, b0 = (bj - 1) >> band_shift;
+  if (b1 != b0) return b1 > b0;
+  if (i != bi) return i > bi;
+  return j > bj;
+}
+
+template <int TYPE, bool SINK>
+__global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_worklist) {
+  const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
+  uint32_t job;
+  if (from_worklist) { if (idx >= *a.work_count) return; job = a.worklist[idx]; }
+  else { if (idx >= a.count) return; job = a.first + idx; }
+  const Job jb = load_job(a, job);
+  const uint8_t* __restrict__ P = a.pbytes + a.poffs[jb.pi];
+  const uint8_t* __restrict__ T = a.tbytes + a.toffs[jb.ti];
+  const int M = (int)jb.M, N = (int)jb.N;
+  uint2* __restrict__ col = a.scratch + idx;
+  const uint32_t stride = a.stride;
+  const int go_t = a.go_t, ge_t = a.ge_t, go_p = a.go_p, ge_p = a.ge_p, match = a.match, mismatch = a.mismatch;
+
+  int best = INT_MIN, bi = -1, bj = -1;
+  for (int block = 0; block < M; block += 8) {
+    int q[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) q[j] = (block + j < M) ? (int)P[block + j] : 256 + j;      // pad columns never match
+    int H[9], F[9];
+#pragma unroll
+    for (int j = 0; j <= 8; j++) {
+      const int c = block + j;
+      H[j] = (TYPE == NVBX_LOCAL || c == 0) ? 0 : go_p + ge_p * (c - 1);                    // gotoh_inl.h:690-695
+      F[j] = kNeg32;
+    }
+    const bool first = block == 0, last = block + 8 >= M;
+    const int mj = last ? M - block : 8;                                                     // valid columns of this band
+    uint2 nxt = first ? make_uint2(0, 0) : col[0];
+    for (int i = 1; i <= N; i++) {
+      int hl, e;
+      if (first) { hl = (TYPE == NVBX_GLOBAL) ? go_t + ge_t * (i - 1) : 0; e = (TYPE == NVBX_LOCAL) ? 0 : kNeg32; }   // gotoh_inl.h:77-88
+      else { hl = (int)nxt.x; e = (int)nxt.y; if (i < N) nxt = col[(size_t)i * stride]; }
+      const int t = (int)T[i - 1];
+      int diag = H[0];
+      H[0] = hl;
+#pragma unroll
+      for (int j = 1; j <= 8; j++) {
+        F[j] = __viaddmax_s32(F[j], ge_t, H[j] + go_t);
+        e = __viaddmax_s32(e, ge_p, H[j - 1] + go_p);
+        const int s = (t == q[j - 1]) ? match : mismatch;
+        const int d = diag + s;
+        const int h = (TYPE == NVBX_LOCAL) ? __vimax3_s32_relu(e, F[j], d) : __vimax3_s32(e, F[j], d);
+        diag = H[j];
+        H[j] = h;
+      }
+      if (!last) col[(size_t)(i - 1) * stride] = make_uint2((uint32_t)H[8], (uint32_t)e);
+      if (TYPE == NVBX_LOCAL) {
+        int rowmax = INT_MIN;
+#pragma unroll
+        for (int j = 1; j <= 8; j++) if (j <= mj) rowmax = max(rowmax, H[j]);
+        if (SINK) {
+          if (rowmax >= best) {
+            int cj = 0;
+#pragma unroll
+            for (int j = 1; j <= 8; j++) if (j <= mj && H[j] == rowmax) cj = j;               // largest column of the row
+            if (rowmax > best || reported_later(i, block + cj, bi, bj, a.band_shift)) { best = rowmax; bi = i; bj = block + cj; }
+          }
+        } else best = max(best, rowmax);
+      } else if (last) {
+        const int hM = select_reg(H, mj);
+        if (TYPE == NVBX_SEMI_GLOBAL) { if (hM >= best) { best = hM; bi = i; bj = M; } }    // utils_inl.h:279-299, BestSink `<=`
+        else if (i == N) { best = hM; bi = N; bj = M; }                                      // gotoh_inl.h:896-897
+      }
+    }
+  }
+  a.score[job] = best;
+  if (SINK) { a.sink_i[job] = bi; a.sink_j[job] = bj; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// fast path: one thread = two jobs (lane L = job 2k, lane H = job 2k+1), s16x2, bands of 16 pattern columns, score only.
+// All values live in the frame Hg = H + Go (symmetric gap costs only), so E' = max(E + Ge, Hg_left), F' = max(F + Ge,
+// Hg_top) and D = Hg_diag + (s - Go) are one instruction each; the substitution tables hold s - Go.
+__device__ __forceinline__ uint32_t select16(const uint32_t (&v)[17], int k) {
+  uint32_t x = v[16];
+#pragma unroll
+  for (int j = 1; j < 16; j++) x = (k == j) ? v[j] : x;
+  return x;
+}
+
+template <int TYPE>
+__global__ void __launch_bounds__(kThreads) k_nvb_s16(const NvbArgs a) {
+  const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
+  if (idx >= (a.count + 1) / 2) return;
+  const uint32_t jobA = a.first + 2 * idx, jobB = min(jobA + 1, a.first + a.count - 1);
+  const Job A = load_job(a, jobA), B = load_job(a, jobB);
+  if (a.pflag[A.pi] | a.tflag[A.ti] | a.pflag[B.pi] | a.tflag[B.ti]) {                       // a symbol outside ACGT: general kernel
+    const uint32_t n = (jobB != jobA) ? 2u : 1u;
+    const uint32_t at = atomicAdd(a.work_count, n);
+    a.worklist[at] = jobA;
+    if (n == 2) a.worklist[at + 1] = jobB;
+    return;
+  }
+  const uint32_t* __restrict__ pA = a.ppk + (a.poffs[A.pi] >> 4) + A.pi;
+  const uint32_t* __restrict__ pB = a.ppk + (a.poffs[B.pi] >> 4) + B.pi;
+  const uint32_t* __restrict__ tA = a.tpk + (a.toffs[A.ti] >> 4) + A.ti;
+  const uint32_t* __restrict__ tB = a.tpk + (a.toffs[B.ti] >> 4) + B.ti;
+  const int MA = (int)A.M, MB = (int)B.M, NA = (int)A.N, NB = (int)B.N;
+  const int Mx = max(MA, MB), Nx = max(NA, NB);
+  uint2* __restrict__ col = a.scratch + idx;
+  const uint32_t stride = a.stride;
+  const int go = a.go_t, ge = a.ge_t;
+  const uint32_t go2 = splat16(go), ge2 = splat16(ge);
+  const uint32_t mis1 = (uint32_t)(a.mismatch - go) & 0xFFu, mis4 = mis1 * 0x01010101u;
+  const uint32_t delta = ((uint32_t)(a.match - go) ^ (uint32_t)(a.mismatch - go)) & 0xFFu;
+
+  int bestA = (TYPE == NVBX_LOCAL) ? 0 : INT_MIN, bestB = bestA;       // LOCAL: H frame; otherwise Hg frame (minus Go at the end)
+  uint32_t best2 = 0;
+  for (int block = 0; block < Mx; block += 16) {
+    const uint32_t wA = (block < MA) ? pA[block >> 4] : 0u, wB = (block < MB) ? pB[block >> 4] : 0u;
+    uint32_t tabA[16], tabB[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      tabA[j] = (block + j < MA) ? (mis4 ^ (delta << (8 * ((wA >> (2 * j)) & 3u)))) : mis4;   // pad columns: mismatch against every base
+      tabB[j] = (block + j < MB) ? (mis4 ^ (delta << (8 * ((wB >> (2 * j)) & 3u)))) : mis4;
+    }
+    uint32_t Hg[17], F[17];
+#pragma unroll
+    for (int j = 0; j <= 16; j++) {
+      const int c = block + j;
+      Hg[j] = splat16(((TYPE == NVBX_LOCAL || c == 0) ? 0 : go + ge * (c - 1)) + go);
+      F[j] = splat16(kNeg16);
+    }
+    const bool first = block == 0, last = block + 16 >= Mx;
+    const bool inA = block < MA && MA <= block + 16, inB = block < MB && MB <= block + 16;
+    const int mjA = MA - block, mjB = MB - block;
+    uint2 nxt = first ? make_uint2(0, 0) : col[0];
+    uint32_t twA = 0, twB = 0;
+    for (int i = 1; i <= Nx; i++) {
+      if (((i - 1) & 15) == 0) { twA = (i <= NA) ? tA[(i - 1) >> 4] : 0u; twB = (i <= NB) ? tB[(i - 1) >> 4] : 0u; }
+      const uint32_t sel = (twA & 3u) * 0x0011u + (twB & 3u) * 0x1100u + 0xC480u;            // bytes: [tA], sign, [4 + tB], sign
+      twA >>= 2; twB >>= 2;
+      uint32_t hl, e;
+      if (first) {
+        hl = splat16(((TYPE == NVBX_GLOBAL) ? go + ge * (i - 1) : 0) + go);
+        e = (TYPE == NVBX_LOCAL) ? 0u : splat16(kNeg16);
+      } else { hl = nxt.x; e = nxt.y; if (i < Nx) nxt = col[(size_t)i * stride]; }
+      uint32_t diag = Hg[0];
+      Hg[0] = hl;
+      uint32_t m = 0, hodd = 0;
+#pragma unroll
+      for (int j = 1; j <= 16; j++) {
+        F[j] = __viaddmax_s16x2(F[j], ge2, Hg[j]);
+        e = __viaddmax_s16x2(e, ge2, Hg[j - 1]);
+        const uint32_t s2 = prmt(tabA[j - 1], tabB[j - 1], sel);
+        const uint32_t d = __vadd2(diag, s2);
+        const uint32_t h = (TYPE == NVBX_LOCAL) ? __vimax3_s16x2_relu(e, F[j], d) : __vimax3_s16x2(e, F[j], d);
+        if (TYPE == NVBX_LOCAL) { if (j & 1) hodd = h; else m = __vimax3_s16x2(m, hodd, h); }   // one max per two cells
+        diag = Hg[j];
+        Hg[j] = __vadd2(h, go2);
+      }
+      if (!last) col[(size_t)(i - 1) * stride] = make_uint2(Hg[16], e);
+      if (TYPE == NVBX_LOCAL) {
+        const uint32_t mask = (i <= NA ? 0x0000FFFFu : 0u) | (i <= NB ? 0xFFFF0000u : 0u);   // rows past a job's text end do not count
+        best2 = __vmaxs2(best2, m & mask);
+      } else {
+        if (inA && i <= NA) {
+          const int h = lo16(select16(Hg, mjA));
+          if (TYPE == NVBX_SEMI_GLOBAL) bestA = max(bestA, h); else if (i == NA) bestA = h;
+        }
+        if (inB && i <= NB) {
+          const int h = hi16(select16(Hg, mjB));
+          if (TYPE == NVBX_SEMI_GLOBAL) bestB = max(bestB, h); else if (i == NB) bestB = h;
+        }
+      }
+    }
+  }
+  if (TYPE == NVBX_LOCAL) { bestA = lo16(best2); bestB = hi16(best2); }
+  else { bestA -= go; bestB -= go; }
+  a.score[jobA] = bestA;
+  if (jobB != jobA) a.score[jobB] = bestB;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+uint64_t g_launches = 0;
+int g_policy = 0;
+
+static int fail(const std::string& m) { g_err = m; fprintf(stderr, "[NVBX ERROR:] %s\n", m.c_str()); return -1; }
+#define NVB_CHECK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(std::string(#x) + ": " + cudaGetErrorString(e_)); return -1; } } while (0)
+#define NVB_CHECKP(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { fail(std::string(#x) + ": " + cudaGetErrorString(e_)); nvbx_stream_destroy(s); return nullptr; } } while (0)
+
+}  // namespace nvb200
+
+struct nvbx_stream {
+  cudaStream_t st = nullptr;
+  uint8_t *pbytes = nullptr, *tbytes = nullptr, *pflag = nullptr, *tflag = nullptr;
+  uint32_t *poffs = nullptr, *toffs = nullptr, *ppk = nullptr, *tpk = nullptr, *pair_p = nullptr, *pair_t = nullptr;
+  uint32_t n_patterns = 0, n_texts = 0, n_pairs = 0, max_m = 0, max_n = 0;
+  int text_shared = 0;
+  uint64_t cells = 0;
+  int32_t *score = nullptr, *sink_i = nullptr, *sink_j = nullptr;
+  uint2* scratch = nullptr; size_t scratch_elems = 0;
+  uint32_t *worklist = nullptr, *work_count = nullptr;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  bool have_sinks = false, enacted = false;
+  std::string kernel = "none";
+};
+
+using namespace nvb200;
+
+extern "C" {
+
+void nvbx_set_policy(int policy) { g_policy = policy; }
+uint64_t nvbx_kernel_launches(void) { return g_launches; }
+const char* nvbx_last_error(void) { return g_err.c_str(); }
+
+void nvbx_stream_destroy(nvbx_stream_t* s) {
+  if (!s) return;
+  cudaFree(s->pbytes); cudaFree(s->tbytes); cudaFree(s->pflag); cudaFree(s->tflag); cudaFree(s->poffs); cudaFree(s->toffs);
+  cudaFree(s->ppk); cudaFree(s->tpk); cudaFree(s->pair_p); cudaFree(s->pair_t); cudaFree(s->score); cudaFree(s->sink_i); cudaFree(s->sink_j);
+  cudaFree(s->scratch); cudaFree(s->worklist); cudaFree(s->work_count);
+  if (s->e0) cudaEventDestroy(s->e0);
+  if (s->e1) cudaEventDestroy(s->e1);
+  delete s;
+}
+
+nvbx_stream_t* nvbx_stream_create(const nvbx_batch_t* b, void* cuda_stream) {
+  if (!b || !b->patterns || !b->texts || !b->pattern_offsets || !b->text_offsets || b->n_patterns == 0 || b->n_texts == 0 || b->n_pairs == 0) {
+    fail("nvbx_stream_create: empty or NULL batch"); return nullptr;
+  }
+  if (b->alphabet != NVBX_CODES && b->alphabet != NVBX_ASCII) { fail("nvbx_stream_create: unknown alphabet"); return nullptr; }
+  if (!b->pair_pattern && b->n_pairs > b->n_patterns) { fail("nvbx_stream_create: n_pairs > n_patterns without pair_pattern"); return nullptr; }
+  const int text_shared = (!b->pair_text && b->n_texts == 1) ? 1 : 0;
+  if (!b->pair_text && !text_shared && b->n_pairs > b->n_texts) { fail("nvbx_stream_create: n_pairs > n_texts without pair_text"); return nullptr; }
+  for (uint32_t i = 0; i < b->n_patterns; i++)
+    if (b->pattern_offsets[i + 1] <= b->pattern_offsets[i]) { fail("nvbx_stream_create: empty pattern or decreasing offsets"); return nullptr; }
+  for (uint32_t i = 0; i < b->n_texts; i++)
+    if (b->text_offsets[i + 1] <= b->text_offsets[i]) { fail("nvbx_stream_create: empty text or decreasing offsets"); return nullptr; }
+  nvbx_stream_t* s = new nvbx_stream();
+  s->st = (cudaStream_t)cuda_stream;
+  s->n_patterns = b->n_patterns; s->n_texts = b->n_texts; s->n_pairs = b->n_pairs; s->text_shared = text_shared;
+  for (uint32_t k = 0; k < b->n_pairs; k++) {
+    const uint32_t pi = b->pair_pattern ? b->pair_pattern[k] : k, ti = text_shared ? 0u : (b->pair_text ? b->pair_text[k] : k);
+    if (pi >= b->n_patterns || ti >= b->n_texts) { fail("nvbx_stream_create: pair index out of range"); delete s; return nullptr; }
+    const uint32_t m = b->pattern_offsets[pi + 1] - b->pattern_offsets[pi], n = b->text_offsets[ti + 1] - b->text_offsets[ti];
+    s->max_m = std::max(s->max_m, m); s->max_n = std::max(s->max_n, n);
+    s->cells += (uint64_t)m * n;
+  }
+  const size_t pb = b->pattern_offsets[b->n_patterns], tb = b->text_offsets[b->n_texts];
+  const size_t ppw = (pb >> 4) + b->n_patterns + 2, tpw = (tb >> 4) + b->n_texts + 2;
+  NVB_CHECKP(cudaMalloc(&s->pbytes, pb)); NVB_CHECKP(cudaMalloc(&s->tbytes, tb));
+  NVB_CHECKP(cudaMalloc(&s->poffs, 4 * (size_t)(b->n_patterns + 1))); NVB_CHECKP(cudaMalloc(&s->toffs, 4 * (size_t)(b->n_texts + 1)));
+  NVB_CHECKP(cudaMalloc(&s->ppk, 4 * ppw)); NVB_CHECKP(cudaMalloc(&s->tpk, 4 * tpw));
+  NVB_CHECKP(cudaMalloc(&s->pflag, b->n_patterns)); NVB_CHECKP(cudaMalloc(&s->tflag, b->n_texts));
+  NVB_CHECKP(cudaMalloc(&s->score, 4 * (size_t)b->n_pairs)); NVB_CHECKP(cudaMalloc(&s->sink_i, 4 * (size_t)b->n_pairs)); NVB_CHECKP(cudaMalloc(&s->sink_j, 4 * (size_t)b->n_pairs));
+  NVB_CHECKP(cudaMalloc(&s->worklist, 4 * (size_t)b->n_pairs + 8)); NVB_CHECKP(cudaMalloc(&s->work_count, 4));
+  NVB_CHECKP(cudaEventCreate(&s->e0)); NVB_CHECKP(cudaEventCreate(&s->e1));
+  NVB_CHECKP(cudaMemcpyAsync(s->pbytes, b->patterns, pb, cudaMemcpyHostToDevice, s->st));
+  NVB_CHECKP(cudaMemcpyAsync(s->tbytes, b->texts, tb, cudaMemcpyHostToDevice, s->st));
+  NVB_CHECKP(cudaMemcpyAsync(s->poffs, b->pattern_offsets, 4 * (size_t)(b->n_patterns + 1), cudaMemcpyHostToDevice, s->st));
+  NVB_CHECKP(cudaMemcpyAsync(s->toffs, b->text_offsets, 4 * (size_t)(b->n_texts + 1), cudaMemcpyHostToDevice, s->st));
+  if (b->pair_pattern) { NVB_CHECKP(cudaMalloc(&s->pair_p, 4 * (size_t)b->n_pairs)); NVB_CHECKP(cudaMemcpyAsync(s->pair_p, b->pair_pattern, 4 * (size_t)b->n_pairs, cudaMemcpyHostToDevice, s->st)); }
+  if (b->pair_text) { NVB_CHECKP(cudaMalloc(&s->pair_t, 4 * (size_t)b->n_pairs)); NVB_CHECKP(cudaMemcpyAsync(s->pair_t, b->pair_text, 4 * (size_t)b->n_pairs, cudaMemcpyHostToDevice, s->st)); }
+  k_nvb_pack<<<(b->n_patterns + 7) / 8, 256, 0, s->st>>>(s->pbytes, s->poffs, b->n_patterns, b->alphabet, s->ppk, s->pflag);
+  k_nvb_pack<<<(b->n_texts + 7) / 8, 256, 0, s->st>>>(s->tbytes, s->toffs, b->n_texts, b->alphabet, s->tpk, s->tflag);
+  NVB_CHECKP(cudaGetLastError());
+  g_launches += 2;
+  return s;
+}
+
+int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks) {
+  if (!s || !al) return fail("nvbx_stream_enact: NULL argument");
+  if (al->type < NVBX_GLOBAL || al->type > NVBX_SEMI_GLOBAL) return fail("nvbx_stream_enact: unknown alignment type");
+  NvbArgs a{};
+  a.pbytes = s->pbytes; a.poffs = s->poffs; a.ppk = s->ppk; a.pflag = s->pflag;
+  a.tbytes = s->tbytes; a.toffs = s->toffs; a.tpk = s->tpk; a.tflag = s->tflag;
+  a.pair_p = s->pair_p; a.pair_t = s->pair_t; a.text_shared = s->text_shared;
+  switch (al->algo) {
+    case NVBX_GOTOH: a.match = al->match; a.mismatch = al->mismatch; a.go_t = a.go_p = al->gap_open; a.ge_t = a.ge_p = al->gap_ext; a.band_shift = 3; break;
+    case NVBX_SMITH_WATERMAN: a.match = al->match; a.mismatch = al->mismatch; a.go_t = a.ge_t = al->gap_open; a.go_p = a.ge_p = al->gap_ext; a.band_shift = 4; break;
+    case NVBX_EDIT_DISTANCE: a.match = 0; a.mismatch = -1; a.go_t = a.ge_t = a.go_p = a.ge_p = -1; a.band_shift = 4; break;
+    default: return fail("nvbx_stream_enact: unknown aligner");
+  }
+  a.score = s->score; a.sink_i = s->sink_i; a.sink_j = s->sink_j; a.worklist = s->worklist; a.work_count = s->work_count;
+
+  // host-side range proof for the s16x2 path: every H + Go, E, F and diagonal sum of any job of the batch (pads included) stays
+  // inside [-31000, 32000]; scores fit the byte tables; symmetric non-positive gap costs
+  const long long mn = std::min(s->max_m, s->max_n), sum = (long long)s->max_m + s->max_n;
+  const long long pos = std::max(0, std::max(a.match, a.mismatch));
+  const long long hi = pos * mn + 2LL * std::abs(a.go_t) + 16;
+  const long long lo = (al->type == NVBX_LOCAL) ? 2LL * a.go_t + std::min(a.mismatch, 0) + a.ge_t
+                                                : 3LL * a.go_t + (long long)a.ge_t * (sum + 2) + std::min(a.mismatch, 0) + std::min(a.match, 0);
+  const bool fits = hi <= 32000 && lo >= -31000 && a.go_t == a.go_p && a.ge_t == a.ge_p && a.go_t <= 0 && a.ge_t <= 0 && a.ge_t >= -700 &&
+                    a.mismatch <= 0 && a.match - a.go_t <= 127 && a.match - a.go_t >= -128 && a.mismatch - a.go_t <= 127 && a.mismatch - a.go_t >= -128;
+  const bool fast = fits && !want_sinks && g_policy == 0;
+
+  // chunk the jobs so that the band-border scratch (8 B per text row per thread) stays below ~2 GB
+  const size_t cap_elems = (size_t)1 << 28;
+  size_t chunk = cap_elems / std::max<size_t>(1, s->max_n);
+  chunk = std::max<size_t>(256, chunk & ~(size_t)255);
+  chunk = std::min<size_t>(chunk, ((size_t)s->n_pairs + 255) & ~(size_t)255);
+  const size_t need = chunk * s->max_n;
+  if (need > s->scratch_elems) {
+    if (s->scratch) cudaFree(s->scratch);
+    s->scratch = nullptr; s->scratch_elems = 0;
+    if (cudaMalloc(&s->scratch, need * sizeof(uint2)) != cudaSuccess) { cudaGetLastError(); return fail("nvbx_stream_enact: cannot allocate the band-border scratch (text too long for this batch)"); }
+    s->scratch_elems = need;
+  }
+  a.scratch = s->scratch; a.stride = (uint32_t)chunk;
+
+  NVB_CHECK(cudaEventRecord(s->e0, s->st));
+  bool used_i32 = !fast;
+  for (size_t first = 0; first < s->n_pairs; first += chunk) {
+    a.first = (uint32_t)first; a.count = (uint32_t)std::min<size_t>(chunk, s->n_pairs - first);
+    const int type = al->type;
+    if (fast) {
+      NVB_CHECK(cudaMemsetAsync(s->work_count, 0, 4, s->st));
+      const uint32_t items = (a.count + 1) / 2, g = (items + kThreads - 1) / kThreads, g2 = (a.count + kThreads - 1) / kThreads;
+      if (type == NVBX_GLOBAL) { k_nvb_s16<NVBX_GLOBAL><<<g, kThreads, 0, s->st>>>(a); k_nvb_i32<NVBX_GLOBAL, false><<<g2, kThreads, 0, s->st>>>(a, 1); }
+      else if (type == NVBX_LOCAL) { k_nvb_s16<NVBX_LOCAL><<<g, kThreads, 0, s->st>>>(a); k_nvb_i32<NVBX_LOCAL, false><<<g2, kThreads, 0, s->st>>>(a, 1); }
+      else { k_nvb_s16<NVBX_SEMI_GLOBAL><<<g, kThreads, 0, s->st>>>(a); k_nvb_i32<NVBX_SEMI_GLOBAL, false><<<g2, kThreads, 0, s->st>>>(a, 1); }
+      g_launches += 2;
+    } else {
+      const uint32_t g = (a.count + kThreads - 1) / kThreads;
+      if (want_sinks) {
+        if (type == NVBX_GLOBAL) k_nvb_i32<NVBX_GLOBAL, true><<<g, kThreads, 0, s->st>>>(a, 0);
+        else if (type == NVBX_LOCAL) k_nvb_i32<NVBX_LOCAL, true><<<g, kThreads, 0, s->st>>>(a, 0);
+        else k_nvb_i32<NVBX_SEMI_GLOBAL, true><<<g, kThreads, 0, s->st>>>(a, 0);
+      } else {
+        if (type == NVBX_GLOBAL) k_nvb_i32<NVBX_GLOBAL, false><<<g, kThreads, 0, s->st>>>(a, 0);
+        else if (type == NVBX_LOCAL) k_nvb_i32<NVBX_LOCAL, false><<<g, kThreads, 0, s->st>>>(a, 0);
+        else k_nvb_i32<NVBX_SEMI_GLOBAL, false><<<g, kThreads, 0, s->st>>>(a, 0);
+      }
+      g_launches += 1;
+    }
+    NVB_CHECK(cudaGetLastError());
+  }
+  NVB_CHECK(cudaEventRecord(s->e1, s->st));
+  s->have_sinks = want_sinks != 0; s->enacted = true;
+  s->kernel = used_i32 ? "int32" : "s16x2";
+  return 0;
+}
+
+int nvbx_stream_results(nvbx_stream_t* s, int32_t* scores, int32_t* sink_text, int32_t* sink_pattern) {
+  if (!s || !scores) return fail("nvbx_stream_results: NULL argument");
+  if (!s->enacted) return fail("nvbx_stream_results: nothing was enacted");
+  if ((sink_text || sink_pattern) && !s->have_sinks) return fail("nvbx_stream_results: sinks were not computed (want_sinks = 0)");
+  NVB_CHECK(cudaMemcpyAsync(scores, s->score, 4 * (size_t)s->n_pairs, cudaMemcpyDeviceToHost, s->st));
+  if (sink_text) NVB_CHECK(cudaMemcpyAsync(sink_text, s->sink_i, 4 * (size_t)s->n_pairs, cudaMemcpyDeviceToHost, s->st));
+  if (sink_pattern) NVB_CHECK(cudaMemcpyAsync(sink_pattern, s->sink_j, 4 * (size_t)s->n_pairs, cudaMemcpyDeviceToHost, s->st));
+  NVB_CHECK(cudaStreamSynchronize(s->st));
+  return 0;
+}
+
+const int32_t* nvbx_stream_scores_device(nvbx_stream_t* s) { return s ? s->score : nullptr; }
+float nvbx_stream_last_ms(nvbx_stream_t* s) {
+  if (!s || !s->enacted) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(s->e1) != cudaSuccess || cudaEventElapsedTime(&ms, s->e0, s->e1) != cudaSuccess) return -1.f;
+  return ms;
+}
+uint64_t nvbx_stream_cells(const nvbx_stream_t* s) { return s ? s->cells : 0; }
+const char* nvbx_stream_kernel(const nvbx_stream_t* s) { return s ? s->kernel.c_str() : "none"; }
+
+int nvbx_batched_score_host(const nvbx_aligner_t* al, const nvbx_batch_t* b, int32_t* scores, int32_t* sink_text, int32_t* sink_pattern, float ms[3]) {
+  cudaEvent_t e[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (auto& x : e) if (cudaEventCreate(&x) != cudaSuccess) return fail("nvbx_batched_score_host: no CUDA device");
+  int rc = -1;
+  cudaEventRecord(e[0], 0);
+  nvbx_stream_t* s = nvbx_stream_create(b, nullptr);
+  if (s) {
+    cudaEventRecord(e[1], 0);
+    rc = nvbx_stream_enact(s, al, (sink_text || sink_pattern) ? 1 : 0);
+    if (rc == 0) {
+      cudaEventRecord(e[2], 0);
+      rc = nvbx_stream_results(s, scores, sink_text, sink_pattern);
+      cudaEventRecord(e[3], 0);
+      cudaEventSynchronize(e[3]);
+      if (rc == 0 && ms) for (int k = 0; k < 3; k++) cudaEventElapsedTime(&ms[k], e[k], e[k + 1]);
+    }
+    nvbx_stream_destroy(s);
+  }
+  for (auto& x : e) cudaEventDestroy(x);
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,143 @@
+"""ctypes binding of the nvbio-style batched alignment scoring adapter (include/nvbio_b200.h; replaces
+aln::BatchedAlignmentScore<...>::enact of Non-CDP/NvB/nvbio/alignment/batched.h:313-335 as driven by
+NvB/sw-benchmark/sw-benchmark.cu:340-444).  No fallback: the functions live in libgasal_b200.so and need a CUDA device."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import capi
+
+GLOBAL, LOCAL, SEMI_GLOBAL = 0, 1, 2                 # aln::AlignmentType (alignment_base.h:54)
+GOTOH, SMITH_WATERMAN, EDIT_DISTANCE = 0, 1, 2
+CODES, ASCII = 0, 1
+NVB_SYMBOLS = ["nvbx_stream_create", "nvbx_stream_enact", "nvbx_stream_results", "nvbx_stream_scores_device", "nvbx_stream_last_ms",
+               "nvbx_stream_cells", "nvbx_stream_kernel", "nvbx_stream_destroy", "nvbx_batched_score_host", "nvbx_set_policy",
+               "nvbx_kernel_launches", "nvbx_last_error"]
+
+
+class AlignerT(C.Structure):
+    _fields_ = [("algo", C.c_int32), ("type", C.c_int32), ("match", C.c_int32), ("mismatch", C.c_int32), ("gap_open", C.c_int32), ("gap_ext", C.c_int32)]
+
+
+class BatchT(C.Structure):
+    _fields_ = [("patterns", C.c_void_p), ("pattern_offsets", C.c_void_p), ("n_patterns", C.c_uint32),
+                ("texts", C.c_void_p), ("text_offsets", C.c_void_p), ("n_texts", C.c_uint32),
+                ("pair_pattern", C.c_void_p), ("pair_text", C.c_void_p), ("n_pairs", C.c_uint32), ("alphabet", C.c_int32)]
+
+
+_bound = False
+
+
+def _lib() -> C.CDLL:
+    global _bound
+    lib = capi.load()
+    if not _bound:
+        lib.nvbx_stream_create.argtypes = [C.POINTER(BatchT), C.c_void_p]; lib.nvbx_stream_create.restype = C.c_void_p
+        lib.nvbx_stream_enact.argtypes = [C.c_void_p, C.POINTER(AlignerT), C.c_int]; lib.nvbx_stream_enact.restype = C.c_int
+        lib.nvbx_stream_results.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]; lib.nvbx_stream_results.restype = C.c_int
+        lib.nvbx_stream_scores_device.argtypes = [C.c_void_p]; lib.nvbx_stream_scores_device.restype = C.c_void_p
+        lib.nvbx_stream_last_ms.argtypes = [C.c_void_p]; lib.nvbx_stream_last_ms.restype = C.c_float
+        lib.nvbx_stream_cells.argtypes = [C.c_void_p]; lib.nvbx_stream_cells.restype = C.c_uint64
+        lib.nvbx_stream_kernel.argtypes = [C.c_void_p]; lib.nvbx_stream_kernel.restype = C.c_char_p
+        lib.nvbx_stream_destroy.argtypes = [C.c_void_p]
+        lib.nvbx_batched_score_host.argtypes = [C.POINTER(AlignerT), C.POINTER(BatchT), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
+        lib.nvbx_batched_score_host.restype = C.c_int
+        lib.nvbx_set_policy.argtypes = [C.c_int]
+        lib.nvbx_kernel_launches.restype = C.c_uint64
+        lib.nvbx_last_error.restype = C.c_char_p
+        _bound = True
+    return lib
+
+
+def concat(seqs: Sequence[np.ndarray]) -> Tuple[np.ndarray, np.ndarray]:
+    """list of uint8 arrays -> (concatenated bytes, offsets[n + 1])"""
+    offs = np.zeros(len(seqs) + 1, dtype=np.uint32)
+    offs[1:] = np.cumsum([len(s) for s in seqs])
+    return (np.concatenate([np.asarray(s, dtype=np.uint8) for s in seqs]) if seqs else np.zeros(0, np.uint8)), offs
+
+
+class Batch:
+    """Host-side job list (the reference's stream_type strings): keeps the numpy arrays alive behind the POD."""
+
+    def __init__(self, patterns: np.ndarray, pattern_offsets: np.ndarray, texts: np.ndarray, text_offsets: np.ndarray,
+                 pair_pattern: Optional[np.ndarray] = None, pair_text: Optional[np.ndarray] = None, n_pairs: Optional[int] = None, alphabet: int = CODES):
+        self.patterns = np.ascontiguousarray(patterns, dtype=np.uint8); self.poffs = np.ascontiguousarray(pattern_offsets, dtype=np.uint32)
+        self.texts = np.ascontiguousarray(texts, dtype=np.uint8); self.toffs = np.ascontiguousarray(text_offsets, dtype=np.uint32)
+        self.pp = None if pair_pattern is None else np.ascontiguousarray(pair_pattern, dtype=np.uint32)
+        self.pt = None if pair_text is None else np.ascontiguousarray(pair_text, dtype=np.uint32)
+        if n_pairs is None:
+            n_pairs = len(self.pp) if self.pp is not None else (len(self.pt) if self.pt is not None else len(self.poffs) - 1)
+        self.n_pairs = int(n_pairs)
+        self.pod = BatchT(self.patterns.ctypes.data, self.poffs.ctypes.data, len(self.poffs) - 1, self.texts.ctypes.data, self.toffs.ctypes.data,
+                          len(self.toffs) - 1, None if self.pp is None else self.pp.ctypes.data, None if self.pt is None else self.pt.ctypes.data,
+                          self.n_pairs, alphabet)
+
+    def job(self, k: int) -> Tuple[np.ndarray, np.ndarray]:
+        pi = k if self.pp is None else int(self.pp[k])
+        ti = (0 if len(self.toffs) == 2 and self.pt is None else k) if self.pt is None else int(self.pt[k])
+        return self.patterns[self.poffs[pi]:self.poffs[pi + 1]], self.texts[self.toffs[ti]:self.toffs[ti + 1]]
+
+
+def aligner(algo: int, type_: int, match: int = 0, mismatch: int = 0, gap_open: int = 0, gap_ext: int = 0) -> AlignerT:
+    return AlignerT(algo, type_, match, mismatch, gap_open, gap_ext)
+
+
+class Stream:
+    """Device-resident batch: create (upload + pack) once, enact any number of aligners on it (BatchedAlignmentScore::enact)."""
+
+    def __init__(self, batch: Batch, cuda_stream: Optional[int] = None):
+        self.batch = batch
+        self._h = _lib().nvbx_stream_create(C.byref(batch.pod), cuda_stream)
+        if not self._h:
+            raise RuntimeError("nvbx_stream_create: " + _lib().nvbx_last_error().decode())
+
+    def enact(self, al: AlignerT, want_sinks: bool = False) -> None:
+        if _lib().nvbx_stream_enact(self._h, C.byref(al), 1 if want_sinks else 0) != 0:
+            raise RuntimeError("nvbx_stream_enact: " + _lib().nvbx_last_error().decode())
+
+    def results(self, want_sinks: bool = False):
+        n = self.batch.n_pairs
+        sc = np.empty(n, np.int32); si = np.empty(n, np.int32) if want_sinks else None; sj = np.empty(n, np.int32) if want_sinks else None
+        rc = _lib().nvbx_stream_results(self._h, sc.ctypes.data, None if si is None else si.ctypes.data, None if sj is None else sj.ctypes.data)
+        if rc != 0:
+            raise RuntimeError("nvbx_stream_results: " + _lib().nvbx_last_error().decode())
+        return sc, si, sj
+
+    def last_ms(self) -> float:
+        return float(_lib().nvbx_stream_last_ms(self._h))
+
+    def cells(self) -> int:
+        return int(_lib().nvbx_stream_cells(self._h))
+
+    def kernel(self) -> str:
+        return _lib().nvbx_stream_kernel(self._h).decode()
+
+    def close(self) -> None:
+        if self._h:
+            _lib().nvbx_stream_destroy(self._h); self._h = None
+
+    def __enter__(self): return self
+    def __exit__(self, *exc): self.close()
+
+
+def batched_score(al: AlignerT, batch: Batch, want_sinks: bool = False):
+    """One-call host-buffer form.  Returns (scores, sink_text, sink_pattern, ms[upload+pack, scoring, download])."""
+    n = batch.n_pairs
+    sc = np.empty(n, np.int32); si = np.empty(n, np.int32) if want_sinks else None; sj = np.empty(n, np.int32) if want_sinks else None
+    ms = (C.c_float * 3)()
+    rc = _lib().nvbx_batched_score_host(C.byref(al), C.byref(batch.pod), sc.ctypes.data, None if si is None else si.ctypes.data,
+                                        None if sj is None else sj.ctypes.data, ms)
+    if rc != 0:
+        raise RuntimeError("nvbx_batched_score_host: " + _lib().nvbx_last_error().decode())
+    return sc, si, sj, (ms[0], ms[1], ms[2])
+
+
+def set_policy(p: int) -> None:
+    _lib().nvbx_set_policy(p)
+
+
+def kernel_launches() -> int:
+    return int(_lib().nvbx_kernel_launches())

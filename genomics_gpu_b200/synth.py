@@ -237,3 +237,37 @@ def random_ragged_pairs(n: int, qmin: int, qmax: int, tmin: int, tmax: int, *, s
             tt[rng.random(tl) < n_frac] = N_CODE
         queries.append(q.tobytes()); targets.append(tt.tobytes())
     return batch_from_sequences(queries, targets)
+
+
+# ---- nvbio-style batched scoring jobs (include/nvbio_b200.h; NvB/sw-benchmark shape: reads against text windows) ----------
+def nvb_jobs(n: int, m_lo: int, m_hi: int, n_lo: int, n_hi: int, seed: int = 1, sub: float = 0.05, indel: float = 0.02, shared_text: bool = False):
+    """n (pattern, text) jobs over codes 0..3: text random, pattern = a window of its text with substitutions and short indels
+    (a third of the patterns are unrelated random strings).  Returns (patterns, pattern_offsets, texts, text_offsets)."""
+    rng = np.random.default_rng(seed)
+    n_texts = 1 if shared_text else n
+    t_lens = rng.integers(n_lo, n_hi + 1, n_texts)
+    texts = [rng.integers(0, 4, int(L)).astype(np.uint8) for L in t_lens]
+    pats = []
+    for k in range(n):
+        t = texts[0 if shared_text else k]
+        m = int(rng.integers(m_lo, m_hi + 1))
+        if k % 3 == 2:
+            p = rng.integers(0, 4, m).astype(np.uint8)
+        else:
+            a = int(rng.integers(0, max(1, len(t) - m + 1)))
+            p = t[a:a + m].copy()
+            flip = rng.random(len(p)) < sub
+            p[flip] = rng.integers(0, 4, int(flip.sum()))
+            if indel > 0 and len(p) > 4:
+                for _ in range(int(rng.binomial(len(p), indel))):
+                    pos = int(rng.integers(1, len(p) - 1))
+                    if rng.random() < 0.5:
+                        p = np.delete(p, pos)
+                    else:
+                        p = np.insert(p, pos, rng.integers(0, 4, int(rng.integers(1, 4)))).astype(np.uint8)
+            if len(p) == 0:
+                p = rng.integers(0, 4, 1).astype(np.uint8)
+        pats.append(np.ascontiguousarray(p, dtype=np.uint8))
+    poffs = np.zeros(n + 1, np.uint32); poffs[1:] = np.cumsum([len(p) for p in pats])
+    toffs = np.zeros(n_texts + 1, np.uint32); toffs[1:] = np.cumsum([len(t) for t in texts])
+    return np.concatenate(pats), poffs, np.concatenate(texts), toffs

@@ -1,0 +1,93 @@
+/* nvbio_b200.h -- C ABI of the nvbio-style batched alignment SCORING adapter.
+ *
+ * Replaces, for the suite's second alignment benchmark, the path
+ *     aln::BatchedAlignmentScore<stream_type, DeviceThreadScheduler>::enact( stream )
+ *         (Non-CDP/NvB/nvbio/alignment/batched.h:313-335, batched_inl.h; one CUDA thread per (pattern, text) job calling
+ *          aln::alignment_score, alignment.h:456-530)
+ * as driven by NvB/sw-benchmark/sw-benchmark.cu:340-444 (batch_score_profile_all: Gotoh global / semi-global / local and
+ * edit-distance semi-global of 256 k reads against a text, BestSink scores written to an int16 array).
+ *
+ * The templated C++ `stream_type` (batched.h:239-300: aligner(), size(), pattern_length(i), text_length(i),
+ * load_strings(i), output(i)) becomes two PODs: nvbx_aligner_t (aligner_type + scoring scheme) and nvbx_batch_t (the
+ * strings of every job).  nvbx_stream_enact is BatchedAlignmentScore::enact; nvbx_stream_results is stream.output(i)
+ * for a BestSink<int32> (sink_inl.h:36-60).  Plain pointers and sizes only; host pointers unless stated otherwise.
+ *
+ * Semantics (bit-exact with the reference's host code path for every job whose DP values stay inside the reference's
+ * int16 column storage, min_score = INT32_MIN i.e. no early exit -- what sw-benchmark uses):
+ *   pattern = horizontal string j = 1..M, text = vertical string i = 1..N (gotoh/gotoh_inl.h:473-593)
+ *   F(i,j) = max(F(i-1,j) + Ge, H(i-1,j) + Go);  E(i,j) = max(E(i,j-1) + Ge, H(i,j-1) + Go)
+ *   H(i,j) = max(E, F, H(i-1,j-1) + (text[i] == pattern[j] ? match : mismatch)) [, 0 for LOCAL]
+ *   (a gap of length k costs Go + (k-1) Ge; scores are SIGNED: penalties are negative numbers, utils.h:114-134)
+ *   GLOBAL: H(N,M).  SEMI_GLOBAL: pattern global, text free at both ends: max_i H(i,M).  LOCAL: max over all cells.
+ *   Smith-Waterman (utils.h:92-109): linear gaps, Go = Ge = deletion for text-consuming gaps, insertion for
+ *   pattern-consuming gaps.  Edit distance (ed/ed_utils.h:45-52): 0 / -1 / -1 / -1, score = -distance.
+ *   Sinks are the reference's BestSink coordinates: (text end i, pattern end j), 1-based, the LAST maximum in the
+ *   reference's report order (bands of 8 (Gotoh) / 16 (SW, ED) pattern columns, then text row, then column).
+ */
+#ifndef NVBIO_B200_H
+#define NVBIO_B200_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* aln::AlignmentType, alignment_base.h:54 (same order) */
+enum { NVBX_GLOBAL = 0, NVBX_LOCAL = 1, NVBX_SEMI_GLOBAL = 2 };
+/* aligner families: aln::GotohAligner / SmithWatermanAligner / EditDistanceAligner (alignment_base.h) */
+enum { NVBX_GOTOH = 0, NVBX_SMITH_WATERMAN = 1, NVBX_EDIT_DISTANCE = 2 };
+/* how the symbol bytes are read: NVBX_CODES = small integer codes (0..3 = A,C,G,T as in nvbio's DNA alphabet; any other
+ * byte value is a symbol of its own), NVBX_ASCII = raw characters.  Either way two symbols match iff their bytes are
+ * equal (utils.h:124); the alphabet only tells the packer which bytes are the four bases of the 2-bit fast path. */
+enum { NVBX_CODES = 0, NVBX_ASCII = 1 };
+
+typedef struct {
+  int32_t algo;        /* NVBX_GOTOH / NVBX_SMITH_WATERMAN / NVBX_EDIT_DISTANCE */
+  int32_t type;        /* NVBX_GLOBAL / NVBX_LOCAL / NVBX_SEMI_GLOBAL */
+  int32_t match;       /* SimpleGotohScheme / SimpleSmithWatermanScheme fields (utils.h:92-134); ignored for edit distance */
+  int32_t mismatch;
+  int32_t gap_open;    /* Gotoh: m_gap_open (cost of the FIRST gap symbol);  SW: m_deletion */
+  int32_t gap_ext;     /* Gotoh: m_gap_ext;                                  SW: m_insertion */
+} nvbx_aligner_t;
+
+/* The jobs of one batch.  Sequences are concatenated; sequence s of a set occupies bytes [offsets[s], offsets[s+1]).
+ * Job k aligns pattern pair_pattern[k] with text pair_text[k].  pair_pattern == NULL means job k uses pattern k;
+ * pair_text == NULL means job k uses text k, or text 0 when n_texts == 1 (sw-benchmark's all-against-one shape). */
+typedef struct {
+  const uint8_t* patterns; const uint32_t* pattern_offsets; uint32_t n_patterns;   /* offsets: n_patterns + 1 entries */
+  const uint8_t* texts;    const uint32_t* text_offsets;    uint32_t n_texts;      /* offsets: n_texts + 1 entries */
+  const uint32_t* pair_pattern; const uint32_t* pair_text; uint32_t n_pairs;
+  int32_t alphabet;                                                                /* NVBX_CODES / NVBX_ASCII */
+} nvbx_batch_t;
+
+typedef struct nvbx_stream nvbx_stream_t;    /* opaque: the device-resident batch (AlignmentStream) + scratch */
+
+/* Upload a batch (H2D on `cuda_stream`, NULL = default stream) and 2-bit pack it on the device.  NULL on error. */
+nvbx_stream_t* nvbx_stream_create(const nvbx_batch_t* batch, void* cuda_stream);
+/* BatchedAlignmentScore::enact: queue the scoring of every job on the stream's CUDA stream; returns without waiting.
+ * want_sinks != 0 also computes the BestSink coordinates (int32 kernel).  0, or -1 on invalid arguments. */
+int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* aligner, int want_sinks);
+/* stream.output(i) for all i: wait for the last enact and copy scores (and sinks, if they were computed and the
+ * pointers are non-NULL) to host arrays of n_pairs int32. */
+int nvbx_stream_results(nvbx_stream_t* s, int32_t* scores, int32_t* sink_text, int32_t* sink_pattern);
+/* device pointer to the int32 scores of the last enact (valid until the next enact / destroy) */
+const int32_t* nvbx_stream_scores_device(nvbx_stream_t* s);
+float nvbx_stream_last_ms(nvbx_stream_t* s);            /* CUDA-event time of the last enact (synchronises) */
+uint64_t nvbx_stream_cells(const nvbx_stream_t* s);     /* sum over jobs of M * N (sw-benchmark.cu:380 GCUPS numerator) */
+const char* nvbx_stream_kernel(const nvbx_stream_t* s); /* "s16x2", "int32" or "s16x2+int32" for the last enact */
+void nvbx_stream_destroy(nvbx_stream_t* s);
+
+/* One-call form with host buffers: create, enact, results, destroy.  ms[0..2] (optional) = upload + pack, scoring,
+ * download in milliseconds.  sink pointers may be NULL (then the score-only fast path is eligible). */
+int nvbx_batched_score_host(const nvbx_aligner_t* aligner, const nvbx_batch_t* batch, int32_t* scores, int32_t* sink_text,
+                            int32_t* sink_pattern, float ms[3]);
+
+/* 0 = automatic (s16x2 two-jobs-per-thread kernel when the host-side range proof allows it, int32 otherwise),
+ * 1 = always the int32 kernel (A/B testing and parity tests). */
+void nvbx_set_policy(int policy);
+uint64_t nvbx_kernel_launches(void);
+const char* nvbx_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NVBIO_B200_H */

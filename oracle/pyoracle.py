@@ -246,3 +246,59 @@ class NwRefHost:
         reference = np.empty(n, dtype=np.uint8); query = np.empty(n, dtype=np.uint8)
         self.lib.nw_ref_generate_query(reference.ctypes.data, query.ctypes.data, n, seed)
         return reference, query
+
+
+# ---- nvbio-style batched scoring (oracle/nvbio_compat.c; reference Non-CDP/NvB/nvbio/alignment/gotoh/gotoh_inl.h:473-900) ----
+NVB_GLOBAL, NVB_LOCAL, NVB_SEMI_GLOBAL = 0, 1, 2
+NVB_GOTOH, NVB_SW, NVB_ED = 0, 1, 2
+NVB_BAND = {NVB_GOTOH: 8, NVB_SW: 16, NVB_ED: 16}     # the reference's BAND_LEN per aligner (gotoh_inl.h:1494-1503, sw_inl.h:1333-1340)
+
+
+class NvbioOracle:
+    """oracle/nvbio_compat.c (restatement) and, when built, oracle/_ref/libnvbio_ref.so (the reference's own host code path)."""
+
+    def __init__(self):
+        path = os.path.join(HERE, "_build", "libnvbio_compat.so")
+        if not os.path.exists(path):
+            build_oracle("oracle")
+        self.lib = C.CDLL(path)
+        self.lib.nvbio_compat_score.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p]
+        self.lib.nvbio_compat_batch.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p,
+                                                C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
+        ref = os.path.join(HERE, "_ref", "libnvbio_ref.so")
+        self.ref = C.CDLL(ref) if os.path.exists(ref) else None
+        if self.ref is not None:
+            self.ref.nvbio_ref_score.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+
+    @staticmethod
+    def _scheme(scheme):
+        return np.asarray(list(scheme) + [0] * (4 - len(scheme)), dtype=np.int32)
+
+    def score(self, algo, type_, scheme, pattern, text):
+        p = np.ascontiguousarray(pattern, dtype=np.uint8); t = np.ascontiguousarray(text, dtype=np.uint8)
+        sc = self._scheme(scheme); out = np.zeros(3, np.int32)
+        rc = self.lib.nvbio_compat_score(algo, type_, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, NVB_BAND[algo], out.ctypes.data)
+        assert rc == 0
+        return tuple(int(x) for x in out)
+
+    def ref_score(self, algo, type_, scheme, pattern, text):
+        p = np.ascontiguousarray(pattern, dtype=np.uint8); t = np.ascontiguousarray(text, dtype=np.uint8)
+        sc = self._scheme(scheme); out = np.zeros(3, np.int32)
+        rc = self.ref.nvbio_ref_score(algo, type_, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, out.ctypes.data)
+        assert rc == 0
+        return tuple(int(x) for x in out)
+
+    def batch(self, algo, type_, scheme, patterns, poffs, texts, toffs, pair_pattern=None, pair_text=None, n_pairs=None):
+        patterns = np.ascontiguousarray(patterns, dtype=np.uint8); texts = np.ascontiguousarray(texts, dtype=np.uint8)
+        poffs = np.ascontiguousarray(poffs, dtype=np.uint32); toffs = np.ascontiguousarray(toffs, dtype=np.uint32)
+        pp = None if pair_pattern is None else np.ascontiguousarray(pair_pattern, dtype=np.uint32)
+        pt = None if pair_text is None else np.ascontiguousarray(pair_text, dtype=np.uint32)
+        if n_pairs is None:
+            n_pairs = len(pp) if pp is not None else (len(pt) if pt is not None else len(poffs) - 1)
+        sc = self._scheme(scheme)
+        s = np.empty(n_pairs, np.int32); si = np.empty(n_pairs, np.int32); sj = np.empty(n_pairs, np.int32)
+        rc = self.lib.nvbio_compat_batch(algo, type_, sc.ctypes.data, patterns.ctypes.data, poffs.ctypes.data, texts.ctypes.data, toffs.ctypes.data,
+                                         len(toffs) - 1, None if pp is None else pp.ctypes.data, None if pt is None else pt.ctypes.data, n_pairs,
+                                         NVB_BAND[algo], s.ctypes.data, si.ctypes.data, sj.ctypes.data)
+        assert rc == 0
+        return s, si, sj

@@ -1,0 +1,156 @@
+"""GPU parity of the nvbio-style batched scoring adapter (include/nvbio_b200.h) against oracle/nvbio_compat.c -- itself pinned to
+the reference's host build of Non-CDP/NvB/nvbio/alignment (tests/test_nvbio_oracle.py) -- and against the committed golden
+vectors of that build.  Every call goes through the C ABI."""
+import os
+
+import numpy as np
+import pytest
+
+from genomics_gpu_b200 import nvb, synth
+from oracle import pyoracle as po
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "nvbio_golden.npz")
+TYPES = (nvb.GLOBAL, nvb.LOCAL, nvb.SEMI_GLOBAL)
+GOTOH_SW = (2, -1, -2, -1)          # sw-benchmark.cu:585-589
+
+
+@pytest.fixture(scope="module")
+def orc():
+    return po.NvbioOracle()
+
+
+def run(al, batch, want_sinks=False, policy=0):
+    nvb.set_policy(policy)
+    try:
+        with nvb.Stream(batch) as st:
+            st.enact(al, want_sinks)
+            s, si, sj = st.results(want_sinks)
+            return s, si, sj, st.kernel()
+    finally:
+        nvb.set_policy(0)
+
+
+def test_golden_vectors_through_the_c_abi():
+    g = np.load(GOLD)
+    batch = nvb.Batch(g["patterns"], g["poffs"], g["texts"], g["toffs"])
+    for ci, cfg in enumerate(g["configs"]):
+        al_args = [int(x) for x in cfg]
+        for type_ in TYPES:
+            want = g[f"res_{ci}_{type_}"]
+            al = nvb.aligner(al_args[0], type_, *al_args[1:])
+            s, si, sj, _ = run(al, batch, want_sinks=True)
+            assert np.array_equal(s, want[:, 0]) and np.array_equal(si, want[:, 1]) and np.array_equal(sj, want[:, 2]), (ci, type_)
+            s2, _, _, _ = run(al, batch)                       # score-only fast path where eligible
+            assert np.array_equal(s2, want[:, 0]), (ci, type_, "fast")
+
+
+@pytest.mark.parametrize("type_", TYPES)
+@pytest.mark.parametrize("scheme", [GOTOH_SW, (1, -4, -7, -1), (3, -2, -5, -5)])
+def test_fast_path_scores_ragged_lengths(orc, type_, scheme):
+    pats, poffs, texts, toffs = synth.nvb_jobs(3001, 1, 210, 1, 330, seed=21)       # odd count: the last thread holds one job
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    want, wi, wj = orc.batch(po.NVB_GOTOH, type_, scheme, pats, poffs, texts, toffs)
+    s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch)
+    assert k == "s16x2"
+    assert np.array_equal(s, want)
+    s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True)
+    assert k == "int32"
+    assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
+    s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, policy=1)
+    assert k == "int32" and np.array_equal(s, want)
+
+
+@pytest.mark.parametrize("type_", TYPES)
+def test_smith_waterman_and_edit_distance(orc, type_):
+    pats, poffs, texts, toffs = synth.nvb_jobs(1500, 5, 120, 5, 260, seed=22)
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    for algo, scheme, fast in ((nvb.SMITH_WATERMAN, (2, -1, -2, -2), True), (nvb.SMITH_WATERMAN, (1, -2, -3, -1), False), (nvb.EDIT_DISTANCE, (0, 0, 0, 0), True)):
+        want, wi, wj = orc.batch(algo, type_, scheme, pats, poffs, texts, toffs)
+        s, _, _, k = run(nvb.aligner(algo, type_, *scheme), batch)
+        assert k == ("s16x2" if fast else "int32"), (algo, scheme)      # asymmetric insertion / deletion costs: general kernel
+        assert np.array_equal(s, want), (algo, scheme)
+        s, si, sj, _ = run(nvb.aligner(algo, type_, *scheme), batch, want_sinks=True)
+        assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj), (algo, scheme)
+
+
+@pytest.mark.parametrize("type_", TYPES)
+def test_symbols_outside_acgt_go_to_the_general_kernel(orc, type_):
+    pats, poffs, texts, toffs = synth.nvb_jobs(2000, 10, 100, 50, 200, seed=23)
+    rng = np.random.default_rng(5)
+    pats = pats.copy(); texts = texts.copy()
+    pats[rng.integers(0, pats.size, 300)] = 4                  # N of nvbio's DNA_N alphabet
+    texts[rng.integers(0, texts.size, 300)] = rng.integers(4, 9, 300)
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    want, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, texts, toffs)
+    s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), batch)
+    assert k == "s16x2" and np.array_equal(s, want)
+    # ASCII strings: upper-case ACGT is the fast alphabet, anything else (N, lower case) is compared as raw bytes
+    lut = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)
+    pa, ta = lut[pats], lut[texts]
+    want_a, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pa, poffs, ta, toffs)
+    s, _, _, _ = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), nvb.Batch(pa, poffs, ta, toffs, alphabet=nvb.ASCII))
+    assert np.array_equal(s, want_a)
+
+
+def test_all_against_one_text_and_indexed_pairs(orc):
+    pats, poffs, texts, toffs = synth.nvb_jobs(777, 30, 150, 2500, 2500, seed=24, shared_text=True)     # sw-benchmark's shape
+    al = nvb.aligner(nvb.GOTOH, nvb.SEMI_GLOBAL, *GOTOH_SW)
+    want, wi, wj = orc.batch(po.NVB_GOTOH, po.NVB_SEMI_GLOBAL, GOTOH_SW, pats, poffs, texts, toffs)
+    s, _, _, k = run(al, nvb.Batch(pats, poffs, texts, toffs))
+    assert k == "s16x2" and np.array_equal(s, want)
+    s, si, sj, _ = run(al, nvb.Batch(pats, poffs, texts, toffs), want_sinks=True)
+    assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
+    rng = np.random.default_rng(9)
+    pp = rng.integers(0, 777, 500).astype(np.uint32); pt = np.zeros(500, np.uint32)
+    s2, _, _, _ = run(al, nvb.Batch(pats, poffs, texts, toffs, pair_pattern=pp, pair_text=pt))
+    assert np.array_equal(s2, want[pp])
+
+
+def test_range_proof_falls_back_to_int32_for_long_global_jobs(orc):
+    pats, poffs, texts, toffs = synth.nvb_jobs(64, 5000, 6000, 6000, 7000, seed=25, sub=0.1, indel=0.01)
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    al = nvb.aligner(nvb.GOTOH, nvb.GLOBAL, 1, -4, -7, -3)          # 3 * 13000 > 31000: outside 16 bits
+    want, _, _ = orc.batch(po.NVB_GOTOH, po.NVB_GLOBAL, (1, -4, -7, -3), pats, poffs, texts, toffs)
+    s, _, _, k = run(al, batch)
+    assert k == "int32" and np.array_equal(s, want)
+    al = nvb.aligner(nvb.GOTOH, nvb.LOCAL, 2, -1, -2, -1)           # local scores stay below 2 * 6000: fast path
+    want, _, _ = orc.batch(po.NVB_GOTOH, po.NVB_LOCAL, (2, -1, -2, -1), pats, poffs, texts, toffs)
+    s, _, _, k = run(al, batch)
+    assert k == "s16x2" and np.array_equal(s, want)
+
+
+def test_sw_benchmark_shape_20k_reads(orc):
+    pats, poffs, texts, toffs = synth.nvb_jobs(20000, 150, 150, 600, 600, seed=26, sub=0.02, indel=0.003)
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    with nvb.Stream(batch) as st:
+        assert st.cells() == int(np.sum(np.diff(poffs).astype(np.int64) * np.diff(toffs).astype(np.int64)))
+        for type_ in TYPES:
+            st.enact(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW))
+            s, _, _ = st.results()
+            want, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, texts, toffs)
+            assert np.array_equal(s, want), type_
+            assert st.last_ms() > 0
+        st.enact(nvb.aligner(nvb.EDIT_DISTANCE, nvb.SEMI_GLOBAL))
+        s, _, _ = st.results()
+        want, _, _ = orc.batch(po.NVB_ED, po.NVB_SEMI_GLOBAL, (), pats, poffs, texts, toffs)
+        assert np.array_equal(s, want)
+
+
+def test_one_call_host_form_and_errors(orc):
+    pats, poffs, texts, toffs = synth.nvb_jobs(300, 10, 80, 40, 160, seed=27)
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    s, si, sj, ms = nvb.batched_score(nvb.aligner(nvb.GOTOH, nvb.LOCAL, *GOTOH_SW), batch, want_sinks=True)
+    want, wi, wj = orc.batch(po.NVB_GOTOH, po.NVB_LOCAL, GOTOH_SW, pats, poffs, texts, toffs)
+    assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj) and min(ms) >= 0
+    bad = poffs.copy(); bad[5] = bad[4]                               # an empty pattern
+    with pytest.raises(RuntimeError):
+        nvb.Stream(nvb.Batch(pats, bad, texts, toffs))
+    with nvb.Stream(batch) as st:
+        with pytest.raises(RuntimeError):
+            st.results()                                              # nothing enacted yet
+        st.enact(nvb.aligner(nvb.GOTOH, nvb.LOCAL, *GOTOH_SW))
+        with pytest.raises(RuntimeError):
+            st.results(want_sinks=True)                               # sinks were not computed
+        with pytest.raises(RuntimeError):
+            st.enact(nvb.aligner(7, nvb.LOCAL))
