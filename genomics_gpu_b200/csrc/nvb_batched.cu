@@ -181,13 +181,28 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
 
 // ------------------------------------------------------------------------------------------------------------------
 // fast path: one thread = two jobs (lane L = job 2k, lane H = job 2k+1), s16x2, bands of 16 pattern columns, score only.
-// All values live in the frame Hg = H + Go (symmetric gap costs only), so E' = max(E + Ge, Hg_left), F' = max(F + Ge,
-// Hg_top) and D = Hg_diag + (s - Go) are one instruction each; the substitution tables hold s - Go.
-__device__ __forceinline__ uint32_t select16(const uint32_t (&v)[17], int k) {
-  uint32_t x = v[16];
-#pragma unroll
-  for (int j = 1; j < 16; j++) x = (k == j) ? v[j] : x;
-  return x;
+//
+// Frame and recurrence (symmetric gap costs with Go <= Ge <= 0, proven on the host): H is kept as it is, F and E are kept as
+// Fg = F - Go and Eg = E - Go.  Because Go <= Ge, E(i,j+1) = max(E(i,j) + Ge, H(i,j) + Go) = max(E(i,j) + Ge, X(i,j) + Go) with
+// X = max(F, D), which takes H off the in-row dependency chain (the chain is ONE VIADDMNMX per cell; all X of a row are
+// independent).  Per cell pair:
+//     Fg = VIADDMNMX(Fg, Ge, H_top)                 ALU     = max(F + Ge, H_top + Go) - Go
+//     s  = PRMT(tabA[j], tabB[j], row selector)     ALU     substitution scores of both jobs
+//     D  = VIADD.16x2(H_diag, s)                    FMA pipe
+//     X  = VIADDMNMX(Fg, Go, D)                     ALU     written in place over H[j] (right-to-left pass: no rotating copy)
+//     Eg'= VIADDMNMX(Eg, Ge, X_left)                ALU     (left-to-right pass)
+//     H  = VIADDMNMX[.RELU](Eg, Go, X)              ALU     = max(E, F, D [, 0])
+// GLOBAL / SEMI_GLOBAL read H(i, M): each job's pattern is RIGHT-aligned in its bands (d = -M mod 16 virtual columns in front),
+// so column M is always register H[16] of the job's last band -- no register select chain.  The virtual columns reproduce
+// column 0 by construction: substitution 0 (SEMI_GLOBAL: H stays 0) or -128 (GLOBAL: H = Go + Ge (i-1) through F).
+#ifndef NVB_PREFETCH_ROWS
+#define NVB_PREFETCH_ROWS 8
+#endif
+constexpr int kPrefetchRows = NVB_PREFETCH_ROWS;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+__device__ __forceinline__ uint32_t band_codes(const uint32_t* __restrict__ pk, int b, int d, int nw) {
+  const uint32_t hi = (b < nw) ? pk[b] : 0u, lo = (b >= 1 && b - 1 < nw) ? pk[b - 1] : 0u;
+  return d ? __funnelshift_r(lo, hi, 32 - 2 * d) : hi;
 }
 
 template <int TYPE>
@@ -208,77 +223,100 @@ __global__ void __launch_bounds__(kThreads) k_nvb_s16(const NvbArgs a) {
   const uint32_t* __restrict__ tA = a.tpk + (a.toffs[A.ti] >> 4) + A.ti;
   const uint32_t* __restrict__ tB = a.tpk + (a.toffs[B.ti] >> 4) + B.ti;
   const int MA = (int)A.M, MB = (int)B.M, NA = (int)A.N, NB = (int)B.N;
-  const int Mx = max(MA, MB), Nx = max(NA, NB);
+  const int Nx = max(NA, NB);
+  const int dA = (TYPE == NVBX_LOCAL) ? 0 : (16 - (MA & 15)) & 15, dB = (TYPE == NVBX_LOCAL) ? 0 : (16 - (MB & 15)) & 15;
+  const int nbA = (MA + dA + 15) >> 4, nbB = (MB + dB + 15) >> 4, nb = max(nbA, nbB);
+  const int nwA = (MA + 15) >> 4, nwB = (MB + 15) >> 4;
   uint2* __restrict__ col = a.scratch + idx;
   const uint32_t stride = a.stride;
   const int go = a.go_t, ge = a.ge_t;
   const uint32_t go2 = splat16(go), ge2 = splat16(ge);
-  const uint32_t mis1 = (uint32_t)(a.mismatch - go) & 0xFFu, mis4 = mis1 * 0x01010101u;
-  const uint32_t delta = ((uint32_t)(a.match - go) ^ (uint32_t)(a.mismatch - go)) & 0xFFu;
+  const uint32_t mis4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
+  const uint32_t front4 = (TYPE == NVBX_GLOBAL) ? 0x80808080u : 0u;                        // virtual columns in front of the pattern
 
-  int bestA = (TYPE == NVBX_LOCAL) ? 0 : INT_MIN, bestB = bestA;       // LOCAL: H frame; otherwise Hg frame (minus Go at the end)
-  uint32_t best2 = 0;
-  for (int block = 0; block < Mx; block += 16) {
-    const uint32_t wA = (block < MA) ? pA[block >> 4] : 0u, wB = (block < MB) ? pB[block >> 4] : 0u;
+  int bestA = INT_MIN, bestB = INT_MIN;
+  uint32_t best2 = (TYPE == NVBX_LOCAL) ? 0u : 0x80008000u;
+  for (int b = 0; b < nb; b++) {
+    const uint32_t wA = band_codes(pA, b, dA, nwA), wB = band_codes(pB, b, dB, nwB);
     uint32_t tabA[16], tabB[16];
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      tabA[j] = (block + j < MA) ? (mis4 ^ (delta << (8 * ((wA >> (2 * j)) & 3u)))) : mis4;   // pad columns: mismatch against every base
-      tabB[j] = (block + j < MB) ? (mis4 ^ (delta << (8 * ((wB >> (2 * j)) & 3u)))) : mis4;
+      const int c = 16 * b + j;
+      tabA[j] = (c < dA) ? front4 : (c < MA + dA) ? (mis4 ^ (delta << (8 * ((wA >> (2 * j)) & 3u)))) : mis4;
+      tabB[j] = (c < dB) ? front4 : (c < MB + dB) ? (mis4 ^ (delta << (8 * ((wB >> (2 * j)) & 3u)))) : mis4;
     }
-    uint32_t Hg[17], F[17];
+    uint32_t H[17], F[17];                                                               // F holds Fg = F - Go
 #pragma unroll
     for (int j = 0; j <= 16; j++) {
-      const int c = block + j;
-      Hg[j] = splat16(((TYPE == NVBX_LOCAL || c == 0) ? 0 : go + ge * (c - 1)) + go);
+      const int ja = 16 * b + j - dA, jb = 16 * b + j - dB;                                // real 1-based column (<= 0: column 0)
+      const int va = (TYPE == NVBX_LOCAL || ja <= 0) ? 0 : go + ge * (ja - 1), vb = (TYPE == NVBX_LOCAL || jb <= 0) ? 0 : go + ge * (jb - 1);
+      H[j] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
       F[j] = splat16(kNeg16);
     }
-    const bool first = block == 0, last = block + 16 >= Mx;
-    const bool inA = block < MA && MA <= block + 16, inB = block < MB && MB <= block + 16;
-    const int mjA = MA - block, mjB = MB - block;
+    const bool first = b == 0, last = b == nb - 1;
+    const bool capA = b == nbA - 1, capB = b == nbB - 1;
+    // band border of the previous band: read one row ahead into registers, kPrefetchRows rows ahead into L1 (the scratch of the
+    // resident threads is larger than L2: without the prefetch the kernel waits on these loads -- ncu long-scoreboard stalls)
+    const uint2* rd = col + stride;                                                        // next row to load
+    const uint2* pfp = col + (size_t)kPrefetchRows * stride;
+    uint2* wr = col;
     uint2 nxt = first ? make_uint2(0, 0) : col[0];
+    if (!first) {
+#pragma unroll
+      for (int r = 1; r < kPrefetchRows; r++) if (r < Nx) prefetch_l1(col + (size_t)r * stride);
+    }
     uint32_t twA = 0, twB = 0;
     for (int i = 1; i <= Nx; i++) {
       if (((i - 1) & 15) == 0) { twA = (i <= NA) ? tA[(i - 1) >> 4] : 0u; twB = (i <= NB) ? tB[(i - 1) >> 4] : 0u; }
       const uint32_t sel = (twA & 3u) * 0x0011u + (twB & 3u) * 0x1100u + 0xC480u;            // bytes: [tA], sign, [4 + tB], sign
       twA >>= 2; twB >>= 2;
-      uint32_t hl, e;
+      uint32_t hl, e;                                                                      // e holds Eg = E - Go
       if (first) {
-        hl = splat16(((TYPE == NVBX_GLOBAL) ? go + ge * (i - 1) : 0) + go);
-        e = (TYPE == NVBX_LOCAL) ? 0u : splat16(kNeg16);
-      } else { hl = nxt.x; e = nxt.y; if (i < Nx) nxt = col[(size_t)i * stride]; }
-      uint32_t diag = Hg[0];
-      Hg[0] = hl;
-      uint32_t m = 0, hodd = 0;
+        hl = splat16((TYPE == NVBX_GLOBAL) ? go + ge * (i - 1) : 0);
+        e = (TYPE == NVBX_LOCAL) ? splat16(-go) : splat16(kNeg16);
+      } else {
+        hl = nxt.x; e = nxt.y;
+        if (i < Nx) nxt = *rd;
+        if (i + kPrefetchRows <= Nx) prefetch_l1(pfp);
+        rd += stride; pfp += stride;
+      }
+      // right-to-left: F, diagonal, X (in place: H[j-1] still holds the previous row when H[j] is overwritten)
+#pragma unroll
+      for (int j = 16; j >= 1; j--) {
+        F[j] = __viaddmax_s16x2(F[j], ge2, H[j]);
+        const uint32_t d = __vadd2(H[j - 1], prmt(tabA[j - 1], tabB[j - 1], sel));
+        H[j] = __viaddmax_s16x2(F[j], go2, d);
+      }
+      H[0] = hl;
+      // left-to-right: the E chain (one instruction per cell) and the final H
+      uint32_t eprev = e;
 #pragma unroll
       for (int j = 1; j <= 16; j++) {
-        F[j] = __viaddmax_s16x2(F[j], ge2, Hg[j]);
-        e = __viaddmax_s16x2(e, ge2, Hg[j - 1]);
-        const uint32_t s2 = prmt(tabA[j - 1], tabB[j - 1], sel);
-        const uint32_t d = __vadd2(diag, s2);
-        const uint32_t h = (TYPE == NVBX_LOCAL) ? __vimax3_s16x2_relu(e, F[j], d) : __vimax3_s16x2(e, F[j], d);
-        if (TYPE == NVBX_LOCAL) { if (j & 1) hodd = h; else m = __vimax3_s16x2(m, hodd, h); }   // one max per two cells
-        diag = Hg[j];
-        Hg[j] = __vadd2(h, go2);
+        e = __viaddmax_s16x2(e, ge2, H[j - 1]);                                              // Eg(i,j): H[j-1] is X(i,j-1) or the full H (same result)
+        if (j > 1) H[j - 1] = (TYPE == NVBX_LOCAL) ? __viaddmax_s16x2_relu(eprev, go2, H[j - 1]) : __viaddmax_s16x2(eprev, go2, H[j - 1]);
+        eprev = e;
       }
-      if (!last) col[(size_t)(i - 1) * stride] = make_uint2(Hg[16], e);
+      H[16] = (TYPE == NVBX_LOCAL) ? __viaddmax_s16x2_relu(e, go2, H[16]) : __viaddmax_s16x2(e, go2, H[16]);
+      if (!last) { *wr = make_uint2(H[16], e); wr += stride; }
       if (TYPE == NVBX_LOCAL) {
+        uint32_t m = best2;
+#pragma unroll
+        for (int j = 1; j <= 16; j += 2) m = __vimax3_s16x2(m, H[j], H[j + 1]);
         const uint32_t mask = (i <= NA ? 0x0000FFFFu : 0u) | (i <= NB ? 0xFFFF0000u : 0u);   // rows past a job's text end do not count
-        best2 = __vmaxs2(best2, m & mask);
+        best2 = (m & mask) | (best2 & ~mask);
+      } else if (TYPE == NVBX_SEMI_GLOBAL) {
+        if (capA | capB) {
+          const uint32_t mask = ((capA && i <= NA) ? 0x0000FFFFu : 0u) | ((capB && i <= NB) ? 0xFFFF0000u : 0u);
+          best2 = __vmaxs2(best2, (H[16] & mask) | (0x80008000u & ~mask));
+        }
       } else {
-        if (inA && i <= NA) {
-          const int h = lo16(select16(Hg, mjA));
-          if (TYPE == NVBX_SEMI_GLOBAL) bestA = max(bestA, h); else if (i == NA) bestA = h;
-        }
-        if (inB && i <= NB) {
-          const int h = hi16(select16(Hg, mjB));
-          if (TYPE == NVBX_SEMI_GLOBAL) bestB = max(bestB, h); else if (i == NB) bestB = h;
-        }
+        if (capA && i == NA) bestA = lo16(H[16]);
+        if (capB && i == NB) bestB = hi16(H[16]);
       }
     }
   }
-  if (TYPE == NVBX_LOCAL) { bestA = lo16(best2); bestB = hi16(best2); }
-  else { bestA -= go; bestB -= go; }
+  if (TYPE != NVBX_GLOBAL) { bestA = lo16(best2); bestB = hi16(best2); }
   a.score[jobA] = bestA;
   if (jobB != jobA) a.score[jobB] = bestB;
 }
@@ -386,15 +424,16 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
   }
   a.score = s->score; a.sink_i = s->sink_i; a.sink_j = s->sink_j; a.worklist = s->worklist; a.work_count = s->work_count;
 
-  // host-side range proof for the s16x2 path: every H + Go, E, F and diagonal sum of any job of the batch (pads included) stays
-  // inside [-31000, 32000]; scores fit the byte tables; symmetric non-positive gap costs
+  // host-side range proof for the s16x2 path: every H + Go, E, F, X and diagonal sum of any job of the batch (pad rows / columns
+  // included) stays inside [-31000, 32000]; substitution scores fit the byte tables (and stay above the -128 of GLOBAL's
+  // virtual columns); symmetric gap costs with Go <= Ge <= 0 (the identity that takes H off the E chain)
   const long long mn = std::min(s->max_m, s->max_n), sum = (long long)s->max_m + s->max_n;
   const long long pos = std::max(0, std::max(a.match, a.mismatch));
   const long long hi = pos * mn + 2LL * std::abs(a.go_t) + 16;
-  const long long lo = (al->type == NVBX_LOCAL) ? 2LL * a.go_t + std::min(a.mismatch, 0) + a.ge_t
-                                                : 3LL * a.go_t + (long long)a.ge_t * (sum + 2) + std::min(a.mismatch, 0) + std::min(a.match, 0);
-  const bool fits = hi <= 32000 && lo >= -31000 && a.go_t == a.go_p && a.ge_t == a.ge_p && a.go_t <= 0 && a.ge_t <= 0 && a.ge_t >= -700 &&
-                    a.mismatch <= 0 && a.match - a.go_t <= 127 && a.match - a.go_t >= -128 && a.mismatch - a.go_t <= 127 && a.mismatch - a.go_t >= -128;
+  const long long lo = (al->type == NVBX_LOCAL) ? 3LL * a.go_t + std::min(a.mismatch, 0) + a.ge_t
+                                                : 4LL * a.go_t + (long long)a.ge_t * (sum + 34) + std::min(a.mismatch, 0) + std::min(a.match, 0) - 128;
+  const bool fits = hi <= 32000 && lo >= -31000 && a.go_t == a.go_p && a.ge_t == a.ge_p && a.go_t <= a.ge_t && a.ge_t <= 0 && a.ge_t > -128 &&
+                    a.go_t > -128 && a.mismatch <= 0 && a.match <= 127 && a.match > -128 && a.mismatch > -128;
   const bool fast = fits && !want_sinks && g_policy == 0;
 
   // chunk the jobs so that the band-border scratch (8 B per text row per thread) stays below ~2 GB
