@@ -195,9 +195,15 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
 // GLOBAL / SEMI_GLOBAL read H(i, M): each job's pattern is RIGHT-aligned in its bands (d = -M mod 16 virtual columns in front),
 // so column M is always register H[16] of the job's last band -- no register select chain.  The virtual columns reproduce
 // column 0 by construction: substitution 0 (SEMI_GLOBAL: H stays 0) or -128 (GLOBAL: H = Go + Ge (i-1) through F).
-#ifndef NVB_PREFETCH_ROWS
-#define NVB_PREFETCH_ROWS 8
+#ifndef NVB_ROW_UNROLL
+#define NVB_ROW_UNROLL 4
 #endif
+#define NVB_PRAGMA(x) _Pragma(#x)
+#define NVB_UNROLL(n) NVB_PRAGMA(unroll n)      // nvcc wants a literal unroll factor
+#ifndef NVB_PREFETCH_ROWS
+#define NVB_PREFETCH_ROWS 7
+#endif
+constexpr uint32_t kFixedStride = 1u << 17;   // threads (job pairs) per fast-path launch; 7 rows x 1 MB stays inside the 24-bit load offset
 constexpr int kPrefetchRows = NVB_PREFETCH_ROWS;
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t band_codes(const uint32_t* __restrict__ pk, int b, int d, int nw) {
@@ -205,8 +211,10 @@ __device__ __forceinline__ uint32_t band_codes(const uint32_t* __restrict__ pk, 
   return d ? __funnelshift_r(lo, hi, 32 - 2 * d) : hi;
 }
 
-template <int TYPE>
-__global__ void __launch_bounds__(kThreads) k_nvb_s16(const NvbArgs a) {
+// FIXED: the scratch row stride is the compile-time kFixedStride, so the next-row load, the prefetch and the store share ONE
+// pointer with immediate offsets (the run-time-stride variant serves batches whose texts are too long for that layout).
+template <int TYPE, bool FIXED>
+__global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
   const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
   if (idx >= (a.count + 1) / 2) return;
   const uint32_t jobA = a.first + 2 * idx, jobB = min(jobA + 1, a.first + a.count - 1);
@@ -228,7 +236,7 @@ __global__ void __launch_bounds__(kThreads) k_nvb_s16(const NvbArgs a) {
   const int nbA = (MA + dA + 15) >> 4, nbB = (MB + dB + 15) >> 4, nb = max(nbA, nbB);
   const int nwA = (MA + 15) >> 4, nwB = (MB + 15) >> 4;
   uint2* __restrict__ col = a.scratch + idx;
-  const uint32_t stride = a.stride;
+  const size_t stride = FIXED ? (size_t)kFixedStride : (size_t)a.stride;
   const int go = a.go_t, ge = a.ge_t;
   const uint32_t go2 = splat16(go), ge2 = splat16(ge);
   const uint32_t mis4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
@@ -258,15 +266,14 @@ __global__ void __launch_bounds__(kThreads) k_nvb_s16(const NvbArgs a) {
     const bool capA = b == nbA - 1, capB = b == nbB - 1;
     // band border of the previous band: read one row ahead into registers, kPrefetchRows rows ahead into L1 (the scratch of the
     // resident threads is larger than L2: without the prefetch the kernel waits on these loads -- ncu long-scoreboard stalls)
-    const uint2* rd = col + stride;                                                        // next row to load
-    const uint2* pfp = col + (size_t)kPrefetchRows * stride;
-    uint2* wr = col;
+    uint2* rp = col;                                                                       // row i of the band border; row i+1 is loaded, row i+kPrefetchRows prefetched
     uint2 nxt = first ? make_uint2(0, 0) : col[0];
     if (!first) {
 #pragma unroll
       for (int r = 1; r < kPrefetchRows; r++) if (r < Nx) prefetch_l1(col + (size_t)r * stride);
     }
     uint32_t twA = 0, twB = 0;
+NVB_UNROLL(NVB_ROW_UNROLL)
     for (int i = 1; i <= Nx; i++) {
       if (((i - 1) & 15) == 0) { twA = (i <= NA) ? tA[(i - 1) >> 4] : 0u; twB = (i <= NB) ? tB[(i - 1) >> 4] : 0u; }
       const uint32_t sel = (twA & 3u) * 0x0011u + (twB & 3u) * 0x1100u + 0xC480u;            // bytes: [tA], sign, [4 + tB], sign
@@ -277,9 +284,8 @@ __global__ void __launch_bounds__(kThreads) k_nvb_s16(const NvbArgs a) {
         e = (TYPE == NVBX_LOCAL) ? splat16(-go) : splat16(kNeg16);
       } else {
         hl = nxt.x; e = nxt.y;
-        if (i < Nx) nxt = *rd;
-        if (i + kPrefetchRows <= Nx) prefetch_l1(pfp);
-        rd += stride; pfp += stride;
+        if (i < Nx) nxt = rp[stride];
+        if (i + kPrefetchRows <= Nx) prefetch_l1(rp + (size_t)kPrefetchRows * stride);
       }
       // right-to-left: F, diagonal, X (in place: H[j-1] still holds the previous row when H[j] is overwritten)
 #pragma unroll
@@ -298,7 +304,8 @@ __global__ void __launch_bounds__(kThreads) k_nvb_s16(const NvbArgs a) {
         eprev = e;
       }
       H[16] = (TYPE == NVBX_LOCAL) ? __viaddmax_s16x2_relu(e, go2, H[16]) : __viaddmax_s16x2(e, go2, H[16]);
-      if (!last) { *wr = make_uint2(H[16], e); wr += stride; }
+      if (!last) *rp = make_uint2(H[16], e);
+      rp += stride;
       if (TYPE == NVBX_LOCAL) {
         uint32_t m = best2;
 #pragma unroll
@@ -436,19 +443,22 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
                     a.go_t > -128 && a.mismatch <= 0 && a.match <= 127 && a.match > -128 && a.mismatch > -128;
   const bool fast = fits && !want_sinks && g_policy == 0;
 
-  // chunk the jobs so that the band-border scratch (8 B per text row per thread) stays below ~2 GB
+  // chunk the jobs so that the band-border scratch (8 B per text row per thread) stays below ~2 GB.  The fast path prefers the
+  // fixed row stride (2 x kFixedStride jobs per launch) when the texts are short enough for it.
   const size_t cap_elems = (size_t)1 << 28;
+  const bool fixed = fast && (size_t)s->max_n * kFixedStride <= cap_elems;
   size_t chunk = cap_elems / std::max<size_t>(1, s->max_n);
   chunk = std::max<size_t>(256, chunk & ~(size_t)255);
   chunk = std::min<size_t>(chunk, ((size_t)s->n_pairs + 255) & ~(size_t)255);
-  const size_t need = chunk * s->max_n;
+  if (fixed) chunk = 2 * (size_t)kFixedStride;
+  const size_t need = (fixed ? (size_t)kFixedStride : chunk) * s->max_n;
   if (need > s->scratch_elems) {
     if (s->scratch) cudaFree(s->scratch);
     s->scratch = nullptr; s->scratch_elems = 0;
     if (cudaMalloc(&s->scratch, need * sizeof(uint2)) != cudaSuccess) { cudaGetLastError(); return fail("nvbx_stream_enact: cannot allocate the band-border scratch (text too long for this batch)"); }
     s->scratch_elems = need;
   }
-  a.scratch = s->scratch; a.stride = (uint32_t)chunk;
+  a.scratch = s->scratch; a.stride = (uint32_t)(fixed ? (size_t)kFixedStride : chunk);
 
   NVB_CHECK(cudaEventRecord(s->e0, s->st));
   bool used_i32 = !fast;
@@ -458,9 +468,13 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
     if (fast) {
       NVB_CHECK(cudaMemsetAsync(s->work_count, 0, 4, s->st));
       const uint32_t items = (a.count + 1) / 2, g = (items + kThreads - 1) / kThreads, g2 = (a.count + kThreads - 1) / kThreads;
-      if (type == NVBX_GLOBAL) { k_nvb_s16<NVBX_GLOBAL><<<g, kThreads, 0, s->st>>>(a); k_nvb_i32<NVBX_GLOBAL, false><<<g2, kThreads, 0, s->st>>>(a, 1); }
-      else if (type == NVBX_LOCAL) { k_nvb_s16<NVBX_LOCAL><<<g, kThreads, 0, s->st>>>(a); k_nvb_i32<NVBX_LOCAL, false><<<g2, kThreads, 0, s->st>>>(a, 1); }
-      else { k_nvb_s16<NVBX_SEMI_GLOBAL><<<g, kThreads, 0, s->st>>>(a); k_nvb_i32<NVBX_SEMI_GLOBAL, false><<<g2, kThreads, 0, s->st>>>(a, 1); }
+#define NVB_LAUNCH_FAST(T) do { \
+        if (fixed) k_nvb_s16<T, true><<<g, kThreads, 0, s->st>>>(a); else k_nvb_s16<T, false><<<g, kThreads, 0, s->st>>>(a); \
+        k_nvb_i32<T, false><<<g2, kThreads, 0, s->st>>>(a, 1); } while (0)
+      if (type == NVBX_GLOBAL) NVB_LAUNCH_FAST(NVBX_GLOBAL);
+      else if (type == NVBX_LOCAL) NVB_LAUNCH_FAST(NVBX_LOCAL);
+      else NVB_LAUNCH_FAST(NVBX_SEMI_GLOBAL);
+#undef NVB_LAUNCH_FAST
       g_launches += 2;
     } else {
       const uint32_t g = (a.count + kThreads - 1) / kThreads;
