@@ -278,6 +278,23 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def nvb_extra(n: int):
+    """The suite's second alignment benchmark shape (NvB/sw-benchmark/sw-benchmark.cu:560-640: Gotoh 2/-1/-2/-1 global / semi-global /
+    local + edit-distance semi-global, scores only) through include/nvbio_b200.h; device-timed, best of 3."""
+    from genomics_gpu_b200 import nvb, synth
+    pats, poffs, texts, toffs = synth.nvb_jobs(n, 150, 150, 600, 600, seed=31, sub=0.02, indel=0.0)
+    out = {}
+    with nvb.Stream(nvb.Batch(pats, poffs, texts, toffs)) as st:
+        cells = st.cells()
+        for name, al in (("gotoh_global", nvb.aligner(nvb.GOTOH, nvb.GLOBAL, 2, -1, -2, -1)), ("gotoh_semi_global", nvb.aligner(nvb.GOTOH, nvb.SEMI_GLOBAL, 2, -1, -2, -1)),
+                         ("gotoh_local", nvb.aligner(nvb.GOTOH, nvb.LOCAL, 2, -1, -2, -1)), ("ed_semi_global", nvb.aligner(nvb.EDIT_DISTANCE, nvb.SEMI_GLOBAL))):
+            best = 1e30
+            for _ in range(3):
+                st.enact(al); best = min(best, st.last_ms())
+            out[name] = {"kernel": st.kernel(), "dp_ms": best, "gcups_dp": cells / best / 1e6}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------
 def run_extras(local_rank: int, n_fwd: int):
     """Device-timed GCUPS of the other BASELINE.json configurations (parity-test cases, reported for context only; bounded
@@ -307,6 +324,7 @@ def run_extras(local_rank: int, n_fwd: int):
         out["C5_mixed_100bp_10kb_local_with_start"] = timed(synth.config5(4000, seed=5), algo=capi.LOCAL, start=capi.WITH_START)
         out["C4_local_250bp_with_cigar_s16x2"] = timed(b4, algo=capi.LOCAL, start=capi.WITH_TB)
         out["NW_linear_full_matrix_N32000"] = nw_extra(32000)
+        out["nvbio_style_batched_scoring_262144x150x600"] = nvb_extra(n_fwd)
         out["note"] = "gcups_dp counts q_len x t_len forward cells per pair (banded and start passes add time, not cells); device-timed DP stage, best of 3"
     except Exception as e:  # context only: never break the bench line
         out["error"] = str(e)[:200]
