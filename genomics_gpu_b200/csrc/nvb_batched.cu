@@ -92,6 +92,17 @@ __device__ __forceinline__ Job load_job(const NvbArgs& a, uint32_t job) {
   return j;
 }
 
+#ifndef NVB_ROW_UNROLL
+#define NVB_ROW_UNROLL 4
+#endif
+#define NVB_PRAGMA(x) _Pragma(#x)
+#define NVB_UNROLL(n) NVB_PRAGMA(unroll n)      // nvcc wants a literal unroll factor
+#ifndef NVB_PREFETCH_ROWS
+#define NVB_PREFETCH_ROWS 7
+#endif
+constexpr uint32_t kFixedStride = 1u << 17;   // threads (job pairs) per fast-path launch; 7 rows x 1 MB stays inside the 24-bit load offset
+constexpr int kPrefetchRows = NVB_PREFETCH_ROWS;
+__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 // ------------------------------------------------------------------------------------------------------------------
 // general path: one thread per job, int32, bands of 8 pattern columns (gotoh_inl.h:473-593 with BAND_LEN = 8)
 template <int N> __device__ __forceinline__ int select_reg(const int (&v)[N], int k) {
@@ -180,6 +191,108 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
 }
 
 // ------------------------------------------------------------------------------------------------------------------
+// int32 path for ordered gap costs (Go <= Ge <= 0 on both sides): one thread per job, bands of 16 pattern columns, the same
+// formulation as the s16x2 kernel below (H as is, F - Go_t, E - Go_p; E chain off H; X written in place right-to-left;
+// GLOBAL / SEMI_GLOBAL patterns right-aligned so H(i, M) is register H[16]).  Adds what the packed kernel cannot do: raw byte
+// comparison (any alphabet), asymmetric Smith-Waterman costs, values beyond 16 bits, and the LOCAL BestSink coordinates: the
+// winner is the maximum by (score, report order key) with key = (band of the reference's BAND_LEN columns, text row,
+// column) -- compared explicitly, so it does not depend on this kernel's own traversal order.
+constexpr int kFrontGlobal = -(1 << 20);        // substitution score of GLOBAL's virtual front columns: the diagonal never wins
+
+template <int TYPE, bool SINK>
+__global__ void __launch_bounds__(kThreads, 4) k_nvb_i32w(const NvbArgs a, int from_worklist) {
+  const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
+  uint32_t job;
+  if (from_worklist) { if (idx >= *a.work_count) return; job = a.worklist[idx]; }
+  else { if (idx >= a.count) return; job = a.first + idx; }
+  const Job jb = load_job(a, job);
+  const uint8_t* __restrict__ P = a.pbytes + a.poffs[jb.pi];
+  const uint8_t* __restrict__ T = a.tbytes + a.toffs[jb.ti];
+  const int M = (int)jb.M, N = (int)jb.N;
+  const int d = (TYPE == NVBX_LOCAL) ? 0 : (16 - (M & 15)) & 15;                           // virtual columns in front of the pattern
+  const int nb = (M + d + 15) >> 4;
+  uint2* __restrict__ col = a.scratch + idx;
+  const size_t stride = a.stride;
+  const int go_t = a.go_t, ge_t = a.ge_t, go_p = a.go_p, ge_p = a.ge_p, match = a.match, mismatch = a.mismatch;
+  const int front = (TYPE == NVBX_GLOBAL) ? kFrontGlobal : 0;
+
+  int best = INT_MIN, bi = -1, bj = -1;
+  for (int b = 0; b < nb; b++) {
+    int q[16], sx[16];                                                                    // symbol (256+: never equal) and non-match score per column
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      const int c = 16 * b + j;
+      const bool real = c >= d && c < M + d;
+      q[j] = real ? (int)P[c - d] : 256 + j;
+      sx[j] = (c < d) ? front : mismatch;
+    }
+    int H[17], F[17];                                                                     // F holds F - Go_t
+#pragma unroll
+    for (int j = 0; j <= 16; j++) {
+      const int jr = 16 * b + j - d;                                                       // real 1-based column (<= 0: column 0)
+      H[j] = (TYPE == NVBX_LOCAL || jr <= 0) ? 0 : go_p + ge_p * (jr - 1);
+      F[j] = kNeg32;
+    }
+    const bool first = b == 0, last = b == nb - 1;
+    uint2* rp = col;
+    uint2 nxt = first ? make_uint2(0, 0) : col[0];
+    if (!first) {
+#pragma unroll
+      for (int r = 1; r < kPrefetchRows; r++) if (r < N) prefetch_l1(col + (size_t)r * stride);
+    }
+NVB_UNROLL(2)
+    for (int i = 1; i <= N; i++) {
+      int hl, e;                                                                           // e holds E - Go_p
+      if (first) {
+        hl = (TYPE == NVBX_GLOBAL) ? go_t + ge_t * (i - 1) : 0;
+        e = (TYPE == NVBX_LOCAL) ? -go_p : kNeg32;
+      } else {
+        hl = (int)nxt.x; e = (int)nxt.y;
+        if (i < N) nxt = rp[stride];
+        if (i + kPrefetchRows <= N) prefetch_l1(rp + (size_t)kPrefetchRows * stride);
+      }
+      const int t = (int)T[i - 1];
+#pragma unroll
+      for (int j = 16; j >= 1; j--) {
+        F[j] = __viaddmax_s32(F[j], ge_t, H[j]);
+        const int dd = H[j - 1] + ((t == q[j - 1]) ? match : sx[j - 1]);
+        H[j] = __viaddmax_s32(F[j], go_t, dd);                                               // X = max(F, D)
+      }
+      H[0] = hl;
+      int eprev = e;
+#pragma unroll
+      for (int j = 1; j <= 16; j++) {
+        e = __viaddmax_s32(e, ge_p, H[j - 1]);
+        if (j > 1) H[j - 1] = (TYPE == NVBX_LOCAL) ? __viaddmax_s32_relu(eprev, go_p, H[j - 1]) : __viaddmax_s32(eprev, go_p, H[j - 1]);
+        eprev = e;
+      }
+      H[16] = (TYPE == NVBX_LOCAL) ? __viaddmax_s32_relu(e, go_p, H[16]) : __viaddmax_s32(e, go_p, H[16]);
+      if (!last) *rp = make_uint2((uint32_t)H[16], (uint32_t)e);
+      rp += stride;
+      if (TYPE == NVBX_LOCAL) {
+        const int mj = last ? M - 16 * b : 16;                                               // valid columns of this band (pad columns never win, but keep exactness)
+        int rowmax = H[1];
+#pragma unroll
+        for (int j = 2; j <= 16; j += 2) rowmax = (j < 16) ? __vimax3_s32(rowmax, H[j], H[j + 1]) : max(rowmax, H[j]);
+        if (SINK) {
+          if (rowmax >= best) {
+            int cj = 0;
+#pragma unroll
+            for (int j = 1; j <= 16; j++) if (j <= mj && H[j] == rowmax) cj = j;             // largest column of the row
+            if (cj > 0 && (rowmax > best || reported_later(i, 16 * b + cj, bi, bj, a.band_shift))) { best = rowmax; bi = i; bj = 16 * b + cj; }
+          }
+        } else best = max(best, rowmax);
+      } else if (last) {
+        if (TYPE == NVBX_SEMI_GLOBAL) { if (H[16] >= best) { best = H[16]; bi = i; bj = M; } }
+        else if (i == N) { best = H[16]; bi = N; bj = M; }
+      }
+    }
+  }
+  a.score[job] = best;
+  if (SINK) { a.sink_i[job] = bi; a.sink_j[job] = bj; }
+}
+
+// ------------------------------------------------------------------------------------------------------------------
 // fast path: one thread = two jobs (lane L = job 2k, lane H = job 2k+1), s16x2, bands of 16 pattern columns, score only.
 //
 // Frame and recurrence (symmetric gap costs with Go <= Ge <= 0, proven on the host): H is kept as it is, F and E are kept as
@@ -195,17 +308,6 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
 // GLOBAL / SEMI_GLOBAL read H(i, M): each job's pattern is RIGHT-aligned in its bands (d = -M mod 16 virtual columns in front),
 // so column M is always register H[16] of the job's last band -- no register select chain.  The virtual columns reproduce
 // column 0 by construction: substitution 0 (SEMI_GLOBAL: H stays 0) or -128 (GLOBAL: H = Go + Ge (i-1) through F).
-#ifndef NVB_ROW_UNROLL
-#define NVB_ROW_UNROLL 4
-#endif
-#define NVB_PRAGMA(x) _Pragma(#x)
-#define NVB_UNROLL(n) NVB_PRAGMA(unroll n)      // nvcc wants a literal unroll factor
-#ifndef NVB_PREFETCH_ROWS
-#define NVB_PREFETCH_ROWS 7
-#endif
-constexpr uint32_t kFixedStride = 1u << 17;   // threads (job pairs) per fast-path launch; 7 rows x 1 MB stays inside the 24-bit load offset
-constexpr int kPrefetchRows = NVB_PREFETCH_ROWS;
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 __device__ __forceinline__ uint32_t band_codes(const uint32_t* __restrict__ pk, int b, int d, int nw) {
   const uint32_t hi = (b < nw) ? pk[b] : 0u, lo = (b >= 1 && b - 1 < nw) ? pk[b - 1] : 0u;
   return d ? __funnelshift_r(lo, hi, 32 - 2 * d) : hi;
@@ -213,7 +315,7 @@ __device__ __forceinline__ uint32_t band_codes(const uint32_t* __restrict__ pk, 
 
 // FIXED: the scratch row stride is the compile-time kFixedStride, so the next-row load, the prefetch and the store share ONE
 // pointer with immediate offsets (the run-time-stride variant serves batches whose texts are too long for that layout).
-template <int TYPE, bool FIXED>
+template <int TYPE, bool FIXED, bool SINK = false>
 __global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
   const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
   if (idx >= (a.count + 1) / 2) return;
@@ -243,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
   const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
   const uint32_t front4 = (TYPE == NVBX_GLOBAL) ? 0x80808080u : 0u;                        // virtual columns in front of the pattern
 
-  int bestA = INT_MIN, bestB = INT_MIN;
+  int bestA = INT_MIN, bestB = INT_MIN, rowA = -1, rowB = -1;                              // rowA/rowB: SEMI_GLOBAL sinks (last maximum wins)
   uint32_t best2 = (TYPE == NVBX_LOCAL) ? 0u : 0x80008000u;
   for (int b = 0; b < nb; b++) {
     const uint32_t wA = band_codes(pA, b, dA, nwA), wB = band_codes(pB, b, dB, nwB);
@@ -313,7 +415,10 @@ NVB_UNROLL(NVB_ROW_UNROLL)
         const uint32_t mask = (i <= NA ? 0x0000FFFFu : 0u) | (i <= NB ? 0xFFFF0000u : 0u);   // rows past a job's text end do not count
         best2 = (m & mask) | (best2 & ~mask);
       } else if (TYPE == NVBX_SEMI_GLOBAL) {
-        if (capA | capB) {
+        if (SINK) {                                                                        // BestSink `score <= new` (sink_inl.h:52-60): the last row wins
+          if (capA && i <= NA) { const int h = lo16(H[16]); if (h >= bestA) { bestA = h; rowA = i; } }
+          if (capB && i <= NB) { const int h = hi16(H[16]); if (h >= bestB) { bestB = h; rowB = i; } }
+        } else if (capA | capB) {
           const uint32_t mask = ((capA && i <= NA) ? 0x0000FFFFu : 0u) | ((capB && i <= NB) ? 0xFFFF0000u : 0u);
           best2 = __vmaxs2(best2, (H[16] & mask) | (0x80008000u & ~mask));
         }
@@ -323,9 +428,13 @@ NVB_UNROLL(NVB_ROW_UNROLL)
       }
     }
   }
-  if (TYPE != NVBX_GLOBAL) { bestA = lo16(best2); bestB = hi16(best2); }
+  if (TYPE == NVBX_LOCAL || (TYPE == NVBX_SEMI_GLOBAL && !SINK)) { bestA = lo16(best2); bestB = hi16(best2); }
   a.score[jobA] = bestA;
   if (jobB != jobA) a.score[jobB] = bestB;
+  if (SINK) {                                                                              // GLOBAL: (N, M); SEMI_GLOBAL: (last best row, M)
+    a.sink_i[jobA] = (TYPE == NVBX_GLOBAL) ? NA : rowA; a.sink_j[jobA] = MA;
+    if (jobB != jobA) { a.sink_i[jobB] = (TYPE == NVBX_GLOBAL) ? NB : rowB; a.sink_j[jobB] = MB; }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -441,7 +550,12 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
                                                 : 4LL * a.go_t + (long long)a.ge_t * (sum + 34) + std::min(a.mismatch, 0) + std::min(a.match, 0) - 128;
   const bool fits = hi <= 32000 && lo >= -31000 && a.go_t == a.go_p && a.ge_t == a.ge_p && a.go_t <= a.ge_t && a.ge_t <= 0 && a.ge_t > -128 &&
                     a.go_t > -128 && a.mismatch <= 0 && a.match <= 127 && a.match > -128 && a.mismatch > -128;
-  const bool fast = fits && !want_sinks && g_policy == 0;
+  // the banded-16 int32 kernel needs ordered, non-positive costs and head room for its -2^20 front-column sentinel
+  const bool wide = a.go_t <= a.ge_t && a.ge_t <= 0 && a.go_p <= a.ge_p && a.ge_p <= 0 && a.mismatch <= 0 &&
+                    (sum + 34) * (long long)std::max(std::abs(a.ge_t), std::abs(a.ge_p)) + 4LL * std::max(std::abs(a.go_t), std::abs(a.go_p)) +
+                        (long long)std::max(std::abs(a.match), std::abs(a.mismatch)) * (mn + 1) < (1LL << 28) &&
+                    std::max(std::abs(a.ge_t), std::abs(a.ge_p)) < (1 << 19);
+  const bool fast = fits && (!want_sinks || al->type != NVBX_LOCAL) && g_policy == 0;    // LOCAL sinks need the reference's band order: int32 kernel
 
   // chunk the jobs so that the band-border scratch (8 B per text row per thread) stays below ~2 GB.  The fast path prefers the
   // fixed row stride (2 x kFixedStride jobs per launch) when the texts are short enough for it.
@@ -468,32 +582,30 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
     if (fast) {
       NVB_CHECK(cudaMemsetAsync(s->work_count, 0, 4, s->st));
       const uint32_t items = (a.count + 1) / 2, g = (items + kThreads - 1) / kThreads, g2 = (a.count + kThreads - 1) / kThreads;
-#define NVB_LAUNCH_FAST(T) do { \
-        if (fixed) k_nvb_s16<T, true><<<g, kThreads, 0, s->st>>>(a); else k_nvb_s16<T, false><<<g, kThreads, 0, s->st>>>(a); \
-        k_nvb_i32<T, false><<<g2, kThreads, 0, s->st>>>(a, 1); } while (0)
-      if (type == NVBX_GLOBAL) NVB_LAUNCH_FAST(NVBX_GLOBAL);
-      else if (type == NVBX_LOCAL) NVB_LAUNCH_FAST(NVBX_LOCAL);
-      else NVB_LAUNCH_FAST(NVBX_SEMI_GLOBAL);
+#define NVB_LAUNCH_FAST(T, S) do { \
+        if (fixed) k_nvb_s16<T, true, S><<<g, kThreads, 0, s->st>>>(a); else k_nvb_s16<T, false, S><<<g, kThreads, 0, s->st>>>(a); \
+        k_nvb_i32w<T, S><<<g2, kThreads, 0, s->st>>>(a, 1); } while (0)
+      if (type == NVBX_LOCAL) NVB_LAUNCH_FAST(NVBX_LOCAL, false);
+      else if (type == NVBX_GLOBAL) { if (want_sinks) NVB_LAUNCH_FAST(NVBX_GLOBAL, true); else NVB_LAUNCH_FAST(NVBX_GLOBAL, false); }
+      else { if (want_sinks) NVB_LAUNCH_FAST(NVBX_SEMI_GLOBAL, true); else NVB_LAUNCH_FAST(NVBX_SEMI_GLOBAL, false); }
 #undef NVB_LAUNCH_FAST
       g_launches += 2;
     } else {
       const uint32_t g = (a.count + kThreads - 1) / kThreads;
+#define NVB_LAUNCH_I32(T, S) do { if (wide) k_nvb_i32w<T, S><<<g, kThreads, 0, s->st>>>(a, 0); else k_nvb_i32<T, S><<<g, kThreads, 0, s->st>>>(a, 0); } while (0)
       if (want_sinks) {
-        if (type == NVBX_GLOBAL) k_nvb_i32<NVBX_GLOBAL, true><<<g, kThreads, 0, s->st>>>(a, 0);
-        else if (type == NVBX_LOCAL) k_nvb_i32<NVBX_LOCAL, true><<<g, kThreads, 0, s->st>>>(a, 0);
-        else k_nvb_i32<NVBX_SEMI_GLOBAL, true><<<g, kThreads, 0, s->st>>>(a, 0);
+        if (type == NVBX_GLOBAL) NVB_LAUNCH_I32(NVBX_GLOBAL, true); else if (type == NVBX_LOCAL) NVB_LAUNCH_I32(NVBX_LOCAL, true); else NVB_LAUNCH_I32(NVBX_SEMI_GLOBAL, true);
       } else {
-        if (type == NVBX_GLOBAL) k_nvb_i32<NVBX_GLOBAL, false><<<g, kThreads, 0, s->st>>>(a, 0);
-        else if (type == NVBX_LOCAL) k_nvb_i32<NVBX_LOCAL, false><<<g, kThreads, 0, s->st>>>(a, 0);
-        else k_nvb_i32<NVBX_SEMI_GLOBAL, false><<<g, kThreads, 0, s->st>>>(a, 0);
+        if (type == NVBX_GLOBAL) NVB_LAUNCH_I32(NVBX_GLOBAL, false); else if (type == NVBX_LOCAL) NVB_LAUNCH_I32(NVBX_LOCAL, false); else NVB_LAUNCH_I32(NVBX_SEMI_GLOBAL, false);
       }
+#undef NVB_LAUNCH_I32
       g_launches += 1;
     }
     NVB_CHECK(cudaGetLastError());
   }
   NVB_CHECK(cudaEventRecord(s->e1, s->st));
   s->have_sinks = want_sinks != 0; s->enacted = true;
-  s->kernel = used_i32 ? "int32" : "s16x2";
+  s->kernel = used_i32 ? (wide ? "int32" : "int32-any") : "s16x2";
   return 0;
 }
 

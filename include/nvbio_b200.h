@@ -64,7 +64,8 @@ typedef struct nvbx_stream nvbx_stream_t;    /* opaque: the device-resident batc
 /* Upload a batch (H2D on `cuda_stream`, NULL = default stream) and 2-bit pack it on the device.  NULL on error. */
 nvbx_stream_t* nvbx_stream_create(const nvbx_batch_t* batch, void* cuda_stream);
 /* BatchedAlignmentScore::enact: queue the scoring of every job on the stream's CUDA stream; returns without waiting.
- * want_sinks != 0 also computes the BestSink coordinates (int32 kernel).  0, or -1 on invalid arguments. */
+ * want_sinks != 0 also computes the BestSink coordinates (GLOBAL / SEMI_GLOBAL stay on the fast path, LOCAL uses the int32
+ * kernel).  0, or -1 on invalid arguments. */
 int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* aligner, int want_sinks);
 /* stream.output(i) for all i: wait for the last enact and copy scores (and sinks, if they were computed and the
  * pointers are non-NULL) to host arrays of n_pairs int32. */
@@ -73,7 +74,7 @@ int nvbx_stream_results(nvbx_stream_t* s, int32_t* scores, int32_t* sink_text, i
 const int32_t* nvbx_stream_scores_device(nvbx_stream_t* s);
 float nvbx_stream_last_ms(nvbx_stream_t* s);            /* CUDA-event time of the last enact (synchronises) */
 uint64_t nvbx_stream_cells(const nvbx_stream_t* s);     /* sum over jobs of M * N (sw-benchmark.cu:380 GCUPS numerator) */
-const char* nvbx_stream_kernel(const nvbx_stream_t* s); /* "s16x2", "int32" or "s16x2+int32" for the last enact */
+const char* nvbx_stream_kernel(const nvbx_stream_t* s); /* last enact: "s16x2", "int32" (ordered costs) or "int32-any" */
 void nvbx_stream_destroy(nvbx_stream_t* s);
 
 /* One-call form with host buffers: create, enact, results, destroy.  ms[0..2] (optional) = upload + pack, scoring,

@@ -55,10 +55,10 @@ def test_fast_path_scores_ragged_lengths(orc, type_, scheme):
     assert k == "s16x2"
     assert np.array_equal(s, want)
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True)
-    assert k == "int32"
+    assert k == ("int32" if type_ == nvb.LOCAL else "s16x2")          # LOCAL sinks need the reference's band order: general kernel
     assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
-    s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, policy=1)
-    assert k == "int32" and np.array_equal(s, want)
+    s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True, policy=1)
+    assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
 
 
 @pytest.mark.parametrize("type_", TYPES)
@@ -154,3 +154,24 @@ def test_one_call_host_form_and_errors(orc):
             st.results(want_sinks=True)                               # sinks were not computed
         with pytest.raises(RuntimeError):
             st.enact(nvb.aligner(7, nvb.LOCAL))
+
+
+def test_batches_larger_than_one_launch(orc):
+    """270001 jobs against one shared text: the fast path cuts launches of 2 x 131072 jobs (compile-time scratch stride), the int32 path
+    cuts by scratch size; job ranges, worklists and the odd last job must line up across launches."""
+    n, m = 270001, 12
+    rng = np.random.default_rng(33)
+    text = rng.integers(0, 4, 1000).astype(np.uint8)
+    starts = rng.integers(0, 1000 - m, n)
+    pats = text[(starts[:, None] + np.arange(m)[None, :])].astype(np.uint8)
+    pats[rng.random(pats.shape) < 0.08] = 3
+    pats[::5000, 3] = 4                                                   # a few jobs with N: worklist entries in both launches
+    pats = np.ascontiguousarray(pats.reshape(-1)); poffs = (np.arange(n + 1) * m).astype(np.uint32)
+    toffs = np.array([0, 1000], np.uint32)
+    batch = nvb.Batch(pats, poffs, text, toffs)
+    for type_ in (nvb.SEMI_GLOBAL, nvb.LOCAL):
+        want, wi, wj = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, text, toffs)
+        s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), batch)
+        assert k == "s16x2" and np.array_equal(s, want), type_
+    s, si, sj, k = run(nvb.aligner(nvb.GOTOH, nvb.LOCAL, *GOTOH_SW), batch, want_sinks=True)
+    assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)

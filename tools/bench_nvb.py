@@ -26,10 +26,11 @@ def main():
                  ("gotoh_local", nvb.aligner(nvb.GOTOH, nvb.LOCAL, 2, -1, -2, -1)), ("ed_semi_global", nvb.aligner(nvb.EDIT_DISTANCE, nvb.SEMI_GLOBAL))]
         for policy, tag in ((0, "auto"), (1, "int32")):
             nvb.set_policy(policy)
-            for name, al in cases:
+            for name, al in cases + [(c[0] + "_sinks", c[1]) for c in cases[1:3]]:
+                sinks = name.endswith("_sinks")
                 best = 1e30
                 for _ in range(reps + 1):
-                    st.enact(al); best = min(best, st.last_ms())
+                    st.enact(al, sinks); best = min(best, st.last_ms())
                 sc, _, _ = st.results()
                 out["results"][f"{name}_{tag}"] = {"kernel": st.kernel(), "ms": best, "gcups": cells / best / 1e6, "score_sum": int(sc.astype(np.int64).sum())}
         nvb.set_policy(0)
