@@ -141,3 +141,47 @@ def set_policy(p: int) -> None:
 
 def kernel_launches() -> int:
     return int(_lib().nvbx_kernel_launches())
+
+
+# ---- one process per GPU: jobs are independent, so the path shards with no data-path collective -----------------
+def shard_jobs(m_lens: np.ndarray, n_lens: np.ndarray, world: int, block: int = 1024):
+    """Per-rank job indices balanced on DP cells: jobs sorted by cells, cut into blocks, blocks dealt by LPT (largest first to the
+    least loaded rank).  Deterministic, so every rank can compute its own share without communication."""
+    cells = np.asarray(m_lens, np.int64) * np.asarray(n_lens, np.int64)
+    order = np.argsort(-cells, kind="stable")
+    load = np.zeros(world, np.int64)
+    per_rank = [[] for _ in range(world)]
+    for s in range(0, len(order), block):
+        idx = order[s:s + block]
+        r = int(np.argmin(load))
+        per_rank[r].append(idx); load[r] += int(cells[idx].sum())
+    return [np.sort(np.concatenate(x)).astype(np.uint32) if x else np.zeros(0, np.uint32) for x in per_rank]
+
+
+def sub_batch(batch: Batch, jobs: np.ndarray) -> Batch:
+    """The given jobs as a batch of their own (pair index arrays into the SAME strings: nothing is copied or re-packed)."""
+    pp = jobs if batch.pp is None else batch.pp[jobs]
+    shared = batch.pt is None and len(batch.toffs) == 2
+    pt = (np.zeros(len(jobs), np.uint32) if shared else jobs) if batch.pt is None else batch.pt[jobs]
+    return Batch(batch.patterns, batch.poffs, batch.texts, batch.toffs, pair_pattern=pp, pair_text=pt, alphabet=batch.pod.alphabet)
+
+
+def score_sharded(batch: Batch, score_fn, dist=None):
+    """Every rank holds the (host) batch, scores its own jobs with `score_fn(sub_batch) -> int32 scores` (on its GPU through the C ABI;
+    a CPU stand-in in the gloo test); rank 0 gathers the scores into the caller's job order (None on the other ranks)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return np.asarray(score_fn(batch), np.int32)
+    rank, world = dist.get_rank(), dist.get_world_size()
+    m = np.diff(batch.poffs)[np.arange(batch.n_pairs) if batch.pp is None else batch.pp]
+    shared = batch.pt is None and len(batch.toffs) == 2
+    n = np.diff(batch.toffs)[(np.zeros(batch.n_pairs, np.int64) if shared else np.arange(batch.n_pairs)) if batch.pt is None else batch.pt]
+    mine = shard_jobs(m, n, world)[rank]
+    res = np.asarray(score_fn(sub_batch(batch, mine)), np.int32) if len(mine) else np.zeros(0, np.int32)
+    gathered = [None] * world if rank == 0 else None
+    dist.gather_object((mine, res), gathered, dst=0)
+    if rank != 0:
+        return None
+    out = np.zeros(batch.n_pairs, np.int32)
+    for idx, r in gathered:
+        out[idx] = r
+    return out
