@@ -42,6 +42,7 @@ struct NvbArgs {
   uint32_t first, count;                                               // job range of this launch
   int match, mismatch, go_t, ge_t, go_p, ge_p;                         // _t: gap consuming text (F), _p: consuming pattern (E)
   int band_shift;                                                      // log2 of the reference's BAND_LEN (tie order of LOCAL sinks)
+  uint32_t sixteen;                                                    // == 16 (run-time operand: see k_nvb_s16)
   int32_t* score; int32_t* sink_i; int32_t* sink_j;
   uint2* scratch; uint32_t stride;                                     // band border (H, E) per text row: scratch[row * stride + thread]
   uint32_t* worklist; uint32_t* work_count;
@@ -313,6 +314,33 @@ __device__ __forceinline__ uint32_t band_codes(const uint32_t* __restrict__ pk, 
   return d ? __funnelshift_r(lo, hi, 32 - 2 * d) : hi;
 }
 
+// LOCAL sinks on the packed path.  Per cell key = H * 16 + (column - 1 within the band); the row's largest key is its candidate
+// (largest column among the row's maxima).  The reference's report order is (band of BAND_LEN columns, text row, column) with the
+// LAST maximum winning: for BAND_LEN = 8 a band of 16 holds two reference bands, so rows are compared on key >> 3 = (H, half) and
+// a later row wins ties; for BAND_LEN = 16 on key >> 4 = H.  best = max(best, c) per lane; lanes where c >= best record the row's
+// key and position.  One asm block so that ptxas fuses the lane compares into the predicate outputs of VIMNMX.S16x2.
+struct SinkTrack { uint32_t bestc, keyL, keyH, posL, posH; };
+__device__ __forceinline__ void sink_update(SinkTrack& t, uint32_t c, uint32_t rowkey, uint32_t pos) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pl, ph;\n\t"
+      ".reg .s16 n0, n1, c0, c1;\n\t"
+      ".reg .b32 nb;\n\t"
+      "max.s16x2 nb, %0, %5;\n\t"
+      "mov.b32 {n0, n1}, nb;\n\t"
+      "mov.b32 {c0, c1}, %5;\n\t"
+      "setp.eq.s16 pl, n0, c0;\n\t"
+      "setp.eq.s16 ph, n1, c1;\n\t"
+      "mov.b32 %0, nb;\n\t"
+      "@pl mov.b32 %1, %6;\n\t"
+      "@pl mov.b32 %3, %7;\n\t"
+      "@ph mov.b32 %2, %6;\n\t"
+      "@ph mov.b32 %4, %7;\n\t"
+      "}"
+      : "+r"(t.bestc), "+r"(t.keyL), "+r"(t.keyH), "+r"(t.posL), "+r"(t.posH)
+      : "r"(c), "r"(rowkey), "r"(pos));
+}
+
 // FIXED: the scratch row stride is the compile-time kFixedStride, so the next-row load, the prefetch and the store share ONE
 // pointer with immediate offsets (the run-time-stride variant serves batches whose texts are too long for that layout).
 template <int TYPE, bool FIXED, bool SINK = false>
@@ -347,6 +375,9 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
 
   int bestA = INT_MIN, bestB = INT_MIN, rowA = -1, rowB = -1;                              // rowA/rowB: SEMI_GLOBAL sinks (last maximum wins)
   uint32_t best2 = (TYPE == NVBX_LOCAL) ? 0u : 0x80008000u;
+  SinkTrack trk = {0u, 0u, 0u, 0u, 0u};                                                    // LOCAL + SINK
+  const uint32_t sixteen = a.sixteen, kshift = (uint32_t)a.band_shift;                       // key >> 3 (BAND_LEN 8) or >> 4 (16); 16 at run time keeps the key an IMAD
+  const uint32_t kmask = (0xFFFFu >> kshift) * 0x00010001u;
   for (int b = 0; b < nb; b++) {
     const uint32_t wA = band_codes(pA, b, dA, nwA), wB = band_codes(pB, b, dB, nwB);
     uint32_t tabA[16], tabB[16];
@@ -366,6 +397,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
     }
     const bool first = b == 0, last = b == nb - 1;
     const bool capA = b == nbA - 1, capB = b == nbB - 1;
+    if (TYPE == NVBX_LOCAL && SINK && a.band_shift == 3) trk.bestc &= 0xFFFEFFFEu;          // a later band wins ties against either half of an earlier one
     // band border of the previous band: read one row ahead into registers, kPrefetchRows rows ahead into L1 (the scratch of the
     // resident threads is larger than L2: without the prefetch the kernel waits on these loads -- ncu long-scoreboard stalls)
     uint2* rp = col;                                                                       // row i of the band border; row i+1 is loaded, row i+kPrefetchRows prefetched
@@ -409,11 +441,20 @@ NVB_UNROLL(NVB_ROW_UNROLL)
       if (!last) *rp = make_uint2(H[16], e);
       rp += stride;
       if (TYPE == NVBX_LOCAL) {
-        uint32_t m = best2;
-#pragma unroll
-        for (int j = 1; j <= 16; j += 2) m = __vimax3_s16x2(m, H[j], H[j + 1]);
         const uint32_t mask = (i <= NA ? 0x0000FFFFu : 0u) | (i <= NB ? 0xFFFF0000u : 0u);   // rows past a job's text end do not count
-        best2 = (m & mask) | (best2 & ~mask);
+        if (SINK) {
+          uint32_t rk = 0;
+#pragma unroll
+          for (int j = 1; j <= 16; j += 2)
+            rk = __vimax3_s16x2(rk, H[j] * sixteen + (uint32_t)(j - 1) * 0x00010001u, H[j + 1] * sixteen + (uint32_t)j * 0x00010001u);
+          rk &= mask;
+          sink_update(trk, (rk >> kshift) & kmask, rk, ((uint32_t)b << 20) | (uint32_t)i);
+        } else {
+          uint32_t m = best2;
+#pragma unroll
+          for (int j = 1; j <= 16; j += 2) m = __vimax3_s16x2(m, H[j], H[j + 1]);
+          best2 = (m & mask) | (best2 & ~mask);
+        }
       } else if (TYPE == NVBX_SEMI_GLOBAL) {
         if (SINK) {                                                                        // BestSink `score <= new` (sink_inl.h:52-60): the last row wins
           if (capA && i <= NA) { const int h = lo16(H[16]); if (h >= bestA) { bestA = h; rowA = i; } }
@@ -431,7 +472,17 @@ NVB_UNROLL(NVB_ROW_UNROLL)
   if (TYPE == NVBX_LOCAL || (TYPE == NVBX_SEMI_GLOBAL && !SINK)) { bestA = lo16(best2); bestB = hi16(best2); }
   a.score[jobA] = bestA;
   if (jobB != jobA) a.score[jobB] = bestB;
-  if (SINK) {                                                                              // GLOBAL: (N, M); SEMI_GLOBAL: (last best row, M)
+  if (SINK && TYPE == NVBX_LOCAL) {
+    // a score of 0 means every cell tied at 0: the last reported cell (N, M) wins (sink_inl.h:52-60)
+    const uint32_t kA = trk.keyL & 0xFFFFu, kB = trk.keyH >> 16;
+    const int sA = (int)(kA >> 4), sB = (int)(kB >> 4);
+    a.score[jobA] = sA;
+    a.sink_i[jobA] = sA ? (int)(trk.posL & 0xFFFFFu) : NA; a.sink_j[jobA] = sA ? (int)(16 * (trk.posL >> 20) + (kA & 15u) + 1) : MA;
+    if (jobB != jobA) {
+      a.score[jobB] = sB;
+      a.sink_i[jobB] = sB ? (int)(trk.posH & 0xFFFFFu) : NB; a.sink_j[jobB] = sB ? (int)(16 * (trk.posH >> 20) + (kB & 15u) + 1) : MB;
+    }
+  } else if (SINK) {                                                                       // GLOBAL: (N, M); SEMI_GLOBAL: (last best row, M)
     a.sink_i[jobA] = (TYPE == NVBX_GLOBAL) ? NA : rowA; a.sink_j[jobA] = MA;
     if (jobB != jobA) { a.sink_i[jobB] = (TYPE == NVBX_GLOBAL) ? NB : rowB; a.sink_j[jobB] = MB; }
   }
@@ -555,7 +606,10 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
                     (sum + 34) * (long long)std::max(std::abs(a.ge_t), std::abs(a.ge_p)) + 4LL * std::max(std::abs(a.go_t), std::abs(a.go_p)) +
                         (long long)std::max(std::abs(a.match), std::abs(a.mismatch)) * (mn + 1) < (1LL << 28) &&
                     std::max(std::abs(a.ge_t), std::abs(a.ge_p)) < (1 << 19);
-  const bool fast = fits && (!want_sinks || al->type != NVBX_LOCAL) && g_policy == 0;    // LOCAL sinks need the reference's band order: int32 kernel
+  // LOCAL sinks on the packed path: keys H * 16 + column must fit 16 bits, and strictly negative penalties keep pad cells from tying
+  const bool local_keys = pos * mn <= 2047 && a.go_t < 0 && a.ge_t < 0 && a.mismatch < 0 && s->max_n < (1u << 20);
+  const bool fast = fits && (!want_sinks || al->type != NVBX_LOCAL || local_keys) && g_policy == 0;
+  a.sixteen = 16;
 
   // chunk the jobs so that the band-border scratch (8 B per text row per thread) stays below ~2 GB.  The fast path prefers the
   // fixed row stride (2 x kFixedStride jobs per launch) when the texts are short enough for it.
@@ -585,7 +639,7 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
 #define NVB_LAUNCH_FAST(T, S) do { \
         if (fixed) k_nvb_s16<T, true, S><<<g, kThreads, 0, s->st>>>(a); else k_nvb_s16<T, false, S><<<g, kThreads, 0, s->st>>>(a); \
         k_nvb_i32w<T, S><<<g2, kThreads, 0, s->st>>>(a, 1); } while (0)
-      if (type == NVBX_LOCAL) NVB_LAUNCH_FAST(NVBX_LOCAL, false);
+      if (type == NVBX_LOCAL) { if (want_sinks) NVB_LAUNCH_FAST(NVBX_LOCAL, true); else NVB_LAUNCH_FAST(NVBX_LOCAL, false); }
       else if (type == NVBX_GLOBAL) { if (want_sinks) NVB_LAUNCH_FAST(NVBX_GLOBAL, true); else NVB_LAUNCH_FAST(NVBX_GLOBAL, false); }
       else { if (want_sinks) NVB_LAUNCH_FAST(NVBX_SEMI_GLOBAL, true); else NVB_LAUNCH_FAST(NVBX_SEMI_GLOBAL, false); }
 #undef NVB_LAUNCH_FAST

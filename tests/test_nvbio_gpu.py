@@ -55,7 +55,7 @@ def test_fast_path_scores_ragged_lengths(orc, type_, scheme):
     assert k == "s16x2"
     assert np.array_equal(s, want)
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True)
-    assert k == ("int32" if type_ == nvb.LOCAL else "s16x2")          # LOCAL sinks need the reference's band order: general kernel
+    assert k == "s16x2"                                               # LOCAL sinks: packed keys (scores here stay below 2048)
     assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True, policy=1)
     assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
@@ -174,4 +174,37 @@ def test_batches_larger_than_one_launch(orc):
         s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), batch)
         assert k == "s16x2" and np.array_equal(s, want), type_
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, nvb.LOCAL, *GOTOH_SW), batch, want_sinks=True)
+    assert k == "s16x2" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
+    s, si, sj, k = run(nvb.aligner(nvb.GOTOH, nvb.LOCAL, *GOTOH_SW), batch, want_sinks=True, policy=1)
     assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
+
+
+@pytest.mark.parametrize("algo,scheme", [(nvb.GOTOH, GOTOH_SW), (nvb.SMITH_WATERMAN, (2, -1, -2, -2))])
+def test_local_sinks_tie_order_and_key_range(orc, algo, scheme):
+    """LOCAL BestSink coordinates on the packed path: repeats make many cells tie, so the reference's report order (bands of 8 for Gotoh, 16
+    for Smith-Waterman; last maximum wins) decides; scores above 2047 do not fit the packed keys and go to the int32 kernel."""
+    rng = np.random.default_rng(41)
+    pats, texts = [], []
+    for k in range(1200):
+        unit = rng.integers(0, 4, int(rng.integers(2, 9))).astype(np.uint8)          # short tandem repeats: ties everywhere
+        t = np.tile(unit, int(rng.integers(6, 40)))[: int(rng.integers(20, 260))]
+        p = np.tile(unit, 30)[: int(rng.integers(3, 70))]
+        if k % 4 == 0:
+            p = rng.integers(0, 4, len(p)).astype(np.uint8)
+        if k % 7 == 0:
+            p = (3 - t[:min(len(t), 40)]).astype(np.uint8)                           # mostly mismatches: score 0 or tiny
+        pats.append(p); texts.append(t)
+    pb, poffs = nvb.concat(pats); tb, toffs = nvb.concat(texts)
+    batch = nvb.Batch(pb, poffs, tb, toffs)
+    want, wi, wj = orc.batch(algo, po.NVB_LOCAL, scheme, pb, poffs, tb, toffs)
+    s, si, sj, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch, want_sinks=True)
+    assert k == "s16x2"
+    assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
+    # long identical strings: score 2 * 1500 > 2047
+    pats, poffs, texts, toffs = synth.nvb_jobs(40, 1400, 1500, 1800, 2000, seed=42, sub=0.01, indel=0.0)
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    want, wi, wj = orc.batch(algo, po.NVB_LOCAL, scheme, pats, poffs, texts, toffs)
+    s, si, sj, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch, want_sinks=True)
+    assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
+    s, _, _, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch)
+    assert k == "s16x2" and np.array_equal(s, want)
