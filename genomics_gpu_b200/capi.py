@@ -89,7 +89,7 @@ EXPORTED_SYMBOLS = [
     "gasal_host_batch_add", "gasal_host_batch_addbase", "gasal_host_batch_print", "gasal_host_batch_printall",
     "gasal_host_alns_resize", "gasal_op_fill", "gasal_set_device",
     "gasal_res_new_host", "gasal_res_new_device", "gasal_res_new_device_cpy", "gasal_res_destroy_host", "gasal_res_destroy_device",
-    "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
+    "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_set_coordinate_fix", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
     "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
     "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all", "gasalx_batcher_release",
     "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_cigar_string",
@@ -134,6 +134,7 @@ def load() -> C.CDLL:
     lib.gasal_set_device.argtypes = [C.c_int, C.c_int]
     lib.gasalx_set_n_code.argtypes = [C.c_int, C.c_int]
     lib.gasalx_set_kernel_policy.argtypes = [C.c_int]
+    lib.gasalx_set_coordinate_fix.argtypes = [C.c_int]
     lib.gasalx_set_revcomp_mode.argtypes = [C.c_int]
     lib.gasalx_last_batch_ms.argtypes = [P(GpuStorage), P(C.c_float)]; lib.gasalx_last_batch_ms.restype = C.c_int
     lib.gasalx_kernel_launches.argtypes = [P(GpuStorage)]; lib.gasalx_kernel_launches.restype = C.c_uint64

@@ -60,6 +60,7 @@ int g_n_code = 0x4E;
 int g_n_penalty = -1;
 int g_kernel_policy = 0;
 int g_revcomp_mode = 0;
+int g_coord_fix = 0;
 
 struct Priv {
   uint32_t* colstate = nullptr; size_t colstate_words = 0;
@@ -75,6 +76,7 @@ struct Priv {
   char* d_text = nullptr; size_t text_bytes = 0;             // gasalx_cigar_text_async
   uint32_t* d_text_lens = nullptr; size_t text_lens_cap = 0;
   uint32_t tb_n = 0; int tb_algo = 0;                         // pairs / algo of the last WITH_TB batch (0: none)
+  uint32_t fix_n = 0; int fix_kind = 0;                       // gasalx_set_coordinate_fix: 1 local start mirror (Q3), 2 / 3 semi-global default coordinates (Q8; 3: with start)
 };
 
 inline Priv* priv(gasal_gpu_storage_t* s) { return (Priv*)s->b200_priv; }
@@ -115,6 +117,7 @@ void gasal_params_default(gasal_params_t* p) {   // src/args_parser.cpp:12-29
 void gasalx_set_n_code(int n_code, int n_penalty) { g_n_code = n_code; g_n_penalty = n_penalty; }
 void gasalx_set_kernel_policy(int policy) { g_kernel_policy = policy; }
 void gasalx_set_revcomp_mode(int mode) { g_revcomp_mode = mode; }
+void gasalx_set_coordinate_fix(int on) { g_coord_fix = on; }
 
 void gasal_copy_subst_scores(gasal_subst_scores* subst) { g_scores = *subst; }   // src/gasal_align.cu:329-339
 
@@ -565,6 +568,11 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
     a.cigar = pv->d_cigar; a.n_cigar_ops = pv->d_n_cigar_ops;
   }
   pv->tb_n = want_tb ? n : 0; pv->tb_algo = want_tb ? params->algo : 0;
+  pv->fix_kind = 0; pv->fix_n = n;
+  if (g_coord_fix) {
+    if (params->algo == LOCAL && start == WITH_START) pv->fix_kind = 1;
+    else if (params->algo == SEMI_GLOBAL && a.head == TARGET && a.tail == TARGET) pv->fix_kind = (start == WITH_START) ? 3 : 2;
+  }
 
   // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
   if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
@@ -733,6 +741,25 @@ int gasal_is_aln_async_done(gasal_gpu_storage_t* s) {   // src/gasal_align.cu:31
   if (err != cudaSuccess) {
     if (err == cudaErrorNotReady) return -1;
     GASAL_FAIL(GASALX_E_CUDA, "[GASAL CUDA ERROR:] %s(CUDA error no.=%d). Line no. %d in file %s\n", cudaGetErrorString(err), (int)err, __LINE__, __FILE__);
+  }
+  // opt-in repair of two reference quirks in the HOST results (never active in parity runs)
+  Priv* pv = priv(s);
+  if (pv && pv->fix_kind && s->host_res) {
+    gasal_res_t* h = s->host_res;
+    if (pv->fix_kind == 1 && h->target_batch_start) {
+      // Q3: reported = 16*floor(ts/8) + 14 - ts (the start is mirrored inside its 8-base word, local_kernel_template.h:41)
+      for (uint32_t i = 0; i < pv->fix_n; i++) {
+        const int r = h->target_batch_start[i] - 7;
+        if (r >= 0) h->target_batch_start[i] = (r & ~7) + 7 - (r & 7);
+      }
+    } else if (pv->fix_kind >= 2 && h->query_batch_end) {
+      // Q8: the default semi-global mode aligns the WHOLE query; the reference reports ref_len / read_len-1-ref_len there
+      for (uint32_t i = 0; i < pv->fix_n; i++) {
+        h->query_batch_end[i] = (int32_t)s->host_query_batch_lens[i] - 1;
+        if (pv->fix_kind == 3 && h->query_batch_start) h->query_batch_start[i] = 0;
+      }
+    }
+    pv->fix_kind = 0;
   }
   gasal_host_batch_reset(s);
   s->is_free = 1;

@@ -214,6 +214,17 @@ void gasalx_set_kernel_policy(int policy);
  *                 operand is folded to 0 (first half of the words zeroed, second half = reversed first half). */
 void gasalx_set_revcomp_mode(int mode);
 
+/* Opt-in "fixed coordinates" mode (default 0 = bit-exact with the reference, which is what every parity test uses).  With 1,
+ * gasal_is_aln_async_done repairs two reference quirks in the host results when a batch completes:
+ *   LOCAL + WITH_START: target_batch_start is un-mirrored (the reference reports 16*floor(ts/8) + 14 - ts because
+ *       src/kernels/local_kernel_template.h:41 walks `gidx + (m-1)` backwards; LOCAL + WITH_TB already reports the true start);
+ *   SEMI_GLOBAL with head = tail = TARGET: query_batch_end = query length - 1 and (WITH_START) query_batch_start = 0 -- the whole
+ *       query is aligned in that mode, while the reference reports ref_len and read_len - 1 - ref_len
+ *       (src/kernels/semiglobal_kernel_template.h:63-64,218,381).
+ * Textbook global / semi-global BOUNDARIES (the reference shifts the top row by one, global.h:57-60) are available through
+ * include/nvbio_b200.h, whose Gotoh aligners use the textbook recurrence. */
+void gasalx_set_coordinate_fix(int on);
+
 /* Device-side timing of the last finished batch of a storage, in milliseconds, measured with CUDA
  * events on gpu_storage->str: [0] whole pipeline (first H2D .. last D2H), [1] pack(+revcomp),
  * [2] DP kernels (+traceback).  Returns 0 on success, -1 if the batch has not finished. */

@@ -278,3 +278,31 @@ def test_non_fatal_error_mode(oracle):
         al.wait(0)
         got = al.results(0, b.n)
     assert_same(got, oracle_align(oracle, b, algo=po.LOCAL), K3, "after soft errors")
+
+
+def test_opt_in_coordinate_fix(oracle):
+    """gasalx_set_coordinate_fix(1): un-mirrors LOCAL WITH_START's target_batch_start (reported = 16*floor(ts/8) + 14 - ts, so the
+    repaired value must equal the TRUE start, which LOCAL WITH_TB reports) and gives the default semi-global mode meaningful query
+    coordinates (Q8); everything else stays bit-exact with the reference, and the default mode (0) is untouched."""
+    b = ragged(31)
+    lib = capi.load()
+    ref_start = run(b, algo=capi.LOCAL, start=capi.WITH_START)
+    tb = run(b, algo=capi.LOCAL, start=capi.WITH_TB)                       # true starts from the traceback walker
+    lib.gasalx_set_coordinate_fix(1)
+    try:
+        fixed = run(b, algo=capi.LOCAL, start=capi.WITH_START)
+        sg = run(b, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)
+    finally:
+        lib.gasalx_set_coordinate_fix(0)
+    hit = ref_start["aln_score"] > 0
+    ts = fixed["target_batch_start"]
+    assert np.array_equal(16 * (ts // 8) + 14 - ts, ref_start["target_batch_start"])                       # the documented mirror formula
+    assert np.mean(ts[hit] == tb["target_batch_start"][hit]) > 0.9                                          # = the true start (co-optimal alignments may differ)
+    for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start"):
+        assert np.array_equal(fixed[k], ref_start[k]), k
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, start=po.WITH_START)
+    for k in ("aln_score", "target_batch_end", "target_batch_start"):
+        assert np.array_equal(sg[k], want[k]), k
+    assert np.array_equal(sg["query_batch_end"], b.q_lens.astype(np.int32) - 1) and not sg["query_batch_start"].any()
+    again = run(b, algo=capi.LOCAL, start=capi.WITH_START)
+    assert np.array_equal(again["target_batch_start"], ref_start["target_batch_start"])
