@@ -218,7 +218,10 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_i32w(const NvbArgs a, int f
   const int front = (TYPE == NVBX_GLOBAL) ? kFrontGlobal : 0;
 
   int best = INT_MIN, bi = -1, bj = -1;
+  int bestc = 0, bestkey = 0, bestpos = 0;                                                 // LOCAL + SINK
+  const int sixteen = (int)a.sixteen;                                                      // run-time 16: the key stays an IMAD (FMA pipe)
   for (int b = 0; b < nb; b++) {
+    if (TYPE == NVBX_LOCAL && SINK && a.band_shift == 3) bestc &= ~1;                      // a later band wins ties against either half of an earlier one
     int q[16], sx[16];                                                                    // symbol (256+: never equal) and non-match score per column
 #pragma unroll
     for (int j = 0; j < 16; j++) {
@@ -271,23 +274,32 @@ NVB_UNROLL(2)
       if (!last) *rp = make_uint2((uint32_t)H[16], (uint32_t)e);
       rp += stride;
       if (TYPE == NVBX_LOCAL) {
-        const int mj = last ? M - 16 * b : 16;                                               // valid columns of this band (pad columns never win, but keep exactness)
-        int rowmax = H[1];
-#pragma unroll
-        for (int j = 2; j <= 16; j += 2) rowmax = (j < 16) ? __vimax3_s32(rowmax, H[j], H[j + 1]) : max(rowmax, H[j]);
         if (SINK) {
-          if (rowmax >= best) {
-            int cj = 0;
+          // key = H * 16 + (column - 1): the row's largest key is its candidate (largest column among the row's maxima, pad columns
+          // masked); rows are compared on key >> band_shift = (H, reference band within this band of 16) and the later row wins ties
+          // (the reference's report order; see sink_update below) -- branch-free, so a warp does not serialise on per-job events
+          const int mj = last ? M - 16 * b : 16;
+          int rk = 0;
 #pragma unroll
-            for (int j = 1; j <= 16; j++) if (j <= mj && H[j] == rowmax) cj = j;             // largest column of the row
-            if (cj > 0 && (rowmax > best || reported_later(i, 16 * b + cj, bi, bj, a.band_shift))) { best = rowmax; bi = i; bj = 16 * b + cj; }
-          }
-        } else best = max(best, rowmax);
+          for (int j = 1; j <= 16; j++) { const int kj = H[j] * sixteen + (j - 1); rk = max(rk, (j <= mj) ? kj : 0); }
+          const int c = rk >> a.band_shift;
+          const bool take = c >= bestc;
+          bestc = take ? c : bestc; bestkey = take ? rk : bestkey; bestpos = take ? ((b << 20) | i) : bestpos;
+        } else {
+          int rowmax = H[1];
+#pragma unroll
+          for (int j = 2; j <= 16; j += 2) rowmax = (j < 16) ? __vimax3_s32(rowmax, H[j], H[j + 1]) : max(rowmax, H[j]);
+          best = max(best, rowmax);
+        }
       } else if (last) {
         if (TYPE == NVBX_SEMI_GLOBAL) { if (H[16] >= best) { best = H[16]; bi = i; bj = M; } }
         else if (i == N) { best = H[16]; bi = N; bj = M; }
       }
     }
+  }
+  if (TYPE == NVBX_LOCAL && SINK) {                                                        // score 0: every cell tied, the last reported cell (N, M) wins
+    best = bestkey >> 4;
+    bi = best ? (bestpos & 0xFFFFF) : N; bj = best ? 16 * (bestpos >> 20) + (bestkey & 15) + 1 : M;
   }
   a.score[job] = best;
   if (SINK) { a.sink_i[job] = bi; a.sink_j[job] = bj; }
