@@ -93,6 +93,15 @@ __device__ __forceinline__ Job load_job(const NvbArgs& a, uint32_t job) {
   return j;
 }
 
+// Two formulations of the packed row update, chosen per alignment type from measurements (262144 x 150 x 600, TCUPS):
+//   chain   : H kept as H + Go, E' = VIADDMNMX(E, Ge, Hg_left), H = VIMNMX3(E, F, D): 4 ALU + 2 FMA-pipe instructions per cell pair,
+//             three dependent instructions per cell          semi-global 4.78, local 4.51, global 4.01
+//   off-chain: E chain off H (see the kernel comment): 5 ALU + 1 FMA-pipe, one dependent instruction per cell
+//                                                            semi-global 4.60, local 4.29, global 4.34
+#ifndef NVB_CHAIN_MASK
+#define NVB_CHAIN_MASK 0x6   // bit t set: alignment type t (0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL) uses the chain formulation
+#endif
+__host__ __device__ constexpr bool chain_for(int type) { return (NVB_CHAIN_MASK >> type) & 1; }
 #ifndef NVB_ROW_UNROLL
 #define NVB_ROW_UNROLL 4
 #endif
@@ -218,10 +227,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_i32w(const NvbArgs a, int f
   const int front = (TYPE == NVBX_GLOBAL) ? kFrontGlobal : 0;
 
   int best = INT_MIN, bi = -1, bj = -1;
-  int bestc = 0, bestkey = 0, bestpos = 0;                                                 // LOCAL + SINK
-  const int sixteen = (int)a.sixteen;                                                      // run-time 16: the key stays an IMAD (FMA pipe)
   for (int b = 0; b < nb; b++) {
-    if (TYPE == NVBX_LOCAL && SINK && a.band_shift == 3) bestc &= ~1;                      // a later band wins ties against either half of an earlier one
     int q[16], sx[16];                                                                    // symbol (256+: never equal) and non-match score per column
 #pragma unroll
     for (int j = 0; j < 16; j++) {
@@ -274,32 +280,23 @@ NVB_UNROLL(2)
       if (!last) *rp = make_uint2((uint32_t)H[16], (uint32_t)e);
       rp += stride;
       if (TYPE == NVBX_LOCAL) {
+        const int mj = last ? M - 16 * b : 16;                                               // valid columns of this band (pad columns never win, but keep exactness)
+        int rowmax = H[1];
+#pragma unroll
+        for (int j = 2; j <= 16; j += 2) rowmax = (j < 16) ? __vimax3_s32(rowmax, H[j], H[j + 1]) : max(rowmax, H[j]);
         if (SINK) {
-          // key = H * 16 + (column - 1): the row's largest key is its candidate (largest column among the row's maxima, pad columns
-          // masked); rows are compared on key >> band_shift = (H, reference band within this band of 16) and the later row wins ties
-          // (the reference's report order; see sink_update below) -- branch-free, so a warp does not serialise on per-job events
-          const int mj = last ? M - 16 * b : 16;
-          int rk = 0;
+          if (rowmax >= best) {
+            int cj = 0;
 #pragma unroll
-          for (int j = 1; j <= 16; j++) { const int kj = H[j] * sixteen + (j - 1); rk = max(rk, (j <= mj) ? kj : 0); }
-          const int c = rk >> a.band_shift;
-          const bool take = c >= bestc;
-          bestc = take ? c : bestc; bestkey = take ? rk : bestkey; bestpos = take ? ((b << 20) | i) : bestpos;
-        } else {
-          int rowmax = H[1];
-#pragma unroll
-          for (int j = 2; j <= 16; j += 2) rowmax = (j < 16) ? __vimax3_s32(rowmax, H[j], H[j + 1]) : max(rowmax, H[j]);
-          best = max(best, rowmax);
-        }
+            for (int j = 1; j <= 16; j++) if (j <= mj && H[j] == rowmax) cj = j;             // largest column of the row
+            if (cj > 0 && (rowmax > best || reported_later(i, 16 * b + cj, bi, bj, a.band_shift))) { best = rowmax; bi = i; bj = 16 * b + cj; }
+          }
+        } else best = max(best, rowmax);
       } else if (last) {
         if (TYPE == NVBX_SEMI_GLOBAL) { if (H[16] >= best) { best = H[16]; bi = i; bj = M; } }
         else if (i == N) { best = H[16]; bi = N; bj = M; }
       }
     }
-  }
-  if (TYPE == NVBX_LOCAL && SINK) {                                                        // score 0: every cell tied, the last reported cell (N, M) wins
-    best = bestkey >> 4;
-    bi = best ? (bestpos & 0xFFFFF) : N; bj = best ? 16 * (bestpos >> 20) + (bestkey & 15) + 1 : M;
   }
   a.score[job] = best;
   if (SINK) { a.sink_i[job] = bi; a.sink_j[job] = bj; }
@@ -381,9 +378,11 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
   const size_t stride = FIXED ? (size_t)kFixedStride : (size_t)a.stride;
   const int go = a.go_t, ge = a.ge_t;
   const uint32_t go2 = splat16(go), ge2 = splat16(ge);
-  const uint32_t mis4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
-  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
-  const uint32_t front4 = (TYPE == NVBX_GLOBAL) ? 0x80808080u : 0u;                        // virtual columns in front of the pattern
+  constexpr bool CHAIN = chain_for(TYPE);
+  const int tsh = CHAIN ? go : 0;                                                          // chain: H is kept as H + Go, the tables hold s - Go
+  const uint32_t mis4 = ((uint32_t)(a.mismatch - tsh) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)(a.match - tsh) ^ (uint32_t)(a.mismatch - tsh)) & 0xFFu;
+  const uint32_t front4 = (TYPE == NVBX_GLOBAL) ? 0x80808080u : ((uint32_t)(0 - tsh) & 0xFFu) * 0x01010101u;   // virtual columns in front of the pattern
 
   int bestA = INT_MIN, bestB = INT_MIN, rowA = -1, rowB = -1;                              // rowA/rowB: SEMI_GLOBAL sinks (last maximum wins)
   uint32_t best2 = (TYPE == NVBX_LOCAL) ? 0u : 0x80008000u;
@@ -404,7 +403,7 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
     for (int j = 0; j <= 16; j++) {
       const int ja = 16 * b + j - dA, jb = 16 * b + j - dB;                                // real 1-based column (<= 0: column 0)
       const int va = (TYPE == NVBX_LOCAL || ja <= 0) ? 0 : go + ge * (ja - 1), vb = (TYPE == NVBX_LOCAL || jb <= 0) ? 0 : go + ge * (jb - 1);
-      H[j] = ((uint32_t)va & 0xFFFFu) | ((uint32_t)vb << 16);
+      H[j] = ((uint32_t)(va + tsh) & 0xFFFFu) | ((uint32_t)(vb + tsh) << 16);
       F[j] = splat16(kNeg16);
     }
     const bool first = b == 0, last = b == nb - 1;
@@ -426,13 +425,35 @@ NVB_UNROLL(NVB_ROW_UNROLL)
       twA >>= 2; twB >>= 2;
       uint32_t hl, e;                                                                      // e holds Eg = E - Go
       if (first) {
-        hl = splat16((TYPE == NVBX_GLOBAL) ? go + ge * (i - 1) : 0);
-        e = (TYPE == NVBX_LOCAL) ? splat16(-go) : splat16(kNeg16);
+        hl = splat16(((TYPE == NVBX_GLOBAL) ? go + ge * (i - 1) : 0) + tsh);
+        e = (TYPE == NVBX_LOCAL) ? splat16(CHAIN ? 0 : -go) : splat16(kNeg16);
       } else {
         hl = nxt.x; e = nxt.y;
         if (i < Nx) nxt = rp[stride];
         if (i + kPrefetchRows <= Nx) prefetch_l1(rp + (size_t)kPrefetchRows * stride);
       }
+      uint32_t mrow = 0;                                                                   // LOCAL: row maximum of H (score) or of the keys (SINK)
+      if (CHAIN) {
+      // right-to-left: F and the diagonal sum D (in place over H[j]: H[j-1] still holds the previous row)
+#pragma unroll
+      for (int j = 16; j >= 1; j--) {
+        F[j] = __viaddmax_s16x2(F[j], ge2, H[j]);
+        H[j] = __vadd2(H[j - 1], prmt(tabA[j - 1], tabB[j - 1], sel));
+      }
+      H[0] = hl;
+      // left-to-right: E, H = max(E, F, D), H + Go
+      uint32_t hodd = 0;
+#pragma unroll
+      for (int j = 1; j <= 16; j++) {
+        e = __viaddmax_s16x2(e, ge2, H[j - 1]);
+        const uint32_t h = (TYPE == NVBX_LOCAL) ? __vimax3_s16x2_relu(e, F[j], H[j]) : __vimax3_s16x2(e, F[j], H[j]);
+        H[j] = __vadd2(h, go2);
+        if (TYPE == NVBX_LOCAL) {
+          const uint32_t v = SINK ? h * sixteen + (uint32_t)(j - 1) * 0x00010001u : h;
+          if (j & 1) hodd = v; else mrow = __vimax3_s16x2(mrow, hodd, v);
+        }
+      }
+      } else {
       // right-to-left: F, diagonal, X (in place: H[j-1] still holds the previous row when H[j] is overwritten)
 #pragma unroll
       for (int j = 16; j >= 1; j--) {
@@ -450,21 +471,22 @@ NVB_UNROLL(NVB_ROW_UNROLL)
         eprev = e;
       }
       H[16] = (TYPE == NVBX_LOCAL) ? __viaddmax_s16x2_relu(e, go2, H[16]) : __viaddmax_s16x2(e, go2, H[16]);
+      if (TYPE == NVBX_LOCAL) {
+#pragma unroll
+        for (int j = 1; j <= 16; j += 2)
+          mrow = SINK ? __vimax3_s16x2(mrow, H[j] * sixteen + (uint32_t)(j - 1) * 0x00010001u, H[j + 1] * sixteen + (uint32_t)j * 0x00010001u)
+                      : __vimax3_s16x2(mrow, H[j], H[j + 1]);
+      }
+      }
       if (!last) *rp = make_uint2(H[16], e);
       rp += stride;
       if (TYPE == NVBX_LOCAL) {
         const uint32_t mask = (i <= NA ? 0x0000FFFFu : 0u) | (i <= NB ? 0xFFFF0000u : 0u);   // rows past a job's text end do not count
         if (SINK) {
-          uint32_t rk = 0;
-#pragma unroll
-          for (int j = 1; j <= 16; j += 2)
-            rk = __vimax3_s16x2(rk, H[j] * sixteen + (uint32_t)(j - 1) * 0x00010001u, H[j + 1] * sixteen + (uint32_t)j * 0x00010001u);
-          rk &= mask;
+          const uint32_t rk = mrow & mask;
           sink_update(trk, (rk >> kshift) & kmask, rk, ((uint32_t)b << 20) | (uint32_t)i);
         } else {
-          uint32_t m = best2;
-#pragma unroll
-          for (int j = 1; j <= 16; j += 2) m = __vimax3_s16x2(m, H[j], H[j + 1]);
+          const uint32_t m = __vmaxs2(best2, mrow);
           best2 = (m & mask) | (best2 & ~mask);
         }
       } else if (TYPE == NVBX_SEMI_GLOBAL) {
@@ -482,6 +504,7 @@ NVB_UNROLL(NVB_ROW_UNROLL)
     }
   }
   if (TYPE == NVBX_LOCAL || (TYPE == NVBX_SEMI_GLOBAL && !SINK)) { bestA = lo16(best2); bestB = hi16(best2); }
+  if (TYPE != NVBX_LOCAL) { bestA -= tsh; bestB -= tsh; }                                  // captured H[16] carries the frame shift
   a.score[jobA] = bestA;
   if (jobB != jobA) a.score[jobB] = bestB;
   if (SINK && TYPE == NVBX_LOCAL) {
@@ -611,8 +634,9 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
   const long long hi = pos * mn + 2LL * std::abs(a.go_t) + 16;
   const long long lo = (al->type == NVBX_LOCAL) ? 3LL * a.go_t + std::min(a.mismatch, 0) + a.ge_t
                                                 : 4LL * a.go_t + (long long)a.ge_t * (sum + 34) + std::min(a.mismatch, 0) + std::min(a.match, 0) - 128;
+  const int tsh = chain_for(al->type) ? a.go_t : 0;                                        // the chain formulation's tables hold s - Go
   const bool fits = hi <= 32000 && lo >= -31000 && a.go_t == a.go_p && a.ge_t == a.ge_p && a.go_t <= a.ge_t && a.ge_t <= 0 && a.ge_t > -128 &&
-                    a.go_t > -128 && a.mismatch <= 0 && a.match <= 127 && a.match > -128 && a.mismatch > -128;
+                    a.go_t > -128 && a.mismatch <= 0 && a.match - tsh <= 127 && a.match - tsh > -128 && a.mismatch - tsh > -128;
   // the banded-16 int32 kernel needs ordered, non-positive costs and head room for its -2^20 front-column sentinel
   const bool wide = a.go_t <= a.ge_t && a.ge_t <= 0 && a.go_p <= a.ge_p && a.ge_p <= 0 && a.mismatch <= 0 &&
                     (sum + 34) * (long long)std::max(std::abs(a.ge_t), std::abs(a.ge_p)) + 4LL * std::max(std::abs(a.go_t), std::abs(a.go_p)) +
