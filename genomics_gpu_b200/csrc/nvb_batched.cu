@@ -101,6 +101,9 @@ __device__ __forceinline__ Job load_job(const NvbArgs& a, uint32_t job) {
 #ifndef NVB_CHAIN_MASK
 #define NVB_CHAIN_MASK 0x6   // bit t set: alignment type t (0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL) uses the chain formulation
 #endif
+#ifndef NVB_CHAIN_MASK_I32
+#define NVB_CHAIN_MASK_I32 0x0  // same choice for the int32 kernel k_nvb_i32w (measured: no gain, 2.15 either way; global 2.01 with the chain)
+#endif
 __host__ __device__ constexpr bool chain_for(int type) { return (NVB_CHAIN_MASK >> type) & 1; }
 #ifndef NVB_ROW_UNROLL
 #define NVB_ROW_UNROLL 4
@@ -225,6 +228,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_i32w(const NvbArgs a, int f
   const size_t stride = a.stride;
   const int go_t = a.go_t, ge_t = a.ge_t, go_p = a.go_p, ge_p = a.ge_p, match = a.match, mismatch = a.mismatch;
   const int front = (TYPE == NVBX_GLOBAL) ? kFrontGlobal : 0;
+  constexpr bool CHAIN = (NVB_CHAIN_MASK_I32 >> TYPE) & 1;                                  // chain: H kept as H + Go_t (see k_nvb_s16)
+  const int tsh = CHAIN ? go_t : 0, dgo = go_p - go_t, matchs = match - tsh;
 
   int best = INT_MIN, bi = -1, bj = -1;
   for (int b = 0; b < nb; b++) {
@@ -234,13 +239,13 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_i32w(const NvbArgs a, int f
       const int c = 16 * b + j;
       const bool real = c >= d && c < M + d;
       q[j] = real ? (int)P[c - d] : 256 + j;
-      sx[j] = (c < d) ? front : mismatch;
+      sx[j] = ((c < d) ? front : mismatch) - tsh;
     }
     int H[17], F[17];                                                                     // F holds F - Go_t
 #pragma unroll
     for (int j = 0; j <= 16; j++) {
       const int jr = 16 * b + j - d;                                                       // real 1-based column (<= 0: column 0)
-      H[j] = (TYPE == NVBX_LOCAL || jr <= 0) ? 0 : go_p + ge_p * (jr - 1);
+      H[j] = ((TYPE == NVBX_LOCAL || jr <= 0) ? 0 : go_p + ge_p * (jr - 1)) + tsh;
       F[j] = kNeg32;
     }
     const bool first = b == 0, last = b == nb - 1;
@@ -254,14 +259,29 @@ NVB_UNROLL(2)
     for (int i = 1; i <= N; i++) {
       int hl, e;                                                                           // e holds E - Go_p
       if (first) {
-        hl = (TYPE == NVBX_GLOBAL) ? go_t + ge_t * (i - 1) : 0;
-        e = (TYPE == NVBX_LOCAL) ? -go_p : kNeg32;
+        hl = ((TYPE == NVBX_GLOBAL) ? go_t + ge_t * (i - 1) : 0) + tsh;
+        e = (TYPE == NVBX_LOCAL) ? (CHAIN ? 0 : -go_p) : kNeg32;
       } else {
         hl = (int)nxt.x; e = (int)nxt.y;
         if (i < N) nxt = rp[stride];
         if (i + kPrefetchRows <= N) prefetch_l1(rp + (size_t)kPrefetchRows * stride);
       }
       const int t = (int)T[i - 1];
+      if (CHAIN) {
+        // H holds H + Go_t, e the true E: F, then D in place (right-to-left); E, H = max(E, F, D), H + Go_t (left-to-right)
+#pragma unroll
+        for (int j = 16; j >= 1; j--) {
+          F[j] = __viaddmax_s32(F[j], ge_t, H[j]);
+          H[j] = H[j - 1] + ((t == q[j - 1]) ? matchs : sx[j - 1]);
+        }
+        H[0] = hl;
+#pragma unroll
+        for (int j = 1; j <= 16; j++) {
+          e = __viaddmax_s32(e, ge_p, H[j - 1] + dgo);
+          const int h = (TYPE == NVBX_LOCAL) ? __vimax3_s32_relu(e, F[j], H[j]) : __vimax3_s32(e, F[j], H[j]);
+          H[j] = h + tsh;
+        }
+      } else {
 #pragma unroll
       for (int j = 16; j >= 1; j--) {
         F[j] = __viaddmax_s32(F[j], ge_t, H[j]);
@@ -277,6 +297,7 @@ NVB_UNROLL(2)
         eprev = e;
       }
       H[16] = (TYPE == NVBX_LOCAL) ? __viaddmax_s32_relu(e, go_p, H[16]) : __viaddmax_s32(e, go_p, H[16]);
+      }
       if (!last) *rp = make_uint2((uint32_t)H[16], (uint32_t)e);
       rp += stride;
       if (TYPE == NVBX_LOCAL) {
@@ -298,7 +319,7 @@ NVB_UNROLL(2)
       }
     }
   }
-  a.score[job] = best;
+  a.score[job] = best - tsh;                                                               // tracked in the kernel's H frame
   if (SINK) { a.sink_i[job] = bi; a.sink_j[job] = bj; }
 }
 
