@@ -44,7 +44,8 @@ struct NvbArgs {
   int band_shift;                                                      // log2 of the reference's BAND_LEN (tie order of LOCAL sinks)
   uint32_t sixteen;                                                    // == 16 (run-time operand: see k_nvb_s16)
   int32_t* score; int32_t* sink_i; int32_t* sink_j;
-  uint2* scratch; uint32_t stride;                                     // band border (H, E) per text row: scratch[row * stride + thread]
+  uint2* scratch; uint32_t stride;                                     // band border (H, E) per text row: scratch[row * stride + thread] ...
+  uint32_t rows_cap;                                                   // ... or, NVB_CTA_LAYOUT, scratch[(cta * rows_cap + row) * 128 + thread in cta]
   uint32_t* worklist; uint32_t* work_count;
 };
 
@@ -101,6 +102,11 @@ __device__ __forceinline__ Job load_job(const NvbArgs& a, uint32_t job) {
 #ifndef NVB_CHAIN_MASK
 #define NVB_CHAIN_MASK 0x6   // bit t set: alignment type t (0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL) uses the chain formulation
 #endif
+// Band-border scratch layout: 1 = [CTA][text row][thread of the CTA] -- a CTA streams through its own contiguous region (1 KB per
+// row, rows adjacent: DRAM-page friendly, compile-time row stride); 0 = [text row][every thread of the launch] (1 KB pieces 1 MB apart).
+#ifndef NVB_CTA_LAYOUT
+#define NVB_CTA_LAYOUT 1
+#endif
 #ifndef NVB_CHAIN_MASK_I32
 #define NVB_CHAIN_MASK_I32 0x0  // same choice for the int32 kernel k_nvb_i32w (measured: no gain, 2.15 either way; global 2.01 with the chain)
 #endif
@@ -143,8 +149,8 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
   const uint8_t* __restrict__ P = a.pbytes + a.poffs[jb.pi];
   const uint8_t* __restrict__ T = a.tbytes + a.toffs[jb.ti];
   const int M = (int)jb.M, N = (int)jb.N;
-  uint2* __restrict__ col = a.scratch + idx;
-  const uint32_t stride = a.stride;
+  uint2* __restrict__ col = NVB_CTA_LAYOUT ? a.scratch + (size_t)blockIdx.x * a.rows_cap * kThreads + threadIdx.x : a.scratch + idx;
+  const uint32_t stride = NVB_CTA_LAYOUT ? (uint32_t)kThreads : a.stride;
   const int go_t = a.go_t, ge_t = a.ge_t, go_p = a.go_p, ge_p = a.ge_p, match = a.match, mismatch = a.mismatch;
 
   int best = INT_MIN, bi = -1, bj = -1;
@@ -224,8 +230,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_i32w(const NvbArgs a, int f
   const int M = (int)jb.M, N = (int)jb.N;
   const int d = (TYPE == NVBX_LOCAL) ? 0 : (16 - (M & 15)) & 15;                           // virtual columns in front of the pattern
   const int nb = (M + d + 15) >> 4;
-  uint2* __restrict__ col = a.scratch + idx;
-  const size_t stride = a.stride;
+  uint2* __restrict__ col = NVB_CTA_LAYOUT ? a.scratch + (size_t)blockIdx.x * a.rows_cap * kThreads + threadIdx.x : a.scratch + idx;
+  const size_t stride = NVB_CTA_LAYOUT ? (size_t)kThreads : (size_t)a.stride;
   const int go_t = a.go_t, ge_t = a.ge_t, go_p = a.go_p, ge_p = a.ge_p, match = a.match, mismatch = a.mismatch;
   const int front = (TYPE == NVBX_GLOBAL) ? kFrontGlobal : 0;
   constexpr bool CHAIN = (NVB_CHAIN_MASK_I32 >> TYPE) & 1;                                  // chain: H kept as H + Go_t (see k_nvb_s16)
@@ -395,8 +401,8 @@ __global__ void __launch_bounds__(kThreads, 4) k_nvb_s16(const NvbArgs a) {
   const int dA = (TYPE == NVBX_LOCAL) ? 0 : (16 - (MA & 15)) & 15, dB = (TYPE == NVBX_LOCAL) ? 0 : (16 - (MB & 15)) & 15;
   const int nbA = (MA + dA + 15) >> 4, nbB = (MB + dB + 15) >> 4, nb = max(nbA, nbB);
   const int nwA = (MA + 15) >> 4, nwB = (MB + 15) >> 4;
-  uint2* __restrict__ col = a.scratch + idx;
-  const size_t stride = FIXED ? (size_t)kFixedStride : (size_t)a.stride;
+  uint2* __restrict__ col = NVB_CTA_LAYOUT ? a.scratch + (size_t)blockIdx.x * a.rows_cap * kThreads + threadIdx.x : a.scratch + idx;
+  const size_t stride = NVB_CTA_LAYOUT ? (size_t)kThreads : FIXED ? (size_t)kFixedStride : (size_t)a.stride;
   const int go = a.go_t, ge = a.ge_t;
   const uint32_t go2 = splat16(go), ge2 = splat16(ge);
   constexpr bool CHAIN = chain_for(TYPE);
@@ -683,7 +689,7 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
     if (cudaMalloc(&s->scratch, need * sizeof(uint2)) != cudaSuccess) { cudaGetLastError(); return fail("nvbx_stream_enact: cannot allocate the band-border scratch (text too long for this batch)"); }
     s->scratch_elems = need;
   }
-  a.scratch = s->scratch; a.stride = (uint32_t)(fixed ? (size_t)kFixedStride : chunk);
+  a.scratch = s->scratch; a.stride = (uint32_t)(fixed ? (size_t)kFixedStride : chunk); a.rows_cap = s->max_n;
 
   NVB_CHECK(cudaEventRecord(s->e0, s->st));
   bool used_i32 = !fast;
