@@ -208,3 +208,24 @@ def test_local_sinks_tie_order_and_key_range(orc, algo, scheme):
     assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
     s, _, _, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch)
     assert k == "s16x2" and np.array_equal(s, want)
+
+
+def test_cpp_front_end(orc, tmp_path):
+    """The reference-named C++ front end (include/nvbio_b200_batched.hpp) through tools/nvb_cpp_example.cpp -- sw-benchmark's
+    batch_score_profile call sequence -- against the oracle: Gotoh global / semi-global / local and edit-distance semi-global, scores and sinks."""
+    import subprocess
+    from test_nvbio_oracle import _write_jobs
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "build", "nvb_cpp_example")
+    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    pats, poffs, texts, toffs = synth.nvb_jobs(501, 5, 120, 30, 260, seed=44)
+    _write_jobs(tmp_path / "jobs.bin", pats, poffs, texts, toffs)
+    r = subprocess.run([exe, str(tmp_path / "jobs.bin")], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    got = np.array([[int(x) for x in ln.split()] for ln in r.stdout.strip().split("\n")], np.int64)
+    assert got.shape == (4 * 501, 4)
+    for block, (algo, type_, scheme) in enumerate([(po.NVB_GOTOH, po.NVB_GLOBAL, GOTOH_SW), (po.NVB_GOTOH, po.NVB_SEMI_GLOBAL, GOTOH_SW),
+                                                    (po.NVB_GOTOH, po.NVB_LOCAL, GOTOH_SW), (po.NVB_ED, po.NVB_SEMI_GLOBAL, ())]):
+        s, si, sj = orc.batch(algo, type_, scheme, pats, poffs, texts, toffs)
+        g = got[block * 501:(block + 1) * 501]
+        assert np.array_equal(g[:, 1], s) and np.array_equal(g[:, 2], si) and np.array_equal(g[:, 3], sj), (algo, type_)
