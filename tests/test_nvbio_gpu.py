@@ -217,7 +217,9 @@ def test_cpp_front_end(orc, tmp_path):
     from test_nvbio_oracle import _write_jobs
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     exe = os.path.join(root, "build", "nvb_cpp_example")
-    assert os.path.exists(exe), "run __graft_entry__.build() first"
+    if not os.path.exists(exe):
+        import __graft_entry__ as g
+        g.build_cpp_example()
     pats, poffs, texts, toffs = synth.nvb_jobs(501, 5, 120, 30, 260, seed=44)
     _write_jobs(tmp_path / "jobs.bin", pats, poffs, texts, toffs)
     r = subprocess.run([exe, str(tmp_path / "jobs.bin")], capture_output=True, text=True, timeout=300)
