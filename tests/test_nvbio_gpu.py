@@ -193,10 +193,14 @@ def test_local_sinks_tie_order_and_key_range(orc, algo, scheme):
             p = rng.integers(0, 4, len(p)).astype(np.uint8)
         if k % 7 == 0:
             p = (3 - t[:min(len(t), 40)]).astype(np.uint8)                           # mostly mismatches: score 0 or tiny
+        if k % 11 == 0:                                                              # nothing matches: score 0, the last reported cell (N, M) wins
+            p = np.zeros(int(rng.integers(1, 50)), np.uint8); t = rng.integers(1, 4, int(rng.integers(1, 90))).astype(np.uint8)
         pats.append(p); texts.append(t)
     pb, poffs = nvb.concat(pats); tb, toffs = nvb.concat(texts)
     batch = nvb.Batch(pb, poffs, tb, toffs)
     want, wi, wj = orc.batch(algo, po.NVB_LOCAL, scheme, pb, poffs, tb, toffs)
+    zero = want == 0
+    assert zero.sum() > 50 and np.array_equal(wi[zero], np.diff(toffs)[zero]) and np.array_equal(wj[zero], np.diff(poffs)[zero])
     s, si, sj, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch, want_sinks=True)
     assert k == "s16x2"
     assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
