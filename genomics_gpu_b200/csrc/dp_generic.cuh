@@ -560,7 +560,7 @@ __global__ void __launch_bounds__(128) k_global_generic(const DpArgs a) {
   a.score[tid] = global_forward<START == START_TB>(a, sc, p, tid);
 }
 
-__global__ void __launch_bounds__(128) k_ksw_generic(const DpArgs a) {
+static __global__ void __launch_bounds__(128) k_ksw_generic(const DpArgs a) {
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   PairCtx p; if (!make_ctx(a, tid, p)) return;
   p.cs = a.colstate + 2 * (size_t)tid;                        // int32 pairs: two words per column entry

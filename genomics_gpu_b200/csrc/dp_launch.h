@@ -1,0 +1,67 @@
+// dp_launch.h -- host-side interface between the runtime (engine.cu) and the kernel translation units.
+// Each kernel family is compiled in its own .cu (dp_launch_s16.cu, dp_launch_wave.cu, dp_launch_generic.cu) so that the
+// library builds in parallel; engine.cu only sees these declarations.  Reference dispatcher: Non-CDP/GASAL2/src/gasal_align.h:7-107.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+#include "dp_common.cuh"
+
+namespace gb200 {
+
+// ---- s16x2 fast path (dp_s16.cuh) -----------------------------------------------------------------------------------
+constexpr uint32_t kFastMaxQ8 = 352;      // (q8 + kSlotPad) * 128 * 5 B must fit one CTA's shared memory
+
+struct FastScratch {
+  uint32_t* worklist = nullptr; uint32_t* work_count = nullptr; size_t cap = 0;
+  uint32_t* colstate = nullptr; size_t colstate_words = 0;
+  uint32_t* order = nullptr; size_t order_cap = 0;                 // device-side length binning (k_bin_*): pair permutation
+  uint32_t* bins = nullptr;                                        // histogram / cursors of the binning pass
+  bool attr_set = false;
+  void release() {
+    if (worklist) cudaFree(worklist);
+    if (work_count) cudaFree(work_count);
+    if (colstate) cudaFree(colstate);
+    if (order) cudaFree(order);
+    if (bins) cudaFree(bins);
+    worklist = work_count = colstate = order = bins = nullptr; cap = 0; colstate_words = 0; order_cap = 0;
+  }
+};
+
+bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t);
+// returns the number of kernel launches, or -1 when a scratch allocation failed
+int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, uint32_t min_q, uint32_t min_t, cudaStream_t str);
+
+// ---- intra-task wavefront kernels (dp_wave.cuh) ---------------------------------------------------------------------
+struct WaveScratch {
+  uint64_t* qoff = nullptr; uint64_t* soff = nullptr; size_t n_cap = 0;
+  uint64_t* h_off = nullptr; size_t h_cap = 0;                    // pinned staging: qoff[n] then soff[n]
+  uint4* bnd = nullptr; size_t bnd_cap = 0;
+  uint32_t next_tag = 1;                                          // boundary tags handed out so far (never reused while bnd lives)
+  int2* cand = nullptr; size_t cand_cap = 0;
+  uint32_t* prog = nullptr; size_t prog_cap = 0;                  // done[n], then the ticket counter
+  void release() {
+    if (qoff) cudaFree(qoff);
+    if (h_off) cudaFreeHost(h_off);
+    if (bnd) cudaFree(bnd);
+    if (cand) cudaFree(cand);
+    if (prog) cudaFree(prog);
+    qoff = soff = nullptr; h_off = nullptr; bnd = nullptr; cand = nullptr; prog = nullptr; n_cap = h_cap = bnd_cap = cand_cap = prog_cap = 0;
+  }
+};
+
+bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t);
+bool wave_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t min_q, uint32_t min_t);
+int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uint32_t* h_qlens, const uint32_t* h_tlens,
+                uint32_t max_t, int n_sm, cudaStream_t str, bool* s16_inout = nullptr, bool force_s16 = false);
+
+// ---- general int32 kernels, pack / reverse-complement, traceback walker, CIGAR text (dp_generic.cuh, pack_tb.cuh) -----
+// number of launches, or -1 if the algorithm is not supported
+int generic_launch(const DpArgs& a, int algo, int start, bool second, cudaStream_t str);
+int launch_pack(const uint8_t* uq, uint32_t* pq, uint32_t q_bytes, const uint8_t* ut, uint32_t* pt, uint32_t t_bytes, int n_sm, cudaStream_t str);
+void launch_revcomp(uint32_t* pq, uint32_t* pt, const uint32_t* q_lens, const uint32_t* t_lens, const uint32_t* q_offs, const uint32_t* t_offs,
+                    const uint8_t* q_op, const uint8_t* t_op, uint32_t n, int mode, cudaStream_t str);
+void launch_get_tb(const DpArgs& a, bool is_local, cudaStream_t str);
+void launch_cigar_text(const uint8_t* cigar, const uint32_t* n_cigar_ops, const uint32_t* q_offs, const uint32_t* q_lens, const int32_t* q_start,
+                       const int32_t* q_end, int n, int style, int clip, char* text, uint32_t stride, uint32_t* lens, cudaStream_t str);
+
+}  // namespace gb200

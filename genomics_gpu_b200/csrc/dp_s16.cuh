@@ -21,6 +21,7 @@
 #pragma once
 #include "dp_common.cuh"
 #include "dp_generic.cuh"
+#include "dp_launch.h"
 #include <type_traits>
 #pragma nv_diag_suppress 128   // "loop is not reachable": k_local_s16<START_TB> returns before the score-only sweeps
 
@@ -30,21 +31,8 @@ namespace gb200 {
 #define GB200_FAST_THREADS 128
 #endif
 constexpr int kFastThreads = GB200_FAST_THREADS;
-constexpr uint32_t kFastMaxQ8 = 352;      // (q8 + kSlotPad) * 128 * 5 B must fit one CTA's shared memory
 constexpr uint32_t kSlotPad = 8;          // dummy column slots: 2 below column 0 (late lanes' phantom columns), 6 above the last column
 constexpr uint32_t kFastFallbackSlots = 8192;
-
-struct FastScratch {
-  uint32_t* worklist = nullptr; uint32_t* work_count = nullptr; size_t cap = 0;
-  uint32_t* colstate = nullptr; size_t colstate_words = 0;
-  bool attr_set = false;
-  void release() {
-    if (worklist) cudaFree(worklist);
-    if (work_count) cudaFree(work_count);
-    if (colstate) cudaFree(colstate);
-    worklist = work_count = colstate = nullptr; cap = 0; colstate_words = 0;
-  }
-};
 
 struct FastArgs {
   DpArgs a;
@@ -948,7 +936,7 @@ __global__ void __launch_bounds__(128) k_worklist(const FastArgs fa) {
 __global__ void k_zero_u32(uint32_t* p) { *p = 0; }
 
 // ---- host side --------------------------------------------------------------------------------------
-inline bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
+bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
   if (second || (start == START_TB && algo != ALGO_LOCAL)) return false;
   const uint32_t q8 = (max_q + 7u) & ~7u, t8 = (max_t + 7u) & ~7u;
   if (q8 == 0 || q8 > kFastMaxQ8 || t8 == 0) return false;
@@ -977,8 +965,8 @@ inline bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second
   return false;
 }
 
-inline int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, cudaStream_t str) {
-  (void)max_t;
+int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, uint32_t min_q, uint32_t min_t, cudaStream_t str) {
+  (void)max_t; (void)min_q; (void)min_t;
   const uint32_t q8 = (max_q + 7u) & ~7u;
   if (fs.cap < (size_t)a.n) {
     if (fs.worklist) cudaFree(fs.worklist);

@@ -26,6 +26,7 @@
 #pragma once
 #include "dp_common.cuh"
 #include "dp_generic.cuh"
+#include "dp_launch.h"
 
 namespace gb200 {
 
@@ -812,32 +813,15 @@ inline bool wave16_global_range(const DpArgs& a, uint32_t max_q, uint32_t max_t,
   return true;
 }
 
-inline bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t) {
+bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t) {
   if (algo == ALGO_GLOBAL) { int k, f; return wave16_global_range(a, max_q, max_t, &k, &f); }
   if (algo != ALGO_LOCAL) return false;
   if ((uint64_t)std::min(max_q, max_t) * (uint64_t)a.match > 32000ull) return false;          // scores stay in 16 bits
   return a.gap_open + a.gap_extend + a.mismatch + std::max(0, -a.n_score) < 8000;
 }
 
-// ---- host side ---------------------------------------------------------------------------------------------
-struct WaveScratch {
-  uint64_t* qoff = nullptr; uint64_t* soff = nullptr; size_t n_cap = 0;
-  uint64_t* h_off = nullptr; size_t h_cap = 0;                    // pinned staging: qoff[n] then soff[n]
-  uint4* bnd = nullptr; size_t bnd_cap = 0;
-  uint32_t next_tag = 1;                                          // boundary tags handed out so far (never reused while bnd lives)
-  int2* cand = nullptr; size_t cand_cap = 0;
-  uint32_t* prog = nullptr; size_t prog_cap = 0;                  // done[n], then the ticket counter
-  void release() {
-    if (qoff) cudaFree(qoff);
-    if (h_off) cudaFreeHost(h_off);
-    if (bnd) cudaFree(bnd);
-    if (cand) cudaFree(cand);
-    if (prog) cudaFree(prog);
-    qoff = soff = nullptr; h_off = nullptr; bnd = nullptr; cand = nullptr; prog = nullptr; n_cap = h_cap = bnd_cap = cand_cap = prog_cap = 0;
-  }
-};
-
-inline bool wave_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t min_q, uint32_t min_t) {
+// ---- host side (WaveScratch: dp_launch.h) ----------------------------------------------------------------------
+bool wave_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t min_q, uint32_t min_t) {
   if (second || start == START_TB) return false;
   if (min_q == 0 || min_t == 0) return false;
   if (a.match < 0 || a.match > 127 || a.mismatch < 0 || a.mismatch > 127) return false;
@@ -859,8 +843,8 @@ inline void wave_launch_kernel(int algo, int blocks, const WaveArgs& wa, cudaStr
 
 // h_qlens / h_tlens: the batch's lengths on the host (the caller's pinned arrays).  Returns the number of kernel
 // launches, or -1 when a scratch allocation failed.
-inline int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uint32_t* h_qlens, const uint32_t* h_tlens,
-                       uint32_t max_t, int n_sm, cudaStream_t str, bool* s16_inout = nullptr, bool force_s16 = false) {
+int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uint32_t* h_qlens, const uint32_t* h_tlens,
+                uint32_t max_t, int n_sm, cudaStream_t str, bool* s16_inout, bool force_s16) {
   const size_t n = (size_t)a.n;
   if (ws.h_cap < 2 * n) {
     if (ws.h_off) cudaFreeHost(ws.h_off);

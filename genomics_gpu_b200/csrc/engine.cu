@@ -12,10 +12,7 @@
 #include <cuda_runtime.h>
 #include "../../include/gasal_b200.h"
 #include "dp_common.cuh"
-#include "pack_tb.cuh"
-#include "dp_generic.cuh"
-#include "dp_s16.cuh"
-#include "dp_wave.cuh"
+#include "dp_launch.h"
 
 using namespace gb200;
 
@@ -515,19 +512,12 @@ static void grow_device(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_byt
   }
 }
 
+static int device_sms() { int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); return sms; }
+
 static void launch_pack(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes) {
   Priv* pv = priv(s);
-  const uint32_t n16q = q_bytes / 16, n16t = t_bytes / 16;
-  const uint32_t total = n16q + n16t;
-  if (total) {
-    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const uint32_t blocks = std::min<uint32_t>((total + 255) / 256, (uint32_t)sms * 8);
-    k_pack<<<blocks, 256, 0, s->str>>>((const uint4*)s->unpacked_query_batch, (uint2*)s->packed_query_batch, n16q,
-                                      (const uint4*)s->unpacked_target_batch, (uint2*)s->packed_target_batch, n16t);
-    CHECK_LAUNCH(); pv->launches++;
-  }
-  if (q_bytes & 8) { k_pack_tail<<<1, 1, 0, s->str>>>((const uint2*)(s->unpacked_query_batch + 16 * (size_t)n16q), s->packed_query_batch + 2 * (size_t)n16q); CHECK_LAUNCH(); pv->launches++; }
-  if (t_bytes & 8) { k_pack_tail<<<1, 1, 0, s->str>>>((const uint2*)(s->unpacked_target_batch + 16 * (size_t)n16t), s->packed_target_batch + 2 * (size_t)n16t); CHECK_LAUNCH(); pv->launches++; }
+  pv->launches += gb200::launch_pack(s->unpacked_query_batch, s->packed_query_batch, q_bytes, s->unpacked_target_batch, s->packed_target_batch, t_bytes, device_sms(), s->str);
+  CHECK_LAUNCH();
 }
 
 struct BatchShape { uint32_t max_q, max_t, min_q, min_t; };
@@ -576,13 +566,10 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
 
   // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
   if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
-    const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, s->str);
+    const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, shape.min_q, shape.min_t, s->str);
     if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); }
     CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "s16x2";
-    if (want_tb) {                                                                        // gasal_align.h:45-53
-      const uint32_t nb = (n + 127) / 128;
-      k_get_tb<true><<<nb, 128, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
-    }
+    if (want_tb) { launch_get_tb(a, true, s->str); CHECK_LAUNCH(); pv->launches++; }      // gasal_align.h:45-53
     return;
   }
 
@@ -590,7 +577,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   // policy 0: whenever the batch is too long for the fast path; policy 2: wherever the wavefront kernel is eligible
   if (g_kernel_policy != 1 && wave_eligible(a, params->algo, start, second, shape.min_q, shape.min_t) &&
       (g_kernel_policy >= 2 || q8 > kFastMaxQ8)) {
-    int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int sms = device_sms();
     bool s16 = g_kernel_policy != 3 && wave16_eligible(a, params->algo, shape.max_q, shape.max_t);
     const int nl = wave_launch(a, params->algo, start, pv->wave, s->host_query_batch_lens, s->host_target_batch_lens, shape.max_t, sms, s->str, &s16, g_kernel_policy == 4);
     if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the wavefront scratch\n"); }
@@ -603,38 +590,10 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   const size_t need = (params->algo == KSW) ? 2 * (size_t)stride * (q8 + 16) : (size_t)stride * std::max<uint32_t>(q8, 8);
   if (pv->colstate_words < need) { dev_realloc(&pv->colstate, need); pv->colstate_words = need; }
   a.colstate = pv->colstate; a.col_stride = stride; a.col_rows = q8;
-  const uint32_t BLOCKDIM = 128, N_BLOCKS = (n + BLOCKDIM - 1) / BLOCKDIM;
   pv->last_kernel = "int32";
-  switch (params->algo) {
-    case LOCAL:
-      if (start == WITH_TB) { if (second) k_local_generic<START_TB, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_local_generic<START_TB, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
-      else if (start == WITH_START) { if (second) k_local_generic<START_POS, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_local_generic<START_POS, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
-      else { if (second) k_local_generic<START_NONE, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_local_generic<START_NONE, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
-      CHECK_LAUNCH(); pv->launches++;
-      if (start == WITH_TB) { k_get_tb<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }   // gasal_align.h:45-53
-      break;
-    case SEMI_GLOBAL:
-      if (start == WITH_START) { if (second) k_semiglobal_generic<START_POS, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_semiglobal_generic<START_POS, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
-      else { if (second) k_semiglobal_generic<START_NONE, true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_semiglobal_generic<START_NONE, false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); }
-      CHECK_LAUNCH(); pv->launches++;
-      break;
-    case GLOBAL:
-      if (start == WITH_TB) k_global_generic<START_TB><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); else k_global_generic<START_NONE><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a);
-      CHECK_LAUNCH(); pv->launches++;
-      if (start == WITH_TB) { k_get_tb<false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }   // gasal_align.h:60-68
-      break;
-    case BANDED:
-      if (start == WITH_TB) {
-        k_banded_generic<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
-        k_get_tb<true><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
-      } else { k_banded_generic<false><<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++; }
-      break;
-    case KSW:                                                                             // gasal_align.h:73-78
-      k_ksw_generic<<<N_BLOCKS, BLOCKDIM, 0, s->str>>>(a); CHECK_LAUNCH(); pv->launches++;
-      break;
-    default:
-      GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo);
-  }
+  const int nl = generic_launch(a, params->algo, start, second, s->str);
+  if (nl < 0) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo); }
+  CHECK_LAUNCH(); pv->launches += nl;
 }
 
 static BatchShape scan_shape(const gasal_gpu_storage_t* s, uint32_t n, const Priv* pv, bool have_host_lens) {
@@ -663,9 +622,8 @@ static void device_stage(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_by
   Priv* pv = priv(s);
   if (!params->isPacked) launch_pack(s, q_bytes, t_bytes);                             // gasal_align.cu:190-201
   if (params->isReverseComplement) {                                                    // :232-246
-    const uint32_t warps = 2 * n, blocks = (warps * 32 + 255) / 256;
-    k_revcomp<<<blocks, 256, 0, s->str>>>(s->packed_query_batch, s->packed_target_batch, s->query_batch_lens, s->target_batch_lens,
-                                          s->query_batch_offsets, s->target_batch_offsets, s->query_op, s->target_op, n, g_revcomp_mode);
+    launch_revcomp(s->packed_query_batch, s->packed_target_batch, s->query_batch_lens, s->target_batch_lens,
+                   s->query_batch_offsets, s->target_batch_offsets, s->query_op, s->target_op, n, g_revcomp_mode, s->str);
     CHECK_LAUNCH(); pv->launches++;
   }
   CHECKCUDAERROR(cudaEventRecord(pv->ev[1], s->str));
@@ -800,9 +758,8 @@ int gasalx_cigar_text_async(gasal_gpu_storage_t* s, int style, char* host_text, 
   if (pv->text_bytes < bytes) { dev_realloc(&pv->d_text, bytes); pv->text_bytes = bytes; }
   if (pv->text_lens_cap < n) { dev_realloc(&pv->d_text_lens, n); pv->text_lens_cap = n; }
   const bool local_like = (pv->tb_algo == LOCAL || pv->tb_algo == BANDED);        // start/end cells exist: soft clips
-  k_cigar_text<<<(n + 127) / 128, 128, 0, s->str>>>(pv->d_cigar, pv->d_n_cigar_ops, s->query_batch_offsets, s->query_batch_lens,
-                                                    s->device_cpy->query_batch_start, s->device_cpy->query_batch_end,
-                                                    (int)n, style, local_like ? 1 : 0, pv->d_text, stride, pv->d_text_lens);
+  launch_cigar_text(pv->d_cigar, pv->d_n_cigar_ops, s->query_batch_offsets, s->query_batch_lens, s->device_cpy->query_batch_start,
+                    s->device_cpy->query_batch_end, (int)n, style, local_like ? 1 : 0, pv->d_text, stride, pv->d_text_lens, s->str);
   CHECK_LAUNCH(); pv->launches++;
   CHECKCUDAERROR(cudaMemcpyAsync(host_text, pv->d_text, bytes, cudaMemcpyDeviceToHost, s->str));
   CHECKCUDAERROR(cudaMemcpyAsync(host_lens, pv->d_text_lens, (size_t)n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s->str));
