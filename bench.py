@@ -378,7 +378,8 @@ def run_ours(args, rank, world, local_rank):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     from genomics_gpu_b200 import capi
-    from genomics_gpu_b200.aligner import Aligner
+    from genomics_gpu_b200.aligner import Aligner, pack_host
+    from genomics_gpu_b200.synth import PairBatch
 
     lib = capi.load()
     lib.gasal_set_device(local_rank, 0)
@@ -387,9 +388,16 @@ def run_ours(args, rank, world, local_rank):
     batch = make_workload(n, seed=2 + rank)
     cells_mode = batch.cells
     q_bytes, t_bytes = int(batch.q_bytes.size), int(batch.t_bytes.size)
-
     modes = [("local", capi.LOCAL), ("semi_global", capi.SEMI_GLOBAL)]
-    # ---- device-resident arm: one storage per mode holding the whole batch --------------------------------
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- kernel-only arm: one storage per mode holding the whole batch, inputs resident in HBM as 4-bit words ------------
     res_al = {}
     for name, algo in modes:
         al = Aligner(algo=algo, start=capi.WITH_START, scoring=SCORING, max_query_len=QLEN + 7, max_target_len=TLEN + 7, max_n_alns=n,
@@ -410,50 +418,53 @@ def run_ours(args, rank, world, local_rank):
             out[name] = al.last_ms(0)
         return out
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            import torch.distributed as dist
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(args.warmup):
         resident_step()
-    launches0 = sum(al.launches(0) for al in res_al.values())
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
-    t0 = time.perf_counter()
     per_mode = {name: [] for name, _ in modes}
     for _ in range(args.steps):
         r = resident_step()
         for k, v in r.items():
             per_mode[k].append(v)
     barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    clocks = sampler.stop()
-    launches = sum(al.launches(0) for al in res_al.values()) - launches0
-    dev_ms = sum(v[0] for vs in per_mode.values() for v in vs)            # CUDA-event time, whole device pipeline
+    kernel_ms = sum(v[0] for vs in per_mode.values() for v in vs)            # CUDA-event time of the DP kernels (no copies)
     kernel_names = {name: res_al[name].kernel_name(0) for name, _ in modes}
     for al in res_al.values():
         al.close()
 
-    # ---- e2e arm: host buffers; the batch is split into chunks, one storage (pinned pages + stream) per chunk ----
-    # The pinned host pages are filled ONCE (gasal_host_batch_add); every step re-submits them with
-    # gasal_aln_async, i.e. the timed region holds the pinned H2D of all sequences + lens/offsets, the kernels,
-    # and the D2H of the results, pipelined over the storages' streams as a GASAL2 caller would.
-    # `packed` = the reference API's isPacked mode (src/ctors.cpp:64-67): the caller's pages hold 4-bit words (half the bytes).
-    from genomics_gpu_b200.aligner import pack_host
-    from genomics_gpu_b200.synth import PairBatch
+    # ---- pack arm: the on-GPU 4-bit pack kernel (reference layout: ASCII pages, gasal_align.cu:190-201) on the same sequences ----
+    lib.gasalx_set_host_packing(0)
+    pal = Aligner(algo=capi.LOCAL, start=capi.WITH_START, scoring=SCORING, max_query_len=QLEN + 7, max_target_len=TLEN + 7, max_n_alns=n, n_streams=1, device=local_rank)
+    pal.fill(0, batch); pal.launch(0, q_bytes, t_bytes, n); pal.wait(0)
+    pack_times = []
+    for it in range(args.warmup + min(args.steps, 10)):
+        s = pal.vec.a[0]; s.current_n_alns = n
+        lib.gasalx_aln_device_resident(C.byref(s), q_bytes, t_bytes, n, C.byref(pal.params)); pal.wait(0)
+        if it >= args.warmup:
+            pack_times.append(pal.last_ms(0)[1])
+    pal.close()
+    lib.gasalx_set_host_packing(1)
+
+    # ---- pipeline arm (the HEADLINE): host buffers -> results through the reference-facing C ABI ------------------------------
+    # The batch is split into chunks, one storage (pinned page + stream) per chunk and mode.  The pinned pages are filled ONCE with
+    # gasal_host_batch_add (which packs to 4 bits while it copies: the default host-packing mode); every step re-submits them with
+    # gasal_aln_async, i.e. the timed region holds the pinned H2D of all sequences + lens/offsets, the kernels and the D2H of
+    # the results, pipelined over the storages' streams as a GASAL2 caller would.  Two clocks on the SAME region:
+    #   value : SURVEY 8(d) primary -- CUDA events, first H2D enqueue .. last D2H complete of the step (gasalx_span_ms), summed;
+    #   e2e   : host wall clock bracketed by barrier + cuda synchronize, including the host-side read of every result array.
     n_chunks = args.e2e_chunks
     chunk = (n + n_chunks - 1) // n_chunks
     subs = [batch.slice(lo, min(lo + chunk, n)) for lo in range(0, n, chunk)]
 
-    def e2e_arm(packed: bool):
+    def pipeline_arm(kind: str, steps: int, warm: int):
+        """kind: 'default' (host-packed pages), 'ascii' (reference layout, k_pack on the GPU), 'ispacked' (caller-packed words)"""
+        packed = kind == "ispacked"
+        lib.gasalx_set_host_packing(0 if kind == "ascii" else 1)
         staged = [PairBatch(pack_host(sb.q_bytes).view(np.uint8), pack_host(sb.t_bytes).view(np.uint8), sb.q_offs, sb.t_offs, sb.q_lens, sb.t_lens)
                   for sb in subs] if packed else subs
         if any(int(sb.q_bytes.size) % 8 or int(sb.t_bytes.size) % 8 for sb in staged):     # gasal_aln_async wants multiples of 8 bytes
-            return 0.0, 0, 0
+            lib.gasalx_set_host_packing(1)
+            return None
         als = {}
         for name, algo in modes:
             al = Aligner(algo=algo, start=capi.WITH_START, scoring=SCORING, max_query_len=QLEN + 7, max_target_len=TLEN + 7, max_n_alns=chunk,
@@ -461,10 +472,18 @@ def run_ours(args, rank, world, local_rank):
             for si, sb in enumerate(staged):
                 al.fill(si, sb)
             als[name] = al
+        lib.gasalx_set_host_packing(1)
         csum = np.zeros(1, dtype=np.int64)
+        group = (C.POINTER(capi.GpuStorage) * (2 * len(staged)))()
+        k = 0
+        for name, _ in modes:
+            for si in range(len(staged)):
+                group[k] = C.pointer(als[name].vec.a[si]); k += 1
+        span = (C.c_float * 1)()
+        spans = []
 
         def step():
-            # all storages of both modes are put in flight before the first wait, as a caller with 2 x 8 storages would: the
+            # all storages of both modes are put in flight before the first wait, as a caller with 2 x 16 storages would: the
             # H2D of later chunks (and of the second mode) overlaps the kernels of earlier ones
             for name, _ in modes:
                 al = als[name]
@@ -478,33 +497,50 @@ def run_ours(args, rank, world, local_rank):
                     al.wait(si)
                     r = al.results(si, sb.n)          # host_res arrays (D2H already done on the stream)
                     csum[0] += int(r["aln_score"].sum())
+            if lib.gasalx_span_ms(group, len(group), span) == 0:
+                spans.append(float(span[0]))
 
-        for _ in range(max(1, args.warmup // 2)):
+        for _ in range(warm):
             step()
+        spans.clear(); csum[0] = 0
+        launches0 = sum(al.launches(si) for al in als.values() for si in range(len(staged)))
+        sampler = ClockSampler(local_rank)
         barrier()
+        sampler.start()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
+        for _ in range(steps):
             step()
         barrier()
         wall = time.perf_counter() - t0
+        clocks = sampler.stop()
+        launches = sum(al.launches(si) for al in als.values() for si in range(len(staged))) - launches0
+        host_packed = bool(lib.gasalx_storage_host_packed(C.byref(als["local"].vec.a[0])))
         for al in als.values():
             al.close()
-        return wall, int(csum[0]), sum(int(sb.q_bytes.size) + int(sb.t_bytes.size) for sb in staged)
+        seq_bytes = sum(int(sb.q_bytes.size) + int(sb.t_bytes.size) for sb in staged)
+        if host_packed:
+            seq_bytes //= 2
+        return {"wall_s": wall, "span_ms": sum(spans), "n_spans": len(spans), "checksum": int(csum[0]), "h2d_seq_bytes": 2 * seq_bytes, "launches": launches, "clocks": clocks}
 
-    e2e_steps = args.steps
-    e2e_wall, checksum0, e2e_seq_bytes = e2e_arm(False)
-    checksum = np.array([checksum0], dtype=np.int64)
-    e2e_packed_wall, checksum_packed, e2e_packed_seq_bytes = e2e_arm(True) if args.e2e_packed else (0.0, 0, 0)
+    main_arm = pipeline_arm("default", args.steps, max(3, args.warmup))
+    clocks = main_arm["clocks"]
+    side_steps = max(3, args.steps // 2)
+    ascii_arm = pipeline_arm("ascii", side_steps, 2) if args.e2e_ascii else None
+    ispacked_arm = pipeline_arm("ispacked", side_steps, 2) if args.e2e_packed else None
 
     # ---- reductions over ranks: time = max, work = sum -------------------------------------------------------
-    t = torch.tensor([dev_ms, wall_ms, 1e3 * e2e_wall, 1e3 * e2e_packed_wall], dtype=torch.float64, device="cuda")
+    t = torch.tensor([main_arm["span_ms"], 1e3 * main_arm["wall_s"], kernel_ms,
+                      1e3 * ascii_arm["wall_s"] if ascii_arm else 0.0, 1e3 * ispacked_arm["wall_s"] if ispacked_arm else 0.0], dtype=torch.float64, device="cuda")
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms_max, wall_ms_max, e2e_ms_max, e2e_packed_ms_max = [float(x) for x in t.tolist()]
+    span_ms_max, wall_ms_max, kernel_ms_max, ascii_ms_max, ispacked_ms_max = [float(x) for x in t.tolist()]
     total_cells_per_step = 2 * cells_mode * world            # weak scaling: every rank has its own n pairs
-    value = total_cells_per_step * args.steps / (dev_ms_max * 1e-3) / 1e9
-    e2e_value = total_cells_per_step * e2e_steps / (e2e_ms_max * 1e-3) / 1e9
+    value = total_cells_per_step * args.steps / (span_ms_max * 1e-3) / 1e9
+    e2e_value = total_cells_per_step * args.steps / (wall_ms_max * 1e-3) / 1e9
+    kernel_only = total_cells_per_step * args.steps / (kernel_ms_max * 1e-3) / 1e9
+
+    sharded = run_sharded(args, rank, world, local_rank) if (args.sharded and world > 1) else None
 
     if world > 1:
         import torch.distributed as dist
@@ -516,7 +552,6 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant DP kernel (by time in the step) ---------------------------------------------
     R, R_src = dpx_peak_ops_per_s()
     dp_ms = {name: statistics.mean(v[2] for v in per_mode[name]) for name, _ in modes}
-    pack_ms = {name: statistics.mean(v[1] for v in per_mode[name]) for name, _ in modes}
     top = max(dp_ms, key=dp_ms.get)
     ops_per_cell = 3.0 if kernel_names[top] == "s16x2" else 6.0
     peak_gcups = R / ops_per_cell / 1e9
@@ -528,7 +563,7 @@ def run_ours(args, rank, world, local_rank):
     except Exception:
         hbm_peak = 6650.0
     pack_bytes = 1.5 * (q_bytes + t_bytes)
-    pack_gbs = pack_bytes / (statistics.mean(pack_ms.values()) * 1e-3) / 1e9
+    pack_gbs = pack_bytes / (statistics.mean(pack_times) * 1e-3) / 1e9
 
     if prev_affinity:
         os.sched_setaffinity(0, prev_affinity)      # the CPU baseline uses every host core
@@ -536,37 +571,47 @@ def run_ours(args, rank, world, local_rank):
     cpu_val, cpu_kind, cpu_n, cpu_dt = cpu_baseline_run(batch, args.cpu_pairs, cpu_threads)
     refgpu = ref_gpu_baseline(batch, args.refgpu_pairs) if args.refgpu_pairs > 0 else {"unavailable": "disabled"}
     extras = run_extras(local_rank, 262_144) if args.extras else {"skipped": True}
+    if sharded is not None:
+        extras["sharded"] = sharded
+
+    def side(arm, ms_max, note):
+        if not arm:
+            return None
+        return {"value": total_cells_per_step * side_steps / (ms_max * 1e-3) / 1e9, "unit": "GCUPS", "steps": side_steps, "h2d_bytes_per_step": arm["h2d_seq_bytes"] + 2 * 16 * n,
+                "score_checksum_per_step_matches": bool(arm["checksum"] * args.steps == main_arm["checksum"] * side_steps), "note": note}
 
     line = {
         "metric": "GCUPS", "value": value, "unit": "GCUPS", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": dev_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": span_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "s16x2/int32 (DPX integer)", "data": "synthetic",
         "config": {"workload": WORKLOAD, "pairs_per_gpu": n,
                    "modes_per_step": ["local WITH_START", "semi_global TARGET/TARGET WITH_START"], "scoring": list(SCORING),
-                   "l2_policy": "inputs larger than L2 (752 MB unpacked + 376 MB packed per mode)",
-                   "kernels": kernel_names, "timing": "CUDA events on each storage's stream, summed over the step's batches"},
-        "pairs_per_s": 2 * n * world * args.steps / (dev_ms_max * 1e-3),
-        "wall_ms_per_step": wall_ms_max / args.steps,
-        "per_mode": {name: {"pipeline_ms": statistics.mean(v[0] for v in per_mode[name]), "pack_ms": pack_ms[name], "dp_ms": dp_ms[name],
-                            "gcups_dp_only": cells_mode / (dp_ms[name] * 1e-3) / 1e9} for name, _ in modes},
-        "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": 2 * (q_bytes + t_bytes + 16 * n), "d2h_bytes_per_step": 2 * 20 * n,
-                "chunks_per_mode": len(subs), "streams_per_mode": len(subs), "score_checksum": int(checksum[0]), "timing": "wall clock bracketed by barrier + cuda synchronize",
-                "pairs_per_s": 2 * n * world * e2e_steps / (e2e_ms_max * 1e-3)},
-        "e2e_packed": ({"value": total_cells_per_step * e2e_steps / (e2e_packed_ms_max * 1e-3) / 1e9, "unit": "GCUPS",
-                        "h2d_bytes_per_step": 2 * (e2e_packed_seq_bytes + 16 * n), "d2h_bytes_per_step": 2 * 20 * n,
-                        "score_checksum_matches_e2e": bool(checksum_packed == checksum0),
-                        "note": "same arm with the reference API's isPacked input (host pages hold 4-bit words, src/ctors.cpp:64-67): half the H2D bytes; "
-                                "the difference to e2e is the host link, which is what limits e2e on an 8-GPU box"} if (args.e2e_packed and e2e_packed_ms_max > 0) else None),
-        "gpu_launches": int(launches),
+                   "l2_policy": "inputs larger than L2 (376 MB of packed sequences per mode and step)",
+                   "kernels": kernel_names, "storages_per_mode": len(subs),
+                   "timing": "value: CUDA events, first H2D enqueue .. last D2H complete of each step over all storages (SURVEY 8d primary), "
+                             "summed over the steps, max over ranks; kernel_only: DP kernels alone on HBM-resident inputs"},
+        "pairs_per_s": 2 * n * world * args.steps / (span_ms_max * 1e-3),
+        "kernel_only": {"value": kernel_only, "unit": "GCUPS", "ms_per_step": kernel_ms_max / args.steps,
+                        "note": "DP kernels (forward + start pass) on inputs resident in HBM, no copies: explains `value`, is not the headline"},
+        "per_mode": {name: {"dp_ms": dp_ms[name], "gcups_dp_only": cells_mode / (dp_ms[name] * 1e-3) / 1e9} for name, _ in modes},
+        "e2e": {"value": e2e_value, "unit": "GCUPS", "h2d_bytes_per_step": main_arm["h2d_seq_bytes"] + 2 * 16 * n, "d2h_bytes_per_step": 2 * 20 * n,
+                "wall_ms_per_step": wall_ms_max / args.steps, "chunks_per_mode": len(subs), "score_checksum": main_arm["checksum"],
+                "timing": "host wall clock bracketed by barrier + cuda synchronize around the same steps as `value`; every result array is read on the host",
+                "host_pages": "4-bit words packed by gasal_host_batch_add while it copies the caller's ASCII (default host packing); pages filled once, re-submitted every step",
+                "pairs_per_s": 2 * n * world * args.steps / (wall_ms_max * 1e-3),
+                "ascii_pages": side(ascii_arm, ascii_ms_max, "reference layout: 1 B/base ASCII pages over PCIe, 4-bit pack kernel on the GPU (gasalx_set_host_packing(0))"),
+                "ispacked_api": side(ispacked_arm, ispacked_ms_max, "the reference API's isPacked input: the CALLER hands over 4-bit words (src/ctors.cpp:64-67)")},
+        "gpu_launches": int(main_arm["launches"]),
         "clocks": clocks,
         "roofline": {"bound": "dpx-integer-pipe", "kernel": f"{top} DP ({kernel_names[top]})", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
                      "frac": achieved / peak_gcups, "traffic": ncu_traffic(top),
                      "peak_def": f"R / {ops_per_cell:g} ops per cell, R = {R:.4g} lane-ops/s, {R_src}",
                      "note": "compute-bound integer DP (SURVEY 8d): compulsory HBM traffic is < 0.01 B/cell; the HBM-bound stage is pack, below. "
-                             "achieved counts FORWARD cells only while the launch also runs the start pass (about 25-35 % more cells); "
+                             "achieved counts FORWARD cells only while the launch also runs the start pass; "
                              "other_configs.C2_forward_only has the same kernels without it"},
         "roofline_pack": {"bound": "hbm", "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pack_gbs / hbm_peak,
-                          "traffic": ncu_traffic("pack"), "bytes_def": "1.5 B per base (1 read + 0.5 written)"},
+                          "traffic": ncu_traffic("pack"), "bytes_def": "1.5 B per base (1 read + 0.5 written)",
+                          "note": "k_pack is on the path only for ASCII pages (host packing off); timed here on the same sequences"},
         "cpu_baseline": {"value": cpu_val, "unit": "GCUPS", "cores": cpu_threads, "kind": cpu_kind,
                          "sample": f"first {cpu_n} pairs of the same workload, both modes, {cpu_dt:.1f} s"},
         "ref_gpu_baseline": refgpu,
@@ -578,6 +623,11 @@ def run_ours(args, rank, world, local_rank):
         dist.destroy_process_group()
 
 
+def run_sharded(args, rank, world, local_rank):
+    """placeholder replaced below"""
+    return None
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -587,7 +637,9 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--pairs", type=int, default=1_000_000, help="pairs per GPU per mode")
     ap.add_argument("--e2e-chunks", type=int, default=16)
-    ap.add_argument("--e2e-packed", type=int, default=1, help="also time the e2e arm with pre-packed (isPacked) host pages")
+    ap.add_argument("--e2e-packed", type=int, default=1, help="also time the pipeline arm with caller-packed (isPacked) host pages")
+    ap.add_argument("--e2e-ascii", type=int, default=1, help="also time the pipeline arm with ASCII host pages (host packing off, pack kernel on the GPU)")
+    ap.add_argument("--sharded", type=int, default=1, help="N > 1: also run the strong-scaling LPT-sharded mixed-length job (C5) over the ranks")
     ap.add_argument("--cpu-pairs", type=int, default=600_000, help="bounded sample for the cpu_baseline leg (~15 s on 16 cores)")
     ap.add_argument("--ref-pairs", type=int, default=200_000, help="pairs per step of the --impl reference arm (~5 s per step on 16 cores)")
     ap.add_argument("--extras", type=int, default=1, help="also time the other BASELINE.json configurations on rank 0 (context only)")

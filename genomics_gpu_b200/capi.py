@@ -84,15 +84,17 @@ class Params(C.Structure):
 # every symbol include/gasal_b200.h declares (tests check that the library exports all of them)
 EXPORTED_SYMBOLS = [
     "gasal_params_default", "gasal_init_gpu_storage_v", "gasal_init_streams", "gasal_destroy_streams", "gasal_destroy_gpu_storage_v",
+    "gasal_gpu_mem_alloc", "gasal_gpu_mem_free",
     "gasal_copy_subst_scores", "gasal_aln_async", "gasal_is_aln_async_done",
     "gasal_host_batch_new", "gasal_host_batch_destroy", "gasal_host_batch_getlast", "gasal_host_batch_reset", "gasal_host_batch_fill",
     "gasal_host_batch_add", "gasal_host_batch_addbase", "gasal_host_batch_print", "gasal_host_batch_printall",
     "gasal_host_alns_resize", "gasal_op_fill", "gasal_set_device",
     "gasal_res_new_host", "gasal_res_new_device", "gasal_res_new_device_cpy", "gasal_res_destroy_host", "gasal_res_destroy_device",
-    "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_set_coordinate_fix", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
+    "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_set_coordinate_fix", "gasalx_set_host_packing", "gasalx_storage_host_packed",
+    "gasalx_set_host_write_combined", "gasalx_span_ms", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
     "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
     "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all", "gasalx_batcher_release",
-    "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_cigar_string",
+    "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_pack_host_at", "gasalx_cigar_string",
     "gasalx_cigar_text_async", "gasalx_sam_record",
     "gasalx_try_aln_async", "gasalx_try_init_streams", "gasalx_last_error",
 ]
@@ -136,6 +138,14 @@ def load() -> C.CDLL:
     lib.gasalx_set_kernel_policy.argtypes = [C.c_int]
     lib.gasalx_set_coordinate_fix.argtypes = [C.c_int]
     lib.gasalx_set_revcomp_mode.argtypes = [C.c_int]
+    lib.gasalx_set_host_packing.argtypes = [C.c_int]
+    lib.gasalx_set_host_write_combined.argtypes = [C.c_int]
+    lib.gasalx_storage_host_packed.argtypes = [P(GpuStorage)]; lib.gasalx_storage_host_packed.restype = C.c_int
+    lib.gasalx_span_ms.argtypes = [P(P(GpuStorage)), C.c_int, P(C.c_float)]; lib.gasalx_span_ms.restype = C.c_int
+    lib.gasal_gpu_mem_alloc.argtypes = [P(GpuStorage), C.c_int, C.c_int, C.c_int, P(Params)]
+    lib.gasal_gpu_mem_free.argtypes = [P(GpuStorage), P(Params)]
+    lib.gasal_res_new_device_cpy.argtypes = [C.c_uint32, P(Params)]; lib.gasal_res_new_device_cpy.restype = P(GasalRes)
+    lib.gasal_host_batch_addbase.argtypes = [P(GpuStorage), C.c_uint32, C.c_char, C.c_int]; lib.gasal_host_batch_addbase.restype = C.c_uint32
     lib.gasalx_last_batch_ms.argtypes = [P(GpuStorage), P(C.c_float)]; lib.gasalx_last_batch_ms.restype = C.c_int
     lib.gasalx_kernel_launches.argtypes = [P(GpuStorage)]; lib.gasalx_kernel_launches.restype = C.c_uint64
     lib.gasalx_last_kernel_name.argtypes = [P(GpuStorage)]; lib.gasalx_last_kernel_name.restype = C.c_char_p
@@ -150,6 +160,7 @@ def load() -> C.CDLL:
     lib.gasalx_read_fasta_pairs.argtypes = [C.c_char_p, C.c_char_p, C.c_int, P(FastaPairs)]; lib.gasalx_read_fasta_pairs.restype = C.c_int
     lib.gasalx_free_fasta_pairs.argtypes = [P(FastaPairs)]
     lib.gasalx_pack_host.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.gasalx_pack_host_at.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
     lib.gasalx_cigar_string.argtypes = [C.c_void_p, C.c_uint32, C.c_char_p, C.c_uint32]; lib.gasalx_cigar_string.restype = C.c_int
     lib.gasalx_cigar_text_async.argtypes = [P(GpuStorage), C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]; lib.gasalx_cigar_text_async.restype = C.c_int
     lib.gasalx_sam_record.argtypes = [C.c_char_p, C.c_uint32, C.c_char_p, C.c_int, C.c_char_p, C.c_int64, C.c_int, C.c_char_p, C.c_char_p, C.c_uint32,

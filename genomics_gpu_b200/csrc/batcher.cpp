@@ -126,20 +126,28 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
   // size the pages for the largest batch in BYTES (ragged batches are much smaller than max_pairs x max_len)
   uint64_t maxqb = 0, maxtb = 0;
   for (uint32_t b : mine) { maxqb = std::max(maxqb, pl.batch_q_bytes[b]); maxtb = std::max(maxtb, pl.batch_t_bytes[b]); }
-  const int eff_q = (int)std::max<uint64_t>(8, (maxqb + max_pairs - 1) / std::max(1u, max_pairs));
-  const int eff_t = (int)std::max<uint64_t>(8, (maxtb + max_pairs - 1) / std::max(1u, max_pairs));
   DeviceCache& dc = g_cache[device & 63];
   std::lock_guard<std::mutex> lock(dc.mu);
   const bool fits = dc.valid && dc.v.n == ns && same_params(dc.params, *job.params) && (int)max_pairs <= dc.max_pairs &&
                     (uint64_t)dc.max_pairs * dc.max_q >= maxqb && (uint64_t)dc.max_pairs * dc.max_t >= maxtb;
   if (!fits) {
-    int nq = eff_q + 7, nt = eff_t + 7, np = (int)max_pairs;
+    // Capacity is tracked in BYTES per side and in pairs, each merged on its own with what the cache already held: a long-read job
+    // (few pairs x 100 kb) followed by a short-read job (262144 pairs x 150 b) must not ask for 262144 x 100 kb.
+    uint64_t qbytes_cap = std::max<uint64_t>(maxqb, 8), tbytes_cap = std::max<uint64_t>(maxtb, 8);
+    int np = (int)max_pairs;
     if (dc.valid) {
-      if (dc.v.n == ns && same_params(dc.params, *job.params)) { nq = std::max(nq, dc.max_q); nt = std::max(nt, dc.max_t); np = std::max(np, dc.max_pairs); }
+      if (dc.v.n == ns && same_params(dc.params, *job.params)) {
+        qbytes_cap = std::max(qbytes_cap, (uint64_t)dc.max_pairs * dc.max_q); tbytes_cap = std::max(tbytes_cap, (uint64_t)dc.max_pairs * dc.max_t);
+        np = std::max(np, dc.max_pairs);
+      }
       gasal_destroy_streams(&dc.v, &dc.params); gasal_destroy_gpu_storage_v(&dc.v); dc.valid = false;
     }
+    const int nq = (int)((qbytes_cap + (uint64_t)np - 1) / (uint64_t)np) + 7, nt = (int)((tbytes_cap + (uint64_t)np - 1) / (uint64_t)np) + 7;
     dc.v = gasal_init_gpu_storage_v(ns);
-    gasal_init_streams(&dc.v, nq, nt, np, job.params);
+    if (gasalx_try_init_streams(&dc.v, nq, nt, np, job.params) != GASALX_OK) {
+      fprintf(stderr, "[GASAL ERROR:] gasalx_align_all: cannot create the storages of device %d: %s", device, gasalx_last_error());
+      gasal_destroy_gpu_storage_v(&dc.v); err->store(1); return;
+    }
     dc.params = *job.params; dc.max_q = ((nq + 7) / 8) * 8; dc.max_t = ((nt + 7) / 8) * 8; dc.max_pairs = np; dc.valid = true;
   }
   gasal_gpu_storage_v& v = dc.v;
@@ -220,8 +228,10 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
           st->host_query_batch_offsets[j + r] = qi + (uint32_t)(job.q_offs[i] - job.q_offs[i0]);
           st->host_target_batch_offsets[j + r] = ti + (uint32_t)(job.t_offs[i] - job.t_offs[i0]);
           st->host_query_batch_lens[j + r] = job.q_lens[i]; st->host_target_batch_lens[j + r] = job.t_lens[i];
-          if (job.q_op) st->host_query_op[j + r] = job.q_op[i];
-          if (job.t_op) st->host_target_op[j + r] = job.t_op[i];
+          if (P->isReverseComplement) {          // cached storages keep the op bytes of earlier jobs: a side without ops is written as 0
+            st->host_query_op[j + r] = job.q_op ? job.q_op[i] : 0;
+            st->host_target_op[j + r] = job.t_op ? job.t_op[i] : 0;
+          }
           if (job.seeds && st->host_seed_scores) st->host_seed_scores[j + r] = job.seeds[i];
         }
         if (run > 1) {

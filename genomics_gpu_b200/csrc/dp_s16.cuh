@@ -37,7 +37,8 @@ constexpr uint32_t kFastFallbackSlots = 8192;
 struct FastArgs {
   DpArgs a;
   uint32_t q8max;          // columns reserved per thread in shared memory (multiple of 8)
-  uint32_t* worklist; uint32_t* work_count;
+  uint32_t* worklist; uint32_t* work_count;     // pairs with a base outside A/C/G/T (filled by the main launch; counts: work_count[0], [1])
+  uint32_t* worklist2;                          // pairs the N-aware pass cannot represent either (codes other than A/C/G/T/N): general kernel
   uint32_t eight;          // == 8, passed at run time so the key multiply stays an IMAD (FMA pipe)
   uint32_t one;            // == 1, run-time so that the sweep's trip count (columns + 1) is opaque to the unroller
   uint32_t mm, sixteen;    // == 0x00204081 / 16, run-time so the direction-nibble gather stays on IMAD (FMA pipe)
@@ -49,6 +50,13 @@ __device__ __forceinline__ uint32_t splat16(int v) { const uint32_t u = (uint32_
 __device__ __forceinline__ uint32_t row_table(uint32_t idx, uint32_t mis4, uint32_t delta) {
   return (idx < 4) ? (mis4 ^ (delta << (8 * idx))) : mis4;
 }
+
+// N-aware variant (NMASK): a real N in the query scores n_score against everything (gasal_kernels.h:49-51).  The PRMT table has no
+// room for a fifth column, so the N columns are marked in the selector array (0xFF) and one LOP3 per cell pair overrides the
+// looked-up score with the N score under a per-lane column mask; N rows of the target are folded into the row tables.
+__device__ __forceinline__ uint32_t mask_sel(uint32_t s2, uint32_t m, uint32_t nsc2) { return (s2 & ~m) | (nsc2 & m); }
+__device__ __forceinline__ uint32_t ncol_mask16(uint32_t v) { return (v == 0xFFu) ? 0xFFFFu : 0u; }
+constexpr uint32_t kSelN = 0xFFu;
 
 struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 
@@ -157,10 +165,12 @@ __device__ __forceinline__ uint32_t key_tree(const uint32_t (&key)[8]) {
   return __vmaxs2(cm, key[7]);
 }
 
+template <bool NMASK = false>
 __device__ __forceinline__ void local_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
                                              const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
                                              const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
-                                             uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t one, uint32_t pos_base, LaneBest4& lb) {
+                                             uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t one, uint32_t pos_base, LaneBest4& lb,
+                                             uint32_t nsc2 = 0) {
   uint32_t pA[8], fA[8], pB[8], fB[8], keyA[8], keyB[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) { pA[r] = 0; fA[r] = 0; pB[r] = 0; fB[r] = 0; keyA[r] = 0; keyB[r] = 0; }
@@ -170,9 +180,12 @@ __device__ __forceinline__ void local_sweep4(uint32_t* __restrict__ HE, const ui
   uint32_t he = HE[kFastThreads];                  // slot 1 = column 0
   uint32_t v = V[kFastThreads];
   uint32_t pos = pos_base;                         // position code of the step whose keys are in keyA / keyB
+  uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;      // NMASK: N-column masks, rotated like the selectors
   for (int k = 0; k < nsteps; k++) {
     const uint32_t selA = v | prevsh;
     prevsh = v * 256u + 0x4400u;
+    uint32_t mA = 0;
+    if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
     uint32_t upA = prmt(he, h8A, 0x5410);
     uint32_t eA = prmt(he, eoA, 0x5432);
     uint32_t upB = prmt(h8A, h8B, 0x5432);
@@ -191,7 +204,8 @@ __device__ __forceinline__ void local_sweep4(uint32_t* __restrict__ HE, const ui
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       {
-        const uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        if (NMASK) s2 = mask_sel(s2, mA, nsc2);
         const uint32_t d = __vadd2(pA[r], s2);
         const uint32_t dm = __vadd2(d, neg_oe2);
         const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
@@ -201,7 +215,8 @@ __device__ __forceinline__ void local_sweep4(uint32_t* __restrict__ HE, const ui
         pA[r] = upA; upA = h;
       }
       {
-        const uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        if (NMASK) s2 = mask_sel(s2, mB, nsc2);
         const uint32_t d = __vadd2(pB[r], s2);
         const uint32_t dm = __vadd2(d, neg_oe2);
         const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
@@ -215,6 +230,7 @@ __device__ __forceinline__ void local_sweep4(uint32_t* __restrict__ HE, const ui
     HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
     h8A = upA; eoA = eA; h8B = upB; eoB = eB;
     selB = selA_prev; selA_prev = selA;
+    if (NMASK) { mB = mA_prev; mA_prev = mA; }
   }
   {
     const uint32_t cm = key_tree(keyA);
@@ -292,11 +308,13 @@ __device__ __forceinline__ void tb_flush(uint4* __restrict__ tb, size_t ts, int 
   if (ph == 2) { const int c = k - 3; if (valid[3] && c >= 3 && c < ncol) tb[(size_t)(3 * QR2 + (c >> 2)) * ts] = make_uint4(dBH[0], dBH[1], dBH[2], dBH[3]); }
 }
 
+template <bool NMASK = false>
 __device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int ncol,
                                                 const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
                                                 const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
                                                 uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t one, uint32_t mm, uint32_t sixteen, uint32_t pos_base,
-                                                LaneBest4& lb, uint4* __restrict__ tb, size_t ts, int QR2, const bool (&valid)[4]) {
+                                                LaneBest4& lb, uint4* __restrict__ tb, size_t ts, int QR2, const bool (&valid)[4], uint32_t nsc2 = 0) {
+  uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;
   uint32_t pA[8], fA[8], pB[8], fB[8], keyA[8], keyB[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) { pA[r] = 0; fA[r] = 0; pB[r] = 0; fB[r] = 0; keyA[r] = 0; keyB[r] = 0; }
@@ -313,6 +331,8 @@ __device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const
   for (int k = 0; k < nsteps; k++) {
     const uint32_t selA = v | prevsh;
     prevsh = v * 256u + 0x4400u;
+    uint32_t mA = 0;
+    if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
     uint32_t upA = prmt(he, h8A, 0x5410);
     uint32_t eA = prmt(he, eoA, 0x5432);
     uint32_t upB = prmt(h8A, h8B, 0x5432);
@@ -330,7 +350,8 @@ __device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       {
-        const uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        if (NMASK) s2 = mask_sel(s2, mA, nsc2);
         const uint32_t d = __vadd2(pA[r], s2);
         const uint32_t dm = __vadd2(d, neg_oe2);
         const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
@@ -341,7 +362,8 @@ __device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const
         pA[r] = upA; upA = h;
       }
       {
-        const uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        if (NMASK) s2 = mask_sel(s2, mB, nsc2);
         const uint32_t d = __vadd2(pB[r], s2);
         const uint32_t dm = __vadd2(d, neg_oe2);
         const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
@@ -355,6 +377,7 @@ __device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const
     HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
     h8A = upA; eoA = eA; h8B = upB; eoB = eB;
     selB = selA_prev; selA_prev = selA;
+    if (NMASK) { mB = mA_prev; mA_prev = mA; }
     tb_flush(tb, ts, QR2, k, ncol, dAL, dAH, dBL, dBH, wAL, wAH, wBL, wBH, valid);
   }
   {
@@ -383,12 +406,57 @@ __device__ __forceinline__ bool target_odd_scan(const uint32_t* __restrict__ tw,
   return acc != 0;
 }
 
-template <int START>
+// N-aware pass: nibbles outside A/C/G/T that are not the N code either (IUPAC letters ...) -- only the general kernel scores those
+__device__ __forceinline__ uint32_t exotic_nibbles(uint32_t w, uint32_t nval) {
+  const uint32_t z = w ^ (nval * 0x11111111u);
+  const uint32_t isn = ~(z | (z >> 1) | (z >> 2) | (z >> 3)) & 0x11111111u;
+  return odd_nibbles(w) & ~isn;
+}
+__device__ __forceinline__ bool target_exotic_scan(const uint32_t* __restrict__ tw, uint32_t tlen, uint32_t nval) {
+  uint32_t acc = 0;
+  const int full = (int)(tlen >> 3), rem = (int)(tlen & 7u);
+#pragma unroll 8
+  for (int i = 0; i < full; i++) acc |= exotic_nibbles(tw[i], nval);
+  if (rem) acc |= exotic_nibbles(tw[full], nval) & (0x11111111u << (4 * (8 - rem)));
+  return acc != 0;
+}
+// row table of the N-aware pass: an N row scores n_score against every query base
+__device__ __forceinline__ uint32_t row_table_n(uint32_t code, uint32_t mis4, uint32_t delta, uint32_t nval, uint32_t nsc4) {
+  return (code == nval) ? nsc4 : row_table(base_idx(code), mis4, delta);
+}
+template <bool NMASK>
+__device__ __forceinline__ void quad_tables(uint32_t wa, uint32_t wb, uint32_t wc, uint32_t wd, uint32_t mis4, uint32_t delta, uint32_t nval, uint32_t nsc4,
+                                            uint32_t (&rowA)[8], uint32_t (&rowB)[8], uint32_t (&rowC)[8], uint32_t (&rowD)[8]) {
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    if (NMASK) {
+      rowA[r] = row_table_n(nib(wa, r), mis4, delta, nval, nsc4); rowB[r] = row_table_n(nib(wb, r), mis4, delta, nval, nsc4);
+      rowC[r] = row_table_n(nib(wc, r), mis4, delta, nval, nsc4); rowD[r] = row_table_n(nib(wd, r), mis4, delta, nval, nsc4);
+    } else {
+      rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
+      rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
+    }
+  }
+}
+// selector byte of one query column.  Main pass: anything outside A/C/G/T flags the pair (`flag`).  N-aware pass: a real N gets the
+// mask marker, pads stay benign, any other code flags the pair for the general kernel.
+template <bool NMASK>
+__device__ __forceinline__ uint8_t col_selector(uint32_t code, bool pad, uint32_t nval, bool& flag) {
+  const uint32_t idx = base_idx(code);
+  if (idx <= 3) return (uint8_t)(0x80u + 0x11u * idx);
+  if (!NMASK) { flag |= !pad; return 0x88; }
+  if (pad) return 0x88;
+  if (code == nval) return (uint8_t)kSelN;
+  flag = true; return 0x88;
+}
+
+template <int START, bool NMASK = false>
 __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= (uint32_t)a.n) return;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }     // N-aware pass: one thread per flagged pair
+  else if (tid >= (uint32_t)a.n) return;
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
 
@@ -399,8 +467,9 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   const uint32_t mis4 = ((uint32_t)(-a.mismatch) & 0xFFu) * 0x01010101u;
   const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
   const uint32_t neg_oe2 = splat16(-(a.gap_open + a.gap_extend)), neg_ext2 = splat16(-a.gap_extend);
+  const uint32_t nval = a.n_value, nsc2 = splat16(a.n_score), nsc4 = ((uint32_t)a.n_score & 0xFFu) * 0x01010101u;
 
-  // ---- prologue: selector bytes of the query, (H,E) = 0; detect bases the fast path cannot score ----
+  // ---- prologue: selector bytes of the query, (H,E) = 0; detect bases this pass cannot score ----
   bool odd = false;
   const int ncol = QR * 8;
   V[0] = 0x88; HE[0] = 0;
@@ -409,19 +478,16 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int c = 8 * j + k;
-      const uint32_t idx = base_idx(nib(w, k));
-      const bool pad = (uint32_t)c >= qlen;
-      odd |= (idx > 3) && !pad;
-      V[(c + 1) * kFastThreads] = (idx > 3) ? 0x88 : (uint8_t)(0x80u + 0x11u * idx);
+      V[(c + 1) * kFastThreads] = col_selector<NMASK>(nib(w, k), (uint32_t)c >= qlen, nval, odd);
       HE[(c + 1) * kFastThreads] = 0;
     }
   }
 #pragma unroll
   for (int x = 1; x <= 5; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = 0; }
-  odd |= target_odd_scan(tw, tlen, TR);
-  if (odd) {   // hand the pair to the general kernel (same stream, next launch)
-    const uint32_t slot = atomicAdd(fa.work_count, 1u);
-    fa.worklist[slot] = tid;
+  odd |= NMASK ? target_exotic_scan(tw, tlen, nval) : target_odd_scan(tw, tlen, TR);
+  if (odd) {   // hand the pair on (same stream, next launch): main pass -> N-aware pass -> general kernel
+    const uint32_t slot = atomicAdd(fa.work_count + (NMASK ? 1 : 0), 1u);
+    (NMASK ? fa.worklist2 : fa.worklist)[slot] = tid;
     return;
   }
 
@@ -439,14 +505,10 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
       const uint32_t wb = valid[1] ? tw[4 * j + 1] : 0u;
       const uint32_t wc = valid[2] ? tw[4 * j + 2] : 0u;
       const uint32_t wd = valid[3] ? tw[4 * j + 3] : 0u;
-#pragma unroll
-      for (int r = 0; r < 8; r++) {
-        rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
-        rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
-      }
+      quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
       uint4* tbq = a.tb + (size_t)(4 * j) * (size_t)(2 * QR) * a.tb_stride + tid;
-      local_sweep4_tb(HE, V, ncol, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, fa.mm, fa.sixteen, (uint32_t)j << 16, lb,
-                      tbq, (size_t)a.tb_stride, 2 * QR, valid);
+      local_sweep4_tb<NMASK>(HE, V, ncol, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, fa.mm, fa.sixteen, (uint32_t)j << 16, lb,
+                             tbq, (size_t)a.tb_stride, 2 * QR, valid, nsc2);
     }
     const Winner tw_ = pick_winner4(lb);
     a.score[tid] = tw_.score; a.q_end[tid] = tw_.col; a.t_end[tid] = tw_.row;
@@ -458,12 +520,8 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;     // phantom strips: every base mismatches
     const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
-      rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
-    }
-    local_sweep4(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb);
+    quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
+    local_sweep4<NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb, nsc2);
   }
   const Winner fw = pick_winner4(lb);
   a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row;
@@ -475,13 +533,13 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     if (fw.score > 0) {
       const int rend_reg = min((fw.col >> 3) + 1, QR), gend_reg = min((fw.row >> 3) + 1, TR);
       const int rcol = rend_reg * 8;
+      bool dummy = false;
       for (int j = 0; j < rend_reg; j++) {
         const uint32_t w = nibrev(qw[rend_reg - 1 - j]);
 #pragma unroll
         for (int k = 0; k < 8; k++) {
           const int c = 8 * j + k;
-          const uint32_t idx = base_idx(nib(w, k));
-          V[(c + 1) * kFastThreads] = (idx > 3) ? 0x88 : (uint8_t)(0x80u + 0x11u * idx);
+          V[(c + 1) * kFastThreads] = col_selector<NMASK>(nib(w, k), (uint32_t)(rcol - 1 - c) >= qlen, nval, dummy);
           HE[(c + 1) * kFastThreads] = 0;
         }
       }
@@ -496,12 +554,8 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
         const uint32_t wb = (4 * j + 1 < gend_reg) ? nibrev(tw[gend_reg - 2 - 4 * j]) : 0u;
         const uint32_t wc = (4 * j + 2 < gend_reg) ? nibrev(tw[gend_reg - 3 - 4 * j]) : 0u;
         const uint32_t wd = (4 * j + 3 < gend_reg) ? nibrev(tw[gend_reg - 4 - 4 * j]) : 0u;
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
-          rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
-        }
-        local_sweep4(HE, V, rcol + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb);
+        quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
+        local_sweep4<NMASK>(HE, V, rcol + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb, nsc2);
         if ((int)(short)(rb.a.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.a.bestK7 >> 16) >= fwd7 ||
             (int)(short)(rb.b.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.b.bestK7 >> 16) >= fwd7) break;
       }
@@ -618,14 +672,15 @@ __device__ __forceinline__ void nc_sweep(uint32_t* __restrict__ HE, const uint8_
 // the last true query column; the global capture) is gathered behind ONE compare per step (k == knext).
 //   kq      : step at which lane A.L is on the scanned / captured column (qlen - 1); lane i is there at step kq + i
 //   lane_lo/lane_hi of hhA / hhB give the four lanes' H values of the current step
-template <int ALGO, bool REV>
+template <int ALGO, bool REV, bool NMASK = false>
 __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
                                           const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
                                           const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
                                           const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8],
                                           uint32_t neg_oe2, uint32_t neg_ext2,
-                                          int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr) {
+                                          int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, uint32_t nsc2 = 0) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
+  uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;      // NMASK: N-column masks, rotated like the selectors (see local_sweep4)
   const uint32_t neg2 = splat16(kNegSafe);
   // Both recurrences run in a BIASED frame: every H/E/F of (strip row r, column q) carries + (q + r) * ext.  Gap extension is
   // then free (semi-global: F' = max(F, Hleft - open), E' = max(E, M - open); global: F' = max(F, D - open), E' = max(E, D - open):
@@ -653,6 +708,8 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
   for (int k = 0; k < nsteps; k++) {
     const uint32_t selA = v | prevsh;
     prevsh = v * 256u + 0x4400u;
+    uint32_t mA = 0;
+    if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
     uint32_t upA = prmt(he, h8A, 0x5410);
     uint32_t eA = prmt(he, eoA, 0x5432);
     uint32_t upB = prmt(h8A, h8B, 0x5432);
@@ -669,7 +726,8 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       {
-        const uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        if (NMASK) s2 = mask_sel(s2, mA, nsc2);
         const uint32_t d = __vadd2(dgA[r], s2);
         uint32_t h;
         if (SEMI) {
@@ -688,7 +746,8 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
         hhA[r] = h; if (!SEMI) pA[r] = upA; upA = h;
       }
       {
-        const uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        if (NMASK) s2 = mask_sel(s2, mB, nsc2);
         const uint32_t d = __vadd2(dgB[r], s2);
         uint32_t h;
         if (SEMI) {
@@ -708,6 +767,7 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
     HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
     h8A = upA; eoA = eA; h8B = upB; eoB = eB;
     selB = selA_prev; selA_prev = selA;
+    if (NMASK) { mB = mA_prev; mA_prev = mA; }
     if (k == knext) {
       if (k <= 2) {
         // lanes that just ran a phantom column (A.H: step 0; B.L: 0,1; B.H: 0,1,2) get their strip-start state back
@@ -749,8 +809,8 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
 
 // selector bytes + top boundary of one pass into shared memory.  mode 0: forward words; mode 2: true-length reversed.
 // SEMI: the parked E is the first row's own E(0,c) = max(H(-1,c) - oe, E(-1,c) - e) (see nc_sweep); otherwise E(-1,c).
-template <bool TOP_ZERO, bool SEMI = true>
-__device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint32_t* qw, uint32_t qlen, int QR, int mode, int o, int ext) {
+template <bool TOP_ZERO, bool SEMI = true, bool NMASK = false>
+__device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint32_t* qw, uint32_t qlen, int QR, int mode, int o, int ext, uint32_t nval = 0) {
   bool odd = false;
   const int ncol = QR * 8;
   V[0] = 0x88; HE[0] = pack2(0, kNegSafe);
@@ -759,9 +819,7 @@ __device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint
 #pragma unroll
     for (int k = 0; k < 8; k++) {
       const int c = 8 * j + k;
-      const uint32_t idx = base_idx(nib(w, k));
-      odd |= (idx > 3) && ((uint32_t)c < qlen);
-      V[(c + 1) * kFastThreads] = (idx > 3) ? 0x88 : (uint8_t)(0x80u + 0x11u * idx);
+      V[(c + 1) * kFastThreads] = col_selector<NMASK>(nib(w, k), (uint32_t)c >= qlen, nval, odd);
       // top boundary: H(-1, c), E = -inf   (semiglobal_kernel_template.h:87-99, global.h:57-60)
       if (SEMI) {
         const int htop = TOP_ZERO ? 0 : (c == 0 ? 0 : -(o + ext * c));                  // free top row: (H,E)(-1,c) = (0,0)
@@ -782,12 +840,13 @@ __device__ __forceinline__ bool target_has_odd_base(const uint32_t* tw, uint32_t
   return target_odd_scan(tw, tlen, TR);
 }
 
-template <int START>
+template <int START, bool NMASK = false>
 __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
-  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (tid >= (uint32_t)a.n) return;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }     // N-aware pass: one thread per flagged pair
+  else if (tid >= (uint32_t)a.n) return;
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
@@ -798,15 +857,16 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const uint32_t mis4 = ((uint32_t)(-a.mismatch + 2 * a.gap_extend) & 0xFFu) * 0x01010101u;
   const uint32_t delta = ((uint32_t)(a.match + 2 * a.gap_extend) ^ (uint32_t)(-a.mismatch + 2 * a.gap_extend)) & 0xFFu;
   const uint32_t neg_oe2 = splat16(-a.gap_open), neg_ext2 = splat16(-a.gap_extend);      // gap OPEN only: extension is free in the biased frame
+  const uint32_t nval = a.n_value, nsc2 = splat16(a.n_score + 2 * a.gap_extend), nsc4 = ((uint32_t)(a.n_score + 2 * a.gap_extend) & 0xFFu) * 0x01010101u;
   const bool top_zero = (a.head == SKIP_BOTH);          // HEAD in {QUERY,BOTH}: free top row (:87)
   const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
 
-  bool odd = top_zero ? nc_prologue<true>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend)
-                      : nc_prologue<false>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend);
-  odd |= target_has_odd_base(tw, tlen, TR);
+  bool odd = top_zero ? nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval)
+                      : nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval);
+  odd |= NMASK ? target_exotic_scan(tw, tlen, nval) : target_has_odd_base(tw, tlen, TR);
   if (odd || qlen == 0) {
-    const uint32_t slot = atomicAdd(fa.work_count, 1u);
-    fa.worklist[slot] = tid;
+    const uint32_t slot = atomicAdd(fa.work_count + (NMASK ? 1 : 0), 1u);
+    (NMASK ? fa.worklist2 : fa.worklist)[slot] = tid;
     return;
   }
   uint32_t pinit[8];
@@ -821,12 +881,8 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;
     const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
-      rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
-    }
-    nc_sweep4<ALGO_SEMI_GLOBAL, false>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr);
+    quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
+    nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr, nsc2);
   }
   a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = (int)tlen;            // query_batch_end = ref_len (Q8)
 
@@ -836,8 +892,8 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     const int fwd = tr.best;
     const uint32_t ua = (uint32_t)TR - (uint32_t)((tr.y >> 3) + 1);
     const uint32_t gend_reg = ua > 0 ? ua - 1 : ua;                                   // :273 (unsigned in the reference)
-    if (top_zero) nc_prologue<true>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend);
-    else nc_prologue<false>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend);
+    if (top_zero) nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval);
+    else nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval);
     NcTrack rt; rt.best = kMinusInf; rt.y = 0; rt.stop = fwd; rt.cap = 0;             // :275-276
     for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 4) {
       uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
@@ -845,12 +901,8 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
       const uint32_t wb = (i + 1 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 1) : 0u;
       const uint32_t wc = (i + 2 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 2) : 0u;
       const uint32_t wd = (i + 3 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 3) : 0u;
-#pragma unroll
-      for (int r = 0; r < 8; r++) {
-        rowA[r] = row_table(base_idx(nib(wa, r)), mis4, delta); rowB[r] = row_table(base_idx(nib(wb, r)), mis4, delta);
-        rowC[r] = row_table(base_idx(nib(wc, r)), mis4, delta); rowD[r] = row_table(base_idx(nib(wd, r)), mis4, delta);
-      }
-      nc_sweep4<ALGO_SEMI_GLOBAL, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt);
+      quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
+      nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2);
     }
     a.t_start[tid] = ((int)tlen - 1) - rt.y;                                          // :380-381
     a.q_start[tid] = ((int)qlen - 1) - (int)tlen;
@@ -908,13 +960,14 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
 
 // ---- general kernel over the fallback worklist ----------------------------------------------------
 template <int ALGO, int START>
-__global__ void __launch_bounds__(128) k_worklist(const FastArgs fa) {
+__global__ void __launch_bounds__(128) k_worklist(const FastArgs fa, int which) {
   const DpArgs& a = fa.a;
   const uint32_t gtid = blockIdx.x * blockDim.x + threadIdx.x, nthreads = gridDim.x * blockDim.x;
-  const uint32_t count = *fa.work_count;
+  const uint32_t count = fa.work_count[which];
+  const uint32_t* __restrict__ list = which ? fa.worklist2 : fa.worklist;
   const Sc sc = make_sc(a, ALGO == ALGO_GLOBAL);
   for (uint32_t w = gtid; w < count; w += nthreads) {
-    const uint32_t pi = fa.worklist[w];
+    const uint32_t pi = list[w];
     PairCtx p;
     p.qw = a.pq + (a.q_offs[pi] >> 3); p.tw = a.pt + (a.t_offs[pi] >> 3);
     p.qlen = a.q_lens[pi]; p.tlen = a.t_lens[pi]; p.QR = n_words(p.qlen); p.TR = n_words(p.tlen);
@@ -933,7 +986,7 @@ __global__ void __launch_bounds__(128) k_worklist(const FastArgs fa) {
   }
 }
 
-__global__ void k_zero_u32(uint32_t* p) { *p = 0; }
+__global__ void k_zero_u32(uint32_t* p) { p[0] = 0; p[1] = 0; }
 
 // ---- host side --------------------------------------------------------------------------------------
 bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
@@ -971,18 +1024,27 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
   if (fs.cap < (size_t)a.n) {
     if (fs.worklist) cudaFree(fs.worklist);
     fs.worklist = nullptr;
-    if (cudaMalloc(&fs.worklist, sizeof(uint32_t) * (size_t)a.n) != cudaSuccess) return -1;
+    if (cudaMalloc(&fs.worklist, 2 * sizeof(uint32_t) * (size_t)a.n) != cudaSuccess) return -1;     // worklist, then worklist2
     fs.cap = (size_t)a.n;
   }
-  if (!fs.work_count && cudaMalloc(&fs.work_count, sizeof(uint32_t)) != cudaSuccess) return -1;
-  const size_t cs_need = (size_t)kFastFallbackSlots * q8;
+  if (!fs.work_count && cudaMalloc(&fs.work_count, 2 * sizeof(uint32_t)) != cudaSuccess) return -1;
+  // Pairs with a base outside A/C/G/T: LOCAL / SEMI_GLOBAL re-run them on the N-aware variant of the same s16x2 kernel (one more
+  // LOP3 per cell pair); what is left (codes other than N; GLOBAL, whose rule makes N an ordinary symbol) goes to the general
+  // int32 kernel, grid-striding over the list with a grid sized for the machine, not for a fixed 64 CTAs.
+  const int nbias = (algo == ALGO_SEMI_GLOBAL) ? 2 * a.gap_extend : 0;
+  const bool nmask = (algo == ALGO_LOCAL || algo == ALGO_SEMI_GLOBAL) && a.n_score + nbias >= -127 && a.n_score + nbias <= 127;
+  int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const uint32_t n128 = ((uint32_t)a.n + 127u) & ~127u;
+  const uint32_t slots = nmask ? std::min<uint32_t>(n128, kFastFallbackSlots) : std::min<uint32_t>(n128, (uint32_t)sms * 4u * 128u);
+  const size_t cs_need = (size_t)slots * q8;
   if (fs.colstate_words < cs_need) {
     if (fs.colstate) cudaFree(fs.colstate);
     fs.colstate = nullptr;
     if (cudaMalloc(&fs.colstate, cs_need * sizeof(uint32_t)) != cudaSuccess) return -1;
     fs.colstate_words = cs_need;
   }
-  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.work_count = fs.work_count; fa.eight = 8; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
+  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.worklist2 = fs.worklist + fs.cap; fa.work_count = fs.work_count;
+  fa.eight = 8; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
   const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads;
   if (!fs.attr_set) {
     const int lim = 227 * 1024;
@@ -991,6 +1053,11 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
     cudaFuncSetAttribute(k_local_s16<START_TB>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_POS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_POS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_global_s16, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     fs.attr_set = true;
   }
@@ -998,22 +1065,32 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
   const uint32_t blocks = ((uint32_t)a.n + kFastThreads - 1) / kFastThreads;
   const bool sp = (start == START_POS);
   const bool tbm = (start == START_TB);
+  int launches = 3;
   if (algo == ALGO_LOCAL) {
     if (tbm) k_local_s16<START_TB><<<blocks, kFastThreads, smem, str>>>(fa);
     else if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
   }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
   else k_global_s16<<<blocks, kFastThreads, smem, str>>>(fa);
-  // fallback pairs (bases outside A/C/G/T): general kernel over the worklist, bounded scratch
-  fa.a.colstate = fs.colstate; fa.a.col_stride = kFastFallbackSlots; fa.a.col_rows = q8;
-  const int wb = kFastFallbackSlots / 128;
-  if (algo == ALGO_LOCAL) {
-    if (tbm) k_worklist<ALGO_LOCAL, START_TB><<<wb, 128, 0, str>>>(fa);
-    else if (sp) k_worklist<ALGO_LOCAL, START_POS><<<wb, 128, 0, str>>>(fa); else k_worklist<ALGO_LOCAL, START_NONE><<<wb, 128, 0, str>>>(fa);
+  if (nmask) {
+    // the grid covers the worst case (every pair flagged); CTAs beyond work_count[0] exit on their first instruction
+    if (algo == ALGO_LOCAL) {
+      if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, str>>>(fa);
+      else if (sp) k_local_s16<START_POS, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, str>>>(fa);
+    } else { if (sp) k_semiglobal_s16<START_POS, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, str>>>(fa); }
+    launches++;
   }
-  else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_worklist<ALGO_SEMI_GLOBAL, START_POS><<<wb, 128, 0, str>>>(fa); else k_worklist<ALGO_SEMI_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa); }
-  else k_worklist<ALGO_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa);
-  return 3;
+  // general kernel over what is left, bounded scratch
+  const int which = nmask ? 1 : 0;
+  fa.a.colstate = fs.colstate; fa.a.col_stride = slots; fa.a.col_rows = q8;
+  const int wb = (int)(slots / 128);
+  if (algo == ALGO_LOCAL) {
+    if (tbm) k_worklist<ALGO_LOCAL, START_TB><<<wb, 128, 0, str>>>(fa, which);
+    else if (sp) k_worklist<ALGO_LOCAL, START_POS><<<wb, 128, 0, str>>>(fa, which); else k_worklist<ALGO_LOCAL, START_NONE><<<wb, 128, 0, str>>>(fa, which);
+  }
+  else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_worklist<ALGO_SEMI_GLOBAL, START_POS><<<wb, 128, 0, str>>>(fa, which); else k_worklist<ALGO_SEMI_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa, which); }
+  else k_worklist<ALGO_GLOBAL, START_NONE><<<wb, 128, 0, str>>>(fa, which);
+  return launches;
 }
 
 }  // namespace gb200

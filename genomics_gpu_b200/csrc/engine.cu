@@ -13,6 +13,7 @@
 #include "../../include/gasal_b200.h"
 #include "dp_common.cuh"
 #include "dp_launch.h"
+#include "host_pack.h"
 
 using namespace gb200;
 
@@ -58,6 +59,8 @@ int g_n_penalty = -1;
 int g_kernel_policy = 0;
 int g_revcomp_mode = 0;
 int g_coord_fix = 0;
+int g_host_pack = 1;      // gasalx_set_host_packing: gasal_host_batch_fill / _add pack to 4 bits while they copy (0.5 B per base over PCIe)
+int g_host_wc = 0;        // gasalx_set_host_write_combined: sequence pages in write-combined pinned memory
 
 struct Priv {
   uint32_t* colstate = nullptr; size_t colstate_words = 0;
@@ -73,6 +76,7 @@ struct Priv {
   char* d_text = nullptr; size_t text_bytes = 0;             // gasalx_cigar_text_async
   uint32_t* d_text_lens = nullptr; size_t text_lens_cap = 0;
   uint32_t tb_n = 0; int tb_algo = 0;                         // pairs / algo of the last WITH_TB batch (0: none)
+  bool host_packed = false;                                   // the sequence pages hold 4-bit words (latched from g_host_pack at init)
   uint32_t fix_n = 0; int fix_kind = 0;                       // gasalx_set_coordinate_fix: 1 local start mirror (Q3), 2 / 3 semi-global default coordinates (Q8; 3: with start)
 };
 
@@ -115,6 +119,9 @@ void gasalx_set_n_code(int n_code, int n_penalty) { g_n_code = n_code; g_n_penal
 void gasalx_set_kernel_policy(int policy) { g_kernel_policy = policy; }
 void gasalx_set_revcomp_mode(int mode) { g_revcomp_mode = mode; }
 void gasalx_set_coordinate_fix(int on) { g_coord_fix = on; }
+void gasalx_set_host_packing(int on) { g_host_pack = on ? 1 : 0; }
+void gasalx_set_host_write_combined(int on) { g_host_wc = on ? 1 : 0; }
+int gasalx_storage_host_packed(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return (pv && pv->host_packed) ? 1 : 0; }
 
 void gasal_copy_subst_scores(gasal_subst_scores* subst) { g_scores = *subst; }   // src/gasal_align.cu:329-339
 
@@ -180,11 +187,43 @@ void gasal_res_destroy_device(gasal_res_t* device_res, gasal_res_t* device_cpy) 
 }
 
 // ---- host staging pages: src/host_batch.cpp ----------------------------------------------------------
-host_batch_t* gasal_host_batch_new(uint32_t batch_bytes, uint32_t offset) {
+// `packed`: the page holds 4-bit words; page_size / data_size / offset stay in BASES (= the reference's bytes), the allocation is half
+static host_batch_t* host_page_new(uint32_t batch_bytes, uint32_t offset, bool packed) {
   host_batch_t* res = (host_batch_t*)calloc(1, sizeof(host_batch_t));
-  CHECKCUDAERROR(cudaHostAlloc(&(res->data), (size_t)batch_bytes * sizeof(uint8_t), cudaHostAllocDefault));
+  const size_t alloc = packed ? ((size_t)batch_bytes + 15) / 16 * 8 + 8 : (size_t)batch_bytes;
+  CHECKCUDAERROR(cudaHostAlloc(&(res->data), alloc, g_host_wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
   res->page_size = batch_bytes; res->data_size = 0; res->is_locked = 0; res->offset = offset; res->next = NULL;
   return res;
+}
+
+host_batch_t* gasal_host_batch_new(uint32_t batch_bytes, uint32_t offset) { return host_page_new(batch_bytes, offset, false); }
+
+// Host-packed storages keep ONE page per side that grows by reallocation (a linked page could start in the middle of a word).
+static void packed_page_reserve(gasal_gpu_storage_t* s, host_batch_t* page, uint32_t* p_batch_bytes, uint64_t need, enum data_source SRC) {
+  if (need <= page->page_size) return;
+  uint64_t new_size = (uint64_t)page->page_size * 2;
+  while (new_size < need) new_size *= 2;
+  if (new_size > 0xFFFFFFF0ull) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] host batch of %llu bytes does not fit the 32-bit byte offsets of the GASAL2 API\n", (unsigned long long)need); }
+  fprintf(stderr, "[GASAL WARNING:] Trying to write up to byte %llu while the %s host page holds %d bytes. Reallocating it with %llu bytes. Doing this repeadtedly slows down the execution.\n",
+          (unsigned long long)need, (SRC == QUERY ? "query" : "target"), page->page_size, (unsigned long long)new_size);
+  uint8_t* nd = NULL;
+  CHECKCUDAERROR(cudaHostAlloc(&nd, (size_t)(new_size + 15) / 16 * 8 + 8, g_host_wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
+  memcpy(nd, page->data, ((size_t)page->data_size + 15) / 16 * 8);
+  CHECKCUDAERROR(cudaFreeHost(page->data));
+  page->data = nd; page->page_size = (uint32_t)new_size;
+  *p_batch_bytes = (uint32_t)new_size;
+  (void)s;
+}
+
+static uint32_t packed_page_write(gasal_gpu_storage_t* s, uint32_t idx, const char* data, uint32_t size, uint32_t pad, enum data_source SRC) {
+  host_batch_t* page = (SRC == QUERY) ? s->extensible_host_unpacked_query_batch : s->extensible_host_unpacked_target_batch;
+  uint32_t* p_batch_bytes = (SRC == QUERY) ? &s->host_max_query_batch_bytes : &s->host_max_target_batch_bytes;
+  const uint64_t end = (uint64_t)idx + size + pad;
+  packed_page_reserve(s, page, p_batch_bytes, end, SRC);
+  gb200::pack_bases_at((uint32_t*)page->data, idx, (const uint8_t*)data, size);
+  if (pad) gb200::fill_nibbles_at((uint32_t*)page->data, (uint64_t)idx + size, pad, (uint32_t)g_n_code & 15u);
+  if (page->data_size < end) page->data_size = (uint32_t)end;
+  return (uint32_t)end;
 }
 
 void gasal_host_batch_destroy(host_batch_t* res) {
@@ -214,6 +253,7 @@ uint32_t gasal_host_batch_fill(gasal_gpu_storage_t* gpu_storage, uint32_t idx, c
     default: GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] gasal_host_batch_fill: SRC must be QUERY or TARGET\n");
   }
   const uint32_t nbr_N = (8u - (size & 7u)) & 7u;
+  if (priv(gpu_storage) && priv(gpu_storage)->host_packed) return packed_page_write(gpu_storage, idx, data, size, nbr_N, SRC);
   while (cur_page->is_locked) cur_page = cur_page->next;
   if (cur_page->next == NULL && cur_page->page_size - cur_page->data_size < size + nbr_N) {
     uint32_t new_size = cur_page->page_size * 2;
@@ -248,6 +288,7 @@ uint32_t gasal_host_batch_add(gasal_gpu_storage_t* gpu_storage, uint32_t idx, co
     case TARGET: cur_page = gpu_storage->extensible_host_unpacked_target_batch; p_batch_bytes = &(gpu_storage->host_max_target_batch_bytes); break;
     default: GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] gasal_host_batch_add: SRC must be QUERY or TARGET\n");
   }
+  if (priv(gpu_storage) && priv(gpu_storage)->host_packed) return packed_page_write(gpu_storage, idx, data, size, 0, SRC);
   int is_done = 0;
   while (!is_done) {
     if (*p_batch_bytes >= idx + size && (cur_page->next == NULL || (cur_page->next->offset >= idx + size))) {
@@ -362,16 +403,18 @@ void gasal_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len,
     Priv* pv = new Priv();
     s->b200_priv = pv;
     pv->max_query_len_8 = max_query_len_8; pv->max_target_len_8 = max_target_len_8;
-    s->extensible_host_unpacked_query_batch = gasal_host_batch_new((uint32_t)qb, 0);
-    s->extensible_host_unpacked_target_batch = gasal_host_batch_new((uint32_t)tb, 0);
-    CHECKCUDAERROR(cudaMalloc(&(s->unpacked_query_batch), qb));
-    CHECKCUDAERROR(cudaMalloc(&(s->unpacked_target_batch), tb));
+    // host packing (default): the pinned pages and the H2D copies carry 4-bit words, the device needs no ASCII buffers at all
+    pv->host_packed = g_host_pack && !params->isPacked;
+    s->extensible_host_unpacked_query_batch = host_page_new((uint32_t)qb, 0, pv->host_packed);
+    s->extensible_host_unpacked_target_batch = host_page_new((uint32_t)tb, 0, pv->host_packed);
+    CHECKCUDAERROR(cudaMalloc(&(s->unpacked_query_batch), pv->host_packed ? qb / 2 : qb));
+    CHECKCUDAERROR(cudaMalloc(&(s->unpacked_target_batch), pv->host_packed ? tb / 2 : tb));
     CHECKCUDAERROR(cudaHostAlloc(&(s->host_query_op), max_n_alns, cudaHostAllocDefault));
     CHECKCUDAERROR(cudaHostAlloc(&(s->host_target_op), max_n_alns, cudaHostAllocDefault));
     memset(s->host_query_op, 0, max_n_alns); memset(s->host_target_op, 0, max_n_alns);
     CHECKCUDAERROR(cudaMalloc(&(s->query_op), max_n_alns));
     CHECKCUDAERROR(cudaMalloc(&(s->target_op), max_n_alns));
-    if (params->isPacked) {   // ctors.cpp:64-67: the "unpacked" buffers ARE the packed words
+    if (params->isPacked || pv->host_packed) {   // ctors.cpp:64-67: the "unpacked" buffers ARE the packed words
       s->packed_query_batch = (uint32_t*)s->unpacked_query_batch;
       s->packed_target_batch = (uint32_t*)s->unpacked_target_batch;
     } else {
@@ -434,10 +477,8 @@ void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_par
     if (s->host_target_batch_lens) CHECKCUDAERROR(cudaFreeHost(s->host_target_batch_lens));
     if (s->unpacked_query_batch) CHECKCUDAERROR(cudaFree(s->unpacked_query_batch));
     if (s->unpacked_target_batch) CHECKCUDAERROR(cudaFree(s->unpacked_target_batch));
-    if (!params->isPacked) {
-      if (s->packed_query_batch) CHECKCUDAERROR(cudaFree(s->packed_query_batch));
-      if (s->packed_target_batch) CHECKCUDAERROR(cudaFree(s->packed_target_batch));
-    }
+    if ((void*)s->packed_query_batch != (void*)s->unpacked_query_batch && s->packed_query_batch) CHECKCUDAERROR(cudaFree(s->packed_query_batch));
+    if ((void*)s->packed_target_batch != (void*)s->unpacked_target_batch && s->packed_target_batch) CHECKCUDAERROR(cudaFree(s->packed_target_batch));
     if (s->query_batch_offsets) CHECKCUDAERROR(cudaFree(s->query_batch_offsets));
     if (s->target_batch_offsets) CHECKCUDAERROR(cudaFree(s->target_batch_offsets));
     if (s->query_batch_lens) CHECKCUDAERROR(cudaFree(s->query_batch_lens));
@@ -460,6 +501,38 @@ void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_par
   }
 }
 
+// Deprecated in the reference (ctors.cpp:202-252): device buffers of ONE storage, no host pages, no stream.
+void gasal_gpu_mem_alloc(gasal_gpu_storage_t* s, int gpu_max_query_batch_bytes, int gpu_max_target_batch_bytes, int gpu_max_n_alns, const gasal_params_t* params) {
+  (void)params;
+  CHECKCUDAERROR(cudaMalloc(&(s->unpacked_query_batch), (size_t)gpu_max_query_batch_bytes));
+  CHECKCUDAERROR(cudaMalloc(&(s->unpacked_target_batch), (size_t)gpu_max_target_batch_bytes));
+  CHECKCUDAERROR(cudaMalloc(&(s->packed_query_batch), ((size_t)gpu_max_query_batch_bytes / 8) * sizeof(uint32_t)));
+  CHECKCUDAERROR(cudaMalloc(&(s->packed_target_batch), ((size_t)gpu_max_target_batch_bytes / 8) * sizeof(uint32_t)));
+  CHECKCUDAERROR(cudaMalloc(&(s->query_batch_lens), (size_t)gpu_max_n_alns * sizeof(uint32_t)));
+  CHECKCUDAERROR(cudaMalloc(&(s->target_batch_lens), (size_t)gpu_max_n_alns * sizeof(uint32_t)));
+  CHECKCUDAERROR(cudaMalloc(&(s->query_batch_offsets), (size_t)gpu_max_n_alns * sizeof(uint32_t)));
+  CHECKCUDAERROR(cudaMalloc(&(s->target_batch_offsets), (size_t)gpu_max_n_alns * sizeof(uint32_t)));
+  if (s->device_cpy) s->device_res = gasal_res_new_device(s->device_cpy);
+  s->gpu_max_query_batch_bytes = (uint32_t)gpu_max_query_batch_bytes; s->gpu_max_target_batch_bytes = (uint32_t)gpu_max_target_batch_bytes;
+  s->gpu_max_n_alns = (uint32_t)gpu_max_n_alns;
+}
+
+void gasal_gpu_mem_free(gasal_gpu_storage_t* s, const gasal_params_t* params) {
+  const bool alias_q = (void*)s->packed_query_batch == (void*)s->unpacked_query_batch, alias_t = (void*)s->packed_target_batch == (void*)s->unpacked_target_batch;
+  if (s->unpacked_query_batch != NULL) CHECKCUDAERROR(cudaFree(s->unpacked_query_batch));
+  if (s->unpacked_target_batch != NULL) CHECKCUDAERROR(cudaFree(s->unpacked_target_batch));
+  if (!alias_q && s->packed_query_batch != NULL) CHECKCUDAERROR(cudaFree(s->packed_query_batch));
+  if (!alias_t && s->packed_target_batch != NULL) CHECKCUDAERROR(cudaFree(s->packed_target_batch));
+  if (s->query_batch_offsets != NULL) CHECKCUDAERROR(cudaFree(s->query_batch_offsets));
+  if (s->target_batch_offsets != NULL) CHECKCUDAERROR(cudaFree(s->target_batch_offsets));
+  if (s->query_batch_lens != NULL) CHECKCUDAERROR(cudaFree(s->query_batch_lens));
+  if (s->target_batch_lens != NULL) CHECKCUDAERROR(cudaFree(s->target_batch_lens));
+  s->unpacked_query_batch = s->unpacked_target_batch = NULL; s->packed_query_batch = s->packed_target_batch = NULL;
+  s->query_batch_offsets = s->target_batch_offsets = s->query_batch_lens = s->target_batch_lens = NULL;
+  gasal_res_destroy_device(s->device_res, s->device_cpy); s->device_res = s->device_cpy = NULL;
+  if (params->secondBest) { gasal_res_destroy_device(s->device_res_second, s->device_cpy_second); s->device_res_second = s->device_cpy_second = NULL; }
+}
+
 void gasal_destroy_gpu_storage_v(gasal_gpu_storage_v* gpu_storage_vec) {
   if (gpu_storage_vec->a != NULL) free(gpu_storage_vec->a);
   gpu_storage_vec->a = NULL; gpu_storage_vec->n = 0;
@@ -474,7 +547,7 @@ static void grow_device(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_byt
             q_bytes, s->gpu_max_query_batch_bytes, s->gpu_max_query_batch_bytes * i, s->gpu_max_query_batch_bytes * i);
     s->gpu_max_query_batch_bytes *= i;
     const bool alias = (void*)s->packed_query_batch == (void*)s->unpacked_query_batch;
-    dev_realloc(&s->unpacked_query_batch, s->gpu_max_query_batch_bytes);
+    dev_realloc(&s->unpacked_query_batch, priv(s)->host_packed ? s->gpu_max_query_batch_bytes / 2 : s->gpu_max_query_batch_bytes);
     if (alias) s->packed_query_batch = (uint32_t*)s->unpacked_query_batch;
     else dev_realloc(&s->packed_query_batch, s->gpu_max_query_batch_bytes / 8);
     if (params->start_pos == WITH_TB) {
@@ -488,7 +561,7 @@ static void grow_device(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_byt
             t_bytes, s->gpu_max_target_batch_bytes, s->gpu_max_target_batch_bytes * i, s->gpu_max_target_batch_bytes * i);
     s->gpu_max_target_batch_bytes *= i;
     const bool alias = (void*)s->packed_target_batch == (void*)s->unpacked_target_batch;
-    dev_realloc(&s->unpacked_target_batch, s->gpu_max_target_batch_bytes);
+    dev_realloc(&s->unpacked_target_batch, priv(s)->host_packed ? s->gpu_max_target_batch_bytes / 2 : s->gpu_max_target_batch_bytes);
     if (alias) s->packed_target_batch = (uint32_t*)s->unpacked_target_batch;
     else dev_realloc(&s->packed_target_batch, s->gpu_max_target_batch_bytes / 8);
   }
@@ -620,7 +693,7 @@ static void validate(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes,
 
 static void device_stage(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n, const gasal_params_t* params, const BatchShape& shape) {
   Priv* pv = priv(s);
-  if (!params->isPacked) launch_pack(s, q_bytes, t_bytes);                             // gasal_align.cu:190-201
+  if (!params->isPacked && !pv->host_packed) launch_pack(s, q_bytes, t_bytes);          // gasal_align.cu:190-201 (host-packed pages arrive as words)
   if (params->isReverseComplement) {                                                    // :232-246
     launch_revcomp(s->packed_query_batch, s->packed_target_batch, s->query_batch_lens, s->target_batch_lens,
                    s->query_batch_offsets, s->target_batch_offsets, s->query_op, s->target_op, n, g_revcomp_mode, s->str);
@@ -642,10 +715,15 @@ void gasal_aln_async(gasal_gpu_storage_t* s, const uint32_t actual_query_batch_b
 
   CHECKCUDAERROR(cudaEventRecord(pv->ev[0], s->str));
   // H2D: one copy per host page (gasal_align.cu:152-175), then lens/offsets (:207-210), seeds, ops
-  for (host_batch_t* cur = s->extensible_host_unpacked_query_batch; cur != NULL; cur = cur->next)
-    if (cur->data_size) CHECKCUDAERROR(cudaMemcpyAsync(&(s->unpacked_query_batch[cur->offset]), cur->data, cur->data_size, cudaMemcpyHostToDevice, s->str));
-  for (host_batch_t* cur = s->extensible_host_unpacked_target_batch; cur != NULL; cur = cur->next)
-    if (cur->data_size) CHECKCUDAERROR(cudaMemcpyAsync(&(s->unpacked_target_batch[cur->offset]), cur->data, cur->data_size, cudaMemcpyHostToDevice, s->str));
+  if (pv->host_packed) {   // one page per side holding 4-bit words: half the bytes, and no pack kernel behind the copy
+    CHECKCUDAERROR(cudaMemcpyAsync(s->packed_query_batch, s->extensible_host_unpacked_query_batch->data, actual_query_batch_bytes / 2, cudaMemcpyHostToDevice, s->str));
+    CHECKCUDAERROR(cudaMemcpyAsync(s->packed_target_batch, s->extensible_host_unpacked_target_batch->data, actual_target_batch_bytes / 2, cudaMemcpyHostToDevice, s->str));
+  } else {
+    for (host_batch_t* cur = s->extensible_host_unpacked_query_batch; cur != NULL; cur = cur->next)
+      if (cur->data_size) CHECKCUDAERROR(cudaMemcpyAsync(&(s->unpacked_query_batch[cur->offset]), cur->data, cur->data_size, cudaMemcpyHostToDevice, s->str));
+    for (host_batch_t* cur = s->extensible_host_unpacked_target_batch; cur != NULL; cur = cur->next)
+      if (cur->data_size) CHECKCUDAERROR(cudaMemcpyAsync(&(s->unpacked_target_batch[cur->offset]), cur->data, cur->data_size, cudaMemcpyHostToDevice, s->str));
+  }
   CHECKCUDAERROR(cudaMemcpyAsync(s->query_batch_lens, s->host_query_batch_lens, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
   CHECKCUDAERROR(cudaMemcpyAsync(s->target_batch_lens, s->host_target_batch_lens, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
   CHECKCUDAERROR(cudaMemcpyAsync(s->query_batch_offsets, s->host_query_batch_offsets, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
@@ -733,6 +811,25 @@ int gasalx_last_batch_ms(gasal_gpu_storage_t* s, float out_ms[3]) {
   CHECKCUDAERROR(cudaEventElapsedTime(&out_ms[2], pv->ev[1], pv->ev[2]));
   float to_packed; CHECKCUDAERROR(cudaEventElapsedTime(&to_packed, pv->ev[0], pv->ev[1]));
   out_ms[1] = to_packed;
+  return 0;
+}
+
+// SURVEY 8(d) primary time: first H2D enqueue .. last D2H complete over a group of storages of one device that were in flight together
+int gasalx_span_ms(gasal_gpu_storage_t* const* storages, int n, float* out_ms) {
+  if (n <= 0 || !storages || !out_ms) return -1;
+  Priv* p0 = priv(storages[0]);
+  if (!p0 || !p0->timing_pending) return -1;
+  float lo = 0.f, hi = 0.f;
+  for (int i = 0; i < n; i++) {
+    Priv* pv = priv(storages[i]);
+    if (!pv || !pv->timing_pending || cudaEventQuery(pv->ev[3]) != cudaSuccess) return -1;
+    float a = 0.f, b = 0.f;
+    CHECKCUDAERROR(cudaEventElapsedTime(&a, p0->ev[0], pv->ev[0]));     // negative when storage i started before storage 0
+    CHECKCUDAERROR(cudaEventElapsedTime(&b, p0->ev[0], pv->ev[3]));
+    if (i == 0 || a < lo) lo = a;
+    if (i == 0 || b > hi) hi = b;
+  }
+  *out_ms = hi - lo;
   return 0;
 }
 

@@ -156,15 +156,7 @@ void gasalx_free_fasta_pairs(gasalx_fasta_pairs_t* p) {
   memset(p, 0, sizeof(*p));
 }
 
-// same nibble layout as the device pack kernel: first base in bits 31:28 ("ACGTNacg" -> 0x1374e137)
-void gasalx_pack_host(const uint8_t* ascii, uint64_t n_bytes, uint32_t* words) {
-  const uint64_t nw = n_bytes / 8;
-  for (uint64_t w = 0; w < nw; w++) {
-    const uint8_t* b = ascii + 8 * w;
-    words[w] = ((uint32_t)(b[0] & 15) << 28) | ((uint32_t)(b[1] & 15) << 24) | ((uint32_t)(b[2] & 15) << 20) | ((uint32_t)(b[3] & 15) << 16) |
-               ((uint32_t)(b[4] & 15) << 12) | ((uint32_t)(b[5] & 15) << 8) | ((uint32_t)(b[6] & 15) << 4) | (uint32_t)(b[7] & 15);
-  }
-}
+// gasalx_pack_host lives in host_pack.cpp (SIMD)
 
 // returns the string length (excluding the terminator), or -(needed capacity) when `cap` is too small
 int gasalx_cigar_string(const uint8_t* cigar, uint32_t n_ops, char* out, uint32_t cap) {

@@ -221,9 +221,10 @@ constexpr int kFrontGlobal = -(1 << 20);        // substitution score of GLOBAL'
 template <int TYPE, bool SINK>
 __global__ void __launch_bounds__(kThreads, 4) k_nvb_i32w(const NvbArgs a, int from_worklist) {
   const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
-  uint32_t job;
-  if (from_worklist) { if (idx >= *a.work_count) return; job = a.worklist[idx]; }
-  else { if (idx >= a.count) return; job = a.first + idx; }
+  // worklist mode: the grid is bounded by the scratch (one band-border column per THREAD), so a thread may take several entries
+  const uint32_t limit = from_worklist ? *a.work_count : a.count, step = gridDim.x * kThreads;
+  for (uint32_t widx = idx; widx < limit; widx += step) {
+  const uint32_t job = from_worklist ? a.worklist[widx] : a.first + widx;
   const Job jb = load_job(a, job);
   const uint8_t* __restrict__ P = a.pbytes + a.poffs[jb.pi];
   const uint8_t* __restrict__ T = a.tbytes + a.toffs[jb.ti];
@@ -327,6 +328,7 @@ NVB_UNROLL(2)
   }
   a.score[job] = best - tsh;                                                               // tracked in the kernel's H frame
   if (SINK) { a.sink_i[job] = bi; a.sink_j[job] = bj; }
+  }   // worklist / job loop
 }
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -698,7 +700,9 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
     const int type = al->type;
     if (fast) {
       NVB_CHECK(cudaMemsetAsync(s->work_count, 0, 4, s->st));
-      const uint32_t items = (a.count + 1) / 2, g = (items + kThreads - 1) / kThreads, g2 = (a.count + kThreads - 1) / kThreads;
+      // the worklist pass runs one job per THREAD on the scratch that was sized for the packed kernel's threads (two jobs each):
+      // its grid is bounded by a.stride threads and loops (k_nvb_i32w), instead of indexing past the allocation
+      const uint32_t items = (a.count + 1) / 2, g = (items + kThreads - 1) / kThreads, g2 = std::min<uint32_t>((a.count + kThreads - 1) / kThreads, a.stride / kThreads);
 #define NVB_LAUNCH_FAST(T, S) do { \
         if (fixed) k_nvb_s16<T, true, S><<<g, kThreads, 0, s->st>>>(a); else k_nvb_s16<T, false, S><<<g, kThreads, 0, s->st>>>(a); \
         k_nvb_i32w<T, S><<<g2, kThreads, 0, s->st>>>(a, 1); } while (0)

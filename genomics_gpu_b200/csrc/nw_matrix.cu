@@ -389,6 +389,7 @@ struct Scratch {
   uint8_t* d_ref = nullptr; uint8_t* d_qry = nullptr; size_t seq_cap = 0;     // nwx_matrix_host
   int* d_mat = nullptr; size_t mat_elems = 0;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t busy = nullptr;          // recorded after every launch: the next launch (any stream) waits on it before it reuses the scratch
   int sms = 0;
 };
 constexpr int kMaxDev = 64;
@@ -415,6 +416,10 @@ int launch(const uint8_t* ref_d, const uint8_t* qry_d, int* mat_d, uint32_t N, c
   if (!sc) { fprintf(stderr, "[NW CUDA ERROR:] no CUDA device\n"); return -1; }
   const uint32_t S = (N + kC - 1) / kC, Spad = (S + kGroup - 1) / kGroup * kGroup;
   const size_t words = (size_t)Spad + 64, entries = 2 * (size_t)Spad * kC;
+  // ONE scratch (ref32, boundary ring, ticket, tags) per device: launches on different streams are ordered on the device through
+  // an event, so a second call cannot overwrite the ring while the first matrix kernel is still running
+  if (!sc->busy) NW_CHECK(cudaEventCreateWithFlags(&sc->busy, cudaEventDisableTiming));
+  else NW_CHECK(cudaStreamWaitEvent(st, sc->busy, 0));
   if (sc->ref_words < words) { if (sc->ref32) cudaFree(sc->ref32); sc->ref32 = nullptr; NW_CHECK(cudaMalloc(&sc->ref32, words * sizeof(uint32_t))); sc->ref_words = words; }
   if (sc->bnd_entries < entries) {
     if (sc->bnd) cudaFree(sc->bnd);
@@ -437,6 +442,7 @@ int launch(const uint8_t* ref_d, const uint8_t* qry_d, int* mat_d, uint32_t N, c
   if (g_variant == 0) { if (aligned) k_nw_matrix_ws<true><<<grid, 64, 0, st>>>(a); else k_nw_matrix_ws<false><<<grid, 64, 0, st>>>(a); }
   else { if (aligned) k_nw_matrix<true><<<grid, 32, 0, st>>>(a); else k_nw_matrix<false><<<grid, 32, 0, st>>>(a); }
   NW_CHECK(cudaGetLastError());
+  NW_CHECK(cudaEventRecord(sc->busy, st));
   g_launches += 2;
   if (debug) {      // development aid: per-row-block timeline on stderr (synchronises)
     unsigned long long* h = (unsigned long long*)malloc((size_t)a.nblocks * 4 * sizeof(unsigned long long));
@@ -527,10 +533,11 @@ void nwx_release(void) {
   int cur = 0; cudaGetDevice(&cur);
   for (int d = 0; d < kMaxDev; d++) {
     Scratch& sc = g_scratch[d];
-    if (!sc.ref32 && !sc.bnd && !sc.ticket && !sc.sum && !sc.d_ref && !sc.d_mat && !sc.ev[0]) continue;
+    if (!sc.ref32 && !sc.bnd && !sc.ticket && !sc.sum && !sc.d_ref && !sc.d_mat && !sc.ev[0] && !sc.busy) continue;
     cudaSetDevice(d);
     cudaFree(sc.ref32); cudaFree(sc.bnd); cudaFree(sc.ticket); cudaFree(sc.sum); cudaFree(sc.d_ref); cudaFree(sc.d_qry); cudaFree(sc.d_mat);
     for (int e = 0; e < 4; e++) if (sc.ev[e]) cudaEventDestroy(sc.ev[e]);
+    if (sc.busy) cudaEventDestroy(sc.busy);
     sc = Scratch();
   }
   cudaSetDevice(cur);

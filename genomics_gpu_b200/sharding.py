@@ -36,7 +36,8 @@ def align_sharded(batch: Optional[PairBatch], align_fn: Callable[[PairBatch], Di
     """Rank 0 holds `batch`; returns the results in original order on rank 0 (None elsewhere).
     `align_fn` runs one rank's shard (on its GPU through the C ABI; a CPU stand-in in the gloo test)."""
     if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
-        return {k: align_fn(batch)[k] for k in keys}
+        res = align_fn(batch)
+        return {k: res[k] for k in keys}
     rank, world = dist.get_rank(), dist.get_world_size()
     shards = None
     if rank == 0:

@@ -271,3 +271,17 @@ def nvb_jobs(n: int, m_lo: int, m_hi: int, n_lo: int, n_hi: int, seed: int = 1, 
     poffs = np.zeros(n + 1, np.uint32); poffs[1:] = np.cumsum([len(p) for p in pats])
     toffs = np.zeros(n_texts + 1, np.uint32); toffs[1:] = np.cumsum([len(t) for t in texts])
     return np.concatenate(pats), poffs, np.concatenate(texts), toffs
+
+
+def with_n_bases(batch: PairBatch, pair_frac: float, seed: int = 1, per_pair: int = 1) -> PairBatch:
+    """Copy of `batch` in which a fraction of the pairs carries `per_pair` real 'N' bases (inside the true length, in the query or
+    the target at random): reads with uncalled bases, the input the s16x2 fast path has to hand to its N-aware second pass."""
+    rng = np.random.default_rng(seed)
+    q = batch.q_bytes.copy(); t = batch.t_bytes.copy()
+    hit = np.nonzero(rng.random(batch.n) < pair_frac)[0]
+    for _ in range(per_pair):
+        in_q = rng.random(hit.size) < 0.5
+        hq, ht = hit[in_q], hit[~in_q]
+        q[batch.q_offs[hq].astype(np.int64) + (rng.random(hq.size) * batch.q_lens[hq]).astype(np.int64)] = N_CODE
+        t[batch.t_offs[ht].astype(np.int64) + (rng.random(ht.size) * batch.t_lens[ht]).astype(np.int64)] = N_CODE
+    return PairBatch(q, t, batch.q_offs, batch.t_offs, batch.q_lens, batch.t_lens)

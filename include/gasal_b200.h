@@ -153,6 +153,11 @@ void gasal_init_streams(gasal_gpu_storage_v* gpu_storage_vec, int max_query_len,
                         const gasal_params_t* params);
 void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_params_t* params);
 void gasal_destroy_gpu_storage_v(gasal_gpu_storage_v* gpu_storage_vec);
+/* Deprecated in the reference (src/ctors.h:9,11, ctors.cpp:202-252) but still declared there: (re)allocate / free only the DEVICE
+ * buffers of one storage (sequences, lens, offsets, device_res from an existing device_cpy).  Kept so that old callers link. */
+void gasal_gpu_mem_alloc(gasal_gpu_storage_t* gpu_storage, int gpu_max_query_batch_bytes, int gpu_max_target_batch_bytes, int gpu_max_n_alns,
+                         const gasal_params_t* params);
+void gasal_gpu_mem_free(gasal_gpu_storage_t* gpu_storage, const gasal_params_t* params);
 
 /* ---- src/gasal_align.h:114-120 --------------------------------------------------------------- */
 void gasal_copy_subst_scores(gasal_subst_scores* subst);
@@ -225,10 +230,28 @@ void gasalx_set_revcomp_mode(int mode);
  * include/nvbio_b200.h, whose Gotoh aligners use the textbook recurrence. */
 void gasalx_set_coordinate_fix(int on);
 
+/* Host-side 4-bit packing (default 1).  The reference copies 1 byte per base to the GPU and packs there (gasal_align.cu:152-201).
+ * With 1, gasal_host_batch_fill / _add / _addbase pack WHILE they copy the caller's ASCII into the pinned page (AVX2), so the page,
+ * the H2D copy and the device hold 4-bit words only: half the PCIe bytes, no device ASCII buffers, no pack kernel in the pipeline.
+ * The caller-visible contract is unchanged (ASCII in, byte offsets and lengths in bases); host_batch_t::page_size / data_size /
+ * offset stay in bases, only the private `data` bytes differ, and such a storage keeps ONE page per side that grows by
+ * reallocation.  0 = the reference's layout (ASCII pages, linked 2x growth, k_pack on the GPU).  The setting is latched per storage
+ * by gasal_init_streams; storages with params->isPacked always take the caller's words as they are. */
+void gasalx_set_host_packing(int on);
+int gasalx_storage_host_packed(const gasal_gpu_storage_t* gpu_storage);
+/* 1: allocate the sequence pages as write-combined pinned memory (cudaHostAllocWriteCombined): faster for the DMA engine to read on
+ * some hosts, slow for the CPU to read back.  Default 0. */
+void gasalx_set_host_write_combined(int on);
+
 /* Device-side timing of the last finished batch of a storage, in milliseconds, measured with CUDA
  * events on gpu_storage->str: [0] whole pipeline (first H2D .. last D2H), [1] pack(+revcomp),
  * [2] DP kernels (+traceback).  Returns 0 on success, -1 if the batch has not finished. */
 int gasalx_last_batch_ms(gasal_gpu_storage_t* gpu_storage, float out_ms[3]);
+
+/* The survey's primary time over a GROUP of storages of one device whose batches were in flight together: milliseconds from the
+ * earliest "first H2D enqueued" event to the latest "last D2H complete" event (CUDA events on the storages' streams).  Returns 0,
+ * or -1 if one of the batches has not finished. */
+int gasalx_span_ms(gasal_gpu_storage_t* const* storages, int n, float* out_ms);
 
 /* Number of kernels the engine has launched on this storage since init (for launch accounting). */
 uint64_t gasalx_kernel_launches(const gasal_gpu_storage_t* gpu_storage);
@@ -300,6 +323,8 @@ int gasalx_read_fasta_pairs(const char* query_path, const char* target_path, int
 void gasalx_free_fasta_pairs(gasalx_fasta_pairs_t* p);
 /* 4-bit packing on the host, device layout (pack_rc_seqs.h:13-53): n_bytes must be a multiple of 8; words[n_bytes / 8]. */
 void gasalx_pack_host(const uint8_t* ascii, uint64_t n_bytes, uint32_t* words);
+/* same, for `n` bases written at BASE position `pos` of an existing word array (any alignment; neighbouring nibbles are kept) */
+void gasalx_pack_host_at(uint32_t* words, uint64_t pos, const uint8_t* ascii, uint64_t n);
 /* gasal_res_t::cigar bytes of one pair (reverse order) -> "12M1X3D..." as test_prog.cpp:382-428 prints it.
  * Returns the length, or -(needed capacity) if cap is too small. */
 int gasalx_cigar_string(const uint8_t* cigar, uint32_t n_ops, char* out, uint32_t cap);

@@ -179,6 +179,26 @@ def test_batches_larger_than_one_launch(orc):
     assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
 
 
+def test_more_flagged_jobs_than_packed_threads(orc):
+    """with the fixed-stride scratch a launch covers 2 x 131072 jobs but the band-border scratch holds one
+    column per THREAD of the packed kernel (131072).  When more than 131072 jobs of a launch are flagged (every pattern carries an
+    N) and the pattern needs the scratch (M > 16), the one-job-per-thread worklist pass must stay inside the allocation."""
+    n, m = 150_000, 40
+    rng = np.random.default_rng(34)
+    text = rng.integers(0, 4, 300).astype(np.uint8)
+    starts = rng.integers(0, 300 - m, n)
+    pats = text[(starts[:, None] + np.arange(m)[None, :])].astype(np.uint8)
+    pats[rng.random(pats.shape) < 0.05] = 2
+    pats[np.arange(n), rng.integers(0, m, n)] = 4                        # one N per pattern: every job goes to the worklist
+    pats = np.ascontiguousarray(pats.reshape(-1)); poffs = (np.arange(n + 1) * m).astype(np.uint32)
+    toffs = np.array([0, 300], np.uint32)
+    batch = nvb.Batch(pats, poffs, text, toffs)
+    for type_ in (nvb.SEMI_GLOBAL, nvb.GLOBAL, nvb.LOCAL):
+        want, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, text, toffs)
+        s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), batch)
+        assert k == "s16x2" and np.array_equal(s, want), type_
+
+
 @pytest.mark.parametrize("algo,scheme", [(nvb.GOTOH, GOTOH_SW), (nvb.SMITH_WATERMAN, (2, -1, -2, -2))])
 def test_local_sinks_tie_order_and_key_range(orc, algo, scheme):
     """LOCAL BestSink coordinates on the packed path: repeats make many cells tie, so the reference's report order (bands of 8 for Gotoh, 16
