@@ -322,6 +322,11 @@ def run_extras(local_rank: int, n_fwd: int):
         b4 = synth.config4(n_fwd, seed=4)
         out["C4_banded_k64_250bp"] = {"score_end": timed(b4, algo=capi.BANDED, k_band=64), "with_cigar": timed(b4, algo=capi.BANDED, k_band=64, start=capi.WITH_TB)}
         out["C5_mixed_100bp_10kb_local_with_start"] = timed(synth.config5(4000, seed=5), algo=capi.LOCAL, start=capi.WITH_START)
+        out["C1_10k_pairs_150x300_local"] = config1_extra(local_rank)
+        # reads with uncalled bases: pairs with an N leave the main s16x2 launch for its N-aware second pass (one more LOP3 per cell pair)
+        out["C2_local_with_start_vs_fraction_of_pairs_with_N"] = {
+            f"{int(100 * f)}%": timed(synth.with_n_bases(b2, f, seed=17) if f else b2, algo=capi.LOCAL, start=capi.WITH_START) for f in (0.0, 0.01, 0.05, 0.20)}
+        out["real_reads_reference_fixture_x66"] = real_reads_extra(timed)
         out["C4_local_250bp_with_cigar_s16x2"] = timed(b4, algo=capi.LOCAL, start=capi.WITH_TB)
         out["NW_linear_full_matrix_N32000"] = nw_extra(32000)
         out["nvbio_style_batched_scoring_262144x150x600"] = nvb_extra(n_fwd)
@@ -329,6 +334,53 @@ def run_extras(local_rank: int, n_fwd: int):
     except Exception as e:  # context only: never break the bench line
         out["error"] = str(e)[:200]
     return out
+
+
+def config1_extra(local_rank: int):
+    """BASELINE config 1: 10,000 pairs 150 x 300, local, score + end: the reference's kernels on the host cores (the CPU path the
+    config names) beside the engine on the same pairs, results compared field by field."""
+    from genomics_gpu_b200 import capi, synth
+    from genomics_gpu_b200.aligner import Aligner
+    from oracle import pyoracle as po
+    b = synth.config1(10_000, seed=1)
+    orc = po.Oracle()
+    pq, pt = orc.pack(b.q_bytes), orc.pack(b.t_bytes)
+    eng, kind = (po.RefHost(1024), "reference kernels compiled for the host") if po.RefHost.available(1024) else (orc, "port (oracle/gotoh_compat.c)")
+    threads = len(os.sched_getaffinity(0)) or 1
+    kw = dict(algo=po.LOCAL, scoring=SCORING, n_threads=threads)
+    if not po.RefHost.available(1024):
+        kw["max_query_len"] = 1024
+    t0 = time.perf_counter(); want = eng.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, **kw); cpu_s = time.perf_counter() - t0
+    with Aligner(algo=capi.LOCAL, max_query_len=157, max_target_len=307, max_n_alns=b.n, n_streams=1, scoring=SCORING, device=local_rank) as al:
+        best = None
+        for _ in range(3):
+            got = al.align(b); ms = al.last_ms(0)
+            best = ms if best is None or ms[0] < best[0] else best
+        kname = al.kernel_name(0)
+    same = all(np.array_equal(got[k], want[k]) for k in ("aln_score", "query_batch_end", "target_batch_end"))
+    return {"pairs": b.n, "cells": b.cells, "cpu": {"kind": kind, "cores": threads, "seconds": cpu_s, "gcups": b.cells / cpu_s / 1e9},
+            "gpu": {"kernel": kname, "pipeline_ms": best[0], "dp_ms": best[2], "gcups_pipeline": b.cells / best[0] / 1e6, "gcups_dp": b.cells / best[2] / 1e6},
+            "results_identical": bool(same)}
+
+
+def real_reads_extra(timed):
+    """The reference's own 20,000 real read / window pairs (GASAL2/test_prog/*.fasta.gz; 4,000 of them are committed as
+    tests/golden/real4000_inputs.npz), replicated to 264,000 pairs in their original (unsorted, ragged: 150 bp vs 152-277 bp) order."""
+    from genomics_gpu_b200 import capi
+    from genomics_gpu_b200.synth import PairBatch
+    g = np.load(os.path.join(ROOT, "tests", "golden", "real4000_inputs.npz"))
+    def ascii_of(words):                  # 4-bit words -> one ASCII byte per base with the same low nibble (first base in bits 31:28)
+        sh = np.array([28, 24, 20, 16, 12, 8, 4, 0], dtype=np.uint32)
+        return (((words[:, None] >> sh[None, :]) & 15) | 0x40).astype(np.uint8).reshape(-1)
+    q1, t1 = ascii_of(g["packed_q"]), ascii_of(g["packed_t"])
+    reps = 66
+    qb, tb = np.tile(q1, reps), np.tile(t1, reps)
+    qo = (g["q_offs"].astype(np.uint64)[None, :] + (np.arange(reps, dtype=np.uint64) * np.uint64(q1.size))[:, None]).reshape(-1).astype(np.uint32)
+    to = (g["t_offs"].astype(np.uint64)[None, :] + (np.arange(reps, dtype=np.uint64) * np.uint64(t1.size))[:, None]).reshape(-1).astype(np.uint32)
+    b = PairBatch(qb, tb, qo, to, np.tile(g["q_lens"], reps), np.tile(g["t_lens"], reps))
+    has_n = float(np.mean([(b"N" in b.query(i)) or (b"N" in b.target(i)) for i in range(0, 4000)]))
+    return {"pairs_with_N_fraction": has_n, "local": timed(b, algo=capi.LOCAL), "local_with_start": timed(b, algo=capi.LOCAL, start=capi.WITH_START),
+            "semi_global_with_start": timed(b, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)}
 
 
 def nw_extra(n: int):
@@ -540,7 +592,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = total_cells_per_step * args.steps / (wall_ms_max * 1e-3) / 1e9
     kernel_only = total_cells_per_step * args.steps / (kernel_ms_max * 1e-3) / 1e9
 
-    sharded = run_sharded(args, rank, world, local_rank) if (args.sharded and world > 1) else None
+    sharded = run_sharded(args, rank, world, local_rank) if args.sharded else None
 
     if world > 1:
         import torch.distributed as dist
@@ -624,8 +676,92 @@ def run_ours(args, rank, world, local_rank):
 
 
 def run_sharded(args, rank, world, local_rank):
-    """placeholder replaced below"""
-    return None
+    """STRONG-scaling job through the sharder (north_star: "length-balanced sharding across 8 B200", BASELINE config 5): 200,000
+    mixed-length pairs (100 bp - 10 kb, local WITH_START).  Rank 0 plans the length-balanced assignment (gasalx_plan_batches: length
+    binning + LPT on DP cells), every rank aligns its shard through the library batcher (gasalx_align_all on its own GPU), and the
+    results are gathered on rank 0 in the caller's order -- no data-path collective.  Every rank builds the same seeded input (8,000
+    distinct synthetic pairs x 25) instead of shipping 1 GB of sequence through the rendezvous.  Also C3 at 16 pairs per GPU."""
+    import torch
+    import torch.distributed as dist
+    from genomics_gpu_b200 import capi, synth
+    from genomics_gpu_b200.aligner import align_all
+    from genomics_gpu_b200.sharding import shard_indices
+    from genomics_gpu_b200.synth import PairBatch
+    out = {}
+    distinct, reps = args.sharded_distinct, args.sharded_reps
+    base = synth.config5(distinct, seed=5)
+    qb, tb = np.tile(base.q_bytes, reps), np.tile(base.t_bytes, reps)
+    qo = (base.q_offs.astype(np.uint64)[None, :] + (np.arange(reps, dtype=np.uint64) * np.uint64(base.q_bytes.size))[:, None]).reshape(-1)
+    to = (base.t_offs.astype(np.uint64)[None, :] + (np.arange(reps, dtype=np.uint64) * np.uint64(base.t_bytes.size))[:, None]).reshape(-1)
+    ql, tl = np.tile(base.q_lens, reps), np.tile(base.t_lens, reps)
+    n = int(ql.size)
+    cells = (ql.astype(np.int64) * tl.astype(np.int64))
+    plan = [None]
+    if rank == 0:
+        plan[0] = shard_indices(ql, tl, world, max_batch_pairs=2048)
+    if world > 1:
+        dist.broadcast_object_list(plan, src=0)
+    idx = plan[0][rank]
+    mine = PairBatch(qb, tb, qo[idx], to[idx], ql[idx], tl[idx])
+    keys = ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start")
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    best = None
+    for it in range(3):                              # one warm-up (storages, pinned pages), two timed passes: best counts
+        sync()
+        t0 = time.perf_counter()
+        res = align_all(mine, algo=capi.LOCAL, start=capi.WITH_START, scoring=SCORING, n_gpus=1, gpu_ids=[local_rank], streams_per_gpu=4) if mine.n else \
+            {k: np.zeros(0, dtype=np.int32) for k in keys}
+        payload = np.stack([res[k] for k in keys]) if mine.n else np.zeros((5, 0), dtype=np.int32)
+        gathered = [None] * world
+        if world > 1:
+            dist.gather_object((idx, payload), gathered if rank == 0 else None, dst=0)       # the host gather: 20 bytes per pair
+        else:
+            gathered[0] = (idx, payload)
+        full = None
+        if rank == 0:
+            full = np.zeros((5, n), dtype=np.int32)
+            for i2, p2 in gathered:
+                full[:, i2] = p2
+        sync()
+        dt = time.perf_counter() - t0
+        if it and (best is None or dt < best[0]):
+            best = (dt, full)
+    tt = torch.tensor([best[0]], dtype=torch.float64, device="cuda")
+    per_rank_cells = torch.zeros(world, dtype=torch.float64, device="cuda"); per_rank_cells[rank] = float(cells[idx].sum())
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX); dist.all_reduce(per_rank_cells, op=dist.ReduceOp.SUM)
+    lib = capi.load(); lib.gasalx_batcher_release()
+    prc = per_rank_cells.tolist()
+    if rank == 0:
+        out["C5_sharded_strong_scaling"] = {
+            "pairs": n, "distinct_pairs": distinct, "cells": int(cells.sum()), "seconds": float(tt[0]), "gcups": float(cells.sum()) / float(tt[0]) / 1e9,
+            "scaling": "strong (total work fixed as N grows)", "per_rank_cells": [int(x) for x in prc],
+            "imbalance_max_over_mean": max(prc) / (sum(prc) / world), "score_checksum": int(best[1][0].astype(np.int64).sum()),
+            "coord_checksum": int(best[1][1:].astype(np.int64).sum()),
+            "timing": "wall clock, barrier to barrier: plan already known; per-rank gasalx_align_all (length-binned batches, pinned streaming, results in shard order) + host gather on rank 0",
+            "note": "score_checksum / coord_checksum are the same at every N when the shards reproduce the single-GPU results"}
+    # C3: 16 pairs of 16k x 16k per GPU (the per-GPU share of BASELINE config 3 on 8 GPUs), weak
+    from genomics_gpu_b200.aligner import Aligner
+    b3 = synth.config3(16, 16384, seed=3 + rank)
+    with Aligner(algo=capi.GLOBAL, max_query_len=16384 + 7, max_target_len=16384 + 7, max_n_alns=16, n_streams=1, scoring=SCORING, device=local_rank) as al:
+        best3 = None
+        for it in range(3):
+            sync()
+            al.align(b3)
+            ms = al.last_ms(0)
+            best3 = ms[2] if best3 is None or ms[2] < best3 else best3
+        kname = al.kernel_name(0)
+    t3 = torch.tensor([best3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        out["C3_16_pairs_per_gpu"] = {"kernel": kname, "pairs_per_gpu": 16, "dp_ms_max_over_ranks": float(t3[0]), "gcups": world * b3.cells / (float(t3[0]) * 1e-3) / 1e9, "scaling": "weak"}
+    return out if rank == 0 else None
 
 
 def main():
@@ -639,7 +775,9 @@ def main():
     ap.add_argument("--e2e-chunks", type=int, default=16)
     ap.add_argument("--e2e-packed", type=int, default=1, help="also time the pipeline arm with caller-packed (isPacked) host pages")
     ap.add_argument("--e2e-ascii", type=int, default=1, help="also time the pipeline arm with ASCII host pages (host packing off, pack kernel on the GPU)")
-    ap.add_argument("--sharded", type=int, default=1, help="N > 1: also run the strong-scaling LPT-sharded mixed-length job (C5) over the ranks")
+    ap.add_argument("--sharded", type=int, default=1, help="also run the strong-scaling LPT-sharded mixed-length job (C5, 200k pairs) over the ranks and C3 at 16 pairs per GPU")
+    ap.add_argument("--sharded-distinct", type=int, default=8000, help="distinct synthetic pairs of the sharded job")
+    ap.add_argument("--sharded-reps", type=int, default=25, help="the sharded job replicates its distinct pairs this many times (8000 x 25 = 200,000 pairs)")
     ap.add_argument("--cpu-pairs", type=int, default=600_000, help="bounded sample for the cpu_baseline leg (~15 s on 16 cores)")
     ap.add_argument("--ref-pairs", type=int, default=200_000, help="pairs per step of the --impl reference arm (~5 s per step on 16 cores)")
     ap.add_argument("--extras", type=int, default=1, help="also time the other BASELINE.json configurations on rank 0 (context only)")

@@ -40,6 +40,7 @@ struct FastArgs {
   uint32_t* worklist; uint32_t* work_count;     // pairs with a base outside A/C/G/T (filled by the main launch; counts: work_count[0], [1])
   uint32_t* worklist2;                          // pairs the N-aware pass cannot represent either (codes other than A/C/G/T/N): general kernel
   uint32_t eight;          // == 8, passed at run time so the key multiply stays an IMAD (FMA pipe)
+  uint32_t thirtytwo;      // == 32, same for the grouped arg-max keys
   uint32_t one;            // == 1, run-time so that the sweep's trip count (columns + 1) is opaque to the unroller
   uint32_t mm, sixteen;    // == 0x00204081 / 16, run-time so the direction-nibble gather stays on IMAD (FMA pipe)
 };
@@ -63,7 +64,33 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 // bestK7 = max.s16x2(bestK7, c7); lanes that strictly improved record (cm, pos).  One asm block so that
 // ptxas fuses the per-lane compares into the predicate outputs of VIMNMX.S16x2 (the CUDA header's
 // __vibmax_s16x2 lost its predicate uses in partially unrolled loops with nvcc 12.9).
+#ifndef GB200_TRACK_IMAD
+#define GB200_TRACK_IMAD 1
+#endif
 __device__ __forceinline__ void track_update(LaneBest& lb, uint32_t c7, uint32_t cm, uint32_t pos, uint32_t one = 1u) {
+#if GB200_TRACK_IMAD
+  // the four predicated records as multiply-adds by a run-time 1: ptxas keeps them as predicated IMADs on the FMA pipe instead of
+  // SELs on the ALU pipe, which is the pipe that bounds these kernels
+  asm volatile(
+      "{\n\t"
+      ".reg .pred pl, ph;\n\t"
+      ".reg .s16 n0, n1, o0, o1;\n\t"
+      ".reg .b32 nb;\n\t"
+      "max.s16x2 nb, %0, %5;\n\t"
+      "mov.b32 {n0, n1}, nb;\n\t"
+      "mov.b32 {o0, o1}, %0;\n\t"
+      "setp.eq.s16 pl, n0, o0;\n\t"
+      "setp.eq.s16 ph, n1, o1;\n\t"
+      "mov.b32 %0, nb;\n\t"
+      "@!pl mad.lo.u32 %1, %6, %8, 0;\n\t"
+      "@!pl mad.lo.u32 %3, %7, %8, 0;\n\t"
+      "@!ph mad.lo.u32 %2, %6, %8, 0;\n\t"
+      "@!ph mad.lo.u32 %4, %7, %8, 0;\n\t"
+      "}"
+      : "+r"(lb.bestK7), "+r"(lb.keyL), "+r"(lb.keyH), "+r"(lb.posL), "+r"(lb.posH)
+      : "r"(c7), "r"(cm), "r"(pos), "r"(one));
+  return;
+#endif
   asm volatile(
       "{\n\t"
       ".reg .pred pl, ph;\n\t"
@@ -240,19 +267,118 @@ __device__ __forceinline__ void local_sweep4(uint32_t* __restrict__ HE, const ui
   }
 }
 
+// ---- grouped arg-max (G4): the column maxima of FOUR consecutive steps are folded into one running maximum per lane before the
+// strict-improvement test and the record, so the compare-and-record (LOP3 + VIMNMX + four selects per register set) runs once per
+// group instead of once per step.  Keys carry the step's phase inside the group above the row: key = H * 32 + (3 - phase) * 8 +
+// (7 - row), so the maximum still picks the earliest column, then the lowest row, of the best score; folding the running maximum
+// into the per-step VIMNMX3 tree is free (nine inputs = four instructions, like eight).  The step loop is written as groups of four
+// unrolled steps: no per-step branch.  Needs score * 32 + 31 < 2^15 (host check), else the per-step variant above runs.
+__device__ __forceinline__ uint32_t key_tree9(uint32_t g, const uint32_t (&key)[8]) {
+  uint32_t cm = __vimax3_s16x2(g, key[0], key[1]);
+  cm = __vimax3_s16x2(cm, key[2], key[3]);
+  cm = __vimax3_s16x2(cm, key[4], key[5]);
+  return __vimax3_s16x2(cm, key[6], key[7]);
+}
+
+template <bool NMASK = false>
+__device__ __forceinline__ void local_sweep4g(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int ngroups,
+                                              const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                              const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                              uint32_t neg_oe2, uint32_t neg_ext2, uint32_t thirtytwo, uint32_t one, uint32_t pos_base, LaneBest4& lb,
+                                              uint32_t nsc2 = 0) {
+  uint32_t pA[8], fA[8], pB[8], fB[8], keyA[8], keyB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { pA[r] = 0; fA[r] = 0; pB[r] = 0; fB[r] = 0; keyA[r] = 0; keyB[r] = 0; }
+  uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
+  uint32_t prevsh = 0xCC00u;
+  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;   // phantom columns: score 0 / -1
+  uint32_t he = HE[kFastThreads];                  // slot 1 = column 0
+  uint32_t v = V[kFastThreads];
+  uint32_t gA = 0, gB = 0;                         // running maxima of the current group
+  uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;
+#pragma unroll 1
+  for (int g = 0; g < ngroups; g++) {
+#pragma unroll
+    for (int ph = 0; ph < 4; ph++) {
+      const int k = 4 * g + ph;
+      const uint32_t selA = v | prevsh;
+      prevsh = v * 256u + 0x4400u;
+      uint32_t mA = 0;
+      if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
+      uint32_t upA = prmt(he, h8A, 0x5410);
+      uint32_t eA = prmt(he, eoA, 0x5432);
+      uint32_t upB = prmt(h8A, h8B, 0x5432);
+      uint32_t eB = prmt(eoA, eoB, 0x5432);
+      he = HE[(k + 2) * kFastThreads];
+      v = V[(k + 2) * kFastThreads];
+      // fold the PREVIOUS step's keys (software-pipelined: no input from this step); a group is closed when its phase-3 keys are in
+      gA = key_tree9(gA, keyA);
+      gB = key_tree9(gB, keyB);
+      if (ph == 0) {
+        const uint32_t pos = pos_base + (uint32_t)g - one;      // the group that just closed (g == 0: nothing but the zero keys, never an improvement)
+        track_update(lb.a, gA | 0x001F001Fu, gA, pos, one);
+        track_update(lb.b, gB | 0x001F001Fu, gB, pos, one);
+        gA = 0; gB = 0;
+      }
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        {
+          uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+          if (NMASK) s2 = mask_sel(s2, mA, nsc2);
+          const uint32_t d = __vadd2(pA[r], s2);
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
+          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, dm);
+          eA = __viaddmax_s16x2(eA, neg_ext2, dm);
+          keyA[r] = h * thirtytwo + (uint32_t)(((3 - ph) * 8 + (7 - r)) * 0x00010001);
+          pA[r] = upA; upA = h;
+        }
+        {
+          uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+          if (NMASK) s2 = mask_sel(s2, mB, nsc2);
+          const uint32_t d = __vadd2(pB[r], s2);
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
+          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, dm);
+          eB = __viaddmax_s16x2(eB, neg_ext2, dm);
+          keyB[r] = h * thirtytwo + (uint32_t)(((3 - ph) * 8 + (7 - r)) * 0x00010001);
+          pB[r] = upB; upB = h;
+        }
+      }
+      // B.H finished column k-3 (slot k-2): park (H,E) for the next quad-strip
+      HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+      h8A = upA; eoA = eA; h8B = upB; eoB = eB;
+      selB = selA_prev; selA_prev = selA;
+      if (NMASK) { mB = mA_prev; mA_prev = mA; }
+    }
+  }
+  {
+    gA = key_tree9(gA, keyA);
+    gB = key_tree9(gB, keyB);
+    const uint32_t pos = pos_base + (uint32_t)ngroups - one;
+    track_update(lb.a, gA | 0x001F001Fu, gA, pos, one);
+    track_update(lb.b, gB | 0x001F001Fu, gB, pos, one);
+  }
+}
+
 __device__ __forceinline__ void lanebest_init(LaneBest& lb) { lb.bestK7 = 0x00070007u; lb.keyL = lb.keyH = 0; lb.posL = lb.posH = 0; }
+__device__ __forceinline__ void lanebest_init_g4(LaneBest& lb) { lb.bestK7 = 0x001F001Fu; lb.keyL = lb.keyH = 0; lb.posL = lb.posH = 0; }
 
 // winner over the four records; pos = (quad-strip index << 16) | step
+template <bool G4 = false>
 __device__ __forceinline__ Winner pick_winner4(const LaneBest4& lb) {
+  constexpr int SH = G4 ? 5 : 3;
   int sc[4], strip[4], col[4], row[4];
-  sc[0] = (int)(short)(lb.a.bestK7 & 0xFFFFu) >> 3; sc[1] = (int)(short)(lb.a.bestK7 >> 16) >> 3;
-  sc[2] = (int)(short)(lb.b.bestK7 & 0xFFFFu) >> 3; sc[3] = (int)(short)(lb.b.bestK7 >> 16) >> 3;
+  sc[0] = (int)(short)(lb.a.bestK7 & 0xFFFFu) >> SH; sc[1] = (int)(short)(lb.a.bestK7 >> 16) >> SH;
+  sc[2] = (int)(short)(lb.b.bestK7 & 0xFFFFu) >> SH; sc[3] = (int)(short)(lb.b.bestK7 >> 16) >> SH;
   const uint32_t pos[4] = {lb.a.posL, lb.a.posH, lb.b.posL, lb.b.posH};
   const uint32_t key[4] = {lb.a.keyL & 0xFFFFu, lb.a.keyH >> 16, lb.b.keyL & 0xFFFFu, lb.b.keyH >> 16};
 #pragma unroll
   for (int i = 0; i < 4; i++) {
     strip[i] = 4 * (int)(pos[i] >> 16) + i;
-    col[i] = (int)(pos[i] & 0xFFFFu) - i;
+    // G4: pos holds the group of four steps, the key holds the step's phase inside it
+    const int step = G4 ? 4 * (int)(pos[i] & 0xFFFFu) + (3 - (int)((key[i] >> 3) & 3u)) : (int)(pos[i] & 0xFFFFu);
+    col[i] = step - i;
     row[i] = strip[i] * 8 + (7 - (int)(key[i] & 7u));
   }
   Winner w; w.score = 0; w.col = 0; w.row = 0;
@@ -450,7 +576,7 @@ __device__ __forceinline__ uint8_t col_selector(uint32_t code, bool pad, uint32_
   flag = true; return 0x88;
 }
 
-template <int START, bool NMASK = false>
+template <int START, bool NMASK = false, bool G4 = false>
 __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
@@ -492,7 +618,8 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   }
 
   // ---- forward pass over quad-strips ----
-  LaneBest4 lb; lanebest_init(lb.a); lanebest_init(lb.b);
+  LaneBest4 lb;
+  if (G4) { lanebest_init_g4(lb.a); lanebest_init_g4(lb.b); } else { lanebest_init(lb.a); lanebest_init(lb.b); }
   const int NQ = (TR + 3) >> 2;
   const int nsteps = ncol + 2 + (int)fa.one;   // run-time 1: keeps the trip count opaque (compiler note)
   if (START == START_TB) {
@@ -521,9 +648,11 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
     quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
-    local_sweep4<NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb, nsc2);
+    // G4: ncol / 4 + 1 groups = ncol + 4 steps (one phantom step more than the skew needs; its slots are dummies)
+    if (G4) local_sweep4g<NMASK>(HE, V, (ncol >> 2) + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, lb, nsc2);
+    else local_sweep4<NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb, nsc2);
   }
-  const Winner fw = pick_winner4(lb);
+  const Winner fw = pick_winner4<G4>(lb);
   a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row;
 
   if (START == START_POS) {
@@ -544,10 +673,11 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
         }
       }
 #pragma unroll
-      for (int x = 1; x <= 4; x++) { V[(rcol + x) * kFastThreads] = 0x88; HE[(rcol + x) * kFastThreads] = 0; }
-      LaneBest4 rb; lanebest_init(rb.a); lanebest_init(rb.b);
+      for (int x = 1; x <= 5; x++) { V[(rcol + x) * kFastThreads] = 0x88; HE[(rcol + x) * kFastThreads] = 0; }
+      LaneBest4 rb;
+      if (G4) { lanebest_init_g4(rb.a); lanebest_init_g4(rb.b); } else { lanebest_init(rb.a); lanebest_init(rb.b); }
       const int RD = (gend_reg + 3) >> 2;
-      const int fwd7 = (fw.score << 3) | 7;
+      const int fwd7 = G4 ? ((fw.score << 5) | 31) : ((fw.score << 3) | 7);
       for (int j = 0; j < RD; j++) {
         uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
         const uint32_t wa = nibrev(tw[gend_reg - 1 - 4 * j]);
@@ -555,11 +685,12 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
         const uint32_t wc = (4 * j + 2 < gend_reg) ? nibrev(tw[gend_reg - 3 - 4 * j]) : 0u;
         const uint32_t wd = (4 * j + 3 < gend_reg) ? nibrev(tw[gend_reg - 4 - 4 * j]) : 0u;
         quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
-        local_sweep4<NMASK>(HE, V, rcol + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb, nsc2);
+        if (G4) local_sweep4g<NMASK>(HE, V, (rcol >> 2) + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, rb, nsc2);
+        else local_sweep4<NMASK>(HE, V, rcol + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb, nsc2);
         if ((int)(short)(rb.a.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.a.bestK7 >> 16) >= fwd7 ||
             (int)(short)(rb.b.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.b.bestK7 >> 16) >= fwd7) break;
       }
-      const Winner rw = pick_winner4(rb);
+      const Winner rw = pick_winner4<G4>(rb);
       if (rw.score > 0) {
         sx = rcol - 1 - rw.col;                                    // ridx
         const int strip = rw.row >> 3, r = rw.row & 7;
@@ -672,6 +803,128 @@ __device__ __forceinline__ void nc_sweep(uint32_t* __restrict__ HE, const uint8_
 // the last true query column; the global capture) is gathered behind ONE compare per step (k == knext).
 //   kq      : step at which lane A.L is on the scanned / captured column (qlen - 1); lane i is there at step kq + i
 //   lane_lo/lane_hi of hhA / hhB give the four lanes' H values of the current step
+#ifndef GB200_NC_SPLIT
+#define GB200_NC_SPLIT 1          // 1: rare steps (phantom-column fix-ups, scan / capture) run in their own loops, the hot loop has no rare code
+#endif
+#ifndef GB200_NC_UNROLL_SEMI
+#define GB200_NC_UNROLL_SEMI 2
+#endif
+constexpr int kNcUnrollSemi = GB200_NC_UNROLL_SEMI;
+struct NcState {
+  uint32_t pA[8], fA[8], glA[8], pB[8], fB[8], glB[8];
+  uint32_t h8A, eoA, h8B, eoB, prevsh, selB, selA_prev, he, v;
+  uint32_t ncm_prev, mB, mA_prev;                 // NMASK: N-column masks, rotated like the selectors (see local_sweep4)
+};
+
+// one step (one query column per lane) of the quad-strip sweep; RARE adds the per-step work that only a handful of steps need
+template <int ALGO, bool REV, bool NMASK, bool RARE>
+__device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict__ HE, const uint8_t* __restrict__ V,
+                                        const uint32_t (&rowA)[8], const uint32_t (&rowB)[8], const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                        const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8], const uint32_t (&hpinit)[8],
+                                        uint32_t neg_oe2, uint32_t neg2, uint32_t conv8, int bias_ext, uint32_t nsc2,
+                                        int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr) {
+  constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
+  const uint32_t selA = st.v | st.prevsh;
+  st.prevsh = st.v * 256u + 0x4400u;
+  uint32_t mA = 0;
+  if (NMASK) { const uint32_t ncm = ncol_mask16(st.v); mA = ncm | (st.ncm_prev << 16); st.ncm_prev = ncm; }
+  uint32_t upA = prmt(st.he, st.h8A, 0x5410);
+  uint32_t eA = prmt(st.he, st.eoA, 0x5432);
+  uint32_t upB = prmt(st.h8A, st.h8B, 0x5432);
+  uint32_t eB = prmt(st.eoA, st.eoB, 0x5432);
+  st.he = HE[(k + 2) * kFastThreads];
+  st.v = V[(k + 2) * kFastThreads];
+  uint32_t hhA[8], hhB[8];
+  // SEMI keeps H of the previous column in glA/glB anyway, and the diagonal input of row r is exactly that H of row r - 1:
+  // reading it from there (pure renaming once the loop is unrolled) instead of a second rotating array saves 16 register moves per step
+  uint32_t dgA[8], dgB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { dgA[r] = SEMI ? (r ? st.glA[r - 1] : st.pA[0]) : st.pA[r]; dgB[r] = SEMI ? (r ? st.glB[r - 1] : st.pB[0]) : st.pB[r]; }
+  if (SEMI) { st.pA[0] = upA; st.pB[0] = upB; }
+#pragma unroll
+  for (int r = 0; r < 8; r++) {
+    {
+      uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+      if (NMASK) s2 = mask_sel(s2, mA, nsc2);
+      const uint32_t d = __vadd2(dgA[r], s2);
+      uint32_t h;
+      if (SEMI) {
+        // H-based opening without the serial H -> E -> H chain: with H = max(D, F, E),
+        // E(t+1,q) = max(H - oe, E - e) = max(max(D, F) - oe, E - e) because oe >= e.  `e` enters a row as E(t,q) and
+        // leaves it as E(t+1,q); the parked / handed-over E is the NEXT row's.
+        st.fA[r] = __viaddmax_s16x2(st.glA[r], neg_oe2, st.fA[r]);    // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e), biased frame
+        h = __vimax3_s16x2(d, st.fA[r], __vadd2(eA, neg_oe2));        // eA holds E + open: the un-shift is an FMA-pipe add off the E chain
+        eA = __vimax3_s16x2(eA, d, st.fA[r]);                         // E(t+1,q) + open = max(E + open, max(D, F)), biased frame
+        st.glA[r] = h;
+      } else {
+        h = __vimax3_s16x2(d, st.fA[r], eA);
+        st.fA[r] = __viaddmax_s16x2(d, neg_oe2, st.fA[r]);            // F(t,q+1) = max(F - e, D - oe), biased frame
+        eA = __viaddmax_s16x2(d, neg_oe2, eA);                        // E(t+1,q) = max(E - e, D - oe), biased frame
+      }
+      hhA[r] = h; if (!SEMI) st.pA[r] = upA; upA = h;
+    }
+    {
+      uint32_t s2 = prmt(rowC[r], rowD[r], st.selB);
+      if (NMASK) s2 = mask_sel(s2, st.mB, nsc2);
+      const uint32_t d = __vadd2(dgB[r], s2);
+      uint32_t h;
+      if (SEMI) {
+        st.fB[r] = __viaddmax_s16x2(st.glB[r], neg_oe2, st.fB[r]);
+        h = __vimax3_s16x2(d, st.fB[r], __vadd2(eB, neg_oe2));
+        eB = __vimax3_s16x2(eB, d, st.fB[r]);
+        st.glB[r] = h;
+      } else {
+        h = __vimax3_s16x2(d, st.fB[r], eB);
+        st.fB[r] = __viaddmax_s16x2(d, neg_oe2, st.fB[r]);
+        eB = __viaddmax_s16x2(d, neg_oe2, eB);
+      }
+      hhB[r] = h; if (!SEMI) st.pB[r] = upB; upB = h;
+    }
+  }
+  upA = __vadd2(upA, conv8); eA = __vadd2(eA, conv8); upB = __vadd2(upB, conv8); eB = __vadd2(eB, conv8);   // bottom row -> next strip's frame
+  HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+  st.h8A = upA; st.eoA = eA; st.h8B = upB; st.eoB = eB;
+  st.selB = st.selA_prev; st.selA_prev = selA;
+  if (NMASK) { st.mB = st.mA_prev; st.mA_prev = mA; }
+  if (RARE) {
+    if (k <= 2) {
+      // lanes that just ran a phantom column (A.H: step 0; B.L: 0,1; B.H: 0,1,2) get their strip-start state back
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        if (k == 0) { st.pA[r] = prmt(st.pA[r], pinitA[r], 0x7610); st.fA[r] = prmt(st.fA[r], neg2, 0x7610); if (SEMI) st.glA[r] = prmt(st.glA[r], hpinit[r], 0x7610); }
+        if (k <= 1) { st.pB[r] = pinitB[r]; st.fB[r] = neg2; if (SEMI) st.glB[r] = hpinit[r]; }
+        else { st.pB[r] = prmt(st.pB[r], pinitB[r], 0x7610); st.fB[r] = prmt(st.fB[r], neg2, 0x7610); if (SEMI) st.glB[r] = prmt(st.glB[r], hpinit[r], 0x7610); }
+      }
+    }
+    const int li = k - kq;
+    if (li >= 0 && li <= 3) {
+      int hv[8];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const uint32_t w = (li & 2) ? hhB[r] : hhA[r];
+        hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (kq + r) * bias_ext;     // back to the unbiased score (this lane is on column kq)
+      }
+      if (SEMI) {
+        // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178); the start
+        // pass stops between strips once the forward score is reached (:301)
+        if (!REV || li == 0 || tr.best < tr.stop) {
+          const int rb = rowbase + 8 * li;
+#pragma unroll
+          for (int r = 0; r < 8; r++) if (rb + r < tlen && hv[r] > tr.best) { tr.best = hv[r]; tr.y = rb + r; }
+        }
+      } else if (li == caplane) {
+#pragma unroll
+        for (int r = 0; r < 8; r++) if (r == caprow) tr.cap = hv[r];
+      }
+    }
+  }
+}
+
+// ---- quad-strip variant of nc_sweep (see local_sweep4): strips 4j..4j+3 as A.L, A.H, B.L, B.H, skewed by one column each.
+// The rare per-step work (re-imposing the strip-start state of the late lanes after their phantom columns, steps 0..2; the scan of
+// the last true query column / the global capture, steps kq..kq+3) runs in loops of its own, so the hot loop carries no rare code
+// and can be unrolled (the diagonal / H rotations become register renaming).
+//   kq      : step at which lane A.L is on the scanned / captured column (qlen - 1); lane i is there at step kq + i
 template <int ALGO, bool REV, bool NMASK = false>
 __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
                                           const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
@@ -680,7 +933,6 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
                                           uint32_t neg_oe2, uint32_t neg_ext2,
                                           int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, uint32_t nsc2 = 0) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
-  uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;      // NMASK: N-column masks, rotated like the selectors (see local_sweep4)
   const uint32_t neg2 = splat16(kNegSafe);
   // Both recurrences run in a BIASED frame: every H/E/F of (strip row r, column q) carries + (q + r) * ext.  Gap extension is
   // then free (semi-global: F' = max(F, Hleft - open), E' = max(E, M - open); global: F' = max(F, D - open), E' = max(E, D - open):
@@ -693,118 +945,34 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
   uint32_t hpinit[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) hpinit[r] = SEMI ? splat16((r - 1) * bias_ext) : neg_oe2;
-  uint32_t pA[8], fA[8], glA[8], pB[8], fB[8], glB[8];
+  NcState st;
 #pragma unroll
-  for (int r = 0; r < 8; r++) { pA[r] = pinitA[r]; fA[r] = neg2; glA[r] = hpinit[r]; pB[r] = pinitB[r]; fB[r] = neg2; glB[r] = hpinit[r]; }
-  uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
-  uint32_t prevsh = 0xCC00u;
-  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;
-  uint32_t he = HE[kFastThreads];
-  uint32_t v = V[kFastThreads];
-  int knext = 0;
-  // GLOBAL: two steps per trip, the p[r] <- up rotation becomes register renaming instead of 16 moves per step (+6 %); the
-  // semi-global body is larger and loses 8 % when unrolled (measured), so it stays rolled
+  for (int r = 0; r < 8; r++) { st.pA[r] = pinitA[r]; st.fA[r] = neg2; st.glA[r] = hpinit[r]; st.pB[r] = pinitB[r]; st.fB[r] = neg2; st.glB[r] = hpinit[r]; }
+  st.h8A = 0; st.eoA = 0; st.h8B = 0; st.eoB = 0;
+  st.prevsh = 0xCC00u; st.selB = 0xCCCCu; st.selA_prev = 0xCCCCu;
+  st.he = HE[kFastThreads]; st.v = V[kFastThreads];
+  st.ncm_prev = 0; st.mB = 0; st.mA_prev = 0;
+#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pinitA, pinitB, hpinit, neg_oe2, neg2, conv8, bias_ext, nsc2, \
+                                                           kq, rowbase, tlen, caplane, caprow, tr)
+#if GB200_NC_SPLIT
+  // segments: rare [0, r0e) -- hot [r0e, h0e) -- rare [h0e, r1e) -- hot [r1e, nsteps)
+  const int r0e = min(3, nsteps);
+  const int h0e = min(max(kq, r0e), nsteps);
+  const int r1e = min(max(kq + 4, h0e), nsteps);
+  int k = 0;
+#pragma unroll 1
+  for (; k < r0e; k++) NC_STEP(true, k);
+#pragma unroll (SEMI ? kNcUnrollSemi : 2)
+  for (; k < h0e; k++) NC_STEP(false, k);
+#pragma unroll 1
+  for (; k < r1e; k++) NC_STEP(true, k);
+#pragma unroll 1
+  for (; k < nsteps; k++) NC_STEP(false, k);
+#else
 #pragma unroll (SEMI ? 1 : 2)
-  for (int k = 0; k < nsteps; k++) {
-    const uint32_t selA = v | prevsh;
-    prevsh = v * 256u + 0x4400u;
-    uint32_t mA = 0;
-    if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
-    uint32_t upA = prmt(he, h8A, 0x5410);
-    uint32_t eA = prmt(he, eoA, 0x5432);
-    uint32_t upB = prmt(h8A, h8B, 0x5432);
-    uint32_t eB = prmt(eoA, eoB, 0x5432);
-    he = HE[(k + 2) * kFastThreads];
-    v = V[(k + 2) * kFastThreads];
-    uint32_t hhA[8], hhB[8];
-    // SEMI keeps H of the previous column in glA/glB anyway, and the diagonal input of row r is exactly that H of row r - 1:
-    // reading it from there (pure renaming) instead of a second rotating array saves 16 register moves per step
-    uint32_t dgA[8], dgB[8];
-#pragma unroll
-    for (int r = 0; r < 8; r++) { dgA[r] = SEMI ? (r ? glA[r - 1] : pA[0]) : pA[r]; dgB[r] = SEMI ? (r ? glB[r - 1] : pB[0]) : pB[r]; }
-    if (SEMI) { pA[0] = upA; pB[0] = upB; }
-#pragma unroll
-    for (int r = 0; r < 8; r++) {
-      {
-        uint32_t s2 = prmt(rowA[r], rowB[r], selA);
-        if (NMASK) s2 = mask_sel(s2, mA, nsc2);
-        const uint32_t d = __vadd2(dgA[r], s2);
-        uint32_t h;
-        if (SEMI) {
-          // H-based opening without the serial H -> E -> H chain: with H = max(D, F, E),
-          // E(t+1,q) = max(H - oe, E - e) = max(max(D, F) - oe, E - e) because oe >= e.  `e` enters a row as E(t,q) and
-          // leaves it as E(t+1,q); the parked / handed-over E is the NEXT row's.
-          fA[r] = __viaddmax_s16x2(glA[r], neg_oe2, fA[r]);    // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e), biased frame
-          h = __vimax3_s16x2(d, fA[r], __vadd2(eA, neg_oe2));  // eA holds E + open: the un-shift is an FMA-pipe add off the E chain
-          eA = __vimax3_s16x2(eA, d, fA[r]);                   // E(t+1,q) + open = max(E + open, max(D, F)), biased frame
-          glA[r] = h;
-        } else {
-          h = __vimax3_s16x2(d, fA[r], eA);
-          fA[r] = __viaddmax_s16x2(d, neg_oe2, fA[r]);         // F(t,q+1) = max(F - e, D - oe), biased frame
-          eA = __viaddmax_s16x2(d, neg_oe2, eA);               // E(t+1,q) = max(E - e, D - oe), biased frame
-        }
-        hhA[r] = h; if (!SEMI) pA[r] = upA; upA = h;
-      }
-      {
-        uint32_t s2 = prmt(rowC[r], rowD[r], selB);
-        if (NMASK) s2 = mask_sel(s2, mB, nsc2);
-        const uint32_t d = __vadd2(dgB[r], s2);
-        uint32_t h;
-        if (SEMI) {
-          fB[r] = __viaddmax_s16x2(glB[r], neg_oe2, fB[r]);
-          h = __vimax3_s16x2(d, fB[r], __vadd2(eB, neg_oe2));
-          eB = __vimax3_s16x2(eB, d, fB[r]);
-          glB[r] = h;
-        } else {
-          h = __vimax3_s16x2(d, fB[r], eB);
-          fB[r] = __viaddmax_s16x2(d, neg_oe2, fB[r]);
-          eB = __viaddmax_s16x2(d, neg_oe2, eB);
-        }
-        hhB[r] = h; if (!SEMI) pB[r] = upB; upB = h;
-      }
-    }
-    upA = __vadd2(upA, conv8); eA = __vadd2(eA, conv8); upB = __vadd2(upB, conv8); eB = __vadd2(eB, conv8);   // bottom row -> next strip's frame
-    HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
-    h8A = upA; eoA = eA; h8B = upB; eoB = eB;
-    selB = selA_prev; selA_prev = selA;
-    if (NMASK) { mB = mA_prev; mA_prev = mA; }
-    if (k == knext) {
-      if (k <= 2) {
-        // lanes that just ran a phantom column (A.H: step 0; B.L: 0,1; B.H: 0,1,2) get their strip-start state back
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          if (k == 0) { pA[r] = prmt(pA[r], pinitA[r], 0x7610); fA[r] = prmt(fA[r], neg2, 0x7610); if (SEMI) glA[r] = prmt(glA[r], hpinit[r], 0x7610); }
-          if (k <= 1) { pB[r] = pinitB[r]; fB[r] = neg2; if (SEMI) glB[r] = hpinit[r]; }
-          else { pB[r] = prmt(pB[r], pinitB[r], 0x7610); fB[r] = prmt(fB[r], neg2, 0x7610); if (SEMI) glB[r] = prmt(glB[r], hpinit[r], 0x7610); }
-        }
-      }
-      const int li = k - kq;
-      if (li >= 0 && li <= 3) {
-        int hv[8];
-#pragma unroll
-        for (int r = 0; r < 8; r++) {
-          const uint32_t w = SEMI ? ((li & 2) ? glB[r] : glA[r]) : ((li & 2) ? hhB[r] : hhA[r]);   // SEMI: gl already holds this step's H
-          hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (kq + r) * bias_ext;     // back to the unbiased score (this lane is on column kq)
-        }
-        if (SEMI) {
-          // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178); the start
-          // pass stops between strips once the forward score is reached (:301)
-          if (!REV || li == 0 || tr.best < tr.stop) {
-            const int rb = rowbase + 8 * li;
-#pragma unroll
-            for (int r = 0; r < 8; r++) if (rb + r < tlen && hv[r] > tr.best) { tr.best = hv[r]; tr.y = rb + r; }
-          }
-        } else if (li == caplane) {
-#pragma unroll
-          for (int r = 0; r < 8; r++) if (r == caprow) tr.cap = hv[r];
-        }
-      }
-      int nxt = -1;
-      if (k < 2) nxt = k + 1; else if (k < kq) nxt = kq;
-      if (k >= kq && k < kq + 3) nxt = k + 1;
-      knext = nxt;
-    }
-  }
+  for (int k = 0; k < nsteps; k++) NC_STEP(true, k);
+#endif
+#undef NC_STEP
 }
 
 // selector bytes + top boundary of one pass into shared memory.  mode 0: forward words; mode 2: true-length reversed.
@@ -1018,8 +1186,11 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
   return false;
 }
 
+#ifndef GB200_LOCAL_G4
+#define GB200_LOCAL_G4 1
+#endif
 int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, uint32_t min_q, uint32_t min_t, cudaStream_t str) {
-  (void)max_t; (void)min_q; (void)min_t;
+  (void)min_q; (void)min_t;
   const uint32_t q8 = (max_q + 7u) & ~7u;
   if (fs.cap < (size_t)a.n) {
     if (fs.worklist) cudaFree(fs.worklist);
@@ -1044,7 +1215,7 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
     fs.colstate_words = cs_need;
   }
   FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.worklist2 = fs.worklist + fs.cap; fa.work_count = fs.work_count;
-  fa.eight = 8; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
+  fa.eight = 8; fa.thirtytwo = 32; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
   const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads;
   if (!fs.attr_set) {
     const int lim = 227 * 1024;
@@ -1059,6 +1230,10 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_global_s16, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_NONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_POS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_NONE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_POS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     fs.attr_set = true;
   }
   k_zero_u32<<<1, 1, 0, str>>>(fs.work_count);
@@ -1066,8 +1241,12 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
   const bool sp = (start == START_POS);
   const bool tbm = (start == START_TB);
   int launches = 3;
+  // grouped arg-max (keys score * 32 + ...) while every possible score stays below 1024, else the per-step keys (score * 8 + ...)
+  const uint32_t t8 = (max_t + 7u) & ~7u;
+  const bool g4 = GB200_LOCAL_G4 && (uint64_t)std::min(q8, t8) * (uint64_t)a.match <= 1000;
   if (algo == ALGO_LOCAL) {
     if (tbm) k_local_s16<START_TB><<<blocks, kFastThreads, smem, str>>>(fa);
+    else if (g4) { if (sp) k_local_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
     else if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
   }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
@@ -1076,6 +1255,7 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
     // the grid covers the worst case (every pair flagged); CTAs beyond work_count[0] exit on their first instruction
     if (algo == ALGO_LOCAL) {
       if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, str>>>(fa);
+      else if (g4) { if (sp) k_local_s16<START_POS, true, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, str>>>(fa); }
       else if (sp) k_local_s16<START_POS, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, str>>>(fa);
     } else { if (sp) k_semiglobal_s16<START_POS, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, str>>>(fa); }
     launches++;

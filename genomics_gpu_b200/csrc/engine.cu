@@ -733,6 +733,17 @@ void gasal_aln_async(gasal_gpu_storage_t* s, const uint32_t actual_query_batch_b
     CHECKCUDAERROR(cudaMemcpyAsync(s->seed_scores, s->host_seed_scores, n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
   }
   if (params->isReverseComplement) {
+    // one-time note: the reference's reverse branch is undefined C (pack_rc_seqs.h:115,136,153); mode 0 is the sane reversal, NOT what
+    // its sm_100 binary computes (mode 1 is)
+    static bool noted = false;
+    if (!noted && g_revcomp_mode == 0) {
+      for (uint32_t i = 0; i < n; i++)
+        if ((s->host_query_op[i] | s->host_target_op[i]) & 1) {
+          fprintf(stderr, "[GASAL NOTE:] a reverse operation is applied with gasalx_set_revcomp_mode(0): sequences are reversed as a whole (padding included); the "
+                          "reference library built by nvcc 12.9 for sm_100 zeroes half of every reversed sequence instead -- gasalx_set_revcomp_mode(1) reproduces that bit for bit\n");
+          noted = true; break;
+        }
+    }
     CHECKCUDAERROR(cudaMemcpyAsync(s->query_op, s->host_query_op, n, cudaMemcpyHostToDevice, s->str));
     CHECKCUDAERROR(cudaMemcpyAsync(s->target_op, s->host_target_op, n, cudaMemcpyHostToDevice, s->str));
   }

@@ -16,9 +16,12 @@ from .aligner import plan_batches
 from .synth import PairBatch
 
 
-def shard_indices(q_lens: np.ndarray, t_lens: np.ndarray, world: int, max_batch_pairs: int = 4096):
-    """Per-rank pair indices, balanced on sum(q*t) by LPT over length-binned batches."""
-    p = plan_batches(q_lens, t_lens, n_gpus=world, max_batch_pairs=max_batch_pairs)
+def shard_indices(q_lens: np.ndarray, t_lens: np.ndarray, world: int, max_batch_pairs: int = 4096, pieces_per_rank: int = 32):
+    """Per-rank pair indices, balanced on sum(q*t) by LPT over length-binned batches.  The sharding batches are cut so that every
+    rank receives about `pieces_per_rank` of them (LPT's imbalance is bounded by one piece)."""
+    total = int((np.asarray(q_lens, dtype=np.int64) * np.asarray(t_lens, dtype=np.int64)).sum())
+    piece = max(total // max(world * pieces_per_rank, 1), 1 << 20)
+    p = plan_batches(q_lens, t_lens, n_gpus=world, max_batch_pairs=max_batch_pairs, max_batch_cells=piece)
     per_rank = [[] for _ in range(world)]
     st = p["batch_start"]
     for b, dev in enumerate(p["batch_gpu"]):

@@ -13,7 +13,7 @@ for algo, name in ((capi.LOCAL, "local"), (capi.SEMI_GLOBAL, "semi_global"), (ca
     for start in (capi.WITHOUT_START, capi.WITH_START):
         if algo == capi.GLOBAL and start == capi.WITH_START:
             continue
-        for policy in (0, 1):
+        for policy in [int(x) for x in os.environ.get('QUICK_POLICIES', '0,1').split(',')]:
             lib.gasalx_set_kernel_policy(policy)
             with Aligner(algo=algo, start=start, max_query_len=157, max_target_len=607, max_n_alns=n, n_streams=1) as al:
                 best = None
