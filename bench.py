@@ -435,6 +435,8 @@ def run_ours(args, rank, world, local_rank):
 
     lib = capi.load()
     lib.gasal_set_device(local_rank, 0)
+    if os.environ.get("GASALX_HOST_WC") == "1":          # experiment switch: write-combined pinned sequence pages
+        lib.gasalx_set_host_write_combined(1)
     prev_affinity = bind_to_gpu_numa_node(local_rank) if args.numa_bind else None
     n = args.pairs
     batch = make_workload(n, seed=2 + rank)

@@ -1,0 +1,4 @@
+set -x
+nvidia-smi --query-gpu=index,name --format=csv | head -10
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 8 --steps 10 --extras 0 --refgpu-pairs 0 --cpu-pairs 20000 > gpurun_out/r2_bench_8gpu.json 2> gpurun_out/r2_bench_8gpu.err; echo rc=$?; tail -3 gpurun_out/r2_bench_8gpu.err
+GASALX_HOST_WC=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 8 --steps 10 --extras 0 --refgpu-pairs 0 --cpu-pairs 20000 --e2e-ascii 0 --e2e-packed 0 --sharded 0 > gpurun_out/r2_bench_8gpu_wc.json 2> gpurun_out/r2_bench_8gpu_wc.err; echo rc=$?; tail -3 gpurun_out/r2_bench_8gpu_wc.err
