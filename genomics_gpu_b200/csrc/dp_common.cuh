@@ -38,6 +38,7 @@ struct DpArgs {
   // traceback
   uint4* tb; uint32_t tb_stride;         // tile t of pair p lives at tb[t * tb_stride + p]
   int tb_banded;                         // 1: only the tile band of banded.h:35,83-85 is stored (see band_geom)
+  const uint64_t* tb_off;                // non-null (long pairs, wavefront kernel): pair p owns tiles tb[tb_off[p] + tile], sized by ITS OWN shape
   uint8_t* cigar; uint32_t* n_cigar_ops;
   int head, tail, k_band;
 };
@@ -84,6 +85,25 @@ __device__ __forceinline__ BandGeom band_geom(int QR, int TR, int k_band) {
 }
 __device__ __forceinline__ int band_lo(const BandGeom& b, int i) { return max(0, i - b.k_other + 1); }
 __device__ __forceinline__ int band_hi(const BandGeom& b, int i, int QR) { return min(b.kw + i, QR); }
+
+// ---- direction nibbles from packed s16x2 lanes (LOCAL WITH_TB; used by dp_s16.cuh and dp_wave.cuh; see dp_s16.cuh for the derivation)
+__device__ __forceinline__ uint32_t lop3_code0(uint32_t a, uint32_t b, uint32_t s) {   // (~a & s) | (a & ~b)
+  uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x3a;" : "=r"(d) : "r"(a), "r"(b), "r"(s)); return d;
+}
+
+__device__ __forceinline__ void tb_nibbles(uint32_t d, uint32_t dm, uint32_t h, uint32_t f, uint32_t e, uint32_t s2,
+                                           uint32_t neg_ext2, uint32_t minus1_2, uint32_t mm, uint32_t sixteen, uint32_t& wL, uint32_t& wH) {
+  const uint32_t fe = __vadd2(f, neg_ext2), ee = __vadd2(e, neg_ext2), dm1 = __vadd2(dm, minus1_2);
+  const uint32_t qf = __vsub2(dm1, fe), qe = __vsub2(dm1, ee), a = __vsub2(d, h), b = __vsub2(f, h);
+  const uint32_t c0 = lop3_code0(a, b, s2);
+  const uint32_t g1 = prmt(c0, a, 0x7351);          // [c0.L, a.L, c0.H, a.H]   (sign-carrying bytes)
+  const uint32_t g2 = prmt(qe, qf, 0x7351);         // [qe.L, qf.L, qe.H, qf.H]
+  const uint32_t xl = prmt(g1, g2, 0x5410) & 0x80808080u, xh = prmt(g1, g2, 0x7632) & 0x80808080u;
+  wL = wL * sixteen + ((xl * mm) >> 28);
+  wH = wH * sixteen + ((xh * mm) >> 28);
+}
+
+__device__ __forceinline__ void tb_push(uint32_t (&d)[4], uint32_t w) { d[0] = d[1]; d[1] = d[2]; d[2] = d[3]; d[3] = w; }
 
 __device__ __forceinline__ short2 u32_as_short2(uint32_t v) { short2 r; r.x = (short)(v & 0xFFFFu); r.y = (short)(v >> 16); return r; }
 __device__ __forceinline__ uint32_t pack_short2(int h, int e) { return ((uint32_t)h & 0xFFFFu) | ((uint32_t)e << 16); }

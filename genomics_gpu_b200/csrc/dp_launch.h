@@ -12,18 +12,20 @@ namespace gb200 {
 constexpr uint32_t kFastMaxQ8 = 352;      // (q8 + kSlotPad) * 128 * 5 B must fit one CTA's shared memory
 
 struct FastScratch {
-  uint32_t* worklist = nullptr; uint32_t* work_count = nullptr; size_t cap = 0;
+  uint32_t* worklist = nullptr; uint32_t* work_count = nullptr; size_t cap = 0;       // worklist[cap] (pairs with N), worklist2[cap] (general kernel)
   uint32_t* colstate = nullptr; size_t colstate_words = 0;
-  uint32_t* order = nullptr; size_t order_cap = 0;                 // device-side length binning (k_bin_*): pair permutation
-  uint32_t* bins = nullptr;                                        // histogram / cursors of the binning pass
+  uint8_t* flags = nullptr;                                                            // k_classify: pass of every pair
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;       // the N-aware launch runs beside the main launch
   bool attr_set = false;
   void release() {
     if (worklist) cudaFree(worklist);
     if (work_count) cudaFree(work_count);
     if (colstate) cudaFree(colstate);
-    if (order) cudaFree(order);
-    if (bins) cudaFree(bins);
-    worklist = work_count = colstate = order = bins = nullptr; cap = 0; colstate_words = 0; order_cap = 0;
+    if (flags) cudaFree(flags);
+    if (side) { cudaStreamSynchronize(side); cudaStreamDestroy(side); }
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    worklist = work_count = colstate = nullptr; flags = nullptr; side = nullptr; ev_fork = ev_join = nullptr; cap = 0; colstate_words = 0;
   }
 };
 
@@ -33,8 +35,8 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
 
 // ---- intra-task wavefront kernels (dp_wave.cuh) ---------------------------------------------------------------------
 struct WaveScratch {
-  uint64_t* qoff = nullptr; uint64_t* soff = nullptr; size_t n_cap = 0;
-  uint64_t* h_off = nullptr; size_t h_cap = 0;                    // pinned staging: qoff[n] then soff[n]
+  uint64_t* qoff = nullptr; uint64_t* soff = nullptr; uint64_t* toff = nullptr; size_t n_cap = 0;    // device: qoff[n], soff[n], toff[n] (traceback tile offsets)
+  uint64_t* h_off = nullptr; size_t h_cap = 0;                    // pinned staging: qoff[n], soff[n], toff[n]
   uint4* bnd = nullptr; size_t bnd_cap = 0;
   uint32_t next_tag = 1;                                          // boundary tags handed out so far (never reused while bnd lives)
   int2* cand = nullptr; size_t cand_cap = 0;
@@ -45,10 +47,12 @@ struct WaveScratch {
     if (bnd) cudaFree(bnd);
     if (cand) cudaFree(cand);
     if (prog) cudaFree(prog);
-    qoff = soff = nullptr; h_off = nullptr; bnd = nullptr; cand = nullptr; prog = nullptr; n_cap = h_cap = bnd_cap = cand_cap = prog_cap = 0;
+    qoff = soff = toff = nullptr; h_off = nullptr; bnd = nullptr; cand = nullptr; prog = nullptr; n_cap = h_cap = bnd_cap = cand_cap = prog_cap = 0;
   }
 };
 
+// tiles (uint4) of the per-pair traceback regions of the wavefront LOCAL WITH_TB kernel: pair p owns 2 QR x TR tiles
+inline uint64_t wave_tb_tiles_of(uint32_t qlen, uint32_t tlen) { return 2ull * ((qlen + 7u) >> 3) * ((tlen + 7u) >> 3); }
 bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t);
 bool wave_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t min_q, uint32_t min_t);
 int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uint32_t* h_qlens, const uint32_t* h_tlens,
@@ -61,6 +65,8 @@ int launch_pack(const uint8_t* uq, uint32_t* pq, uint32_t q_bytes, const uint8_t
 void launch_revcomp(uint32_t* pq, uint32_t* pt, const uint32_t* q_lens, const uint32_t* t_lens, const uint32_t* q_offs, const uint32_t* t_offs,
                     const uint8_t* q_op, const uint8_t* t_op, uint32_t n, int mode, cudaStream_t str);
 void launch_get_tb(const DpArgs& a, bool is_local, cudaStream_t str);
+// mixed-class batches: dst[k][order[i]] = src[k][i] for the (up to five) result arrays that exist
+void launch_scatter_results(const uint32_t* order, uint32_t n, int32_t* const src[5], int32_t* const dst[5], cudaStream_t str);
 void launch_cigar_text(const uint8_t* cigar, const uint32_t* n_cigar_ops, const uint32_t* q_offs, const uint32_t* q_lens, const int32_t* q_start,
                        const int32_t* q_end, int n, int style, int clip, char* text, uint32_t stride, uint32_t* lens, cudaStream_t str);
 

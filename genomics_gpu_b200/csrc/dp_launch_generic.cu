@@ -66,6 +66,21 @@ void launch_get_tb(const DpArgs& a, bool is_local, cudaStream_t str) {
   if (is_local) k_get_tb<true><<<nb, 128, 0, str>>>(a); else k_get_tb<false><<<nb, 128, 0, str>>>(a);
 }
 
+struct ScatterArgs { const int32_t* src[5]; int32_t* dst[5]; };
+__global__ void __launch_bounds__(256) k_scatter_results(const uint32_t* __restrict__ order, uint32_t n, const ScatterArgs sa) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const uint32_t p = order[i];
+#pragma unroll
+  for (int k = 0; k < 5; k++) if (sa.src[k] && sa.dst[k]) sa.dst[k][p] = sa.src[k][i];
+}
+
+void launch_scatter_results(const uint32_t* order, uint32_t n, int32_t* const src[5], int32_t* const dst[5], cudaStream_t str) {
+  ScatterArgs sa;
+  for (int k = 0; k < 5; k++) { sa.src[k] = src[k]; sa.dst[k] = dst[k]; }
+  k_scatter_results<<<(n + 255) / 256, 256, 0, str>>>(order, n, sa);
+}
+
 void launch_cigar_text(const uint8_t* cigar, const uint32_t* n_cigar_ops, const uint32_t* q_offs, const uint32_t* q_lens, const int32_t* q_start,
                        const int32_t* q_end, int n, int style, int clip, char* text, uint32_t stride, uint32_t* lens, cudaStream_t str) {
   k_cigar_text<<<(n + 127) / 128, 128, 0, str>>>(cigar, n_cigar_ops, q_offs, q_lens, q_start, q_end, n, style, clip, text, stride, lens);

@@ -39,6 +39,7 @@ struct FastArgs {
   uint32_t q8max;          // columns reserved per thread in shared memory (multiple of 8)
   uint32_t* worklist; uint32_t* work_count;     // pairs with a base outside A/C/G/T (filled by the main launch; counts: work_count[0], [1])
   uint32_t* worklist2;                          // pairs the N-aware pass cannot represent either (codes other than A/C/G/T/N): general kernel
+  const uint8_t* flags;                         // k_classify: 0 = pure A/C/G/T pair (main launch), else listed in worklist / worklist2
   uint32_t eight;          // == 8, passed at run time so the key multiply stays an IMAD (FMA pipe)
   uint32_t thirtytwo;      // == 32, same for the grouped arg-max keys
   uint32_t one;            // == 1, run-time so that the sweep's trip count (columns + 1) is opaque to the unroller
@@ -400,28 +401,13 @@ __device__ __forceinline__ Winner pick_winner4(const LaneBest4& lb) {
 // Two PRMTs gather the sign-carrying bytes of the four words lane by lane, and one multiply by 0x00204081 moves the four sign
 // bits of a lane into one nibble (the "movemask" multiplication), which a second multiply-add appends to the row word:
 // 9 ALU + 11 FMA-pipe instructions per cell pair on top of the recurrence, no compares, no selects.
-__device__ __forceinline__ uint32_t lop3_code0(uint32_t a, uint32_t b, uint32_t s) {   // (~a & s) | (a & ~b)
-  uint32_t d; asm("lop3.b32 %0, %1, %2, %3, 0x3a;" : "=r"(d) : "r"(a), "r"(b), "r"(s)); return d;
-}
-
-__device__ __forceinline__ void tb_nibbles(uint32_t d, uint32_t dm, uint32_t h, uint32_t f, uint32_t e, uint32_t s2,
-                                           uint32_t neg_ext2, uint32_t minus1_2, uint32_t mm, uint32_t sixteen, uint32_t& wL, uint32_t& wH) {
-  const uint32_t fe = __vadd2(f, neg_ext2), ee = __vadd2(e, neg_ext2), dm1 = __vadd2(dm, minus1_2);
-  const uint32_t qf = __vsub2(dm1, fe), qe = __vsub2(dm1, ee), a = __vsub2(d, h), b = __vsub2(f, h);
-  const uint32_t c0 = lop3_code0(a, b, s2);
-  const uint32_t g1 = prmt(c0, a, 0x7351);          // [c0.L, a.L, c0.H, a.H]   (sign-carrying bytes)
-  const uint32_t g2 = prmt(qe, qf, 0x7351);         // [qe.L, qf.L, qe.H, qf.H]
-  const uint32_t xl = prmt(g1, g2, 0x5410) & 0x80808080u, xh = prmt(g1, g2, 0x7632) & 0x80808080u;
-  wL = wL * sixteen + ((xl * mm) >> 28);
-  wH = wH * sixteen + ((xh * mm) >> 28);
-}
+// (lop3_code0 / tb_nibbles live in dp_common.cuh: the wavefront traceback kernel uses them too)
 
 // One quad-strip sweep with direction output.  tb points at this thread's element of tile 0 of strip 4j (A.L); tiles of one
 // strip are 2*QR apart; `ts` = tb_stride.  valid[i]: strip 4j+i exists.  Each lane keeps the words of its last four columns
 // in a 4-deep shift register and stores them as one uint4 when its column index reaches 3 mod 4; the lanes are one column
 // apart, so exactly one of the four stores fires per step.  (A 4x unrolled variant with compile-time phases was 40 KB of
 // code and ran at the speed of the int32 kernel: instruction-cache bound.)
-__device__ __forceinline__ void tb_push(uint32_t (&d)[4], uint32_t w) { d[0] = d[1]; d[1] = d[2]; d[2] = d[3]; d[3] = w; }
 
 __device__ __forceinline__ void tb_flush(uint4* __restrict__ tb, size_t ts, int QR2, int k, int ncol,
                                          uint32_t (&dAL)[4], uint32_t (&dAH)[4], uint32_t (&dBL)[4], uint32_t (&dBH)[4],
@@ -514,6 +500,134 @@ __device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const
   }
 }
 
+// ---- BANDED + WITH_TB on the packed lanes ------------------------------------------------------------------------------------
+// The engine's banded traceback (an extension: the reference's banded kernel has no traceback) is the LOCAL recurrence and its
+// direction nibbles over the reference's TILE band (banded.h:35,83-85): strip i covers query words [lo(i), hi(i)), cells outside
+// read as 0, every strip starts from a zero state at its first word (dp_generic.cuh banded_tb_forward).  A quad-strip sweep only
+// walks the union of its four strips' bands.  Each lane has a window of steps in which it is inside ITS OWN band:
+//   * at the step a lane enters its window, its halves of the diagonal / F registers are cleared (the strip's zero start state);
+//   * whatever a lane hands on while it is outside its window (bottom H / E to the next lane or to shared memory) is masked to 0,
+//     which is exactly what a cell outside the band reads as; its keys are masked out of the arg-max; its tiles are not stored.
+// The sweep is cut into segments at the (at most eight) enter / exit steps, so the step body only carries six AND masks.
+struct BandWin { int enter[4], exitk[4]; long long tile_base[4]; };
+
+template <bool NMASK = false>
+__device__ __forceinline__ void local_sweep4_tbb(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, const BandWin& bw,
+                                                 const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                                 const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                                 uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t one, uint32_t mm, uint32_t sixteen, uint32_t pos_base,
+                                                 LaneBest4& lb, uint4* __restrict__ tb, size_t ts, int c0, uint32_t nsc2 = 0) {
+  uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;
+  uint32_t pA[8], fA[8], pB[8], fB[8], keyA[8], keyB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { pA[r] = 0; fA[r] = 0; pB[r] = 0; fB[r] = 0; keyA[r] = 0; keyB[r] = 0; }
+  uint32_t dAL[4] = {0, 0, 0, 0}, dAH[4] = {0, 0, 0, 0}, dBL[4] = {0, 0, 0, 0}, dBH[4] = {0, 0, 0, 0};
+  uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
+  uint32_t prevsh = 0xCC00u;
+  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;
+  uint32_t he = HE[kFastThreads];
+  uint32_t v = V[kFastThreads];
+  uint32_t pos = pos_base;
+  const uint32_t minus1_2 = 0xFFFFFFFFu;
+  int nsteps = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) nsteps = max(nsteps, bw.exitk[i]);
+  uint32_t inA = 0, inB = 0, inA_prev = 0, inB_prev = 0;
+  int k = 0;
+  while (k < nsteps) {
+    // ---- segment boundary: lanes entering at k start from the zero state; masks of the lanes inside during [k, next)
+    int next = nsteps;
+    uint32_t keepA = 0xFFFFFFFFu, keepB = 0xFFFFFFFFu;
+    inA = 0; inB = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (bw.enter[i] > k) next = min(next, bw.enter[i]);
+      if (bw.exitk[i] > k) next = min(next, bw.exitk[i]);
+      const bool inside = bw.enter[i] <= k && k < bw.exitk[i];
+      const uint32_t half = (i & 1) ? 0xFFFF0000u : 0x0000FFFFu;
+      if (inside) { if (i < 2) inA |= half; else inB |= half; }
+      if (bw.enter[i] == k) { if (i < 2) keepA &= ~half; else keepB &= ~half; }
+    }
+    if (keepA != 0xFFFFFFFFu) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) { pA[r] &= keepA; fA[r] &= keepA; }
+    }
+    if (keepB != 0xFFFFFFFFu) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) { pB[r] &= keepB; fB[r] &= keepB; }
+    }
+    const bool stA0 = (inA & 0xFFFFu) != 0, stA1 = (inA >> 16) != 0, stB0 = (inB & 0xFFFFu) != 0, stB1 = (inB >> 16) != 0;
+#pragma unroll 1
+    for (; k < next; k++) {
+      const uint32_t selA = v | prevsh;
+      prevsh = v * 256u + 0x4400u;
+      uint32_t mA = 0;
+      if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
+      uint32_t upA = prmt(he, h8A, 0x5410);
+      uint32_t eA = prmt(he, eoA, 0x5432);
+      uint32_t upB = prmt(h8A, h8B, 0x5432);
+      uint32_t eB = prmt(eoA, eoB, 0x5432);
+      he = HE[(k + 2) * kFastThreads];
+      v = V[(k + 2) * kFastThreads];
+      {
+        const uint32_t cm = key_tree(keyA) & inA_prev;               // the keys are the previous step's: masked with that step's windows
+        track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+        const uint32_t cn = key_tree(keyB) & inB_prev;
+        track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+        pos = pos_base + (uint32_t)k;
+      }
+      uint32_t wAL = 0, wAH = 0, wBL = 0, wBH = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        {
+          uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+          if (NMASK) s2 = mask_sel(s2, mA, nsc2);
+          const uint32_t d = __vadd2(pA[r], s2);
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
+          tb_nibbles(d, dm, h, fA[r], eA, s2, neg_ext2, minus1_2, mm, sixteen, wAL, wAH);
+          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, dm);
+          eA = __viaddmax_s16x2(eA, neg_ext2, dm);
+          keyA[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+          pA[r] = upA; upA = h;
+        }
+        {
+          uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+          if (NMASK) s2 = mask_sel(s2, mB, nsc2);
+          const uint32_t d = __vadd2(pB[r], s2);
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
+          tb_nibbles(d, dm, h, fB[r], eB, s2, neg_ext2, minus1_2, mm, sixteen, wBL, wBH);
+          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, dm);
+          eB = __viaddmax_s16x2(eB, neg_ext2, dm);
+          keyB[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+          pB[r] = upB; upB = h;
+        }
+      }
+      // what a lane outside its band hands on reads as 0
+      upA &= inA; eA &= inA; upB &= inB; eB &= inB;
+      HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+      h8A = upA; eoA = eA; h8B = upB; eoB = eB;
+      selB = selA_prev; selA_prev = selA;
+      inA_prev = inA; inB_prev = inB;
+      if (NMASK) { mB = mA_prev; mA_prev = mA; }
+      // one of the four lanes completes a tile of four columns per step (its column index reaches 3 mod 4)
+      tb_push(dAL, wAL); tb_push(dAH, wAH); tb_push(dBL, wBL); tb_push(dBH, wBH);
+      const int ph = k & 3;
+      if (ph == 3) { if (stA0) tb[(size_t)(bw.tile_base[0] + ((c0 + k) >> 2)) * ts] = make_uint4(dAL[0], dAL[1], dAL[2], dAL[3]); }
+      if (ph == 0) { if (stA1) tb[(size_t)(bw.tile_base[1] + ((c0 + k - 1) >> 2)) * ts] = make_uint4(dAH[0], dAH[1], dAH[2], dAH[3]); }
+      if (ph == 1) { if (stB0) tb[(size_t)(bw.tile_base[2] + ((c0 + k - 2) >> 2)) * ts] = make_uint4(dBL[0], dBL[1], dBL[2], dBL[3]); }
+      if (ph == 2) { if (stB1) tb[(size_t)(bw.tile_base[3] + ((c0 + k - 3) >> 2)) * ts] = make_uint4(dBH[0], dBH[1], dBH[2], dBH[3]); }
+    }
+  }
+  {
+    const uint32_t cm = key_tree(keyA) & inA_prev;
+    track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+    const uint32_t cn = key_tree(keyB) & inB_prev;
+    track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+  }
+}
+
 // Does the target hold a base outside A/C/G/T inside its true length?  Word-parallel (a nibble is valid iff it is 0001, 0011,
 // 0100 or 0111) and WITHOUT an early exit: the loads of a thread are independent and pipeline, where the per-nibble loop with
 // `&& !odd` serialised 75 dependent global loads per pair (7 % of the local kernel's time in the ncu source view).
@@ -576,13 +690,48 @@ __device__ __forceinline__ uint8_t col_selector(uint32_t code, bool pad, uint32_
   flag = true; return 0x88;
 }
 
+// ---- k_classify: which pass scores a pair? --------------------------------------------------------------------------------
+// One WARP per pair reads its packed words once (coalesced) and files the pair: 0 = only A/C/G/T inside the true lengths (main
+// launch), 1 = also N (N-aware launch, worklist), 2 = any other code or an empty sequence (general kernel, worklist2).  Because
+// the lists exist BEFORE the main launch, the N-aware launch runs beside it on a second stream instead of behind it, so a batch
+// with 1 % of N-carrying reads no longer pays a whole extra (nearly empty) wave, and the main kernel needs no target scan.
+__global__ void __launch_bounds__(256) k_classify(const FastArgs fa, uint8_t* __restrict__ flags, int nmask_ok, int zero_q_is_odd, int zero_t_is_odd) {
+  const DpArgs& a = fa.a;
+  const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (pair >= (uint32_t)a.n) return;
+  const uint32_t qlen = a.q_lens[pair], tlen = a.t_lens[pair];
+  const uint32_t* qw = a.pq + (a.q_offs[pair] >> 3);
+  const uint32_t* tw = a.pt + (a.t_offs[pair] >> 3);
+  const uint32_t nq = n_words(qlen), nt = n_words(tlen), nval = a.n_value;
+  uint32_t odd = 0, exo = 0;
+  for (uint32_t w = lane; w < nq + nt; w += 32) {
+    const bool isq = w < nq;
+    const uint32_t wi = isq ? w : w - nq, len = isq ? qlen : tlen;
+    const uint32_t x = isq ? qw[wi] : tw[wi];
+    const uint32_t left = len - 8 * wi;                                  // >= 1 bases of this word are real
+    const uint32_t m = left >= 8 ? 0x11111111u : (0x11111111u << (4 * (8 - left)));
+    odd |= odd_nibbles(x) & m; exo |= exotic_nibbles(x, nval) & m;
+  }
+  const bool any_odd = __any_sync(0xFFFFFFFFu, odd != 0), any_exo = __any_sync(0xFFFFFFFFu, exo != 0);
+  if (lane == 0) {
+    int kind = any_exo ? 2 : (any_odd ? 1 : 0);
+    if ((zero_q_is_odd && qlen == 0) || (zero_t_is_odd && tlen == 0)) kind = 2;
+    if (kind == 1 && !nmask_ok) kind = 2;
+    flags[pair] = (uint8_t)kind;
+    if (kind) {
+      const uint32_t slot = atomicAdd(fa.work_count + (kind - 1), 1u);
+      (kind == 1 ? fa.worklist : fa.worklist2)[slot] = pair;
+    }
+  }
+}
+
 template <int START, bool NMASK = false, bool G4 = false>
 __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }     // N-aware pass: one thread per flagged pair
-  else if (tid >= (uint32_t)a.n) return;
+  else { if (tid >= (uint32_t)a.n) return; if (fa.flags[tid]) return; }           // flagged pairs belong to the other passes (k_classify)
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
 
@@ -610,10 +759,9 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   }
 #pragma unroll
   for (int x = 1; x <= 5; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = 0; }
-  odd |= NMASK ? target_exotic_scan(tw, tlen, nval) : target_odd_scan(tw, tlen, TR);
-  if (odd) {   // hand the pair on (same stream, next launch): main pass -> N-aware pass -> general kernel
-    const uint32_t slot = atomicAdd(fa.work_count + (NMASK ? 1 : 0), 1u);
-    (NMASK ? fa.worklist2 : fa.worklist)[slot] = tid;
+  if (odd) {   // cannot happen (k_classify filed this pair for this pass from the same words); kept as a safety net: general kernel
+    const uint32_t slot = atomicAdd(fa.work_count + 1, 1u);
+    fa.worklist2[slot] = tid;
     return;
   }
 
@@ -699,6 +847,77 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     }
     a.q_start[tid] = sx; a.t_start[tid] = sy;
   }
+}
+
+// BANDED + WITH_TB: the LOCAL recurrence with direction nibbles over the tile band (see local_sweep4_tbb); only the band's tiles are
+// stored: tile (strip * W + word - lo(strip)) * 2 + half, W = widest strip (dp_common.cuh band_geom), which k_get_tb addresses the same way
+template <bool NMASK = false>
+__global__ void __launch_bounds__(kFastThreads) k_banded_tb_s16(const FastArgs fa) {
+  extern __shared__ uint32_t smem[];
+  const DpArgs& a = fa.a;
+  uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }
+  else { if (tid >= (uint32_t)a.n) return; if (fa.flags[tid]) return; }
+  uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
+  uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
+  const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
+  const uint32_t* tw = a.pt + (a.t_offs[tid] >> 3);
+  const uint32_t qlen = a.q_lens[tid], tlen = a.t_lens[tid];
+  const int QR = (int)n_words(qlen), TR = (int)n_words(tlen);
+  const uint32_t mis4 = ((uint32_t)(-a.mismatch) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)a.match ^ (uint32_t)(-a.mismatch)) & 0xFFu;
+  const uint32_t neg_oe2 = splat16(-(a.gap_open + a.gap_extend)), neg_ext2 = splat16(-a.gap_extend);
+  const uint32_t nval = a.n_value, nsc2 = splat16(a.n_score), nsc4 = ((uint32_t)a.n_score & 0xFFu) * 0x01010101u;
+  bool odd = false;
+  const int ncol = QR * 8;
+  V[0] = 0x88; HE[0] = 0;
+  for (int j = 0; j < QR; j++) {
+    const uint32_t w = qw[j];
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const int c = 8 * j + k;
+      V[(c + 1) * kFastThreads] = col_selector<NMASK>(nib(w, k), (uint32_t)c >= qlen, nval, odd);
+      HE[(c + 1) * kFastThreads] = 0;
+    }
+  }
+#pragma unroll
+  for (int x = 1; x <= 5; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = 0; }
+  if (odd) { const uint32_t slot = atomicAdd(fa.work_count + 1, 1u); fa.worklist2[slot] = tid; return; }     // cannot happen (k_classify)
+
+  const BandGeom bg = band_geom(QR, TR, a.k_band);
+  LaneBest4 lb; lanebest_init(lb.a); lanebest_init(lb.b);
+  const int NQ = (TR + 3) >> 2;
+  for (int j = 0; j < NQ; j++) {
+    uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
+    BandWin bw;
+    int ulo = 0x7FFFFFFF;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const int strip = 4 * j + i;
+      int lo = band_lo(bg, strip), hi = band_hi(bg, strip, QR);
+      if (strip >= TR || lo >= hi) { lo = 0; hi = 0; }                // no cell of this strip is inside the band
+      else ulo = min(ulo, lo);
+      bw.enter[i] = lo; bw.exitk[i] = hi;                              // words for now
+      bw.tile_base[i] = ((long long)strip * bg.W - lo) * 2;
+    }
+    if (ulo == 0x7FFFFFFF) continue;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      const bool empty = bw.enter[i] >= bw.exitk[i];
+      bw.enter[i] = empty ? 0 : (bw.enter[i] - ulo) * 8 + i;
+      bw.exitk[i] = empty ? 0 : (bw.exitk[i] - ulo) * 8 + i;
+    }
+    const uint32_t wa = tw[4 * j];
+    const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;
+    const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
+    const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
+    quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
+    const int c0 = ulo * 8;
+    local_sweep4_tbb<NMASK>(HE + (size_t)c0 * kFastThreads, V + (size_t)c0 * kFastThreads, bw, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, fa.mm, fa.sixteen,
+                            ((uint32_t)j << 16) + (uint32_t)c0, lb, a.tb + tid, (size_t)a.tb_stride, c0, nsc2);
+  }
+  const Winner w_ = pick_winner4(lb);
+  a.score[tid] = w_.score; a.q_end[tid] = w_.col; a.t_end[tid] = w_.row;
 }
 
 // =====================================================================================================
@@ -1014,7 +1233,7 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }     // N-aware pass: one thread per flagged pair
-  else if (tid >= (uint32_t)a.n) return;
+  else { if (tid >= (uint32_t)a.n) return; if (fa.flags[tid]) return; }           // flagged pairs belong to the other passes (k_classify)
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
@@ -1031,10 +1250,9 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
 
   bool odd = top_zero ? nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval)
                       : nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval);
-  odd |= NMASK ? target_exotic_scan(tw, tlen, nval) : target_has_odd_base(tw, tlen, TR);
-  if (odd || qlen == 0) {
-    const uint32_t slot = atomicAdd(fa.work_count + (NMASK ? 1 : 0), 1u);
-    (NMASK ? fa.worklist2 : fa.worklist)[slot] = tid;
+  if (odd || qlen == 0) {   // cannot happen (see k_classify); safety net
+    const uint32_t slot = atomicAdd(fa.work_count + 1, 1u);
+    fa.worklist2[slot] = tid;
     return;
   }
   uint32_t pinit[8];
@@ -1082,6 +1300,7 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
   const DpArgs& a = fa.a;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (uint32_t)a.n) return;
+  if (fa.flags[tid]) return;                                     // general kernel (k_classify)
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
@@ -1095,10 +1314,9 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
   const uint32_t neg_oe2 = splat16(-o), neg_ext2 = splat16(-ext);
   const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
   bool odd = nc_prologue<false, false>(HE, V, qw, qlen, QR, 0, o, ext);
-  odd |= target_has_odd_base(tw, tlen, TR);
-  if (odd || qlen == 0 || tlen == 0) {
-    const uint32_t slot = atomicAdd(fa.work_count, 1u);
-    fa.worklist[slot] = tid;
+  if (odd || qlen == 0 || tlen == 0) {   // cannot happen (see k_classify); safety net
+    const uint32_t slot = atomicAdd(fa.work_count + 1, 1u);
+    fa.worklist2[slot] = tid;
     return;
   }
   NcTrack tr; tr.best = 0; tr.y = 0; tr.stop = 0; tr.cap = 0;
@@ -1142,7 +1360,7 @@ __global__ void __launch_bounds__(128) k_worklist(const FastArgs fa, int which) 
     p.cs = a.colstate + gtid; p.stride = a.col_stride;
     if (ALGO == ALGO_LOCAL) {
       int best, bq, bt;
-      if (START == START_TB) local_forward<true, false>(a, sc, p, pi, best, bq, bt);
+      if (START == START_TB) { if (a.tb_banded) banded_tb_forward(a, sc, p, pi, best, bq, bt); else local_forward<true, false>(a, sc, p, pi, best, bq, bt); }
       else local_forward<false, false>(a, sc, p, pi, best, bq, bt);
       a.score[pi] = best; a.q_end[pi] = bq; a.t_end[pi] = bt;
       if (START == START_POS) { int sx, sy; local_reverse(sc, p, best, bq, bt, sx, sy); a.q_start[pi] = sx; a.t_start[pi] = sy; }
@@ -1157,7 +1375,14 @@ __global__ void __launch_bounds__(128) k_worklist(const FastArgs fa, int which) 
 __global__ void k_zero_u32(uint32_t* p) { p[0] = 0; p[1] = 0; }
 
 // ---- host side --------------------------------------------------------------------------------------
+#ifndef GB200_BANDED_TB_S16
+#define GB200_BANDED_TB_S16 1
+#endif
 bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
+  if (algo == ALGO_BANDED) {                     // banded traceback = LOCAL recurrence over the tile band; score-only BANDED is another recurrence
+    if (start != START_TB || !GB200_BANDED_TB_S16 || a.k_band < 8) return false;
+    algo = ALGO_LOCAL;
+  }
   if (second || (start == START_TB && algo != ALGO_LOCAL)) return false;
   const uint32_t q8 = (max_q + 7u) & ~7u, t8 = (max_t + 7u) & ~7u;
   if (q8 == 0 || q8 > kFastMaxQ8 || t8 == 0) return false;
@@ -1189,20 +1414,29 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
 #ifndef GB200_LOCAL_G4
 #define GB200_LOCAL_G4 1
 #endif
-int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, uint32_t min_q, uint32_t min_t, cudaStream_t str) {
+int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, uint32_t min_q, uint32_t min_t, cudaStream_t str) {
   (void)min_q; (void)min_t;
+  int algo = algo_in;
   const uint32_t q8 = (max_q + 7u) & ~7u;
   if (fs.cap < (size_t)a.n) {
     if (fs.worklist) cudaFree(fs.worklist);
-    fs.worklist = nullptr;
+    if (fs.flags) cudaFree(fs.flags);
+    fs.worklist = nullptr; fs.flags = nullptr;
     if (cudaMalloc(&fs.worklist, 2 * sizeof(uint32_t) * (size_t)a.n) != cudaSuccess) return -1;     // worklist, then worklist2
+    if (cudaMalloc(&fs.flags, (size_t)a.n) != cudaSuccess) return -1;
     fs.cap = (size_t)a.n;
+  }
+  if (!fs.side) {
+    if (cudaStreamCreateWithFlags(&fs.side, cudaStreamNonBlocking) != cudaSuccess) return -1;
+    if (cudaEventCreateWithFlags(&fs.ev_fork, cudaEventDisableTiming) != cudaSuccess || cudaEventCreateWithFlags(&fs.ev_join, cudaEventDisableTiming) != cudaSuccess) return -1;
   }
   if (!fs.work_count && cudaMalloc(&fs.work_count, 2 * sizeof(uint32_t)) != cudaSuccess) return -1;
   // Pairs with a base outside A/C/G/T: LOCAL / SEMI_GLOBAL re-run them on the N-aware variant of the same s16x2 kernel (one more
   // LOP3 per cell pair); what is left (codes other than N; GLOBAL, whose rule makes N an ordinary symbol) goes to the general
   // int32 kernel, grid-striding over the list with a grid sized for the machine, not for a fixed 64 CTAs.
   const int nbias = (algo == ALGO_SEMI_GLOBAL) ? 2 * a.gap_extend : 0;
+  const bool banded = (algo == ALGO_BANDED);
+  if (banded) algo = ALGO_LOCAL;                 // BANDED + WITH_TB (fast_path_eligible): LOCAL recurrence, banded sweep
   const bool nmask = (algo == ALGO_LOCAL || algo == ALGO_SEMI_GLOBAL) && a.n_score + nbias >= -127 && a.n_score + nbias <= 127;
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint32_t n128 = ((uint32_t)a.n + 127u) & ~127u;
@@ -1214,7 +1448,7 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
     if (cudaMalloc(&fs.colstate, cs_need * sizeof(uint32_t)) != cudaSuccess) return -1;
     fs.colstate_words = cs_need;
   }
-  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.worklist2 = fs.worklist + fs.cap; fa.work_count = fs.work_count;
+  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.worklist2 = fs.worklist + fs.cap; fa.work_count = fs.work_count; fa.flags = fs.flags;
   fa.eight = 8; fa.thirtytwo = 32; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
   const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads;
   if (!fs.attr_set) {
@@ -1230,6 +1464,8 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_global_s16, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_banded_tb_s16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_banded_tb_s16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_local_s16<START_NONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_local_s16<START_POS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_local_s16<START_NONE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -1237,31 +1473,40 @@ int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint
     fs.attr_set = true;
   }
   k_zero_u32<<<1, 1, 0, str>>>(fs.work_count);
+  // which pass scores which pair (one coalesced read of the packed sequences); SEMI_GLOBAL / GLOBAL cannot run empty sequences
+  k_classify<<<((uint32_t)a.n * 32u + 255u) / 256u, 256, 0, str>>>(fa, fs.flags, nmask ? 1 : 0, algo != ALGO_LOCAL, algo == ALGO_GLOBAL);
   const uint32_t blocks = ((uint32_t)a.n + kFastThreads - 1) / kFastThreads;
   const bool sp = (start == START_POS);
   const bool tbm = (start == START_TB);
-  int launches = 3;
+  int launches = 4;
   // grouped arg-max (keys score * 32 + ...) while every possible score stays below 1024, else the per-step keys (score * 8 + ...)
   const uint32_t t8 = (max_t + 7u) & ~7u;
   const bool g4 = GB200_LOCAL_G4 && (uint64_t)std::min(q8, t8) * (uint64_t)a.match <= 1000;
-  if (algo == ALGO_LOCAL) {
+  if (nmask) {
+    // N-aware launch on the side stream, beside the main launch.  Its grid covers the worst case (every pair flagged); CTAs
+    // beyond work_count[0] exit on their first instruction.
+    cudaEventRecord(fs.ev_fork, str);
+    cudaStreamWaitEvent(fs.side, fs.ev_fork, 0);
+    if (banded) k_banded_tb_s16<true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+    else if (algo == ALGO_LOCAL) {
+      if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+      else if (g4) { if (sp) k_local_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
+      else if (sp) k_local_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+    } else { if (sp) k_semiglobal_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
+    cudaEventRecord(fs.ev_join, fs.side);
+    launches++;
+  }
+  if (banded) k_banded_tb_s16<false><<<blocks, kFastThreads, smem, str>>>(fa);
+  else if (algo == ALGO_LOCAL) {
     if (tbm) k_local_s16<START_TB><<<blocks, kFastThreads, smem, str>>>(fa);
     else if (g4) { if (sp) k_local_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
     else if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
   }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
   else k_global_s16<<<blocks, kFastThreads, smem, str>>>(fa);
-  if (nmask) {
-    // the grid covers the worst case (every pair flagged); CTAs beyond work_count[0] exit on their first instruction
-    if (algo == ALGO_LOCAL) {
-      if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, str>>>(fa);
-      else if (g4) { if (sp) k_local_s16<START_POS, true, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, str>>>(fa); }
-      else if (sp) k_local_s16<START_POS, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, str>>>(fa);
-    } else { if (sp) k_semiglobal_s16<START_POS, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, str>>>(fa); }
-    launches++;
-  }
+  if (nmask) cudaStreamWaitEvent(str, fs.ev_join, 0);
   // general kernel over what is left, bounded scratch
-  const int which = nmask ? 1 : 0;
+  const int which = 1;                      // k_classify files everything the s16x2 passes cannot score in worklist2
   fa.a.colstate = fs.colstate; fa.a.col_stride = slots; fa.a.col_rows = q8;
   const int wb = (int)(slots / 128);
   if (algo == ALGO_LOCAL) {

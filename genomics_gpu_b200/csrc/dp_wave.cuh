@@ -47,6 +47,7 @@ struct WaveArgs {
   uint32_t* ticket;          // global ticket counter
   uint32_t* done;            // per pair: finished row-blocks
   int kshift, floor16;       // k_wave16_global: constant subtracted from every biased value; finite -infinity (both fit 16 bits)
+  uint32_t mm, sixteen;      // k_wave16_local_t<true>: 0x00204081 / 16 at run time (the direction-nibble gather stays on IMAD, see dp_s16.cuh)
 };
 
 struct WaveGeom {
@@ -432,6 +433,8 @@ struct Wave16Lane {
   uint32_t bestpk;                // running per-half maxima, packed (fast improvement test)
   int bestL, bestH, bposL, bposH;
 };
+// traceback variant: the direction words (8 nibbles = 8 rows of one column) of the last four columns of both halves
+struct Wave16Tb { uint32_t dL[4], dH[4]; };
 
 // record an improvement of the running maxima: hh = the H values of step k (low half on column k - 2*lane, high half one behind)
 __device__ __forceinline__ void wave16_track(Wave16Lane& L, int k, int ncol, int lane) {
@@ -459,9 +462,10 @@ __device__ __forceinline__ void wave16_track(Wave16Lane& L, int k, int ncol, int
   }
 }
 
-template <bool EXOTIC>
+template <bool EXOTIC, bool TB = false>
 __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const uint2* sin, const uint32_t* ssel, uint2* sout,
-                                             int k0, int kend, int ncol, int lane, uint32_t neg_oe2, uint32_t neg_ext2) {
+                                             int k0, int kend, int ncol, int lane, uint32_t neg_oe2, uint32_t neg_ext2,
+                                             Wave16Tb* T = nullptr, uint4* __restrict__ tbL = nullptr, uint4* __restrict__ tbH = nullptr, uint32_t mm = 0, uint32_t sixteen = 0) {
   for (int k = k0; k < kend; k++) {
     const uint2 top = sin[k & 31];
     const uint32_t v = ssel[(k - 2 * lane) & 127];
@@ -482,6 +486,7 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
 #pragma unroll
     for (int r = 1; r < 8; r++) dg[r] = L.hh[r - 1];
     L.p[0] = up;
+    uint32_t wL = 0, wH = 0;
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       uint32_t s2;
@@ -492,6 +497,7 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
       const uint32_t d = __vadd2(dg[r], s2);
       const uint32_t dm = __vadd2(d, neg_oe2);
       const uint32_t h = __vimax3_s16x2_relu(d, L.f[r], e);
+      if (TB) tb_nibbles(d, dm, h, L.f[r], e, s2, neg_ext2, 0xFFFFFFFFu, mm, sixteen, wL, wH);
       L.f[r] = __viaddmax_s16x2(L.f[r], neg_ext2, dm);
       e = __viaddmax_s16x2(e, neg_ext2, dm);
       L.hh[r] = h; up = h;
@@ -499,13 +505,26 @@ __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const 
     L.out_h = up; L.out_e = e;
     L.vprev = v;
     if (lane == 31) sout[k & 31] = make_uint2((uint32_t)(int)(short)(up >> 16), (uint32_t)(int)(short)(e >> 16));
+    if (TB) {
+      // a half completes a tile (4 query columns x 8 rows, one uint4) when its column index reaches 3 mod 4; tiles of one strip
+      // are consecutive: tile = strip * 2 QR + (column >> 2) (local_kernel_template.h:257,380), tbL / tbH point at the strips' first tiles
+      tb_push(T->dL, wL); tb_push(T->dH, wH);
+      const int cL = k - 2 * lane, cH = cL - 1;
+      if ((cL & 3) == 3 && cL >= 0 && cL < ncol && tbL) tbL[cL >> 2] = make_uint4(T->dL[0], T->dL[1], T->dL[2], T->dL[3]);
+      if ((cH & 3) == 3 && cH >= 0 && cH < ncol && tbH) tbH[cH >> 2] = make_uint4(T->dH[0], T->dH[1], T->dH[2], T->dH[3]);
+    }
   }
 }
 
 #ifndef WAVE16_MIN_CTAS
 #define WAVE16_MIN_CTAS 4
 #endif
-__global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_local(const WaveArgs w) {
+// TB = true: LOCAL WITH_TB for long pairs -- the same pipeline also emits the reference's 4-bit direction codes
+// (local_kernel_template.h:45-60) from the packed lanes (tb_nibbles, dp_common.cuh) in the reference's tile numbering, but into a
+// PER-PAIR region of the matrix (DpArgs::tb_off): long pairs differ in size by orders of magnitude, and the reference layout
+// (tile t of pair p at tb[t * n + p]) would size every pair for the largest one.  k_get_tb walks the region afterwards.
+template <bool TB>
+__global__ void __launch_bounds__(kWaveWarps * 32, TB ? 2 : WAVE16_MIN_CTAS) k_wave16_local_t(const WaveArgs w) {
   __shared__ uint2 s_in[kWaveWarps][32];
   __shared__ uint32_t s_sel[kWaveWarps][128];
   __shared__ uint2 s_out[kWaveWarps][32];
@@ -554,6 +573,16 @@ __global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_loc
 #pragma unroll
     for (int i = 0; i < 4; i++) ssel[lane + 32 * i] = 0x88u;     // columns before 0 / after the end: score 0 or -1
     __syncwarp();
+    Wave16Tb Tb;
+    uint4* tbL = nullptr; uint4* tbH = nullptr;
+    if (TB) {
+#pragma unroll
+      for (int i = 0; i < 4; i++) { Tb.dL[i] = 0; Tb.dH[i] = 0; }
+      uint4* base = a.tb + a.tb_off[pair];
+      const size_t per_strip = (size_t)(ncol >> 2);               // 2 QR tiles per strip
+      if (lstrip < g.nstrips) tbL = base + (size_t)lstrip * per_strip;
+      if (lstrip + 1 < g.nstrips) tbH = base + (size_t)(lstrip + 1) * per_strip;
+    }
 
     const uint4* bnd_in = w.bnd + (uint64_t)((blk + 1) & 1) * w.bnd_stride + w.qoff[pair];
     uint4* bnd_out = w.bnd + (uint64_t)(blk & 1) * w.bnd_stride + w.qoff[pair];
@@ -593,8 +622,8 @@ __global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_loc
         __syncwarp();
       }
       const int kend = min(k0 + 32, nsteps);
-      if (exo_hist & 7) wave16_steps<true>(L, sc, sin, ssel, sout, k0, kend, ncol, lane, neg_oe2, neg_ext2);
-      else wave16_steps<false>(L, sc, sin, ssel, sout, k0, kend, ncol, lane, neg_oe2, neg_ext2);
+      if (exo_hist & 7) wave16_steps<true, TB>(L, sc, sin, ssel, sout, k0, kend, ncol, lane, neg_oe2, neg_ext2, &Tb, tbL, tbH, w.mm, w.sixteen);
+      else wave16_steps<false, TB>(L, sc, sin, ssel, sout, k0, kend, ncol, lane, neg_oe2, neg_ext2, &Tb, tbL, tbH, w.mm, w.sixteen);
       // ---- lane 31's high strip finished columns k0-63 .. kend-64 during this chunk ----
       if (!last_blk) {
         __syncwarp();
@@ -822,7 +851,8 @@ bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t) 
 
 // ---- host side (WaveScratch: dp_launch.h) ----------------------------------------------------------------------
 bool wave_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t min_q, uint32_t min_t) {
-  if (second || start == START_TB) return false;
+  if (second) return false;
+  if (start == START_TB && algo != ALGO_LOCAL) return false;   // traceback: LOCAL on the s16x2 lanes only (the caller checks wave16_eligible)
   if (min_q == 0 || min_t == 0) return false;
   if (a.match < 0 || a.match > 127 || a.mismatch < 0 || a.mismatch > 127) return false;
   if (a.n_score < -127) return false;
@@ -846,23 +876,24 @@ inline void wave_launch_kernel(int algo, int blocks, const WaveArgs& wa, cudaStr
 int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uint32_t* h_qlens, const uint32_t* h_tlens,
                 uint32_t max_t, int n_sm, cudaStream_t str, bool* s16_inout, bool force_s16) {
   const size_t n = (size_t)a.n;
-  if (ws.h_cap < 2 * n) {
+  if (ws.h_cap < 3 * n) {
     if (ws.h_off) cudaFreeHost(ws.h_off);
     ws.h_off = nullptr;
-    if (cudaHostAlloc(&ws.h_off, 2 * n * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) return -1;
-    ws.h_cap = 2 * n;
+    if (cudaHostAlloc(&ws.h_off, 3 * n * sizeof(uint64_t), cudaHostAllocDefault) != cudaSuccess) return -1;
+    ws.h_cap = 3 * n;
   }
   if (ws.n_cap < n) {
     if (ws.qoff) cudaFree(ws.qoff);
     ws.qoff = nullptr;
-    if (cudaMalloc(&ws.qoff, 2 * n * sizeof(uint64_t)) != cudaSuccess) return -1;
-    ws.soff = ws.qoff + n; ws.n_cap = n;
+    if (cudaMalloc(&ws.qoff, 3 * n * sizeof(uint64_t)) != cudaSuccess) return -1;
+    ws.n_cap = n;
   }
-  ws.soff = ws.qoff + ws.n_cap;
-  uint64_t qs = 0, ss = 0, tasks1 = 0, tasks2 = 0;
+  ws.soff = ws.qoff + ws.n_cap; ws.toff = ws.qoff + 2 * ws.n_cap;
+  uint64_t qs = 0, ss = 0, tasks1 = 0, tasks2 = 0, tiles = 0;
   uint32_t max_q = 0;
   for (size_t i = 0; i < n; i++) {
-    ws.h_off[i] = qs; ws.h_off[n + i] = ss;
+    ws.h_off[i] = qs; ws.h_off[n + i] = ss; ws.h_off[2 * n + i] = tiles;
+    tiles += wave_tb_tiles_of(h_qlens[i], h_tlens[i]);
     max_q = std::max(max_q, h_qlens[i]);
     const uint64_t tr = ((uint64_t)h_tlens[i] + 7u) >> 3;
     qs += ((uint64_t)h_qlens[i] + 7u) & ~7ull;
@@ -877,7 +908,9 @@ int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uin
   // GLOBAL: the s16x2 kernel wins once there are two row-blocks per scheduler (16k x 16k: 48 pairs and up, 3670 vs 2757 GCUPS at
   // 128); below that the finer int32 blocks keep more schedulers busy (32 pairs: 2521 vs 1964)
   const bool many16 = (algo == ALGO_GLOBAL) ? (tasks2 >= (uint64_t)n_sm * 8) : many;
-  const bool use_s16 = s16_inout && *s16_inout && (many16 || force_s16);
+  const bool tbm = (start == START_TB);
+  if (tbm && !(s16_inout && *s16_inout && algo == ALGO_LOCAL)) return -1;     // the traceback variant exists for the s16x2 LOCAL kernel only
+  const bool use_s16 = s16_inout && *s16_inout && (many16 || force_s16 || tbm);
   if (s16_inout) *s16_inout = use_s16;
   const int SR = (many || use_s16) ? 2 : 1;
   const uint64_t tasks = (SR == 2) ? tasks2 : tasks1;
@@ -911,11 +944,12 @@ int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uin
   }
   cudaMemcpyAsync(ws.qoff, ws.h_off, n * sizeof(uint64_t), cudaMemcpyHostToDevice, str);
   cudaMemcpyAsync(ws.soff, ws.h_off + n, n * sizeof(uint64_t), cudaMemcpyHostToDevice, str);
-  WaveArgs wa; wa.a = a; wa.algo = algo; wa.maxblk = maxblk; wa.qoff = ws.qoff; wa.soff = ws.soff;
+  if (tbm) cudaMemcpyAsync(ws.toff, ws.h_off + 2 * n, n * sizeof(uint64_t), cudaMemcpyHostToDevice, str);
+  WaveArgs wa; wa.a = a; if (tbm) wa.a.tb_off = ws.toff; wa.algo = algo; wa.maxblk = maxblk; wa.qoff = ws.qoff; wa.soff = ws.soff;
   wa.bnd = ws.bnd; wa.bnd_stride = qs; wa.cand = ws.cand; wa.done = ws.prog; wa.ticket = ws.prog + n;
-  wa.kshift = 0; wa.floor16 = 0;
+  wa.kshift = 0; wa.floor16 = 0; wa.mm = 0x00204081u; wa.sixteen = 16;
   if (use_s16 && algo == ALGO_GLOBAL && !wave16_global_range(a, max_q, max_t, &wa.kshift, &wa.floor16)) return -1;   // cannot happen: checked by wave16_eligible
-  const int ctas_per_sm = use_s16 ? WAVE16_MIN_CTAS : 4;
+  const int ctas_per_sm = tbm ? 2 : (use_s16 ? WAVE16_MIN_CTAS : 4);
   // <= 16 (24) warp-workers per SM.  Once there is at least one CTA (= one warp per scheduler) for every SM, only whole multiples of
   // the SM count are started: a pipeline runs at the pace of its most crowded scheduler, so 1.7 workers per scheduler (two on
   // some, one on others) is slower than one everywhere and a second round of tickets (32 pairs of 16k x 16k: 1651 -> see DESIGN.md)
@@ -927,7 +961,8 @@ int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uin
     cudaMemsetAsync(ws.prog, 0, prog_words * sizeof(uint32_t), str);
     wa.pass = pass; wa.tag_base = ws.next_tag; ws.next_tag += maxblk;
     if (use_s16 && algo == ALGO_GLOBAL) k_wave16_global<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
-    else if (use_s16) k_wave16_local<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
+    else if (use_s16 && tbm) k_wave16_local_t<true><<<blocks, kWaveWarps * 32, 0, str>>>(wa);
+    else if (use_s16) k_wave16_local_t<false><<<blocks, kWaveWarps * 32, 0, str>>>(wa);
     else if (SR == 2) wave_launch_kernel<2>(algo, blocks, wa, str); else wave_launch_kernel<1>(algo, blocks, wa, str);
     launches++;
   }

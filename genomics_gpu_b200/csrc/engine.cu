@@ -77,6 +77,11 @@ struct Priv {
   uint32_t* d_text_lens = nullptr; size_t text_lens_cap = 0;
   uint32_t tb_n = 0; int tb_algo = 0;                         // pairs / algo of the last WITH_TB batch (0: none)
   bool host_packed = false;                                   // the sequence pages hold 4-bit words (latched from g_host_pack at init)
+  // mixed-class batches (per-pair kernel choice): pairs regrouped by length class; [order | q_lens | t_lens | q_offs | t_offs] staged in
+  // pinned memory and mirrored on the device, followed by five compact result arrays
+  uint32_t* mix_host = nullptr; uint32_t* mix_dev = nullptr; size_t mix_cap = 0;
+  FastScratch fast_mix; WaveScratch wave_mix; uint32_t* colstate_mix = nullptr; size_t colstate_mix_words = 0;
+  char kernel_name_buf[48] = "";
   uint32_t fix_n = 0; int fix_kind = 0;                       // gasalx_set_coordinate_fix: 1 local start mirror (Q3), 2 / 3 semi-global default coordinates (Q8; 3: with start)
 };
 
@@ -493,6 +498,10 @@ void gasal_destroy_streams(gasal_gpu_storage_v* gpu_storage_vec, const gasal_par
       if (pv->d_text_lens) CHECKCUDAERROR(cudaFree(pv->d_text_lens));
       pv->fast.release();
       pv->wave.release();
+      pv->fast_mix.release(); pv->wave_mix.release();
+      if (pv->colstate_mix) CHECKCUDAERROR(cudaFree(pv->colstate_mix));
+      if (pv->mix_host) CHECKCUDAERROR(cudaFreeHost(pv->mix_host));
+      if (pv->mix_dev) CHECKCUDAERROR(cudaFree(pv->mix_dev));
       for (int e = 0; e < 4; e++) if (pv->ev[e]) CHECKCUDAERROR(cudaEventDestroy(pv->ev[e]));
       delete pv;
     }
@@ -595,6 +604,87 @@ static void launch_pack(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_byt
 
 struct BatchShape { uint32_t max_q, max_t, min_q, min_t; };
 
+// ---- per-pair kernel choice (one submission, several kernel families) ---------------------------------------------------------
+// The reference runs every pair of a batch on the same one-thread-per-pair kernel.  Here the kernel family depends on the pair's
+// shape, and a plain gasal_aln_async caller may mix shapes freely: when a batch holds both short queries (s16x2 inter-task fast
+// path) and long ones (intra-task wavefront kernel), the pairs are regrouped by class on the host (the lengths are in the
+// caller's pinned arrays anyway), each class runs on its own kernel family over compact copies of the lens / offsets arrays, and
+// one small kernel scatters the compact results back to the caller's pair order.  The sequences themselves do not move.
+// Returns false when the batch is not mixed (or the mode has no mixed path): the caller then dispatches the whole batch as before.
+static bool launch_dp_mixed(gasal_gpu_storage_t* s, uint32_t n, const gasal_params_t* params, const DpArgs& a0, const BatchShape& shape) {
+  Priv* pv = priv(s);
+  const int algo = params->algo, start = params->start_pos;
+  if (g_kernel_policy != 0 || params->secondBest || start == WITH_TB) return false;
+  if (!(algo == LOCAL || algo == SEMI_GLOBAL || algo == GLOBAL)) return false;
+  if (round8(shape.max_q) <= kFastMaxQ8 || round8(shape.min_q) > kFastMaxQ8 || n < 2) return false;   // all short or all long
+  const uint32_t* ql = s->host_query_batch_lens; const uint32_t* tl = s->host_target_batch_lens;
+  BatchShape sh[2];
+  uint32_t cnt[2] = {0, 0};
+  for (int c = 0; c < 2; c++) { sh[c].max_q = sh[c].max_t = 0; sh[c].min_q = sh[c].min_t = 0xFFFFFFFFu; }
+  for (uint32_t i = 0; i < n; i++) {
+    const int c = round8(ql[i]) <= kFastMaxQ8 ? 0 : 1;
+    cnt[c]++;
+    sh[c].max_q = std::max(sh[c].max_q, ql[i]); sh[c].max_t = std::max(sh[c].max_t, tl[i]);
+    sh[c].min_q = std::min(sh[c].min_q, ql[i]); sh[c].min_t = std::min(sh[c].min_t, tl[i]);
+  }
+  if (cnt[0] == 0 || cnt[1] == 0) return false;
+  if (!fast_path_eligible(a0, algo, start, false, sh[0].max_q, sh[0].max_t)) return false;
+  // staging: [order | q_lens | t_lens | q_offs | t_offs] (5n words, pinned + device), then 5n words of compact results on the device
+  if (pv->mix_cap < n) {
+    if (pv->mix_host) CHECKCUDAERROR(cudaFreeHost(pv->mix_host));
+    if (pv->mix_dev) CHECKCUDAERROR(cudaFree(pv->mix_dev));
+    pv->mix_host = nullptr; pv->mix_dev = nullptr;
+    CHECKCUDAERROR(cudaHostAlloc(&pv->mix_host, 5 * (size_t)n * sizeof(uint32_t), cudaHostAllocDefault));
+    CHECKCUDAERROR(cudaMalloc(&pv->mix_dev, 10 * (size_t)n * sizeof(uint32_t)));
+    pv->mix_cap = n;
+  }
+  const size_t N = pv->mix_cap;
+  uint32_t* h = pv->mix_host;
+  uint32_t at[2] = {0, cnt[0]};
+  for (uint32_t i = 0; i < n; i++) {
+    const int c = round8(ql[i]) <= kFastMaxQ8 ? 0 : 1;
+    const uint32_t k = at[c]++;
+    h[k] = i; h[N + k] = ql[i]; h[2 * N + k] = tl[i]; h[3 * N + k] = s->host_query_batch_offsets[i]; h[4 * N + k] = s->host_target_batch_offsets[i];
+  }
+  uint32_t* d = pv->mix_dev;
+  for (int k = 0; k < 5; k++) CHECKCUDAERROR(cudaMemcpyAsync(d + k * N, h + k * N, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice, s->str));
+  int32_t* res[5];
+  for (int k = 0; k < 5; k++) res[k] = (int32_t*)(d + (5 + k) * N);
+  int32_t* dst[5] = {a0.score, a0.q_end, a0.t_end, a0.q_start, a0.t_start};
+  const char* names[2] = {"s16x2", "int32"};
+  for (int c = 0; c < 2; c++) {
+    const uint32_t off = c ? cnt[0] : 0;
+    DpArgs a = a0;
+    a.n = (int)cnt[c];
+    a.q_lens = d + N + off; a.t_lens = d + 2 * N + off; a.q_offs = d + 3 * N + off; a.t_offs = d + 4 * N + off;
+    a.score = res[0] + off; a.q_end = dst[1] ? res[1] + off : nullptr; a.t_end = dst[2] ? res[2] + off : nullptr;
+    a.q_start = dst[3] ? res[3] + off : nullptr; a.t_start = dst[4] ? res[4] + off : nullptr;
+    if (c == 0) {
+      const int nl = fast_path_launch(a, algo, start, pv->fast_mix, sh[0].max_q, sh[0].max_t, sh[0].min_q, sh[0].min_t, s->str);
+      if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); }
+      CHECK_LAUNCH(); pv->launches += nl;
+    } else if (wave_eligible(a, algo, start, false, sh[1].min_q, sh[1].min_t)) {
+      bool s16 = wave16_eligible(a, algo, sh[1].max_q, sh[1].max_t);
+      const int nl = wave_launch(a, algo, start, pv->wave_mix, h + N + off, h + 2 * N + off, sh[1].max_t, device_sms(), s->str, &s16, false);
+      if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the wavefront scratch\n"); }
+      CHECK_LAUNCH(); pv->launches += nl; names[1] = s16 ? "wave16" : "wave";
+    } else {
+      const uint32_t q8 = round8(sh[1].max_q), stride = (cnt[1] + 31u) & ~31u;
+      const size_t need = (size_t)stride * std::max<uint32_t>(q8, 8);
+      if (pv->colstate_mix_words < need) { dev_realloc(&pv->colstate_mix, need); pv->colstate_mix_words = need; }
+      a.colstate = pv->colstate_mix; a.col_stride = stride; a.col_rows = q8;
+      const int nl = generic_launch(a, algo, start, false, s->str);
+      if (nl < 0) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] algo %d is not supported by this build\n", algo); }
+      CHECK_LAUNCH(); pv->launches += nl;
+    }
+  }
+  for (int k = 0; k < 5; k++) if (!dst[k]) res[k] = nullptr;
+  launch_scatter_results(d, n, res, dst, s->str); CHECK_LAUNCH(); pv->launches++;
+  snprintf(pv->kernel_name_buf, sizeof(pv->kernel_name_buf), "mixed(%s+%s)", names[0], names[1]);
+  pv->last_kernel = pv->kernel_name_buf;
+  return true;
+}
+
 static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, const gasal_params_t* params, const BatchShape& shape) {
   Priv* pv = priv(s);
   DpArgs a; memset(&a, 0, sizeof(a));
@@ -612,8 +702,21 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   const int start = params->start_pos;
   const bool want_tb = (start == WITH_TB) && (params->algo == LOCAL || params->algo == GLOBAL || params->algo == BANDED);
 
+  // LOCAL WITH_TB on long pairs: the s16x2 wavefront kernel emits the direction matrix into per-pair regions (DpArgs::tb_off)
+  const bool wave_tb = want_tb && params->algo == LOCAL && !second && g_kernel_policy != 1 && g_kernel_policy != 3 &&
+                       (g_kernel_policy >= 2 || q8 > kFastMaxQ8) && wave_eligible(a, params->algo, start, second, shape.min_q, shape.min_t) &&
+                       wave16_eligible(a, params->algo, shape.max_q, shape.max_t);
   if (want_tb) {
-    if (params->algo == BANDED) {
+    if (wave_tb) {
+      uint64_t tiles = 2;
+      for (uint32_t i = 0; i < n; i++) tiles += wave_tb_tiles_of(s->host_query_batch_lens[i], s->host_target_batch_lens[i]);
+      if (tiles > s->packed_tb_matrix_size) {
+        if (s->packed_tb_matrices) CHECKCUDAERROR(cudaFree(s->packed_tb_matrices));
+        s->packed_tb_matrices = NULL; s->packed_tb_matrix_size = 0;
+        CHECKCUDAERROR(cudaMalloc(&(s->packed_tb_matrices), tiles * sizeof(uint4)));
+        s->packed_tb_matrix_size = tiles;
+      }
+    } else if (params->algo == BANDED) {
       // band matrix: TR strips x W words x 2 tiles, W = widest strip of any pair in the batch (dp_common.cuh band_geom)
       const int qr_max = (int)(q8 >> 3), qr_min = (int)((shape.min_q + 7) >> 3), tr_max = (int)(t8 >> 3), kw = params->k_band >> 3;
       const int w_max = std::max(1, std::min(qr_max, kw + (tr_max - (qr_min - kw)) - 1));
@@ -637,6 +740,9 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
     else if (params->algo == SEMI_GLOBAL && a.head == TARGET && a.tail == TARGET) pv->fix_kind = (start == WITH_START) ? 3 : 2;
   }
 
+  // ---- batches that mix short and long queries: one kernel family per class ----
+  if (launch_dp_mixed(s, n, params, a, shape)) return;
+
   // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
   if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
     const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, shape.min_q, shape.min_t, s->str);
@@ -646,9 +752,19 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
     return;
   }
 
+  if (wave_tb) {
+    bool s16 = true;
+    const int nl = wave_launch(a, params->algo, start, pv->wave, s->host_query_batch_lens, s->host_target_batch_lens, shape.max_t, device_sms(), s->str, &s16, true);
+    if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the wavefront scratch\n"); }
+    CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "wave16";
+    a.tb_off = pv->wave.toff;                                                             // per-pair regions: the walker addresses them the same way
+    launch_get_tb(a, true, s->str); CHECK_LAUNCH(); pv->launches++;                       // gasal_align.h:45-53
+    return;
+  }
+
   // ---- long pairs: intra-task wavefront kernel (dp_wave.cuh) ----
   // policy 0: whenever the batch is too long for the fast path; policy 2: wherever the wavefront kernel is eligible
-  if (g_kernel_policy != 1 && wave_eligible(a, params->algo, start, second, shape.min_q, shape.min_t) &&
+  if (g_kernel_policy != 1 && start != WITH_TB && wave_eligible(a, params->algo, start, second, shape.min_q, shape.min_t) &&
       (g_kernel_policy >= 2 || q8 > kFastMaxQ8)) {
     const int sms = device_sms();
     bool s16 = g_kernel_policy != 3 && wave16_eligible(a, params->algo, shape.max_q, shape.max_t);

@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) k_get_tb(const DpArgs a) {
       tile_no = cell >> 5;
       in_tile = cell - (tile_no << 5);
     }
-    if (tile_no != prev_tile) { tile = a.tb[(size_t)tile_no * a.tb_stride + tid]; prev_tile = tile_no; }
+    if (tile_no != prev_tile) { tile = a.tb_off ? a.tb[a.tb_off[tid] + (uint64_t)tile_no] : a.tb[(size_t)tile_no * a.tb_stride + tid]; prev_tile = tile_no; }
     const int reg_no = in_tile >> 3, cell_in_reg = in_tile & 7;
     const uint32_t reg = reg_no == 0 ? tile.x : (reg_no == 1 ? tile.y : (reg_no == 2 ? tile.z : tile.w));
     const uint32_t cell_op = (reg >> (28 - (cell_in_reg << 2))) & 15u;

@@ -73,3 +73,21 @@ def test_banded_tb_narrow_band_rescoring(oracle):
         # the walker stops ON the first aligned cell (get_tb.h:100-103,142-145): start..end inclusive
         assert got["query_batch_end"][i] - got["query_batch_start"][i] + 1 == q_span
         assert got["target_batch_end"][i] - got["target_batch_start"][i] + 1 == t_span
+
+
+def test_banded_tb_runs_on_the_packed_kernel(oracle):
+    """north_star (4): BANDED + WITH_TB on the s16x2 lanes (k_banded_tb_s16), incl. pairs with N (N-aware pass) and odd band geometry"""
+    b = synth.with_n_bases(synth.config4(4096, seed=45), 0.1, seed=3)
+    want = oracle_align(oracle, b, algo=po.BANDED, start=po.WITH_TB, k_band=64)
+    mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
+    with Aligner(algo=capi.BANDED, start=capi.WITH_TB, k_band=64, max_query_len=mq, max_target_len=mt, max_n_alns=b.n, n_streams=1) as al:
+        got = al.align(b)
+        assert al.kernel_name(0) == "s16x2"
+    assert_same(got, want, K5 + ["n_cigar_ops"], "banded tb s16x2, C4 shape with N")
+    assert cigar_slices(got, b) == cigar_slices(want, b)
+    for k_band, qmax, tmax in ((8, 40, 330), (24, 220, 60), (40, 330, 330), (4096, 100, 200)):
+        b = synth.random_ragged_pairs(500, 9, qmax, 9, tmax, seed=600 + k_band, n_frac=0.01)
+        want = oracle_align(oracle, b, algo=po.BANDED, start=po.WITH_TB, k_band=k_band)
+        got = run(b, algo=capi.BANDED, start=capi.WITH_TB, k_band=k_band)
+        assert_same(got, want, K5 + ["n_cigar_ops"], f"banded tb s16x2 k={k_band} q<={qmax} t<={tmax}")
+        assert cigar_slices(got, b) == cigar_slices(want, b)

@@ -148,3 +148,31 @@ def test_wave_matches_general_kernel_on_mixed_lengths(oracle):
     w = run(b, policy=0, algo=capi.LOCAL, start=capi.WITH_START)
     assert a["_kernel"] == "int32" and w["_kernel"] in ("wave", "wave16")
     assert_same(w, a, K5, "wave vs general kernel, mixed lengths")
+
+
+@pytest.mark.parametrize("scoring", [(1, 4, 6, 1), (2, 3, 5, 2)])
+def test_wave16_local_traceback_long_pairs(oracle, scoring):
+    """LOCAL WITH_TB on long pairs (missing #3): the s16x2 wavefront kernel emits the direction matrix into per-pair
+    regions and k_get_tb walks them -- no fall-back to the one-thread-per-pair int32 kernel.  CIGAR bytes, starts, ends vs the oracle."""
+    from helpers import cigar_slices, cigar_rescore
+    b = long_pairs(410 + scoring[0], n=20, lo=400, hi=4000)
+    want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_TB, scoring=scoring, max_query_len=8192)
+    got = run(b, policy=0, algo=capi.LOCAL, start=capi.WITH_TB, scoring=scoring)
+    assert got["_kernel"] == "wave16"
+    assert_same(got, want, K5 + ["n_cigar_ops"], f"wave16 local WITH_TB {scoring}")
+    gc, wc = cigar_slices(got, b), cigar_slices(want, b)
+    assert gc == wc
+    if scoring == (1, 4, 6, 1):
+        for i, c in enumerate(gc):
+            assert cigar_rescore(c, scoring) == got["aln_score"][i]
+
+
+def test_wave16_local_traceback_ragged_short(oracle):
+    """the same kernel forced onto ragged short pairs (policy 4): one-strip targets, partial row-blocks, pads, N and IUPAC columns"""
+    from helpers import cigar_slices
+    b = ragged(415, n=400)
+    want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_TB)
+    got = run(b, policy=4, algo=capi.LOCAL, start=capi.WITH_TB)
+    assert got["_kernel"] == "wave16"
+    assert_same(got, want, K5 + ["n_cigar_ops"], "wave16 local WITH_TB ragged")
+    assert cigar_slices(got, b) == cigar_slices(want, b)
