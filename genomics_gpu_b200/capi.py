@@ -91,7 +91,7 @@ EXPORTED_SYMBOLS = [
     "gasal_host_alns_resize", "gasal_op_fill", "gasal_set_device",
     "gasal_res_new_host", "gasal_res_new_device", "gasal_res_new_device_cpy", "gasal_res_destroy_host", "gasal_res_destroy_device",
     "gasalx_set_n_code", "gasalx_set_kernel_policy", "gasalx_set_revcomp_mode", "gasalx_set_coordinate_fix", "gasalx_set_host_packing", "gasalx_storage_host_packed",
-    "gasalx_set_host_write_combined", "gasalx_span_ms", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
+    "gasalx_set_host_write_combined", "gasalx_set_fast_path_passes", "gasalx_span_ms", "gasalx_last_batch_ms", "gasalx_kernel_launches", "gasalx_last_kernel_name",
     "gasalx_aln_device_resident", "gasalx_host_batch_rearm", "gasalx_version",
     "gasalx_sched_default", "gasalx_plan_batches", "gasalx_align_all", "gasalx_batcher_release",
     "gasalx_read_fasta_pairs", "gasalx_free_fasta_pairs", "gasalx_pack_host", "gasalx_pack_host_at", "gasalx_cigar_string",
@@ -140,6 +140,7 @@ def load() -> C.CDLL:
     lib.gasalx_set_revcomp_mode.argtypes = [C.c_int]
     lib.gasalx_set_host_packing.argtypes = [C.c_int]
     lib.gasalx_set_host_write_combined.argtypes = [C.c_int]
+    lib.gasalx_set_fast_path_passes.argtypes = [C.c_int]
     lib.gasalx_storage_host_packed.argtypes = [P(GpuStorage)]; lib.gasalx_storage_host_packed.restype = C.c_int
     lib.gasalx_span_ms.argtypes = [P(P(GpuStorage)), C.c_int, P(C.c_float)]; lib.gasalx_span_ms.restype = C.c_int
     lib.gasal_gpu_mem_alloc.argtypes = [P(GpuStorage), C.c_int, C.c_int, C.c_int, P(Params)]

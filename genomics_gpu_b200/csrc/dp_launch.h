@@ -14,7 +14,7 @@ constexpr uint32_t kFastMaxQ8 = 352;      // (q8 + kSlotPad) * 128 * 5 B must fi
 struct FastScratch {
   uint32_t* worklist = nullptr; uint32_t* work_count = nullptr; size_t cap = 0;       // worklist[cap] (pairs with N), worklist2[cap] (general kernel)
   uint32_t* colstate = nullptr; size_t colstate_words = 0;
-  uint8_t* flags = nullptr;                                                            // k_classify: pass of every pair
+  uint32_t* flags = nullptr;                                                           // k_classify: pass bits of every pair
   cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr, ev_join = nullptr;       // the N-aware launch runs beside the main launch
   bool attr_set = false;
   void release() {
@@ -31,7 +31,8 @@ struct FastScratch {
 
 bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t);
 // returns the number of kernel launches, or -1 when a scratch allocation failed
-int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, uint32_t min_q, uint32_t min_t, cudaStream_t str);
+// maybe_odd: the batch may hold bases outside A/C/G/T (false: the host packer saw none, the extra passes are skipped)
+int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, bool maybe_odd, int force_passes, cudaStream_t str);
 
 // ---- intra-task wavefront kernels (dp_wave.cuh) ---------------------------------------------------------------------
 struct WaveScratch {

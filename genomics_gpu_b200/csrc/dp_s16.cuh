@@ -39,7 +39,8 @@ struct FastArgs {
   uint32_t q8max;          // columns reserved per thread in shared memory (multiple of 8)
   uint32_t* worklist; uint32_t* work_count;     // pairs with a base outside A/C/G/T (filled by the main launch; counts: work_count[0], [1])
   uint32_t* worklist2;                          // pairs the N-aware pass cannot represent either (codes other than A/C/G/T/N): general kernel
-  const uint8_t* flags;                         // k_classify: 0 = pure A/C/G/T pair (main launch), else listed in worklist / worklist2
+  const uint32_t* flags;                        // k_classify: 0 = pure A/C/G/T pair (main launch), bit 0: N (worklist), bit 1: general kernel (worklist2);
+                                                // nullptr: the host packer saw nothing but A/C/G/T in this batch, there is nothing to skip
   uint32_t eight;          // == 8, passed at run time so the key multiply stays an IMAD (FMA pipe)
   uint32_t thirtytwo;      // == 32, same for the grouped arg-max keys
   uint32_t one;            // == 1, run-time so that the sweep's trip count (columns + 1) is opaque to the unroller
@@ -691,37 +692,49 @@ __device__ __forceinline__ uint8_t col_selector(uint32_t code, bool pad, uint32_
 }
 
 // ---- k_classify: which pass scores a pair? --------------------------------------------------------------------------------
-// One WARP per pair reads its packed words once (coalesced) and files the pair: 0 = only A/C/G/T inside the true lengths (main
-// launch), 1 = also N (N-aware launch, worklist), 2 = any other code or an empty sequence (general kernel, worklist2).  Because
-// the lists exist BEFORE the main launch, the N-aware launch runs beside it on a second stream instead of behind it, so a batch
-// with 1 % of N-carrying reads no longer pays a whole extra (nearly empty) wave, and the main kernel needs no target scan.
-__global__ void __launch_bounds__(256) k_classify(const FastArgs fa, uint8_t* __restrict__ flags, int nmask_ok, int zero_q_is_odd, int zero_t_is_odd) {
+// The packed sequences are read once, EIGHT WORDS PER THREAD (thread t: pair t / chunks, words 8 (t % chunks) .. + 7 of the pair's
+// query-then-target word sequence; neighbouring threads read neighbouring 32-byte pieces), and every pair that holds a base outside
+// A/C/G/T inside its true lengths is flagged and listed: bit 0 = an N (N-aware launch, worklist), bit 1 = any other code or an
+// empty sequence (general kernel, worklist2; wins over bit 0).  Because the lists exist BEFORE the main launch, the N-aware launch
+// runs beside it on a second stream instead of behind it, so a batch with 1 % of N-carrying reads no longer pays a whole extra
+// (nearly empty) wave, and the main kernel needs no target scan.  flags[] is zeroed by the launcher.
+__global__ void __launch_bounds__(256) k_classify(const FastArgs fa, uint32_t* __restrict__ flags, uint32_t chunks, int nmask_ok, int zero_q_is_odd, int zero_t_is_odd) {
   const DpArgs& a = fa.a;
-  const uint32_t pair = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t pair = t / chunks, chunk = t - pair * chunks;
   if (pair >= (uint32_t)a.n) return;
   const uint32_t qlen = a.q_lens[pair], tlen = a.t_lens[pair];
-  const uint32_t* qw = a.pq + (a.q_offs[pair] >> 3);
-  const uint32_t* tw = a.pt + (a.t_offs[pair] >> 3);
   const uint32_t nq = n_words(qlen), nt = n_words(tlen), nval = a.n_value;
   uint32_t odd = 0, exo = 0;
-  for (uint32_t w = lane; w < nq + nt; w += 32) {
-    const bool isq = w < nq;
-    const uint32_t wi = isq ? w : w - nq, len = isq ? qlen : tlen;
-    const uint32_t x = isq ? qw[wi] : tw[wi];
-    const uint32_t left = len - 8 * wi;                                  // >= 1 bases of this word are real
-    const uint32_t m = left >= 8 ? 0x11111111u : (0x11111111u << (4 * (8 - left)));
-    odd |= odd_nibbles(x) & m; exo |= exotic_nibbles(x, nval) & m;
-  }
-  const bool any_odd = __any_sync(0xFFFFFFFFu, odd != 0), any_exo = __any_sync(0xFFFFFFFFu, exo != 0);
-  if (lane == 0) {
-    int kind = any_exo ? 2 : (any_odd ? 1 : 0);
-    if ((zero_q_is_odd && qlen == 0) || (zero_t_is_odd && tlen == 0)) kind = 2;
-    if (kind == 1 && !nmask_ok) kind = 2;
-    flags[pair] = (uint8_t)kind;
-    if (kind) {
-      const uint32_t slot = atomicAdd(fa.work_count + (kind - 1), 1u);
-      (kind == 1 ? fa.worklist : fa.worklist2)[slot] = pair;
+  bool bX = (chunk == 0) && ((zero_q_is_odd && qlen == 0) || (zero_t_is_odd && tlen == 0));
+  const uint32_t w0 = 8 * chunk;
+  if (w0 < nq + nt) {
+    const uint32_t* qw = a.pq + (a.q_offs[pair] >> 3);
+    const uint32_t* tw = a.pt + (a.t_offs[pair] >> 3);
+    uint32_t x[8];
+#pragma unroll
+    for (int i = 0; i < 8; i++) {                                       // all loads first: eight independent requests per thread
+      const uint32_t w = w0 + i;
+      x[i] = (w < nq) ? qw[w] : ((w < nq + nt) ? tw[w - nq] : 0x11111111u);
     }
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+      const uint32_t w = w0 + i;
+      if (w >= nq + nt) continue;
+      const bool isq = w < nq;
+      const uint32_t left = (isq ? qlen : tlen) - 8 * (isq ? w : w - nq);  // >= 1 bases of this word are real
+      const uint32_t m = left >= 8 ? 0x11111111u : (0x11111111u << (4 * (8 - left)));
+      odd |= odd_nibbles(x[i]) & m; exo |= exotic_nibbles(x[i], nval) & m;
+    }
+  }
+  bX |= (exo != 0);
+  bool bN = (odd & ~exo) != 0;
+  if (!nmask_ok) { bX |= bN; bN = false; }
+  if (bN || bX) {
+    const uint32_t bits = (bN ? 1u : 0u) | (bX ? 2u : 0u);
+    const uint32_t old = atomicOr(flags + pair, bits);
+    if ((bits & 2u) && !(old & 2u)) fa.worklist2[atomicAdd(fa.work_count + 1, 1u)] = pair;
+    if ((bits & 1u) && !(old & 1u)) fa.worklist[atomicAdd(fa.work_count, 1u)] = pair;
   }
 }
 
@@ -730,8 +743,8 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }     // N-aware pass: one thread per flagged pair
-  else { if (tid >= (uint32_t)a.n) return; if (fa.flags[tid]) return; }           // flagged pairs belong to the other passes (k_classify)
+  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; if (fa.flags[tid] & 2u) return; }   // N-aware pass: one thread per listed pair
+  else { if (tid >= (uint32_t)a.n) return; if (fa.flags && fa.flags[tid]) return; }   // flagged pairs belong to the other passes (k_classify)
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
 
@@ -856,8 +869,8 @@ __global__ void __launch_bounds__(kFastThreads) k_banded_tb_s16(const FastArgs f
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }
-  else { if (tid >= (uint32_t)a.n) return; if (fa.flags[tid]) return; }
+  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; if (fa.flags[tid] & 2u) return; }
+  else { if (tid >= (uint32_t)a.n) return; if (fa.flags && fa.flags[tid]) return; }
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
@@ -1232,8 +1245,8 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
-  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; }     // N-aware pass: one thread per flagged pair
-  else { if (tid >= (uint32_t)a.n) return; if (fa.flags[tid]) return; }           // flagged pairs belong to the other passes (k_classify)
+  if (NMASK) { if (tid >= fa.work_count[0]) return; tid = fa.worklist[tid]; if (fa.flags[tid] & 2u) return; }   // N-aware pass: one thread per listed pair
+  else { if (tid >= (uint32_t)a.n) return; if (fa.flags && fa.flags[tid]) return; }   // flagged pairs belong to the other passes (k_classify)
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
@@ -1300,7 +1313,7 @@ __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) 
   const DpArgs& a = fa.a;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
   if (tid >= (uint32_t)a.n) return;
-  if (fa.flags[tid]) return;                                     // general kernel (k_classify)
+  if (fa.flags && fa.flags[tid]) return;                         // general kernel (k_classify)
   uint32_t* HE = smem + 2 * kFastThreads + threadIdx.x;          // slot s holds column s - 1; slots -2..0 are dummies
   uint8_t* V = (uint8_t*)(smem + (fa.q8max + kSlotPad) * kFastThreads) + threadIdx.x;
   const uint32_t* qw = a.pq + (a.q_offs[tid] >> 3);
@@ -1414,16 +1427,16 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
 #ifndef GB200_LOCAL_G4
 #define GB200_LOCAL_G4 1
 #endif
-int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, uint32_t min_q, uint32_t min_t, cudaStream_t str) {
-  (void)min_q; (void)min_t;
+int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, bool maybe_odd, int force_passes, cudaStream_t str) {
   int algo = algo_in;
+  const bool passes = maybe_odd || force_passes;        // false: nothing but A/C/G/T in this batch (host packer): one launch, no lists
   const uint32_t q8 = (max_q + 7u) & ~7u;
   if (fs.cap < (size_t)a.n) {
     if (fs.worklist) cudaFree(fs.worklist);
     if (fs.flags) cudaFree(fs.flags);
     fs.worklist = nullptr; fs.flags = nullptr;
     if (cudaMalloc(&fs.worklist, 2 * sizeof(uint32_t) * (size_t)a.n) != cudaSuccess) return -1;     // worklist, then worklist2
-    if (cudaMalloc(&fs.flags, (size_t)a.n) != cudaSuccess) return -1;
+    if (cudaMalloc(&fs.flags, sizeof(uint32_t) * (size_t)a.n) != cudaSuccess) return -1;
     fs.cap = (size_t)a.n;
   }
   if (!fs.side) {
@@ -1448,7 +1461,7 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     if (cudaMalloc(&fs.colstate, cs_need * sizeof(uint32_t)) != cudaSuccess) return -1;
     fs.colstate_words = cs_need;
   }
-  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.worklist2 = fs.worklist + fs.cap; fa.work_count = fs.work_count; fa.flags = fs.flags;
+  FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.worklist2 = fs.worklist + fs.cap; fa.work_count = fs.work_count; fa.flags = passes ? fs.flags : nullptr;
   fa.eight = 8; fa.thirtytwo = 32; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
   const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads;
   if (!fs.attr_set) {
@@ -1473,16 +1486,22 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     fs.attr_set = true;
   }
   k_zero_u32<<<1, 1, 0, str>>>(fs.work_count);
-  // which pass scores which pair (one coalesced read of the packed sequences); SEMI_GLOBAL / GLOBAL cannot run empty sequences
-  k_classify<<<((uint32_t)a.n * 32u + 255u) / 256u, 256, 0, str>>>(fa, fs.flags, nmask ? 1 : 0, algo != ALGO_LOCAL, algo == ALGO_GLOBAL);
+  int launches = 2;
+  if (passes) {
+    // which pass scores which pair (one coalesced read of the packed sequences); SEMI_GLOBAL / GLOBAL cannot run empty sequences
+    cudaMemsetAsync(fs.flags, 0, sizeof(uint32_t) * (size_t)a.n, str);
+    const uint32_t chunks = std::max<uint32_t>(1u, (((max_q + 7u) >> 3) + ((max_t + 7u) >> 3) + 7u) / 8u);
+    const uint64_t threads = (uint64_t)a.n * chunks;
+    k_classify<<<(uint32_t)((threads + 255) / 256), 256, 0, str>>>(fa, fs.flags, chunks, nmask ? 1 : 0, algo != ALGO_LOCAL, algo == ALGO_GLOBAL);
+    launches += 2;
+  }
   const uint32_t blocks = ((uint32_t)a.n + kFastThreads - 1) / kFastThreads;
   const bool sp = (start == START_POS);
   const bool tbm = (start == START_TB);
-  int launches = 4;
   // grouped arg-max (keys score * 32 + ...) while every possible score stays below 1024, else the per-step keys (score * 8 + ...)
   const uint32_t t8 = (max_t + 7u) & ~7u;
   const bool g4 = GB200_LOCAL_G4 && (uint64_t)std::min(q8, t8) * (uint64_t)a.match <= 1000;
-  if (nmask) {
+  if (nmask && passes) {
     // N-aware launch on the side stream, beside the main launch.  Its grid covers the worst case (every pair flagged); CTAs
     // beyond work_count[0] exit on their first instruction.
     cudaEventRecord(fs.ev_fork, str);
@@ -1504,7 +1523,8 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
   }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
   else k_global_s16<<<blocks, kFastThreads, smem, str>>>(fa);
-  if (nmask) cudaStreamWaitEvent(str, fs.ev_join, 0);
+  if (nmask && passes) cudaStreamWaitEvent(str, fs.ev_join, 0);
+  if (!passes) return launches;             // (the kernels' own safety-net lists stay empty: the packer's verdict is exact)
   // general kernel over what is left, bounded scratch
   const int which = 1;                      // k_classify files everything the s16x2 passes cannot score in worklist2
   fa.a.colstate = fs.colstate; fa.a.col_stride = slots; fa.a.col_rows = q8;

@@ -60,7 +60,8 @@ int g_kernel_policy = 0;
 int g_revcomp_mode = 0;
 int g_coord_fix = 0;
 int g_host_pack = 1;      // gasalx_set_host_packing: gasal_host_batch_fill / _add pack to 4 bits while they copy (0.5 B per base over PCIe)
-int g_host_wc = 0;        // gasalx_set_host_write_combined: sequence pages in write-combined pinned memory
+int g_host_wc = 0;
+int g_fast_passes = 0;    // gasalx_set_fast_path_passes: 1 = always run the classification / N-aware / general passes (testing)        // gasalx_set_host_write_combined: sequence pages in write-combined pinned memory
 
 struct Priv {
   uint32_t* colstate = nullptr; size_t colstate_words = 0;
@@ -77,6 +78,9 @@ struct Priv {
   uint32_t* d_text_lens = nullptr; size_t text_lens_cap = 0;
   uint32_t tb_n = 0; int tb_algo = 0;                         // pairs / algo of the last WITH_TB batch (0: none)
   bool host_packed = false;                                   // the sequence pages hold 4-bit words (latched from g_host_pack at init)
+  // host-packed pages: did the packer see a base outside A/C/G/T since the pages were last reset?  A clean batch skips the
+  // classification kernel and the N-aware / general passes of the s16x2 fast path.  (`saved`: state before the last reset, for rearm)
+  bool host_odd = false, host_odd_saved = false;
   // mixed-class batches (per-pair kernel choice): pairs regrouped by length class; [order | q_lens | t_lens | q_offs | t_offs] staged in
   // pinned memory and mirrored on the device, followed by five compact result arrays
   uint32_t* mix_host = nullptr; uint32_t* mix_dev = nullptr; size_t mix_cap = 0;
@@ -126,6 +130,7 @@ void gasalx_set_revcomp_mode(int mode) { g_revcomp_mode = mode; }
 void gasalx_set_coordinate_fix(int on) { g_coord_fix = on; }
 void gasalx_set_host_packing(int on) { g_host_pack = on ? 1 : 0; }
 void gasalx_set_host_write_combined(int on) { g_host_wc = on ? 1 : 0; }
+void gasalx_set_fast_path_passes(int always) { g_fast_passes = always ? 1 : 0; }
 int gasalx_storage_host_packed(const gasal_gpu_storage_t* s) { const Priv* pv = (const Priv*)s->b200_priv; return (pv && pv->host_packed) ? 1 : 0; }
 
 void gasal_copy_subst_scores(gasal_subst_scores* subst) { g_scores = *subst; }   // src/gasal_align.cu:329-339
@@ -225,7 +230,7 @@ static uint32_t packed_page_write(gasal_gpu_storage_t* s, uint32_t idx, const ch
   uint32_t* p_batch_bytes = (SRC == QUERY) ? &s->host_max_query_batch_bytes : &s->host_max_target_batch_bytes;
   const uint64_t end = (uint64_t)idx + size + pad;
   packed_page_reserve(s, page, p_batch_bytes, end, SRC);
-  gb200::pack_bases_at((uint32_t*)page->data, idx, (const uint8_t*)data, size);
+  if (gb200::pack_bases_at_odd((uint32_t*)page->data, idx, (const uint8_t*)data, size)) priv(s)->host_odd = true;
   if (pad) gb200::fill_nibbles_at((uint32_t*)page->data, (uint64_t)idx + size, pad, (uint32_t)g_n_code & 15u);
   if (page->data_size < end) page->data_size = (uint32_t)end;
   return (uint32_t)end;
@@ -244,6 +249,7 @@ void gasal_host_batch_destroy(host_batch_t* res) {
 host_batch_t* gasal_host_batch_getlast(host_batch_t* arg) { while (arg->next != NULL) arg = arg->next; return arg; }
 
 void gasal_host_batch_reset(gasal_gpu_storage_t* gpu_storage) {   // :49-75
+  if (priv(gpu_storage)) { priv(gpu_storage)->host_odd_saved = priv(gpu_storage)->host_odd; priv(gpu_storage)->host_odd = false; }
   host_batch_t* heads[2] = {gpu_storage->extensible_host_unpacked_query_batch, gpu_storage->extensible_host_unpacked_target_batch};
   for (int i = 0; i < 2; i++)
     for (host_batch_t* cur = heads[i]; cur != NULL; cur = cur->next) { cur->data_size = 0; cur->offset = 0; cur->is_locked = 0; }
@@ -660,7 +666,7 @@ static bool launch_dp_mixed(gasal_gpu_storage_t* s, uint32_t n, const gasal_para
     a.score = res[0] + off; a.q_end = dst[1] ? res[1] + off : nullptr; a.t_end = dst[2] ? res[2] + off : nullptr;
     a.q_start = dst[3] ? res[3] + off : nullptr; a.t_start = dst[4] ? res[4] + off : nullptr;
     if (c == 0) {
-      const int nl = fast_path_launch(a, algo, start, pv->fast_mix, sh[0].max_q, sh[0].max_t, sh[0].min_q, sh[0].min_t, s->str);
+      const int nl = fast_path_launch(a, algo, start, pv->fast_mix, sh[0].max_q, sh[0].max_t, !(pv->host_packed && !pv->host_odd), g_fast_passes, s->str);
       if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); }
       CHECK_LAUNCH(); pv->launches += nl;
     } else if (wave_eligible(a, algo, start, false, sh[1].min_q, sh[1].min_t)) {
@@ -745,7 +751,7 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
 
   // ---- fast path: s16x2 DPX kernels (dp_s16.cuh) ----
   if (g_kernel_policy == 0 && fast_path_eligible(a, params->algo, start, second, shape.max_q, shape.max_t)) {
-    const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, shape.min_q, shape.min_t, s->str);
+    const int nl = fast_path_launch(a, params->algo, start, pv->fast, shape.max_q, shape.max_t, !(pv->host_packed && !pv->host_odd), g_fast_passes, s->str);
     if (nl < 0) { GASAL_FAIL(GASALX_E_NOMEM, "[GASAL CUDA ERROR:] out of device memory for the fast-path scratch\n"); }
     CHECK_LAUNCH(); pv->launches += nl; pv->last_kernel = "s16x2";
     if (want_tb) { launch_get_tb(a, true, s->str); CHECK_LAUNCH(); pv->launches++; }      // gasal_align.h:45-53
@@ -890,6 +896,7 @@ void gasal_aln_async(gasal_gpu_storage_t* s, const uint32_t actual_query_batch_b
 
 void gasalx_aln_device_resident(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n, const gasal_params_t* params) {
   Priv* pv = priv(s);
+  pv->host_odd = pv->host_odd_saved;                              // the device still holds the batch that was uploaded last
   BatchShape shape = scan_shape(s, n, pv, true);
   CHECKCUDAERROR(cudaEventRecord(pv->ev[0], s->str));
   device_stage(s, q_bytes, t_bytes, n, params, shape);
@@ -961,6 +968,7 @@ int gasalx_span_ms(gasal_gpu_storage_t* const* storages, int n, float* out_ms) {
 }
 
 void gasalx_host_batch_rearm(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t t_bytes, uint32_t n_alns) {
+  if (priv(s)) priv(s)->host_odd = priv(s)->host_odd_saved;       // the same bytes are still in the pages
   host_batch_t* heads[2] = {s->extensible_host_unpacked_query_batch, s->extensible_host_unpacked_target_batch};
   uint32_t want[2] = {q_bytes, t_bytes};
   for (int i = 0; i < 2; i++) {

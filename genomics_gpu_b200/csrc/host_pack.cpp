@@ -38,6 +38,39 @@ __attribute__((target("avx2"))) static void pack_words_avx2(const uint8_t* src, 
   for (; w < nw; w++) dst[w] = pack8_scalar(src + 8 * w);
 }
 
+// ---- "does the data hold a base outside A/C/G/T?" while packing (nibbles 1, 3, 4, 7 are A, C, T, G) --------------------------
+static inline bool odd_nibble(uint32_t n) { n &= 15u; return !(n == 1u || n == 3u || n == 4u || n == 7u); }
+
+static bool pack_words_scalar_odd(const uint8_t* src, uint64_t nw, uint32_t* dst) {
+  bool odd = false;
+  for (uint64_t w = 0; w < nw; w++) {
+    const uint8_t* b = src + 8 * w;
+    for (int k = 0; k < 8; k++) odd |= odd_nibble(b[k]);
+    dst[w] = pack8_scalar(b);
+  }
+  return odd;
+}
+
+__attribute__((target("avx2"))) static bool pack_words_avx2_odd(const uint8_t* src, uint64_t nw, uint32_t* dst) {
+  const __m256i lo4 = _mm256_set1_epi8(0x0F), mul = _mm256_set1_epi16(0x0110);
+  const __m256i rev = _mm256_setr_epi8(3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12, 3, 2, 1, 0, 7, 6, 5, 4, 11, 10, 9, 8, 15, 14, 13, 12);
+  // table over the 16 nibble values: 0 for A/C/G/T (1, 3, 7, 4), 0xFF otherwise
+  const __m256i bad = _mm256_setr_epi8(-1, 0, -1, 0, 0, -1, -1, 0, -1, -1, -1, -1, -1, -1, -1, -1, -1, 0, -1, 0, 0, -1, -1, 0, -1, -1, -1, -1, -1, -1, -1, -1);
+  __m256i acc = _mm256_setzero_si256();
+  uint64_t w = 0;
+  for (; w + 4 <= nw; w += 4) {
+    const __m256i x = _mm256_and_si256(_mm256_loadu_si256((const __m256i*)(src + 8 * w)), lo4);
+    acc = _mm256_or_si256(acc, _mm256_shuffle_epi8(bad, x));
+    const __m256i m = _mm256_maddubs_epi16(x, mul);
+    const __m256i p = _mm256_shuffle_epi8(_mm256_packus_epi16(m, m), rev);
+    const __m256i q = _mm256_permute4x64_epi64(p, 0x08);
+    _mm_storeu_si128((__m128i*)(dst + w), _mm256_castsi256_si128(q));
+  }
+  bool odd = !_mm256_testz_si256(acc, acc);
+  for (; w < nw; w++) { const uint8_t* b = src + 8 * w; for (int k = 0; k < 8; k++) odd |= odd_nibble(b[k]); dst[w] = pack8_scalar(b); }
+  return odd;
+}
+
 static bool have_avx2() {
   static const bool v = __builtin_cpu_supports("avx2");
   return v;
@@ -58,6 +91,18 @@ void pack_bases_at(uint32_t* words, uint64_t pos, const uint8_t* src, uint64_t n
   const uint64_t nw = n >> 3;
   if (nw) { pack_words(src, nw, words + (pos >> 3)); pos += 8 * nw; src += 8 * nw; n -= 8 * nw; }
   while (n) { set_nibble(words, pos, *src); pos++; src++; n--; }
+}
+
+bool pack_bases_at_odd(uint32_t* words, uint64_t pos, const uint8_t* src, uint64_t n) {
+  bool odd = false;
+  while (n && (pos & 7)) { odd |= odd_nibble(*src); set_nibble(words, pos, *src); pos++; src++; n--; }
+  const uint64_t nw = n >> 3;
+  if (nw) {
+    odd |= have_avx2() ? pack_words_avx2_odd(src, nw, words + (pos >> 3)) : pack_words_scalar_odd(src, nw, words + (pos >> 3));
+    pos += 8 * nw; src += 8 * nw; n -= 8 * nw;
+  }
+  while (n) { odd |= odd_nibble(*src); set_nibble(words, pos, *src); pos++; src++; n--; }
+  return odd;
 }
 
 void fill_nibbles_at(uint32_t* words, uint64_t pos, uint64_t n, uint32_t code) {

@@ -242,6 +242,10 @@ int gasalx_storage_host_packed(const gasal_gpu_storage_t* gpu_storage);
 /* 1: allocate the sequence pages as write-combined pinned memory (cudaHostAllocWriteCombined): faster for the DMA engine to read on
  * some hosts, slow for the CPU to read back.  Default 0. */
 void gasalx_set_host_write_combined(int on);
+/* The s16x2 fast path files every pair with a base outside A/C/G/T for its N-aware / general passes (a classification kernel reads
+ * the packed sequences once).  With host packing the packer already knows whether a batch holds any such base, and a clean batch
+ * skips those launches.  1 = run them regardless (testing); default 0. */
+void gasalx_set_fast_path_passes(int always);
 
 /* Device-side timing of the last finished batch of a storage, in milliseconds, measured with CUDA
  * events on gpu_storage->str: [0] whole pipeline (first H2D .. last D2H), [1] pack(+revcomp),

@@ -91,3 +91,38 @@ def test_deprecated_gpu_mem_alloc_free_link_and_run():
     lib.gasal_gpu_mem_free(C.byref(s), C.byref(p))
     assert not s.packed_query_batch and not s.query_batch_lens
     lib.gasal_destroy_gpu_storage_v(C.byref(v))
+
+
+def test_clean_batches_skip_the_extra_passes(oracle):
+    """host packing knows whether a batch holds any base outside A/C/G/T (pads excluded when gasal_host_batch_fill writes them): a clean
+    batch runs ONE DP launch; the same batch with real N bases runs classification + the N-aware pass; both equal the oracle"""
+    lib = capi.load()
+    clean = synth.make_read_window_pairs(3000, 152, 304, sub=0.03, indel=0.003, seed=4400)        # lengths are multiples of 8: no pads at all
+    dirty = synth.with_n_bases(clean, 0.05, seed=4401)
+    for name, b, want_launches in (("clean", clean, 2), ("with N", dirty, None)):
+        want = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_START)
+        with Aligner(algo=capi.LOCAL, start=capi.WITH_START, max_query_len=160, max_target_len=312, max_n_alns=b.n, n_streams=1) as al:
+            before = al.launches(0)
+            got = al.align(b)
+            n_launches = al.launches(0) - before
+            assert al.kernel_name(0) == "s16x2"
+            assert_same(got, want, K5, name)
+            if want_launches is not None:
+                assert n_launches == want_launches, n_launches                                   # counter reset + the DP kernel
+            else:
+                assert n_launches >= 5
+            # one sequence at a time (gasal_host_batch_fill pads by itself): same verdict, same results
+            al.vec.a[0].current_n_alns = 0
+            al.fill_one_by_one(0, [b.query(i) for i in range(b.n)], [b.target(i) for i in range(b.n)])
+            qb, tb = al._last_bytes
+            al.launch(0, qb, tb, b.n); al.wait(0)
+            assert_same(al.results(0, b.n), want, K5, name + ", fill one by one")
+    lib.gasalx_set_fast_path_passes(1)
+    try:
+        with Aligner(algo=capi.SEMI_GLOBAL, start=capi.WITH_START, max_query_len=160, max_target_len=312, max_n_alns=clean.n, n_streams=1) as al:
+            before = al.launches(0)
+            got = al.align(clean)
+            assert al.launches(0) - before >= 5
+        assert_same(got, oracle_align(oracle, clean, algo=po.SEMI_GLOBAL, start=po.WITH_START, max_query_len=1024), K5, "forced passes")
+    finally:
+        lib.gasalx_set_fast_path_passes(0)

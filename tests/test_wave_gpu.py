@@ -146,7 +146,11 @@ def test_wave_matches_general_kernel_on_mixed_lengths(oracle):
     b = synth.config5(96, seed=7, lo=100, hi=6000)
     a = run(b, policy=1, algo=capi.LOCAL, start=capi.WITH_START)
     w = run(b, policy=0, algo=capi.LOCAL, start=capi.WITH_START)
-    assert a["_kernel"] == "int32" and w["_kernel"] in ("wave", "wave16")
+    # policy 0 regroups the batch by length class: short queries on the s16x2 fast path, long ones on the wavefront kernel
+    assert a["_kernel"] == "int32" and (w["_kernel"] in ("wave", "wave16") or w["_kernel"].startswith("mixed(s16x2+wave"))
+    w2 = run(b, policy=2, algo=capi.LOCAL, start=capi.WITH_START)
+    assert w2["_kernel"] in ("wave", "wave16")
+    assert_same(w2, a, K5, "wavefront kernel alone vs general kernel, mixed lengths")
     assert_same(w, a, K5, "wave vs general kernel, mixed lengths")
 
 
