@@ -66,6 +66,9 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 // bestK7 = max.s16x2(bestK7, c7); lanes that strictly improved record (cm, pos).  One asm block so that
 // ptxas fuses the per-lane compares into the predicate outputs of VIMNMX.S16x2 (the CUDA header's
 // __vibmax_s16x2 lost its predicate uses in partially unrolled loops with nvcc 12.9).
+#ifndef GB200_PRUNE_ARGMAX
+#define GB200_PRUNE_ARGMAX 1
+#endif
 #ifndef GB200_TRACK_IMAD
 #define GB200_TRACK_IMAD 1
 #endif
@@ -282,8 +285,13 @@ __device__ __forceinline__ uint32_t key_tree9(uint32_t g, const uint32_t (&key)[
   return __vimax3_s16x2(cm, key[6], key[7]);
 }
 
+// Score-bound pruning of the arg-max (exact): a local alignment that ends in query column q has at most q + 1 matches, so every
+// cell of that column has H <= match * (q + 1).  The forward pass only records STRICT improvements of the running best, and the
+// start pass only needs the cells that reach the forward score -- so the columns with match * (q + 1) <= bound can never be
+// recorded and their steps run without keys, trees and compare-and-record (`gfree` leading groups of four steps; the lanes of a
+// step sit on columns <= the step index).  After a read has been found, almost the whole sweep runs in this tracking-free loop.
 template <bool NMASK = false>
-__device__ __forceinline__ void local_sweep4g(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int ngroups,
+__device__ __forceinline__ void local_sweep4g(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int ngroups, int gfree,
                                               const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
                                               const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
                                               uint32_t neg_oe2, uint32_t neg_ext2, uint32_t thirtytwo, uint32_t one, uint32_t pos_base, LaneBest4& lb,
@@ -298,8 +306,55 @@ __device__ __forceinline__ void local_sweep4g(uint32_t* __restrict__ HE, const u
   uint32_t v = V[kFastThreads];
   uint32_t gA = 0, gB = 0;                         // running maxima of the current group
   uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;
+  gfree = min(gfree, ngroups);
+  // ---- tracking-free groups ----
 #pragma unroll 1
-  for (int g = 0; g < ngroups; g++) {
+  for (int g = 0; g < gfree; g++) {
+#pragma unroll
+    for (int ph = 0; ph < 4; ph++) {
+      const int k = 4 * g + ph;
+      const uint32_t selA = v | prevsh;
+      prevsh = v * 256u + 0x4400u;
+      uint32_t mA = 0;
+      if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
+      uint32_t upA = prmt(he, h8A, 0x5410);
+      uint32_t eA = prmt(he, eoA, 0x5432);
+      uint32_t upB = prmt(h8A, h8B, 0x5432);
+      uint32_t eB = prmt(eoA, eoB, 0x5432);
+      he = HE[(k + 2) * kFastThreads];
+      v = V[(k + 2) * kFastThreads];
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        {
+          uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+          if (NMASK) s2 = mask_sel(s2, mA, nsc2);
+          const uint32_t d = __vadd2(pA[r], s2);
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
+          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, dm);
+          eA = __viaddmax_s16x2(eA, neg_ext2, dm);
+          pA[r] = upA; upA = h;
+        }
+        {
+          uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+          if (NMASK) s2 = mask_sel(s2, mB, nsc2);
+          const uint32_t d = __vadd2(pB[r], s2);
+          const uint32_t dm = __vadd2(d, neg_oe2);
+          const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
+          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, dm);
+          eB = __viaddmax_s16x2(eB, neg_ext2, dm);
+          pB[r] = upB; upB = h;
+        }
+      }
+      HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+      h8A = upA; eoA = eA; h8B = upB; eoB = eB;
+      selB = selA_prev; selA_prev = selA;
+      if (NMASK) { mB = mA_prev; mA_prev = mA; }
+    }
+  }
+  // ---- tracked groups (the pipelined keys start as zeros: never an improvement) ----
+#pragma unroll 1
+  for (int g = gfree; g < ngroups; g++) {
 #pragma unroll
     for (int ph = 0; ph < 4; ph++) {
       const int k = 4 * g + ph;
@@ -317,7 +372,7 @@ __device__ __forceinline__ void local_sweep4g(uint32_t* __restrict__ HE, const u
       gA = key_tree9(gA, keyA);
       gB = key_tree9(gB, keyB);
       if (ph == 0) {
-        const uint32_t pos = pos_base + (uint32_t)g - one;      // the group that just closed (g == 0: nothing but the zero keys, never an improvement)
+        const uint32_t pos = pos_base + (uint32_t)g - one;      // the group that just closed (first tracked group: nothing but the zero keys)
         track_update(lb.a, gA | 0x001F001Fu, gA, pos, one);
         track_update(lb.b, gB | 0x001F001Fu, gB, pos, one);
         gA = 0; gB = 0;
@@ -354,7 +409,7 @@ __device__ __forceinline__ void local_sweep4g(uint32_t* __restrict__ HE, const u
       if (NMASK) { mB = mA_prev; mA_prev = mA; }
     }
   }
-  {
+  if (gfree < ngroups) {
     gA = key_tree9(gA, keyA);
     gB = key_tree9(gB, keyB);
     const uint32_t pos = pos_base + (uint32_t)ngroups - one;
@@ -364,6 +419,10 @@ __device__ __forceinline__ void local_sweep4g(uint32_t* __restrict__ HE, const u
 }
 
 __device__ __forceinline__ void lanebest_init(LaneBest& lb) { lb.bestK7 = 0x00070007u; lb.keyL = lb.keyH = 0; lb.posL = lb.posH = 0; }
+__device__ __forceinline__ int lanebest_score_g4(const LaneBest& a, const LaneBest& b) {      // best score over the four lanes (keys score * 32 + 31)
+  const int m = max(max((int)(short)(a.bestK7 & 0xFFFFu), (int)(short)(a.bestK7 >> 16)), max((int)(short)(b.bestK7 & 0xFFFFu), (int)(short)(b.bestK7 >> 16)));
+  return m >> 5;
+}
 __device__ __forceinline__ void lanebest_init_g4(LaneBest& lb) { lb.bestK7 = 0x001F001Fu; lb.keyL = lb.keyH = 0; lb.posL = lb.posH = 0; }
 
 // winner over the four records; pos = (quad-strip index << 16) | step
@@ -810,7 +869,12 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
     quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
     // G4: ncol / 4 + 1 groups = ncol + 4 steps (one phantom step more than the skew needs; its slots are dummies)
-    if (G4) local_sweep4g<NMASK>(HE, V, (ncol >> 2) + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, lb, nsc2);
+    // (columns q with match * (q + 1) <= best so far cannot improve it: their groups of steps run without the arg-max)
+    // (the count is made WARP-UNIFORM -- the minimum over the converged lanes, which is conservative for each of them -- or the two
+    // loops of the sweep would run divergent: measured 1.5x SLOWER with per-pair counts)
+    if (G4) local_sweep4g<NMASK>(HE, V, (ncol >> 2) + (int)fa.one,
+                                 GB200_PRUNE_ARGMAX && a.match > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)((lanebest_score_g4(lb.a, lb.b) / a.match) >> 2)) : 0,
+                                 rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, lb, nsc2);
     else local_sweep4<NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb, nsc2);
   }
   const Winner fw = pick_winner4<G4>(lb);
@@ -846,7 +910,10 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
         const uint32_t wc = (4 * j + 2 < gend_reg) ? nibrev(tw[gend_reg - 3 - 4 * j]) : 0u;
         const uint32_t wd = (4 * j + 3 < gend_reg) ? nibrev(tw[gend_reg - 4 - 4 * j]) : 0u;
         quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
-        if (G4) local_sweep4g<NMASK>(HE, V, (rcol >> 2) + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, rb, nsc2);
+        // (only cells that reach the forward score matter here: columns q with match * (q + 1) < fwd score need no arg-max)
+        if (G4) local_sweep4g<NMASK>(HE, V, (rcol >> 2) + (int)fa.one,
+                                     GB200_PRUNE_ARGMAX && a.match > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)(((fw.score - 1) / a.match) >> 2)) : 0,
+                                     rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, rb, nsc2);
         else local_sweep4<NMASK>(HE, V, rcol + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb, nsc2);
         if ((int)(short)(rb.a.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.a.bestK7 >> 16) >= fwd7 ||
             (int)(short)(rb.b.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.b.bestK7 >> 16) >= fwd7) break;
