@@ -69,6 +69,9 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 #ifndef GB200_PRUNE_ARGMAX
 #define GB200_PRUNE_ARGMAX 1
 #endif
+#ifndef GB200_PRUNE_REVERSE
+#define GB200_PRUNE_REVERSE 1
+#endif
 #ifndef GB200_TRACK_IMAD
 #define GB200_TRACK_IMAD 1
 #endif
@@ -838,6 +841,7 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   }
 
   // ---- forward pass over quad-strips ----
+  const int mstep = NMASK ? max(a.match, a.n_score) : a.match;      // the most one diagonal step can add (score bounds of the prunings below)
   LaneBest4 lb;
   if (G4) { lanebest_init_g4(lb.a); lanebest_init_g4(lb.b); } else { lanebest_init(lb.a); lanebest_init(lb.b); }
   const int NQ = (TR + 3) >> 2;
@@ -873,7 +877,7 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     // (the count is made WARP-UNIFORM -- the minimum over the converged lanes, which is conservative for each of them -- or the two
     // loops of the sweep would run divergent: measured 1.5x SLOWER with per-pair counts)
     if (G4) local_sweep4g<NMASK>(HE, V, (ncol >> 2) + (int)fa.one,
-                                 GB200_PRUNE_ARGMAX && a.match > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)((lanebest_score_g4(lb.a, lb.b) / a.match) >> 2)) : 0,
+                                 GB200_PRUNE_ARGMAX && mstep > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)((lanebest_score_g4(lb.a, lb.b) / mstep) >> 2)) : 0,
                                  rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, lb, nsc2);
     else local_sweep4<NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb, nsc2);
   }
@@ -903,7 +907,17 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
       if (G4) { lanebest_init_g4(rb.a); lanebest_init_g4(rb.b); } else { lanebest_init(rb.a); lanebest_init(rb.b); }
       const int RD = (gend_reg + 3) >> 2;
       const int fwd7 = G4 ? ((fw.score << 5) | 31) : ((fw.score << 3) | 7);
+      // Score-bound pruning of the reversed rectangle (exact): a path through the cell (row i, column c) with c > i has at most
+      // i + 1 diagonal steps up to that cell and at most rcol - 1 - c after it, so it scores <= match * (rcol - (c - i)); no path
+      // that reaches the forward score enters the columns c > i + slack, slack = rcol - ceil(score / match).  Quad-strip j (rows
+      // < 32 (j + 1)) therefore stops after column 32 (j + 1) + slack: the cells beyond keep the initial state (0, a lower bound
+      // that the 0 clamp makes harmless), every cell on a path that reaches the forward score is still computed from exact
+      // inputs, and no cell exceeds its true value -- the first cell that reaches the score, in the reference's order, is the same.
+      // (slack is made warp-uniform, the maximum over the converged lanes: conservative for each of them, see the note on gfree)
+      const int slack = GB200_PRUNE_REVERSE && mstep > 0
+                            ? (int)__reduce_max_sync(__activemask(), (unsigned)(rcol - (fw.score + mstep - 1) / mstep)) : rcol;
       for (int j = 0; j < RD; j++) {
+        const int lim = min(rcol, (32 * (j + 1) + slack + 3) & ~3);
         uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
         const uint32_t wa = nibrev(tw[gend_reg - 1 - 4 * j]);
         const uint32_t wb = (4 * j + 1 < gend_reg) ? nibrev(tw[gend_reg - 2 - 4 * j]) : 0u;
@@ -911,10 +925,10 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
         const uint32_t wd = (4 * j + 3 < gend_reg) ? nibrev(tw[gend_reg - 4 - 4 * j]) : 0u;
         quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
         // (only cells that reach the forward score matter here: columns q with match * (q + 1) < fwd score need no arg-max)
-        if (G4) local_sweep4g<NMASK>(HE, V, (rcol >> 2) + (int)fa.one,
-                                     GB200_PRUNE_ARGMAX && a.match > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)(((fw.score - 1) / a.match) >> 2)) : 0,
+        if (G4) local_sweep4g<NMASK>(HE, V, (lim >> 2) + (int)fa.one,
+                                     GB200_PRUNE_ARGMAX && mstep > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)(((fw.score - 1) / mstep) >> 2)) : 0,
                                      rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, rb, nsc2);
-        else local_sweep4<NMASK>(HE, V, rcol + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb, nsc2);
+        else local_sweep4<NMASK>(HE, V, lim + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb, nsc2);
         if ((int)(short)(rb.a.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.a.bestK7 >> 16) >= fwd7 ||
             (int)(short)(rb.b.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.b.bestK7 >> 16) >= fwd7) break;
       }
