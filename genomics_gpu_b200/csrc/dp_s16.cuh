@@ -1290,8 +1290,11 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
 
 // selector bytes + top boundary of one pass into shared memory.  mode 0: forward words; mode 2: true-length reversed.
 // SEMI: the parked E is the first row's own E(0,c) = max(H(-1,c) - oe, E(-1,c) - e) (see nc_sweep); otherwise E(-1,c).
+// floor_from: columns >= floor_from get the -infinity floor instead of the top boundary (pruned start pass: the first quad-strip never
+// reads them, and for the later ones the cell above such a column is outside every path that reaches the forward score)
 template <bool TOP_ZERO, bool SEMI = true, bool NMASK = false>
-__device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint32_t* qw, uint32_t qlen, int QR, int mode, int o, int ext, uint32_t nval = 0) {
+__device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint32_t* qw, uint32_t qlen, int QR, int mode, int o, int ext, uint32_t nval = 0,
+                                            int floor_from = 0x7FFFFFFF) {
   bool odd = false;
   const int ncol = QR * 8;
   V[0] = 0x88; HE[0] = pack2(0, kNegSafe);
@@ -1306,7 +1309,8 @@ __device__ __forceinline__ bool nc_prologue(uint32_t* HE, uint8_t* V, const uint
         const int htop = TOP_ZERO ? 0 : (c == 0 ? 0 : -(o + ext * c));                  // free top row: (H,E)(-1,c) = (0,0)
         // biased frame of nc_sweep4: H(-1,c) carries (c - 1) ext, E(0,c) carries c ext
         // ... and E is kept as E + open (nc_sweep4 takes max(E + open, D, F) in one VIMNMX3)
-        HE[(c + 1) * kFastThreads] = pack2(htop + (c - 1) * ext, (TOP_ZERO ? -ext : htop - (o + ext)) + c * ext + o);
+        HE[(c + 1) * kFastThreads] = (c >= floor_from) ? pack2(kNegSafe, kNegSafe)
+                                                       : pack2(htop + (c - 1) * ext, (TOP_ZERO ? -ext : htop - (o + ext)) + c * ext + o);
       } else {
         HE[(c + 1) * kFastThreads] = pack2((c == 0 ? 0 : -(o + ext * c)) + (c - 1) * ext, kNegSafe);   // H(-1,c) in the biased frame
       }
@@ -1372,17 +1376,44 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     const int fwd = tr.best;
     const uint32_t ua = (uint32_t)TR - (uint32_t)((tr.y >> 3) + 1);
     const uint32_t gend_reg = ua > 0 ? ua - 1 : ua;                                   // :273 (unsigned in the reference)
-    if (top_zero) nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval);
-    else nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval);
-    NcTrack rt; rt.best = kMinusInf; rt.y = 0; rt.stop = fwd; rt.cap = 0;             // :275-276
-    for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 4) {
-      uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
-      const uint32_t wa = rev_true_word(tw, (int)tlen, (int)i);
-      const uint32_t wb = (i + 1 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 1) : 0u;
-      const uint32_t wc = (i + 2 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 2) : 0u;
-      const uint32_t wd = (i + 3 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 3) : 0u;
-      quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
-      nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2);
+    // Score-bound pruning (exact; see the LOCAL start pass): a path through the cell (row i of this pass, column c) with d = c - i > 0
+    // has at most i + 1 diagonal steps before that cell and qlen - 1 - c after it, and at least d of its columns sit in gaps, which
+    // cost at least open + (d - 1) ext (the cheapest case is one gap on the top boundary, quirk Q4), so it scores at most
+    // m (qlen - d) - open - (d - 1) ext, m = the best substitution score.  No path that reaches the forward score enters the columns
+    // c > i + slack, slack = (m qlen - score - open + ext) / (m + ext): quad-strip k of the pass stops after column 32 (k + 1) + slack,
+    // the cells beyond act as -infinity (a lower bound of their true value; every cell on a path that reaches the score keeps exact
+    // inputs, no cell exceeds its true value), and rows whose last column was not computed cannot hold the score.  If the pruned
+    // pass ends WITHOUT reaching the forward score (possible when the forward path starts with a gap on the top boundary, which the
+    // reversed DP prices differently), it is run again unpruned, so that the reference's "first best row" is reproduced as well.
+    // HEAD == BOTH has a free top row: no bound, no pruning.  (slack is warp-uniform, the maximum over the converged lanes.)
+    const int mstep = NMASK ? max(a.match, a.n_score) : a.match;
+    int slack = ncol;
+    if (GB200_PRUNE_REVERSE && !top_zero && mstep + a.gap_extend > 0) {
+      const int num = mstep * (int)qlen - fwd - a.gap_open + a.gap_extend;
+      slack = (int)__reduce_max_sync(__activemask(), (unsigned)max(num, 0) / (unsigned)(mstep + a.gap_extend));
+    }
+    NcTrack rt;
+    for (int attempt = 0; attempt < 2; attempt++) {
+      const int lim0 = min(ncol, (32 + slack + 3) & ~3);
+      if (top_zero) nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval);
+      else nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval, lim0 < ncol ? lim0 : 0x7FFFFFFF);
+      rt.best = kMinusInf; rt.y = 0; rt.stop = fwd; rt.cap = 0;                         // :275-276
+      int lim = lim0;
+      for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 4) {
+        uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
+        const uint32_t wa = rev_true_word(tw, (int)tlen, (int)i);
+        const uint32_t wb = (i + 1 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 1) : 0u;
+        const uint32_t wc = (i + 2 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 2) : 0u;
+        const uint32_t wd = (i + 3 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 3) : 0u;
+        quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
+        // a truncated sweep computes the columns < lim in all four lanes; if it stops on the scanned column (qlen - 1 >= lim) the lanes
+        // that get there only see values below the forward score, which never decide the result
+        const int ns = (lim < ncol) ? lim + 2 + (int)fa.one : nsteps;
+        nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE, V, ns, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2);
+        lim = min(ncol, lim + 32);
+      }
+      if (rt.best >= fwd || slack >= ncol) break;
+      slack = ncol;                                                                    // not reached under the bound: the exact, unpruned pass
     }
     a.t_start[tid] = ((int)tlen - 1) - rt.y;                                          // :380-381
     a.q_start[tid] = ((int)qlen - 1) - (int)tlen;

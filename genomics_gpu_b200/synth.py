@@ -285,3 +285,31 @@ def with_n_bases(batch: PairBatch, pair_frac: float, seed: int = 1, per_pair: in
         q[batch.q_offs[hq].astype(np.int64) + (rng.random(hq.size) * batch.q_lens[hq]).astype(np.int64)] = N_CODE
         t[batch.t_offs[ht].astype(np.int64) + (rng.random(ht.size) * batch.t_lens[ht]).astype(np.int64)] = N_CODE
     return PairBatch(q, t, batch.q_offs, batch.t_offs, batch.q_lens, batch.t_lens)
+
+
+def overhanging_reads(n: int, seed: int, qlen: int = 150, tlen: int = 400) -> PairBatch:
+    """reads that hang off either end of their window, start on its first bases, or carry long gaps: the shapes where the pruned start
+    pass (score bound on the reversed rectangle) must fall back or must keep the far corner"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    qs, ts = [], []
+    for i in range(n):
+        g = acgt[rng.integers(0, 4, tlen + 2 * qlen)]
+        t = g[qlen:qlen + tlen]
+        kind = i % 6
+        if kind == 0: s = qlen - int(rng.integers(1, 40))                      # first bases of the read lie before the window
+        elif kind == 1: s = qlen + tlen - qlen + int(rng.integers(1, 40))       # last bases lie behind it
+        elif kind == 2: s = qlen + int(rng.integers(0, 3))                      # starts on the first rows
+        elif kind == 3: s = qlen + tlen - qlen - int(rng.integers(0, 3))        # ends on the last rows
+        else: s = qlen + int(rng.integers(0, tlen - qlen))
+        q = g[s:s + qlen].copy()
+        if kind == 4:                                                          # a long deletion / insertion inside the read
+            cut = int(rng.integers(20, 120)); L = int(rng.integers(5, 30))
+            q = np.concatenate([q[:cut], q[cut + L:], acgt[rng.integers(0, 4, L)]])[:qlen]
+        if kind == 5:
+            cut = int(rng.integers(20, 120)); L = int(rng.integers(5, 30))
+            q = np.concatenate([q[:cut], acgt[rng.integers(0, 4, L)], q[cut:]])[:qlen]
+        sub = rng.random(q.size) < 0.02
+        q[sub] = acgt[rng.integers(0, 4, int(sub.sum()))]
+        qs.append(q.tobytes()); ts.append(t.tobytes())
+    return batch_from_sequences(qs, ts)

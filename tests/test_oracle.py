@@ -83,6 +83,21 @@ def test_oracle_matches_reference_live(oracle, seed):
             assert_same(got, want, keys, f"{kw} {sc}")
 
 
+@pytest.mark.skipif(not po.RefHost.available(1024), reason="oracle/_ref host build of the reference not present")
+@pytest.mark.parametrize("scoring", [(1, 4, 6, 1), (2, 3, 5, 2), (1, 1, 0, 1), (3, 2, 8, 0)])
+def test_oracle_matches_reference_on_overhanging_reads(oracle, scoring):
+    """reads that hang off their window / long gaps / zero gap costs: the shapes the GPU start-pass pruning is tested on
+    (tests/test_parity_holes_gpu.py) -- here the oracle itself is pinned to the reference's kernels on them"""
+    ref = po.RefHost(1024)
+    b = synth.overhanging_reads(600, seed=77)
+    pq, pt = oracle.pack(b.q_bytes), oracle.pack(b.t_bytes)
+    for kw in (dict(algo=po.LOCAL, start=po.WITH_START), dict(algo=po.SEMI_GLOBAL, start=po.WITH_START),
+               dict(algo=po.SEMI_GLOBAL, head=po.BOTH, start=po.WITH_START)):
+        want = ref.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, scoring=scoring, **kw)
+        got = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, scoring=scoring, max_query_len=1024, **kw)
+        assert_same(got, want, K5, f"{kw} {scoring}")
+
+
 def test_real_reads_golden(oracle):
     """4000 of the 20,000 real read/window pairs the reference ships, against outputs of the reference kernels."""
     inp = np.load(os.path.join(HERE, "golden", "real4000_inputs.npz"))

@@ -138,3 +138,15 @@ def test_config4_20000_pairs_banded_cigar_vs_oracle(oracle):
     ref = oracle_align(oracle, b, algo=po.LOCAL, start=po.WITH_TB)
     assert_same(got, ref, K5 + ["n_cigar_ops"], "C4 x 20000 banded + CIGAR vs the reference's unbanded LOCAL WITH_TB")
     assert cigar_slices(got, b) == cigar_slices(ref, b)
+
+
+@pytest.mark.parametrize("scoring", [(1, 4, 6, 1), (2, 3, 5, 2), (1, 1, 0, 1), (3, 2, 8, 0)])
+def test_start_pass_pruning_edge_shapes_vs_oracle(oracle, scoring):
+    """the start passes skip the cells a score bound rules out (dp_s16.cuh): reads hanging off the window, long gaps, zero gap costs"""
+    b = synth.overhanging_reads(6144, seed=77)
+    for algo, oalgo, extra in ((capi.LOCAL, po.LOCAL, {}), (capi.SEMI_GLOBAL, po.SEMI_GLOBAL, dict(max_query_len=1024))):
+        for head in ((capi.TARGET, capi.BOTH) if algo == capi.SEMI_GLOBAL else (capi.TARGET,)):
+            want = oracle_align(oracle, b, algo=oalgo, start=po.WITH_START, scoring=scoring, head=head, **extra)
+            got = run(b, algo=algo, start=capi.WITH_START, scoring=scoring, head=head)
+            assert got["_kernel"] == "s16x2" or scoring[2] == 0 or scoring[3] == 0
+            assert_same(got, want, K5, f"overhanging reads, algo {algo}, head {head}, scoring {scoring}")
