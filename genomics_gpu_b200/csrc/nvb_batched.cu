@@ -552,6 +552,10 @@ NVB_UNROLL(NVB_ROW_UNROLL)
   }
 }
 
+}  // namespace nvb200
+#include "nvb_tb.cuh"       // banded scoring + traceback kernels (k_nvb_banded, k_nvb_tb_fwd, k_nvb_tb_walk, k_nvb_banded_walk)
+namespace nvb200 {
+
 // ------------------------------------------------------------------------------------------------------------------
 thread_local std::string g_err;
 uint64_t g_launches = 0;
@@ -574,6 +578,9 @@ struct nvbx_stream {
   uint2* scratch = nullptr; size_t scratch_elems = 0;
   uint32_t *worklist = nullptr, *work_count = nullptr;
   cudaEvent_t e0 = nullptr, e1 = nullptr;
+  uint32_t* dirs = nullptr; size_t dirs_words = 0;                 // flow words of one chunk of jobs (traceback)
+  int32_t *src_i = nullptr, *src_j = nullptr; uint32_t* n_ops = nullptr; uint8_t* ops = nullptr; uint32_t ops_stride = 0;
+  bool have_tb = false;
   bool have_sinks = false, enacted = false;
   std::string kernel = "none";
 };
@@ -591,6 +598,7 @@ void nvbx_stream_destroy(nvbx_stream_t* s) {
   cudaFree(s->pbytes); cudaFree(s->tbytes); cudaFree(s->pflag); cudaFree(s->tflag); cudaFree(s->poffs); cudaFree(s->toffs);
   cudaFree(s->ppk); cudaFree(s->tpk); cudaFree(s->pair_p); cudaFree(s->pair_t); cudaFree(s->score); cudaFree(s->sink_i); cudaFree(s->sink_j);
   cudaFree(s->scratch); cudaFree(s->worklist); cudaFree(s->work_count);
+  cudaFree(s->dirs); cudaFree(s->src_i); cudaFree(s->src_j); cudaFree(s->n_ops); cudaFree(s->ops);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   delete s;
@@ -725,8 +733,178 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
     NVB_CHECK(cudaGetLastError());
   }
   NVB_CHECK(cudaEventRecord(s->e1, s->st));
-  s->have_sinks = want_sinks != 0; s->enacted = true;
+  s->have_sinks = want_sinks != 0; s->enacted = true; s->have_tb = false;
   s->kernel = used_i32 ? (wide ? "int32" : "int32-any") : "s16x2";
+  return 0;
+}
+
+}  // extern "C"
+
+// ---- banded scoring and traceback batches (kernels: nvb_tb.cuh) ------------------------------------------------------------------
+static int base_args(nvbx_stream_t* s, const nvbx_aligner_t* al, NvbArgs& a, const char* who) {
+  if (!s || !al) return fail(std::string(who) + ": NULL argument");
+  if (al->type < NVBX_GLOBAL || al->type > NVBX_SEMI_GLOBAL) return fail(std::string(who) + ": unknown alignment type");
+  a.pbytes = s->pbytes; a.poffs = s->poffs; a.ppk = s->ppk; a.pflag = s->pflag;
+  a.tbytes = s->tbytes; a.toffs = s->toffs; a.tpk = s->tpk; a.tflag = s->tflag;
+  a.pair_p = s->pair_p; a.pair_t = s->pair_t; a.text_shared = s->text_shared;
+  switch (al->algo) {
+    case NVBX_GOTOH: a.match = al->match; a.mismatch = al->mismatch; a.go_t = a.go_p = al->gap_open; a.ge_t = a.ge_p = al->gap_ext; a.band_shift = 3; break;
+    case NVBX_SMITH_WATERMAN: a.match = al->match; a.mismatch = al->mismatch; a.go_t = a.ge_t = al->gap_open; a.go_p = a.ge_p = al->gap_ext; a.band_shift = 4; break;
+    case NVBX_EDIT_DISTANCE: a.match = 0; a.mismatch = -1; a.go_t = a.ge_t = a.go_p = a.ge_p = -1; a.band_shift = 4; break;
+    default: return fail(std::string(who) + ": unknown aligner");
+  }
+  a.score = s->score; a.sink_i = s->sink_i; a.sink_j = s->sink_j; a.worklist = s->worklist; a.work_count = s->work_count; a.sixteen = 16;
+  return 0;
+}
+// banded costs: the pattern-consuming move (F) / the text-consuming move (E) / the row-zero init.  Gotoh uses one (open, extend)
+// pair for all three; the banded Smith-Waterman prices the pattern-consuming move with deletion() and the text-consuming one with
+// insertion() (sw_banded_inl.h:378-379,432-434 -- the opposite of its full-matrix code) and fills row zero with j * deletion().
+static void banded_costs(const nvbx_aligner_t* al, const NvbArgs& a, TbArgs& tb) {
+  if (al->algo == NVBX_GOTOH) { tb.f_o = tb.e_o = tb.init_o = a.go_t; tb.f_e = tb.e_e = tb.init_e = a.ge_t; tb.no_sink = 0; }
+  else { tb.f_o = tb.f_e = tb.init_o = tb.init_e = a.go_t; tb.e_o = tb.e_e = a.go_p; tb.no_sink = 1; }
+}
+static int ensure_tb_outputs(nvbx_stream_t* s) {
+  if (s->src_i) return 0;
+  s->ops_stride = ((s->max_m + s->max_n + 64u) + 3u) & ~3u;
+  NVB_CHECK(cudaMalloc(&s->src_i, 4 * (size_t)s->n_pairs)); NVB_CHECK(cudaMalloc(&s->src_j, 4 * (size_t)s->n_pairs));
+  NVB_CHECK(cudaMalloc(&s->n_ops, 4 * (size_t)s->n_pairs));
+  if (cudaMalloc(&s->ops, (size_t)s->n_pairs * s->ops_stride) != cudaSuccess) { cudaGetLastError(); return fail("nvbx traceback: cannot allocate the edit-op buffer"); }
+  return 0;
+}
+static int ensure_dirs(nvbx_stream_t* s, size_t words) {
+  if (words <= s->dirs_words) return 0;
+  if (s->dirs) cudaFree(s->dirs);
+  s->dirs = nullptr; s->dirs_words = 0;
+  if (cudaMalloc(&s->dirs, words * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); return fail("nvbx traceback: cannot allocate the flow matrix"); }
+  s->dirs_words = words;
+  return 0;
+}
+static bool band_ok(int b) { return b == 3 || b == 5 || b == 7 || b == 15 || b == 31; }
+
+template <int B, bool DIRS>
+static void launch_banded(int type, uint32_t g, cudaStream_t st, const NvbArgs& a, const TbArgs& tb, int want_sinks) {
+  if (type == NVBX_GLOBAL) k_nvb_banded<B, NVBX_GLOBAL, DIRS><<<g, kThreads, 0, st>>>(a, tb, want_sinks);
+  else if (type == NVBX_LOCAL) k_nvb_banded<B, NVBX_LOCAL, DIRS><<<g, kThreads, 0, st>>>(a, tb, want_sinks);
+  else k_nvb_banded<B, NVBX_SEMI_GLOBAL, DIRS><<<g, kThreads, 0, st>>>(a, tb, want_sinks);
+}
+template <bool DIRS>
+static void launch_banded_b(int band, int type, uint32_t g, cudaStream_t st, const NvbArgs& a, const TbArgs& tb, int want_sinks) {
+  switch (band) {
+    case 3: launch_banded<3, DIRS>(type, g, st, a, tb, want_sinks); break;
+    case 5: launch_banded<5, DIRS>(type, g, st, a, tb, want_sinks); break;
+    case 7: launch_banded<7, DIRS>(type, g, st, a, tb, want_sinks); break;
+    case 15: launch_banded<15, DIRS>(type, g, st, a, tb, want_sinks); break;
+    default: launch_banded<31, DIRS>(type, g, st, a, tb, want_sinks); break;
+  }
+}
+
+extern "C" {
+
+int nvbx_stream_enact_banded(nvbx_stream_t* s, const nvbx_aligner_t* al, int band_len, int want_sinks) {
+  NvbArgs a{}; TbArgs tb{};
+  if (base_args(s, al, a, "nvbx_stream_enact_banded") != 0) return -1;
+  if (!band_ok(band_len)) return fail("nvbx_stream_enact_banded: band_len must be 3, 5, 7, 15 or 31 (the reference's instantiations)");
+  banded_costs(al, a, tb);
+  NVB_CHECK(cudaEventRecord(s->e0, s->st));
+  a.first = 0; a.count = s->n_pairs;
+  launch_banded_b<false>(band_len, al->type, (a.count + kThreads - 1) / kThreads, s->st, a, tb, want_sinks ? 1 : 0);
+  NVB_CHECK(cudaGetLastError());
+  g_launches += 1;
+  NVB_CHECK(cudaEventRecord(s->e1, s->st));
+  s->have_sinks = want_sinks != 0; s->enacted = true; s->have_tb = false;
+  s->kernel = "banded-int32";
+  return 0;
+}
+
+int nvbx_stream_traceback(nvbx_stream_t* s, const nvbx_aligner_t* al, int band_len) {
+  NvbArgs a{}; TbArgs tb{};
+  if (base_args(s, al, a, "nvbx_stream_traceback") != 0) return -1;
+  if (band_len != 0 && !band_ok(band_len)) return fail("nvbx_stream_traceback: band_len must be 0 (full matrix), 3, 5, 7, 15 or 31");
+  if (ensure_tb_outputs(s) != 0) return -1;
+  tb.src_i = s->src_i; tb.src_j = s->src_j; tb.n_ops = s->n_ops; tb.ops = s->ops; tb.ops_stride = s->ops_stride;
+  const size_t budget_words = (size_t)3 << 29;                                             // <= 6 GB of flow words per chunk
+  NVB_CHECK(cudaEventRecord(s->e0, s->st));
+  if (band_len) {
+    banded_costs(al, a, tb);
+    const size_t per_job = (size_t)s->max_m * ((band_len + 7) / 8);
+    size_t chunk = std::max<size_t>(kThreads, (budget_words / std::max<size_t>(1, per_job)) & ~(size_t)(kThreads - 1));
+    chunk = std::min<size_t>(chunk, ((size_t)s->n_pairs + kThreads - 1) & ~(size_t)(kThreads - 1));
+    if (ensure_dirs(s, per_job * chunk) != 0) return -1;
+    tb.dirs = s->dirs; tb.slots = chunk; tb.rows_cap = s->max_m;
+    for (size_t first = 0; first < s->n_pairs; first += chunk) {
+      a.first = (uint32_t)first; a.count = (uint32_t)std::min<size_t>(chunk, s->n_pairs - first);
+      const uint32_t g = (a.count + kThreads - 1) / kThreads;
+      launch_banded_b<true>(band_len, al->type, g, s->st, a, tb, 1);
+      switch (band_len) {
+        case 3: k_nvb_banded_walk<3><<<g, kThreads, 0, s->st>>>(a, tb, al->type); break;
+        case 5: k_nvb_banded_walk<5><<<g, kThreads, 0, s->st>>>(a, tb, al->type); break;
+        case 7: k_nvb_banded_walk<7><<<g, kThreads, 0, s->st>>>(a, tb, al->type); break;
+        case 15: k_nvb_banded_walk<15><<<g, kThreads, 0, s->st>>>(a, tb, al->type); break;
+        default: k_nvb_banded_walk<31><<<g, kThreads, 0, s->st>>>(a, tb, al->type); break;
+      }
+      NVB_CHECK(cudaGetLastError());
+      g_launches += 2;
+    }
+    s->kernel = "banded-int32+tb";
+  } else {
+    const size_t nbands = (s->max_m + 7) / 8, per_job = nbands * s->max_n;
+    size_t chunk = std::max<size_t>(kThreads, (budget_words / std::max<size_t>(1, per_job)) & ~(size_t)(kThreads - 1));
+    chunk = std::min<size_t>(chunk, ((size_t)s->n_pairs + kThreads - 1) & ~(size_t)(kThreads - 1));
+    if (ensure_dirs(s, per_job * chunk) != 0) return -1;
+    const size_t need = chunk * s->max_n;                                                  // band-border scratch, [CTA][text row][thread]
+    if (need > s->scratch_elems) {
+      if (s->scratch) cudaFree(s->scratch);
+      s->scratch = nullptr; s->scratch_elems = 0;
+      if (cudaMalloc(&s->scratch, need * sizeof(uint2)) != cudaSuccess) { cudaGetLastError(); return fail("nvbx_stream_traceback: cannot allocate the band-border scratch"); }
+      s->scratch_elems = need;
+    }
+    a.scratch = s->scratch; a.stride = (uint32_t)chunk; a.rows_cap = s->max_n;
+    tb.dirs = s->dirs; tb.slots = chunk; tb.rows_cap = s->max_n;
+    for (size_t first = 0; first < s->n_pairs; first += chunk) {
+      a.first = (uint32_t)first; a.count = (uint32_t)std::min<size_t>(chunk, s->n_pairs - first);
+      const uint32_t g = (a.count + kThreads - 1) / kThreads;
+      if (al->type == NVBX_GLOBAL) k_nvb_tb_fwd<NVBX_GLOBAL><<<g, kThreads, 0, s->st>>>(a, tb);
+      else if (al->type == NVBX_LOCAL) k_nvb_tb_fwd<NVBX_LOCAL><<<g, kThreads, 0, s->st>>>(a, tb);
+      else k_nvb_tb_fwd<NVBX_SEMI_GLOBAL><<<g, kThreads, 0, s->st>>>(a, tb);
+      k_nvb_tb_walk<<<g, kThreads, 0, s->st>>>(a, tb, al->type);
+      NVB_CHECK(cudaGetLastError());
+      g_launches += 2;
+    }
+    s->kernel = "int32+tb";
+  }
+  NVB_CHECK(cudaEventRecord(s->e1, s->st));
+  s->have_sinks = true; s->enacted = true; s->have_tb = true;
+  return 0;
+}
+
+uint32_t nvbx_stream_ops_stride(const nvbx_stream_t* s) { return s ? (s->ops_stride ? s->ops_stride : (((s->max_m + s->max_n + 64u) + 3u) & ~3u)) : 0; }
+
+int nvbx_stream_alignments(nvbx_stream_t* s, nvbx_alignment_t* alns, uint8_t* ops) {
+  if (!s || !alns) return fail("nvbx_stream_alignments: NULL argument");
+  if (!s->have_tb) return fail("nvbx_stream_alignments: no traceback was enacted");
+  const size_t n = s->n_pairs;
+  std::vector<int32_t> h(5 * n); std::vector<uint32_t> hn(n);
+  NVB_CHECK(cudaMemcpyAsync(h.data(), s->score, 4 * n, cudaMemcpyDeviceToHost, s->st));
+  NVB_CHECK(cudaMemcpyAsync(h.data() + n, s->src_i, 4 * n, cudaMemcpyDeviceToHost, s->st));
+  NVB_CHECK(cudaMemcpyAsync(h.data() + 2 * n, s->src_j, 4 * n, cudaMemcpyDeviceToHost, s->st));
+  NVB_CHECK(cudaMemcpyAsync(h.data() + 3 * n, s->sink_i, 4 * n, cudaMemcpyDeviceToHost, s->st));
+  NVB_CHECK(cudaMemcpyAsync(h.data() + 4 * n, s->sink_j, 4 * n, cudaMemcpyDeviceToHost, s->st));
+  NVB_CHECK(cudaMemcpyAsync(hn.data(), s->n_ops, 4 * n, cudaMemcpyDeviceToHost, s->st));
+  if (ops) NVB_CHECK(cudaMemcpyAsync(ops, s->ops, n * s->ops_stride, cudaMemcpyDeviceToHost, s->st));
+  NVB_CHECK(cudaStreamSynchronize(s->st));
+  std::vector<uint32_t> hm(s->n_patterns + 1);
+  NVB_CHECK(cudaMemcpy(hm.data(), s->poffs, 4 * (size_t)(s->n_patterns + 1), cudaMemcpyDeviceToHost));
+  std::vector<uint32_t> pp;
+  if (s->pair_p) { pp.resize(n); NVB_CHECK(cudaMemcpy(pp.data(), s->pair_p, 4 * n, cudaMemcpyDeviceToHost)); }
+  for (size_t k = 0; k < n; k++) {
+    nvbx_alignment_t& o = alns[k];
+    o.score = h[k]; o.source_text = h[n + k]; o.source_pattern = h[2 * n + k]; o.sink_text = h[3 * n + k]; o.sink_pattern = h[4 * n + k];
+    o.n_ops = hn[k];
+    const uint32_t pi = s->pair_p ? pp[k] : (uint32_t)k, m = hm[pi + 1] - hm[pi];
+    const bool none = o.sink_text < 0 || o.sink_pattern < 0;
+    o.clip_end = none ? 0u : m - (uint32_t)o.sink_pattern;                                  // backtracer.clip( pattern.length() - sink.y )
+    o.clip_begin = none ? 0u : (uint32_t)o.source_pattern;                                  // backtracer.clip( source.y )
+  }
   return 0;
 }
 

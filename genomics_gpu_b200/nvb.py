@@ -15,7 +15,10 @@ GOTOH, SMITH_WATERMAN, EDIT_DISTANCE = 0, 1, 2
 CODES, ASCII = 0, 1
 NVB_SYMBOLS = ["nvbx_stream_create", "nvbx_stream_enact", "nvbx_stream_results", "nvbx_stream_scores_device", "nvbx_stream_last_ms",
                "nvbx_stream_cells", "nvbx_stream_kernel", "nvbx_stream_destroy", "nvbx_batched_score_host", "nvbx_set_policy",
-               "nvbx_kernel_launches", "nvbx_last_error"]
+               "nvbx_kernel_launches", "nvbx_last_error", "nvbx_stream_enact_banded", "nvbx_stream_traceback", "nvbx_stream_ops_stride",
+               "nvbx_stream_alignments"]
+OP_SUBSTITUTION, OP_INSERTION, OP_DELETION = 0, 1, 2      # aln::DirectionVector values a Backtracer sees (alignment_base.h:139-142)
+BAND_LENS = (3, 5, 7, 15, 31)                             # the reference's BatchedBandedAlignmentScore instantiations
 
 
 class AlignerT(C.Structure):
@@ -26,6 +29,12 @@ class BatchT(C.Structure):
     _fields_ = [("patterns", C.c_void_p), ("pattern_offsets", C.c_void_p), ("n_patterns", C.c_uint32),
                 ("texts", C.c_void_p), ("text_offsets", C.c_void_p), ("n_texts", C.c_uint32),
                 ("pair_pattern", C.c_void_p), ("pair_text", C.c_void_p), ("n_pairs", C.c_uint32), ("alphabet", C.c_int32)]
+
+
+class AlignmentT(C.Structure):
+    """nvbx_alignment_t: aln::Alignment<int32> (alignment_base.h:124-136) + what the Backtracer receives"""
+    _fields_ = [("score", C.c_int32), ("source_text", C.c_int32), ("source_pattern", C.c_int32), ("sink_text", C.c_int32), ("sink_pattern", C.c_int32),
+                ("n_ops", C.c_uint32), ("clip_end", C.c_uint32), ("clip_begin", C.c_uint32)]
 
 
 _bound = False
@@ -45,6 +54,10 @@ def _lib() -> C.CDLL:
         lib.nvbx_stream_destroy.argtypes = [C.c_void_p]
         lib.nvbx_batched_score_host.argtypes = [C.POINTER(AlignerT), C.POINTER(BatchT), C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_float)]
         lib.nvbx_batched_score_host.restype = C.c_int
+        lib.nvbx_stream_enact_banded.argtypes = [C.c_void_p, C.POINTER(AlignerT), C.c_int, C.c_int]; lib.nvbx_stream_enact_banded.restype = C.c_int
+        lib.nvbx_stream_traceback.argtypes = [C.c_void_p, C.POINTER(AlignerT), C.c_int]; lib.nvbx_stream_traceback.restype = C.c_int
+        lib.nvbx_stream_ops_stride.argtypes = [C.c_void_p]; lib.nvbx_stream_ops_stride.restype = C.c_uint32
+        lib.nvbx_stream_alignments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; lib.nvbx_stream_alignments.restype = C.c_int
         lib.nvbx_set_policy.argtypes = [C.c_int]
         lib.nvbx_kernel_launches.restype = C.c_uint64
         lib.nvbx_last_error.restype = C.c_char_p
@@ -105,6 +118,27 @@ class Stream:
         if rc != 0:
             raise RuntimeError("nvbx_stream_results: " + _lib().nvbx_last_error().decode())
         return sc, si, sj
+
+    def enact_banded(self, al: AlignerT, band_len: int, want_sinks: bool = False) -> None:
+        """BatchedBandedAlignmentScore<BAND_LEN, stream>::enact (batched.h:337-357)"""
+        if _lib().nvbx_stream_enact_banded(self._h, C.byref(al), band_len, 1 if want_sinks else 0) != 0:
+            raise RuntimeError("nvbx_stream_enact_banded: " + _lib().nvbx_last_error().decode())
+
+    def traceback(self, al: AlignerT, band_len: int = 0) -> None:
+        """BatchedAlignmentTraceback::enact (band_len 0) / BatchedBandedAlignmentTraceback<BAND_LEN>::enact (batched.h:436-478)"""
+        if _lib().nvbx_stream_traceback(self._h, C.byref(al), band_len) != 0:
+            raise RuntimeError("nvbx_stream_traceback: " + _lib().nvbx_last_error().decode())
+
+    def alignments(self, want_ops: bool = True):
+        """(structured array of nvbx_alignment_t, ops[n_pairs, stride] uint8 in push order or None)"""
+        n = self.batch.n_pairs
+        alns = np.zeros(n, dtype=np.dtype([("score", "<i4"), ("source_text", "<i4"), ("source_pattern", "<i4"), ("sink_text", "<i4"), ("sink_pattern", "<i4"),
+                                           ("n_ops", "<u4"), ("clip_end", "<u4"), ("clip_begin", "<u4")]))
+        stride = int(_lib().nvbx_stream_ops_stride(self._h))
+        ops = np.zeros((n, stride), np.uint8) if want_ops else None
+        if _lib().nvbx_stream_alignments(self._h, alns.ctypes.data, None if ops is None else ops.ctypes.data) != 0:
+            raise RuntimeError("nvbx_stream_alignments: " + _lib().nvbx_last_error().decode())
+        return alns, ops
 
     def last_ms(self) -> float:
         return float(_lib().nvbx_stream_last_ms(self._h))

@@ -273,6 +273,36 @@ def nvb_jobs(n: int, m_lo: int, m_hi: int, n_lo: int, n_hi: int, seed: int = 1, 
     return np.concatenate(pats), poffs, np.concatenate(texts), toffs
 
 
+def nvb_banded_jobs(n: int, m_lo: int, m_hi: int, band: int, seed: int = 1, sub: float = 0.05, indel: float = 0.02, slack: int = 6):
+    """n jobs for the banded aligners (row = pattern symbol, band entry j = text symbol i + j): text = pattern length + band - 1 + up to
+    `slack` symbols (the reference's banded-traceback domain), pattern = the text from an offset inside the band, with substitutions and
+    short indels; every seventh pattern is unrelated.  Codes 0..3.  Returns (patterns, pattern_offsets, texts, text_offsets)."""
+    rng = np.random.default_rng(seed)
+    pats, texts = [], []
+    for k in range(n):
+        m = int(rng.integers(m_lo, m_hi + 1))
+        t = rng.integers(0, 4, m + band - 1 + int(rng.integers(0, slack + 1)) + 4).astype(np.uint8)
+        if k % 7 == 6:
+            p = rng.integers(0, 4, m).astype(np.uint8)
+        else:
+            a = int(rng.integers(0, band))
+            p = t[a:a + m].copy()
+            flip = rng.random(len(p)) < sub
+            p[flip] = rng.integers(0, 4, int(flip.sum()))
+            if indel > 0 and len(p) > 4:
+                for _ in range(int(rng.binomial(len(p), indel))):
+                    pos = int(rng.integers(1, len(p) - 1))
+                    p = np.delete(p, pos) if rng.random() < 0.5 else np.insert(p, pos, rng.integers(0, 4, int(rng.integers(1, 3)))).astype(np.uint8)
+            p = p[:m] if len(p) > m else p
+            if len(p) == 0:
+                p = rng.integers(0, 4, 1).astype(np.uint8)
+        t = t[:max(len(t) - 4, len(p) + band - 1)]
+        pats.append(np.ascontiguousarray(p, dtype=np.uint8)); texts.append(np.ascontiguousarray(t, dtype=np.uint8))
+    poffs = np.zeros(n + 1, np.uint32); poffs[1:] = np.cumsum([len(p) for p in pats])
+    toffs = np.zeros(n + 1, np.uint32); toffs[1:] = np.cumsum([len(t) for t in texts])
+    return np.concatenate(pats), poffs, np.concatenate(texts), toffs
+
+
 def with_n_bases(batch: PairBatch, pair_frac: float, seed: int = 1, per_pair: int = 1) -> PairBatch:
     """Copy of `batch` in which a fraction of the pairs carries `per_pair` real 'N' bases (inside the true length, in the query or
     the target at random): reads with uncalled bases, the input the s16x2 fast path has to hand to its N-aware second pass."""

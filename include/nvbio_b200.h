@@ -74,8 +74,48 @@ int nvbx_stream_results(nvbx_stream_t* s, int32_t* scores, int32_t* sink_text, i
 const int32_t* nvbx_stream_scores_device(nvbx_stream_t* s);
 float nvbx_stream_last_ms(nvbx_stream_t* s);            /* CUDA-event time of the last enact (synchronises) */
 uint64_t nvbx_stream_cells(const nvbx_stream_t* s);     /* sum over jobs of M * N (sw-benchmark.cu:380 GCUPS numerator) */
-const char* nvbx_stream_kernel(const nvbx_stream_t* s); /* last enact: "s16x2", "int32" (ordered costs) or "int32-any" */
+const char* nvbx_stream_kernel(const nvbx_stream_t* s); /* last enact: "s16x2", "int32" (ordered costs), "int32-any", "banded-int32", "int32+tb", "banded-int32+tb" */
 void nvbx_stream_destroy(nvbx_stream_t* s);
+
+/* ---- banded scoring and traceback batches (round 2) ------------------------------------------------------------------------------
+ * BatchedBandedAlignmentScore<BAND_LEN, stream_type>::enact (batched.h:337-357; banded_alignment_score<BAND_LEN>,
+ * gotoh/gotoh_banded_inl.h:405-627, sw/sw_banded_inl.h:341-512, ed/ed_banded_inl.h): row i = pattern symbol i, band entry j =
+ * text symbol i + j, j < band_len.  band_len is one of the reference's instantiations 3, 5, 7, 15, 31
+ * (nvBowtie score_*_inl.h, alignment_test.cu).  Results through nvbx_stream_results: sinks are (text end, pattern end), 1-based.
+ * Reference behaviour that is reproduced: a job whose text is shorter than its pattern reports nothing (score -(1 << 30) = the reference's Field_traits<int32>::min(), sinks -1);
+ * GLOBAL reports band entry band_len - 1 of the last row, i.e. text end M + band_len - 1, whatever the text length; LOCAL reports
+ * every band cell, also those past the end of the text; band_len 31 uses the reference's 2-bit text cache (cached text symbols
+ * are truncated to their low two bits: meant for 2-bit DNA codes); the banded Smith-Waterman prices the pattern-consuming move
+ * with `gap_open` (m_deletion) and the text-consuming one with `gap_ext` (m_insertion) -- the opposite of the full-matrix code.
+ * Domain: text length >= band_len - 1 (the reference reads the first band_len - 1 text symbols unguarded; here positions past
+ * the end read as 255).  0, or -1 on invalid arguments. */
+int nvbx_stream_enact_banded(nvbx_stream_t* s, const nvbx_aligner_t* aligner, int band_len, int want_sinks);
+
+/* An alignment as the reference's traceback returns it: aln::Alignment<int32> (alignment_base.h:124-136: score, source and sink
+ * cells) plus what its Backtracer model receives (alignment.h:138-150): the soft-clip lengths and the edit operations. */
+typedef struct {
+  int32_t score;
+  int32_t source_text, source_pattern;   /* where the walk ended: 0-based START offsets (text, pattern); -1 / -1: nothing reported */
+  int32_t sink_text, sink_pattern;       /* BestSink: 1-based END coordinates (text, pattern) */
+  uint32_t n_ops;                        /* number of edit operations pushed */
+  uint32_t clip_end, clip_begin;         /* backtracer.clip(): pattern symbols after the alignment / before it */
+} nvbx_alignment_t;
+enum { NVBX_OP_SUBSTITUTION = 0, NVBX_OP_INSERTION = 1, NVBX_OP_DELETION = 2 };   /* aln::DirectionVector values a Backtracer sees */
+
+/* BatchedAlignmentTraceback<CHECKPOINTS, stream_type>::enact (batched.h:436-451; alignment_traceback, alignment_inl.h:361-467)
+ * when band_len == 0, BatchedBandedAlignmentTraceback<BAND_LEN, CHECKPOINTS, stream_type>::enact (batched.h:463-478;
+ * banded_alignment_traceback, banded_inl.h:363-427) when band_len is 3, 5, 7, 15 or 31: score, BestSink, source cell and the
+ * edit operations of every job, queued on the stream's CUDA stream.  The reference recomputes 4-bit flow windows from short2
+ * checkpoints; here the whole flow matrix of a chunk of jobs is kept in HBM (0.5 B per cell) and walked by a second kernel.
+ * Banded domain: text length >= pattern length + band_len - 1 (the reference's window recomputation reads past the text
+ * otherwise: undefined there). */
+int nvbx_stream_traceback(nvbx_stream_t* s, const nvbx_aligner_t* aligner, int band_len);
+/* bytes reserved per job in the edit-op buffer (max pattern + max text + 64, rounded up to 4) */
+uint32_t nvbx_stream_ops_stride(const nvbx_stream_t* s);
+/* wait for the last nvbx_stream_traceback; alns: n_pairs entries; ops (may be NULL): n_pairs * nvbx_stream_ops_stride(s) bytes,
+ * job k's operations at ops[k * stride .. + n_ops) in PUSH order -- from the END of the alignment to its source, as the
+ * reference's backtracer receives them (alignment.h:151-153). */
+int nvbx_stream_alignments(nvbx_stream_t* s, nvbx_alignment_t* alns, uint8_t* ops);
 
 /* One-call form with host buffers: create, enact, results, destroy.  ms[0..2] (optional) = upload + pack, scoring,
  * download in milliseconds.  sink pointers may be NULL (then the score-only fast path is eligible). */

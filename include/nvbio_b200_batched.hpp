@@ -9,6 +9,9 @@
 //   typedef aln::BatchedAlignmentScore<stream_type, scheduler> batch_type;                      same (the scheduler tag is accepted and ignored)
 //   batch_type::max_temp_storage( max_pattern_len, max_text_len, size )                         same (returns 0: scratch is internal)
 //   batch.enact( stream, temp_size, temp )                                                      same
+//   aln::BatchedBandedAlignmentScore<BAND_LEN, stream, scheduler>  (batched.h:337-357)           same
+//   aln::BatchedAlignmentTraceback<CHECKPOINTS, stream, scheduler> (batched.h:436-451)           same, over aln::HostTracebackStream
+//   aln::BatchedBandedAlignmentTraceback<BAND_LEN, CHECKPOINTS, stream, scheduler> (:463-478)    same
 //
 // The reference's stream_type is a user-written template over packed device strings (batched.h:239-300); here it is the concrete
 // aln::HostStringStream<aligner_type>: host string sets (concatenated symbols + offsets), an optional pair list, and the output
@@ -97,6 +100,69 @@ struct BatchedAlignmentScore {
     if (nvbx_batched_score_host(&a, &stream.m_batch, stream.m_scores, stream.m_sink_text, stream.m_sink_pattern, ms) != 0)
       throw std::runtime_error(std::string("BatchedAlignmentScore::enact: ") + nvbx_last_error());
   }
+};
+
+// A stream whose jobs also want their alignments traced back: the reference's traceback stream_type hands every job a
+// backtracer in its context (batched.h:358-433); here the Alignment<int32> of job i lands in alignments[i] and the operations its
+// backtracer would receive in ops[i * ops_stride .. + alignments[i].n_ops), push order (end of the alignment first).
+template <typename aligner_t>
+struct HostTracebackStream : HostStringStream<aligner_t> {
+  HostTracebackStream(const aligner_t& aligner, uint32_t n_jobs, const uint8_t* patterns, const uint32_t* pattern_offsets, uint32_t n_patterns,
+                      const uint8_t* texts, const uint32_t* text_offsets, uint32_t n_texts, nvbx_alignment_t* alignments, uint8_t* ops, uint32_t ops_stride,
+                      const uint32_t* pair_pattern = nullptr, const uint32_t* pair_text = nullptr, int alphabet = NVBX_CODES)
+      : HostStringStream<aligner_t>(aligner, n_jobs, patterns, pattern_offsets, n_patterns, texts, text_offsets, n_texts, nullptr, nullptr, nullptr,
+                                    pair_pattern, pair_text, alphabet),
+        m_alignments(alignments), m_ops(ops), m_ops_stride(ops_stride) {}
+  // bytes per job the op buffer needs (what nvbx_stream_ops_stride reports for this batch)
+  uint32_t ops_stride() const { return ((this->m_max_pattern + this->m_max_text + 64u) + 3u) & ~3u; }
+  nvbx_alignment_t* m_alignments; uint8_t* m_ops; uint32_t m_ops_stride;
+};
+
+namespace detail {
+struct StreamHandle {            // nvbx_stream_t with scope-bound lifetime
+  explicit StreamHandle(const nvbx_batch_t* b, const char* who) : h(nvbx_stream_create(b, nullptr)) {
+    if (!h) throw std::runtime_error(std::string(who) + ": " + nvbx_last_error());
+  }
+  ~StreamHandle() { nvbx_stream_destroy(h); }
+  nvbx_stream_t* h;
+};
+template <typename stream_type>
+inline void traceback(stream_type& stream, int band_len, const char* who) {
+  StreamHandle s(&stream.m_batch, who);
+  const nvbx_aligner_t a = stream.aligner().pod();
+  if (stream.m_ops && stream.m_ops_stride != nvbx_stream_ops_stride(s.h)) throw std::runtime_error(std::string(who) + ": ops_stride must be stream.ops_stride()");
+  if (nvbx_stream_traceback(s.h, &a, band_len) != 0 || nvbx_stream_alignments(s.h, stream.m_alignments, stream.m_ops) != 0)
+    throw std::runtime_error(std::string(who) + ": " + nvbx_last_error());
+}
+}  // namespace detail
+
+// batched.h:337-357
+template <uint32_t BAND_LEN, typename stream_type, typename algorithm_type = DeviceThreadScheduler>
+struct BatchedBandedAlignmentScore {
+  typedef typename stream_type::aligner_type aligner_type;
+  static uint64_t min_temp_storage(uint32_t, uint32_t, uint32_t) { return 0; }
+  static uint64_t max_temp_storage(uint32_t, uint32_t, uint32_t) { return 0; }
+  void enact(stream_type stream, uint64_t /*temp_size*/ = 0u, uint8_t* /*temp*/ = nullptr) {
+    detail::StreamHandle s(&stream.m_batch, "BatchedBandedAlignmentScore::enact");
+    const nvbx_aligner_t a = stream.aligner().pod();
+    if (nvbx_stream_enact_banded(s.h, &a, (int)BAND_LEN, (stream.m_sink_text || stream.m_sink_pattern) ? 1 : 0) != 0 ||
+        nvbx_stream_results(s.h, stream.m_scores, stream.m_sink_text, stream.m_sink_pattern) != 0)
+      throw std::runtime_error(std::string("BatchedBandedAlignmentScore::enact: ") + nvbx_last_error());
+  }
+};
+// batched.h:436-451 (CHECKPOINTS is accepted and ignored: the flow matrix is kept whole)
+template <uint32_t CHECKPOINTS, typename stream_type, typename algorithm_type = DeviceThreadScheduler>
+struct BatchedAlignmentTraceback {
+  static uint64_t min_temp_storage(uint32_t, uint32_t, uint32_t) { return 0; }
+  static uint64_t max_temp_storage(uint32_t, uint32_t, uint32_t) { return 0; }
+  void enact(stream_type stream, uint64_t /*temp_size*/ = 0u, uint8_t* /*temp*/ = nullptr) { detail::traceback(stream, 0, "BatchedAlignmentTraceback::enact"); }
+};
+// batched.h:463-478
+template <uint32_t BAND_LEN, uint32_t CHECKPOINTS, typename stream_type, typename algorithm_type = DeviceThreadScheduler>
+struct BatchedBandedAlignmentTraceback {
+  static uint64_t min_temp_storage(uint32_t, uint32_t, uint32_t) { return 0; }
+  static uint64_t max_temp_storage(uint32_t, uint32_t, uint32_t) { return 0; }
+  void enact(stream_type stream, uint64_t /*temp_size*/ = 0u, uint8_t* /*temp*/ = nullptr) { detail::traceback(stream, (int)BAND_LEN, "BatchedBandedAlignmentTraceback::enact"); }
 };
 
 }  // namespace aln

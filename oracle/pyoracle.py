@@ -267,8 +267,16 @@ class NvbioOracle:
                                                 C.c_void_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         ref = os.path.join(HERE, "_ref", "libnvbio_ref.so")
         self.ref = C.CDLL(ref) if os.path.exists(ref) else None
+        V, U = C.c_void_p, C.c_uint32
+        self.lib.nvbio_compat_banded_score.argtypes = [C.c_int, C.c_int, C.c_int, V, V, U, V, U, V]
+        self.lib.nvbio_compat_traceback.argtypes = [C.c_int, C.c_int, V, V, U, V, U, U, V, V, U]
+        self.lib.nvbio_compat_banded_traceback.argtypes = [C.c_int, C.c_int, C.c_int, V, V, U, V, U, V, V, U]
         if self.ref is not None:
             self.ref.nvbio_ref_score.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p]
+            if hasattr(self.ref, "nvbio_ref_traceback"):
+                self.ref.nvbio_ref_banded_score.argtypes = [C.c_int, C.c_int, C.c_int, V, V, U, V, U, V]
+                self.ref.nvbio_ref_traceback.argtypes = [C.c_int, C.c_int, V, V, U, V, U, V, V, U]
+                self.ref.nvbio_ref_banded_traceback.argtypes = [C.c_int, C.c_int, C.c_int, V, V, U, V, U, V, V, U]
 
     @staticmethod
     def _scheme(scheme):
@@ -288,6 +296,34 @@ class NvbioOracle:
         assert rc == 0
         return tuple(int(x) for x in out)
 
+    # ---- banded scoring and traceback (banded_inl.h, alignment_inl.h:361-467); ref=True runs the reference's own host code ----
+    def banded_score(self, algo, type_, band, scheme, pattern, text, ref=False):
+        """(score, sink text end, sink pattern end, ok)"""
+        p = np.ascontiguousarray(pattern, dtype=np.uint8); t = np.ascontiguousarray(text, dtype=np.uint8)
+        sc = self._scheme(scheme); out = np.zeros(4, np.int32)
+        fn = self.ref.nvbio_ref_banded_score if ref else self.lib.nvbio_compat_banded_score
+        rc = fn(algo, type_, band, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, out.ctypes.data)
+        assert rc == 0, rc
+        return tuple(int(x) for x in out)
+
+    def traceback(self, algo, type_, scheme, pattern, text, band=0, ref=False):
+        """band = 0: full-matrix alignment_traceback; else banded_alignment_traceback<band>.  Returns a dict: score, source (text,
+        pattern), sink (text, pattern), ops (uint8, push order: from the END of the alignment to its source; 0 substitution,
+        1 insertion, 2 deletion), clip_end, clip_begin."""
+        p = np.ascontiguousarray(pattern, dtype=np.uint8); t = np.ascontiguousarray(text, dtype=np.uint8)
+        sc = self._scheme(scheme); out = np.zeros(9, np.int32); cap = p.size + t.size + 8; ops = np.zeros(cap, np.uint8)
+        if band:
+            fn = self.ref.nvbio_ref_banded_traceback if ref else self.lib.nvbio_compat_banded_traceback
+            rc = fn(algo, type_, band, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, out.ctypes.data, ops.ctypes.data, cap)
+        elif ref:
+            rc = self.ref.nvbio_ref_traceback(algo, type_, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, out.ctypes.data, ops.ctypes.data, cap)
+        else:
+            rc = self.lib.nvbio_compat_traceback(algo, type_, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, NVB_BAND[algo],
+                                                 out.ctypes.data, ops.ctypes.data, cap)
+        assert rc == 0, rc
+        return dict(score=int(out[0]), source=(int(out[1]), int(out[2])), sink=(int(out[3]), int(out[4])), ops=ops[:int(out[5])].copy(),
+                    clip_end=int(out[6]), clip_begin=int(out[7]))
+
     def batch(self, algo, type_, scheme, patterns, poffs, texts, toffs, pair_pattern=None, pair_text=None, n_pairs=None):
         patterns = np.ascontiguousarray(patterns, dtype=np.uint8); texts = np.ascontiguousarray(texts, dtype=np.uint8)
         poffs = np.ascontiguousarray(poffs, dtype=np.uint32); toffs = np.ascontiguousarray(toffs, dtype=np.uint32)
@@ -302,3 +338,17 @@ class NvbioOracle:
                                          NVB_BAND[algo], s.ctypes.data, si.ctypes.data, sj.ctypes.data)
         assert rc == 0
         return s, si, sj
+
+
+def nvb_rle(ops, order="push") -> str:
+    """run-length string of a traceback's ops in the letters of the reference's test program (M / I / D,
+    NvB/nvbio-test/alignment_test.cu); order="push" keeps the reference's push order (end of the alignment first)"""
+    seq = list(ops) if order == "push" else list(ops)[::-1]
+    out, i = [], 0
+    while i < len(seq):
+        j = i
+        while j < len(seq) and seq[j] == seq[i]:
+            j += 1
+        out.append(f"{j - i}{'MID'[seq[i]]}")
+        i = j
+    return "".join(out)

@@ -22,6 +22,26 @@ static void batch_score_profile(const aligner_type aligner, uint32_t n, const st
   for (uint32_t i = 0; i < n; ++i) printf("%d %d %d %d\n", type_id, score[i], si[i], sj[i]);
 }
 
+// the reference's traceback batch (batched.h:436-451): prints "type score source_text source_pattern sink_text sink_pattern n_ops" and the ops
+template <typename aligner_type>
+static void batch_traceback(const aligner_type aligner, uint32_t n, const std::vector<uint8_t>& p, const std::vector<uint32_t>& po,
+                            const std::vector<uint8_t>& t, const std::vector<uint32_t>& to, int type_id) {
+  typedef aln::HostTracebackStream<aligner_type> stream_type;
+  typedef aln::BatchedAlignmentTraceback<32u, stream_type> batch_type;
+  std::vector<nvbx_alignment_t> alns(n);
+  stream_type probe(aligner, n, p.data(), po.data(), (uint32_t)po.size() - 1, t.data(), to.data(), (uint32_t)to.size() - 1, alns.data(), NULL, 0);
+  const uint32_t stride = probe.ops_stride();
+  std::vector<uint8_t> ops((size_t)n * stride);
+  stream_type stream(aligner, n, p.data(), po.data(), (uint32_t)po.size() - 1, t.data(), to.data(), (uint32_t)to.size() - 1, alns.data(), ops.data(), stride);
+  batch_type batch;
+  batch.enact(stream);
+  for (uint32_t i = 0; i < n; ++i) {
+    printf("%d %d %d %d %d %d %u ", type_id, alns[i].score, alns[i].source_text, alns[i].source_pattern, alns[i].sink_text, alns[i].sink_pattern, alns[i].n_ops);
+    for (uint32_t k = 0; k < alns[i].n_ops; ++k) putchar("MID"[ops[(size_t)i * stride + k]]);
+    putchar('\n');
+  }
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { fprintf(stderr, "usage: %s jobs.bin\n", argv[0]); return 2; }
   FILE* f = fopen(argv[1], "rb");
@@ -40,6 +60,7 @@ int main(int argc, char** argv) {
     batch_score_profile(aln::make_gotoh_aligner<aln::SEMI_GLOBAL>(scoring), np, p, po, t, to, 2);
     batch_score_profile(aln::make_gotoh_aligner<aln::LOCAL>(scoring), np, p, po, t, to, 1);
     batch_score_profile(aln::make_edit_distance_aligner<aln::SEMI_GLOBAL>(), np, p, po, t, to, 3);
+    if (argc > 2) batch_traceback(aln::make_gotoh_aligner<aln::LOCAL>(scoring), np, p, po, t, to, 4);     // any second argument: also trace the local alignments back
   } catch (const std::exception& e) { fprintf(stderr, "%s\n", e.what()); return 1; }
   return 0;
 }
