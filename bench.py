@@ -292,6 +292,26 @@ def nvb_extra(n: int):
             for _ in range(3):
                 st.enact(al); best = min(best, st.last_ms())
             out[name] = {"kernel": st.kernel(), "dp_ms": best, "gcups_dp": cells / best / 1e6}
+        # BatchedAlignmentTraceback (batched.h:436-451): full flow matrix + walk, Gotoh local / semi-global
+        for name, al in (("traceback_gotoh_local", nvb.aligner(nvb.GOTOH, nvb.LOCAL, 2, -1, -2, -1)), ("traceback_gotoh_semi_global", nvb.aligner(nvb.GOTOH, nvb.SEMI_GLOBAL, 2, -1, -2, -1))):
+            best = 1e30
+            for _ in range(2):
+                st.traceback(al); best = min(best, st.last_ms())
+            out[name] = {"kernel": st.kernel(), "ms": best, "gcups": cells / best / 1e6, "alignments_per_s": n / best * 1e3,
+                         "flow_bytes_per_launch_set": 0.5 * cells}
+    # BatchedBandedAlignmentScore<31> / BatchedBandedAlignmentTraceback<31> (batched.h:337-357, :463-478): 150 bp reads in 150 + 31 + 3 bp windows
+    pats, poffs, texts, toffs = synth.nvb_banded_jobs(n, 150, 150, 31, seed=32, sub=0.02, indel=0.002, slack=3)
+    with nvb.Stream(nvb.Batch(pats, poffs, texts, toffs)) as st:
+        band_cells = float(np.diff(poffs).astype(np.int64).sum()) * 31
+        al = nvb.aligner(nvb.GOTOH, nvb.SEMI_GLOBAL, 2, -1, -2, -1)
+        best = 1e30
+        for _ in range(3):
+            st.enact_banded(al, 31); best = min(best, st.last_ms())
+        out["banded31_gotoh_semi_global"] = {"kernel": st.kernel(), "dp_ms": best, "band_gcups": band_cells / best / 1e6, "jobs_per_s": n / best * 1e3}
+        best = 1e30
+        for _ in range(3):
+            st.traceback(al, 31); best = min(best, st.last_ms())
+        out["banded31_traceback_gotoh_semi_global"] = {"kernel": st.kernel(), "ms": best, "band_gcups": band_cells / best / 1e6, "alignments_per_s": n / best * 1e3}
     return out
 
 

@@ -72,6 +72,9 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 #ifndef GB200_PRUNE_REVERSE
 #define GB200_PRUNE_REVERSE 1
 #endif
+#ifndef GB200_PRUNE_RISKY_LANES
+#define GB200_PRUNE_RISKY_LANES 4
+#endif
 #ifndef GB200_TRACK_IMAD
 #define GB200_TRACK_IMAD 1
 #endif
@@ -1391,6 +1394,14 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     if (GB200_PRUNE_REVERSE && !top_zero && mstep + a.gap_extend > 0) {
       const int num = mstep * (int)qlen - fwd - a.gap_open + a.gap_extend;
       slack = (int)__reduce_max_sync(__activemask(), (unsigned)max(num, 0) / (unsigned)(mstep + a.gap_extend));
+      // The bound pass cannot reach the forward score when the forward path starts with a gap on the top boundary (the reversed DP
+      // prices that gap one extension higher), and then the exact pass has to follow: twice the work.  Such a path starts on target
+      // row 0, i.e. it spends tr.y + 1 - qlen deletions or more, which the score allows only up to (m qlen - score - open) / ext.
+      // Where several pairs of a warp are in that position (reads in tight windows: the reference's real-read fixture), the warp
+      // runs the exact pass straight away; a few such pairs (C2: reads anywhere in a 600 bp window) are not worth giving the bound up.
+      const int maxdel = a.gap_extend > 0 ? max(mstep * (int)qlen - fwd - a.gap_open, 0) / a.gap_extend : 0x7FFFFFF;
+      const bool risky = (tr.y + 1 - (int)qlen) <= maxdel;
+      if (__popc(__ballot_sync(__activemask(), risky)) >= GB200_PRUNE_RISKY_LANES) slack = ncol;
     }
     NcTrack rt;
     for (int attempt = 0; attempt < 2; attempt++) {
