@@ -199,11 +199,13 @@ def dpx_peak_ops_per_s():
         return 148 * 64 * 1.965e9, "a-priori 148 SM x 64 lanes/clk x 1.965 GHz (microbenchmark file missing)"
 
 
-def ncu_traffic(kernel_key: str):
-    p = os.path.join(ROOT, "profiles", "ncu_summary_r01.json")
+def ncu_traffic(kernel_key: str, pairs_per_launch: int):
+    """DRAM bytes per launch of the kernel from the committed `ncu --set full` capture (profiles/ncu_summary_r02.json: bytes per pair of
+    one 65536-pair launch), scaled to this run's pairs per launch"""
+    p = os.path.join(ROOT, "profiles", "ncu_summary_r02.json")
     try:
         with open(p) as f:
-            return json.load(f)[kernel_key]["dram_bytes_per_launch"]
+            return json.load(f)[kernel_key]["dram_bytes_per_pair"] * pairs_per_launch
     except Exception:
         return None
 
@@ -678,13 +680,13 @@ def run_ours(args, rank, world, local_rank):
         "gpu_launches": int(main_arm["launches"]),
         "clocks": clocks,
         "roofline": {"bound": "dpx-integer-pipe", "kernel": f"{top} DP ({kernel_names[top]})", "achieved": achieved, "peak": peak_gcups, "unit": "GCUPS",
-                     "frac": achieved / peak_gcups, "traffic": ncu_traffic(top),
+                     "frac": achieved / peak_gcups, "traffic": ncu_traffic(top, n // max(1, len(subs))), "algorithmic_bytes": 396 * (n // max(1, len(subs))),
                      "peak_def": f"R / {ops_per_cell:g} ops per cell, R = {R:.4g} lane-ops/s, {R_src}",
                      "note": "compute-bound integer DP (SURVEY 8d): compulsory HBM traffic is < 0.01 B/cell; the HBM-bound stage is pack, below. "
                              "achieved counts FORWARD cells only while the launch also runs the start pass; "
                              "other_configs.C2_forward_only has the same kernels without it"},
         "roofline_pack": {"bound": "hbm", "achieved": pack_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": pack_gbs / hbm_peak,
-                          "traffic": ncu_traffic("pack"), "bytes_def": "1.5 B per base (1 read + 0.5 written)",
+                          "traffic": ncu_traffic("pack", n // max(1, len(subs))), "bytes_def": "1.5 B per base (1 read + 0.5 written)",
                           "note": "k_pack is on the path only for ASCII pages (host packing off); timed here on the same sequences"},
         "cpu_baseline": {"value": cpu_val, "unit": "GCUPS", "cores": cpu_threads, "kind": cpu_kind,
                          "sample": f"first {cpu_n} pairs of the same workload, both modes, {cpu_dt:.1f} s"},

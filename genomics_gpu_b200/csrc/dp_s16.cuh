@@ -23,6 +23,7 @@
 #include "dp_generic.cuh"
 #include "dp_launch.h"
 #include <type_traits>
+#include <stdlib.h>
 #pragma nv_diag_suppress 128   // "loop is not reachable": k_local_s16<START_TB> returns before the score-only sweeps
 
 namespace gb200 {
@@ -1586,7 +1587,9 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
   }
   FastArgs fa; fa.a = a; fa.q8max = q8; fa.worklist = fs.worklist; fa.worklist2 = fs.worklist + fs.cap; fa.work_count = fs.work_count; fa.flags = passes ? fs.flags : nullptr;
   fa.eight = 8; fa.thirtytwo = 32; fa.one = 1; fa.mm = 0x00204081u; fa.sixteen = 16;
-  const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads;
+  // GASALX_FAST_SMEM_PAD_KB (experiments only): extra dynamic shared memory per CTA, to measure the same kernel at a lower residency
+  static const size_t smem_pad = [] { const char* e = getenv("GASALX_FAST_SMEM_PAD_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
+  const size_t smem = (size_t)(q8 + kSlotPad) * kFastThreads * 4 + (size_t)(q8 + kSlotPad) * kFastThreads + smem_pad;
   if (!fs.attr_set) {
     const int lim = 227 * 1024;
     cudaFuncSetAttribute(k_local_s16<START_NONE>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
