@@ -73,6 +73,16 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 #ifndef GB200_PRUNE_REVERSE
 #define GB200_PRUNE_REVERSE 1
 #endif
+#ifndef GB200_TBB_UNROLL
+#define GB200_TBB_UNROLL 2          // step loop of the banded direction sweep: 2 = +24 % (shift registers and diagonal rotation become renaming); 4 = -35 % (instruction cache)
+#endif
+#ifndef GB200_TB_UNROLL
+#define GB200_TB_UNROLL 2          // same for the unbanded direction sweep: +8 %
+#endif
+#define GB200_PRAGMA_(x) _Pragma(#x)
+#define GB200_UNROLL_(n) GB200_PRAGMA_(unroll n)
+#define GB200_TBB_UNROLL_PRAGMA GB200_UNROLL_(GB200_TBB_UNROLL)
+#define GB200_TB_UNROLL_PRAGMA GB200_UNROLL_(GB200_TB_UNROLL)
 #ifndef GB200_PRUNE_RISKY_LANES
 #define GB200_PRUNE_RISKY_LANES 4
 #endif
@@ -506,7 +516,7 @@ __device__ __forceinline__ void local_sweep4_tb(uint32_t* __restrict__ HE, const
   uint32_t pos = pos_base;
   const uint32_t minus1_2 = 0xFFFFFFFFu;
   const int nsteps = ncol + 2 + (int)one;          // run-time 1: opaque trip count (see the compiler note in DESIGN.md)
-#pragma unroll 1
+GB200_TB_UNROLL_PRAGMA
   for (int k = 0; k < nsteps; k++) {
     const uint32_t selA = v | prevsh;
     prevsh = v * 256u + 0x4400u;
@@ -624,7 +634,7 @@ __device__ __forceinline__ void local_sweep4_tbb(uint32_t* __restrict__ HE, cons
       for (int r = 0; r < 8; r++) { pB[r] &= keepB; fB[r] &= keepB; }
     }
     const bool stA0 = (inA & 0xFFFFu) != 0, stA1 = (inA >> 16) != 0, stB0 = (inB & 0xFFFFu) != 0, stB1 = (inB >> 16) != 0;
-#pragma unroll 1
+GB200_TBB_UNROLL_PRAGMA
     for (; k < next; k++) {
       const uint32_t selA = v | prevsh;
       prevsh = v * 256u + 0x4400u;
