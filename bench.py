@@ -344,6 +344,9 @@ def run_extras(local_rank: int, n_fwd: int):
         b4 = synth.config4(n_fwd, seed=4)
         out["C4_banded_k64_250bp"] = {"score_end": timed(b4, algo=capi.BANDED, k_band=64), "with_cigar": timed(b4, algo=capi.BANDED, k_band=64, start=capi.WITH_TB)}
         out["C5_mixed_100bp_10kb_local_with_start"] = timed(synth.config5(4000, seed=5), algo=capi.LOCAL, start=capi.WITH_START)
+        # long reads in flanked windows, semi-global (read global, window free at both ends): the s16x2 wavefront lanes (k_wave16_semi)
+        lr = synth.long_read_windows(600, 2000, 9000, 1500, seed=5)
+        out["long_reads_2kb_9kb_semi_global"] = {"score_end": timed(lr, algo=capi.SEMI_GLOBAL), "with_start": timed(lr, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)}
         out["C1_10k_pairs_150x300_local"] = config1_extra(local_rank)
         # reads with uncalled bases: pairs with an N leave the main s16x2 launch for its N-aware second pass (one more LOP3 per cell pair)
         out["C2_local_with_start_vs_fraction_of_pairs_with_N"] = {

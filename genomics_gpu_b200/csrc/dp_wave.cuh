@@ -157,6 +157,15 @@ __device__ __forceinline__ void wave_finalize(const WaveArgs& w, uint32_t pair, 
   }
 }
 
+#ifndef WAVE16_STEP_UNROLL
+#define WAVE16_STEP_UNROLL 1
+#endif
+#define WAVE_PRAGMA_(x) _Pragma(#x)
+#define WAVE_UNROLL_(n) WAVE_PRAGMA_(unroll n)
+#define WAVE16_UNROLL_PRAGMA WAVE_UNROLL_(WAVE16_STEP_UNROLL)
+#ifndef WAVE16_SEMI
+#define WAVE16_SEMI 1
+#endif
 constexpr int kWaveSteadyUnroll = 4;
 template <int SR>
 struct WaveLane {
@@ -466,6 +475,7 @@ template <bool EXOTIC, bool TB = false>
 __device__ __forceinline__ void wave16_steps(Wave16Lane& L, const Sc& sc, const uint2* sin, const uint32_t* ssel, uint2* sout,
                                              int k0, int kend, int ncol, int lane, uint32_t neg_oe2, uint32_t neg_ext2,
                                              Wave16Tb* T = nullptr, uint4* __restrict__ tbL = nullptr, uint4* __restrict__ tbH = nullptr, uint32_t mm = 0, uint32_t sixteen = 0) {
+WAVE16_UNROLL_PRAGMA
   for (int k = k0; k < kend; k++) {
     const uint2 top = sin[k & 31];
     const uint32_t v = ssel[(k - 2 * lane) & 127];
@@ -666,6 +676,7 @@ template <bool EXOTIC>
 __device__ __forceinline__ void wave16g_steps(Wave16G& L, const Sc& sc, const uint2* sin, const uint32_t* ssel, uint2* sout,
                                               int k0, int kend, int lane, uint32_t neg_o2, uint32_t conv8, const uint32_t (&dinit)[8], uint32_t floor2,
                                               int kcapL, int kcapH, int caprow, int unbias_cap, int32_t* score_out) {
+WAVE16_UNROLL_PRAGMA
   for (int k = k0; k < kend; k++) {
     const uint2 top = sin[k & 31];
     const uint32_t v = ssel[(k - 2 * lane) & 127];
@@ -827,6 +838,222 @@ __global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_glo
   }
 }
 
+// =====================================================================================================
+// k_wave16_semi: SEMI_GLOBAL (TAIL = TARGET, HEAD in {TARGET, BOTH}: semiglobal_kernel_template.h:39-388) on the same s16x2
+// row-block pipeline, in the biased and shifted frame of k_wave16_global.  Recurrence of dp_s16.cuh nc_step (H-based opening
+// without the H -> E -> H chain; E parked as E + open): per cell pair PRMT, VIADDMNMX (F from the previous column's H),
+// VIMNMX3 (H), VIMNMX3 (E + open) + two VIADD.16x2.  Free left column: every half enters the matrix with H(r, -1) = 0.  The last
+// true query column is scanned per strip (rows inside the target, strict '>' top-down, :160-178); the last finishing block folds
+// the per-strip candidates (wave_finalize: the start pass stops after the first strip that reaches the forward score, :301).
+struct Wave16S {
+  uint32_t rowA[8], rowB[8];
+  uint32_t f[8], hh[8];           // hh: H of the previous step = F input of the same row and diagonal input of the row below
+  uint32_t p0;                    // incoming top H of the previous step = diagonal input of row 0
+  uint32_t out_h, out_e, prevsh, vprev;
+  uint32_t twA, twB;
+  int bestL, bestH, yL, yH;       // per-strip candidates: best H(row, qlen - 1) and its row (sequence numbering of the pass)
+};
+
+template <bool EXOTIC>
+__device__ __forceinline__ void wave16s_steps(Wave16S& L, const Sc& sc, const uint2* sin, const uint32_t* ssel, uint2* sout,
+                                              int k0, int kend, int lane, uint32_t neg_o2, uint32_t conv8, const uint32_t (&dinit)[9], uint32_t floor2,
+                                              int kscanL, int kscanH, int rowbaseL, int rowbaseH, int tlen, int unbias0) {
+WAVE16_UNROLL_PRAGMA
+  for (int k = k0; k < kend; k++) {
+    const uint2 top = sin[k & 31];
+    const uint32_t v = ssel[(k - 2 * lane) & 127];
+    uint32_t xh = __shfl_up_sync(0xFFFFFFFFu, L.out_h, 1);
+    uint32_t xe = __shfl_up_sync(0xFFFFFFFFu, L.out_e, 1);
+    if (lane == 0) { xh = top.x << 16; xe = top.y << 16; }
+    uint32_t up = prmt(xh, L.out_h, 0x5432);       // low half <- lane above, high strip; high half <- own low strip, previous step
+    uint32_t e = prmt(xe, L.out_e, 0x5432);
+    const uint32_t sel = (v & 0xFFu) | L.prevsh;
+    L.prevsh = (v & 0xFFu) * 256u + 0x4400u;
+    // a half enters the matrix: low half at step 2 * lane (column 0), high half one step later: impose the free left column
+    const int kin = k - 2 * lane;
+    if ((unsigned)kin < 2u) {
+      const uint32_t m = kin ? 0x7610u : 0x3254u;
+      L.p0 = prmt(L.p0, dinit[0], m);
+#pragma unroll
+      for (int r = 0; r < 8; r++) L.hh[r] = prmt(L.hh[r], dinit[r + 1], m);    // H(r, -1) = 0 in the frame of (r, -1): F input of row r, diagonal input of row r + 1
+#pragma unroll
+      for (int r = 0; r < 8; r++) L.f[r] = prmt(L.f[r], floor2, m);
+    }
+    uint32_t dg[8];
+    dg[0] = L.p0;
+#pragma unroll
+    for (int r = 1; r < 8; r++) dg[r] = L.hh[r - 1];
+    L.p0 = up;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t s2;
+      if (EXOTIC && ((v | L.vprev) & kWaveExotic)) {
+        const int sl = score_general(sc, (v >> 20) & 15u, nib(L.twA, r)) + 2 * sc.ext, sh = score_general(sc, (L.vprev >> 20) & 15u, nib(L.twB, r)) + 2 * sc.ext;
+        s2 = ((uint32_t)sl & 0xFFFFu) | ((uint32_t)sh << 16);
+      } else s2 = prmt(L.rowA[r], L.rowB[r], sel);
+      const uint32_t d = __vadd2(dg[r], s2);
+      L.f[r] = __viaddmax_s16x2(L.hh[r], neg_o2, L.f[r]);              // F(t,q) = max(H(t,q-1) - oe, F(t,q-1) - e), biased frame
+      const uint32_t h = __vimax3_s16x2(d, L.f[r], __vadd2(e, neg_o2)); // e holds E + open
+      e = __vimax3_s16x2(e, d, L.f[r]);                                // E(t+1,q) + open = max(E + open, max(D, F)), biased frame
+      L.hh[r] = h; up = h;
+    }
+    if (k == kscanL || k == kscanH) {                                  // this half is on the last true query column (:160-178)
+      const bool low = (k == kscanL);
+      const int rb = low ? rowbaseL : rowbaseH;
+      int best = low ? L.bestL : L.bestH, y = low ? L.yL : L.yH;
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        const int hv = (low ? (int)(short)(L.hh[r] & 0xFFFFu) : (int)(short)(L.hh[r] >> 16)) - (unbias0 + r * sc.ext);
+        if (rb + r < tlen && hv > best) { best = hv; y = rb + r; }
+      }
+      if (low) { L.bestL = best; L.yL = y; } else { L.bestH = best; L.yH = y; }
+    }
+    L.out_h = __vadd2(up, conv8); L.out_e = __vadd2(e, conv8);          // into the frame of the strip below
+    L.vprev = v;
+    if (lane == 31) sout[k & 31] = make_uint2((uint32_t)(int)(short)(L.out_h >> 16), (uint32_t)(int)(short)(L.out_e >> 16));
+  }
+}
+
+__global__ void __launch_bounds__(kWaveWarps * 32, WAVE16_MIN_CTAS) k_wave16_semi(const WaveArgs w) {
+  __shared__ uint2 s_in[kWaveWarps][32];
+  __shared__ uint32_t s_sel[kWaveWarps][128];
+  __shared__ uint2 s_out[kWaveWarps][32];
+  const DpArgs& a = w.a;
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  uint2* sin = s_in[wib]; uint32_t* ssel = s_sel[wib]; uint2* sout = s_out[wib];
+  const Sc sc = make_sc(a, false);
+  const int ext = sc.ext, o = sc.o, K = w.kshift;
+  const bool top_zero = (a.head == SKIP_BOTH);
+  const uint32_t total = (uint32_t)a.n * w.maxblk;
+  const uint32_t neg_o2 = (((uint32_t)(-o)) & 0xFFFFu) * 0x00010001u, conv8 = (((uint32_t)(-8 * ext)) & 0xFFFFu) * 0x00010001u;
+  const uint32_t floor2 = (((uint32_t)w.floor16) & 0xFFFFu) * 0x00010001u;
+
+  for (;;) {
+    uint32_t T = 0;
+    if (lane == 0) T = atomicAdd(w.ticket, 1u);
+    T = __shfl_sync(0xFFFFFFFFu, T, 0);
+    if (T >= total) break;
+    const uint32_t blk = T / (uint32_t)a.n, pair = T - blk * (uint32_t)a.n;
+    const WaveGeom g = wave_geometry(w, pair);
+    const int nblk = (g.nstrips + 63) / 64;
+    if ((int)blk >= nblk) {
+      if (blk == 0) wave_finalize<ALGO_SEMI_GLOBAL>(w, pair, g, lane);   // empty problem: defaults
+      continue;
+    }
+    const int qlen = (int)a.q_lens[pair], tlen = (int)a.t_lens[pair];
+    const uint32_t* qw = a.pq + (a.q_offs[pair] >> 3);
+    const uint32_t* tw = a.pt + (a.t_offs[pair] >> 3);
+    const int ncol = g.ncol;
+    const int lstrip = ((int)blk * 32 + lane) * 2;
+    const bool last_blk = ((int)blk == nblk - 1);
+
+    Wave16S L;
+    L.twA = (lstrip < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip) : 0u;
+    L.twB = (lstrip + 1 < g.nstrips) ? wave_tword(w, g, tw, tlen, lstrip + 1) : 0u;
+    uint32_t dinit[9];
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      uint32_t ta = 0, tb = 0;
+      const uint32_t ca = nib(L.twA, r), cb = nib(L.twB, r);
+      const uint32_t qcodes[4] = {1u, 3u, 7u, 4u};
+#pragma unroll
+      for (int i = 0; i < 4; i++) {
+        ta |= ((uint32_t)(score_general(sc, qcodes[i], ca) + 2 * ext) & 0xFFu) << (8 * i);
+        tb |= ((uint32_t)(score_general(sc, qcodes[i], cb) + 2 * ext) & 0xFFu) << (8 * i);
+      }
+      L.rowA[r] = ta; L.rowB[r] = tb; L.f[r] = floor2; L.hh[r] = 0;
+    }
+    // free left column (:114-121): dinit[r] = H(r - 1, -1) = 0 in the frame of (r - 1, -1), shifted by K
+#pragma unroll
+    for (int r = 0; r < 9; r++) dinit[r] = (((uint32_t)((r - 2) * ext - K)) & 0xFFFFu) * 0x00010001u;
+    L.p0 = 0; L.out_h = 0; L.out_e = 0; L.prevsh = 0xCC00u; L.vprev = 0x88u;
+    L.bestL = L.bestH = kMinusInf; L.yL = L.yH = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) ssel[lane + 32 * i] = 0x88u;
+    __syncwarp();
+    const int kscanL = (lstrip < g.nstrips) ? (qlen - 1) + 2 * lane : -1, kscanH = (lstrip + 1 < g.nstrips) ? (qlen - 1) + 2 * lane + 1 : -1;
+    const int rowbaseL = 8 * (g.strip0 + lstrip), rowbaseH = rowbaseL + 8;
+    const int unbias0 = (qlen - 1) * ext - K;
+
+    const uint4* bnd_in = w.bnd + (uint64_t)((blk + 1) & 1) * w.bnd_stride + w.qoff[pair];
+    uint4* bnd_out = w.bnd + (uint64_t)(blk & 1) * w.bnd_stride + w.qoff[pair];
+    const uint32_t tag_in = w.tag_base + blk - 1, tag_out = w.tag_base + blk;
+    uint4 pre = make_uint4(0, 0, 0, 0);
+    if (blk != 0 && lane < ncol) pre = ld_bnd(bnd_in + lane);
+
+    const int nsteps = ncol + 63;
+    int exo_hist = 0;
+    for (int k0 = 0; k0 < nsteps; k0 += 32) {
+      exo_hist <<= 1;
+      {
+        const int c = k0 + lane;
+        uint2 v = make_uint2(0u, 0u);
+        uint32_t selv = 0x88u;
+        if (k0 < ncol) {
+          if (blk != 0) {
+            bool ok = (c >= ncol) || (pre.y == tag_in && pre.w == tag_in);
+            while (!__all_sync(0xFFFFFFFFu, ok)) {
+              __nanosleep(20);
+              if (!ok) { pre = ld_bnd(bnd_in + c); ok = (pre.y == tag_in && pre.w == tag_in); }
+            }
+            v.x = pre.x; v.y = pre.z;
+            if (c + 32 < ncol) pre = ld_bnd(bnd_in + c + 32);
+          } else if (c < ncol) {
+            // top boundary (:87-99): H(-1,c) = c ? -(o + e c) : 0 (HEAD = BOTH: 0) in the frame of (row -1, column c); the first row's
+            // own E(0,c) = H(-1,c) - oe (HEAD = BOTH: max(0 - oe, 0 - e) = -e), parked as E + open in the frame of (row 0, column c)
+            const int htop = top_zero ? 0 : ((c == 0) ? 0 : -(o + ext * c));
+            v.x = (uint32_t)(htop + (c - 1) * ext - K);
+            v.y = (uint32_t)((top_zero ? -ext : htop - (o + ext)) + c * ext + o - K);
+          }
+          if (c < ncol) {
+            const uint32_t qword = wave_qword(w, g, qw, qlen, c >> 3);
+            const uint32_t qc = nib(qword, c & 7);
+            const uint32_t idx = base_idx(qc);
+            selv = (idx < 4) ? (0x80u + 0x11u * idx) | (qc << 20) : (0x88u | kWaveExotic | (qc << 20));
+          }
+        }
+        if (__any_sync(0xFFFFFFFFu, (selv & kWaveExotic) != 0)) exo_hist |= 1;
+        __syncwarp();
+        sin[lane] = v;
+        ssel[c & 127] = selv;
+        __syncwarp();
+      }
+      const int kend = min(k0 + 32, nsteps);
+      if (exo_hist & 7) wave16s_steps<true>(L, sc, sin, ssel, sout, k0, kend, lane, neg_o2, conv8, dinit, floor2, kscanL, kscanH, rowbaseL, rowbaseH, tlen, unbias0);
+      else wave16s_steps<false>(L, sc, sin, ssel, sout, k0, kend, lane, neg_o2, conv8, dinit, floor2, kscanL, kscanH, rowbaseL, rowbaseH, tlen, unbias0);
+      if (!last_blk) {
+        __syncwarp();
+        const int cb = k0 - 63 + lane;
+        if (cb >= 0 && cb < ncol && k0 + lane < kend) { const uint2 ov = sout[lane]; st_bnd(bnd_out + cb, make_uint4(ov.x, tag_out, ov.y, tag_out)); }
+        __syncwarp();
+      }
+    }
+    int2* cand = w.cand + w.soff[pair];
+    if (lstrip < g.nstrips) __stcg(&cand[lstrip], make_int2(L.bestL, L.bestL == kMinusInf ? 0 : L.yL));
+    if (lstrip + 1 < g.nstrips) __stcg(&cand[lstrip + 1], make_int2(L.bestH, L.bestH == kMinusInf ? 0 : L.yH));
+    __syncwarp();
+    uint32_t old = 0;
+    if (lane == 0) { __threadfence(); old = atomicAdd(w.done + pair, 1u); }
+    old = __shfl_sync(0xFFFFFFFFu, old, 0);
+    if ((int)old == nblk - 1) { __threadfence(); wave_finalize<ALGO_SEMI_GLOBAL>(w, pair, g, lane); }
+  }
+}
+
+// Range proof for k_wave16_semi: biased values X + (c + r) ext - K of every real H / E + open / F.  The free left column makes the
+// lower end independent of the lengths (every cell can be reached from H(t, -1) = 0 by one gap of c + 1 columns, which the frame
+// cancels): lower >= -(3 oe + mismatch + 9 ext + 64); upper: H <= match * min(q, t), bias <= (q8 + 64 + 8) ext, E carries + open.
+inline bool wave16_semi_range(const DpArgs& a, uint32_t max_q, uint32_t max_t, int* kshift, int* floor16) {
+  if (a.match < 0 || a.mismatch < 0 || a.gap_open < 0 || a.gap_extend < 0 || a.match + 2 * a.gap_extend > 127) return false;
+  if (a.n_score < -127 || a.n_score + 2 * a.gap_extend > 127) return false;
+  const int64_t q8 = (max_q + 7) & ~7ll, t8 = (max_t + 7) & ~7ll, oe = (int64_t)a.gap_open + a.gap_extend;
+  const int64_t ub = (int64_t)a.match * std::min<int64_t>(q8, t8) + (q8 + 72) * a.gap_extend + a.gap_open + 64;
+  const int64_t lb = -(3 * oe + (int64_t)a.mismatch + 9 * a.gap_extend + std::max(0, -a.n_score) + 64);
+  const int64_t K = (ub + lb) / 2, fl = lb - K - 1000;
+  if (ub - K > 32000 || fl < -32700 || K > 32000 || K < -32000) return false;
+  *kshift = (int)K; *floor16 = (int)fl;
+  return true;
+}
+
 // Range proof for k_wave16_global: biased values X + (c + r) ext - K of every real H / E / F, for all pairs of the batch.
 //   upper: H <= match * min(q, t), bias <= (q8 + 64 + 8) ext        lower: H, E, F >= -(2 oe + ext * (t8 + 8) + mismatch + 64) (bias >= 0 cancels the query side)
 // The shift K centres the interval; the floor sits 1000 below the lower end and must itself fit.
@@ -844,6 +1071,10 @@ inline bool wave16_global_range(const DpArgs& a, uint32_t max_q, uint32_t max_t,
 
 bool wave16_eligible(const DpArgs& a, int algo, uint32_t max_q, uint32_t max_t) {
   if (algo == ALGO_GLOBAL) { int k, f; return wave16_global_range(a, max_q, max_t, &k, &f); }
+  if (algo == ALGO_SEMI_GLOBAL) {
+    int k, f;
+    return WAVE16_SEMI && a.tail == SKIP_TARGET && (a.head == SKIP_TARGET || a.head == SKIP_BOTH) && wave16_semi_range(a, max_q, max_t, &k, &f);
+  }
   if (algo != ALGO_LOCAL) return false;
   if ((uint64_t)std::min(max_q, max_t) * (uint64_t)a.match > 32000ull) return false;          // scores stay in 16 bits
   return a.gap_open + a.gap_extend + a.mismatch + std::max(0, -a.n_score) < 8000;
@@ -949,6 +1180,7 @@ int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uin
   wa.bnd = ws.bnd; wa.bnd_stride = qs; wa.cand = ws.cand; wa.done = ws.prog; wa.ticket = ws.prog + n;
   wa.kshift = 0; wa.floor16 = 0; wa.mm = 0x00204081u; wa.sixteen = 16;
   if (use_s16 && algo == ALGO_GLOBAL && !wave16_global_range(a, max_q, max_t, &wa.kshift, &wa.floor16)) return -1;   // cannot happen: checked by wave16_eligible
+  if (use_s16 && algo == ALGO_SEMI_GLOBAL && !wave16_semi_range(a, max_q, max_t, &wa.kshift, &wa.floor16)) return -1;
   const int ctas_per_sm = tbm ? 2 : (use_s16 ? WAVE16_MIN_CTAS : 4);
   // <= 16 (24) warp-workers per SM.  Once there is at least one CTA (= one warp per scheduler) for every SM, only whole multiples of
   // the SM count are started: a pipeline runs at the pace of its most crowded scheduler, so 1.7 workers per scheduler (two on
@@ -961,6 +1193,7 @@ int wave_launch(const DpArgs& a, int algo, int start, WaveScratch& ws, const uin
     cudaMemsetAsync(ws.prog, 0, prog_words * sizeof(uint32_t), str);
     wa.pass = pass; wa.tag_base = ws.next_tag; ws.next_tag += maxblk;
     if (use_s16 && algo == ALGO_GLOBAL) k_wave16_global<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
+    else if (use_s16 && algo == ALGO_SEMI_GLOBAL) k_wave16_semi<<<blocks, kWaveWarps * 32, 0, str>>>(wa);
     else if (use_s16 && tbm) k_wave16_local_t<true><<<blocks, kWaveWarps * 32, 0, str>>>(wa);
     else if (use_s16) k_wave16_local_t<false><<<blocks, kWaveWarps * 32, 0, str>>>(wa);
     else if (SR == 2) wave_launch_kernel<2>(algo, blocks, wa, str); else wave_launch_kernel<1>(algo, blocks, wa, str);

@@ -273,6 +273,19 @@ def nvb_jobs(n: int, m_lo: int, m_hi: int, n_lo: int, n_hi: int, seed: int = 1, 
     return np.concatenate(pats), poffs, np.concatenate(texts), toffs
 
 
+def long_read_windows(n: int, lo: int, hi: int, flank: int, seed: int = 5) -> PairBatch:
+    """n long reads (length uniform in [lo, hi), NW-benchmark style errors: 80 % copy / 10 % insert / 10 % delete) against their source
+    window extended by up to `flank` random bases on either side: the semi-global read-vs-window shape for long reads"""
+    rng = np.random.default_rng(seed)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+    qs, ts = [], []
+    for _ in range(n):
+        t, q = nw_style_pair(rng, int(rng.integers(lo, hi)))
+        qs.append(q)
+        ts.append(bytes(rng.choice(acgt, size=int(rng.integers(0, flank + 1)))) + t + bytes(rng.choice(acgt, size=int(rng.integers(0, flank + 1)))))
+    return batch_from_sequences(qs, ts)
+
+
 def nvb_banded_jobs(n: int, m_lo: int, m_hi: int, band: int, seed: int = 1, sub: float = 0.05, indel: float = 0.02, slack: int = 6):
     """n jobs for the banded aligners (row = pattern symbol, band entry j = text symbol i + j): text = pattern length + band - 1 + up to
     `slack` symbols (the reference's banded-traceback domain), pattern = the text from an offset inside the band, with substitutions and

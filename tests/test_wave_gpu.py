@@ -71,7 +71,7 @@ def test_wave_global_ragged(oracle, scoring):
 def test_wave_semiglobal_ragged(oracle, scoring, head):
     b = ragged(303 + head)
     want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, head=head, tail=po.TARGET, start=po.WITH_START, scoring=scoring, max_query_len=1024)
-    got = run(b, algo=capi.SEMI_GLOBAL, head=head, tail=capi.TARGET, start=capi.WITH_START, scoring=scoring)
+    got = run(b, policy=3, algo=capi.SEMI_GLOBAL, head=head, tail=capi.TARGET, start=capi.WITH_START, scoring=scoring)   # policy 3: int32 lanes
     assert got["_kernel"] == "wave"
     assert_same(got, want, K5, f"wave semi-global head={head} {scoring}")
 
@@ -139,6 +139,55 @@ def test_wave_long_semiglobal_with_start(oracle):
     got = run(b, policy=0, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)
     assert got["_kernel"] == "wave"
     assert_same(got, want, K5, "wave long semi-global")
+
+
+@pytest.mark.parametrize("head", [po.TARGET, po.BOTH])
+@pytest.mark.parametrize("scoring", SCORINGS + [(1, 4, 6, 0), (2, 3, 0, 2), (3, 5, 9, 7)])
+def test_wave16_semiglobal_ragged(oracle, scoring, head):
+    """policy 4: k_wave16_semi (s16x2 lanes, biased + shifted frame, free left column) on ragged short pairs: pairs shorter than one
+    strip / one lane / one row-block, N codes, zero and large extension costs, both HEAD variants, with and without the start pass"""
+    b = ragged(70 + scoring[0] + 7 * head)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, head=head, tail=po.TARGET, start=po.WITH_START, scoring=scoring, max_query_len=1024)
+    got = run(b, policy=4, algo=capi.SEMI_GLOBAL, head=head, tail=capi.TARGET, start=capi.WITH_START, scoring=scoring)
+    assert got["_kernel"] == "wave16"
+    assert_same(got, want, K5, f"wave16 semi-global head={head} {scoring}")
+    got = run(b, policy=4, algo=capi.SEMI_GLOBAL, head=head, tail=capi.TARGET, scoring=scoring)
+    assert got["_kernel"] == "wave16"
+    assert_same(got, want, K3, f"wave16 semi-global (no start) head={head} {scoring}")
+
+
+def test_wave16_semiglobal_long_and_automatic(oracle):
+    """long reads in flanked windows on the s16x2 lanes (forced), then enough of them that the launcher picks those lanes itself;
+    IUPAC codes take the compare path"""
+    rng = np.random.default_rng(44)
+    acgt = np.frombuffer(b"ACGT", dtype=np.uint8)
+
+    def make(n, lo, hi, flank):
+        qs, ts = [], []
+        for _ in range(n):
+            t, q = synth.nw_style_pair(rng, int(rng.integers(lo, hi)))
+            qs.append(q); ts.append(bytes(rng.choice(acgt, size=int(rng.integers(0, flank)))) + t + bytes(rng.choice(acgt, size=int(rng.integers(0, flank)))))
+        return synth.batch_from_sequences(qs, ts)
+
+    b = make(24, 800, 3000, 900)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, start=po.WITH_START, max_query_len=8192)
+    for policy, kernel in ((4, "wave16"), (3, "wave")):
+        got = run(b, policy=policy, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)
+        assert got["_kernel"] == kernel
+        assert_same(got, want, K5, f"{kernel} long semi-global")
+    b = make(700, 700, 1500, 500)                                          # >= 444 row-blocks of 512 rows: automatic choice
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, start=po.WITH_START, max_query_len=8192)
+    got = run(b, policy=0, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)
+    assert got["_kernel"] == "wave16"
+    assert_same(got, want, K5, "wave16 semi-global, launcher's own choice")
+    alpha = np.frombuffer(b"ACGTACGTACGTNRYK", dtype=np.uint8)
+    qs = [bytes(alpha[rng.integers(0, alpha.size, size=int(rng.integers(20, 400)))]) for _ in range(200)]
+    ts = [bytes(alpha[rng.integers(0, alpha.size, size=int(rng.integers(20, 600)))]) for _ in range(200)]
+    b = synth.batch_from_sequences(qs, ts)
+    want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, start=po.WITH_START, max_query_len=1024)
+    got = run(b, policy=4, algo=capi.SEMI_GLOBAL, start=capi.WITH_START)
+    assert got["_kernel"] == "wave16"
+    assert_same(got, want, K5, "wave16 semi-global, IUPAC codes")
 
 
 def test_wave_matches_general_kernel_on_mixed_lengths(oracle):
