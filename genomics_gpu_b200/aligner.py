@@ -182,10 +182,11 @@ def plan_batches(q_lens: np.ndarray, t_lens: np.ndarray, *, n_gpus: int = 1, max
 
 def align_all(batch: PairBatch, *, algo: int, start: int = capi.WITHOUT_START, second_best: bool = False, head: int = capi.TARGET,
               tail: int = capi.TARGET, k_band: int = 0, scoring: Sequence[int] = (1, 4, 6, 1), n_gpus: int = 1, gpu_ids: Optional[Sequence[int]] = None,
-              streams_per_gpu: int = 2, max_batch_pairs: int = 262144, max_batch_cells: int = 1 << 36, q_op=None, t_op=None,
-              keep_input_order: bool = False, host_threads_per_gpu: int = 0) -> Dict[str, np.ndarray]:
+              streams_per_gpu: int = 0, max_batch_pairs: int = 0, max_batch_cells: int = 1 << 36, q_op=None, t_op=None,
+              keep_input_order: bool = False, host_threads_per_gpu: int = 0, out: Optional[Dict[str, np.ndarray]] = None) -> Dict[str, np.ndarray]:
     """The whole job through the library-side batcher (gasalx_align_all): length binning, LPT sharding over the GPUs of this
-    process, pinned streaming on per-storage streams, host-side gather in the caller's order."""
+    process, pinned streaming on per-storage streams, host-side gather in the caller's order.  `out`: the dict of a previous call
+    on a job of the same size, to write the results into the same (already touched) arrays."""
     lib = capi.load()
     params = capi.Params(); lib.gasal_params_default(C.byref(params))
     params.algo = algo; params.start_pos = start; params.secondBest = int(bool(second_best))
@@ -199,10 +200,11 @@ def align_all(batch: PairBatch, *, algo: int, start: int = capi.WITHOUT_START, s
     if gpu_ids is not None:
         ids = (C.c_int32 * n_gpus)(*gpu_ids); sched.gpu_ids = ids
     n = batch.n
-    out = {k: np.zeros(n, dtype=np.int32) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start",
-                                                    "aln_score2", "query_batch_end2", "target_batch_end2")}
-    out["n_cigar_ops"] = np.zeros(n, dtype=np.uint32)
-    out["cigar"] = np.zeros(batch.q_bytes.size if start == capi.WITH_TB else 8, dtype=np.uint8)
+    if out is None or len(out.get("aln_score", ())) != n:
+        out = {k: np.zeros(n, dtype=np.int32) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start", "target_batch_start",
+                                                        "aln_score2", "query_batch_end2", "target_batch_end2")}
+        out["n_cigar_ops"] = np.zeros(n, dtype=np.uint32)
+        out["cigar"] = np.zeros(batch.q_bytes.size if start == capi.WITH_TB else 8, dtype=np.uint8)
     res = capi.Results(*[out[k].ctypes.data_as(C.POINTER(C.c_int32)) for k in ("aln_score", "query_batch_end", "target_batch_end", "query_batch_start",
                                                                                 "target_batch_start", "aln_score2", "query_batch_end2", "target_batch_end2")],
                        out["cigar"].ctypes.data_as(C.POINTER(C.c_uint8)), out["n_cigar_ops"].ctypes.data_as(C.POINTER(C.c_uint32)))

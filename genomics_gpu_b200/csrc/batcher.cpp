@@ -36,8 +36,28 @@ struct Plan {
 
 inline uint32_t pad8(uint32_t x) { return (x + 7u) & ~7u; }
 
+// Defaults chosen from measurements (1 M pairs of 150 x 600 on one B200, 16 host cores, tools/bench_batcher_sweep.py): staging a batch
+// into the pinned pages (read ASCII, pack, write) is host-memory work of ~10 GB/s per thread, a 131072-pair batch takes ~10 ms
+// to stage and 3 ms to align, so throughput comes from MANY small batches in flight on many storages, filled by several threads:
+// 4 storages x 4 threads x 131072 pairs: 47.8 ms; 16 storages x 8 threads x 32768 pairs: 30.4 ms (the kernels alone: 19.3 ms).
+inline int auto_streams(const gasalx_sched_t* sc) { return sc->streams_per_gpu > 0 ? sc->streams_per_gpu : 16; }
+inline int auto_threads(const gasalx_sched_t* sc, int ns) {
+  int t = sc->host_threads_per_gpu;
+  if (t <= 0) {
+    const int hw = (int)std::thread::hardware_concurrency(), g = sc->n_gpus > 0 ? sc->n_gpus : 1;
+    t = std::max(2, (hw > 0 ? hw : 8) / (2 * g));
+    t = std::min(t, 8);
+  }
+  return std::max(1, std::min(t, ns));
+}
+inline uint32_t auto_batch_pairs(const gasalx_sched_t* sc, uint64_t n) {
+  if (sc->max_batch_pairs) return sc->max_batch_pairs;
+  const uint64_t g = sc->n_gpus > 0 ? sc->n_gpus : 1, per = (n + g * 2 * auto_streams(sc) - 1) / (g * 2 * auto_streams(sc));   // two rounds per storage
+  return (uint32_t)std::min<uint64_t>(262144, std::max<uint64_t>(16384, (per + 4095) & ~4095ull));
+}
+
 void make_plan(const uint32_t* q_lens, const uint32_t* t_lens, uint64_t n, const gasalx_sched_t* sc, Plan& pl) {
-  const uint32_t max_pairs = sc->max_batch_pairs ? sc->max_batch_pairs : 262144u;
+  const uint32_t max_pairs = auto_batch_pairs(sc, n);
   const uint64_t max_bytes = sc->max_batch_bytes ? sc->max_batch_bytes : (1ull << 30);
   const uint64_t max_cells = sc->max_batch_cells ? sc->max_batch_cells : (1ull << 36);
   const int n_gpus = sc->n_gpus > 0 ? sc->n_gpus : 1;
@@ -122,7 +142,7 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
   if (mine.empty()) return;
   // process big batches first so the tail is short
   std::stable_sort(mine.begin(), mine.end(), [&](uint32_t a, uint32_t b) { return pl.batch_cells[a] > pl.batch_cells[b]; });
-  const int ns = sc->streams_per_gpu > 0 ? sc->streams_per_gpu : 2;
+  const int ns = std::max(1, std::min<int>(auto_streams(sc), (int)mine.size()));      // never more storages than batches
   // size the pages for the largest batch in BYTES (ragged batches are much smaller than max_pairs x max_len)
   uint64_t maxqb = 0, maxtb = 0;
   for (uint32_t b : mine) { maxqb = std::max(maxqb, pl.batch_q_bytes[b]); maxtb = std::max(maxtb, pl.batch_t_bytes[b]); }
@@ -155,8 +175,7 @@ void worker(int gpu_slot, int device, const Plan& pl, const Job& job, const gasa
   // Staging (one bulk copy per run of neighbouring pairs into the pinned pages) and the scatter of the results are host
   // memory traffic: one thread per GPU moves ~11 GB/s, less than a B200 consumes on short reads.  The storages of a GPU are
   // therefore split over `nthreads` host threads; each owns its storages (and their streams) and pulls batches from one queue.
-  int nthreads = sc->host_threads_per_gpu > 0 ? sc->host_threads_per_gpu : std::min(ns, 4);
-  nthreads = std::max(1, std::min(nthreads, ns));
+  const int nthreads = auto_threads(sc, ns);
   std::atomic<size_t> next(0), done(0);
   std::mutex ms_mu;
   double ms_total = 0;
@@ -265,7 +284,7 @@ extern "C" {
 
 void gasalx_sched_default(gasalx_sched_t* s) {
   memset(s, 0, sizeof(*s));
-  s->n_gpus = 1; s->streams_per_gpu = 2; s->max_batch_pairs = 262144; s->max_batch_bytes = 1ull << 30; s->max_batch_cells = 1ull << 36;
+  s->n_gpus = 1; s->streams_per_gpu = 0; s->max_batch_pairs = 0; s->max_batch_bytes = 1ull << 30; s->max_batch_cells = 1ull << 36;   // 0 = automatic
   s->host_threads_per_gpu = 0;
 }
 

@@ -282,12 +282,12 @@ void gasalx_host_batch_rearm(gasal_gpu_storage_t* gpu_storage, uint32_t q_bytes,
 typedef struct {
   int32_t n_gpus;                /* GPUs of this process to use (>= 1) */
   const int32_t* gpu_ids;        /* NULL: 0 .. n_gpus-1 */
-  int32_t streams_per_gpu;       /* storages (streams) per GPU, default 2 (reference NB_STREAMS, test_prog.cpp:12) */
-  uint32_t max_batch_pairs;      /* default 262144 (the reference's commented GPU-filling STREAM_BATCH_SIZE, test_prog.cpp:14) */
+  int32_t streams_per_gpu;       /* storages (streams) per GPU; 0 = automatic: 16, never more than the GPU has batches (the reference's NB_STREAMS is 2, test_prog.cpp:12) */
+  uint32_t max_batch_pairs;      /* 0 = automatic: two rounds of batches per storage, 16384 .. 262144 pairs (262144 = the reference's commented GPU-filling STREAM_BATCH_SIZE, test_prog.cpp:14) */
   uint64_t max_batch_bytes;      /* per sequence side, default 1 GiB (must stay < 4 GiB: 32-bit offsets of the GASAL2 API) */
   uint64_t max_batch_cells;      /* default 2^36 DP cells */
   int32_t keep_input_order;      /* 1: no length binning (batches follow input order, like test_prog) */
-  int32_t host_threads_per_gpu;  /* host threads that stage batches / gather results per GPU; 0 = auto (min(streams_per_gpu, 4)) */
+  int32_t host_threads_per_gpu;  /* host threads that stage batches / gather results per GPU; 0 = automatic: half the cores divided by the GPUs, 2 .. 8 */
 } gasalx_sched_t;
 
 typedef struct {                 /* any pointer may be NULL; arrays have one entry per pair of the job */
