@@ -22,6 +22,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <limits.h>
 #include <algorithm>
 #include <string>
@@ -780,6 +781,12 @@ static int ensure_dirs(nvbx_stream_t* s, size_t words) {
   return 0;
 }
 static bool band_ok(int b) { return b == 3 || b == 5 || b == 7 || b == 15 || b == 31; }
+// jobs per traceback launch: as many as the flow-word budget holds, in warps of 32 slots, never more than the batch has (long
+// strings: a handful of jobs must not reserve 128 slots of half a gigabyte each)
+static size_t tb_chunk(size_t budget_words, size_t per_job, size_t n_pairs) {
+  size_t chunk = std::max<size_t>(32, (budget_words / std::max<size_t>(1, per_job)) & ~(size_t)31);
+  return std::min<size_t>(chunk, (n_pairs + 31) & ~(size_t)31);
+}
 
 template <int B, bool DIRS>
 static void launch_banded(int type, uint32_t g, cudaStream_t st, const NvbArgs& a, const TbArgs& tb, int want_sinks) {
@@ -822,13 +829,13 @@ int nvbx_stream_traceback(nvbx_stream_t* s, const nvbx_aligner_t* al, int band_l
   if (band_len != 0 && !band_ok(band_len)) return fail("nvbx_stream_traceback: band_len must be 0 (full matrix), 3, 5, 7, 15 or 31");
   if (ensure_tb_outputs(s) != 0) return -1;
   tb.src_i = s->src_i; tb.src_j = s->src_j; tb.n_ops = s->n_ops; tb.ops = s->ops; tb.ops_stride = s->ops_stride;
-  const size_t budget_words = (size_t)3 << 29;                                             // <= 6 GB of flow words per chunk
+  size_t budget_words = (size_t)3 << 29;                                                   // <= 6 GB of flow words per chunk
+  if (const char* e = getenv("NVBX_TB_BUDGET_WORDS")) budget_words = std::max<size_t>(1, (size_t)strtoull(e, nullptr, 10));   // tests: force several chunks
   NVB_CHECK(cudaEventRecord(s->e0, s->st));
   if (band_len) {
     banded_costs(al, a, tb);
     const size_t per_job = (size_t)s->max_m * ((band_len + 7) / 8);
-    size_t chunk = std::max<size_t>(kThreads, (budget_words / std::max<size_t>(1, per_job)) & ~(size_t)(kThreads - 1));
-    chunk = std::min<size_t>(chunk, ((size_t)s->n_pairs + kThreads - 1) & ~(size_t)(kThreads - 1));
+    size_t chunk = tb_chunk(budget_words, per_job, s->n_pairs);
     if (ensure_dirs(s, per_job * chunk) != 0) return -1;
     tb.dirs = s->dirs; tb.slots = chunk; tb.rows_cap = s->max_m;
     for (size_t first = 0; first < s->n_pairs; first += chunk) {
@@ -848,10 +855,9 @@ int nvbx_stream_traceback(nvbx_stream_t* s, const nvbx_aligner_t* al, int band_l
     s->kernel = "banded-int32+tb";
   } else {
     const size_t nbands = (s->max_m + 7) / 8, per_job = nbands * s->max_n;
-    size_t chunk = std::max<size_t>(kThreads, (budget_words / std::max<size_t>(1, per_job)) & ~(size_t)(kThreads - 1));
-    chunk = std::min<size_t>(chunk, ((size_t)s->n_pairs + kThreads - 1) & ~(size_t)(kThreads - 1));
+    size_t chunk = tb_chunk(budget_words, per_job, s->n_pairs);
     if (ensure_dirs(s, per_job * chunk) != 0) return -1;
-    const size_t need = chunk * s->max_n;                                                  // band-border scratch, [CTA][text row][thread]
+    const size_t need = ((chunk + kThreads - 1) / kThreads) * kThreads * s->max_n;         // band-border scratch, [CTA][text row][thread]
     if (need > s->scratch_elems) {
       if (s->scratch) cudaFree(s->scratch);
       s->scratch = nullptr; s->scratch_elems = 0;

@@ -148,9 +148,29 @@ def test_banded_short_texts_indexed_pairs_and_ascii(orc):
         assert np.array_equal(rows, wr) and np.array_equal(flat, wf)
 
 
-def test_traceback_in_chunks_and_error_paths(orc):
-    """more jobs than one flow-matrix chunk would hold is not testable cheaply; instead: a second traceback on the same stream (buffers
-    reused), alignments() before any traceback, unknown band lengths"""
+def test_traceback_in_several_chunks(orc, monkeypatch):
+    """a flow-word budget that holds only a few dozen jobs (NVBX_TB_BUDGET_WORDS): the chunk loop, partial last chunk, long strings"""
+    pats, poffs, texts, toffs = synth.nvb_jobs(333, 40, 300, 200, 900, seed=81)
+    jobs = jobs_of(pats, poffs, texts, toffs)
+    monkeypatch.setenv("NVBX_TB_BUDGET_WORDS", str(38 * 900 * 64))            # ~64 jobs of the largest shape per chunk
+    with nvb.Stream(nvb.Batch(pats, poffs, texts, toffs)) as st:
+        for type_ in TYPES:
+            st.traceback(nvb.aligner(nvb.GOTOH, type_, 2, -1, -2, -1))
+            rows, flat = rows_and_ops(*st.alignments())
+            wr, wf = want_rows([orc.traceback(po.NVB_GOTOH, type_, (2, -1, -2, -1), p, t) for p, t in jobs])
+            assert np.array_equal(rows, wr) and np.array_equal(flat, wf), type_
+    pats, poffs, texts, toffs = synth.nvb_banded_jobs(333, 40, 300, 31, seed=82)
+    jobs = jobs_of(pats, poffs, texts, toffs)
+    monkeypatch.setenv("NVBX_TB_BUDGET_WORDS", str(300 * 4 * 40))
+    with nvb.Stream(nvb.Batch(pats, poffs, texts, toffs)) as st:
+        st.traceback(nvb.aligner(nvb.GOTOH, nvb.LOCAL, 2, -1, -2, -1), 31)
+        rows, flat = rows_and_ops(*st.alignments())
+        wr, wf = want_rows([orc.traceback(po.NVB_GOTOH, po.NVB_LOCAL, (2, -1, -2, -1), p, t, band=31) for p, t in jobs])
+        assert np.array_equal(rows, wr) and np.array_equal(flat, wf)
+
+
+def test_traceback_reuse_and_error_paths(orc):
+    """a second traceback on the same stream (buffers reused), alignments() before any traceback, unknown band lengths"""
     pats, poffs, texts, toffs = synth.nvb_jobs(300, 10, 60, 20, 90, seed=4)
     with nvb.Stream(nvb.Batch(pats, poffs, texts, toffs)) as st:
         with pytest.raises(RuntimeError, match="no traceback"):
