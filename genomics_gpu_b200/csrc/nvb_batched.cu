@@ -765,11 +765,16 @@ static void banded_costs(const nvbx_aligner_t* al, const NvbArgs& a, TbArgs& tb)
   else { tb.f_o = tb.f_e = tb.init_o = tb.init_e = a.go_t; tb.e_o = tb.e_e = a.go_p; tb.no_sink = 1; }
 }
 static int ensure_tb_outputs(nvbx_stream_t* s) {
-  if (s->src_i) return 0;
+  if (s->ops) return 0;                                               // all four exist, or none
   s->ops_stride = ((s->max_m + s->max_n + 64u) + 3u) & ~3u;
-  NVB_CHECK(cudaMalloc(&s->src_i, 4 * (size_t)s->n_pairs)); NVB_CHECK(cudaMalloc(&s->src_j, 4 * (size_t)s->n_pairs));
-  NVB_CHECK(cudaMalloc(&s->n_ops, 4 * (size_t)s->n_pairs));
-  if (cudaMalloc(&s->ops, (size_t)s->n_pairs * s->ops_stride) != cudaSuccess) { cudaGetLastError(); return fail("nvbx traceback: cannot allocate the edit-op buffer"); }
+  const bool ok = cudaMalloc(&s->src_i, 4 * (size_t)s->n_pairs) == cudaSuccess && cudaMalloc(&s->src_j, 4 * (size_t)s->n_pairs) == cudaSuccess &&
+                  cudaMalloc(&s->n_ops, 4 * (size_t)s->n_pairs) == cudaSuccess && cudaMalloc(&s->ops, (size_t)s->n_pairs * s->ops_stride) == cudaSuccess;
+  if (!ok) {
+    cudaGetLastError();
+    cudaFree(s->src_i); cudaFree(s->src_j); cudaFree(s->n_ops); cudaFree(s->ops);
+    s->src_i = s->src_j = nullptr; s->n_ops = nullptr; s->ops = nullptr;
+    return fail("nvbx traceback: cannot allocate the alignment / edit-op buffers");
+  }
   return 0;
 }
 static int ensure_dirs(nvbx_stream_t* s, size_t words) {
