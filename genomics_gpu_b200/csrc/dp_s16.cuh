@@ -83,6 +83,9 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 #define GB200_UNROLL_(n) GB200_PRAGMA_(unroll n)
 #define GB200_TBB_UNROLL_PRAGMA GB200_UNROLL_(GB200_TBB_UNROLL)
 #define GB200_TB_UNROLL_PRAGMA GB200_UNROLL_(GB200_TB_UNROLL)
+#ifndef GB200_PRUNE_REVERSE_LOW
+#define GB200_PRUNE_REVERSE_LOW 1
+#endif
 #ifndef GB200_PRUNE_RISKY_LANES
 #define GB200_PRUNE_RISKY_LANES 4
 #endif
@@ -921,17 +924,34 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
       if (G4) { lanebest_init_g4(rb.a); lanebest_init_g4(rb.b); } else { lanebest_init(rb.a); lanebest_init(rb.b); }
       const int RD = (gend_reg + 3) >> 2;
       const int fwd7 = G4 ? ((fw.score << 5) | 31) : ((fw.score << 3) | 7);
-      // Score-bound pruning of the reversed rectangle (exact): a path through the cell (row i, column c) with c > i has at most
-      // i + 1 diagonal steps up to that cell and at most rcol - 1 - c after it, so it scores <= match * (rcol - (c - i)); no path
-      // that reaches the forward score enters the columns c > i + slack, slack = rcol - ceil(score / match).  Quad-strip j (rows
-      // < 32 (j + 1)) therefore stops after column 32 (j + 1) + slack: the cells beyond keep the initial state (0, a lower bound
-      // that the 0 clamp makes harmless), every cell on a path that reaches the forward score is still computed from exact
-      // inputs, and no cell exceeds its true value -- the first cell that reaches the score, in the reference's order, is the same.
-      // (slack is made warp-uniform, the maximum over the converged lanes: conservative for each of them, see the note on gfree)
-      const int slack = GB200_PRUNE_REVERSE && mstep > 0
-                            ? (int)__reduce_max_sync(__activemask(), (unsigned)(rcol - (fw.score + mstep - 1) / mstep)) : rcol;
+      // Score-bound pruning of the reversed rectangle (exact).  A cell of this pass whose H reaches the forward score S is the start
+      // of an optimal alignment that ENDS, in forward coordinates, on a cell with H = S inside the rectangle; the forward pass
+      // recorded the FIRST such cell of the reference's (strip, column, row) order, so any other lies in the same strip at a column
+      // >= the recorded one -- in this pass: every score-S path STARTS in the corner tile (row < 8, column < 8).  A path from
+      // there through the cell (row i, column c):
+      //   c - i = d > 0: at least d - 7 of its columns sit in horizontal gaps, which also cost it as many diagonal steps:
+      //                  S <= m (rcol - (d - 7)) - open - (d - 7) ext        ->  d <= 7 + (m rcol - S - open) / (m + ext)
+      //                  (and, whatever the gap costs, S <= m (rcol - d)     ->  d <= rcol - ceil(S / m))
+      //   i - c = d > 0: at least d - 7 of its rows sit in vertical gaps:    S <= m rcol - open - (d - 7) ext  ->  d <= 7 + (m rcol - S - open) / ext
+      // (m = the best substitution score; 7 alone when not even one gap is affordable).  Quad-strip j (rows 32 j .. 32 j + 31)
+      // therefore only sweeps the columns [32 j - slackL, 32 (j + 1) + slackU): the cells outside read as the initial state (0, a
+      // lower bound that the 0 clamp makes harmless), every cell on a path that reaches S keeps exact inputs and no cell exceeds
+      // its true value, so the first cell that reaches S in the reference's order is the same.  For a 150 bp read with S = 130 the
+      // five quad-strips sweep 47 + 70 + 70 + 70 + 47 columns instead of 5 x 152.
+      // (both slacks are made warp-uniform, the maximum over the converged lanes: conservative for each of them, see the note on gfree)
+      constexpr int kNoBound = 1 << 24;                               // more rows than any target has
+      int slackU = kNoBound, slackL = kNoBound;
+      if (GB200_PRUNE_REVERSE && mstep > 0) {
+        const int num = mstep * rcol - fw.score - a.gap_open;
+        const int up = min(rcol - (fw.score + mstep - 1) / mstep, 7 + (num >= 0 ? num / (mstep + a.gap_extend) : 0));
+        const int lo = num < 0 ? 7 : (a.gap_extend > 0 ? 7 + num / a.gap_extend : kNoBound);     // free extension: a vertical gap of any length
+        slackU = (int)__reduce_max_sync(__activemask(), (unsigned)max(up, 0));
+        slackL = (int)__reduce_max_sync(__activemask(), (unsigned)min(lo, kNoBound));
+      }
+      const int gfree_abs = GB200_PRUNE_ARGMAX && mstep > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)(((fw.score - 1) / mstep) >> 2)) : 0;
       for (int j = 0; j < RD; j++) {
-        const int lim = min(rcol, (32 * (j + 1) + slack + 3) & ~3);
+        const int c_lo = GB200_PRUNE_REVERSE_LOW ? min(max(32 * j - slackL, 0) & ~3, max(rcol - 4, 0)) : 0;
+        const int lim = (int)min((long long)rcol, ((long long)32 * (j + 1) + slackU + 3) & ~3ll);     // > c_lo: rcol is a multiple of 8
         uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
         const uint32_t wa = nibrev(tw[gend_reg - 1 - 4 * j]);
         const uint32_t wb = (4 * j + 1 < gend_reg) ? nibrev(tw[gend_reg - 2 - 4 * j]) : 0u;
@@ -939,10 +959,12 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
         const uint32_t wd = (4 * j + 3 < gend_reg) ? nibrev(tw[gend_reg - 4 - 4 * j]) : 0u;
         quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
         // (only cells that reach the forward score matter here: columns q with match * (q + 1) < fwd score need no arg-max)
-        if (G4) local_sweep4g<NMASK>(HE, V, (lim >> 2) + (int)fa.one,
-                                     GB200_PRUNE_ARGMAX && mstep > 0 ? (int)__reduce_min_sync(__activemask(), (unsigned)(((fw.score - 1) / mstep) >> 2)) : 0,
-                                     rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, rb, nsc2);
-        else local_sweep4<NMASK>(HE, V, lim + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, rb, nsc2);
+        uint32_t* HEw = HE + (size_t)c_lo * kFastThreads;          // the sweep's column 0 is column c_lo: its zero start state IS the "reads as 0" left of the window
+        const uint8_t* Vw = V + (size_t)c_lo * kFastThreads;
+        if (G4) local_sweep4g<NMASK>(HEw, Vw, ((lim - c_lo) >> 2) + (int)fa.one, max(gfree_abs - (c_lo >> 2), 0),
+                                     rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, ((uint32_t)j << 16) + (uint32_t)(c_lo >> 2), rb, nsc2);
+        else local_sweep4<NMASK>(HEw, Vw, (lim - c_lo) + 2 + (int)fa.one, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one,
+                                 ((uint32_t)j << 16) + (uint32_t)c_lo, rb, nsc2);
         if ((int)(short)(rb.a.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.a.bestK7 >> 16) >= fwd7 ||
             (int)(short)(rb.b.bestK7 & 0xFFFFu) >= fwd7 || (int)(short)(rb.b.bestK7 >> 16) >= fwd7) break;
       }
