@@ -1171,7 +1171,7 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
                                         const uint32_t (&rowA)[8], const uint32_t (&rowB)[8], const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
                                         const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8], const uint32_t (&hpinit)[8],
                                         uint32_t neg_oe2, uint32_t neg2, uint32_t conv8, int bias_ext, uint32_t nsc2,
-                                        int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr) {
+                                        int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, int col0 = 0) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
   const uint32_t selA = st.v | st.prevsh;
   st.prevsh = st.v * 256u + 0x4400u;
@@ -1251,7 +1251,7 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
 #pragma unroll
       for (int r = 0; r < 8; r++) {
         const uint32_t w = (li & 2) ? hhB[r] : hhA[r];
-        hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (kq + r) * bias_ext;     // back to the unbiased score (this lane is on column kq)
+        hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (col0 + kq + r) * bias_ext;     // back to the unbiased score (this lane is on column col0 + kq)
       }
       if (SEMI) {
         // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178); the start
@@ -1280,7 +1280,11 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
                                           const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
                                           const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8],
                                           uint32_t neg_oe2, uint32_t neg_ext2,
-                                          int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, uint32_t nsc2 = 0) {
+                                          int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, uint32_t nsc2 = 0,
+                                          int col0 = 0, bool closed_left = false) {
+  // col0 / closed_left (pruned start pass): HE / V point at column col0 of the matrix (kq is relative to it; the frame of the parked
+  // values is absolute, so only the un-biasing of the scanned column needs col0), and what lies left of it reads as -infinity
+  // instead of the free left column.
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
   const uint32_t neg2 = splat16(kNegSafe);
   // Both recurrences run in a BIASED frame: every H/E/F of (strip row r, column q) carries + (q + r) * ext.  Gap extension is
@@ -1291,18 +1295,21 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
   // (r - 1) ext; the diagonal inputs (pinit) carry (r - 2) ext.  The -infinity floors stay unbiased: they only ever lose a max.
   const int bias_ext = -lane_lo(neg_ext2);
   const uint32_t conv8 = splat16(-8 * bias_ext);
-  uint32_t hpinit[8];
+  uint32_t hpinit[8], pA0[8], pB0[8];
 #pragma unroll
-  for (int r = 0; r < 8; r++) hpinit[r] = SEMI ? splat16((r - 1) * bias_ext) : neg_oe2;
+  for (int r = 0; r < 8; r++) {
+    hpinit[r] = closed_left ? neg2 : (SEMI ? splat16((r - 1) * bias_ext) : neg_oe2);
+    pA0[r] = closed_left ? neg2 : pinitA[r]; pB0[r] = closed_left ? neg2 : pinitB[r];
+  }
   NcState st;
 #pragma unroll
-  for (int r = 0; r < 8; r++) { st.pA[r] = pinitA[r]; st.fA[r] = neg2; st.glA[r] = hpinit[r]; st.pB[r] = pinitB[r]; st.fB[r] = neg2; st.glB[r] = hpinit[r]; }
+  for (int r = 0; r < 8; r++) { st.pA[r] = pA0[r]; st.fA[r] = neg2; st.glA[r] = hpinit[r]; st.pB[r] = pB0[r]; st.fB[r] = neg2; st.glB[r] = hpinit[r]; }
   st.h8A = 0; st.eoA = 0; st.h8B = 0; st.eoB = 0;
   st.prevsh = 0xCC00u; st.selB = 0xCCCCu; st.selA_prev = 0xCCCCu;
   st.he = HE[kFastThreads]; st.v = V[kFastThreads];
   st.ncm_prev = 0; st.mB = 0; st.mA_prev = 0;
-#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pinitA, pinitB, hpinit, neg_oe2, neg2, conv8, bias_ext, nsc2, \
-                                                           kq, rowbase, tlen, caplane, caprow, tr)
+#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pA0, pB0, hpinit, neg_oe2, neg2, conv8, bias_ext, nsc2, \
+                                                           kq, rowbase, tlen, caplane, caprow, tr, col0)
 #if GB200_NC_SPLIT
   // segments: rare [0, r0e) -- hot [r0e, h0e) -- rare [h0e, r1e) -- hot [r1e, nsteps)
   const int r0e = min(3, nsteps);
@@ -1436,14 +1443,28 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
       const bool risky = (tr.y + 1 - (int)qlen) <= maxdel;
       if (__popc(__ballot_sync(__activemask(), risky)) >= GB200_PRUNE_RISKY_LANES) slack = ncol;
     }
+    // The other side of the band.  A path of this pass that reaches the forward score is the mirror of a forward alignment that ends
+    // on a row t' with H(t', qlen - 1) = score; the forward scan recorded the FIRST such row (strict '>' top-down) and this pass starts
+    // at most one strip before the strip that holds it, so such a path leaves the left boundary within the first 16 rows of the pass
+    // (or comes off the top boundary, which is tighter still).  Through the cell (row i, column c) with i - c = d > 0 it has spent at
+    // least d - 15 rows in vertical gaps: score <= m qlen - open - (d - 15) ext  ->  d <= 15 + (m qlen - score - open) / ext (15 when
+    // not even one gap is affordable; no bound when extension is free).  Quad-strip k sweeps the columns [32 k - slackL, 32 (k + 1) +
+    // slack); what lies left of the window reads as -infinity (nc_sweep4 closed_left), not as the free left column.
+    int slackL = 1 << 24;
+    if (GB200_PRUNE_REVERSE && GB200_PRUNE_REVERSE_LOW && slack < ncol) {
+      const int numL = mstep * (int)qlen - fwd - a.gap_open;
+      const int lo = numL < 0 ? 15 : (a.gap_extend > 0 ? 15 + numL / a.gap_extend : (1 << 24));
+      slackL = (int)__reduce_max_sync(__activemask(), (unsigned)lo);
+    }
+    const int c_max = (int)((qlen - 1) & ~3u);                                          // the scanned column stays inside every window
     NcTrack rt;
     for (int attempt = 0; attempt < 2; attempt++) {
       const int lim0 = min(ncol, (32 + slack + 3) & ~3);
       if (top_zero) nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval);
       else nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval, lim0 < ncol ? lim0 : 0x7FFFFFFF);
       rt.best = kMinusInf; rt.y = 0; rt.stop = fwd; rt.cap = 0;                         // :275-276
-      int lim = lim0;
-      for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 4) {
+      int lim = lim0, row_lo = 0;
+      for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 4, row_lo += 32) {
         uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
         const uint32_t wa = rev_true_word(tw, (int)tlen, (int)i);
         const uint32_t wb = (i + 1 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 1) : 0u;
@@ -1452,8 +1473,10 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
         quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
         // a truncated sweep computes the columns < lim in all four lanes; if it stops on the scanned column (qlen - 1 >= lim) the lanes
         // that get there only see values below the forward score, which never decide the result
-        const int ns = (lim < ncol) ? lim + 2 + (int)fa.one : nsteps;
-        nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE, V, ns, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2);
+        const int c_lo = (slack < ncol) ? min(max(row_lo - slackL, 0) & ~3, c_max) : 0;
+        const int ns = ((lim < ncol) ? lim + 2 + (int)fa.one : nsteps) - c_lo;
+        nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE + (size_t)c_lo * kFastThreads, V + (size_t)c_lo * kFastThreads, ns, rowA, rowB, rowC, rowD, pinit, pinit,
+                                                 neg_oe2, neg_ext2, (int)qlen - 1 - c_lo, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2, c_lo, c_lo > 0);
         lim = min(ncol, lim + 32);
       }
       if (rt.best >= fwd || slack >= ncol) break;
