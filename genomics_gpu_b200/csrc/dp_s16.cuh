@@ -83,6 +83,10 @@ struct LaneBest { uint32_t bestK7, keyL, keyH, posL, posH; };
 #define GB200_UNROLL_(n) GB200_PRAGMA_(unroll n)
 #define GB200_TBB_UNROLL_PRAGMA GB200_UNROLL_(GB200_TBB_UNROLL)
 #define GB200_TB_UNROLL_PRAGMA GB200_UNROLL_(GB200_TB_UNROLL)
+#ifndef GB200_BSC_UNROLL
+#define GB200_BSC_UNROLL 2          // step loop of the score-only banded sweep
+#endif
+#define GB200_BSC_UNROLL_PRAGMA GB200_UNROLL_(GB200_BSC_UNROLL)
 #ifndef GB200_PRUNE_REVERSE_LOW
 #define GB200_PRUNE_REVERSE_LOW 1
 #endif
@@ -708,6 +712,116 @@ GB200_TBB_UNROLL_PRAGMA
   }
 }
 
+// ---- score-only BANDED (banded.h:10-139) on the same window machinery: local-type with the zero clamp, but H-BASED gap opening
+// (F from H of the previous column, E from H of the row above: banded.h:99-114), so it is not the LOCAL recurrence of the traceback
+// sweep above.  Chain formulation per cell pair: PRMT (substitution), VIADDMNMX (F), VIADDMNMX (E), VIMNMX3.RELU (H) on the ALU pipe;
+// D = diag + s, H - oe (feeds the next row's E and the next column's F) and the arg-max key on the FMA pipe.  The parked / handed-on
+// E is the row's OWN E (the next row advances it), and (0, 0) for whatever lies outside a strip's band: every H is clamped at 0, so
+// F / E values <= 0 are interchangeable and the cleared start state (F = 0, H - oe = 0) of a lane that enters its window is exact.
+template <bool NMASK = false>
+__device__ __forceinline__ void banded_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, const BandWin& bw,
+                                              const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                              const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                              uint32_t neg_oe2, uint32_t neg_ext2, uint32_t eight, uint32_t one, uint32_t pos_base,
+                                              LaneBest4& lb, uint32_t nsc2 = 0) {
+  uint32_t ncm_prev = 0, mB = 0, mA_prev = 0;
+  uint32_t pA[8], fA[8], glA[8], pB[8], fB[8], glB[8], keyA[8], keyB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { pA[r] = 0; fA[r] = 0; glA[r] = 0; pB[r] = 0; fB[r] = 0; glB[r] = 0; keyA[r] = 0; keyB[r] = 0; }
+  uint32_t h8A = 0, eoA = 0, h8B = 0, eoB = 0;
+  uint32_t prevsh = 0xCC00u;
+  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;
+  uint32_t he = HE[kFastThreads];
+  uint32_t v = V[kFastThreads];
+  uint32_t pos = pos_base;
+  int nsteps = 0;
+#pragma unroll
+  for (int i = 0; i < 4; i++) nsteps = max(nsteps, bw.exitk[i]);
+  uint32_t inA = 0, inB = 0, inA_prev = 0, inB_prev = 0;
+  int k = 0;
+  while (k < nsteps) {
+    int next = nsteps;
+    uint32_t keepA = 0xFFFFFFFFu, keepB = 0xFFFFFFFFu;
+    inA = 0; inB = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      if (bw.enter[i] > k) next = min(next, bw.enter[i]);
+      if (bw.exitk[i] > k) next = min(next, bw.exitk[i]);
+      const bool inside = bw.enter[i] <= k && k < bw.exitk[i];
+      const uint32_t half = (i & 1) ? 0xFFFF0000u : 0x0000FFFFu;
+      if (inside) { if (i < 2) inA |= half; else inB |= half; }
+      if (bw.enter[i] == k) { if (i < 2) keepA &= ~half; else keepB &= ~half; }
+    }
+    if (keepA != 0xFFFFFFFFu) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) { pA[r] &= keepA; fA[r] &= keepA; glA[r] &= keepA; }
+    }
+    if (keepB != 0xFFFFFFFFu) {
+#pragma unroll
+      for (int r = 0; r < 8; r++) { pB[r] &= keepB; fB[r] &= keepB; glB[r] &= keepB; }
+    }
+GB200_BSC_UNROLL_PRAGMA
+    for (; k < next; k++) {
+      const uint32_t selA = v | prevsh;
+      prevsh = v * 256u + 0x4400u;
+      uint32_t mA = 0;
+      if (NMASK) { const uint32_t ncm = ncol_mask16(v); mA = ncm | (ncm_prev << 16); ncm_prev = ncm; }
+      uint32_t upA = prmt(he, h8A, 0x5410);
+      uint32_t eA = prmt(he, eoA, 0x5432);
+      uint32_t upB = prmt(h8A, h8B, 0x5432);
+      uint32_t eB = prmt(eoA, eoB, 0x5432);
+      he = HE[(k + 2) * kFastThreads];
+      v = V[(k + 2) * kFastThreads];
+      {
+        const uint32_t cm = key_tree(keyA) & inA_prev;               // the keys are the previous step's: masked with that step's windows
+        track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+        const uint32_t cn = key_tree(keyB) & inB_prev;
+        track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+        pos = pos_base + (uint32_t)k;
+      }
+      uint32_t gupA = __vadd2(upA, neg_oe2), gupB = __vadd2(upB, neg_oe2);       // H of the row above - oe
+#pragma unroll
+      for (int r = 0; r < 8; r++) {
+        {
+          uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+          if (NMASK) s2 = mask_sel(s2, mA, nsc2);
+          const uint32_t d = __vadd2(pA[r], s2);
+          fA[r] = __viaddmax_s16x2(fA[r], neg_ext2, glA[r]);          // F = max(F - e, H(left) - oe)      (banded.h:101)
+          eA = __viaddmax_s16x2(eA, neg_ext2, gupA);                  // E = max(E - e, H(above) - oe)     (:102)
+          const uint32_t h = __vimax3_s16x2_relu(d, fA[r], eA);
+          gupA = __vadd2(h, neg_oe2); glA[r] = gupA;
+          keyA[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+          pA[r] = upA; upA = h;
+        }
+        {
+          uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+          if (NMASK) s2 = mask_sel(s2, mB, nsc2);
+          const uint32_t d = __vadd2(pB[r], s2);
+          fB[r] = __viaddmax_s16x2(fB[r], neg_ext2, glB[r]);
+          eB = __viaddmax_s16x2(eB, neg_ext2, gupB);
+          const uint32_t h = __vimax3_s16x2_relu(d, fB[r], eB);
+          gupB = __vadd2(h, neg_oe2); glB[r] = gupB;
+          keyB[r] = h * eight + (uint32_t)((7 - r) * 0x00010001);
+          pB[r] = upB; upB = h;
+        }
+      }
+      // what a lane outside its band hands on reads as 0
+      upA &= inA; eA &= inA; upB &= inB; eB &= inB;
+      HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
+      h8A = upA; eoA = eA; h8B = upB; eoB = eB;
+      selB = selA_prev; selA_prev = selA;
+      inA_prev = inA; inB_prev = inB;
+      if (NMASK) { mB = mA_prev; mA_prev = mA; }
+    }
+  }
+  {
+    const uint32_t cm = key_tree(keyA) & inA_prev;
+    track_update(lb.a, cm | 0x00070007u, cm, pos, one);
+    const uint32_t cn = key_tree(keyB) & inB_prev;
+    track_update(lb.b, cn | 0x00070007u, cn, pos, one);
+  }
+}
+
 // Does the target hold a base outside A/C/G/T inside its true length?  Word-parallel (a nibble is valid iff it is 0001, 0011,
 // 0100 or 0111) and WITHOUT an early exit: the loads of a thread are independent and pipeline, where the per-nibble loop with
 // `&& !odd` serialised 75 dependent global loads per pair (7 % of the local kernel's time in the ncu source view).
@@ -981,7 +1095,8 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
 
 // BANDED + WITH_TB: the LOCAL recurrence with direction nibbles over the tile band (see local_sweep4_tbb); only the band's tiles are
 // stored: tile (strip * W + word - lo(strip)) * 2 + half, W = widest strip (dp_common.cuh band_geom), which k_get_tb addresses the same way
-template <bool NMASK = false>
+// TB = false: the reference's score-only BANDED kernel (banded.h: H-based opening, score + end cell) on the same tile band.
+template <bool NMASK = false, bool TB = true>
 __global__ void __launch_bounds__(kFastThreads) k_banded_tb_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
@@ -1043,8 +1158,10 @@ __global__ void __launch_bounds__(kFastThreads) k_banded_tb_s16(const FastArgs f
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
     quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
     const int c0 = ulo * 8;
-    local_sweep4_tbb<NMASK>(HE + (size_t)c0 * kFastThreads, V + (size_t)c0 * kFastThreads, bw, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, fa.mm, fa.sixteen,
-                            ((uint32_t)j << 16) + (uint32_t)c0, lb, a.tb + tid, (size_t)a.tb_stride, c0, nsc2);
+    if (TB) local_sweep4_tbb<NMASK>(HE + (size_t)c0 * kFastThreads, V + (size_t)c0 * kFastThreads, bw, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, fa.mm, fa.sixteen,
+                                    ((uint32_t)j << 16) + (uint32_t)c0, lb, a.tb + tid, (size_t)a.tb_stride, c0, nsc2);
+    else banded_sweep4<NMASK>(HE + (size_t)c0 * kFastThreads, V + (size_t)c0 * kFastThreads, bw, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one,
+                              ((uint32_t)j << 16) + (uint32_t)c0, lb, nsc2);
   }
   const Winner w_ = pick_winner4(lb);
   a.score[tid] = w_.score; a.q_end[tid] = w_.col; a.t_end[tid] = w_.row;
@@ -1556,6 +1673,10 @@ __global__ void __launch_bounds__(128) k_worklist(const FastArgs fa, int which) 
       else local_forward<false, false>(a, sc, p, pi, best, bq, bt);
       a.score[pi] = best; a.q_end[pi] = bq; a.t_end[pi] = bt;
       if (START == START_POS) { int sx, sy; local_reverse(sc, p, best, bq, bt, sx, sy); a.q_start[pi] = sx; a.t_start[pi] = sy; }
+    } else if (ALGO == ALGO_BANDED) {
+      int best, bq, bt;
+      banded_forward(a, sc, p, best, bq, bt);
+      a.score[pi] = best; a.q_end[pi] = bq; a.t_end[pi] = bt;
     } else if (ALGO == ALGO_SEMI_GLOBAL) {
       semiglobal_pair<START, false>(a, sc, p, pi);
     } else {
@@ -1570,10 +1691,15 @@ __global__ void k_zero_u32(uint32_t* p) { p[0] = 0; p[1] = 0; }
 #ifndef GB200_BANDED_TB_S16
 #define GB200_BANDED_TB_S16 1
 #endif
+#ifndef GB200_BANDED_S16
+#define GB200_BANDED_S16 1
+#endif
 bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint32_t max_q, uint32_t max_t) {
-  if (algo == ALGO_BANDED) {                     // banded traceback = LOCAL recurrence over the tile band; score-only BANDED is another recurrence
-    if (start != START_TB || !GB200_BANDED_TB_S16 || a.k_band < 8) return false;
-    algo = ALGO_LOCAL;
+  if (algo == ALGO_BANDED) {                     // banded traceback = LOCAL recurrence over the tile band; score-only BANDED = H-based opening (banded_sweep4)
+    if (a.k_band < 8) return false;
+    if (start == START_TB ? !GB200_BANDED_TB_S16 : !GB200_BANDED_S16) return false;
+    algo = ALGO_LOCAL;                           // same value range: clamped at 0, keys score * 8 + 7
+    if (start != START_TB) start = START_NONE;   // the banded kernel reports score + end cell whatever start_pos says (gasal_align.h:78-81)
   }
   if (second || (start == START_TB && algo != ALGO_LOCAL)) return false;
   const uint32_t q8 = (max_q + 7u) & ~7u, t8 = (max_t + 7u) & ~7u;
@@ -1628,7 +1754,8 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
   // int32 kernel, grid-striding over the list with a grid sized for the machine, not for a fixed 64 CTAs.
   const int nbias = (algo == ALGO_SEMI_GLOBAL) ? 2 * a.gap_extend : 0;
   const bool banded = (algo == ALGO_BANDED);
-  if (banded) algo = ALGO_LOCAL;                 // BANDED + WITH_TB (fast_path_eligible): LOCAL recurrence, banded sweep
+  const bool banded_sc = banded && start != START_TB;     // score-only BANDED: H-based recurrence, no direction matrix
+  if (banded) { algo = ALGO_LOCAL; if (banded_sc) start = START_NONE; }      // (fast_path_eligible): clamped recurrences, banded sweep
   const bool nmask = (algo == ALGO_LOCAL || algo == ALGO_SEMI_GLOBAL) && a.n_score + nbias >= -127 && a.n_score + nbias <= 127;
   int dev = 0, sms = 148; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const uint32_t n128 = ((uint32_t)a.n + 127u) & ~127u;
@@ -1660,6 +1787,8 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     cudaFuncSetAttribute(k_global_s16, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_banded_tb_s16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_banded_tb_s16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_banded_tb_s16<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_banded_tb_s16<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_local_s16<START_NONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_local_s16<START_POS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_local_s16<START_NONE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -1687,7 +1816,8 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     // beyond work_count[0] exit on their first instruction.
     cudaEventRecord(fs.ev_fork, str);
     cudaStreamWaitEvent(fs.side, fs.ev_fork, 0);
-    if (banded) k_banded_tb_s16<true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+    if (banded_sc) k_banded_tb_s16<true, false><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+    else if (banded) k_banded_tb_s16<true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
     else if (algo == ALGO_LOCAL) {
       if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
       else if (g4) { if (sp) k_local_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
@@ -1696,7 +1826,8 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     cudaEventRecord(fs.ev_join, fs.side);
     launches++;
   }
-  if (banded) k_banded_tb_s16<false><<<blocks, kFastThreads, smem, str>>>(fa);
+  if (banded_sc) k_banded_tb_s16<false, false><<<blocks, kFastThreads, smem, str>>>(fa);
+  else if (banded) k_banded_tb_s16<false><<<blocks, kFastThreads, smem, str>>>(fa);
   else if (algo == ALGO_LOCAL) {
     if (tbm) k_local_s16<START_TB><<<blocks, kFastThreads, smem, str>>>(fa);
     else if (g4) { if (sp) k_local_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
@@ -1710,7 +1841,8 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
   const int which = 1;                      // k_classify files everything the s16x2 passes cannot score in worklist2
   fa.a.colstate = fs.colstate; fa.a.col_stride = slots; fa.a.col_rows = q8;
   const int wb = (int)(slots / 128);
-  if (algo == ALGO_LOCAL) {
+  if (banded_sc) k_worklist<ALGO_BANDED, START_NONE><<<wb, 128, 0, str>>>(fa, which);
+  else if (algo == ALGO_LOCAL) {
     if (tbm) k_worklist<ALGO_LOCAL, START_TB><<<wb, 128, 0, str>>>(fa, which);
     else if (sp) k_worklist<ALGO_LOCAL, START_POS><<<wb, 128, 0, str>>>(fa, which); else k_worklist<ALGO_LOCAL, START_NONE><<<wb, 128, 0, str>>>(fa, which);
   }

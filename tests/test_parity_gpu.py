@@ -309,3 +309,28 @@ def test_opt_in_coordinate_fix(oracle):
     assert np.array_equal(sg["query_batch_end"], b.q_lens.astype(np.int32) - 1) and not sg["query_batch_start"].any()
     again = run(b, algo=capi.LOCAL, start=capi.WITH_START)
     assert np.array_equal(again["target_batch_start"], ref_start["target_batch_start"])
+
+
+def test_banded_score_runs_on_the_packed_kernel(oracle):
+    """a14 on the s16x2 lanes (k_banded_tb_s16<NMASK, TB = false>, H-based recurrence of banded.h:99-114 over the tile band): C4's
+    shape with N in 10 % of the pairs (N-aware pass), odd band geometries (band wider than the matrix, query longer than the
+    target, band of one tile), other scorings, and start_pos = WITH_START (the banded kernel ignores it: gasal_align.h:78-81)"""
+    b = synth.with_n_bases(synth.config4(8192, seed=46), 0.1, seed=4)
+    want = oracle_align(oracle, b, algo=po.BANDED, k_band=64)
+    got = run(b, algo=capi.BANDED, k_band=64)
+    assert got["_kernel"] == "s16x2"
+    assert_same(got, want, K3, "banded s16x2, C4 shape with N")
+    pol1 = run(b, policy=1, algo=capi.BANDED, k_band=64)
+    assert pol1["_kernel"] == "int32"
+    assert_same(pol1, want, K3, "banded int32, C4 shape with N")
+    for k_band, qmax, tmax, scoring in ((8, 40, 330, (1, 4, 6, 1)), (24, 220, 60, (2, 3, 5, 2)), (40, 330, 330, (5, 4, 10, 1)),
+                                        (4096, 100, 200, (1, 4, 6, 1)), (16, 300, 300, (1, 1, 0, 1)), (72, 250, 250, (3, 5, 0, 0))):
+        b = synth.random_ragged_pairs(700, 9, qmax, 9, tmax, seed=700 + k_band, n_frac=0.02)
+        want = oracle_align(oracle, b, algo=po.BANDED, k_band=k_band, scoring=scoring)
+        got = run(b, algo=capi.BANDED, k_band=k_band, scoring=scoring)
+        assert got["_kernel"] == "s16x2", (k_band, got["_kernel"])
+        assert_same(got, want, K3, f"banded s16x2 k={k_band} q<={qmax} t<={tmax} {scoring}")
+    b = synth.random_ragged_pairs(300, 9, 200, 9, 300, seed=733)
+    want = oracle_align(oracle, b, algo=po.BANDED, k_band=32)
+    got = run(b, algo=capi.BANDED, k_band=32, start=capi.WITH_START)
+    assert_same(got, want, K3, "banded s16x2 with start_pos = WITH_START")
