@@ -34,6 +34,22 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
 // maybe_odd: the batch may hold bases outside A/C/G/T (false: the host packer saw none, the extra passes are skipped)
 int fast_path_launch(const DpArgs& a, int algo, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, bool maybe_odd, int force_passes, cudaStream_t str);
 
+// ---- nvbio-style batched scoring on the quad-strip layout (nvb_strip.cuh; called by nvb_batched.cu) -----------------------
+struct NvbStripArgs {
+  const uint32_t* poffs; const uint32_t* ppk; const uint8_t* pflag;       // pattern byte offsets, 2-bit packed codes (k_nvb_pack), "not pure ACGT" flags
+  const uint32_t* toffs; const uint32_t* tpk; const uint8_t* tflag;
+  const uint32_t* pair_p; const uint32_t* pair_t; int text_shared;
+  uint32_t first, count;                                                  // job range of this launch
+  int match, mismatch, oe, ext;                                           // GASAL2-style magnitudes: mismatch >= 0, oe = -Go, ext = -Ge
+  int32_t* score; int32_t* sink_i; int32_t* sink_j;
+  uint32_t* worklist; uint32_t* work_count;                               // jobs with a symbol outside A/C/G/T (int32 kernel)
+  uint32_t m8max;                                                         // columns reserved per thread in shared memory (multiple of 8)
+  uint32_t eight, one;                                                    // == 8, 1 at run time (see FastArgs)
+};
+// type: 0 GLOBAL, 1 LOCAL, 2 SEMI_GLOBAL (aln::AlignmentType order)
+bool nvb_strip_eligible(int type, int match, int mismatch_pen, int oe, int ext, uint32_t max_m, uint32_t max_n, int want_sinks);
+int nvb_strip_launch(const NvbStripArgs& a, int type, int want_sinks, cudaStream_t str);
+
 // ---- intra-task wavefront kernels (dp_wave.cuh) ---------------------------------------------------------------------
 struct WaveScratch {
   uint64_t* qoff = nullptr; uint64_t* soff = nullptr; uint64_t* toff = nullptr; size_t n_cap = 0;    // device: qoff[n], soff[n], toff[n] (traceback tile offsets)

@@ -1183,6 +1183,8 @@ struct NcTrack {
   int best, y;          // semi-global: running (maxHH, maxXY_y)
   int stop;             // reverse pass: stop once best >= stop
   int cap;              // global: captured H(tlen-1, qlen-1)
+  int tie = 0;          // 1: a later row with the SAME score replaces the record (nvbio's BestSink, nvb_strip.cuh); 0: strict '>' (GASAL2)
+  int capture = 0;      // 1: the H-based (semi-global) recurrence captures (caplane, caprow) instead of scanning the column (nvbio GLOBAL)
 };
 
 template <int ALGO, bool REV>
@@ -1286,7 +1288,7 @@ struct NcState {
 template <int ALGO, bool REV, bool NMASK, bool RARE>
 __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict__ HE, const uint8_t* __restrict__ V,
                                         const uint32_t (&rowA)[8], const uint32_t (&rowB)[8], const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
-                                        const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8], const uint32_t (&hpinit)[8],
+                                        const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8], const uint32_t (&hpinitA)[8], const uint32_t (&hpinitB)[8],
                                         uint32_t neg_oe2, uint32_t neg2, uint32_t conv8, int bias_ext, uint32_t nsc2,
                                         int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, int col0 = 0) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
@@ -1357,9 +1359,9 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
       // lanes that just ran a phantom column (A.H: step 0; B.L: 0,1; B.H: 0,1,2) get their strip-start state back
 #pragma unroll
       for (int r = 0; r < 8; r++) {
-        if (k == 0) { st.pA[r] = prmt(st.pA[r], pinitA[r], 0x7610); st.fA[r] = prmt(st.fA[r], neg2, 0x7610); if (SEMI) st.glA[r] = prmt(st.glA[r], hpinit[r], 0x7610); }
-        if (k <= 1) { st.pB[r] = pinitB[r]; st.fB[r] = neg2; if (SEMI) st.glB[r] = hpinit[r]; }
-        else { st.pB[r] = prmt(st.pB[r], pinitB[r], 0x7610); st.fB[r] = prmt(st.fB[r], neg2, 0x7610); if (SEMI) st.glB[r] = prmt(st.glB[r], hpinit[r], 0x7610); }
+        if (k == 0) { st.pA[r] = prmt(st.pA[r], pinitA[r], 0x7610); st.fA[r] = prmt(st.fA[r], neg2, 0x7610); if (SEMI) st.glA[r] = prmt(st.glA[r], hpinitA[r], 0x7610); }
+        if (k <= 1) { st.pB[r] = pinitB[r]; st.fB[r] = neg2; if (SEMI) st.glB[r] = hpinitB[r]; }
+        else { st.pB[r] = prmt(st.pB[r], pinitB[r], 0x7610); st.fB[r] = prmt(st.fB[r], neg2, 0x7610); if (SEMI) st.glB[r] = prmt(st.glB[r], hpinitB[r], 0x7610); }
       }
     }
     const int li = k - kq;
@@ -1370,13 +1372,13 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
         const uint32_t w = (li & 2) ? hhB[r] : hhA[r];
         hv[r] = ((li & 1) ? lane_hi(w) : lane_lo(w)) - (col0 + kq + r) * bias_ext;     // back to the unbiased score (this lane is on column col0 + kq)
       }
-      if (SEMI) {
+      if (SEMI && !tr.capture) {
         // TAIL == TARGET: the last true query column, rows inside the target, strict '>' top-down (:160-178); the start
         // pass stops between strips once the forward score is reached (:301)
         if (!REV || li == 0 || tr.best < tr.stop) {
           const int rb = rowbase + 8 * li;
 #pragma unroll
-          for (int r = 0; r < 8; r++) if (rb + r < tlen && hv[r] > tr.best) { tr.best = hv[r]; tr.y = rb + r; }
+          for (int r = 0; r < 8; r++) if (rb + r < tlen && hv[r] > tr.best - tr.tie) { tr.best = hv[r]; tr.y = rb + r; }
         }
       } else if (li == caplane) {
 #pragma unroll
@@ -1398,7 +1400,8 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
                                           const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8],
                                           uint32_t neg_oe2, uint32_t neg_ext2,
                                           int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, uint32_t nsc2 = 0,
-                                          int col0 = 0, bool closed_left = false) {
+                                          int col0 = 0, bool closed_left = false, const uint32_t* hpA = nullptr, const uint32_t* hpB = nullptr) {
+  // hpA / hpB (nvb_strip.cuh, GLOBAL): H of the left boundary column per strip row and lane, biased, instead of the free column
   // col0 / closed_left (pruned start pass): HE / V point at column col0 of the matrix (kq is relative to it; the frame of the parked
   // values is absolute, so only the un-biasing of the scanned column needs col0), and what lies left of it reads as -infinity
   // instead of the free left column.
@@ -1412,20 +1415,21 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
   // (r - 1) ext; the diagonal inputs (pinit) carry (r - 2) ext.  The -infinity floors stay unbiased: they only ever lose a max.
   const int bias_ext = -lane_lo(neg_ext2);
   const uint32_t conv8 = splat16(-8 * bias_ext);
-  uint32_t hpinit[8], pA0[8], pB0[8];
+  uint32_t hpinitA[8], hpinitB[8], pA0[8], pB0[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    hpinit[r] = closed_left ? neg2 : (SEMI ? splat16((r - 1) * bias_ext) : neg_oe2);
+    const uint32_t hp = closed_left ? neg2 : (SEMI ? splat16((r - 1) * bias_ext) : neg_oe2);
+    hpinitA[r] = hpA ? hpA[r] : hp; hpinitB[r] = hpB ? hpB[r] : hp;
     pA0[r] = closed_left ? neg2 : pinitA[r]; pB0[r] = closed_left ? neg2 : pinitB[r];
   }
   NcState st;
 #pragma unroll
-  for (int r = 0; r < 8; r++) { st.pA[r] = pA0[r]; st.fA[r] = neg2; st.glA[r] = hpinit[r]; st.pB[r] = pB0[r]; st.fB[r] = neg2; st.glB[r] = hpinit[r]; }
+  for (int r = 0; r < 8; r++) { st.pA[r] = pA0[r]; st.fA[r] = neg2; st.glA[r] = hpinitA[r]; st.pB[r] = pB0[r]; st.fB[r] = neg2; st.glB[r] = hpinitB[r]; }
   st.h8A = 0; st.eoA = 0; st.h8B = 0; st.eoB = 0;
   st.prevsh = 0xCC00u; st.selB = 0xCCCCu; st.selA_prev = 0xCCCCu;
   st.he = HE[kFastThreads]; st.v = V[kFastThreads];
   st.ncm_prev = 0; st.mB = 0; st.mA_prev = 0;
-#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pA0, pB0, hpinit, neg_oe2, neg2, conv8, bias_ext, nsc2, \
+#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pA0, pB0, hpinitA, hpinitB, neg_oe2, neg2, conv8, bias_ext, nsc2, \
                                                            kq, rowbase, tlen, caplane, caprow, tr, col0)
 #if GB200_NC_SPLIT
   // segments: rare [0, r0e) -- hot [r0e, h0e) -- rare [h0e, r1e) -- hot [r1e, nsteps)

@@ -28,6 +28,7 @@
 #include <string>
 #include <vector>
 #include "../../include/nvbio_b200.h"
+#include "dp_launch.h"       // nvb_strip_launch: the quad-strip scoring kernel lives in the s16x2 translation unit (nvb_strip.cuh)
 
 namespace nvb200 {
 
@@ -682,8 +683,19 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
                     std::max(std::abs(a.ge_t), std::abs(a.ge_p)) < (1 << 19);
   // LOCAL sinks on the packed path: keys H * 16 + column must fit 16 bits, and strictly negative penalties keep pad cells from tying
   const bool local_keys = pos * mn <= 2047 && a.go_t < 0 && a.ge_t < 0 && a.mismatch < 0 && s->max_n < (1u << 20);
-  const bool fast = fits && (!want_sinks || al->type != NVBX_LOCAL || local_keys) && g_policy == 0;
+  // quad-strip kernel (nvb_strip.cuh): K2's blocking, no band-border scratch; scores of all three types, sinks of GLOBAL / SEMI_GLOBAL
+  const bool strip = g_policy == 0 && wide && a.go_t == a.go_p && a.ge_t == a.ge_p &&
+                     gb200::nvb_strip_eligible(al->type, a.match, -a.mismatch, -a.go_t, -a.ge_t, s->max_m, s->max_n, want_sinks);
+  const bool fast = strip || (fits && (!want_sinks || al->type != NVBX_LOCAL || local_keys) && (g_policy == 0 || g_policy == 2));
   a.sixteen = 16;
+  gb200::NvbStripArgs sa{};
+  if (strip) {
+    sa.poffs = s->poffs; sa.ppk = s->ppk; sa.pflag = s->pflag; sa.toffs = s->toffs; sa.tpk = s->tpk; sa.tflag = s->tflag;
+    sa.pair_p = s->pair_p; sa.pair_t = s->pair_t; sa.text_shared = s->text_shared;
+    sa.match = a.match; sa.mismatch = -a.mismatch; sa.oe = -a.go_t; sa.ext = -a.ge_t;
+    sa.score = s->score; sa.sink_i = s->sink_i; sa.sink_j = s->sink_j; sa.worklist = s->worklist; sa.work_count = s->work_count;
+    sa.m8max = (s->max_m + 7u) & ~7u; sa.eight = 8; sa.one = 1;
+  }
 
   // chunk the jobs so that the band-border scratch (8 B per text row per thread) stays below ~2 GB.  The fast path prefers the
   // fixed row stride (2 x kFixedStride jobs per launch) when the texts are short enough for it.
@@ -713,7 +725,8 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
       // its grid is bounded by a.stride threads and loops (k_nvb_i32w), instead of indexing past the allocation
       const uint32_t items = (a.count + 1) / 2, g = (items + kThreads - 1) / kThreads, g2 = std::min<uint32_t>((a.count + kThreads - 1) / kThreads, a.stride / kThreads);
 #define NVB_LAUNCH_FAST(T, S) do { \
-        if (fixed) k_nvb_s16<T, true, S><<<g, kThreads, 0, s->st>>>(a); else k_nvb_s16<T, false, S><<<g, kThreads, 0, s->st>>>(a); \
+        if (strip) { sa.first = a.first; sa.count = a.count; gb200::nvb_strip_launch(sa, T, S ? 1 : 0, s->st); } \
+        else if (fixed) k_nvb_s16<T, true, S><<<g, kThreads, 0, s->st>>>(a); else k_nvb_s16<T, false, S><<<g, kThreads, 0, s->st>>>(a); \
         k_nvb_i32w<T, S><<<g2, kThreads, 0, s->st>>>(a, 1); } while (0)
       if (type == NVBX_LOCAL) { if (want_sinks) NVB_LAUNCH_FAST(NVBX_LOCAL, true); else NVB_LAUNCH_FAST(NVBX_LOCAL, false); }
       else if (type == NVBX_GLOBAL) { if (want_sinks) NVB_LAUNCH_FAST(NVBX_GLOBAL, true); else NVB_LAUNCH_FAST(NVBX_GLOBAL, false); }
@@ -735,7 +748,7 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
   }
   NVB_CHECK(cudaEventRecord(s->e1, s->st));
   s->have_sinks = want_sinks != 0; s->enacted = true; s->have_tb = false;
-  s->kernel = used_i32 ? (wide ? "int32" : "int32-any") : "s16x2";
+  s->kernel = used_i32 ? (wide ? "int32" : "int32-any") : (strip ? "s16x2-strip" : "s16x2");
   return 0;
 }
 

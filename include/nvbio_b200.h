@@ -74,7 +74,7 @@ int nvbx_stream_results(nvbx_stream_t* s, int32_t* scores, int32_t* sink_text, i
 const int32_t* nvbx_stream_scores_device(nvbx_stream_t* s);
 float nvbx_stream_last_ms(nvbx_stream_t* s);            /* CUDA-event time of the last enact (synchronises) */
 uint64_t nvbx_stream_cells(const nvbx_stream_t* s);     /* sum over jobs of M * N (sw-benchmark.cu:380 GCUPS numerator) */
-const char* nvbx_stream_kernel(const nvbx_stream_t* s); /* last enact: "s16x2", "int32" (ordered costs), "int32-any", "banded-int32", "int32+tb", "banded-int32+tb" */
+const char* nvbx_stream_kernel(const nvbx_stream_t* s); /* last enact: "s16x2-strip", "s16x2", "int32" (ordered costs), "int32-any", "banded-int32", "int32+tb", "banded-int32+tb" */
 void nvbx_stream_destroy(nvbx_stream_t* s);
 
 /* ---- banded scoring and traceback batches (round 2) ------------------------------------------------------------------------------
@@ -122,8 +122,10 @@ int nvbx_stream_alignments(nvbx_stream_t* s, nvbx_alignment_t* alns, uint8_t* op
 int nvbx_batched_score_host(const nvbx_aligner_t* aligner, const nvbx_batch_t* batch, int32_t* scores, int32_t* sink_text,
                             int32_t* sink_pattern, float ms[3]);
 
-/* 0 = automatic (s16x2 two-jobs-per-thread kernel when the host-side range proof allows it, int32 otherwise),
- * 1 = always the int32 kernel (A/B testing and parity tests). */
+/* 0 = automatic: the quad-strip s16x2 kernel ("s16x2-strip": one job per thread, column state in shared memory, nothing parked in
+ *     HBM) for scores and GLOBAL / SEMI_GLOBAL sinks of patterns up to 352 symbols, the band-blocked s16x2 kernel ("s16x2": two jobs
+ *     per thread, the reference's blocking) where its range proof allows it, int32 otherwise;
+ * 1 = always the int32 kernel, 2 = never the quad-strip kernel (A/B testing and parity tests). */
 void nvbx_set_policy(int policy);
 uint64_t nvbx_kernel_launches(void);
 const char* nvbx_last_error(void);

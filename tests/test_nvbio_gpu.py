@@ -20,7 +20,22 @@ def orc():
     return po.NvbioOracle()
 
 
-def run(al, batch, want_sinks=False, policy=0):
+FAST = ("s16x2", "s16x2-strip")     # the band-blocked packed kernel (k_nvb_s16) / the quad-strip kernel (k_nvb_strip, nvb_strip.cuh)
+_POLICY = [0]
+
+
+@pytest.fixture(autouse=True, params=[0, 2], ids=["auto", "no-strip"])
+def _fast_policy(request):
+    """every test of this module runs twice: with the automatic kernel choice (quad-strip kernel where it is eligible) and with the
+    quad-strip kernel switched off (policy 2), so that both packed kernels keep their parity coverage"""
+    _POLICY[0] = request.param
+    yield
+    _POLICY[0] = 0
+    nvb.set_policy(0)
+
+
+def run(al, batch, want_sinks=False, policy=None):
+    policy = _POLICY[0] if policy is None else policy
     nvb.set_policy(policy)
     try:
         with nvb.Stream(batch) as st:
@@ -52,10 +67,10 @@ def test_fast_path_scores_ragged_lengths(orc, type_, scheme):
     batch = nvb.Batch(pats, poffs, texts, toffs)
     want, wi, wj = orc.batch(po.NVB_GOTOH, type_, scheme, pats, poffs, texts, toffs)
     s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch)
-    assert k == "s16x2"
+    assert k in FAST
     assert np.array_equal(s, want)
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True)
-    assert k == "s16x2"                                               # LOCAL sinks: packed keys (scores here stay below 2048)
+    assert k in FAST                                               # LOCAL sinks: packed keys (scores here stay below 2048)
     assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True, policy=1)
     assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
@@ -68,7 +83,7 @@ def test_smith_waterman_and_edit_distance(orc, type_):
     for algo, scheme, fast in ((nvb.SMITH_WATERMAN, (2, -1, -2, -2), True), (nvb.SMITH_WATERMAN, (1, -2, -3, -1), False), (nvb.EDIT_DISTANCE, (0, 0, 0, 0), True)):
         want, wi, wj = orc.batch(algo, type_, scheme, pats, poffs, texts, toffs)
         s, _, _, k = run(nvb.aligner(algo, type_, *scheme), batch)
-        assert k == ("s16x2" if fast else "int32"), (algo, scheme)      # asymmetric insertion / deletion costs: general kernel
+        assert (k in FAST) if fast else (k == "int32"), (algo, scheme, k)      # asymmetric insertion / deletion costs: general kernel
         assert np.array_equal(s, want), (algo, scheme)
         s, si, sj, _ = run(nvb.aligner(algo, type_, *scheme), batch, want_sinks=True)
         assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj), (algo, scheme)
@@ -84,7 +99,7 @@ def test_symbols_outside_acgt_go_to_the_general_kernel(orc, type_):
     batch = nvb.Batch(pats, poffs, texts, toffs)
     want, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, texts, toffs)
     s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), batch)
-    assert k == "s16x2" and np.array_equal(s, want)
+    assert k in FAST and np.array_equal(s, want)
     # ASCII strings: upper-case ACGT is the fast alphabet, anything else (N, lower case) is compared as raw bytes
     lut = np.frombuffer(b"ACGTNacgt", dtype=np.uint8)
     pa, ta = lut[pats], lut[texts]
@@ -98,7 +113,7 @@ def test_all_against_one_text_and_indexed_pairs(orc):
     al = nvb.aligner(nvb.GOTOH, nvb.SEMI_GLOBAL, *GOTOH_SW)
     want, wi, wj = orc.batch(po.NVB_GOTOH, po.NVB_SEMI_GLOBAL, GOTOH_SW, pats, poffs, texts, toffs)
     s, _, _, k = run(al, nvb.Batch(pats, poffs, texts, toffs))
-    assert k == "s16x2" and np.array_equal(s, want)
+    assert k in FAST and np.array_equal(s, want)
     s, si, sj, _ = run(al, nvb.Batch(pats, poffs, texts, toffs), want_sinks=True)
     assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
     rng = np.random.default_rng(9)
@@ -117,7 +132,7 @@ def test_range_proof_falls_back_to_int32_for_long_global_jobs(orc):
     al = nvb.aligner(nvb.GOTOH, nvb.LOCAL, 2, -1, -2, -1)           # local scores stay below 2 * 6000: fast path
     want, _, _ = orc.batch(po.NVB_GOTOH, po.NVB_LOCAL, (2, -1, -2, -1), pats, poffs, texts, toffs)
     s, _, _, k = run(al, batch)
-    assert k == "s16x2" and np.array_equal(s, want)
+    assert k in FAST and np.array_equal(s, want)
 
 
 def test_sw_benchmark_shape_20k_reads(orc):
@@ -172,9 +187,9 @@ def test_batches_larger_than_one_launch(orc):
     for type_ in (nvb.SEMI_GLOBAL, nvb.LOCAL):
         want, wi, wj = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, text, toffs)
         s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), batch)
-        assert k == "s16x2" and np.array_equal(s, want), type_
+        assert k in FAST and np.array_equal(s, want), type_
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, nvb.LOCAL, *GOTOH_SW), batch, want_sinks=True)
-    assert k == "s16x2" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
+    assert k in FAST and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
     s, si, sj, k = run(nvb.aligner(nvb.GOTOH, nvb.LOCAL, *GOTOH_SW), batch, want_sinks=True, policy=1)
     assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
 
@@ -196,7 +211,7 @@ def test_more_flagged_jobs_than_packed_threads(orc):
     for type_ in (nvb.SEMI_GLOBAL, nvb.GLOBAL, nvb.LOCAL):
         want, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, text, toffs)
         s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), batch)
-        assert k == "s16x2" and np.array_equal(s, want), type_
+        assert k in FAST and np.array_equal(s, want), type_
 
 
 @pytest.mark.parametrize("algo,scheme", [(nvb.GOTOH, GOTOH_SW), (nvb.SMITH_WATERMAN, (2, -1, -2, -2))])
@@ -222,7 +237,7 @@ def test_local_sinks_tie_order_and_key_range(orc, algo, scheme):
     zero = want == 0
     assert zero.sum() > 50 and np.array_equal(wi[zero], np.diff(toffs)[zero]) and np.array_equal(wj[zero], np.diff(poffs)[zero])
     s, si, sj, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch, want_sinks=True)
-    assert k == "s16x2"
+    assert k in FAST
     assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
     # long identical strings: score 2 * 1500 > 2047
     pats, poffs, texts, toffs = synth.nvb_jobs(40, 1400, 1500, 1800, 2000, seed=42, sub=0.01, indel=0.0)
@@ -231,7 +246,7 @@ def test_local_sinks_tie_order_and_key_range(orc, algo, scheme):
     s, si, sj, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch, want_sinks=True)
     assert k == "int32" and np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj)
     s, _, _, k = run(nvb.aligner(algo, nvb.LOCAL, *scheme), batch)
-    assert k == "s16x2" and np.array_equal(s, want)
+    assert k in FAST and np.array_equal(s, want)
 
 
 def test_cpp_front_end(orc, tmp_path):
@@ -255,3 +270,38 @@ def test_cpp_front_end(orc, tmp_path):
         s, si, sj = orc.batch(algo, type_, scheme, pats, poffs, texts, toffs)
         g = got[block * 501:(block + 1) * 501]
         assert np.array_equal(g[:, 1], s) and np.array_equal(g[:, 2], si) and np.array_equal(g[:, 3], sj), (algo, type_)
+
+
+@pytest.mark.parametrize("type_", TYPES)
+def test_quad_strip_kernel(orc, type_):
+    """k_nvb_strip (nvb_strip.cuh): K2's blocking -- one job per thread, four text strips in the 16-bit lanes, pattern-side column state in
+    shared memory, no band-border scratch -- for scores of all three types and the sinks of GLOBAL / SEMI_GLOBAL.  Ragged lengths
+    from 1 symbol up (pad rows and pad columns, texts that end in every lane of a quad-strip), several schemes incl. edit
+    distance and zero-cost extension, jobs with N (worklist), the all-against-one text shape, patterns beyond the shared-memory
+    limit (falls back to the band-blocked kernel)."""
+    for seed, (mlo, mhi, nlo, nhi), scheme in ((51, (1, 210, 1, 330), GOTOH_SW), (52, (1, 40, 1, 70), (1, -4, -7, -1)), (53, (100, 320, 1, 500), (3, -2, -5, -5)),
+                                               (54, (5, 150, 5, 700), (2, -3, -4, 0)), (55, (1, 64, 200, 260), (1, -1, -1, -1))):
+        pats, poffs, texts, toffs = synth.nvb_jobs(2501, mlo, mhi, nlo, nhi, seed=seed)
+        batch = nvb.Batch(pats, poffs, texts, toffs)
+        want, wi, wj = orc.batch(po.NVB_GOTOH, type_, scheme, pats, poffs, texts, toffs)
+        s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, policy=0)
+        assert k == "s16x2-strip", (seed, k)
+        assert np.array_equal(s, want), (seed, scheme, np.nonzero(s != want)[0][:5])
+        s, si, sj, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, want_sinks=True, policy=0)
+        assert k == ("s16x2" if type_ == nvb.LOCAL and scheme[3] < 0 else "int32" if type_ == nvb.LOCAL else "s16x2-strip"), (seed, k)
+        assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj), (seed, scheme)
+        s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *scheme), batch, policy=2)
+        assert k != "s16x2-strip" and np.array_equal(s, want), (seed, k)
+    # edit distance + symbols outside ACGT + one shared text
+    pats, poffs, texts, toffs = synth.nvb_jobs(1500, 20, 150, 900, 900, seed=56, shared_text=True)
+    pats = pats.copy(); pats[np.random.default_rng(6).integers(0, pats.size, 200)] = 4
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    for algo, oalgo, scheme in ((nvb.EDIT_DISTANCE, po.NVB_ED, ()), (nvb.SMITH_WATERMAN, po.NVB_SW, (2, -1, -2, -2)), (nvb.GOTOH, po.NVB_GOTOH, GOTOH_SW)):
+        want, wi, wj = orc.batch(oalgo, type_, scheme, pats, poffs, texts, toffs)
+        s, _, _, k = run(nvb.aligner(algo, type_, *scheme), batch, policy=0)
+        assert k == "s16x2-strip" and np.array_equal(s, want), (algo, k)
+    # a pattern of 353+ symbols does not fit the shared-memory column state
+    pats, poffs, texts, toffs = synth.nvb_jobs(200, 300, 420, 300, 500, seed=57)
+    want, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, texts, toffs)
+    s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), nvb.Batch(pats, poffs, texts, toffs), policy=0)
+    assert k == "s16x2" and np.array_equal(s, want)

@@ -24,7 +24,7 @@ def main():
         cells = st.cells()
         cases = [("gotoh_global", nvb.aligner(nvb.GOTOH, nvb.GLOBAL, 2, -1, -2, -1)), ("gotoh_semi_global", nvb.aligner(nvb.GOTOH, nvb.SEMI_GLOBAL, 2, -1, -2, -1)),
                  ("gotoh_local", nvb.aligner(nvb.GOTOH, nvb.LOCAL, 2, -1, -2, -1)), ("ed_semi_global", nvb.aligner(nvb.EDIT_DISTANCE, nvb.SEMI_GLOBAL))]
-        for policy, tag in ((0, "auto"), (1, "int32")):
+        for policy, tag in ((0, "auto"), (2, "band_blocked"), (1, "int32")):
             nvb.set_policy(policy)
             for name, al in cases + [(c[0] + "_sinks", c[1]) for c in cases[1:3]]:
                 sinks = name.endswith("_sinks")
