@@ -718,6 +718,10 @@ GB200_TBB_UNROLL_PRAGMA
 // D = diag + s, H - oe (feeds the next row's E and the next column's F) and the arg-max key on the FMA pipe.  The parked / handed-on
 // E is the row's OWN E (the next row advances it), and (0, 0) for whatever lies outside a strip's band: every H is clamped at 0, so
 // F / E values <= 0 are interchangeable and the cleared start state (F = 0, H - oe = 0) of a lane that enters its window is exact.
+// (ptxas folds the single-use add D = diag + s into the H maximum: VIADDMNMX + VIMNMX on the ALU pipe instead of VIADD.16x2 +
+// VIMNMX3, 6.9 instead of 5.9 ALU-pipe instructions per cell pair.  Giving D a second use through the keys was measured: keys built
+// from D need non-negative lanes (the packed multiply carries a negative low lane into the high one), and D times a run-time zero
+// costs the IMAD it saves: 3.17 ms vs 3.15 ms on config 4.  Kept simple.)
 template <bool NMASK = false>
 __device__ __forceinline__ void banded_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, const BandWin& bw,
                                               const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],

@@ -12,9 +12,8 @@
 //   GLOBAL / SEMI_GLOBAL : nc_sweep4<ALGO_SEMI_GLOBAL> (biased frame, E off the H chain), nvbio's boundaries
 //                          H(0, j) = Go + Ge (j - 1), H(i, 0) = 0 (SEMI_GLOBAL) or Go + Ge (i - 1) (GLOBAL), E(i, 0) = F(0, j) = -inf;
 //                          SEMI_GLOBAL scans column M (BestSink: the LAST best row wins, sink_inl.h:52-60), GLOBAL captures (N, M)
-//   LOCAL                : banded_sweep4 with every strip's window = the whole pattern (clamped at 0, chain formulation); the score
-//                          is the maximum over the true cells (pad columns are masked out by the windows, pad rows score the
-//                          mismatch against everything and cannot exceed the cell above them)
+//   LOCAL                : nvb_local_sweep4 (clamped at 0, chain formulation, unbiased frame); the score is the running maximum of H
+//                          (pad columns score 0 / -1 on the diagonal, pad rows the mismatch: they never exceed a true cell)
 // LOCAL sinks keep the reference's band-major tie order (k_nvb_s16 / k_nvb_i32w); this kernel serves scores, and the sinks of
 // GLOBAL / SEMI_GLOBAL.  Jobs with a symbol outside A/C/G/T go to the int32 worklist exactly as in k_nvb_s16.
 #pragma once
@@ -25,6 +24,74 @@ namespace gb200 {
 
 __device__ __forceinline__ uint32_t nvb_row_table(uint32_t w, int sh, bool inside, uint32_t mis4, uint32_t delta) {
   return inside ? (mis4 ^ (delta << (8u * ((w >> sh) & 3u)))) : mis4;
+}
+
+// Score-only LOCAL sweep (H-based opening, clamped at 0): the chain formulation in an unbiased frame, without windows, keys or
+// records.  Everything that travels -- the parked / handed-on column state, the left neighbours, the diagonal inputs -- is kept as
+// G = H - oe, and the substitution tables hold s + oe, so that per cell pair there are exactly
+//     ALU pipe : PRMT (s + oe), VIADDMNMX.RELU (F = max(F - e, G(left), 0)), VIADDMNMX (E = max(E - e, G(above))), VIMNMX3 (H = max(D, F, E))
+//     FMA pipe : VIADD.16x2 (D = G(diagonal) + s + oe), VIADD.16x2 (G = H - oe)
+// plus half a VIMNMX3 for the running maximum, and no register moves (the diagonal input of row r is the OLD G of row r - 1: renaming).
+// The maximum is taken over the DIAGONAL candidates D, not over H: a positive maximum of H is always attained on a cell with H = D
+// (a cell that takes its value from E or F is matched or beaten by the cell its gap started from), and the second use of D keeps
+// ptxas from folding the add into the H maximum (VIADDMNMX + VIMNMX on the ALU pipe instead of VIADD.16x2 + VIMNMX3).  No masks
+// are needed: phantom and pad columns score <= 0 on the diagonal (selector 0x88 / 0xCC: the sign byte of a table entry) and pad rows
+// score the mismatch, so a cell outside the true matrix never exceeds the cell it was derived from; F is carried clamped at 0
+// (F values <= 0 are interchangeable under the clamp of H), which is also what clamps H.
+__device__ __forceinline__ void nvb_local_sweep4(uint32_t* __restrict__ GE, const uint8_t* __restrict__ V, int nsteps,
+                                                 const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
+                                                 const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
+                                                 uint32_t neg_oe2, uint32_t neg_ext2, uint32_t& bestA, uint32_t& bestB) {
+  uint32_t fA[8], glA[8], fB[8], glB[8];
+#pragma unroll
+  for (int r = 0; r < 8; r++) { fA[r] = 0; glA[r] = neg_oe2; fB[r] = 0; glB[r] = neg_oe2; }   // H = 0 left of column 0
+  uint32_t g8A = neg_oe2, eoA = 0, g8B = neg_oe2, eoB = 0;      // bottom-row (G, E) of lanes A.L / A.H and B.L / B.H, handed on one step later
+  uint32_t dg0A = neg_oe2, dg0B = neg_oe2;                      // G above row 0 in the previous column: row 0's diagonal input
+  uint32_t prevsh = 0xCC00u;
+  uint32_t selB = 0xCCCCu, selA_prev = 0xCCCCu;                 // phantom columns: score <= 0
+  uint32_t ge = GE[kFastThreads];
+  uint32_t v = V[kFastThreads];
+  auto step = [&](int k) {
+    const uint32_t selA = v | prevsh;
+    prevsh = v * 256u + 0x4400u;
+    const uint32_t gupA = prmt(ge, g8A, 0x5410), gupB = prmt(g8A, g8B, 0x5432);     // G of the row above each lane's strip, this column
+    uint32_t eA = prmt(ge, eoA, 0x5432);
+    uint32_t eB = prmt(eoA, eoB, 0x5432);
+    ge = GE[(k + 2) * kFastThreads];
+    v = V[(k + 2) * kFastThreads];
+    uint32_t dgA = dg0A, dgB = dg0B, gA = gupA, gB = gupB, hpA = 0, hpB = 0;
+    dg0A = gupA; dg0B = gupB;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      {
+        const uint32_t s2 = prmt(rowA[r], rowB[r], selA);
+        const uint32_t d = __vadd2(dgA, s2);
+        dgA = glA[r];                                               // old G(left) of this row = the next row's diagonal input
+        fA[r] = __viaddmax_s16x2_relu(fA[r], neg_ext2, glA[r]);     // max(F - e, H(left) - oe, 0)
+        eA = __viaddmax_s16x2(eA, neg_ext2, gA);                    // max(E - e, H(above) - oe)
+        const uint32_t h = __vimax3_s16x2(d, fA[r], eA);            // F >= 0 carries the clamp
+        gA = __vadd2(h, neg_oe2); glA[r] = gA;
+        if (r & 1) bestA = __vimax3_s16x2(bestA, hpA, d); else hpA = d;
+      }
+      {
+        const uint32_t s2 = prmt(rowC[r], rowD[r], selB);
+        const uint32_t d = __vadd2(dgB, s2);
+        dgB = glB[r];
+        fB[r] = __viaddmax_s16x2_relu(fB[r], neg_ext2, glB[r]);
+        eB = __viaddmax_s16x2(eB, neg_ext2, gB);
+        const uint32_t h = __vimax3_s16x2(d, fB[r], eB);
+        gB = __vadd2(h, neg_oe2); glB[r] = gB;
+        if (r & 1) bestB = __vimax3_s16x2(bestB, hpB, d); else hpB = d;
+      }
+    }
+    GE[(k - 2) * kFastThreads] = prmt(gB, eB, 0x7632);          // B.H finished column k - 3 (slot k - 2): park (G, E) for the next quad-strip
+    g8A = gA; eoA = eA; g8B = gB; eoB = eB;
+    selB = selA_prev; selA_prev = selA;
+  };
+  int k = 0;
+#pragma unroll 1
+  for (; k + 1 < nsteps; k += 2) { step(k); step(k + 1); }
+  if (k < nsteps) step(k);
 }
 
 template <int TYPE, bool SINK>
@@ -46,11 +113,12 @@ __global__ void __launch_bounds__(kFastThreads) k_nvb_strip(const NvbStripArgs a
   const int oe = a.oe, ext = a.ext, o = oe - ext;
   constexpr bool LOC = (TYPE == 1);                                        // NVBX_LOCAL
   const int bias2 = LOC ? 0 : 2 * ext;                                     // biased frame: a diagonal step carries + 2 ext
-  const uint32_t mis4 = ((uint32_t)(-a.mismatch + bias2) & 0xFFu) * 0x01010101u;
-  const uint32_t delta = ((uint32_t)(a.match + bias2) ^ (uint32_t)(-a.mismatch + bias2)) & 0xFFu;
+  const int tsh = LOC ? oe : bias2;                                        // LOCAL: the tables hold s + oe (diagonal inputs travel as H - oe)
+  const uint32_t mis4 = ((uint32_t)(-a.mismatch + tsh) & 0xFFu) * 0x01010101u;
+  const uint32_t delta = ((uint32_t)(a.match + tsh) ^ (uint32_t)(-a.mismatch + tsh)) & 0xFFu;
 
   // selector bytes of the pattern columns + the top boundary row
-  V[0] = 0x88; HE[0] = LOC ? 0u : pack2(0, kNegSafe);
+  V[0] = 0x88; HE[0] = LOC ? pack2(-oe, 0) : pack2(0, kNegSafe);      // LOCAL parks (G = H - oe, E), see nvb_local_sweep4
   for (int w = 0; w < (ncol + 15) >> 4; w++) {
     const uint32_t codes = pw[min(w, (M - 1) >> 4)];
 #pragma unroll
@@ -58,7 +126,7 @@ __global__ void __launch_bounds__(kFastThreads) k_nvb_strip(const NvbStripArgs a
       const int c = 16 * w + k;
       if (c < ncol) {
         V[(c + 1) * kFastThreads] = (c < M) ? (uint8_t)(0x80u + 0x11u * ((codes >> (2 * k)) & 3u)) : (uint8_t)0x88;
-        if (LOC) HE[(c + 1) * kFastThreads] = 0u;
+        if (LOC) HE[(c + 1) * kFastThreads] = pack2(-oe, 0);
         else {
           // H(0, j = c + 1) = Go + Ge c; biased frame of nc_sweep4: H(-1, c) carries (c - 1) ext; the parked E is the first row's own
           // E(0, c) = H(-1, c) - oe, carries c ext, and is kept as E + open
@@ -69,31 +137,26 @@ __global__ void __launch_bounds__(kFastThreads) k_nvb_strip(const NvbStripArgs a
     }
   }
 #pragma unroll
-  for (int x = 1; x <= 5; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = LOC ? 0u : pack2(0, kNegSafe); }
+  for (int x = 1; x <= 5; x++) { V[(ncol + x) * kFastThreads] = 0x88; HE[(ncol + x) * kFastThreads] = LOC ? pack2(-oe, 0) : pack2(0, kNegSafe); }
 
   const int NQ = (N + 31) >> 5;
   if (LOC) {
     const uint32_t neg_oe2 = splat16(-oe), neg_ext2 = splat16(-ext);
-    LaneBest4 lb; lanebest_init(lb.a); lanebest_init(lb.b);
+    uint32_t bestA = 0, bestB = 0;
+    const int nsteps = M + 2 + (int)a.one;                                   // lane B.H parks column M - 1 at step M + 2; pad columns are never needed
     for (int j = 0; j < NQ; j++) {
       uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
       const uint32_t w0 = tw[min(2 * j, nwT - 1)], w1 = tw[min(2 * j + 1, nwT - 1)];
-      BandWin bw;
-#pragma unroll
-      for (int i = 0; i < 4; i++) {
-        const bool have = 32 * j + 8 * i < N;
-        bw.enter[i] = have ? i : 0; bw.exitk[i] = have ? M + i : 0; bw.tile_base[i] = 0;     // the window of a strip: columns [0, M)
-      }
 #pragma unroll
       for (int r = 0; r < 8; r++) {
         const int t = 32 * j + r;
         rowA[r] = nvb_row_table(w0, 2 * r, t < N, mis4, delta);      rowB[r] = nvb_row_table(w0, 16 + 2 * r, t + 8 < N, mis4, delta);
         rowC[r] = nvb_row_table(w1, 2 * r, t + 16 < N, mis4, delta); rowD[r] = nvb_row_table(w1, 16 + 2 * r, t + 24 < N, mis4, delta);
       }
-      banded_sweep4<false>(HE, V, bw, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, a.eight, a.one, (uint32_t)j << 16, lb);
+      nvb_local_sweep4(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, bestA, bestB);
     }
-    const Winner w_ = pick_winner4(lb);
-    a.score[job] = w_.score;
+    const uint32_t b2 = __vmaxs2(bestA, bestB);
+    a.score[job] = max(lane_lo(b2), lane_hi(b2));
     return;
   }
 
@@ -141,7 +204,7 @@ bool nvb_strip_eligible(int type, int match, int mismatch_pen, int oe, int ext, 
   if (match < 0 || match > 127 || mismatch_pen < 0 || mismatch_pen > 127) return false;
   if (ext < 0 || oe < ext || oe > 2000) return false;             // Go <= Ge <= 0
   const int64_t mn = std::min(m8, n8);
-  if (type == 1) return (uint64_t)mn * (uint64_t)match <= 4000;   // keys are score * 8 + 7 in a signed 16-bit lane
+  if (type == 1) return match + oe <= 127 && (uint64_t)mn * (uint64_t)match <= 30000;  // table bytes hold s + oe; plain scores in signed 16-bit lanes
   // biased frame: the same bounds as the GASAL2 semi-global / global fast path (fast_path_eligible), with nvbio's boundaries
   if (match + 2 * ext > 127) return false;
   const int64_t span = (type == 0) ? (int64_t)m8 + n8 + 2 : (int64_t)m8 + 2;

@@ -25,7 +25,8 @@
  * Parity: PINNED to the reference's own host build of these headers (oracle/ref_nvbio/nvbio_ref.cpp ->
  * oracle/_ref/libnvbio_ref.so) by tests/test_nvbio_oracle.py and to the golden vectors generated from it
  * (tests/golden/nvbio_scores.json, generator tools/make_nvbio_golden.py).  Domain: every H/E/F value inside the
- * reference's int16 column storage (gotoh_inl.h:599-602 asserts), min_score = INT32_MIN (no early exit).
+ * reference's int16 column storage (gotoh_inl.h:599-602 asserts).  nvbio_compat_score is the min_score = INT32_MIN case (no early
+ * exit, what sw-benchmark passes); nvbio_compat_score_min adds the early exit.
  */
 #include <stdint.h>
 #include <stdlib.h>
@@ -77,6 +78,63 @@ int nvbio_compat_score(int algo, int type, const int32_t* scheme, const uint8_t*
     return 0;
 }
 
+/* min_score early exit (alignment.h:456-530 `min_score`; gotoh_inl.h:826-830, sw_inl.h:699-701): after each band of `band` pattern
+ * columns EXCEPT the last one, the reference takes max_score = max over the text rows of H(i, last column of the band) and gives up
+ * -- returns false, the sink keeps what was reported so far -- when max_score + (columns still to come) * match < min_score.
+ * LOCAL reports from every band, so it keeps the best cell of the bands processed (in their report order); GLOBAL / SEMI_GLOBAL
+ * only report from the last band, so their sink stays at BestSink's initial state (score Field_traits<int32>::min() = -(1 << 30),
+ * sink (-1, -1); sink_inl.h:40).  Columns only depend on the columns to their left, so the bands processed before the exit hold the
+ * values of the full DP: the restatement finds the exit band from the column maxima of a full DP and, for LOCAL, rescoring the
+ * pattern truncated after that band.  out[3] = the function's bool result (1: ran to the end, 0: gave up).
+ * Edit distance scores a match 0, so its bound is max_score itself. */
+int nvbio_compat_score_min(int algo, int type, const int32_t* scheme, const uint8_t* pattern, uint32_t M, const uint8_t* text,
+                           uint32_t N, uint32_t band, int32_t min_score, int32_t* out) {
+    int match = scheme[0], mismatch = scheme[1];
+    int go_t, ge_t, go_p, ge_p;
+    if (algo == 0) { go_t = go_p = scheme[2]; ge_t = ge_p = scheme[3]; }
+    else if (algo == 1) { go_t = ge_t = scheme[2]; go_p = ge_p = scheme[3]; }
+    else { match = 0; mismatch = -1; go_t = ge_t = go_p = ge_p = -1; }
+    if (band == 0) band = 8;
+    out[3] = 1;
+    const uint32_t nb = (M + band - 1) / band;                 /* bands; the last one is never checked */
+    if (nb > 1 && N > 0) {
+        int* H = (int*)malloc(sizeof(int) * (M + 1));
+        int* F = (int*)malloc(sizeof(int) * (M + 1));
+        int* cmax = (int*)malloc(sizeof(int) * (M + 1));
+        if (!H || !F || !cmax) return -1;
+        H[0] = 0;
+        for (uint32_t j = 1; j <= M; ++j) { H[j] = (type == 1) ? 0 : go_p + ge_p * (int)(j - 1); F[j] = NEG; cmax[j] = INT32_MIN; }
+        for (uint32_t i = 1; i <= N; ++i) {
+            int diag = H[0];
+            H[0] = (type == 0) ? go_t + ge_t * (int)(i - 1) : 0;
+            int E = (type == 1) ? 0 : NEG;
+            for (uint32_t j = 1; j <= M; ++j) {
+                F[j] = max2(F[j] + ge_t, H[j] + go_t);
+                E = max2(E + ge_p, H[j - 1] + go_p);
+                const int s = (text[i - 1] == pattern[j - 1]) ? match : mismatch;
+                int h = max2(max2(E, F[j]), diag + s);
+                if (type == 1) h = max2(h, 0);
+                diag = H[j];
+                H[j] = h;
+                if (h > cmax[j]) cmax[j] = h;
+            }
+        }
+        uint32_t exit_cols = 0;
+        for (uint32_t b = 0; b + 1 < nb && !exit_cols; ++b) {
+            const uint32_t c = (b + 1) * band;                 /* last column of band b (always <= M here) */
+            if ((int64_t)cmax[c] + (int64_t)(M - c) * match < (int64_t)min_score) exit_cols = c;
+        }
+        free(H); free(F); free(cmax);
+        if (exit_cols) {
+            out[3] = 0;
+            if (type == 1) return nvbio_compat_score(algo, type, scheme, pattern, exit_cols, text, N, band, out);
+            out[0] = -(1 << 30); out[1] = -1; out[2] = -1;
+            return 0;
+        }
+    }
+    return nvbio_compat_score(algo, type, scheme, pattern, M, text, N, band, out);
+}
+
 /* Batch form: job k aligns pattern pair_pattern[k] (or k) with text pair_text[k] (or k, or 0 when n_texts == 1): the
  * host-side meaning of include/nvbio_b200.h's nvbx_batch_t.  out: scores[n], sink_i[n], sink_j[n] (sinks may be NULL). */
 int nvbio_compat_batch(int algo, int type, const int32_t* scheme, const uint8_t* patterns, const uint32_t* poffs,
@@ -91,6 +149,27 @@ int nvbio_compat_batch(int algo, int type, const int32_t* scheme, const uint8_t*
         int32_t out[3];
         if (nvbio_compat_score(algo, type, scheme, patterns + poffs[pi], poffs[pi + 1] - poffs[pi], texts + toffs[ti],
                                toffs[ti + 1] - toffs[ti], band, out) != 0) { rc = -1; continue; }
+        scores[k] = out[0];
+        if (sink_i) sink_i[k] = out[1];
+        if (sink_j) sink_j[k] = out[2];
+    }
+    return rc;
+}
+
+
+/* batch form with the early exit: min_scores == NULL -> `min_score` for every job */
+int nvbio_compat_batch_min(int algo, int type, const int32_t* scheme, const uint8_t* patterns, const uint32_t* poffs,
+                           const uint8_t* texts, const uint32_t* toffs, uint32_t n_texts, const uint32_t* pair_pattern,
+                           const uint32_t* pair_text, uint32_t n_pairs, uint32_t band, const int32_t* min_scores, int32_t min_score,
+                           int32_t* scores, int32_t* sink_i, int32_t* sink_j) {
+    int rc = 0;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int64_t k = 0; k < (int64_t)n_pairs; ++k) {
+        const uint32_t pi = pair_pattern ? pair_pattern[k] : (uint32_t)k;
+        const uint32_t ti = pair_text ? pair_text[k] : (n_texts == 1 ? 0u : (uint32_t)k);
+        int32_t out[4];
+        if (nvbio_compat_score_min(algo, type, scheme, patterns + poffs[pi], poffs[pi + 1] - poffs[pi], texts + toffs[ti],
+                                   toffs[ti + 1] - toffs[ti], band, min_scores ? min_scores[k] : min_score, out) != 0) { rc = -1; continue; }
         scores[k] = out[0];
         if (sink_i) sink_i[k] = out[1];
         if (sink_j) sink_j[k] = out[2];

@@ -268,6 +268,10 @@ class NvbioOracle:
         ref = os.path.join(HERE, "_ref", "libnvbio_ref.so")
         self.ref = C.CDLL(ref) if os.path.exists(ref) else None
         V, U = C.c_void_p, C.c_uint32
+        self.lib.nvbio_compat_score_min.argtypes = [C.c_int, C.c_int, V, V, U, V, U, U, C.c_int32, V]
+        self.lib.nvbio_compat_batch_min.argtypes = [C.c_int, C.c_int, V, V, V, V, V, U, V, V, U, U, V, C.c_int32, V, V, V]
+        if self.ref is not None and hasattr(self.ref, "nvbio_ref_score_min"):
+            self.ref.nvbio_ref_score_min.argtypes = [C.c_int, C.c_int, V, V, U, V, U, C.c_int32, V]
         self.lib.nvbio_compat_banded_score.argtypes = [C.c_int, C.c_int, C.c_int, V, V, U, V, U, V]
         self.lib.nvbio_compat_traceback.argtypes = [C.c_int, C.c_int, V, V, U, V, U, U, V, V, U]
         self.lib.nvbio_compat_banded_traceback.argtypes = [C.c_int, C.c_int, C.c_int, V, V, U, V, U, V, V, U]
@@ -295,6 +299,31 @@ class NvbioOracle:
         rc = self.ref.nvbio_ref_score(algo, type_, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, out.ctypes.data)
         assert rc == 0
         return tuple(int(x) for x in out)
+
+    def score_min(self, algo, type_, scheme, pattern, text, min_score, ref=False):
+        """alignment_score with a min_score threshold: (score, sink text end, sink pattern end, ok); ok = 0 when it gave up early"""
+        p = np.ascontiguousarray(pattern, dtype=np.uint8); t = np.ascontiguousarray(text, dtype=np.uint8)
+        sc = self._scheme(scheme); out = np.zeros(4, np.int32)
+        if ref:
+            rc = self.ref.nvbio_ref_score_min(algo, type_, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, int(min_score), out.ctypes.data)
+        else:
+            rc = self.lib.nvbio_compat_score_min(algo, type_, sc.ctypes.data, p.ctypes.data, p.size, t.ctypes.data, t.size, NVB_BAND[algo], int(min_score),
+                                                 out.ctypes.data)
+        assert rc == 0, rc
+        return tuple(int(x) for x in out)
+
+    def batch_min(self, algo, type_, scheme, patterns, poffs, texts, toffs, min_score=-(1 << 31), min_scores=None):
+        patterns = np.ascontiguousarray(patterns, dtype=np.uint8); texts = np.ascontiguousarray(texts, dtype=np.uint8)
+        poffs = np.ascontiguousarray(poffs, dtype=np.uint32); toffs = np.ascontiguousarray(toffs, dtype=np.uint32)
+        n_pairs = len(poffs) - 1
+        ms = None if min_scores is None else np.ascontiguousarray(min_scores, dtype=np.int32)
+        sc = self._scheme(scheme)
+        s = np.empty(n_pairs, np.int32); si = np.empty(n_pairs, np.int32); sj = np.empty(n_pairs, np.int32)
+        rc = self.lib.nvbio_compat_batch_min(algo, type_, sc.ctypes.data, patterns.ctypes.data, poffs.ctypes.data, texts.ctypes.data, toffs.ctypes.data,
+                                             len(toffs) - 1, None, None, n_pairs, NVB_BAND[algo], None if ms is None else ms.ctypes.data, int(min_score),
+                                             s.ctypes.data, si.ctypes.data, sj.ctypes.data)
+        assert rc == 0
+        return s, si, sj
 
     # ---- banded scoring and traceback (banded_inl.h, alignment_inl.h:361-467); ref=True runs the reference's own host code ----
     def banded_score(self, algo, type_, band, scheme, pattern, text, ref=False):

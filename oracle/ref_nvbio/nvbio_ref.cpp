@@ -16,21 +16,22 @@ const uint32 MAX_TEXT = 16384;
 typedef vector_view<const uint8*> str_t;
 
 template <typename aligner_t>
-int run(const aligner_t aligner, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n, int32_t* out) {
+int run(const aligner_t aligner, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n, int32_t* out, int32_t min_score, bool want_ok) {
     aln::BestSink<int32> sink;
-    aln::alignment_score<MAX_TEXT>(aligner, str_t(m, p), aln::trivial_quality_string(), str_t(n, t),
-                                   Field_traits<int32>::min(), sink);
+    const bool ok = aln::alignment_score<MAX_TEXT>(aligner, str_t(m, p), aln::trivial_quality_string(), str_t(n, t), min_score, sink);
     out[0] = sink.score;
     out[1] = int32_t(sink.sink.x);
     out[2] = int32_t(sink.sink.y);
+    if (want_ok) out[3] = ok ? 1 : 0;
     return 0;
 }
 
 template <aln::AlignmentType TYPE>
-int run_type(int algo, const int32_t* sc, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n, int32_t* out) {
-    if (algo == 0) return run(aln::make_gotoh_aligner<TYPE>(aln::SimpleGotohScheme(sc[0], sc[1], sc[2], sc[3])), p, m, t, n, out);
-    if (algo == 1) return run(aln::make_smith_waterman_aligner<TYPE>(aln::SimpleSmithWatermanScheme(sc[0], sc[1], sc[2], sc[3])), p, m, t, n, out);
-    if (algo == 2) return run(aln::make_edit_distance_aligner<TYPE>(), p, m, t, n, out);
+int run_type(int algo, const int32_t* sc, const uint8_t* p, uint32_t m, const uint8_t* t, uint32_t n, int32_t* out,
+             int32_t min_score = Field_traits<int32>::min(), bool want_ok = false) {
+    if (algo == 0) return run(aln::make_gotoh_aligner<TYPE>(aln::SimpleGotohScheme(sc[0], sc[1], sc[2], sc[3])), p, m, t, n, out, min_score, want_ok);
+    if (algo == 1) return run(aln::make_smith_waterman_aligner<TYPE>(aln::SimpleSmithWatermanScheme(sc[0], sc[1], sc[2], sc[3])), p, m, t, n, out, min_score, want_ok);
+    if (algo == 2) return run(aln::make_edit_distance_aligner<TYPE>(), p, m, t, n, out, min_score, want_ok);
     return -1;
 }
 }  // namespace
@@ -49,6 +50,17 @@ extern "C" int nvbio_ref_score(int algo, int type, const int32_t* scheme, const 
     return -1;
 }
 
+// the same call with a min_score threshold (the early exit of gotoh_inl.h:826-830 / sw_inl.h:699-701); out[3] = the function's bool result
+extern "C" int nvbio_ref_score_min(int algo, int type, const int32_t* scheme, const uint8_t* pattern, uint32_t m,
+                                   const uint8_t* text, uint32_t n, int32_t min_score, int32_t* out) {
+    if (n > MAX_TEXT) return -2;
+    switch (type) {
+        case 0: return run_type<aln::GLOBAL>(algo, scheme, pattern, m, text, n, out, min_score, true);
+        case 1: return run_type<aln::LOCAL>(algo, scheme, pattern, m, text, n, out, min_score, true);
+        case 2: return run_type<aln::SEMI_GLOBAL>(algo, scheme, pattern, m, text, n, out, min_score, true);
+    }
+    return -1;
+}
 
 // ---- banded scoring and traceback (round 2: the rest of SURVEY row f4) -------------------------------------------------
 //   aln::banded_alignment_score<BAND_LEN>( aligner, pattern, quals, text, min_score, sink )   (banded_inl.h:57-75)
