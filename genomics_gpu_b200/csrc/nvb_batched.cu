@@ -49,6 +49,7 @@ struct NvbArgs {
   uint2* scratch; uint32_t stride;                                     // band border (H, E) per text row: scratch[row * stride + thread] ...
   uint32_t rows_cap;                                                   // ... or, NVB_CTA_LAYOUT, scratch[(cta * rows_cap + row) * 128 + thread in cta]
   uint32_t* worklist; uint32_t* work_count;
+  const int32_t* min_scores; int32_t min_score;                        // k_nvb_i32<.., MINSC = true>: per-job thresholds (or NULL: min_score for every job)
 };
 
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t c) {
@@ -141,7 +142,13 @@ __device__ __forceinline__ bool reported_later(int i, int j, int bi, int bj, int
   return j > bj;
 }
 
-template <int TYPE, bool SINK>
+// MINSC: alignment_score's min_score threshold (alignment.h:456-530).  After each of the reference's bands of BAND_LEN = 1 <<
+// band_shift pattern columns except the last one, max_score = the maximum over the text rows of H(i, last column of the band); the
+// job gives up when max_score + (columns still to come) * match < min_score (gotoh_inl.h:826-830, sw_inl.h:699-701).  LOCAL keeps
+// what the bands processed so far reported; GLOBAL / SEMI_GLOBAL report from the last band only, so they return BestSink's initial
+// state: score -(1 << 30) (Field_traits<int32>::min()), sink (-1, -1).  This kernel's bands of 8 ARE the reference's for Gotoh;
+// for Smith-Waterman / edit distance (bands of 16) the check falls on every second band.
+template <int TYPE, bool SINK, bool MINSC = false>
 __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_worklist) {
   const uint32_t idx = blockIdx.x * kThreads + threadIdx.x;
   uint32_t job;
@@ -156,7 +163,10 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
   const int go_t = a.go_t, ge_t = a.ge_t, go_p = a.go_p, ge_p = a.ge_p, match = a.match, mismatch = a.mismatch;
 
   int best = INT_MIN, bi = -1, bj = -1;
+  const int min_score = MINSC ? (a.min_scores ? a.min_scores[job] : a.min_score) : 0;
+  const int ref_bands = (M + (1 << a.band_shift) - 1) >> a.band_shift;
   for (int block = 0; block < M; block += 8) {
+    int colmax = INT_MIN;                                                                   // MINSC: max over the rows of H(i, block + 8)
     int q[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) q[j] = (block + j < M) ? (int)P[block + j] : 256 + j;      // pad columns never match
@@ -188,6 +198,7 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
         H[j] = h;
       }
       if (!last) col[(size_t)(i - 1) * stride] = make_uint2((uint32_t)H[8], (uint32_t)e);
+      if (MINSC) colmax = max(colmax, H[8]);
       if (TYPE == NVBX_LOCAL) {
         int rowmax = INT_MIN;
 #pragma unroll
@@ -204,6 +215,14 @@ __global__ void __launch_bounds__(kThreads) k_nvb_i32(const NvbArgs a, int from_
         const int hM = select_reg(H, mj);
         if (TYPE == NVBX_SEMI_GLOBAL) { if (hM >= best) { best = hM; bi = i; bj = M; } }    // utils_inl.h:279-299, BestSink `<=`
         else if (i == N) { best = hM; bi = N; bj = M; }                                      // gotoh_inl.h:896-897
+      }
+    }
+    if (MINSC) {
+      const int done = block + 8;                                                            // pattern columns processed so far
+      if ((done & ((1 << a.band_shift) - 1)) == 0 && (done >> a.band_shift) < ref_bands &&
+          (long long)colmax + (long long)(M - done) * match < (long long)min_score) {
+        if (TYPE != NVBX_LOCAL) { best = -(1 << 30); bi = -1; bj = -1; }
+        break;
       }
     }
   }
@@ -584,6 +603,7 @@ struct nvbx_stream {
   int32_t *src_i = nullptr, *src_j = nullptr; uint32_t* n_ops = nullptr; uint8_t* ops = nullptr; uint32_t ops_stride = 0;
   bool have_tb = false;
   bool have_sinks = false, enacted = false;
+  int32_t* min_scores = nullptr; int32_t min_score = INT32_MIN; bool use_min_score = false;     // nvbx_stream_set_min_scores
   std::string kernel = "none";
 };
 
@@ -600,7 +620,7 @@ void nvbx_stream_destroy(nvbx_stream_t* s) {
   cudaFree(s->pbytes); cudaFree(s->tbytes); cudaFree(s->pflag); cudaFree(s->tflag); cudaFree(s->poffs); cudaFree(s->toffs);
   cudaFree(s->ppk); cudaFree(s->tpk); cudaFree(s->pair_p); cudaFree(s->pair_t); cudaFree(s->score); cudaFree(s->sink_i); cudaFree(s->sink_j);
   cudaFree(s->scratch); cudaFree(s->worklist); cudaFree(s->work_count);
-  cudaFree(s->dirs); cudaFree(s->src_i); cudaFree(s->src_j); cudaFree(s->n_ops); cudaFree(s->ops);
+  cudaFree(s->min_scores); cudaFree(s->dirs); cudaFree(s->src_i); cudaFree(s->src_j); cudaFree(s->n_ops); cudaFree(s->ops);
   if (s->e0) cudaEventDestroy(s->e0);
   if (s->e1) cudaEventDestroy(s->e1);
   delete s;
@@ -650,6 +670,21 @@ nvbx_stream_t* nvbx_stream_create(const nvbx_batch_t* b, void* cuda_stream) {
   return s;
 }
 
+int nvbx_stream_set_min_scores(nvbx_stream_t* s, const int32_t* per_job, int32_t uniform) {
+  if (!s) return fail("nvbx_stream_set_min_scores: NULL stream");
+  if (per_job) {
+    if (!s->min_scores) NVB_CHECK(cudaMalloc(&s->min_scores, 4 * (size_t)s->n_pairs));
+    NVB_CHECK(cudaMemcpyAsync(s->min_scores, per_job, 4 * (size_t)s->n_pairs, cudaMemcpyHostToDevice, s->st));
+    NVB_CHECK(cudaStreamSynchronize(s->st));                  // the caller's array may be pageable and short-lived
+    s->use_min_score = true;
+  } else {
+    if (s->min_scores) { cudaFree(s->min_scores); s->min_scores = nullptr; }
+    s->use_min_score = uniform != INT32_MIN;
+  }
+  s->min_score = uniform;
+  return 0;
+}
+
 int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks) {
   if (!s || !al) return fail("nvbx_stream_enact: NULL argument");
   if (al->type < NVBX_GLOBAL || al->type > NVBX_SEMI_GLOBAL) return fail("nvbx_stream_enact: unknown alignment type");
@@ -686,6 +721,42 @@ int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* al, int want_sinks
   // quad-strip kernel (nvb_strip.cuh): K2's blocking, no band-border scratch; scores of all three types, sinks of GLOBAL / SEMI_GLOBAL
   const bool strip = g_policy == 0 && wide && a.go_t == a.go_p && a.ge_t == a.ge_p &&
                      gb200::nvb_strip_eligible(al->type, a.match, -a.mismatch, -a.go_t, -a.ge_t, s->max_m, s->max_n, want_sinks);
+  if (s->use_min_score) {
+    // thresholds set: the band-of-8 int32 kernel, whose bands are the reference's (one thread per job, any alphabet, any costs)
+    a.min_scores = s->min_scores; a.min_score = s->min_score;
+    size_t chunk = ((size_t)1 << 28) / std::max<size_t>(1, s->max_n);
+    chunk = std::max<size_t>(256, chunk & ~(size_t)255);
+    chunk = std::min<size_t>(chunk, ((size_t)s->n_pairs + 255) & ~(size_t)255);
+    const size_t need = chunk * s->max_n;
+    if (need > s->scratch_elems) {
+      if (s->scratch) cudaFree(s->scratch);
+      s->scratch = nullptr; s->scratch_elems = 0;
+      if (cudaMalloc(&s->scratch, need * sizeof(uint2)) != cudaSuccess) { cudaGetLastError(); return fail("nvbx_stream_enact: cannot allocate the band-border scratch (text too long for this batch)"); }
+      s->scratch_elems = need;
+    }
+    a.scratch = s->scratch; a.stride = (uint32_t)chunk; a.rows_cap = s->max_n; a.sixteen = 16;
+    NVB_CHECK(cudaEventRecord(s->e0, s->st));
+    for (size_t first = 0; first < s->n_pairs; first += chunk) {
+      a.first = (uint32_t)first; a.count = (uint32_t)std::min<size_t>(chunk, s->n_pairs - first);
+      const uint32_t g = (a.count + kThreads - 1) / kThreads;
+      const int type = al->type;
+      if (want_sinks) {
+        if (type == NVBX_GLOBAL) k_nvb_i32<NVBX_GLOBAL, true, true><<<g, kThreads, 0, s->st>>>(a, 0);
+        else if (type == NVBX_LOCAL) k_nvb_i32<NVBX_LOCAL, true, true><<<g, kThreads, 0, s->st>>>(a, 0);
+        else k_nvb_i32<NVBX_SEMI_GLOBAL, true, true><<<g, kThreads, 0, s->st>>>(a, 0);
+      } else {
+        if (type == NVBX_GLOBAL) k_nvb_i32<NVBX_GLOBAL, false, true><<<g, kThreads, 0, s->st>>>(a, 0);
+        else if (type == NVBX_LOCAL) k_nvb_i32<NVBX_LOCAL, false, true><<<g, kThreads, 0, s->st>>>(a, 0);
+        else k_nvb_i32<NVBX_SEMI_GLOBAL, false, true><<<g, kThreads, 0, s->st>>>(a, 0);
+      }
+      g_launches += 1;
+      NVB_CHECK(cudaGetLastError());
+    }
+    NVB_CHECK(cudaEventRecord(s->e1, s->st));
+    s->have_sinks = want_sinks != 0; s->enacted = true; s->have_tb = false;
+    s->kernel = "int32-minscore";
+    return 0;
+  }
   const bool fast = strip || (fits && (!want_sinks || al->type != NVBX_LOCAL || local_keys) && (g_policy == 0 || g_policy == 2));
   a.sixteen = 16;
   gb200::NvbStripArgs sa{};

@@ -16,7 +16,7 @@ CODES, ASCII = 0, 1
 NVB_SYMBOLS = ["nvbx_stream_create", "nvbx_stream_enact", "nvbx_stream_results", "nvbx_stream_scores_device", "nvbx_stream_last_ms",
                "nvbx_stream_cells", "nvbx_stream_kernel", "nvbx_stream_destroy", "nvbx_batched_score_host", "nvbx_set_policy",
                "nvbx_kernel_launches", "nvbx_last_error", "nvbx_stream_enact_banded", "nvbx_stream_traceback", "nvbx_stream_ops_stride",
-               "nvbx_stream_alignments"]
+               "nvbx_stream_alignments", "nvbx_stream_set_min_scores"]
 OP_SUBSTITUTION, OP_INSERTION, OP_DELETION = 0, 1, 2      # aln::DirectionVector values a Backtracer sees (alignment_base.h:139-142)
 BAND_LENS = (3, 5, 7, 15, 31)                             # the reference's BatchedBandedAlignmentScore instantiations
 
@@ -58,6 +58,7 @@ def _lib() -> C.CDLL:
         lib.nvbx_stream_traceback.argtypes = [C.c_void_p, C.POINTER(AlignerT), C.c_int]; lib.nvbx_stream_traceback.restype = C.c_int
         lib.nvbx_stream_ops_stride.argtypes = [C.c_void_p]; lib.nvbx_stream_ops_stride.restype = C.c_uint32
         lib.nvbx_stream_alignments.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]; lib.nvbx_stream_alignments.restype = C.c_int
+        lib.nvbx_stream_set_min_scores.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]; lib.nvbx_stream_set_min_scores.restype = C.c_int
         lib.nvbx_set_policy.argtypes = [C.c_int]
         lib.nvbx_kernel_launches.restype = C.c_uint64
         lib.nvbx_last_error.restype = C.c_char_p
@@ -110,6 +111,15 @@ class Stream:
     def enact(self, al: AlignerT, want_sinks: bool = False) -> None:
         if _lib().nvbx_stream_enact(self._h, C.byref(al), 1 if want_sinks else 0) != 0:
             raise RuntimeError("nvbx_stream_enact: " + _lib().nvbx_last_error().decode())
+
+    def set_min_scores(self, per_job: Optional[np.ndarray] = None, uniform: int = -(1 << 31)) -> None:
+        """the reference's per-job context_type::min_score (batched.h:249): early-exit threshold of the following enact calls;
+        (None, INT32_MIN) switches it off"""
+        arr = None if per_job is None else np.ascontiguousarray(per_job, dtype=np.int32)
+        if arr is not None and arr.size != self.batch.n_pairs:
+            raise ValueError("set_min_scores: one threshold per job")
+        if _lib().nvbx_stream_set_min_scores(self._h, None if arr is None else arr.ctypes.data, int(uniform)) != 0:
+            raise RuntimeError("nvbx_stream_set_min_scores: " + _lib().nvbx_last_error().decode())
 
     def results(self, want_sinks: bool = False):
         n = self.batch.n_pairs

@@ -13,7 +13,7 @@
  * for a BestSink<int32> (sink_inl.h:36-60).  Plain pointers and sizes only; host pointers unless stated otherwise.
  *
  * Semantics (bit-exact with the reference's host code path for every job whose DP values stay inside the reference's
- * int16 column storage, min_score = INT32_MIN i.e. no early exit -- what sw-benchmark uses):
+ * int16 column storage; min_score defaults to INT32_MIN i.e. no early exit -- what sw-benchmark uses -- see nvbx_stream_set_min_scores):
  *   pattern = horizontal string j = 1..M, text = vertical string i = 1..N (gotoh/gotoh_inl.h:473-593)
  *   F(i,j) = max(F(i-1,j) + Ge, H(i-1,j) + Go);  E(i,j) = max(E(i,j-1) + Ge, H(i,j-1) + Go)
  *   H(i,j) = max(E, F, H(i-1,j-1) + (text[i] == pattern[j] ? match : mismatch)) [, 0 for LOCAL]
@@ -67,6 +67,14 @@ nvbx_stream_t* nvbx_stream_create(const nvbx_batch_t* batch, void* cuda_stream);
  * want_sinks != 0 also computes the BestSink coordinates (GLOBAL / SEMI_GLOBAL stay on the fast path, LOCAL uses the int32
  * kernel).  0, or -1 on invalid arguments. */
 int nvbx_stream_enact(nvbx_stream_t* s, const nvbx_aligner_t* aligner, int want_sinks);
+/* The reference's per-job `context_type::min_score` (batched.h:249; alignment.h:456-530 "threshold alignment score"): the DP of a job
+ * is given up after a band of BAND_LEN pattern columns (8 Gotoh, 16 Smith-Waterman / edit distance; never after the last one) once
+ * max_i H(i, last column of the band) + (columns still to come) * match < min_score (gotoh_inl.h:826-830, sw_inl.h:699-701).  A job
+ * that gives up returns what its sink held: LOCAL the best cell of the bands processed so far, GLOBAL / SEMI_GLOBAL BestSink's
+ * initial state (score -(1 << 30), sinks -1).  per_job: n_pairs host values, or NULL to use `uniform` for every job;
+ * (NULL, INT32_MIN) -- the default, what sw-benchmark passes -- switches the threshold off.  Applies to the following
+ * nvbx_stream_enact calls (full-matrix scoring), which then run on the band-of-8 int32 kernel ("int32-minscore"). */
+int nvbx_stream_set_min_scores(nvbx_stream_t* s, const int32_t* per_job, int32_t uniform);
 /* stream.output(i) for all i: wait for the last enact and copy scores (and sinks, if they were computed and the
  * pointers are non-NULL) to host arrays of n_pairs int32. */
 int nvbx_stream_results(nvbx_stream_t* s, int32_t* scores, int32_t* sink_text, int32_t* sink_pattern);

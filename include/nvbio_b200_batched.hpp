@@ -71,7 +71,8 @@ struct HostStringStream {
                    const uint8_t* texts, const uint32_t* text_offsets, uint32_t n_texts, int32_t* scores, int32_t* sink_text = nullptr,
                    int32_t* sink_pattern = nullptr, const uint32_t* pair_pattern = nullptr, const uint32_t* pair_text = nullptr,
                    int alphabet = NVBX_CODES)
-      : m_aligner(aligner), m_scores(scores), m_sink_text(sink_text), m_sink_pattern(sink_pattern), m_max_pattern(0), m_max_text(0) {
+      : m_aligner(aligner), m_scores(scores), m_sink_text(sink_text), m_sink_pattern(sink_pattern), m_max_pattern(0), m_max_text(0),
+        m_min_scores(nullptr), m_min_score(INT32_MIN) {
     m_batch.patterns = patterns; m_batch.pattern_offsets = pattern_offsets; m_batch.n_patterns = n_patterns;
     m_batch.texts = texts; m_batch.text_offsets = text_offsets; m_batch.n_texts = n_texts;
     m_batch.pair_pattern = pair_pattern; m_batch.pair_text = pair_text; m_batch.n_pairs = n_jobs; m_batch.alphabet = alphabet;
@@ -87,6 +88,9 @@ struct HostStringStream {
   nvbx_batch_t m_batch;
   int32_t *m_scores, *m_sink_text, *m_sink_pattern;
   uint32_t m_max_pattern, m_max_text;
+  // the reference's context_type::min_score (batched.h:249): per-job thresholds (n_jobs values) or one for every job; INT32_MIN = off
+  void set_min_scores(const int32_t* per_job, int32_t uniform = INT32_MIN) { m_min_scores = per_job; m_min_score = uniform; }
+  const int32_t* m_min_scores; int32_t m_min_score;
 };
 
 template <typename stream_type, typename algorithm_type = DeviceThreadScheduler>
@@ -97,6 +101,15 @@ struct BatchedAlignmentScore {
   // enact the batch execution (batched.h:330-334); ms (optional) = upload + pack, scoring, download in milliseconds
   void enact(stream_type stream, uint64_t /*temp_size*/ = 0u, uint8_t* /*temp*/ = nullptr, float* ms = nullptr) {
     const nvbx_aligner_t a = stream.aligner().pod();
+    if (stream.m_min_scores || stream.m_min_score != INT32_MIN) {        // thresholds: the stream form (create, set, enact, results)
+      nvbx_stream_t* h = nvbx_stream_create(&stream.m_batch, nullptr);
+      const bool sinks = stream.m_sink_text || stream.m_sink_pattern;
+      const bool ok = h && nvbx_stream_set_min_scores(h, stream.m_min_scores, stream.m_min_score) == 0 && nvbx_stream_enact(h, &a, sinks ? 1 : 0) == 0 &&
+                      nvbx_stream_results(h, stream.m_scores, stream.m_sink_text, stream.m_sink_pattern) == 0;
+      if (h) nvbx_stream_destroy(h);
+      if (!ok) throw std::runtime_error(std::string("BatchedAlignmentScore::enact: ") + nvbx_last_error());
+      return;
+    }
     if (nvbx_batched_score_host(&a, &stream.m_batch, stream.m_scores, stream.m_sink_text, stream.m_sink_pattern, ms) != 0)
       throw std::runtime_error(std::string("BatchedAlignmentScore::enact: ") + nvbx_last_error());
   }

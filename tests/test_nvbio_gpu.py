@@ -305,3 +305,33 @@ def test_quad_strip_kernel(orc, type_):
     want, _, _ = orc.batch(po.NVB_GOTOH, type_, GOTOH_SW, pats, poffs, texts, toffs)
     s, _, _, k = run(nvb.aligner(nvb.GOTOH, type_, *GOTOH_SW), nvb.Batch(pats, poffs, texts, toffs), policy=0)
     assert k == "s16x2" and np.array_equal(s, want)
+
+
+@pytest.mark.parametrize("algo,oalgo,scheme", [(nvb.GOTOH, po.NVB_GOTOH, GOTOH_SW), (nvb.SMITH_WATERMAN, po.NVB_SW, (2, -1, -2, -2)), (nvb.EDIT_DISTANCE, po.NVB_ED, ())])
+def test_min_score_early_exit(orc, algo, oalgo, scheme):
+    """the reference's per-job min_score threshold (batched.h:249, alignment.h:456-530; nvbx_stream_set_min_scores): jobs that give up
+    keep what their sink held; per-job and uniform thresholds; switching it off restores the fast path.  The restatement it is
+    compared with is pinned to the reference's host build (tests/test_nvbio_oracle.py::test_min_score_early_exit_equals_reference_host_path)."""
+    if _POLICY[0] != 0:
+        pytest.skip("one kernel serves the threshold: nothing to A/B")
+    pats, poffs, texts, toffs = synth.nvb_jobs(3000, 1, 200, 1, 300, seed=61)
+    pats = pats.copy(); pats[np.random.default_rng(7).integers(0, pats.size, 100)] = 4          # any alphabet
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    rng = np.random.default_rng(8)
+    with nvb.Stream(batch) as st:
+        for type_ in TYPES:
+            al = nvb.aligner(algo, type_, *scheme)
+            full, _, _ = orc.batch(oalgo, type_, scheme, pats, poffs, texts, toffs)
+            per_job = (full + rng.integers(-30, 30, full.size)).astype(np.int32)
+            for per, uni in ((per_job, 0), (None, 25), (None, -40), (None, 1 << 20)):
+                want, wi, wj = orc.batch_min(oalgo, type_, scheme, pats, poffs, texts, toffs, min_score=uni, min_scores=per)
+                st.set_min_scores(per, uni)
+                st.enact(al, True)
+                s, si, sj = st.results(True)
+                assert st.kernel() == "int32-minscore"
+                assert np.array_equal(s, want) and np.array_equal(si, wi) and np.array_equal(sj, wj), (type_, uni, np.nonzero(s != want)[0][:5])
+                assert (want != full).sum() > 20 or uni == -40 or (algo == nvb.EDIT_DISTANCE and type_ == nvb.LOCAL)     # (edit-distance LOCAL scores are all 0)
+            st.set_min_scores(None)                                                             # off again
+            st.enact(al)
+            s, _, _ = st.results()
+            assert st.kernel() != "int32-minscore" and np.array_equal(s, full)
