@@ -1293,6 +1293,7 @@ template <int ALGO, bool REV, bool NMASK, bool RARE>
 __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict__ HE, const uint8_t* __restrict__ V,
                                         const uint32_t (&rowA)[8], const uint32_t (&rowB)[8], const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
                                         const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8], const uint32_t (&hpinitA)[8], const uint32_t (&hpinitB)[8],
+                                        const uint32_t (&finitA)[8], const uint32_t (&finitB)[8],
                                         uint32_t neg_oe2, uint32_t neg2, uint32_t conv8, int bias_ext, uint32_t nsc2,
                                         int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, int col0 = 0) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
@@ -1363,9 +1364,9 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
       // lanes that just ran a phantom column (A.H: step 0; B.L: 0,1; B.H: 0,1,2) get their strip-start state back
 #pragma unroll
       for (int r = 0; r < 8; r++) {
-        if (k == 0) { st.pA[r] = prmt(st.pA[r], pinitA[r], 0x7610); st.fA[r] = prmt(st.fA[r], neg2, 0x7610); if (SEMI) st.glA[r] = prmt(st.glA[r], hpinitA[r], 0x7610); }
-        if (k <= 1) { st.pB[r] = pinitB[r]; st.fB[r] = neg2; if (SEMI) st.glB[r] = hpinitB[r]; }
-        else { st.pB[r] = prmt(st.pB[r], pinitB[r], 0x7610); st.fB[r] = prmt(st.fB[r], neg2, 0x7610); if (SEMI) st.glB[r] = prmt(st.glB[r], hpinitB[r], 0x7610); }
+        if (k == 0) { st.pA[r] = prmt(st.pA[r], pinitA[r], 0x7610); st.fA[r] = prmt(st.fA[r], finitA[r], 0x7610); if (SEMI) st.glA[r] = prmt(st.glA[r], hpinitA[r], 0x7610); }
+        if (k <= 1) { st.pB[r] = pinitB[r]; st.fB[r] = finitB[r]; if (SEMI) st.glB[r] = hpinitB[r]; }
+        else { st.pB[r] = prmt(st.pB[r], pinitB[r], 0x7610); st.fB[r] = prmt(st.fB[r], finitB[r], 0x7610); if (SEMI) st.glB[r] = prmt(st.glB[r], hpinitB[r], 0x7610); }
       }
     }
     const int li = k - kq;
@@ -1404,8 +1405,10 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
                                           const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8],
                                           uint32_t neg_oe2, uint32_t neg_ext2,
                                           int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, uint32_t nsc2 = 0,
-                                          int col0 = 0, bool closed_left = false, const uint32_t* hpA = nullptr, const uint32_t* hpB = nullptr) {
-  // hpA / hpB (nvb_strip.cuh, GLOBAL): H of the left boundary column per strip row and lane, biased, instead of the free column
+                                          int col0 = 0, bool closed_left = false, const uint32_t* hpA = nullptr, const uint32_t* hpB = nullptr,
+                                          const uint32_t* fpA = nullptr, const uint32_t* fpB = nullptr) {
+  // hpA / hpB (nvb_strip.cuh GLOBAL; charged left column of the semi-global HEAD variants): H of the left boundary column per strip
+  // row and lane, biased, instead of the free column; fpA / fpB: F of that column (default: -infinity)
   // col0 / closed_left (pruned start pass): HE / V point at column col0 of the matrix (kq is relative to it; the frame of the parked
   // values is absolute, so only the un-biasing of the scanned column needs col0), and what lies left of it reads as -infinity
   // instead of the free left column.
@@ -1419,21 +1422,22 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
   // (r - 1) ext; the diagonal inputs (pinit) carry (r - 2) ext.  The -infinity floors stay unbiased: they only ever lose a max.
   const int bias_ext = -lane_lo(neg_ext2);
   const uint32_t conv8 = splat16(-8 * bias_ext);
-  uint32_t hpinitA[8], hpinitB[8], pA0[8], pB0[8];
+  uint32_t hpinitA[8], hpinitB[8], finitA[8], finitB[8], pA0[8], pB0[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
     const uint32_t hp = closed_left ? neg2 : (SEMI ? splat16((r - 1) * bias_ext) : neg_oe2);
     hpinitA[r] = hpA ? hpA[r] : hp; hpinitB[r] = hpB ? hpB[r] : hp;
+    finitA[r] = fpA ? fpA[r] : neg2; finitB[r] = fpB ? fpB[r] : neg2;
     pA0[r] = closed_left ? neg2 : pinitA[r]; pB0[r] = closed_left ? neg2 : pinitB[r];
   }
   NcState st;
 #pragma unroll
-  for (int r = 0; r < 8; r++) { st.pA[r] = pA0[r]; st.fA[r] = neg2; st.glA[r] = hpinitA[r]; st.pB[r] = pB0[r]; st.fB[r] = neg2; st.glB[r] = hpinitB[r]; }
+  for (int r = 0; r < 8; r++) { st.pA[r] = pA0[r]; st.fA[r] = finitA[r]; st.glA[r] = hpinitA[r]; st.pB[r] = pB0[r]; st.fB[r] = finitB[r]; st.glB[r] = hpinitB[r]; }
   st.h8A = 0; st.eoA = 0; st.h8B = 0; st.eoB = 0;
   st.prevsh = 0xCC00u; st.selB = 0xCCCCu; st.selA_prev = 0xCCCCu;
   st.he = HE[kFastThreads]; st.v = V[kFastThreads];
   st.ncm_prev = 0; st.mB = 0; st.mA_prev = 0;
-#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pA0, pB0, hpinitA, hpinitB, neg_oe2, neg2, conv8, bias_ext, nsc2, \
+#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pA0, pB0, hpinitA, hpinitB, finitA, finitB, neg_oe2, neg2, conv8, bias_ext, nsc2, \
                                                            kq, rowbase, tlen, caplane, caprow, tr, col0)
 #if GB200_NC_SPLIT
   // segments: rare [0, r0e) -- hot [r0e, h0e) -- rare [h0e, r1e) -- hot [r1e, nsteps)
@@ -1511,7 +1515,8 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const uint32_t delta = ((uint32_t)(a.match + 2 * a.gap_extend) ^ (uint32_t)(-a.mismatch + 2 * a.gap_extend)) & 0xFFu;
   const uint32_t neg_oe2 = splat16(-a.gap_open), neg_ext2 = splat16(-a.gap_extend);      // gap OPEN only: extension is free in the biased frame
   const uint32_t nval = a.n_value, nsc2 = splat16(a.n_score + 2 * a.gap_extend), nsc4 = ((uint32_t)(a.n_score + 2 * a.gap_extend) & 0xFFu) * 0x01010101u;
-  const bool top_zero = (a.head == SKIP_BOTH);          // HEAD in {QUERY,BOTH}: free top row (:87)
+  const bool top_zero = (a.head == SKIP_BOTH || a.head == SKIP_QUERY);          // HEAD in {QUERY,BOTH}: free top row (:87)
+  const bool head_t = (a.head == SKIP_TARGET || a.head == SKIP_BOTH);           // HEAD in {TARGET,BOTH}: free left column (:114-121)
   const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
 
   bool odd = top_zero ? nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval)
@@ -1524,6 +1529,26 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   uint32_t pinit[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) pinit[r] = splat16((r - 2) * a.gap_extend);   // HEAD in {TARGET,BOTH}: free left column, diag H(r-1,-1) = 0 (:114-121), biased
+  // HEAD in {NONE,QUERY}: the left column is charged (:123-128): H(t, -1) = -(o + e t), and the diagonal input of row t in column 0 is
+  // the SAME value (0 for t = 0), not H(t - 1, -1) -- t counted from the first strip of the PASS (the start pass restarts the count).
+  // The sweep takes the diagonal input of strip row r from the left neighbour of row r - 1, so the left-neighbour column it is given
+  // is the DIAGONAL column shifted up by one row (entry r = the diagonal input of row r + 1 = -(o + e (t + 1))), row 0's diagonal
+  // comes through pinit, and what the true left neighbour contributes to column 0 -- F(t, 0) = H(t, -1) - oe -- is handed over as
+  // the F of the boundary column.  Biased frame: the diagonal input sits in the frame of (row r - 1, column -1), left neighbour and
+  // F in (row r, column -1); F(t, 0) + r e = [H(t, -1) + (r - 1) e] - open.
+  auto left_column = [&](int t0, uint32_t (&pA)[8], uint32_t (&pB)[8], uint32_t (&hA)[8], uint32_t (&hB)[8], uint32_t (&fA)[8], uint32_t (&fB)[8]) {
+    const int o = a.gap_open, ext = a.gap_extend;
+#pragma unroll
+    for (int r = 0; r < 8; r++) {
+      const int t = t0 + r, fd = (r - 2) * ext, fh = (r - 1) * ext;
+      pA[r] = pack2((t == 0 ? 0 : -(o + ext * t)) + fd, -(o + ext * (t + 8)) + fd);
+      pB[r] = pack2(-(o + ext * (t + 16)) + fd, -(o + ext * (t + 24)) + fd);
+      hA[r] = pack2(-(o + ext * (t + 1)) + fh, -(o + ext * (t + 9)) + fh);
+      hB[r] = pack2(-(o + ext * (t + 17)) + fh, -(o + ext * (t + 25)) + fh);
+      fA[r] = pack2(-(o + ext * t) + fh - o, -(o + ext * (t + 8)) + fh - o);
+      fB[r] = pack2(-(o + ext * (t + 16)) + fh - o, -(o + ext * (t + 24)) + fh - o);
+    }
+  };
 
   NcTrack tr; tr.best = kMinusInf; tr.y = (int)qlen; tr.stop = 0; tr.cap = 0;       // :63-64
   const int NQ = (TR + 3) >> 2;
@@ -1534,7 +1559,13 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
     quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
-    nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr, nsc2);
+    if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr, nsc2);
+    else {
+      uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
+      left_column(32 * j, pA, pB, hA, hB, fA, fB);
+      nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr, nsc2, 0, false,
+                                                hA, hB, fA, fB);
+    }
   }
   a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = (int)tlen;            // query_batch_end = ref_len (Q8)
 
@@ -1556,7 +1587,7 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     // HEAD == BOTH has a free top row: no bound, no pruning.  (slack is warp-uniform, the maximum over the converged lanes.)
     const int mstep = NMASK ? max(a.match, a.n_score) : a.match;
     int slack = ncol;
-    if (GB200_PRUNE_REVERSE && !top_zero && mstep + a.gap_extend > 0) {
+    if (GB200_PRUNE_REVERSE && !top_zero && head_t && mstep + a.gap_extend > 0) {       // (a charged left column has no such bound either)
       const int num = mstep * (int)qlen - fwd - a.gap_open + a.gap_extend;
       slack = (int)__reduce_max_sync(__activemask(), (unsigned)max(num, 0) / (unsigned)(mstep + a.gap_extend));
       // The bound pass cannot reach the forward score when the forward path starts with a gap on the top boundary (the reversed DP
@@ -1600,8 +1631,14 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
         // that get there only see values below the forward score, which never decide the result
         const int c_lo = (slack < ncol) ? min(max(row_lo - slackL, 0) & ~3, c_max) : 0;
         const int ns = ((lim < ncol) ? lim + 2 + (int)fa.one : nsteps) - c_lo;
-        nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE + (size_t)c_lo * kFastThreads, V + (size_t)c_lo * kFastThreads, ns, rowA, rowB, rowC, rowD, pinit, pinit,
-                                                 neg_oe2, neg_ext2, (int)qlen - 1 - c_lo, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2, c_lo, c_lo > 0);
+        if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE + (size_t)c_lo * kFastThreads, V + (size_t)c_lo * kFastThreads, ns, rowA, rowB, rowC, rowD, pinit, pinit,
+                                                             neg_oe2, neg_ext2, (int)qlen - 1 - c_lo, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2, c_lo, c_lo > 0);
+        else {
+          uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
+          left_column(row_lo, pA, pB, hA, hB, fA, fB);                                  // rows counted from the first strip of this pass
+          nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
+                                                   0, false, hA, hB, fA, fB);
+        }
         lim = min(ncol, lim + 32);
       }
       if (rt.best >= fwd || slack >= ncol) break;
@@ -1610,6 +1647,19 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     a.t_start[tid] = ((int)tlen - 1) - rt.y;                                          // :380-381
     a.q_start[tid] = ((int)qlen - 1) - (int)tlen;
   }
+}
+
+// SEMI_GLOBAL with TAIL = NONE: neither the last query column nor the last target row is ever scanned (semiglobal_kernel_template.h:
+// the scans of :160-178 and :185-216 are the only writers of maxHH), so every pair reports the initial state of the reference's
+// trackers: score MINUS_INF, target end = read_len, query end = ref_len (:63-64); the start pass stops before its first strip
+// (:301: maxHH >= the "forward score") and reports ref_len - 1 and read_len - 1 - ref_len (:380-381).  No DP runs.
+template <int START>
+__global__ void __launch_bounds__(256) k_semiglobal_tail_none(const DpArgs a) {
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid >= (uint32_t)a.n) return;
+  const int qlen = (int)a.q_lens[tid], tlen = (int)a.t_lens[tid];
+  a.score[tid] = kMinusInf; a.t_end[tid] = qlen; a.q_end[tid] = tlen;
+  if (START == START_POS) { a.t_start[tid] = tlen - 1; a.q_start[tid] = qlen - 1 - tlen; }
 }
 
 __global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) {
@@ -1720,10 +1770,14 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
     return (uint64_t)std::min(q8, t8) * (uint64_t)a.match <= 4000;
   }
   if (algo == ALGO_SEMI_GLOBAL) {
-    // default read-vs-window shape only (free target head/tail); the other 14 head/tail variants use the general kernel
-    if (a.tail != SKIP_TARGET || !(a.head == SKIP_TARGET || a.head == SKIP_BOTH)) return false;
-    // every H/E/F is >= -(2*oe + ext*(q8+2) + mismatch) and <= q8*match: keep both well inside (kNegSafe, 32767)
-    if (2 * oe + (int64_t)a.gap_extend * (q8 + 2) + a.mismatch + 64 > 12000) return false;
+    // TAIL = TARGET (scan of the last query column) with any HEAD, and TAIL = NONE (nothing is ever scanned: the reference's result is
+    // its initial state, k_semiglobal_tail_none); TAIL in {QUERY, BOTH} (scan of the last padded target row) uses the general kernel
+    if (a.tail == SKIP_NONE) return true;
+    if (a.tail != SKIP_TARGET) return false;
+    const bool head_t = (a.head == SKIP_TARGET || a.head == SKIP_BOTH);
+    // every H/E/F is >= -(2*oe + ext*(q8+2) + mismatch) and <= q8*match: keep both well inside (kNegSafe, 32767); a charged left
+    // column (HEAD in {NONE, QUERY}) adds ext * t8
+    if (2 * oe + (int64_t)a.gap_extend * (q8 + 2 + (head_t ? 0 : t8 + 32)) + a.mismatch + 64 > 12000) return false;
     // the biased frame adds up to (q8 + 16) * ext to every value, and the substitution bytes carry + 2 ext
     if (a.match + 2 * a.gap_extend > 127) return false;
     return (int64_t)q8 * a.match + (int64_t)(q8 + 24) * a.gap_extend <= 30000;
@@ -1742,6 +1796,11 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
 #endif
 int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, bool maybe_odd, int force_passes, cudaStream_t str) {
   int algo = algo_in;
+  if (algo == ALGO_SEMI_GLOBAL && a.tail == SKIP_NONE) {
+    const uint32_t g = ((uint32_t)a.n + 255u) / 256u;
+    if (start == START_POS) k_semiglobal_tail_none<START_POS><<<g, 256, 0, str>>>(a); else k_semiglobal_tail_none<START_NONE><<<g, 256, 0, str>>>(a);
+    return 1;
+  }
   const bool passes = maybe_odd || force_passes;        // false: nothing but A/C/G/T in this batch (host packer): one launch, no lists
   const uint32_t q8 = (max_q + 7u) & ~7u;
   if (fs.cap < (size_t)a.n) {

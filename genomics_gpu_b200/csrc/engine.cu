@@ -621,7 +621,7 @@ static bool launch_dp_mixed(gasal_gpu_storage_t* s, uint32_t n, const gasal_para
   Priv* pv = priv(s);
   const int algo = params->algo, start = params->start_pos;
   if (g_kernel_policy != 0 || params->secondBest || start == WITH_TB) return false;
-  if (!(algo == LOCAL || algo == SEMI_GLOBAL || algo == GLOBAL)) return false;
+  if (!(algo == LOCAL || algo == SEMI_GLOBAL || algo == GLOBAL || algo == BANDED)) return false;      // (BANDED: short class on the s16x2 banded sweep, long class on the int32 banded kernel)
   if (round8(shape.max_q) <= kFastMaxQ8 || round8(shape.min_q) > kFastMaxQ8 || n < 2) return false;   // all short or all long
   const uint32_t* ql = s->host_query_batch_lens; const uint32_t* tl = s->host_target_batch_lens;
   BatchShape sh[2];

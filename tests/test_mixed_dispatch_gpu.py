@@ -61,6 +61,15 @@ def test_mixed_global(oracle):
     assert_same(got, want, ["aln_score"], "mixed global")
 
 
+def test_mixed_banded(oracle):
+    """BANDED score/end: the short class on the s16x2 banded sweep, the long class on the int32 banded kernel"""
+    b = mixed_batch(6350, n_short=1200, n_long=25)
+    want = oracle_align(oracle, b, algo=po.BANDED, k_band=48, max_query_len=4096)
+    got = run(b, algo=capi.BANDED, k_band=48)
+    assert got["_kernel"] == "mixed(s16x2+int32)", got["_kernel"]
+    assert_same(got, want, K3, "mixed banded")
+
+
 def test_one_long_read_does_not_take_a_short_read_batch_off_the_fast_path(oracle):
     """20,000 short pairs + ONE 5 kb pair: the short pairs stay on the s16x2 kernel"""
     rng = np.random.default_rng(7)

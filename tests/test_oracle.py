@@ -84,6 +84,22 @@ def test_oracle_matches_reference_live(oracle, seed):
 
 
 @pytest.mark.skipif(not po.RefHost.available(1024), reason="oracle/_ref host build of the reference not present")
+@pytest.mark.parametrize("head", [po.NONE, po.QUERY, po.TARGET, po.BOTH])
+def test_oracle_matches_reference_all_head_tail(oracle, head):
+    """all 16 semiglobal_skipping_head / _tail variants (semiglobal_kernel_template.h:39-388) with start positions: the restatement
+    against the reference's own kernels compiled for the host, incl. reads with N"""
+    ref = po.RefHost(1024)
+    b = synth.random_ragged_pairs(160, 9, 200, 9, 330, seed=300 + head, n_frac=0.05)
+    pq, pt = oracle.pack(b.q_bytes), oracle.pack(b.t_bytes)
+    for tail in (po.NONE, po.QUERY, po.TARGET, po.BOTH):
+        for sc in [(1, 4, 6, 1), (2, 3, 5, 2)]:
+            kw = dict(algo=po.SEMI_GLOBAL, head=head, tail=tail, start=po.WITH_START)
+            want = ref.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, scoring=sc, **kw)
+            got = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, scoring=sc, max_query_len=1024, **kw)
+            assert_same(got, want, K5, f"head {head} tail {tail} {sc}")
+
+
+@pytest.mark.skipif(not po.RefHost.available(1024), reason="oracle/_ref host build of the reference not present")
 @pytest.mark.parametrize("scoring", [(1, 4, 6, 1), (2, 3, 5, 2), (1, 1, 0, 1), (3, 2, 8, 0)])
 def test_oracle_matches_reference_on_overhanging_reads(oracle, scoring):
     """reads that hang off their window / long gaps / zero gap costs: the shapes the GPU start-pass pruning is tested on
