@@ -1189,7 +1189,27 @@ struct NcTrack {
   int cap;              // global: captured H(tlen-1, qlen-1)
   int tie = 0;          // 1: a later row with the SAME score replaces the record (nvbio's BestSink, nvb_strip.cuh); 0: strict '>' (GASAL2)
   int capture = 0;      // 1: the H-based (semi-global) recurrence captures (caplane, caprow) instead of scanning the column (nvbio GLOBAL)
+  int last = 0;         // start pass: highest lane of the quad-strip whose strip the reference would still have processed (its scan ran)
 };
+// TAIL in {QUERY, BOTH} (semiglobal_kernel_template.h:185-216): the reference scans the bottom row of the LAST PROCESSED strip over the
+// query columns, strict '>' left to right.  Which strip that is may only be known after the sweep (the start pass stops between
+// strips), so the sweep keeps, for each of its four lanes, the first maximum of that lane's bottom row over the true query columns.
+struct NcBottom {
+  LaneBest a, b;              // running (value, step) per lane: a = lanes A.L / A.H, b = B.L / B.H; values un-biased
+  uint32_t biasA, biasB;      // frame bias of the bottom rows at the current step: (column + 7) ext per lane
+  int nq;                     // true query columns from the sweep's first column on
+};
+__device__ __forceinline__ void ncbottom_init(NcBottom& bt, int col0, int qlen, int ext) {
+  bt.a.bestK7 = bt.b.bestK7 = 0x80008000u; bt.a.keyL = bt.a.keyH = bt.b.keyL = bt.b.keyH = 0; bt.a.posL = bt.a.posH = bt.b.posL = bt.b.posH = 0;
+  bt.biasA = pack2((col0 + 7) * ext, (col0 + 6) * ext); bt.biasB = pack2((col0 + 5) * ext, (col0 + 4) * ext);
+  bt.nq = qlen - col0;
+}
+// (value, column) of lane i after the sweep
+__device__ __forceinline__ void ncbottom_get(const NcBottom& bt, int lane, int col0, int& v, int& col) {
+  const LaneBest& lb = (lane & 2) ? bt.b : bt.a;
+  v = (lane & 1) ? lane_hi(lb.bestK7) : lane_lo(lb.bestK7);
+  col = col0 + (int)((lane & 1) ? lb.posH : lb.posL) - lane;
+}
 
 template <int ALGO, bool REV>
 __device__ __forceinline__ void nc_sweep(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
@@ -1289,13 +1309,13 @@ struct NcState {
 };
 
 // one step (one query column per lane) of the quad-strip sweep; RARE adds the per-step work that only a handful of steps need
-template <int ALGO, bool REV, bool NMASK, bool RARE>
+template <int ALGO, bool REV, bool NMASK, bool RARE, bool BROW = false>
 __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict__ HE, const uint8_t* __restrict__ V,
                                         const uint32_t (&rowA)[8], const uint32_t (&rowB)[8], const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
                                         const uint32_t (&pinitA)[8], const uint32_t (&pinitB)[8], const uint32_t (&hpinitA)[8], const uint32_t (&hpinitB)[8],
                                         const uint32_t (&finitA)[8], const uint32_t (&finitB)[8],
                                         uint32_t neg_oe2, uint32_t neg2, uint32_t conv8, int bias_ext, uint32_t nsc2,
-                                        int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, int col0 = 0) {
+                                        int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, int col0 = 0, NcBottom* bt = nullptr) {
   constexpr bool SEMI = (ALGO == ALGO_SEMI_GLOBAL);
   const uint32_t selA = st.v | st.prevsh;
   st.prevsh = st.v * 256u + 0x4400u;
@@ -1354,6 +1374,17 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
       hhB[r] = h; if (!SEMI) st.pB[r] = upB; upB = h;
     }
   }
+  if (BROW) {
+    // first maximum of each lane's bottom row over the true query columns (lane i is on column col0 + k - i)
+    uint32_t vA = __vsub2(upA, bt->biasA), vB = __vsub2(upB, bt->biasB);
+    const uint32_t e2 = splat16(bias_ext), nq = (uint32_t)bt->nq;
+    bt->biasA = __vadd2(bt->biasA, e2); bt->biasB = __vadd2(bt->biasB, e2);
+    const uint32_t kA = ((uint32_t)k < nq ? 0x0000FFFFu : 0u) | ((uint32_t)(k - 1) < nq ? 0xFFFF0000u : 0u);
+    const uint32_t kB = ((uint32_t)(k - 2) < nq ? 0x0000FFFFu : 0u) | ((uint32_t)(k - 3) < nq ? 0xFFFF0000u : 0u);
+    vA = (vA & kA) | (0x80008000u & ~kA); vB = (vB & kB) | (0x80008000u & ~kB);
+    track_update(bt->a, vA, vA, (uint32_t)k);
+    track_update(bt->b, vB, vB, (uint32_t)k);
+  }
   upA = __vadd2(upA, conv8); eA = __vadd2(eA, conv8); upB = __vadd2(upB, conv8); eB = __vadd2(eB, conv8);   // bottom row -> next strip's frame
   HE[(k - 2) * kFastThreads] = prmt(upB, eB, 0x7632);
   st.h8A = upA; st.eoA = eA; st.h8B = upB; st.eoB = eB;
@@ -1382,6 +1413,7 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
         // pass stops between strips once the forward score is reached (:301)
         if (!REV || li == 0 || tr.best < tr.stop) {
           const int rb = rowbase + 8 * li;
+          if (rb < tlen) tr.last = li;
 #pragma unroll
           for (int r = 0; r < 8; r++) if (rb + r < tlen && hv[r] > tr.best - tr.tie) { tr.best = hv[r]; tr.y = rb + r; }
         }
@@ -1398,7 +1430,7 @@ __device__ __forceinline__ void nc_step(NcState& st, int k, uint32_t* __restrict
 // the last true query column / the global capture, steps kq..kq+3) runs in loops of its own, so the hot loop carries no rare code
 // and can be unrolled (the diagonal / H rotations become register renaming).
 //   kq      : step at which lane A.L is on the scanned / captured column (qlen - 1); lane i is there at step kq + i
-template <int ALGO, bool REV, bool NMASK = false>
+template <int ALGO, bool REV, bool NMASK = false, bool BROW = false>
 __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8_t* __restrict__ V, int nsteps,
                                           const uint32_t (&rowA)[8], const uint32_t (&rowB)[8],
                                           const uint32_t (&rowC)[8], const uint32_t (&rowD)[8],
@@ -1406,7 +1438,7 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
                                           uint32_t neg_oe2, uint32_t neg_ext2,
                                           int kq, int rowbase, int tlen, int caplane, int caprow, NcTrack& tr, uint32_t nsc2 = 0,
                                           int col0 = 0, bool closed_left = false, const uint32_t* hpA = nullptr, const uint32_t* hpB = nullptr,
-                                          const uint32_t* fpA = nullptr, const uint32_t* fpB = nullptr) {
+                                          const uint32_t* fpA = nullptr, const uint32_t* fpB = nullptr, NcBottom* bt = nullptr) {
   // hpA / hpB (nvb_strip.cuh GLOBAL; charged left column of the semi-global HEAD variants): H of the left boundary column per strip
   // row and lane, biased, instead of the free column; fpA / fpB: F of that column (default: -infinity)
   // col0 / closed_left (pruned start pass): HE / V point at column col0 of the matrix (kq is relative to it; the frame of the parked
@@ -1437,8 +1469,8 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
   st.prevsh = 0xCC00u; st.selB = 0xCCCCu; st.selA_prev = 0xCCCCu;
   st.he = HE[kFastThreads]; st.v = V[kFastThreads];
   st.ncm_prev = 0; st.mB = 0; st.mA_prev = 0;
-#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_>(st, K_, HE, V, rowA, rowB, rowC, rowD, pA0, pB0, hpinitA, hpinitB, finitA, finitB, neg_oe2, neg2, conv8, bias_ext, nsc2, \
-                                                           kq, rowbase, tlen, caplane, caprow, tr, col0)
+#define NC_STEP(RARE_, K_) nc_step<ALGO, REV, NMASK, RARE_, BROW>(st, K_, HE, V, rowA, rowB, rowC, rowD, pA0, pB0, hpinitA, hpinitB, finitA, finitB, neg_oe2, neg2, conv8, bias_ext, nsc2, \
+                                                                 kq, rowbase, tlen, caplane, caprow, tr, col0, bt)
 #if GB200_NC_SPLIT
   // segments: rare [0, r0e) -- hot [r0e, h0e) -- rare [h0e, r1e) -- hot [r1e, nsteps)
   const int r0e = min(3, nsteps);
@@ -1497,7 +1529,9 @@ __device__ __forceinline__ bool target_has_odd_base(const uint32_t* tw, uint32_t
   return target_odd_scan(tw, tlen, TR);
 }
 
-template <int START, bool NMASK = false>
+// TAILQ: TAIL in {QUERY, BOTH} -- the bottom row of the last processed (padded) strip is scanned as well (NcBottom); its own
+// instantiations, so that the default kernels carry none of it.
+template <int START, bool NMASK = false, bool TAILQ = false>
 __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
@@ -1551,6 +1585,9 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   };
 
   NcTrack tr; tr.best = kMinusInf; tr.y = (int)qlen; tr.stop = 0; tr.cap = 0;       // :63-64
+  NcBottom bot;
+  const bool tail_t = !TAILQ || a.tail == SKIP_BOTH;                                // the last query column is scanned (:160-178)
+  const int kq_scan = tail_t ? (int)qlen - 1 : -1000;
   const int NQ = (TR + 3) >> 2;
   for (int j = 0; j < NQ; j++) {
     uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
@@ -1558,16 +1595,31 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;
     const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
-    quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
-    if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr, nsc2);
+    quad_tables<NMASK || TAILQ>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);   // TAILQ: the pad rows of the last strip count, and the pads are N
+    if (TAILQ && j == NQ - 1) {
+      // last quad-strip: keep the first maximum of every lane's bottom row (the lane of strip TR - 1 is read below)
+      uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
+      if (!head_t) left_column(32 * j, pA, pB, hA, hB, fA, fB);
+      ncbottom_init(bot, 0, (int)qlen, a.gap_extend);
+      if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2,
+                                                                  0, false, nullptr, nullptr, nullptr, nullptr, &bot);
+      else nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2,
+                                                           0, false, hA, hB, fA, fB, &bot);
+    } else if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2);
     else {
       uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
       left_column(32 * j, pA, pB, hA, hB, fA, fB);
-      nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, (int)qlen - 1, 32 * j, (int)tlen, 0, 0, tr, nsc2, 0, false,
+      nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2, 0, false,
                                                 hA, hB, fA, fB);
     }
   }
-  a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = (int)tlen;            // query_batch_end = ref_len (Q8)
+  int tr_x = (int)tlen;                                                             // query_batch_end = ref_len unless the bottom-row scan finds a column (Q8)
+  if (TAILQ) {                                                                      // :185-216, strict '>' after the column scan; :214 `if (maxXY_x != ref_len)`
+    int v, m; ncbottom_get(bot, (TR - 1) & 3, 0, v, m);
+    if (v > tr.best) { tr.best = v; tr_x = m; }
+    if (tr_x != (int)tlen) tr.y = (int)qlen;
+  }
+  a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = tr_x;
 
   if (START == START_POS) {
     // start pass (:227-384): the same DP over the TRUE-LENGTH reversed sequences, from the strip that holds the
@@ -1587,7 +1639,7 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     // HEAD == BOTH has a free top row: no bound, no pruning.  (slack is warp-uniform, the maximum over the converged lanes.)
     const int mstep = NMASK ? max(a.match, a.n_score) : a.match;
     int slack = ncol;
-    if (GB200_PRUNE_REVERSE && !top_zero && head_t && mstep + a.gap_extend > 0) {       // (a charged left column has no such bound either)
+    if (GB200_PRUNE_REVERSE && !TAILQ && !top_zero && head_t && mstep + a.gap_extend > 0) {       // (a charged left column / a bottom-row scan: no such bound either)
       const int num = mstep * (int)qlen - fwd - a.gap_open + a.gap_extend;
       slack = (int)__reduce_max_sync(__activemask(), (unsigned)max(num, 0) / (unsigned)(mstep + a.gap_extend));
       // The bound pass cannot reach the forward score when the forward path starts with a gap on the top boundary (the reversed DP
@@ -1614,24 +1666,40 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     }
     const int c_max = (int)((qlen - 1) & ~3u);                                          // the scanned column stays inside every window
     NcTrack rt;
+    int bot_v = 0, bot_m = 0;
     for (int attempt = 0; attempt < 2; attempt++) {
       const int lim0 = min(ncol, (32 + slack + 3) & ~3);
       if (top_zero) nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval);
       else nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 2, a.gap_open, a.gap_extend, nval, lim0 < ncol ? lim0 : 0x7FFFFFFF);
       rt.best = kMinusInf; rt.y = 0; rt.stop = fwd; rt.cap = 0;                         // :275-276
       int lim = lim0, row_lo = 0;
+      // TAILQ: bottom row of the last strip the reference processes; no strip at all: the top boundary, whose first maximum is column 0, value 0
+      if (TAILQ) { bot_v = 0; bot_m = 0; }
       for (uint32_t i = gend_reg; i < (uint32_t)TR && rt.best < fwd; i += 4, row_lo += 32) {
         uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
         const uint32_t wa = rev_true_word(tw, (int)tlen, (int)i);
         const uint32_t wb = (i + 1 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 1) : 0u;
         const uint32_t wc = (i + 2 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 2) : 0u;
         const uint32_t wd = (i + 3 < (uint32_t)TR) ? rev_true_word(tw, (int)tlen, (int)i + 3) : 0u;
-        quad_tables<NMASK>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);
+        quad_tables<NMASK || TAILQ>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);   // TAILQ: the pad rows of the last strip count, and the pads are N
         // a truncated sweep computes the columns < lim in all four lanes; if it stops on the scanned column (qlen - 1 >= lim) the lanes
         // that get there only see values below the forward score, which never decide the result
         const int c_lo = (slack < ncol) ? min(max(row_lo - slackL, 0) & ~3, c_max) : 0;
         const int ns = ((lim < ncol) ? lim + 2 + (int)fa.one : nsteps) - c_lo;
-        if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE + (size_t)c_lo * kFastThreads, V + (size_t)c_lo * kFastThreads, ns, rowA, rowB, rowC, rowD, pinit, pinit,
+        if (TAILQ) {
+          uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
+          if (!head_t) left_column(row_lo, pA, pB, hA, hB, fA, fB);
+          ncbottom_init(bot, 0, (int)qlen, a.gap_extend);
+          rt.last = 0;
+          if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
+                                                                     0, false, nullptr, nullptr, nullptr, nullptr, &bot);
+          else nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
+                                                              0, false, hA, hB, fA, fB, &bot);
+          // the last strip of this quad-strip that the reference processes: with the column scan, the last lane whose scan ran (the pass
+          // stops between strips once the forward score is reached); without it, every strip up to TR - 1
+          const int last = tail_t ? rt.last : min(3, TR - 1 - (int)i);
+          ncbottom_get(bot, last, 0, bot_v, bot_m);
+        } else if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE + (size_t)c_lo * kFastThreads, V + (size_t)c_lo * kFastThreads, ns, rowA, rowB, rowC, rowD, pinit, pinit,
                                                              neg_oe2, neg_ext2, (int)qlen - 1 - c_lo, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2, c_lo, c_lo > 0);
         else {
           uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
@@ -1644,8 +1712,13 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
       if (rt.best >= fwd || slack >= ncol) break;
       slack = ncol;                                                                    // not reached under the bound: the exact, unpruned pass
     }
+    int rt_x = tr_x;                                                                  // (maxXY_x is not reset between the passes)
+    if (TAILQ) {
+      if (bot_v > rt.best) { rt.best = bot_v; rt_x = bot_m; }
+      if (rt_x != (int)tlen) rt.y = (int)qlen;
+    }
     a.t_start[tid] = ((int)tlen - 1) - rt.y;                                          // :380-381
-    a.q_start[tid] = ((int)qlen - 1) - (int)tlen;
+    a.q_start[tid] = ((int)qlen - 1) - rt_x;
   }
 }
 
@@ -1770,10 +1843,11 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
     return (uint64_t)std::min(q8, t8) * (uint64_t)a.match <= 4000;
   }
   if (algo == ALGO_SEMI_GLOBAL) {
-    // TAIL = TARGET (scan of the last query column) with any HEAD, and TAIL = NONE (nothing is ever scanned: the reference's result is
-    // its initial state, k_semiglobal_tail_none); TAIL in {QUERY, BOTH} (scan of the last padded target row) uses the general kernel
+    // every HEAD / TAIL variant: TAIL = TARGET scans the last query column, TAIL in {QUERY, BOTH} also / only the bottom row of the last
+    // processed strip (k_semiglobal_s16<.., TAILQ>), TAIL = NONE scans nothing (the reference's result is its initial state, k_semiglobal_tail_none)
     if (a.tail == SKIP_NONE) return true;
-    if (a.tail != SKIP_TARGET) return false;
+    // the bottom-row scan reads PAD rows, and the pads of a forward sequence are N: their score must fit the byte tables
+    if (a.tail != SKIP_TARGET && (a.n_score + 2 * a.gap_extend < -127 || a.n_score + 2 * a.gap_extend > 127)) return false;
     const bool head_t = (a.head == SKIP_TARGET || a.head == SKIP_BOTH);
     // every H/E/F is >= -(2*oe + ext*(q8+2) + mismatch) and <= q8*match: keep both well inside (kNegSafe, 32767); a charged left
     // column (HEAD in {NONE, QUERY}) adds ext * t8
@@ -1851,6 +1925,10 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     cudaFuncSetAttribute(k_local_s16<START_TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_POS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_POS, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_global_s16, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_banded_tb_s16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_banded_tb_s16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -1875,6 +1953,7 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
   const uint32_t blocks = ((uint32_t)a.n + kFastThreads - 1) / kFastThreads;
   const bool sp = (start == START_POS);
   const bool tbm = (start == START_TB);
+  const bool tailq = (algo == ALGO_SEMI_GLOBAL) && (a.tail == SKIP_QUERY || a.tail == SKIP_BOTH);
   // grouped arg-max (keys score * 32 + ...) while every possible score stays below 1024, else the per-step keys (score * 8 + ...)
   const uint32_t t8 = (max_t + 7u) & ~7u;
   const bool g4 = GB200_LOCAL_G4 && (uint64_t)std::min(q8, t8) * (uint64_t)a.match <= 1000;
@@ -1889,7 +1968,8 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
       if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
       else if (g4) { if (sp) k_local_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
       else if (sp) k_local_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
-    } else { if (sp) k_semiglobal_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
+    } else if (tailq) { if (sp) k_semiglobal_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_semiglobal_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
+    else { if (sp) k_semiglobal_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
     cudaEventRecord(fs.ev_join, fs.side);
     launches++;
   }
@@ -1900,6 +1980,7 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     else if (g4) { if (sp) k_local_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
     else if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
   }
+  else if (algo == ALGO_SEMI_GLOBAL && tailq) { if (sp) k_semiglobal_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
   else k_global_s16<<<blocks, kFastThreads, smem, str>>>(fa);
   if (nmask && passes) cudaStreamWaitEvent(str, fs.ev_join, 0);

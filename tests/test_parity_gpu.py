@@ -79,17 +79,19 @@ def test_semiglobal_all_head_tail(oracle, head, tail):
     want = oracle_align(oracle, b, algo=po.SEMI_GLOBAL, head=head, tail=tail, start=po.WITH_START, max_query_len=mql)
     got = run(b, algo=capi.SEMI_GLOBAL, head=head, tail=tail, start=capi.WITH_START)
     assert_same(got, want, K5, f"semi-global h{head} t{tail} with start")
-    # TAIL in {TARGET, NONE} with any HEAD runs on the s16x2 lanes (a charged left column = per-lane start values); TAIL in {QUERY, BOTH} on int32
-    assert got["_kernel"] == ("s16x2" if tail in (po.TARGET, po.NONE) else "int32"), got["_kernel"]
+    # every variant runs on the s16x2 lanes: a charged left column = per-lane start values of the sweep, TAIL in {QUERY, BOTH} = per-lane
+    # bottom-row trackers, TAIL = NONE = constants
+    assert got["_kernel"] == "s16x2", got["_kernel"]
     got = run(b, algo=capi.SEMI_GLOBAL, head=head, tail=tail)
     assert_same(got, want, K3, f"semi-global h{head} t{tail}")
     pol1 = run(b, policy=1, algo=capi.SEMI_GLOBAL, head=head, tail=tail, start=capi.WITH_START)
     assert pol1["_kernel"] == "int32"
     assert_same(pol1, want, K5, f"semi-global h{head} t{tail} with start, int32")
-    if tail in (po.TARGET, po.NONE):
-        # other scorings, reads with N in 20 % of the pairs (N-aware pass), longer targets (the charged left column reaches further down)
+    if True:
+        # other scorings, reads with N in 20 % of the pairs (N-aware pass), longer targets (the charged left column reaches further down),
+        # queries longer than their targets (the bottom-row scan can land on column ref_len: the reference's `maxXY_x != ref_len` test)
         for seed, scoring in ((3, (2, 3, 5, 2)), (4, (5, 4, 10, 1)), (5, (1, 1, 0, 1))):
-            b2 = synth.with_n_bases(synth.random_ragged_pairs(400, 9, 330, 9, 700, seed=900 + 16 * seed + 4 * head + tail), 0.2, seed=seed)
+            b2 = synth.with_n_bases(synth.random_ragged_pairs(400, 9, 330, 9, 700 if seed != 4 else 120, seed=900 + 16 * seed + 4 * head + tail), 0.2, seed=seed)
             want = oracle_align(oracle, b2, algo=po.SEMI_GLOBAL, head=head, tail=tail, start=po.WITH_START, max_query_len=mql, scoring=scoring)
             got = run(b2, algo=capi.SEMI_GLOBAL, head=head, tail=tail, start=capi.WITH_START, scoring=scoring)
             assert got["_kernel"] == "s16x2"
