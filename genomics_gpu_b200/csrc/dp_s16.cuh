@@ -1457,9 +1457,9 @@ __device__ __forceinline__ void nc_sweep4(uint32_t* __restrict__ HE, const uint8
   uint32_t hpinitA[8], hpinitB[8], finitA[8], finitB[8], pA0[8], pB0[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) {
-    const uint32_t hp = closed_left ? neg2 : (SEMI ? splat16((r - 1) * bias_ext) : neg_oe2);
-    hpinitA[r] = hpA ? hpA[r] : hp; hpinitB[r] = hpB ? hpB[r] : hp;
-    finitA[r] = fpA ? fpA[r] : neg2; finitB[r] = fpB ? fpB[r] : neg2;
+    const uint32_t hp = SEMI ? splat16((r - 1) * bias_ext) : neg_oe2;
+    hpinitA[r] = closed_left ? neg2 : (hpA ? hpA[r] : hp); hpinitB[r] = closed_left ? neg2 : (hpB ? hpB[r] : hp);
+    finitA[r] = (fpA && !closed_left) ? fpA[r] : neg2; finitB[r] = (fpB && !closed_left) ? fpB[r] : neg2;
     pA0[r] = closed_left ? neg2 : pinitA[r]; pB0[r] = closed_left ? neg2 : pinitB[r];
   }
   NcState st;
@@ -1572,6 +1572,11 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   // F in (row r, column -1); F(t, 0) + r e = [H(t, -1) + (r - 1) e] - open.
   auto left_column = [&](int t0, uint32_t (&pA)[8], uint32_t (&pB)[8], uint32_t (&hA)[8], uint32_t (&hB)[8], uint32_t (&fA)[8], uint32_t (&fB)[8]) {
     const int o = a.gap_open, ext = a.gap_extend;
+    if (head_t) {                       // free left column: H(t, -1) = 0, F = -infinity (one sweep call site serves both cases)
+#pragma unroll
+      for (int r = 0; r < 8; r++) { pA[r] = pB[r] = pinit[r]; hA[r] = hB[r] = splat16((r - 1) * ext); fA[r] = fB[r] = splat16(kNegSafe); }
+      return;
+    }
 #pragma unroll
     for (int r = 0; r < 8; r++) {
       const int t = t0 + r, fd = (r - 2) * ext, fh = (r - 1) * ext;
@@ -1596,22 +1601,22 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     const uint32_t wc = (4 * j + 2 < TR) ? tw[4 * j + 2] : 0u;
     const uint32_t wd = (4 * j + 3 < TR) ? tw[4 * j + 3] : 0u;
     quad_tables<NMASK || TAILQ>(wa, wb, wc, wd, mis4, delta, nval, nsc4, rowA, rowB, rowC, rowD);   // TAILQ: the pad rows of the last strip count, and the pads are N
+    // Measured (C2, 262144 pairs): handing the free column's start state to the sweep as run-time arrays (one call site for both HEAD
+    // kinds) makes the score-only kernel faster (3.87 -> 3.71 ms) and the kernel with the start pass slower (4.59 -> 4.91 ms: the arrays
+    // stay live next to the second pass's state), so the latter keeps a call site of its own for the free column.
+    if (START == START_POS && !TAILQ && head_t) {
+      nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2);
+      continue;
+    }
+    uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
+    left_column(32 * j, pA, pB, hA, hB, fA, fB);
     if (TAILQ && j == NQ - 1) {
       // last quad-strip: keep the first maximum of every lane's bottom row (the lane of strip TR - 1 is read below)
-      uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
-      if (!head_t) left_column(32 * j, pA, pB, hA, hB, fA, fB);
       ncbottom_init(bot, 0, (int)qlen, a.gap_extend);
-      if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2,
-                                                                  0, false, nullptr, nullptr, nullptr, nullptr, &bot);
-      else nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2,
-                                                           0, false, hA, hB, fA, fB, &bot);
-    } else if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2);
-    else {
-      uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
-      left_column(32 * j, pA, pB, hA, hB, fA, fB);
-      nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2, 0, false,
-                                                hA, hB, fA, fB);
-    }
+      nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2,
+                                                      0, false, hA, hB, fA, fB, &bot);
+    } else nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2,
+                                                     0, false, hA, hB, fA, fB);
   }
   int tr_x = (int)tlen;                                                             // query_batch_end = ref_len unless the bottom-row scan finds a column (Q8)
   if (TAILQ) {                                                                      // :185-216, strict '>' after the column scan; :214 `if (maxXY_x != ref_len)`
@@ -1686,27 +1691,25 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
         // that get there only see values below the forward score, which never decide the result
         const int c_lo = (slack < ncol) ? min(max(row_lo - slackL, 0) & ~3, c_max) : 0;
         const int ns = ((lim < ncol) ? lim + 2 + (int)fa.one : nsteps) - c_lo;
+        if (!TAILQ && head_t) {                       // (short pruned sweeps: the constant start state of the free column is cheaper to set up)
+          nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE + (size_t)c_lo * kFastThreads, V + (size_t)c_lo * kFastThreads, ns, rowA, rowB, rowC, rowD, pinit, pinit,
+                                                   neg_oe2, neg_ext2, (int)qlen - 1 - c_lo, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2, c_lo, c_lo > 0);
+          lim = min(ncol, lim + 32);
+          continue;
+        }
+        uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
+        left_column(row_lo, pA, pB, hA, hB, fA, fB);                                    // rows counted from the first strip of this pass
         if (TAILQ) {
-          uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
-          if (!head_t) left_column(row_lo, pA, pB, hA, hB, fA, fB);
           ncbottom_init(bot, 0, (int)qlen, a.gap_extend);
           rt.last = 0;
-          if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
-                                                                     0, false, nullptr, nullptr, nullptr, nullptr, &bot);
-          else nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
-                                                              0, false, hA, hB, fA, fB, &bot);
+          nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK, true>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, kq_scan, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
+                                                         0, false, hA, hB, fA, fB, &bot);
           // the last strip of this quad-strip that the reference processes: with the column scan, the last lane whose scan ran (the pass
           // stops between strips once the forward score is reached); without it, every strip up to TR - 1
           const int last = tail_t ? rt.last : min(3, TR - 1 - (int)i);
           ncbottom_get(bot, last, 0, bot_v, bot_m);
-        } else if (head_t) nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE + (size_t)c_lo * kFastThreads, V + (size_t)c_lo * kFastThreads, ns, rowA, rowB, rowC, rowD, pinit, pinit,
-                                                             neg_oe2, neg_ext2, (int)qlen - 1 - c_lo, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2, c_lo, c_lo > 0);
-        else {
-          uint32_t pA[8], pB[8], hA[8], hB[8], fA[8], fB[8];
-          left_column(row_lo, pA, pB, hA, hB, fA, fB);                                  // rows counted from the first strip of this pass
-          nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
-                                                   0, false, hA, hB, fA, fB);
-        }
+        } else nc_sweep4<ALGO_SEMI_GLOBAL, true, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pA, pB, neg_oe2, neg_ext2, (int)qlen - 1, 8 * (int)i, (int)tlen, 0, 0, rt, nsc2,
+                                                        0, false, hA, hB, fA, fB);
         lim = min(ncol, lim + 32);
       }
       if (rt.best >= fwd || slack >= ncol) break;
