@@ -954,11 +954,13 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   const uint32_t neg_oe2 = splat16(-(a.gap_open + a.gap_extend)), neg_ext2 = splat16(-a.gap_extend);
   const uint32_t nval = a.n_value, nsc2 = splat16(a.n_score), nsc4 = ((uint32_t)a.n_score & 0xFFu) * 0x01010101u;
 
+  // START_REV: the start pass as a launch of its own behind the score-only kernel (see k_semiglobal_s16)
+  constexpr bool FWD = (START != START_REV), REVP = (START == START_POS || START == START_REV);
   // ---- prologue: selector bytes of the query, (H,E) = 0; detect bases this pass cannot score ----
   bool odd = false;
   const int ncol = QR * 8;
   V[0] = 0x88; HE[0] = 0;
-  for (int j = 0; j < QR; j++) {
+  for (int j = 0; FWD && j < QR; j++) {
     const uint32_t w = qw[j];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -1000,7 +1002,7 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     a.score[tid] = tw_.score; a.q_end[tid] = tw_.col; a.t_end[tid] = tw_.row;
     return;
   }
-  for (int j = 0; j < NQ; j++) {
+  for (int j = 0; FWD && j < NQ; j++) {
     uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
     const uint32_t wa = tw[4 * j];
     const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;     // phantom strips: every base mismatches
@@ -1016,10 +1018,11 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
                                  rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, lb, nsc2);
     else local_sweep4<NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb, nsc2);
   }
-  const Winner fw = pick_winner4<G4>(lb);
-  a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row;
+  Winner fw;
+  if (FWD) { fw = pick_winner4<G4>(lb); a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row; }
+  else { fw.score = a.score[tid]; fw.col = a.q_end[tid]; fw.row = a.t_end[tid]; }      // the forward launch's results
 
-  if (START == START_POS) {
+  if (REVP) {
     // ---- reverse pass (local_kernel_template.h:441-511): same recurrence over the reversed words that hold the
     // end cell; the first cell that reaches the forward score is the start (target coordinate mirrored, Q3) ----
     int sx = 0, sy = 0;
@@ -1553,13 +1556,18 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const bool head_t = (a.head == SKIP_TARGET || a.head == SKIP_BOTH);           // HEAD in {TARGET,BOTH}: free left column (:114-121)
   const int ncol = QR * 8, nsteps = ncol + 2 + (int)fa.one;
 
-  bool odd = top_zero ? nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval)
-                      : nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval);
-  if (odd || qlen == 0) {   // cannot happen (see k_classify); safety net
-    const uint32_t slot = atomicAdd(fa.work_count + 1, 1u);
-    fa.worklist2[slot] = tid;
-    return;
-  }
+  // START_REV: the start pass as a launch of its own behind the score-only kernel (the two passes as ONE kernel keep each other's
+  // state live: the forward sweep of the fused kernel runs 4 - 10 % slower than the same sweep alone; measured)
+  constexpr bool FWD = (START != START_REV), REVP = (START == START_POS || START == START_REV);
+  if (FWD) {
+    bool odd = top_zero ? nc_prologue<true, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval)
+                        : nc_prologue<false, true, NMASK>(HE, V, qw, qlen, QR, 0, a.gap_open, a.gap_extend, nval);
+    if (odd || qlen == 0) {   // cannot happen (see k_classify); safety net
+      const uint32_t slot = atomicAdd(fa.work_count + 1, 1u);
+      fa.worklist2[slot] = tid;
+      return;
+    }
+  } else if (qlen == 0) return;
   uint32_t pinit[8];
 #pragma unroll
   for (int r = 0; r < 8; r++) pinit[r] = splat16((r - 2) * a.gap_extend);   // HEAD in {TARGET,BOTH}: free left column, diag H(r-1,-1) = 0 (:114-121), biased
@@ -1594,7 +1602,7 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
   const bool tail_t = !TAILQ || a.tail == SKIP_BOTH;                                // the last query column is scanned (:160-178)
   const int kq_scan = tail_t ? (int)qlen - 1 : -1000;
   const int NQ = (TR + 3) >> 2;
-  for (int j = 0; j < NQ; j++) {
+  for (int j = 0; FWD && j < NQ; j++) {
     uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
     const uint32_t wa = tw[4 * j];
     const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;
@@ -1604,7 +1612,7 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
     // Measured (C2, 262144 pairs): handing the free column's start state to the sweep as run-time arrays (one call site for both HEAD
     // kinds) makes the score-only kernel faster (3.87 -> 3.71 ms) and the kernel with the start pass slower (4.59 -> 4.91 ms: the arrays
     // stay live next to the second pass's state), so the latter keeps a call site of its own for the free column.
-    if (START == START_POS && !TAILQ && head_t) {
+    if (START == START_POS && !TAILQ && head_t) {      // (fused kernel only)
       nc_sweep4<ALGO_SEMI_GLOBAL, false, NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, pinit, pinit, neg_oe2, neg_ext2, kq_scan, 32 * j, (int)tlen, 0, 0, tr, nsc2);
       continue;
     }
@@ -1619,14 +1627,16 @@ __global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs 
                                                      0, false, hA, hB, fA, fB);
   }
   int tr_x = (int)tlen;                                                             // query_batch_end = ref_len unless the bottom-row scan finds a column (Q8)
-  if (TAILQ) {                                                                      // :185-216, strict '>' after the column scan; :214 `if (maxXY_x != ref_len)`
-    int v, m; ncbottom_get(bot, (TR - 1) & 3, 0, v, m);
-    if (v > tr.best) { tr.best = v; tr_x = m; }
-    if (tr_x != (int)tlen) tr.y = (int)qlen;
-  }
-  a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = tr_x;
+  if (FWD) {
+    if (TAILQ) {                                                                    // :185-216, strict '>' after the column scan; :214 `if (maxXY_x != ref_len)`
+      int v, m; ncbottom_get(bot, (TR - 1) & 3, 0, v, m);
+      if (v > tr.best) { tr.best = v; tr_x = m; }
+      if (tr_x != (int)tlen) tr.y = (int)qlen;
+    }
+    a.score[tid] = tr.best; a.t_end[tid] = tr.y; a.q_end[tid] = tr_x;
+  } else { tr.best = a.score[tid]; tr.y = a.t_end[tid]; tr_x = a.q_end[tid]; }      // the forward launch's results
 
-  if (START == START_POS) {
+  if (REVP) {
     // start pass (:227-384): the same DP over the TRUE-LENGTH reversed sequences, from the strip that holds the
     // end row, until the running best reaches the forward score
     const int fwd = tr.best;
@@ -1871,6 +1881,12 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
 #ifndef GB200_LOCAL_G4
 #define GB200_LOCAL_G4 1
 #endif
+#ifndef GB200_LOCAL_SPLIT_START
+#define GB200_LOCAL_SPLIT_START 0    // same for LOCAL WITH_START: measured 4.97 ms vs 4.95 ms fused on C2 -- no gain, off (semi-global: 4.54 vs 4.60, on)
+#endif
+#ifndef GB200_SEMI_SPLIT_START
+#define GB200_SEMI_SPLIT_START 1     // semi-global WITH_START: score-only kernel + start-pass kernel (START_REV) instead of the fused kernel
+#endif
 int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, uint32_t max_q, uint32_t max_t, bool maybe_odd, int force_passes, cudaStream_t str) {
   int algo = algo_in;
   if (algo == ALGO_SEMI_GLOBAL && a.tail == SKIP_NONE) {
@@ -1928,6 +1944,12 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     cudaFuncSetAttribute(k_local_s16<START_TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_REV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_REV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_local_s16<START_REV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
+    cudaFuncSetAttribute(k_semiglobal_s16<START_REV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -1969,9 +1991,19 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     else if (banded) k_banded_tb_s16<true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
     else if (algo == ALGO_LOCAL) {
       if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+      else if (sp && GB200_LOCAL_SPLIT_START) {
+        if (g4) { k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); k_local_s16<START_REV, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
+        else { k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); k_local_s16<START_REV, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
+        launches++;
+      }
       else if (g4) { if (sp) k_local_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
       else if (sp) k_local_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
     } else if (tailq) { if (sp) k_semiglobal_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_semiglobal_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
+    else if (sp && GB200_SEMI_SPLIT_START) {
+      k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+      k_semiglobal_s16<START_REV, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
+      launches++;
+    }
     else { if (sp) k_semiglobal_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_semiglobal_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
     cudaEventRecord(fs.ev_join, fs.side);
     launches++;
@@ -1980,10 +2012,20 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
   else if (banded) k_banded_tb_s16<false><<<blocks, kFastThreads, smem, str>>>(fa);
   else if (algo == ALGO_LOCAL) {
     if (tbm) k_local_s16<START_TB><<<blocks, kFastThreads, smem, str>>>(fa);
+    else if (sp && GB200_LOCAL_SPLIT_START) {
+      if (g4) { k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); k_local_s16<START_REV, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
+      else { k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); k_local_s16<START_REV><<<blocks, kFastThreads, smem, str>>>(fa); }
+      launches++;
+    }
     else if (g4) { if (sp) k_local_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
     else if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
   }
   else if (algo == ALGO_SEMI_GLOBAL && tailq) { if (sp) k_semiglobal_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
+  else if (algo == ALGO_SEMI_GLOBAL && sp && GB200_SEMI_SPLIT_START) {
+    k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
+    k_semiglobal_s16<START_REV><<<blocks, kFastThreads, smem, str>>>(fa);
+    launches++;
+  }
   else if (algo == ALGO_SEMI_GLOBAL) { if (sp) k_semiglobal_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_semiglobal_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); }
   else k_global_s16<<<blocks, kFastThreads, smem, str>>>(fa);
   if (nmask && passes) cudaStreamWaitEvent(str, fs.ev_join, 0);

@@ -83,3 +83,46 @@ def test_config4_full_shape_banded_cigar_properties(oracle):
     assert gc == lc
     for i, c in enumerate(gc):
         assert cigar_rescore(c, (1, 4, 6, 1)) == ban["aln_score"][i]
+
+
+def test_config4_full_batch_banded_score(oracle):
+    """C4 at a full 262,144-pair batch, score/end only: the s16x2 banded sweep (banded.h's H-based recurrence over the tile band) equals
+    the int32 banded kernel on every pair, the oracle on 20,000 of them, and results do not depend on how the batch was cut"""
+    b = synth.config4(262_144, seed=45)
+    full = run(b, algo=capi.BANDED, k_band=64)
+    assert full["_kernel"] == "s16x2"
+    gen = run(b, policy=1, algo=capi.BANDED, k_band=64)
+    assert gen["_kernel"] == "int32"
+    assert_same(full, gen, K3, "banded score/end: s16x2 vs int32, 262144 pairs")
+    sub = b.slice(100_000, 120_000)
+    want = oracle_align(oracle, sub, algo=po.BANDED, k_band=64)
+    assert_same({k: full[k][100_000:120_000] for k in K3}, want, K3, "banded score/end vs the oracle, 20000 pairs")
+    part = run(sub, algo=capi.BANDED, k_band=64)
+    assert_same(part, want, K3, "banded score/end: batch-composition independence")
+    assert np.median(full["aln_score"]) > 150
+
+
+def test_sw_benchmark_full_batch_two_packed_kernels():
+    """the nvbio adapter at sw-benchmark's batch size (262,144 reads of 150 bp against 600 bp windows): the quad-strip kernel and the
+    band-blocked kernel -- two independent implementations (K2's blocking / the reference's blocking) -- agree on every score of all
+    three alignment types and on the GLOBAL / SEMI_GLOBAL sinks, and with the int32 kernel on a 30,000-job slice"""
+    from genomics_gpu_b200 import nvb
+    pats, poffs, texts, toffs = synth.nvb_jobs(262_144, 150, 150, 600, 600, seed=71, sub=0.03, indel=0.005)
+    batch = nvb.Batch(pats, poffs, texts, toffs)
+    k = 30_000
+    small = nvb.Batch(pats[:poffs[k]], poffs[:k + 1], texts[:toffs[k]], toffs[:k + 1])
+    try:
+        with nvb.Stream(batch) as st, nvb.Stream(small) as st_small:
+            for type_ in (nvb.GLOBAL, nvb.LOCAL, nvb.SEMI_GLOBAL):
+                al = nvb.aligner(nvb.GOTOH, type_, 2, -1, -2, -1)
+                sinks = type_ != nvb.LOCAL
+                nvb.set_policy(0); st.enact(al, sinks); a = st.results(sinks); ka = st.kernel()
+                nvb.set_policy(2); st.enact(al, sinks); b2 = st.results(sinks); kb = st.kernel()
+                assert ka == "s16x2-strip" and kb == "s16x2", (ka, kb)
+                assert np.array_equal(a[0], b2[0]), type_
+                if sinks:
+                    assert np.array_equal(a[1], b2[1]) and np.array_equal(a[2], b2[2]), type_
+                nvb.set_policy(1); st_small.enact(al, sinks); c = st_small.results(sinks)
+                assert st_small.kernel() == "int32" and np.array_equal(c[0], a[0][:k]), type_
+    finally:
+        nvb.set_policy(0)
