@@ -954,13 +954,11 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
   const uint32_t neg_oe2 = splat16(-(a.gap_open + a.gap_extend)), neg_ext2 = splat16(-a.gap_extend);
   const uint32_t nval = a.n_value, nsc2 = splat16(a.n_score), nsc4 = ((uint32_t)a.n_score & 0xFFu) * 0x01010101u;
 
-  // START_REV: the start pass as a launch of its own behind the score-only kernel (see k_semiglobal_s16)
-  constexpr bool FWD = (START != START_REV), REVP = (START == START_POS || START == START_REV);
   // ---- prologue: selector bytes of the query, (H,E) = 0; detect bases this pass cannot score ----
   bool odd = false;
   const int ncol = QR * 8;
   V[0] = 0x88; HE[0] = 0;
-  for (int j = 0; FWD && j < QR; j++) {
+  for (int j = 0; j < QR; j++) {
     const uint32_t w = qw[j];
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -1002,7 +1000,7 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
     a.score[tid] = tw_.score; a.q_end[tid] = tw_.col; a.t_end[tid] = tw_.row;
     return;
   }
-  for (int j = 0; FWD && j < NQ; j++) {
+  for (int j = 0; j < NQ; j++) {
     uint32_t rowA[8], rowB[8], rowC[8], rowD[8];
     const uint32_t wa = tw[4 * j];
     const uint32_t wb = (4 * j + 1 < TR) ? tw[4 * j + 1] : 0u;     // phantom strips: every base mismatches
@@ -1018,11 +1016,10 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
                                  rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.thirtytwo, fa.one, (uint32_t)j << 16, lb, nsc2);
     else local_sweep4<NMASK>(HE, V, nsteps, rowA, rowB, rowC, rowD, neg_oe2, neg_ext2, fa.eight, fa.one, (uint32_t)j << 16, lb, nsc2);
   }
-  Winner fw;
-  if (FWD) { fw = pick_winner4<G4>(lb); a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row; }
-  else { fw.score = a.score[tid]; fw.col = a.q_end[tid]; fw.row = a.t_end[tid]; }      // the forward launch's results
+  const Winner fw = pick_winner4<G4>(lb);
+  a.score[tid] = fw.score; a.q_end[tid] = fw.col; a.t_end[tid] = fw.row;
 
-  if (REVP) {
+  if (START == START_POS) {
     // ---- reverse pass (local_kernel_template.h:441-511): same recurrence over the reversed words that hold the
     // end cell; the first cell that reaches the forward score is the start (target coordinate mirrored, Q3) ----
     int sx = 0, sy = 0;
@@ -1881,9 +1878,7 @@ bool fast_path_eligible(const DpArgs& a, int algo, int start, bool second, uint3
 #ifndef GB200_LOCAL_G4
 #define GB200_LOCAL_G4 1
 #endif
-#ifndef GB200_LOCAL_SPLIT_START
-#define GB200_LOCAL_SPLIT_START 0    // same for LOCAL WITH_START: measured 4.97 ms vs 4.95 ms fused on C2 -- no gain, off (semi-global: 4.54 vs 4.60, on)
-#endif
+// (the same split for LOCAL WITH_START was measured: 4.97 ms against 4.95 ms fused on C2 -- no gain, not kept)
 #ifndef GB200_SEMI_SPLIT_START
 #define GB200_SEMI_SPLIT_START 1     // semi-global WITH_START: score-only kernel + start-pass kernel (START_REV) instead of the fused kernel
 #endif
@@ -1944,10 +1939,6 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     cudaFuncSetAttribute(k_local_s16<START_TB, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_POS, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_local_s16<START_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_local_s16<START_REV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_local_s16<START_REV, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
-    cudaFuncSetAttribute(k_local_s16<START_REV, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_REV, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
     cudaFuncSetAttribute(k_semiglobal_s16<START_NONE, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, lim);
@@ -1991,11 +1982,6 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
     else if (banded) k_banded_tb_s16<true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
     else if (algo == ALGO_LOCAL) {
       if (tbm) k_local_s16<START_TB, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
-      else if (sp && GB200_LOCAL_SPLIT_START) {
-        if (g4) { k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); k_local_s16<START_REV, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
-        else { k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); k_local_s16<START_REV, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
-        launches++;
-      }
       else if (g4) { if (sp) k_local_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
       else if (sp) k_local_s16<START_POS, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_local_s16<START_NONE, true><<<blocks, kFastThreads, smem, fs.side>>>(fa);
     } else if (tailq) { if (sp) k_semiglobal_s16<START_POS, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); else k_semiglobal_s16<START_NONE, true, true><<<blocks, kFastThreads, smem, fs.side>>>(fa); }
@@ -2012,11 +1998,6 @@ int fast_path_launch(const DpArgs& a, int algo_in, int start, FastScratch& fs, u
   else if (banded) k_banded_tb_s16<false><<<blocks, kFastThreads, smem, str>>>(fa);
   else if (algo == ALGO_LOCAL) {
     if (tbm) k_local_s16<START_TB><<<blocks, kFastThreads, smem, str>>>(fa);
-    else if (sp && GB200_LOCAL_SPLIT_START) {
-      if (g4) { k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); k_local_s16<START_REV, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
-      else { k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa); k_local_s16<START_REV><<<blocks, kFastThreads, smem, str>>>(fa); }
-      launches++;
-    }
     else if (g4) { if (sp) k_local_s16<START_POS, false, true><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE, false, true><<<blocks, kFastThreads, smem, str>>>(fa); }
     else if (sp) k_local_s16<START_POS><<<blocks, kFastThreads, smem, str>>>(fa); else k_local_s16<START_NONE><<<blocks, kFastThreads, smem, str>>>(fa);
   }
