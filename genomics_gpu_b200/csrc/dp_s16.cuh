@@ -32,6 +32,14 @@ namespace gb200 {
 #define GB200_FAST_THREADS 128
 #endif
 constexpr int kFastThreads = GB200_FAST_THREADS;
+// launch bounds of the s16x2 kernels; GB200_FAST_MINBLOCKS (experiments): promise the compiler that many resident CTAs per SM.
+// Measured on C2 (262144 pairs; ms for local / local+start / semi / semi+start / global): default 4.28 / 4.95 / 3.72 / 4.54 / 3.62,
+// 2 CTAs (more registers) 4.29 / 4.92 / 3.99 / 4.81 / 3.66, 3 CTAs 4.28 / 4.95 / 3.82 / 4.62 / 3.66 -- the default stays.
+#ifdef GB200_FAST_MINBLOCKS
+#define GB200_FAST_LB __launch_bounds__(kFastThreads, GB200_FAST_MINBLOCKS)
+#else
+#define GB200_FAST_LB __launch_bounds__(kFastThreads)
+#endif
 constexpr uint32_t kSlotPad = 8;          // dummy column slots: 2 below column 0 (late lanes' phantom columns), 6 above the last column
 constexpr uint32_t kFastFallbackSlots = 8192;
 
@@ -936,7 +944,7 @@ __global__ void __launch_bounds__(256) k_classify(const FastArgs fa, uint32_t* _
 }
 
 template <int START, bool NMASK = false, bool G4 = false>
-__global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
+__global__ void GB200_FAST_LB k_local_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1101,7 +1109,7 @@ __global__ void __launch_bounds__(kFastThreads) k_local_s16(const FastArgs fa) {
 // stored: tile (strip * W + word - lo(strip)) * 2 + half, W = widest strip (dp_common.cuh band_geom), which k_get_tb addresses the same way
 // TB = false: the reference's score-only BANDED kernel (banded.h: H-based opening, score + end cell) on the same tile band.
 template <bool NMASK = false, bool TB = true>
-__global__ void __launch_bounds__(kFastThreads) k_banded_tb_s16(const FastArgs fa) {
+__global__ void GB200_FAST_LB k_banded_tb_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1532,7 +1540,7 @@ __device__ __forceinline__ bool target_has_odd_base(const uint32_t* tw, uint32_t
 // TAILQ: TAIL in {QUERY, BOTH} -- the bottom row of the last processed (padded) strip is scanned as well (NcBottom); its own
 // instantiations, so that the default kernels carry none of it.
 template <int START, bool NMASK = false, bool TAILQ = false>
-__global__ void __launch_bounds__(kFastThreads) k_semiglobal_s16(const FastArgs fa) {
+__global__ void GB200_FAST_LB k_semiglobal_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1745,7 +1753,7 @@ __global__ void __launch_bounds__(256) k_semiglobal_tail_none(const DpArgs a) {
   if (START == START_POS) { a.t_start[tid] = tlen - 1; a.q_start[tid] = qlen - 1 - tlen; }
 }
 
-__global__ void __launch_bounds__(kFastThreads) k_global_s16(const FastArgs fa) {
+__global__ void GB200_FAST_LB k_global_s16(const FastArgs fa) {
   extern __shared__ uint32_t smem[];
   const DpArgs& a = fa.a;
   const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;

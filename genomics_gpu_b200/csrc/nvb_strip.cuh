@@ -95,7 +95,7 @@ __device__ __forceinline__ void nvb_local_sweep4(uint32_t* __restrict__ GE, cons
 }
 
 template <int TYPE, bool SINK>
-__global__ void __launch_bounds__(kFastThreads) k_nvb_strip(const NvbStripArgs a) {
+__global__ void GB200_FAST_LB k_nvb_strip(const NvbStripArgs a) {
   extern __shared__ uint32_t smem[];
   const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= a.count) return;
