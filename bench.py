@@ -339,6 +339,11 @@ def run_extras(local_rank: int, n_fwd: int):
     try:
         b2 = synth.config2(n_fwd, seed=2)
         out["C2_forward_only"] = {"local": timed(b2, algo=capi.LOCAL), "semi_global": timed(b2, algo=capi.SEMI_GLOBAL), "global": timed(b2, algo=capi.GLOBAL)}
+        # the other semiglobal_skipping_head / _tail variants of the reference API (semiglobal_kernel_template.h:39-388): all on the s16x2 lanes
+        out["C2_semi_global_head_tail_variants_with_start"] = {
+            f"head_{hn}_tail_{tn}": timed(b2, algo=capi.SEMI_GLOBAL, head=h, tail=t, start=capi.WITH_START)
+            for (hn, h), (tn, t) in ((("none", capi.NONE), ("target", capi.TARGET)), (("query", capi.QUERY), ("target", capi.TARGET)),
+                                     (("target", capi.TARGET), ("query", capi.QUERY)), (("both", capi.BOTH), ("both", capi.BOTH)))}
         out["C3_global_16k_x_16k"] = {"n128": timed(synth.config3(128, 16384, seed=3), algo=capi.GLOBAL), "n32": timed(synth.config3(32, 16384, seed=3), algo=capi.GLOBAL),
                                       "n16": timed(synth.config3(16, 16384, seed=3), algo=capi.GLOBAL)}
         b4 = synth.config4(n_fwd, seed=4)
