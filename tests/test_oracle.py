@@ -84,6 +84,21 @@ def test_oracle_matches_reference_live(oracle, seed):
 
 
 @pytest.mark.skipif(not po.RefHost.available(1024), reason="oracle/_ref host build of the reference not present")
+@pytest.mark.parametrize("k_band,qmax,tmax,scoring", [(8, 40, 330, (1, 4, 6, 1)), (24, 220, 60, (2, 3, 5, 2)), (40, 330, 330, (5, 4, 10, 1)),
+                                                       (4096, 100, 200, (1, 4, 6, 1)), (16, 300, 300, (1, 1, 0, 1)), (72, 250, 250, (3, 5, 0, 0))])
+def test_oracle_matches_reference_banded_shapes(oracle, k_band, qmax, tmax, scoring):
+    """gasal_banded_tiled_kernel (banded.h:10-139) on the band geometries and scorings the s16x2 banded sweep is tested with
+    (tests/test_parity_gpu.py::test_banded_score_runs_on_the_packed_kernel): band of one tile, band wider than the matrix, query
+    longer than the target, free gaps -- the restatement against the reference's own kernel compiled for the host"""
+    ref = po.RefHost(1024)
+    b = synth.random_ragged_pairs(250, 9, qmax, 9, tmax, seed=700 + k_band, n_frac=0.02)
+    pq, pt = oracle.pack(b.q_bytes), oracle.pack(b.t_bytes)
+    want = ref.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, scoring=scoring, algo=po.BANDED, k_band=k_band)
+    got = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, scoring=scoring, max_query_len=1024, algo=po.BANDED, k_band=k_band)
+    assert_same(got, want, K3, f"banded k={k_band} {scoring}")
+
+
+@pytest.mark.skipif(not po.RefHost.available(1024), reason="oracle/_ref host build of the reference not present")
 @pytest.mark.parametrize("head", [po.NONE, po.QUERY, po.TARGET, po.BOTH])
 def test_oracle_matches_reference_all_head_tail(oracle, head):
     """all 16 semiglobal_skipping_head / _tail variants (semiglobal_kernel_template.h:39-388) with start positions: the restatement
