@@ -344,6 +344,21 @@ def run_extras(local_rank: int, n_fwd: int):
             f"head_{hn}_tail_{tn}": timed(b2, algo=capi.SEMI_GLOBAL, head=h, tail=t, start=capi.WITH_START)
             for (hn, h), (tn, t) in ((("none", capi.NONE), ("target", capi.TARGET)), (("query", capi.QUERY), ("target", capi.TARGET)),
                                      (("target", capi.TARGET), ("query", capi.QUERY)), (("both", capi.BOTH), ("both", capi.BOTH)))}
+        # KSW seed extension (algo = KSW, host_seed_scores; ksw_kernel_template.h:46-199): one thread per pair, literal semantics
+        try:
+            bk = synth.make_extension_pairs(n_fwd, 150, 200)          # the read is a mutated copy of the window's first 150 bases: the extension runs the whole read
+            with Aligner(max_query_len=157, max_target_len=207, max_n_alns=bk.n, n_streams=1, scoring=SCORING, device=local_rank, algo=capi.KSW) as al:
+                seeds = np.full(bk.n, 20, dtype=np.uint32)
+                best = None
+                for _ in range(3):
+                    rk = al.align(bk, seeds=seeds)
+                    ms = al.last_ms(0)
+                    best = ms if best is None or ms[2] < best[2] else best
+                out["KSW_extension_150x200_seed20"] = {"kernel": al.kernel_name(0), "pairs": bk.n, "dp_ms": best[2], "pairs_per_s": bk.n / (best[2] * 1e-3),
+                                                       "gcups_dp_full_rectangle": bk.cells / (best[2] * 1e-3) / 1e9, "mean_query_end": float(rk["query_batch_end"].mean()),
+                                                       "note": "gcups over the full 150 x 200 rectangle; ksw_extend itself narrows the band row by row"}
+        except Exception as exc:  # noqa: BLE001
+            out["KSW_extension_150x200_seed20"] = {"error": repr(exc)}
         out["C3_global_16k_x_16k"] = {"n128": timed(synth.config3(128, 16384, seed=3), algo=capi.GLOBAL), "n32": timed(synth.config3(32, 16384, seed=3), algo=capi.GLOBAL),
                                       "n16": timed(synth.config3(16, 16384, seed=3), algo=capi.GLOBAL)}
         b4 = synth.config4(n_fwd, seed=4)

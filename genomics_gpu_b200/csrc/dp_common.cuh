@@ -12,6 +12,7 @@ enum { START_NONE = 0, START_POS = 1, START_TB = 2 };
 constexpr int START_REV = 3;      // kernel-internal: the start pass alone, on the forward results already in the result arrays (dp_s16.cuh)
 enum { SKIP_NONE = 0, SKIP_QUERY = 1, SKIP_TARGET = 2, SKIP_BOTH = 3 };
 enum { ALGO_GLOBAL = 1, ALGO_SEMI_GLOBAL = 2, ALGO_LOCAL = 3, ALGO_BANDED = 5, ALGO_KSW = 6 };
+constexpr int ALGO_KSW_SMEM = 106;   // launcher-internal: KSW with the (H, E) row in shared memory (generic_launch; chosen by engine.cu)
 
 constexpr int kMinusInf = -32768;   // MINUS_INF = SHRT_MIN, src/gasal_kernels.h:35
 

@@ -445,16 +445,33 @@ __device__ __forceinline__ void banded_tb_forward(const DpArgs& a, const Sc& sc,
 // pair; the (H, E) row lives in the coalesced scratch as int32 pairs (the reference keeps eh_t eh[MAX_QUERY_LEN] per
 // thread in local memory and zeroes all of it).  Quirk kept: the query word count is (qlen >> 3) + 1, so when qlen is a
 // multiple of 8 the loop variable ends on j == qlen in EVERY row and the to-end score is always considered (:57,142-145).
-__device__ __forceinline__ void ksw_extend(const DpArgs& a, const Sc& sc, const PairCtx& p, uint32_t tid, int& o_score, int& o_qe, int& o_te) {
+// Where the (H, E) row of a pair lives.  KswRowGlobal: int32 pairs in the coalesced scratch ([column][pair]; any query length, any
+// score).  KswRowShared: u16 pairs in shared memory ([column][thread of the CTA]) -- every stored value is >= 0 (H and E are clamped
+// at 0, ksw_kernel_template.h:126-137), so 16 unsigned bits hold it while h0 + qlen * match <= 65535 (host check): the row never
+// leaves the SM, where the global row costs 16 B of L2 / HBM traffic per cell (126 GB for 262144 extensions of 150 x 200).
+struct KswRowGlobal {
+  uint2* eh; size_t st;
+  __device__ __forceinline__ void get(int j, int& h, int& e) const { const uint2 v = eh[(size_t)j * st]; h = (int)v.x; e = (int)v.y; }
+  __device__ __forceinline__ void set(int j, int h, int e) const { eh[(size_t)j * st] = make_uint2((uint32_t)h, (uint32_t)e); }
+  __device__ __forceinline__ bool nonzero(int j) const { const uint2 v = eh[(size_t)j * st]; return v.x != 0u || v.y != 0u; }
+};
+template <int THREADS>
+struct KswRowShared {
+  uint32_t* eh;                                               // this thread's column 0
+  __device__ __forceinline__ void get(int j, int& h, int& e) const { const uint32_t v = eh[j * THREADS]; h = (int)(v & 0xFFFFu); e = (int)(v >> 16); }
+  __device__ __forceinline__ void set(int j, int h, int e) const { eh[j * THREADS] = (uint32_t)h | ((uint32_t)e << 16); }
+  __device__ __forceinline__ bool nonzero(int j) const { return eh[j * THREADS] != 0u; }
+};
+
+template <typename Row>
+__device__ __forceinline__ void ksw_extend(const DpArgs& a, const Sc& sc, const PairCtx& p, uint32_t tid, const Row eh, int& o_score, int& o_qe, int& o_te) {
   const int qlen = (int)p.qlen, tlen = (int)p.tlen, h0 = (int)a.seed_scores[tid];
   const int e_del = sc.ext, e_ins = sc.ext, oe_del = sc.oe, oe_ins = sc.oe;
-  uint2* eh = (uint2*)p.cs;                                   // eh[j * stride] = (h, e)
-  const size_t st = p.stride;
-  for (int j = 0; j <= qlen + 1; j++) eh[(size_t)j * st] = make_uint2(0u, 0u);
-  { uint2 v = eh[0]; v.x = (uint32_t)h0; eh[0] = v; }
+  for (int j = 0; j <= qlen + 1; j++) eh.set(j, 0, 0);
+  eh.set(0, h0, 0);
   int prev = h0 > oe_ins ? h0 - oe_ins : 0;
-  { uint2 v = eh[st]; v.x = (uint32_t)prev; eh[st] = v; }
-  for (int j = 2; j <= qlen && prev > e_ins; ++j) { prev -= e_ins; uint2 v = eh[(size_t)j * st]; v.x = (uint32_t)prev; eh[(size_t)j * st] = v; }
+  eh.set(1, prev, 0);
+  for (int j = 2; j <= qlen && prev > e_ins; ++j) { prev -= e_ins; eh.set(j, prev, 0); }
   int mx = h0, max_i = -1, max_j = -1, max_ie = -1, gscore = -1, beg = 0, end = qlen;
   const int qt_last = qlen >> 3;                              // last query word the reference visits
   bool stop = false;
@@ -467,8 +484,7 @@ __device__ __forceinline__ void ksw_extend(const DpArgs& a, const Sc& sc, const 
     for (int j = beg; j < end; j++) {
       if ((j & 7) == 0 || j == beg) rpac = p.qw[j >> 3];
       const uint32_t rbase = nib(rpac, j & 7);
-      const uint2 cell = eh[(size_t)j * st];
-      int M = (int)cell.x, e = (int)cell.y;
+      int M, e; eh.get(j, M, e);
       int s = (rbase == gbase) ? sc.match : sc.nmis;
       s = (gn || rbase == sc.nval) ? sc.nscore : s;
       M = M ? M + s : 0;                                      // separating H and M to disallow a cigar like "100M3I3D20M" (:126)
@@ -476,11 +492,11 @@ __device__ __forceinline__ void ksw_extend(const DpArgs& a, const Sc& sc, const 
       mj = m > h ? mj : j;
       m = m > h ? m : h;
       int t = M - oe_del; t = t > 0 ? t : 0; e -= e_del; e = e > t ? e : t;
-      eh[(size_t)j * st] = make_uint2((uint32_t)h1, (uint32_t)e);     // H(i,j-1) for the next row, E(i+1,j)
+      eh.set(j, h1, e);                                       // H(i,j-1) for the next row, E(i+1,j)
       h1 = h;
       t = M - oe_ins; t = t > 0 ? t : 0; f -= e_ins; f = f > t ? f : t;
     }
-    eh[(size_t)end * st] = make_uint2((uint32_t)h1, 0u);
+    eh.set(end, h1, 0);
     const int j_final = max(end, qt_last * 8);                // value of the reference's loop variable after the sweep
     if (j_final == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
     if (m == 0) {
@@ -490,9 +506,9 @@ __device__ __forceinline__ void ksw_extend(const DpArgs& a, const Sc& sc, const 
     }
     if (m > mx) { mx = m; max_i = i; max_j = mj; }
     int j = beg;
-    for (; j < end; ++j) { const uint2 v = eh[(size_t)j * st]; if (v.x != 0u || v.y != 0u) break; }
+    for (; j < end; ++j) if (eh.nonzero(j)) break;
     beg = j;
-    for (j = end; j >= beg; --j) { const uint2 v = eh[(size_t)j * st]; if (v.x != 0u || v.y != 0u) break; }
+    for (j = end; j >= beg; --j) if (eh.nonzero(j)) break;
     end = j + 2 < qlen ? j + 2 : qlen;
   }
   if (gscore <= 0 || gscore <= mx - 5) { o_score = mx; o_qe = max_j + 1; o_te = max_i + 1; }    // PEN_CLIP5 (:22,189-198)
@@ -566,7 +582,21 @@ static __global__ void __launch_bounds__(128) k_ksw_generic(const DpArgs a) {
   p.cs = a.colstate + 2 * (size_t)tid;                        // int32 pairs: two words per column entry
   const Sc sc = make_sc(a, false);
   int score, qe, te;
-  ksw_extend(a, sc, p, tid, score, qe, te);
+  KswRowGlobal row; row.eh = (uint2*)p.cs; row.st = p.stride;
+  ksw_extend(a, sc, p, tid, row, score, qe, te);
+  a.score[tid] = score; a.q_end[tid] = qe; a.t_end[tid] = te;
+}
+
+// the same extension with the (H, E) row in shared memory (KswRowShared): dynamic shared memory = (max query length + 2) * 128 * 4 B
+constexpr int kKswThreads = 128;
+static __global__ void __launch_bounds__(kKswThreads) k_ksw_smem(const DpArgs a) {
+  extern __shared__ uint32_t ksw_rows[];
+  const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x;
+  PairCtx p; if (!make_ctx(a, tid, p)) return;
+  const Sc sc = make_sc(a, false);
+  int score, qe, te;
+  KswRowShared<kKswThreads> row; row.eh = ksw_rows + threadIdx.x;
+  ksw_extend(a, sc, p, tid, row, score, qe, te);
   a.score[tid] = score; a.q_end[tid] = qe; a.t_end[tid] = te;
 }
 

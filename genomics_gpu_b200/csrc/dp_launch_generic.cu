@@ -35,6 +35,14 @@ int generic_launch(const DpArgs& a, int algo, int start, bool second, cudaStream
     case ALGO_KSW:                                                                          // gasal_align.h:73-78
       k_ksw_generic<<<N_BLOCKS, BLOCKDIM, 0, str>>>(a);
       break;
+    case ALGO_KSW_SMEM: {                                                                   // row in shared memory (engine.cu proves the 16-bit range)
+      const size_t smem = (size_t)(a.col_rows + 2) * kKswThreads * sizeof(uint32_t);
+      static bool attr_done[64] = {};
+      int dev = 0; cudaGetDevice(&dev);
+      if (!attr_done[dev & 63]) { cudaFuncSetAttribute(k_ksw_smem, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024); attr_done[dev & 63] = true; }
+      k_ksw_smem<<<(n + kKswThreads - 1) / kKswThreads, kKswThreads, smem, str>>>(a);
+      break;
+    }
     default:
       return -1;
   }

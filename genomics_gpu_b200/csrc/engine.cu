@@ -786,7 +786,18 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
   if (pv->colstate_words < need) { dev_realloc(&pv->colstate, need); pv->colstate_words = need; }
   a.colstate = pv->colstate; a.col_stride = stride; a.col_rows = q8;
   pv->last_kernel = "int32";
-  const int nl = generic_launch(a, params->algo, start, second, s->str);
+  int galgo = params->algo;
+  if (params->algo == KSW && g_kernel_policy == 0 && s->host_seed_scores) {
+    // KSW keeps every stored H / E >= 0, so a u16 row in shared memory is exact while h0 + qlen * match stays below 2^16 (k_ksw_smem):
+    // the row of a 150 bp read is 608 B per thread, two CTAs per SM, and none of the 16 B per cell goes through L2 / HBM
+    uint32_t max_h0 = 0;
+    for (uint32_t i = 0; i < n; i++) max_h0 = std::max(max_h0, s->host_seed_scores[i]);
+    const uint64_t top = (uint64_t)max_h0 + (uint64_t)q8 * (uint64_t)std::max(a.match, 0) + 16;
+    if (top <= 65535u && a.match >= 0 && a.mismatch >= 0 && a.gap_open >= 0 && a.gap_extend >= 0 && (size_t)(q8 + 2) * 128 * 4 <= (size_t)227 * 1024) {
+      galgo = ALGO_KSW_SMEM; pv->last_kernel = "int32-smem";
+    }
+  }
+  const int nl = generic_launch(a, galgo, start, second, s->str);
   if (nl < 0) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo); }
   CHECK_LAUNCH(); pv->launches += nl;
 }

@@ -128,6 +128,15 @@ def make_read_window_pairs(n: int, qlen: int, tlen: int, *, sub: float, indel: f
     return _uniform_batch(q, targets)
 
 
+def make_extension_pairs(n: int, qlen: int, tlen: int, *, sub: float = 0.02, indel: float = 0.002, seed: int = 9) -> PairBatch:
+    """seed-extension shape (KSW, ksw_kernel_template.h): the query is a mutated copy of the target's FIRST qlen bases, so an extension that
+    starts at (0, 0) with a seed score runs the whole query"""
+    rng = np.random.default_rng(seed)
+    targets = ACGT[rng.integers(0, 4, size=(n, tlen))]
+    q = _mutated_windows(rng, targets, np.zeros(n, dtype=np.int64), qlen, sub, indel, 3)
+    return _uniform_batch(q, targets)
+
+
 def config1(n: int = 10_000, seed: int = 1) -> PairBatch:
     """C1: 150 bp query / 300 bp target, 3 % substitutions (local)."""
     return make_read_window_pairs(n, 150, 300, sub=0.03, seed=seed)

@@ -213,6 +213,19 @@ def test_multi_storage_round_robin(oracle):
         assert_same(outs[lo], sub_want, K5, f"chunk {lo}:{hi}")
 
 
+def run_ksw(batch, seeds, policy=0, **kw):
+    lib = capi.load()
+    lib.gasalx_set_kernel_policy(policy)
+    try:
+        mq = int(batch.q_lens.max()) + 7; mt = int(batch.t_lens.max()) + 7
+        with Aligner(algo=capi.KSW, max_query_len=mq, max_target_len=mt, max_n_alns=batch.n, n_streams=1, **kw) as al:
+            res = al.align(batch, seeds=seeds)
+            res["_kernel"] = al.kernel_name(0)
+    finally:
+        lib.gasalx_set_kernel_policy(0)
+    return res
+
+
 @pytest.mark.parametrize("scoring", SCORINGS)
 def test_ksw_seed_extension(oracle, scoring):
     """algo=KSW (BWA ksw_extend, ksw_kernel_template.h:46-199): h0 from host_seed_scores, adaptive beg/end window, clip rule.
@@ -226,7 +239,17 @@ def test_ksw_seed_extension(oracle, scoring):
     mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
     with Aligner(algo=capi.KSW, scoring=scoring, max_query_len=mq, max_target_len=mt, max_n_alns=b.n, n_streams=1) as al:
         got = al.align(b, seeds=seeds)
+        assert al.kernel_name(0) == "int32-smem"           # the (H, E) row as u16 pairs in shared memory (k_ksw_smem)
     assert_same(got, want, K3, f"ksw {scoring}")
+    pol1 = run_ksw(b, seeds, policy=1, scoring=scoring)
+    assert pol1["_kernel"] == "int32"                      # the row in the global scratch (k_ksw_generic)
+    assert_same(pol1, want, K3, f"ksw {scoring}, global row")
+    # a seed score that does not fit the u16 row sends the batch to the global-row kernel by itself
+    big = seeds.copy(); big[5] = 70000
+    want = oracle.align(pq, pt, b.q_lens, b.t_lens, b.q_offs, b.t_offs, algo=po.KSW, scoring=scoring, seed_scores=big, max_query_len=1024)
+    got = run_ksw(b, big, scoring=scoring)
+    assert got["_kernel"] == "int32"
+    assert_same(got, want, K3, f"ksw {scoring}, large seed score")
 
 
 def test_ksw_extension_from_matching_prefix(oracle):
@@ -248,7 +271,15 @@ def test_ksw_extension_from_matching_prefix(oracle):
     mq = int(b.q_lens.max()) + 7; mt = int(b.t_lens.max()) + 7
     with Aligner(algo=capi.KSW, max_query_len=mq, max_target_len=mt, max_n_alns=b.n, n_streams=1) as al:
         got = al.align(b, seeds=seeds)
+        assert al.kernel_name(0) == "int32-smem"
     assert_same(got, want, K3, "ksw prefix extension")
+    assert_same(run_ksw(b, seeds, policy=1), want, K3, "ksw prefix extension, global row")
+    # the bench shape: 20,000 extensions of 150 bp reads along 200 bp windows, both kernels
+    bk = synth.make_extension_pairs(20_000, 150, 200)
+    sk = np.full(bk.n, 20, dtype=np.uint32)
+    wk = oracle.align(oracle.pack(bk.q_bytes), oracle.pack(bk.t_bytes), bk.q_lens, bk.t_lens, bk.q_offs, bk.t_offs, algo=po.KSW, seed_scores=sk, max_query_len=1024)
+    assert_same(run_ksw(bk, sk), wk, K3, "ksw 150 x 200 extensions")
+    assert_same(run_ksw(bk, sk, policy=1), wk, K3, "ksw 150 x 200 extensions, global row")
     assert (got["query_batch_end"] == b.q_lens.astype(np.int32)).sum() > 100      # the to-end branch was exercised
 
 
