@@ -782,9 +782,6 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
 
   // ---- general int32 kernels ----
   const uint32_t stride = (n + 31u) & ~31u;
-  const size_t need = (params->algo == KSW) ? 2 * (size_t)stride * (q8 + 16) : (size_t)stride * std::max<uint32_t>(q8, 8);
-  if (pv->colstate_words < need) { dev_realloc(&pv->colstate, need); pv->colstate_words = need; }
-  a.colstate = pv->colstate; a.col_stride = stride; a.col_rows = q8;
   pv->last_kernel = "int32";
   int galgo = params->algo;
   if (params->algo == KSW && g_kernel_policy == 0 && s->host_seed_scores) {
@@ -797,6 +794,10 @@ static void launch_dp(gasal_gpu_storage_t* s, uint32_t q_bytes, uint32_t n, cons
       galgo = ALGO_KSW_SMEM; pv->last_kernel = "int32-smem";
     }
   }
+  // column state in the coalesced global scratch (not needed when the KSW row lives in shared memory)
+  const size_t need = (galgo == ALGO_KSW_SMEM) ? 0 : (params->algo == KSW) ? 2 * (size_t)stride * (q8 + 16) : (size_t)stride * std::max<uint32_t>(q8, 8);
+  if (pv->colstate_words < need) { dev_realloc(&pv->colstate, need); pv->colstate_words = need; }
+  a.colstate = pv->colstate; a.col_stride = stride; a.col_rows = q8;
   const int nl = generic_launch(a, galgo, start, second, s->str);
   if (nl < 0) { GASAL_FAIL(GASALX_E_ARG, "[GASAL ERROR:] algo %d is not supported by this build\n", params->algo); }
   CHECK_LAUNCH(); pv->launches += nl;
